@@ -1,0 +1,249 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes loader for oracle/_build/liboracle.so, the CPU restatement of the reference's stiffness
+hot path (see fem_oracle.hpp for the file:line citations). Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module. The product package
+(finite_element_method_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+ERROR_TEXT = {}
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+_i64p = C.POINTER(C.c_int64)
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (g++ only; no reference sources involved)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "fem_oracle.hpp", "fem_oracle_fast.hpp")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_error_text.restype = C.c_char_p
+        _lib.oracle_model_create.restype = C.c_void_p
+        _lib.oracle_model_create.argtypes = [C.c_double, C.c_double, C.c_uint32]
+        _lib.oracle_model_destroy.argtypes = [C.c_void_p]
+        _lib.oracle_model_nnz.restype = C.c_int64
+        _lib.oracle_model_nnz.argtypes = [C.c_void_p]
+        _lib.oracle_fast_assemble.restype = C.c_double
+        _lib.oracle_faithful_time.restype = C.c_double
+    return _lib
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _u(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(_u32p)
+
+
+class OracleError(Exception):
+    def __init__(self, code, at=None):
+        self.code = int(code)
+        self.at = at
+        super().__init__(f"{lib().oracle_error_text(int(code)).decode()} (code {code}, element {at})")
+
+
+# ------------------------------------------------------------------ element level
+def truss(p1, p2, E, A, A2=None, rel_tol=1e-4, abs_tol=1e-12):
+    q = np.zeros(9); kl = np.zeros(36); kg = np.zeros(36)
+    _, a = _d(p1); _, b = _d(p2)
+    err = lib().oracle_truss_f64(a, b, C.c_double(E), C.c_double(A),
+                                 C.c_double(float("nan") if A2 is None else A2),
+                                 C.c_double(rel_tol), C.c_double(abs_tol),
+                                 q.ctypes.data_as(_dp), kl.ctypes.data_as(_dp), kg.ctypes.data_as(_dp))
+    if err:
+        raise OracleError(err)
+    return q.reshape(3, 3), kl.reshape(6, 6), kg.reshape(6, 6)
+
+
+def truss_f32(p1, p2, E, A, A2=None, rel_tol=1e-4, abs_tol=1e-12):
+    q = np.zeros(9, np.float32); kl = np.zeros(36, np.float32); kg = np.zeros(36, np.float32)
+    a = np.ascontiguousarray(p1, np.float32); b = np.ascontiguousarray(p2, np.float32)
+    err = lib().oracle_truss_f32(a.ctypes.data_as(_fp), b.ctypes.data_as(_fp), C.c_float(E), C.c_float(A),
+                                 C.c_float(float("nan") if A2 is None else A2),
+                                 C.c_float(rel_tol), C.c_float(abs_tol),
+                                 q.ctypes.data_as(_fp), kl.ctypes.data_as(_fp), kg.ctypes.data_as(_fp))
+    if err:
+        raise OracleError(err)
+    return q.reshape(3, 3), kl.reshape(6, 6), kg.reshape(6, 6)
+
+
+def beam(p1, p2, E, nu, A, I11, I22, I12, It, ks, axis1, rel_tol=1e-4, abs_tol=1e-12):
+    q = np.zeros(9); pr = np.zeros(3); kl = np.zeros(144); kg = np.zeros(144)
+    _, a = _d(p1); _, b = _d(p2); _, ax = _d(axis1)
+    err = lib().oracle_beam_f64(a, b, *[C.c_double(v) for v in (E, nu, A, I11, I22, I12, It, ks)], ax,
+                                C.c_double(rel_tol), C.c_double(abs_tol), q.ctypes.data_as(_dp),
+                                pr.ctypes.data_as(_dp), kl.ctypes.data_as(_dp), kg.ctypes.data_as(_dp))
+    if err:
+        raise OracleError(err)
+    return q.reshape(3, 3), pr, kl.reshape(12, 12), kg.reshape(12, 12)
+
+
+def plate(p1, p2, p3, p4, E, nu, t, ks, rel_tol=1e-4, abs_tol=1e-12):
+    q = np.zeros(9); kl = np.zeros(576); kg = np.zeros(576)
+    ps = [_d(p)[1] for p in (p1, p2, p3, p4)]
+    err = lib().oracle_plate_f64(*ps, *[C.c_double(v) for v in (E, nu, t, ks)],
+                                 C.c_double(rel_tol), C.c_double(abs_tol), q.ctypes.data_as(_dp),
+                                 kl.ctypes.data_as(_dp), kg.ctypes.data_as(_dp))
+    if err:
+        raise OracleError(err)
+    return q.reshape(3, 3), kl.reshape(24, 24), kg.reshape(24, 24)
+
+
+def reference_truss_test_f32():
+    """Replays the reference's own f32 test model; returns (k00, u2x, r1x, force_r) as float32."""
+    v = [C.c_float() for _ in range(4)]
+    err = lib().oracle_reference_truss_test_f32(*[C.byref(x) for x in v])
+    if err:
+        raise OracleError(err)
+    return tuple(np.float32(x.value) for x in v)
+
+
+# ------------------------------------------------------------------ model level (faithful)
+class Model:
+    """Faithful single-thread assembly into a position-keyed map, in the order add_* is called.
+
+    Node arguments are 0-based node *indices* (insertion order), not user numbers.
+    """
+
+    def __init__(self, rel_tol, abs_tol, nodes_number):
+        self._h = C.c_void_p(lib().oracle_model_create(rel_tol, abs_tol, nodes_number))
+        self.n_rows = 6 * nodes_number
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_model_destroy(self._h)
+            self._h = None
+
+    def set_nodes(self, x, y, z):
+        x, px = _d(x); y, py = _d(y); z, pz = _d(z)
+        if lib().oracle_model_set_nodes(self._h, C.c_int64(len(x)), px, py, pz):
+            raise ValueError("more nodes than nodes_number")
+
+    def add_truss(self, n1, n2, E, A, A2=None):
+        n1, p1 = _u(n1); n2, p2 = _u(n2); E, pE = _d(E); A, pA = _d(A)
+        if A2 is None:
+            A2 = np.full(len(n1), np.nan)
+        A2, pA2 = _d(A2)
+        at = C.c_int64(-1)
+        err = lib().oracle_model_add_truss(self._h, C.c_int64(len(n1)), p1, p2, pE, pA, pA2, C.byref(at))
+        if err:
+            raise OracleError(err, at.value)
+
+    def add_beam(self, n1, n2, E, nu, A, I11, I22, I12, It, ks, axis1):
+        n1, p1 = _u(n1); n2, p2 = _u(n2)
+        arrs = [_d(v) for v in (E, nu, A, I11, I22, I12, It, ks)]
+        ax = np.ascontiguousarray(np.asarray(axis1, np.float64).reshape(3, -1))
+        at = C.c_int64(-1)
+        err = lib().oracle_model_add_beam(self._h, C.c_int64(len(n1)), p1, p2, *[a[1] for a in arrs],
+                                          ax.ctypes.data_as(_dp), C.byref(at))
+        if err:
+            raise OracleError(err, at.value)
+
+    def add_plate(self, n1, n2, n3, n4, E, nu, t, ks):
+        ns = [_u(v) for v in (n1, n2, n3, n4)]
+        arrs = [_d(v) for v in (E, nu, t, ks)]
+        at = C.c_int64(-1)
+        err = lib().oracle_model_add_plate(self._h, C.c_int64(len(ns[0][0])), *[a[1] for a in ns],
+                                           *[a[1] for a in arrs], C.byref(at))
+        if err:
+            raise OracleError(err, at.value)
+
+    def coo(self):
+        """Stored entries sorted by (row, col): (rows, cols, vals)."""
+        nnz = lib().oracle_model_nnz(self._h)
+        r = np.zeros(nnz, np.int64); c = np.zeros(nnz, np.int64); v = np.zeros(nnz, np.float64)
+        lib().oracle_model_get_coo(self._h, r.ctypes.data_as(_i64p), c.ctypes.data_as(_i64p),
+                                   v.ctypes.data_as(_dp))
+        return r, c, v
+
+
+# ------------------------------------------------------------------ mesh-level helpers
+def _mesh_args(mesh):
+    """mesh: dict produced by finite_element_method_b200.meshes generators (plain numpy arrays)."""
+    keep = []
+
+    def d(a):
+        a, p = _d(a); keep.append(a); return p
+
+    def u(a):
+        a, p = _u(a); keep.append(a); return p
+
+    nt, nb, npl = len(mesh["t_n1"]), len(mesh["b_n1"]), len(mesh["p_n"][0]) if len(mesh["p_n"]) else 0
+    t_A2 = mesh.get("t_A2")
+    if t_A2 is None:
+        t_A2 = np.full(nt, np.nan)
+    args = [C.c_int64(len(mesh["x"])), d(mesh["x"]), d(mesh["y"]), d(mesh["z"]),
+            C.c_int64(nt), u(mesh["t_n1"]), u(mesh["t_n2"]), d(mesh["t_E"]), d(mesh["t_A"]), d(t_A2),
+            C.c_int64(nb), u(mesh["b_n1"]), u(mesh["b_n2"]),
+            d(np.asarray(mesh["b_props"], np.float64).reshape(8, -1)),
+            d(np.asarray(mesh["b_axis"], np.float64).reshape(3, -1)),
+            C.c_int64(npl), u(np.asarray(mesh["p_n"], np.uint32).reshape(4, -1)),
+            d(np.asarray(mesh["p_props"], np.float64).reshape(4, -1)),
+            C.c_double(mesh["rel_tol"]), C.c_double(mesh["abs_tol"])]
+    return args, keep
+
+
+def fast_assemble(mesh, n_threads=0, repeats=1, want_coo=False):
+    """Multi-core owner-computes CPU assembly. Returns dict(seconds, nnz, checksum[, coo])."""
+    args, keep = _mesh_args(mesh)
+    nnz = C.c_int64(0); cs = C.c_double(0.0)
+    null_i = C.cast(None, _i64p); null_d = C.cast(None, _dp)
+    sec = lib().oracle_fast_assemble(*args, C.c_int(n_threads), C.c_int(repeats), C.byref(nnz),
+                                     C.byref(cs), null_i, null_i, null_d)
+    out = {"seconds": sec, "nnz": nnz.value, "checksum": cs.value}
+    if sec < 0:
+        raise OracleError(-1)
+    if want_coo:
+        r = np.zeros(nnz.value, np.int64); c = np.zeros(nnz.value, np.int64); v = np.zeros(nnz.value)
+        lib().oracle_fast_assemble(*args, C.c_int(n_threads), C.c_int(1), C.byref(nnz), C.byref(cs),
+                                   r.ctypes.data_as(_i64p), c.ctypes.data_as(_i64p), v.ctypes.data_as(_dp))
+        out["coo"] = (r, c, v)
+    return out
+
+
+def faithful_time(mesh):
+    """Seconds for the single-thread faithful add_* loop over the whole mesh (plates, beams, trusses)."""
+    args, keep = _mesh_args(mesh)
+    return lib().oracle_faithful_time(*args)
+
+
+def faithful_coo(mesh):
+    """Faithful assembly of a mesh dict in the order plates -> beams -> trusses."""
+    m = Model(mesh["rel_tol"], mesh["abs_tol"], mesh.get("nodes_number", len(mesh["x"])))
+    m.set_nodes(mesh["x"], mesh["y"], mesh["z"])
+    if len(mesh["p_n"]) and len(mesh["p_n"][0]):
+        pn = np.asarray(mesh["p_n"]).reshape(4, -1); pp = np.asarray(mesh["p_props"]).reshape(4, -1)
+        m.add_plate(pn[0], pn[1], pn[2], pn[3], pp[0], pp[1], pp[2], pp[3])
+    if len(mesh["b_n1"]):
+        bp = np.asarray(mesh["b_props"]).reshape(8, -1)
+        m.add_beam(mesh["b_n1"], mesh["b_n2"], *[bp[i] for i in range(8)], mesh["b_axis"])
+    if len(mesh["t_n1"]):
+        m.add_truss(mesh["t_n1"], mesh["t_n2"], mesh["t_E"], mesh["t_A"], mesh.get("t_A2"))
+    return m.coo()
