@@ -1,0 +1,9 @@
+"""finite_element_method_b200 — B200-native (sm_100a) drop-in for the stiffness-assembly hot path of
+RomanShushakov/finite_element_method: truss / beam / plate local stiffness + deterministic
+assembly into the global FP64 CSR matrix. The product is libfemgpu.so (C ABI in include/femgpu.h);
+this package is its Python host mirror (`FEM`) plus synthetic mesh generators for the benchmarks.
+"""
+from .fem import BEAM, PLATE, TRUSS, FEM, FemError  # noqa: F401
+from . import meshes  # noqa: F401
+
+__all__ = ["FEM", "FemError", "TRUSS", "BEAM", "PLATE", "meshes"]

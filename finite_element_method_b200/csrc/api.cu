@@ -1,0 +1,752 @@
+// C ABI entry points (include/femgpu.h): host-side bookkeeping that mirrors the reference's
+// FEM<V> container — node numbering, duplicate checks, error texts — plus staging of the
+// struct-of-arrays element data into HBM. All numerics run on the device (prep.cu, symbolic.cu,
+// numeric.cu); there is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace femgpu;
+
+namespace {
+
+Status g_create_status;  // errors before a handle exists
+
+// Rust's `{:?}` for f64 (used inside the reference's error messages): shortest round-trip digits,
+// plain decimal with at least one fractional digit for 1e-4 <= |x| < 1e16, scientific otherwise.
+std::string rust_debug_f64(double v) {
+  if (std::isnan(v)) return "NaN";
+  if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+  if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+  char buf[64];
+  int prec = 1;
+  for (; prec <= 17; ++prec) {
+    snprintf(buf, sizeof buf, "%.*e", prec - 1, v);
+    if (strtod(buf, nullptr) == v) break;
+  }
+  // buf = d.ddddde[+-]XX
+  std::string s(buf);
+  size_t epos = s.find('e');
+  std::string mant = s.substr(0, epos);
+  int exp10 = atoi(s.c_str() + epos + 1);
+  bool neg = mant[0] == '-';
+  if (neg) mant = mant.substr(1);
+  std::string digits;
+  for (char c : mant)
+    if (c != '.') digits += c;
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  std::string out;
+  double a = std::fabs(v);
+  if (a >= 1e-4 && a < 1e16) {
+    if (exp10 >= 0) {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), size_t(exp10) + 1));
+      while (ip.size() < size_t(exp10) + 1) ip += '0';
+      std::string fp = digits.size() > size_t(exp10) + 1 ? digits.substr(size_t(exp10) + 1) : "0";
+      out = ip + "." + fp;
+    } else {
+      out = "0." + std::string(size_t(-exp10 - 1), '0') + digits;
+    }
+  } else {
+    out = digits.substr(0, 1);
+    if (digits.size() > 1) out += "." + digits.substr(1);
+    out += "e" + std::to_string(exp10);
+  }
+  return neg ? "-" + out : out;
+}
+
+inline uint64_t bits_of(double v) {
+  if (v == 0.0) v = 0.0;  // -0.0 == 0.0 in the reference's `==`
+  uint64_t u;
+  std::memcpy(&u, &v, 8);
+  return u;
+}
+
+const char* family_name(int f) { return f == FEMGPU_TRUSS ? "Truss" : (f == FEMGPU_BEAM ? "Beam" : "Plate"); }
+
+// Texts of the element-level checks (structs/truss.rs:29-42, structs/beam.rs:37-61,
+// structs/plate.rs:37-56). The reference prints young_modulus inside the Poisson (beam, plate) and
+// Thickness (plate) messages; that quirk is kept.
+std::string element_error_text(const Handle* h, int family, size_t i, int code) {
+  const FamilyHost& f = h->fh[family];
+  auto P = [&](int k) { return rust_debug_f64(f.props[k][i]); };
+  uint32_t number = f.number[i];
+  switch (code) {
+    case FEMGPU_E_YOUNG_MODULUS: return "Young's modulus " + P(0) + " is less or equal to zero!";
+    case FEMGPU_E_POISSON_RATIO: return "Poisson's ratio " + P(0) + " is less or equal to zero!";
+    case FEMGPU_E_AREA: return "Area " + P(family == FEMGPU_TRUSS ? 1 : 2) + " is less or equal to zero!";
+    case FEMGPU_E_AREA2: return "Area2 " + P(2) + " is less or equal to zero!";
+    case FEMGPU_E_I11: return "I11 " + P(3) + " is less or equal to zero!";
+    case FEMGPU_E_I22: return "I22 " + P(4) + " is less or equal to zero!";
+    case FEMGPU_E_IT: return "It " + P(6) + " is less or equal to zero!";
+    case FEMGPU_E_SHEAR_FACTOR:
+      return "Shear factor " + P(family == FEMGPU_BEAM ? 7 : 3) + " is less or equal to zero!";
+    case FEMGPU_E_PARALLEL_LOCAL_AXIS:
+      return "Local axis 1 direction [" + P(8) + ", " + P(9) + ", " + P(10) + "] parallel to element " +
+             std::to_string(number) + "!";
+    case FEMGPU_E_THICKNESS: return "Thickness " + P(0) + " is less or equal to zero!";
+    case FEMGPU_E_NODES_ON_LINE: return "Some nodes of " + std::to_string(number) + " element lie on the line!";
+    case FEMGPU_E_NODES_NOT_ON_PLANE:
+      return "Not all nodes of element " + std::to_string(number) + " lie on the plane!";
+    case FEMGPU_E_NOT_CONVEX: return "Element " + std::to_string(number) + " non-convex!";
+    default: return "element error " + std::to_string(code);
+  }
+}
+
+// host-side half of the property checks: the sign tests, in the reference's order
+int property_check(int family, const double* p /* props of one element */) {
+  switch (family) {
+    case FEMGPU_TRUSS:
+      if (p[0] <= 0.0) return FEMGPU_E_YOUNG_MODULUS;
+      if (p[1] <= 0.0) return FEMGPU_E_AREA;
+      if (!std::isnan(p[2]) && p[2] <= 0.0) return FEMGPU_E_AREA2;
+      return 0;
+    case FEMGPU_BEAM:
+      if (p[0] <= 0.0) return FEMGPU_E_YOUNG_MODULUS;
+      if (p[1] <= 0.0) return FEMGPU_E_POISSON_RATIO;
+      if (p[2] <= 0.0) return FEMGPU_E_AREA;
+      if (p[3] <= 0.0) return FEMGPU_E_I11;
+      if (p[4] <= 0.0) return FEMGPU_E_I22;
+      if (p[6] <= 0.0) return FEMGPU_E_IT;
+      if (p[7] <= 0.0) return FEMGPU_E_SHEAR_FACTOR;
+      return 0;
+    default:
+      if (p[0] <= 0.0) return FEMGPU_E_YOUNG_MODULUS;
+      if (p[1] <= 0.0) return FEMGPU_E_POISSON_RATIO;
+      if (p[2] <= 0.0) return FEMGPU_E_THICKNESS;
+      if (p[3] <= 0.0) return FEMGPU_E_SHEAR_FACTOR;
+      return 0;
+  }
+}
+
+void invalidate(Handle* h) { h->symbolic_valid = false; }
+
+// Drop every element inserted at or after element `index` of `family` (global insertion order).
+void rollback_to(Handle* h, int family, size_t index) {
+  size_t keep[kFamilies] = {0, 0, 0};
+  size_t new_journal = 0;
+  bool found = false;
+  for (size_t j = 0; j < h->journal.size() && !found; ++j) {
+    int f = h->journal[j].first;
+    size_t cnt = h->journal[j].second;
+    if (f == family && index < keep[f] + cnt) {
+      size_t take = index - keep[f];
+      keep[f] += take;
+      h->journal[j].second = take;
+      new_journal = take ? j + 1 : j;
+      found = true;
+    } else {
+      keep[f] += cnt;
+    }
+  }
+  if (!found) return;
+  h->journal.resize(new_journal);
+  for (int f = 0; f < kFamilies; ++f) {
+    FamilyHost& fh = h->fh[f];
+    size_t n = fh.size();
+    if (keep[f] >= n) continue;
+    for (size_t i = keep[f]; i < n; ++i) {
+      fh.by_number.erase(fh.number[i]);
+      if (f == FEMGPU_PLATE) {
+        PlateKey k{{fh.conn[0][i], fh.conn[1][i], fh.conn[2][i], fh.conn[3][i]}};
+        std::sort(k.n, k.n + 4);
+        auto it = h->plate_seen.find(k);
+        if (it != h->plate_seen.end() && it->second == i) h->plate_seen.erase(it);
+      } else {
+        uint32_t a = fh.conn[0][i], b = fh.conn[1][i];
+        uint64_t k = (uint64_t(std::min(a, b)) << 32) | std::max(a, b);
+        auto it = h->pair_seen[f].find(k);
+        if (it != h->pair_seen[f].end() && it->second == i) h->pair_seen[f].erase(it);
+      }
+    }
+    fh.number.resize(keep[f]);
+    for (int c = 0; c < kNodesPerElem[f]; ++c) {
+      fh.conn[c].resize(keep[f]);
+      fh.conn_number[c].resize(keep[f]);
+    }
+    for (int p = 0; p < kPropsPerElem[f]; ++p) fh.props[p].resize(keep[f]);
+    fh.cbase.resize(keep[f]);
+    h->fd[f].uploaded = std::min(h->fd[f].uploaded, keep[f]);
+    h->fd[f].validated = std::min(h->fd[f].validated, keep[f]);
+  }
+  int64_t nc = 0;
+  for (int f = 0; f < kFamilies; ++f) nc += int64_t(h->fh[f].size()) * kPairsPerElem[f];
+  h->n_contrib = nc;
+  invalidate(h);
+}
+
+// device validation of everything pending; on error rolls back and fills the reference message
+int32_t no_device(Handle* h) {
+  return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
+                                       "femgpu has no CPU fallback");
+}
+
+int32_t validate_pending(Handle* h, int32_t* family, uint32_t* number, int32_t* code) {
+  bool pending = false;
+  for (int f = 0; f < kFamilies; ++f) pending |= h->fd[f].validated < h->fh[f].size();
+  if (!pending) return 0;
+  if (h->device < 0) return no_device(h);
+  int32_t st = upload_pending(h);
+  if (st) return st;
+  st = run_prep(h, /*validate_only=*/true);
+  if (st) return st;
+  int ef = -1, ec = 0;
+  size_t ei = 0;
+  st = first_error(h, &ef, &ei, &ec);
+  if (st) return st;
+  if (ef < 0) {
+    for (int f = 0; f < kFamilies; ++f) h->fd[f].validated = h->fh[f].size();
+    return 0;
+  }
+  std::string text = element_error_text(h, ef, ei, ec);
+  if (family) *family = ef;
+  if (number) *number = h->fh[ef].number[ei];
+  if (code) *code = ec;
+  rollback_to(h, ef, ei);
+  for (int f = 0; f < kFamilies; ++f) h->fd[f].validated = h->fh[f].size();
+  return h->fail(ec, text);
+}
+
+// A host-side check failed at element k of a batch: the reference would have reported any error of
+// an earlier element first, so validate the accepted prefix on the device before answering.
+int32_t fail_after_prefix(Handle* h, int32_t code, const std::string& text) {
+  if (h->device < 0) return h->fail(code, text);
+  int32_t st = validate_pending(h, nullptr, nullptr, nullptr);
+  if (st) return st;
+  return h->fail(code, text);
+}
+
+int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
+                     const uint32_t* const* nodes, const double* const* props) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (n == 0) return 0;
+  if (!number) return h->fail(FEMGPU_ERR_USAGE, "null element number array");
+  const int nn = kNodesPerElem[family], np = kPropsPerElem[family];
+  FamilyHost& fh = h->fh[family];
+  const size_t start = fh.size();
+  if (start + n >= (1u << 26))
+    return h->fail(FEMGPU_ERR_LIMIT, "more than 2^26 elements of one family on one device");
+  // reserve
+  fh.number.reserve(start + n);
+  for (int c = 0; c < nn; ++c) {
+    fh.conn[c].reserve(start + n);
+    fh.conn_number[c].reserve(start + n);
+  }
+  for (int p = 0; p < np; ++p) fh.props[p].reserve(start + n);
+  fh.cbase.reserve(start + n);
+
+  size_t accepted = 0;
+  int32_t status = 0;
+  std::string text;
+  for (size_t e = 0; e < n; ++e) {
+    uint32_t idx[4];
+    // check_node_exist, in argument order (methods_for_truss_data_handle.rs:58-59 and siblings)
+    bool ok = true;
+    for (int c = 0; c < nn && ok; ++c) {
+      if (!h->node_by_number.find(nodes[c][e], &idx[c])) {
+        status = FEMGPU_E_NODE_NOT_EXIST;
+        text = "Node with number " + std::to_string(nodes[c][e]) + " does not exist!";
+        ok = false;
+      }
+    }
+    if (!ok) break;
+    // check_*_data: duplicate number, then same node set (:32-47)
+    uint32_t dummy;
+    if (fh.by_number.find(number[e], &dummy)) {
+      status = FEMGPU_E_ELEMENT_NUMBER_EXISTS;
+      text = std::string(family_name(family)) + " element with number " + std::to_string(number[e]) +
+             " already exists!";
+      break;
+    }
+    const uint32_t self = uint32_t(start + e);
+    if (family == FEMGPU_PLATE) {
+      PlateKey k{{idx[0], idx[1], idx[2], idx[3]}};
+      std::sort(k.n, k.n + 4);
+      bool distinct = k.n[0] != k.n[1] && k.n[1] != k.n[2] && k.n[2] != k.n[3];
+      bool dup = false;
+      if (distinct) {
+        dup = !h->plate_seen.emplace(k, self).second;
+      } else {
+        // Plate::is_nodes_numbers_same (structs/plate.rs:1114-1118) is a subset test; with repeated
+        // node numbers that is not set equality, so fall back to a scan (degenerate input only).
+        for (size_t i = 0; i < fh.size() && !dup; ++i) {
+          bool all = true;
+          for (int c = 0; c < 4 && all; ++c) {
+            bool in = false;
+            for (int d = 0; d < 4; ++d) in |= fh.conn[d][i] == idx[c];
+            all = in;
+          }
+          dup = all;
+        }
+      }
+      if (dup) {
+        status = FEMGPU_E_ELEMENT_SAME_NODES;
+        text = "Plate element with nodes numbers [" + std::to_string(nodes[0][e]) + ", " +
+               std::to_string(nodes[1][e]) + ", " + std::to_string(nodes[2][e]) + ", " +
+               std::to_string(nodes[3][e]) + "] already exists!";
+        break;
+      }
+    } else {
+      uint64_t k = (uint64_t(std::min(idx[0], idx[1])) << 32) | std::max(idx[0], idx[1]);
+      if (!h->pair_seen[family].emplace(k, self).second) {
+        status = FEMGPU_E_ELEMENT_SAME_NODES;
+        text = std::string(family_name(family)) + " element with node number " +
+               std::to_string(nodes[0][e]) + " and " + std::to_string(nodes[1][e]) + " already exists!";
+        break;
+      }
+    }
+    // property sign checks of *::create (geometry checks run on the device)
+    double pv[11];
+    for (int p = 0; p < np; ++p) pv[p] = props[p] ? props[p][e] : NAN;
+    fh.number.push_back(number[e]);
+    for (int c = 0; c < nn; ++c) {
+      fh.conn[c].push_back(idx[c]);
+      fh.conn_number[c].push_back(nodes[c][e]);
+    }
+    for (int p = 0; p < np; ++p) fh.props[p].push_back(pv[p]);
+    fh.cbase.push_back(h->n_contrib);
+    int pc = property_check(family, pv);
+    if (pc) {
+      status = pc;
+      text = element_error_text(h, family, fh.size() - 1, pc);
+      // undo the tentative push
+      if (family == FEMGPU_PLATE) {
+        PlateKey k{{idx[0], idx[1], idx[2], idx[3]}};
+        std::sort(k.n, k.n + 4);
+        auto it = h->plate_seen.find(k);
+        if (it != h->plate_seen.end() && it->second == self) h->plate_seen.erase(it);
+      } else {
+        uint64_t k = (uint64_t(std::min(idx[0], idx[1])) << 32) | std::max(idx[0], idx[1]);
+        h->pair_seen[family].erase(k);
+      }
+      fh.number.pop_back();
+      for (int c = 0; c < nn; ++c) {
+        fh.conn[c].pop_back();
+        fh.conn_number[c].pop_back();
+      }
+      for (int p = 0; p < np; ++p) fh.props[p].pop_back();
+      fh.cbase.pop_back();
+      break;
+    }
+    fh.by_number.insert(number[e], self);
+    h->n_contrib += kPairsPerElem[family];
+    ++accepted;
+  }
+  if (accepted) {
+    if (!h->journal.empty() && h->journal.back().first == family)
+      h->journal.back().second += accepted;
+    else
+      h->journal.emplace_back(family, accepted);
+    invalidate(h);
+  }
+  if (status) return fail_after_prefix(h, status, text);
+  return 0;
+}
+
+template <typename T>
+int32_t append_to_device(Handle* h, DevBuf<T>& buf, const std::vector<T>& host, size_t from) {
+  size_t n = host.size();
+  if (n <= from) return 0;
+  if (n > buf.cap) {
+    // grow: allocate new, re-upload everything (simple; growth is geometric)
+    DevBuf<T> nb;
+    nb.tally = buf.tally;
+    FEMGPU_CUDA_CHECK(h, nb.reserve(n));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(nb.p, host.data(), n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    buf.release();
+    buf = nb;
+    return 0;
+  }
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(buf.p + from, host.data() + from, (n - from) * sizeof(T),
+                                       cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+}  // namespace
+
+namespace femgpu {
+
+int32_t upload_pending(Handle* h) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  int32_t st;
+  if ((st = append_to_device(h, h->d_x, h->nx, h->nodes_uploaded))) return st;
+  if ((st = append_to_device(h, h->d_y, h->ny, h->nodes_uploaded))) return st;
+  if ((st = append_to_device(h, h->d_z, h->nz, h->nodes_uploaded))) return st;
+  h->nodes_uploaded = h->n_nodes();
+  for (int f = 0; f < kFamilies; ++f) {
+    FamilyHost& fh = h->fh[f];
+    FamilyDev& fd = h->fd[f];
+    for (int c = 0; c < kNodesPerElem[f]; ++c)
+      if ((st = append_to_device(h, fd.conn[c], fh.conn[c], fd.uploaded))) return st;
+    for (int p = 0; p < kPropsPerElem[f]; ++p)
+      if ((st = append_to_device(h, fd.props[p], fh.props[p], fd.uploaded))) return st;
+    if ((st = append_to_device(h, fd.cbase, fh.cbase, fd.uploaded))) return st;
+    fd.uploaded = fh.size();
+  }
+  return 0;
+}
+
+}  // namespace femgpu
+
+extern "C" {
+
+int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t nodes_number,
+                      int32_t device) {
+  if (!out) return FEMGPU_ERR_USAGE;
+  *out = nullptr;
+  if (device == FEMGPU_DEVICE_NONE) {
+    // staging-only handle: host bookkeeping (numbering, duplicate checks, error texts) works,
+    // every call that needs the GPU answers FEMGPU_ERR_NO_DEVICE. Used by the CPU-side tests.
+    femgpu_t* h = new femgpu_t();
+    h->rel_tol = rel_tol;
+    h->abs_tol = abs_tol;
+    h->nodes_number = nodes_number;
+    h->device = FEMGPU_DEVICE_NONE;
+    *out = h;
+    return 0;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_status.code = FEMGPU_ERR_NO_DEVICE;
+    g_create_status.text = std::string("no CUDA device available (") +
+                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                           "); femgpu has no CPU fallback";
+    return FEMGPU_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    g_create_status.code = FEMGPU_ERR_USAGE;
+    g_create_status.text = "device ordinal out of range";
+    return FEMGPU_ERR_USAGE;
+  }
+  femgpu_t* h = new femgpu_t();
+  h->rel_tol = rel_tol;
+  h->abs_tol = abs_tol;
+  h->nodes_number = nodes_number;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_status.code = FEMGPU_ERR_CUDA;
+    g_create_status.text = "could not create a CUDA stream";
+    delete h;
+    return FEMGPU_ERR_CUDA;
+  }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return 0;
+}
+
+static void free_device(femgpu_t* h) {
+  if (h->device < 0) return;
+  cudaSetDevice(h->device);
+  h->d_x.release(); h->d_y.release(); h->d_z.release();
+  for (auto& f : h->fd) {
+    for (auto& c : f.conn) c.release();
+    for (auto& p : f.props) p.release();
+    f.cbase.release(); f.rec.release(); f.mat.release(); f.err.release();
+    f.uploaded = f.validated = 0;
+  }
+  h->blk_key.release(); h->blk_full.release(); h->blk_cptr.release(); h->contrib.release();
+  h->blk_meta.release(); h->blk_order.release(); h->node_blk_ptr.release(); h->node_base.release();
+  h->node_len.release(); h->blk_off.release(); h->slabs.release(); h->row_ptr.release();
+  h->col_idx.release(); h->values.release(); h->scratch.release(); h->d_flag.release();
+  h->dist.send_buf.release(); h->dist.recv_buf.release(); h->dist.recv_slot.release();
+  h->dist.recv_meta.release();
+}
+
+int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device >= 0) cudaStreamSynchronize(h->stream);
+  free_device(h);
+  h->nodes_number = nodes_number;
+  h->node_number.clear(); h->nx.clear(); h->ny.clear(); h->nz.clear();
+  h->node_by_number.clear(); h->node_by_xyz.clear();
+  h->nodes_uploaded = 0;
+  for (auto& f : h->fh) f = FamilyHost();
+  h->pair_seen[0].clear(); h->pair_seen[1].clear(); h->plate_seen.clear();
+  h->n_contrib = 0;
+  h->journal.clear();
+  h->symbolic_valid = false;
+  h->n_rows = h->nnz = 0;
+  h->n_blocks = h->n_slabs = 0;
+  return 0;
+}
+
+void femgpu_destroy(femgpu_t* h) {
+  if (!h) return;
+  if (h->device < 0) {
+    delete h;
+    return;
+  }
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  dist_destroy(h);
+  free_device(h);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* femgpu_last_error(const femgpu_t* h) {
+  if (!h) return g_create_status.text.c_str();
+  return h->last.text.c_str();
+}
+
+int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const double* x,
+                         const double* y, const double* z) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (n && (!number || !x || !y || !z)) return h->fail(FEMGPU_ERR_USAGE, "null node array");
+  h->node_number.reserve(h->n_nodes() + n);
+  h->nx.reserve(h->n_nodes() + n);
+  h->ny.reserve(h->n_nodes() + n);
+  h->nz.reserve(h->n_nodes() + n);
+  for (size_t i = 0; i < n; ++i) {
+    size_t node_index = h->n_nodes();
+    // methods_for_node_data_handle.rs:42-64: limit, then number, (index,) coordinates
+    if (h->nodes_number == 0 || node_index > size_t(h->nodes_number) - 1)
+      return h->fail(FEMGPU_E_NODE_LIMIT,
+                     "Nodes number could not be greater than " + std::to_string(h->nodes_number) + "!");
+    uint32_t dummy;
+    if (h->node_by_number.find(number[i], &dummy))
+      return h->fail(FEMGPU_E_NODE_NUMBER_EXISTS,
+                     "Node with number " + std::to_string(number[i]) + " already exists!");
+    bool has_nan = std::isnan(x[i]) || std::isnan(y[i]) || std::isnan(z[i]);
+    if (!has_nan) {
+      NodeKey k{bits_of(x[i]), bits_of(y[i]), bits_of(z[i])};
+      if (!h->node_by_xyz.emplace(k, uint32_t(node_index)).second)
+        return h->fail(FEMGPU_E_NODE_COORDINATES_EXIST,
+                       "Node with coordinates x: " + rust_debug_f64(x[i]) + ", y: " + rust_debug_f64(y[i]) +
+                           ", z: " + rust_debug_f64(z[i]) + " already exists!");
+    }
+    h->node_by_number.insert(number[i], uint32_t(node_index));
+    h->node_number.push_back(number[i]);
+    h->nx.push_back(x[i]);
+    h->ny.push_back(y[i]);
+    h->nz.push_back(z[i]);
+  }
+  if (n) invalidate(h);
+  return 0;
+}
+
+int32_t femgpu_add_truss(femgpu_t* h, size_t n, const uint32_t* number, const uint32_t* node_1,
+                         const uint32_t* node_2, const double* young_modulus, const double* area,
+                         const double* area_2) {
+  const uint32_t* nodes[4] = {node_1, node_2, nullptr, nullptr};
+  const double* props[11] = {young_modulus, area, area_2};
+  if (h && n && (!node_1 || !node_2 || !young_modulus || !area))
+    return h->fail(FEMGPU_ERR_USAGE, "null truss array");
+  return add_elements(h, FEMGPU_TRUSS, n, number, nodes, props);
+}
+
+int32_t femgpu_add_beam(femgpu_t* h, size_t n, const uint32_t* number, const uint32_t* node_1,
+                        const uint32_t* node_2, const double* young_modulus,
+                        const double* poisson_ratio, const double* area, const double* i11,
+                        const double* i22, const double* i12, const double* it,
+                        const double* shear_factor, const double* local_axis_1) {
+  if (h && n && (!node_1 || !node_2 || !young_modulus || !poisson_ratio || !area || !i11 || !i22 ||
+                 !i12 || !it || !shear_factor || !local_axis_1))
+    return h->fail(FEMGPU_ERR_USAGE, "null beam array");
+  const uint32_t* nodes[4] = {node_1, node_2, nullptr, nullptr};
+  const double* props[11] = {young_modulus, poisson_ratio, area, i11, i22, i12, it, shear_factor,
+                             local_axis_1, local_axis_1 ? local_axis_1 + n : nullptr,
+                             local_axis_1 ? local_axis_1 + 2 * n : nullptr};
+  return add_elements(h, FEMGPU_BEAM, n, number, nodes, props);
+}
+
+int32_t femgpu_add_plate(femgpu_t* h, size_t n, const uint32_t* number, const uint32_t* node_1,
+                         const uint32_t* node_2, const uint32_t* node_3, const uint32_t* node_4,
+                         const double* young_modulus, const double* poisson_ratio,
+                         const double* thickness, const double* shear_factor) {
+  if (h && n && (!node_1 || !node_2 || !node_3 || !node_4 || !young_modulus || !poisson_ratio ||
+                 !thickness || !shear_factor))
+    return h->fail(FEMGPU_ERR_USAGE, "null plate array");
+  const uint32_t* nodes[4] = {node_1, node_2, node_3, node_4};
+  const double* props[11] = {young_modulus, poisson_ratio, thickness, shear_factor};
+  return add_elements(h, FEMGPU_PLATE, n, number, nodes, props);
+}
+
+int32_t femgpu_validate(femgpu_t* h, int32_t* family, uint32_t* number, int32_t* code) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  return validate_pending(h, family, number, code);
+}
+
+int32_t femgpu_counts(const femgpu_t* h, uint64_t* nodes, uint64_t* truss, uint64_t* beam,
+                      uint64_t* plate) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (nodes) *nodes = h->n_nodes();
+  if (truss) *truss = h->fh[0].size();
+  if (beam) *beam = h->fh[1].size();
+  if (plate) *plate = h->fh[2].size();
+  return 0;
+}
+
+int32_t femgpu_symbolic(femgpu_t* h, int64_t* n_rows, int64_t* nnz) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  int32_t st = validate_pending(h, nullptr, nullptr, nullptr);
+  if (st) return st;
+  if (!h->symbolic_valid) {
+    if ((st = upload_pending(h))) return st;
+    if ((st = run_symbolic(h))) return st;
+    h->symbolic_valid = true;
+  }
+  if (n_rows) *n_rows = h->n_rows;
+  if (nnz) *nnz = h->nnz;
+  return 0;
+}
+
+int32_t femgpu_numeric(femgpu_t* h) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "femgpu_numeric before femgpu_symbolic");
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[0], h->stream));
+  int32_t st = run_prep(h, /*validate_only=*/false);
+  if (st) return st;
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[1], h->stream));
+  if ((st = run_assembly(h))) return st;
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[2], h->stream));
+  if (h->dist.enabled && (st = dist_numeric_exchange(h))) return st;
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[3], h->stream));
+  return 0;
+}
+
+int32_t femgpu_synchronize(femgpu_t* h) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t femgpu_assemble(femgpu_t* h, int64_t* n_rows, int64_t* nnz) {
+  int32_t st = femgpu_symbolic(h, n_rows, nnz);
+  if (st) return st;
+  if ((st = femgpu_numeric(h))) return st;
+  return femgpu_synchronize(h);
+}
+
+int32_t femgpu_get_csr(femgpu_t* h, int64_t* row_ptr, int32_t* col_idx, double* values) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "no assembled matrix");
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  if (row_ptr)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(row_ptr, h->row_ptr.p, size_t(h->n_rows + 1) * 8,
+                                         cudaMemcpyDeviceToHost, h->stream));
+  if (col_idx && h->nnz)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(col_idx, h->col_idx.p, size_t(h->nnz) * 4,
+                                         cudaMemcpyDeviceToHost, h->stream));
+  if (values && h->nnz)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(values, h->values.p, size_t(h->nnz) * 8,
+                                         cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t femgpu_get_csr_device(femgpu_t* h, const int64_t** row_ptr, const int32_t** col_idx,
+                              const double** values, int64_t* row_begin, int64_t* row_end) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "no assembled matrix");
+  if (row_ptr) *row_ptr = h->row_ptr.p;
+  if (col_idx) *col_idx = h->col_idx.p;
+  if (values) *values = h->values.p;
+  int64_t rb = 0, re = h->n_rows;
+  if (h->dist.enabled && h->dist.ownership_set) {
+    rb = 6 * int64_t(h->dist.own_begin);
+    re = 6 * int64_t(h->dist.own_end);
+  }
+  if (row_begin) *row_begin = rb;
+  if (row_end) *row_end = re;
+  return 0;
+}
+
+int32_t femgpu_get_nonzero_coo(femgpu_t* h, int64_t* count, int64_t* rows, int64_t* cols,
+                               double* values) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "no assembled matrix");
+  return nonzero_coo(h, count, rows, cols, values);
+}
+
+static int32_t find_element(femgpu_t* h, int32_t family, uint32_t number, size_t* index) {
+  if (family < 0 || family >= kFamilies) return h->fail(FEMGPU_ERR_USAGE, "bad family");
+  uint32_t idx;
+  if (!h->fh[family].by_number.find(number, &idx))
+    // check_*_element_exist (methods_for_truss_data_handle.rs:130-135 and siblings)
+    return h->fail(FEMGPU_E_ELEMENT_NOT_EXIST, std::string(family_name(family)) + " element with number " +
+                                                   std::to_string(number) + " does not exist!");
+  *index = idx;
+  return 0;
+}
+
+int32_t femgpu_rotation_elements(femgpu_t* h, int32_t family, uint32_t number, double out[9]) {
+  if (!h || !out) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  size_t idx;
+  int32_t st = find_element(h, family, number, &idx);
+  if (st) return st;
+  if ((st = validate_pending(h, nullptr, nullptr, nullptr))) return st;
+  if ((st = upload_pending(h))) return st;
+  return element_rotation(h, family, idx, out);
+}
+
+int32_t femgpu_element_matrix(femgpu_t* h, int32_t family, uint32_t number, double* out) {
+  if (!h || !out) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  size_t idx;
+  int32_t st = find_element(h, family, number, &idx);
+  if (st) return st;
+  if ((st = validate_pending(h, nullptr, nullptr, nullptr))) return st;
+  if ((st = upload_pending(h))) return st;
+  return element_matrix(h, family, idx, out);
+}
+
+int32_t femgpu_element_slots(femgpu_t* h, int32_t family, uint32_t number, int64_t* out) {
+  if (!h || !out) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  size_t idx;
+  int32_t st = find_element(h, family, number, &idx);
+  if (st) return st;
+  if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "femgpu_element_slots before femgpu_symbolic");
+  return element_slots(h, family, idx, out);
+}
+
+int32_t femgpu_launch_count(femgpu_t* h, int32_t reset, uint64_t* launches) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (launches) *launches = h->launches;
+  if (reset) h->launches = 0;
+  return 0;
+}
+
+int32_t femgpu_last_numeric_ms(femgpu_t* h, float out[4]) {
+  if (!h || !out) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  FEMGPU_CUDA_CHECK(h, cudaEventSynchronize(h->ev[3]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[0], h->ev[0], h->ev[3]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[1], h->ev[0], h->ev[1]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[2], h->ev[1], h->ev[2]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[3], h->ev[2], h->ev[3]));
+  return 0;
+}
+
+int32_t femgpu_device_bytes(const femgpu_t* h, uint64_t* bytes) {
+  if (!h || !bytes) return FEMGPU_ERR_USAGE;
+  *bytes = h->dev_bytes;
+  return 0;
+}
+
+int32_t femgpu_stream(femgpu_t* h, void** stream) {
+  if (!h || !stream) return FEMGPU_ERR_USAGE;
+  *stream = (void*)h->stream;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// Shared declarations of the femgpu library: device buffers, the handle, kernel launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/femgpu.h"
+
+namespace femgpu {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+struct Status {
+  int32_t code = 0;
+  std::string text;
+};
+
+#define FEMGPU_CUDA_CHECK(h, expr)                                                        \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      return (h)->fail(FEMGPU_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + \
+                                            " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    }                                                                                     \
+  } while (0)
+
+// ---- device buffer ----------------------------------------------------------------------------
+// Grow-only typed device allocation. The handle owns every byte it allocates; sizes are tracked so
+// femgpu_device_bytes() is exact.
+struct Handle;
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  size_t* tally = nullptr;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = n + n / 8 + 16;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) {
+      cudaFree(p);
+      if (tally) *tally -= cap * sizeof(T);
+    }
+    p = q;
+    cap = want;
+    if (tally) *tally += cap * sizeof(T);
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) {
+      cudaFree(p);
+      if (tally) *tally -= cap * sizeof(T);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- data layout ------------------------------------------------------------------------------
+// Host staging keeps struct-of-arrays copies of everything the caller added (needed for rollback,
+// lookups by element number and re-upload after reset); the device holds the same SoA arrays.
+
+struct NodeKey {
+  uint64_t x, y, z;
+  bool operator==(const NodeKey& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct NodeKeyHash {
+  size_t operator()(const NodeKey& k) const {
+    uint64_t h = k.x * 0x9E3779B97F4A7C15ull;
+    h ^= (k.y + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.z + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    return size_t(h);
+  }
+};
+
+// number -> index map with a dense fast path (labels are usually 1..n)
+struct NumberMap {
+  std::vector<uint32_t> dense;  // value+1, 0 = absent
+  std::unordered_map<uint32_t, uint32_t> sparse;
+  size_t count = 0;
+  static constexpr uint32_t kDenseLimit = 1u << 28;
+  bool find(uint32_t number, uint32_t* idx) const {
+    if (number < dense.size()) {
+      uint32_t v = dense[number];
+      if (v) {
+        *idx = v - 1;
+        return true;
+      }
+      return false;
+    }
+    auto it = sparse.find(number);
+    if (it == sparse.end()) return false;
+    *idx = it->second;
+    return true;
+  }
+  void insert(uint32_t number, uint32_t idx) {
+    if (number < kDenseLimit && number <= 8 * (count + 1024)) {
+      if (number >= dense.size()) dense.resize(std::max<size_t>(size_t(number) + 1, dense.size() * 2), 0);
+      dense[number] = idx + 1;
+    } else {
+      sparse[number] = idx;
+    }
+    ++count;
+  }
+  void erase(uint32_t number) {
+    if (number < dense.size() && dense[number]) {
+      dense[number] = 0;
+      --count;
+      return;
+    }
+    if (sparse.erase(number)) --count;
+  }
+  void clear() {
+    dense.clear();
+    sparse.clear();
+    count = 0;
+  }
+};
+
+struct PlateKey {
+  uint32_t n[4];  // sorted
+  bool operator==(const PlateKey& o) const {
+    return n[0] == o.n[0] && n[1] == o.n[1] && n[2] == o.n[2] && n[3] == o.n[3];
+  }
+};
+struct PlateKeyHash {
+  size_t operator()(const PlateKey& k) const {
+    uint64_t a = (uint64_t(k.n[0]) << 32) | k.n[1], b = (uint64_t(k.n[2]) << 32) | k.n[3];
+    a *= 0x9E3779B97F4A7C15ull;
+    a ^= (b + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2));
+    return size_t(a);
+  }
+};
+
+constexpr int kFamilies = 3;
+constexpr int kNodesPerElem[kFamilies] = {2, 2, 4};
+constexpr int kPairsPerElem[kFamilies] = {4, 4, 16};
+constexpr int kPropsPerElem[kFamilies] = {3, 11, 4};  // truss: E,A,A2; beam: 8 props + axis[3]; plate: 4
+constexpr int kRecDoubles[kFamilies] = {4, 16, 16};   // per-element record written by the prep kernels
+
+struct FamilyHost {
+  std::vector<uint32_t> number;       // user label
+  std::vector<uint32_t> conn[4];      // node indices (0-based), SoA
+  std::vector<uint32_t> conn_number[4];  // node numbers as given (for messages)
+  std::vector<double> props[11];      // SoA
+  std::vector<int64_t> cbase;         // offset of the element's first contribution in global
+                                      // insertion order (= accumulation order of the reference)
+  NumberMap by_number;
+  size_t size() const { return number.size(); }
+};
+
+struct FamilyDev {
+  DevBuf<uint32_t> conn[4];
+  DevBuf<double> props[11];
+  DevBuf<int64_t> cbase;
+  DevBuf<double> rec;    // kRecDoubles per element
+  DevBuf<double> mat;    // plates only: Cm, Cb, Cs, nu
+  DevBuf<int32_t> err;   // per-element validation code
+  size_t uploaded = 0;   // elements already on the device
+  size_t validated = 0;  // elements already checked by the prep kernel
+};
+
+// block metadata consumed by the assembly kernel, in thread order (slab-major)
+struct BlockMeta {
+  uint32_t seg0;     // slab-relative offset of the block's first entry in dof rows 0..2
+  uint32_t seg3;     // same for dof rows 3..5, 0xFFFFFFFF for a 3x3 (truss-only) block
+  uint32_t strides;  // row length of rows 0..2 (low 16 bits) | rows 3..5 (high 16 bits)
+  uint32_t cptr;     // first contribution (thread order); count = next block's cptr - cptr
+};
+
+struct SlabDesc {
+  int64_t val_base;    // first CSR value of the slab
+  uint32_t val_count;  // values in the slab
+  uint32_t blk_begin;  // first block (thread order)
+  uint32_t blk_count;
+  uint32_t flags;      // bit 0: too large for shared memory -> write straight to global
+};
+
+struct DistState {
+  bool enabled = false;
+  int rank = 0, world = 1;
+  void* comm = nullptr;  // ncclComm_t
+  uint32_t own_begin = 0, own_end = 0;
+  bool ownership_set = false;
+  // ghost exchange plan (built by the symbolic pass)
+  std::vector<int64_t> send_blocks, recv_blocks;    // per peer: number of node-pair blocks
+  std::vector<int64_t> send_vals, recv_vals;        // per peer: doubles
+  DevBuf<double> send_buf, recv_buf;
+  DevBuf<int64_t> recv_slot;   // per received block: value index of its (row 0, col 0) entry
+  DevBuf<uint32_t> recv_meta;  // per received block: strides / kind to place rows
+  uint64_t last_sent = 0, last_recv = 0;
+};
+
+struct Handle {
+  // ---- properties (structs/props.rs) ----
+  double rel_tol = 0, abs_tol = 0;
+  uint32_t nodes_number = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  mutable Status last;
+  size_t dev_bytes = 0;
+  uint64_t launches = 0;
+  float last_ms[4] = {0, 0, 0, 0};
+
+  // ---- nodes ----
+  std::vector<uint32_t> node_number;
+  std::vector<double> nx, ny, nz;
+  NumberMap node_by_number;
+  std::unordered_map<NodeKey, uint32_t, NodeKeyHash> node_by_xyz;
+  DevBuf<double> d_x, d_y, d_z;
+  size_t nodes_uploaded = 0;
+
+  // ---- elements ----
+  FamilyHost fh[kFamilies];
+  FamilyDev fd[kFamilies];
+  std::unordered_map<uint64_t, uint32_t> pair_seen[2];  // truss, beam: sorted node-index pair
+  std::unordered_map<PlateKey, uint32_t, PlateKeyHash> plate_seen;
+  int64_t n_contrib = 0;  // running contribution counter (global insertion order)
+  // insertion journal for prefix rollback: (family, count) runs in global order
+  std::vector<std::pair<int, size_t>> journal;
+
+  // ---- symbolic products ----
+  bool symbolic_valid = false;
+  int64_t n_rows = 0, nnz = 0;
+  uint32_t n_blocks = 0, n_slabs = 0;
+  int key_bits = 1;
+  DevBuf<uint64_t> blk_key;        // sorted unique (a << key_bits | b)
+  DevBuf<uint8_t> blk_full;        // 1 = 6x6, 0 = 3x3
+  DevBuf<uint32_t> blk_cptr;       // [n_blocks+1] contributions, thread order
+  DevBuf<uint32_t> contrib;        // family<<30 | pair<<26 | element, thread order
+  DevBuf<BlockMeta> blk_meta;      // thread order
+  DevBuf<uint32_t> blk_order;      // thread position -> sorted block id
+  DevBuf<uint32_t> node_blk_ptr;   // [n_nodes_total+1]
+  DevBuf<int64_t> node_base;       // [n_nodes_total+1] first value of the node's rows
+  DevBuf<uint32_t> node_len;       // [2*n_nodes_total] len03, len35
+  DevBuf<uint32_t> blk_off;        // [2*n_blocks] off03, off35 within the node's rows
+  DevBuf<SlabDesc> slabs;
+  DevBuf<int64_t> row_ptr;         // [n_rows+1]
+  DevBuf<int32_t> col_idx;         // [nnz]
+  DevBuf<double> values;           // [nnz]
+  DevBuf<uint8_t> scratch;         // CUB temp storage and sort double-buffers
+  DevBuf<int32_t> d_flag;          // small device scalars
+
+  DistState dist;
+
+  Handle() {
+    auto tie = [&](auto& b) { b.tally = &dev_bytes; };
+    tie(d_x); tie(d_y); tie(d_z);
+    for (auto& f : fd) {
+      for (auto& c : f.conn) tie(c);
+      for (auto& p : f.props) tie(p);
+      tie(f.cbase); tie(f.rec); tie(f.mat); tie(f.err);
+    }
+    tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order);
+    tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
+    tie(col_idx); tie(values); tie(scratch); tie(d_flag);
+    tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_slot); tie(dist.recv_meta);
+  }
+
+  int32_t fail(int32_t code, const std::string& text) const {
+    last.code = code;
+    last.text = text;
+    return code;
+  }
+  size_t n_nodes() const { return node_number.size(); }
+};
+
+// ---- kernels' host entry points (one per translation unit) -------------------------------------
+int32_t upload_pending(Handle* h);                       // api.cu
+int32_t run_prep(Handle* h, bool validate_only);         // prep.cu
+int32_t first_error(Handle* h, int* family, size_t* index, int* code);  // prep.cu
+int32_t run_symbolic(Handle* h);                         // symbolic.cu
+int32_t run_assembly(Handle* h);                         // numeric.cu
+int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);   // numeric.cu
+int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
+int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host);   // symbolic.cu
+int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals);  // symbolic.cu
+int32_t dist_symbolic_exchange(Handle* h);               // dist.cu
+int32_t dist_numeric_exchange(Handle* h);                // dist.cu
+void dist_destroy(Handle* h);                            // dist.cu
+
+constexpr int kAsmThreads = 128;       // threads per assembly CTA (one node-pair block each)
+constexpr int kSlabQuota = 112;        // node-pair blocks a slab aims for (< kAsmThreads so a
+                                       // trailing node rarely spills into a second round)
+constexpr int kSlabSmemBytes = 72 * 1024;  // staging capacity; larger slabs write straight to HBM
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return uint32_t((a + b - 1) / b); }
+
+}  // namespace femgpu
+
+struct femgpu_handle : femgpu::Handle {};

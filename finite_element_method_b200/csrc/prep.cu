@@ -1,0 +1,258 @@
+// Element-record kernels: one thread per element computes everything that needs transcendental
+// functions or the abs_tol clipping (rotation matrices, principal inertia, Jacobian scalars) and
+// the element-level validity checks of Truss/Beam/Plate::create, and writes a compact record the
+// assembly kernel reads (truss 32 B, beam 128 B, plate 128 B + 32 B material).
+//
+// Compiled with -fmad=false: this file follows the reference's operation order, and Rust does not
+// contract a*b+c.
+//
+// Loads are struct-of-arrays and coalesced (thread i reads element i of every property array);
+// node coordinates are gathered through the read-only path. Records are written as 16-byte
+// vectors.
+#include "common.cuh"
+#include "element_math.cuh"
+
+namespace femgpu {
+
+namespace {
+
+constexpr int kPrepThreads = 256;
+
+__device__ __forceinline__ void load_xyz(const double* __restrict__ x, const double* __restrict__ y,
+                                         const double* __restrict__ z, uint32_t i, double p[3]) {
+  p[0] = __ldg(x + i);
+  p[1] = __ldg(y + i);
+  p[2] = __ldg(z + i);
+}
+
+template <bool kWriteErr>
+__global__ void __launch_bounds__(kPrepThreads)
+truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
+                  const uint32_t* __restrict__ n2, const double* __restrict__ E,
+                  const double* __restrict__ A, const double* __restrict__ A2,
+                  const double* __restrict__ x, const double* __restrict__ y,
+                  const double* __restrict__ z, double abs_tol, double4* __restrict__ rec,
+                  int32_t* __restrict__ err) {
+  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double p1[3], p2[3], q[9], k00 = 0.0;
+  load_xyz(x, y, z, n1[e], p1);
+  load_xyz(x, y, z, n2[e], p2);
+  int code = truss_record(p1, p2, E[e], A[e], A2[e], abs_tol, q, &k00);
+  if (code) {
+    q[0] = q[1] = q[2] = 0.0;
+    k00 = 0.0;
+  }
+  rec[e] = make_double4(q[0], q[1], q[2], k00);
+  if (kWriteErr) err[e] = code;
+}
+
+template <bool kWriteErr>
+__global__ void __launch_bounds__(kPrepThreads)
+beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
+                 const uint32_t* __restrict__ n2, const double* __restrict__ E,
+                 const double* __restrict__ nu, const double* __restrict__ A,
+                 const double* __restrict__ I11, const double* __restrict__ I22,
+                 const double* __restrict__ I12, const double* __restrict__ It,
+                 const double* __restrict__ ks, const double* __restrict__ ax,
+                 const double* __restrict__ ay, const double* __restrict__ az,
+                 const double* __restrict__ x, const double* __restrict__ y,
+                 const double* __restrict__ z, double rel_tol, double abs_tol,
+                 double* __restrict__ rec, int32_t* __restrict__ err) {
+  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double p1[3], p2[3], r[16];
+  load_xyz(x, y, z, n1[e], p1);
+  load_xyz(x, y, z, n2[e], p2);
+  double axis[3] = {ax[e], ay[e], az[e]};
+  int code = beam_record(p1, p2, E[e], nu[e], A[e], I11[e], I22[e], I12[e], It[e], ks[e], axis,
+                         rel_tol, abs_tol, r);
+  if (code) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0.0;
+  }
+  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = make_double2(r[2 * i], r[2 * i + 1]);
+  if (kWriteErr) err[e] = code;
+}
+
+template <bool kWriteErr>
+__global__ void __launch_bounds__(kPrepThreads)
+plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
+                  const uint32_t* __restrict__ n2, const uint32_t* __restrict__ n3,
+                  const uint32_t* __restrict__ n4, const double* __restrict__ E,
+                  const double* __restrict__ nu, const double* __restrict__ t,
+                  const double* __restrict__ ks, const double* __restrict__ x,
+                  const double* __restrict__ y, const double* __restrict__ z, double abs_tol,
+                  double* __restrict__ rec, double4* __restrict__ mat, int32_t* __restrict__ err) {
+  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double p1[3], p2[3], p3[3], p4[3], r[16], m[4];
+  load_xyz(x, y, z, n1[e], p1);
+  load_xyz(x, y, z, n2[e], p2);
+  load_xyz(x, y, z, n3[e], p3);
+  load_xyz(x, y, z, n4[e], p4);
+  int code = plate_record(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m);
+  if (code) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0.0;
+    m[0] = m[1] = m[2] = m[3] = 0.0;
+  }
+  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = make_double2(r[2 * i], r[2 * i + 1]);
+  mat[e] = make_double4(m[0], m[1], m[2], m[3]);
+  if (kWriteErr) err[e] = code;
+}
+
+// smallest insertion position (cbase) among failing elements; family in the low 2 bits
+__global__ void first_error_kernel(uint32_t from, uint32_t n, int family,
+                                   const int32_t* __restrict__ err,
+                                   const int64_t* __restrict__ cbase,
+                                   unsigned long long* __restrict__ out) {
+  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (err[e] != 0) {
+    unsigned long long key = ((unsigned long long)cbase[e] << 2) | (unsigned)family;
+    atomicMin(out, key);  // integer min: order independent
+  }
+}
+
+__global__ void rotation_kernel(int family, uint32_t e, const uint32_t* n1, const uint32_t* n2,
+                                const uint32_t* n3, const uint32_t* n4, const double* const* props,
+                                const double* x, const double* y, const double* z, double rel_tol,
+                                double abs_tol, double* out) {
+  double p1[3], p2[3], p3[3], p4[3];
+  load_xyz(x, y, z, n1[e], p1);
+  load_xyz(x, y, z, n2[e], p2);
+  if (family == FEMGPU_TRUSS) {
+    double q[9], k00;
+    truss_record(p1, p2, 1.0, 1.0, NAN, abs_tol, q, &k00);
+    for (int i = 0; i < 9; ++i) out[i] = q[i];
+  } else if (family == FEMGPU_BEAM) {
+    double r[16];
+    double axis[3] = {props[8][e], props[9][e], props[10][e]};
+    beam_record(p1, p2, props[0][e], props[1][e], props[2][e], props[3][e], props[4][e],
+                props[5][e], props[6][e], props[7][e], axis, rel_tol, abs_tol, r);
+    for (int i = 0; i < 9; ++i) out[i] = r[i];
+  } else {
+    load_xyz(x, y, z, n3[e], p3);
+    load_xyz(x, y, z, n4[e], p4);
+    double q[9];
+    plate_rotation(p2, p3, p4, abs_tol, q);
+    for (int i = 0; i < 9; ++i) out[i] = q[i];
+  }
+}
+
+}  // namespace
+
+int32_t run_prep(Handle* h, bool validate_only) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  for (int f = 0; f < kFamilies; ++f) {
+    FamilyDev& fd = h->fd[f];
+    size_t n = h->fh[f].size();
+    size_t from = validate_only ? fd.validated : 0;
+    if (n == 0) continue;
+    // records are needed for every element either way (the buffers may have been reallocated)
+    size_t before = fd.rec.cap;
+    FEMGPU_CUDA_CHECK(h, fd.rec.reserve(n * size_t(kRecDoubles[f])));
+    if (f == FEMGPU_PLATE) FEMGPU_CUDA_CHECK(h, fd.mat.reserve(n * 4));
+    FEMGPU_CUDA_CHECK(h, fd.err.reserve(n));
+    if (fd.rec.cap != before) from = validate_only ? fd.validated : 0;
+    if (from >= n) continue;
+    uint32_t grid = div_up(n - from, kPrepThreads);
+    const double* x = h->d_x.p;
+    const double* y = h->d_y.p;
+    const double* z = h->d_z.p;
+    auto P = [&](int k) { return (const double*)fd.props[k].p; };
+    if (f == FEMGPU_TRUSS) {
+      if (validate_only)
+        truss_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
+            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
+            h->abs_tol, reinterpret_cast<double4*>(fd.rec.p), fd.err.p);
+      else
+        truss_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
+            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
+            h->abs_tol, reinterpret_cast<double4*>(fd.rec.p), fd.err.p);
+    } else if (f == FEMGPU_BEAM) {
+      if (validate_only)
+        beam_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
+            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
+            P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
+      else
+        beam_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
+            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
+            P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
+    } else {
+      if (validate_only)
+        plate_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
+            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
+            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p,
+            reinterpret_cast<double4*>(fd.mat.p), fd.err.p);
+      else
+        plate_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
+            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
+            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p,
+            reinterpret_cast<double4*>(fd.mat.p), fd.err.p);
+    }
+    h->launches++;
+    FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+int32_t first_error(Handle* h, int* family, size_t* index, int* code) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  FEMGPU_CUDA_CHECK(h, h->d_flag.reserve(16));
+  unsigned long long* d_key = reinterpret_cast<unsigned long long*>(h->d_flag.p);
+  unsigned long long init = ~0ull;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_key, &init, 8, cudaMemcpyHostToDevice, h->stream));
+  for (int f = 0; f < kFamilies; ++f) {
+    FamilyDev& fd = h->fd[f];
+    size_t n = h->fh[f].size(), from = fd.validated;
+    if (from >= n) continue;
+    first_error_kernel<<<div_up(n - from, 256), 256, 0, h->stream>>>(uint32_t(from), uint32_t(n), f,
+                                                                      fd.err.p, fd.cbase.p, d_key);
+    h->launches++;
+  }
+  unsigned long long key = 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  if (key == ~0ull) {
+    *family = -1;
+    return 0;
+  }
+  int f = int(key & 3);
+  int64_t cb = int64_t(key >> 2);
+  const auto& cbv = h->fh[f].cbase;
+  size_t idx = size_t(std::lower_bound(cbv.begin(), cbv.end(), cb) - cbv.begin());
+  int32_t ec = 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&ec, h->fd[f].err.p + idx, 4, cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  *family = f;
+  *index = idx;
+  *code = ec;
+  return 0;
+}
+
+int32_t element_rotation(Handle* h, int family, size_t index, double* out_host) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  FamilyDev& fd = h->fd[family];
+  FEMGPU_CUDA_CHECK(h, h->scratch.reserve(4096));
+  const double* hp[11];
+  for (int k = 0; k < 11; ++k) hp[k] = fd.props[k].p;
+  const double** d_props = reinterpret_cast<const double**>(h->scratch.p);
+  double* d_out = reinterpret_cast<double*>(h->scratch.p + 1024);
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_props, hp, sizeof hp, cudaMemcpyHostToDevice, h->stream));
+  rotation_kernel<<<1, 1, 0, h->stream>>>(family, uint32_t(index), fd.conn[0].p, fd.conn[1].p,
+                                          fd.conn[2].p, fd.conn[3].p, d_props, h->d_x.p, h->d_y.p,
+                                          h->d_z.p, h->rel_tol, h->abs_tol, d_out);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(out_host, d_out, 72, cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // namespace femgpu

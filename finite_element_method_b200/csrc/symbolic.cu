@@ -1,0 +1,543 @@
+// One-time symbolic pass (integer work only, bit-exact by construction):
+//   global DOF numbering  row = 6*node_index + dof            (structs/node.rs:8, fem.rs:37)
+//   node-pair block list  sort/unique of (row node, col node) keys of every element's local pairs
+//                         — the start_positions tables of methods_for_truss_data_handle.rs:83-109,
+//                         methods_for_beam_data_handle.rs:96-123, methods_for_plate_data_handle.rs:113-132
+//   CSR row_ptr / col_idx on the structural pattern (3x3 per truss-only pair, 6x6 otherwise)
+//   gather map            per block, the (family, local pair, element) contributions in global
+//                         insertion order (= the order the reference accumulates in)
+//   slabs                 contiguous node ranges whose CSR values one CTA stages in shared memory,
+//                         blocks inside a slab ordered by contribution count so the threads of a
+//                         warp loop the same number of times.
+// Sorting/scanning uses CUB device primitives; everything else is hand-written kernels.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace femgpu {
+
+namespace {
+
+struct Tmp {  // RAII scratch allocation
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  ~Tmp() {
+    if (p) cudaFree(p);
+  }
+  template <typename T>
+  T* as() {
+    return static_cast<T*>(p);
+  }
+};
+
+template <int kNodes>
+__global__ void gen_contrib_kernel(uint32_t n_elem, int family, const uint32_t* __restrict__ c0,
+                                   const uint32_t* __restrict__ c1, const uint32_t* __restrict__ c2,
+                                   const uint32_t* __restrict__ c3,
+                                   const int64_t* __restrict__ cbase, int key_bits,
+                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  constexpr int kPairs = kNodes * kNodes;
+  uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t e = uint32_t(t / kPairs);
+  int pair = int(t % kPairs);
+  if (e >= n_elem) return;
+  int la = pair / kNodes, lb = pair % kNodes;
+  const uint32_t* cs[4] = {c0, c1, c2, c3};
+  uint32_t a = cs[la][e], b = cs[lb][e];
+  int64_t pos = cbase[e] + pair;
+  keys[pos] = (uint64_t(a) << key_bits) | b;
+  vals[pos] = (uint32_t(family) << 30) | (uint32_t(pair) << 26) | e;
+}
+
+__global__ void block_kind_kernel(uint32_t n_blocks, const uint32_t* __restrict__ cptr,
+                                  const uint32_t* __restrict__ contrib, uint8_t* __restrict__ full) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks) return;
+  uint8_t f = 0;
+  for (uint32_t c = cptr[i]; c < cptr[i + 1]; ++c)
+    if ((contrib[c] >> 30) != FEMGPU_TRUSS) {
+      f = 1;
+      break;
+    }
+  full[i] = f;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ a, uint32_t n,
+                                                    uint64_t v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t n,
+                                                    uint32_t v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// node_blk_ptr[a] = first block whose row node is >= a, for a in [0, n_nodes]
+__global__ void node_ptr_kernel(uint32_t n_nodes, uint32_t n_blocks, int key_bits,
+                                const uint64_t* __restrict__ blk_key,
+                                uint32_t* __restrict__ node_blk_ptr) {
+  uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > n_nodes) return;
+  node_blk_ptr[a] = (a == n_nodes) ? n_blocks : lower_bound_u64(blk_key, n_blocks, uint64_t(a) << key_bits);
+}
+
+// per node: offsets of its blocks inside dof rows 0..2 / 3..5, the two row lengths, value count
+__global__ void node_layout_kernel(uint32_t n_nodes, const uint32_t* __restrict__ node_blk_ptr,
+                                   const uint8_t* __restrict__ full, uint32_t* __restrict__ blk_off,
+                                   uint32_t* __restrict__ node_len, int64_t* __restrict__ node_size,
+                                   int32_t* __restrict__ overflow) {
+  uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_nodes) return;
+  uint32_t l03 = 0, l35 = 0;
+  for (uint32_t b = node_blk_ptr[a]; b < node_blk_ptr[a + 1]; ++b) {
+    blk_off[2 * b] = l03;
+    blk_off[2 * b + 1] = full[b] ? l35 : 0xFFFFFFFFu;
+    l03 += full[b] ? 6 : 3;
+    l35 += full[b] ? 6 : 0;
+  }
+  node_len[2 * a] = l03;
+  node_len[2 * a + 1] = l35;
+  node_size[a] = 3 * int64_t(l03) + 3 * int64_t(l35);
+  if (l03 >= 65536u) *overflow = 1;
+}
+
+__global__ void row_ptr_kernel(uint32_t n_nodes, const int64_t* __restrict__ node_base,
+                               const uint32_t* __restrict__ node_len, int64_t* __restrict__ row_ptr) {
+  uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > n_nodes) return;
+  if (a == n_nodes) {
+    row_ptr[6 * size_t(a)] = node_base[a];
+    return;
+  }
+  int64_t base = node_base[a];
+  uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) row_ptr[6 * size_t(a) + i] = base + int64_t(i) * l03;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) row_ptr[6 * size_t(a) + 3 + i] = base + 3 * int64_t(l03) + int64_t(i) * l35;
+}
+
+// one warp per node: lanes stride over (block, dof row, dof col) of the node's blocks
+__global__ void col_idx_kernel(uint32_t n_nodes, int key_bits, const uint64_t* __restrict__ blk_key,
+                               const uint32_t* __restrict__ node_blk_ptr,
+                               const uint8_t* __restrict__ full, const uint32_t* __restrict__ blk_off,
+                               const uint32_t* __restrict__ node_len,
+                               const int64_t* __restrict__ node_base, int32_t* __restrict__ col_idx) {
+  uint32_t warp = uint32_t((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= n_nodes) return;
+  uint32_t a = warp;
+  uint32_t b0 = node_blk_ptr[a], b1 = node_blk_ptr[a + 1];
+  if (b0 == b1) return;
+  uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+  int64_t base = node_base[a];
+  const uint64_t mask = (uint64_t(1) << key_bits) - 1;
+  uint32_t total = (b1 - b0) * 36;
+  for (uint32_t t = lane; t < total; t += 32) {
+    uint32_t blk = b0 + t / 36, i = (t % 36) / 6, j = t % 6;
+    bool f = full[blk] != 0;
+    if (!f && (i >= 3 || j >= 3)) continue;
+    uint32_t col_node = uint32_t(blk_key[blk] & mask);
+    int64_t pos = (i < 3) ? base + int64_t(i) * l03 + blk_off[2 * blk] + j
+                          : base + 3 * int64_t(l03) + int64_t(i - 3) * l35 + blk_off[2 * blk + 1] + j;
+    col_idx[pos] = int32_t(6 * col_node + j);
+  }
+}
+
+__global__ void slab_kernel(uint32_t n_slabs, uint32_t quota, uint32_t n_nodes,
+                            const uint32_t* __restrict__ node_blk_ptr,
+                            const int64_t* __restrict__ node_base, uint32_t smem_doubles,
+                            SlabDesc* __restrict__ slabs, int32_t* __restrict__ overflow) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_slabs) return;
+  uint32_t first = lower_bound_u32(node_blk_ptr, n_nodes, k * quota);
+  uint32_t next = (k + 1 == n_slabs) ? n_nodes : lower_bound_u32(node_blk_ptr, n_nodes, (k + 1) * quota);
+  SlabDesc d;
+  d.val_base = node_base[first];
+  int64_t cnt = node_base[next] - d.val_base;
+  if (cnt >= (int64_t(1) << 32)) *overflow = 2;
+  d.val_count = uint32_t(cnt);
+  d.blk_begin = node_blk_ptr[first];
+  d.blk_count = node_blk_ptr[next] - d.blk_begin;
+  d.flags = (d.val_count > smem_doubles) ? 1u : 0u;
+  slabs[k] = d;
+}
+
+// sort key for the in-slab thread order: slab id, then descending contribution count
+__global__ void order_key_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
+                                 const uint64_t* __restrict__ blk_key,
+                                 const uint32_t* __restrict__ node_blk_ptr,
+                                 const uint32_t* __restrict__ cptr, uint64_t* __restrict__ okey,
+                                 uint32_t* __restrict__ oval) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks) return;
+  uint32_t a = uint32_t(blk_key[i] >> key_bits);
+  uint32_t slab = node_blk_ptr[a] / quota;
+  uint32_t cnt = cptr[i + 1] - cptr[i];
+  okey[i] = (uint64_t(slab) << 8) | (255u - min(cnt, 255u));
+  oval[i] = i;
+}
+
+__global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restrict__ order,
+                                     const uint32_t* __restrict__ cptr, uint32_t* __restrict__ cnt) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_blocks) return;
+  uint32_t i = order[p];
+  cnt[p] = cptr[i + 1] - cptr[i];
+}
+
+__global__ void ordered_meta_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
+                                    const uint32_t* __restrict__ order,
+                                    const uint64_t* __restrict__ blk_key,
+                                    const uint32_t* __restrict__ node_blk_ptr,
+                                    const uint32_t* __restrict__ blk_off,
+                                    const uint32_t* __restrict__ node_len,
+                                    const int64_t* __restrict__ node_base,
+                                    const SlabDesc* __restrict__ slabs,
+                                    const uint32_t* __restrict__ cptr_sorted,
+                                    const uint32_t* __restrict__ contrib_sorted,
+                                    const uint32_t* __restrict__ cptr_ord,
+                                    uint32_t* __restrict__ contrib_ord, BlockMeta* __restrict__ meta) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_blocks) return;
+  uint32_t i = order[p];
+  uint32_t a = uint32_t(blk_key[i] >> key_bits);
+  uint32_t slab = node_blk_ptr[a] / quota;
+  uint32_t rel = uint32_t(node_base[a] - slabs[slab].val_base);
+  uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+  uint32_t o03 = blk_off[2 * i], o35 = blk_off[2 * i + 1];
+  BlockMeta m;
+  m.seg0 = rel + o03;
+  m.seg3 = (o35 == 0xFFFFFFFFu) ? 0xFFFFFFFFu : rel + 3 * l03 + o35;
+  m.strides = l03 | (l35 << 16);
+  m.cptr = cptr_ord[p];
+  meta[p] = m;
+  uint32_t src = cptr_sorted[i], n = cptr_sorted[i + 1] - src, dst = cptr_ord[p];
+  for (uint32_t c = 0; c < n; ++c) contrib_ord[dst + c] = contrib_sorted[src + c];
+}
+
+__global__ void element_slots_kernel(int n_nodes_elem, int dof, const uint32_t* __restrict__ nodes,
+                                     uint32_t n_blocks, int key_bits,
+                                     const uint64_t* __restrict__ blk_key,
+                                     const uint32_t* __restrict__ blk_off,
+                                     const uint32_t* __restrict__ node_len,
+                                     const int64_t* __restrict__ node_base, int64_t* __restrict__ out) {
+  int n = n_nodes_elem * dof;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * n) return;
+  int row = t / n, col = t % n;
+  int la = row / dof, i = row % dof, lb = col / dof, j = col % dof;
+  uint32_t a = nodes[la], b = nodes[lb];
+  uint64_t key = (uint64_t(a) << key_bits) | b;
+  uint32_t blk = lower_bound_u64(blk_key, n_blocks, key);
+  int64_t slot = -1;
+  if (blk < n_blocks && blk_key[blk] == key) {
+    uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+    uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
+    bool full = o35 != 0xFFFFFFFFu;
+    if (i < 3 && (j < 3 || full)) slot = node_base[a] + int64_t(i) * l03 + o03 + j;
+    if (i >= 3 && full) slot = node_base[a] + 3 * int64_t(l03) + int64_t(i - 3) * l35 + o35 + j;
+  }
+  out[t] = slot;
+}
+
+__global__ void nz_flag_kernel(int64_t nnz, const double* __restrict__ values, int64_t* __restrict__ flag) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < nnz) flag[i] = values[i] != 0.0 ? 1 : 0;
+}
+
+__global__ void nz_write_kernel(int64_t nnz, int64_t n_rows, const double* __restrict__ values,
+                                const int64_t* __restrict__ pos, const int64_t* __restrict__ row_ptr,
+                                const int32_t* __restrict__ col_idx, int64_t* __restrict__ rows,
+                                int64_t* __restrict__ cols, double* __restrict__ vals) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  double v = values[i];
+  if (v == 0.0) return;
+  // row = last r with row_ptr[r] <= i
+  int64_t lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (row_ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  int64_t p = pos[i];
+  rows[p] = lo;
+  cols[p] = col_idx[i];
+  vals[p] = v;
+}
+
+}  // namespace
+
+#define SYM_CHECK(expr) FEMGPU_CUDA_CHECK(h, (expr))
+
+int32_t run_symbolic(Handle* h) {
+  SYM_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const uint32_t N = h->nodes_number;
+  h->n_rows = 6 * int64_t(N);
+  const int64_t NC = h->n_contrib;
+  if (NC >= (int64_t(1) << 31)) return h->fail(FEMGPU_ERR_LIMIT, "more than 2^31 node-pair contributions on one device");
+  int kb = 1;
+  while ((uint64_t(1) << kb) < uint64_t(N)) ++kb;
+  h->key_bits = kb;
+
+  SYM_CHECK(h->node_blk_ptr.reserve(size_t(N) + 1));
+  SYM_CHECK(h->node_base.reserve(size_t(N) + 1));
+  SYM_CHECK(h->node_len.reserve(2 * size_t(N) + 2));
+  SYM_CHECK(h->row_ptr.reserve(size_t(h->n_rows) + 1));
+  SYM_CHECK(h->d_flag.reserve(16));
+  SYM_CHECK(cudaMemsetAsync(h->d_flag.p, 0, 64, s));
+
+  if (NC == 0) {
+    SYM_CHECK(cudaMemsetAsync(h->node_blk_ptr.p, 0, (size_t(N) + 1) * 4, s));
+    SYM_CHECK(cudaMemsetAsync(h->node_base.p, 0, (size_t(N) + 1) * 8, s));
+    SYM_CHECK(cudaMemsetAsync(h->node_len.p, 0, (2 * size_t(N) + 2) * 4, s));
+    SYM_CHECK(cudaMemsetAsync(h->row_ptr.p, 0, (size_t(h->n_rows) + 1) * 8, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+    h->n_blocks = h->n_slabs = 0;
+    h->nnz = 0;
+    return 0;
+  }
+
+  // ---- 1. contributions in global insertion order, then stable sort by (row node, col node)
+  Tmp keys_a, keys_b, vals_a, vals_b;
+  SYM_CHECK(keys_a.alloc(size_t(NC) * 8));
+  SYM_CHECK(keys_b.alloc(size_t(NC) * 8));
+  SYM_CHECK(vals_a.alloc(size_t(NC) * 4));
+  SYM_CHECK(vals_b.alloc(size_t(NC) * 4));
+  for (int f = 0; f < kFamilies; ++f) {
+    FamilyDev& fd = h->fd[f];
+    size_t n = h->fh[f].size();
+    if (!n) continue;
+    uint64_t threads = uint64_t(n) * kPairsPerElem[f];
+    uint32_t grid = div_up(threads, 256);
+    if (f == FEMGPU_PLATE)
+      gen_contrib_kernel<4><<<grid, 256, 0, s>>>(uint32_t(n), f, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p,
+                                                 fd.conn[3].p, fd.cbase.p, kb, keys_a.as<uint64_t>(),
+                                                 vals_a.as<uint32_t>());
+    else
+      gen_contrib_kernel<2><<<grid, 256, 0, s>>>(uint32_t(n), f, fd.conn[0].p, fd.conn[1].p, nullptr, nullptr,
+                                                 fd.cbase.p, kb, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+    h->launches++;
+  }
+  SYM_CHECK(cudaGetLastError());
+  {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(),
+                                    vals_a.as<uint32_t>(), vals_b.as<uint32_t>(), int(NC), 0, 2 * kb, s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(),
+                                              vals_a.as<uint32_t>(), vals_b.as<uint32_t>(), int(NC), 0,
+                                              2 * kb, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  uint64_t* keys_sorted = keys_b.as<uint64_t>();
+  uint32_t* contrib_sorted = vals_b.as<uint32_t>();
+
+  // ---- 2. unique blocks + contribution counts
+  Tmp uniq, counts, nruns;
+  SYM_CHECK(uniq.alloc(size_t(NC) * 8));
+  SYM_CHECK(counts.alloc((size_t(NC) + 1) * 4));
+  SYM_CHECK(nruns.alloc(16));
+  {
+    size_t tb = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, tb, keys_sorted, uniq.as<uint64_t>(), counts.as<uint32_t>(),
+                                       nruns.as<uint32_t>(), int(NC), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceRunLengthEncode::Encode(t.p, tb, keys_sorted, uniq.as<uint64_t>(),
+                                                 counts.as<uint32_t>(), nruns.as<uint32_t>(), int(NC), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  uint32_t nblk = 0;
+  SYM_CHECK(cudaMemcpy(&nblk, nruns.p, 4, cudaMemcpyDeviceToHost));
+  h->n_blocks = nblk;
+  SYM_CHECK(h->blk_key.reserve(nblk));
+  SYM_CHECK(cudaMemcpyAsync(h->blk_key.p, uniq.p, size_t(nblk) * 8, cudaMemcpyDeviceToDevice, s));
+  Tmp cptr_sorted;
+  SYM_CHECK(cptr_sorted.alloc((size_t(nblk) + 1) * 4));
+  {
+    // exclusive scan over nblk+1 items (the extra item makes the last entry the total)
+    SYM_CHECK(cudaMemsetAsync(counts.as<uint32_t>() + nblk, 0, 4, s));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), cptr_sorted.as<uint32_t>(), int(nblk + 1), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, counts.as<uint32_t>(), cptr_sorted.as<uint32_t>(),
+                                            int(nblk + 1), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+
+  // ---- 3. block kinds, node ranges, row layout
+  SYM_CHECK(h->blk_full.reserve(nblk));
+  SYM_CHECK(h->blk_off.reserve(2 * size_t(nblk)));
+  block_kind_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, cptr_sorted.as<uint32_t>(), contrib_sorted, h->blk_full.p);
+  node_ptr_kernel<<<div_up(size_t(N) + 1, 256), 256, 0, s>>>(N, nblk, kb, h->blk_key.p, h->node_blk_ptr.p);
+  Tmp node_size;
+  SYM_CHECK(node_size.alloc((size_t(N) + 1) * 8));
+  SYM_CHECK(cudaMemsetAsync(node_size.p, 0, (size_t(N) + 1) * 8, s));
+  node_layout_kernel<<<div_up(N, 256), 256, 0, s>>>(N, h->node_blk_ptr.p, h->blk_full.p, h->blk_off.p,
+                                                    h->node_len.p, node_size.as<int64_t>(), h->d_flag.p);
+  h->launches += 3;
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, node_size.as<int64_t>(), h->node_base.p, int(N + 1), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, node_size.as<int64_t>(), h->node_base.p, int(N + 1), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  int64_t nnz = 0;
+  SYM_CHECK(cudaMemcpy(&nnz, h->node_base.p + N, 8, cudaMemcpyDeviceToHost));
+  h->nnz = nnz;
+  int32_t overflow = 0;
+  SYM_CHECK(cudaMemcpy(&overflow, h->d_flag.p, 4, cudaMemcpyDeviceToHost));
+  if (overflow) return h->fail(FEMGPU_ERR_LIMIT, "a node has 65536 or more entries per row (>= 10923 neighbours)");
+
+  SYM_CHECK(h->col_idx.reserve(size_t(nnz)));
+  SYM_CHECK(h->values.reserve(size_t(nnz)));
+  row_ptr_kernel<<<div_up(size_t(N) + 1, 256), 256, 0, s>>>(N, h->node_base.p, h->node_len.p, h->row_ptr.p);
+  col_idx_kernel<<<div_up(uint64_t(N) * 32, 256), 256, 0, s>>>(N, kb, h->blk_key.p, h->node_blk_ptr.p, h->blk_full.p,
+                                                              h->blk_off.p, h->node_len.p, h->node_base.p,
+                                                              h->col_idx.p);
+  h->launches += 2;
+
+  // ---- 4. slabs and the in-slab thread order
+  const uint32_t quota = kSlabQuota;
+  uint32_t n_slabs = div_up(nblk, quota);
+  h->n_slabs = n_slabs;
+  SYM_CHECK(h->slabs.reserve(n_slabs));
+  slab_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, quota, N, h->node_blk_ptr.p, h->node_base.p,
+                                                   uint32_t(kSlabSmemBytes / 8), h->slabs.p, h->d_flag.p);
+  h->launches++;
+  Tmp okey_a, okey_b, oval_a;
+  SYM_CHECK(okey_a.alloc(size_t(nblk) * 8));
+  SYM_CHECK(okey_b.alloc(size_t(nblk) * 8));
+  SYM_CHECK(oval_a.alloc(size_t(nblk) * 4));
+  SYM_CHECK(h->blk_order.reserve(nblk));
+  order_key_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_key.p, h->node_blk_ptr.p,
+                                                     cptr_sorted.as<uint32_t>(), okey_a.as<uint64_t>(),
+                                                     oval_a.as<uint32_t>());
+  h->launches++;
+  {
+    int sbits = 8;
+    while ((uint64_t(1) << (sbits - 8)) < uint64_t(n_slabs) + 1) ++sbits;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, okey_a.as<uint64_t>(), okey_b.as<uint64_t>(),
+                                    oval_a.as<uint32_t>(), h->blk_order.p, int(nblk), 0, sbits, s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, okey_a.as<uint64_t>(), okey_b.as<uint64_t>(),
+                                              oval_a.as<uint32_t>(), h->blk_order.p, int(nblk), 0, sbits, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  Tmp ocnt;
+  SYM_CHECK(ocnt.alloc((size_t(nblk) + 1) * 4));
+  SYM_CHECK(cudaMemsetAsync(ocnt.as<uint32_t>() + nblk, 0, 4, s));
+  ordered_count_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, h->blk_order.p, cptr_sorted.as<uint32_t>(),
+                                                         ocnt.as<uint32_t>());
+  h->launches++;
+  SYM_CHECK(h->blk_cptr.reserve(size_t(nblk) + 1));
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, ocnt.as<uint32_t>(), h->blk_cptr.p, int(nblk + 1), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, ocnt.as<uint32_t>(), h->blk_cptr.p, int(nblk + 1), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  SYM_CHECK(h->contrib.reserve(size_t(NC)));
+  SYM_CHECK(h->blk_meta.reserve(nblk));
+  ordered_meta_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_order.p, h->blk_key.p,
+                                                        h->node_blk_ptr.p, h->blk_off.p, h->node_len.p,
+                                                        h->node_base.p, h->slabs.p, cptr_sorted.as<uint32_t>(),
+                                                        contrib_sorted, h->blk_cptr.p, h->contrib.p,
+                                                        h->blk_meta.p);
+  h->launches++;
+  SYM_CHECK(cudaGetLastError());
+  SYM_CHECK(cudaStreamSynchronize(s));
+  SYM_CHECK(cudaMemcpy(&overflow, h->d_flag.p, 4, cudaMemcpyDeviceToHost));
+  if (overflow) return h->fail(FEMGPU_ERR_LIMIT, "a slab holds 2^32 or more values");
+
+  if (h->dist.enabled) {
+    int32_t st = dist_symbolic_exchange(h);
+    if (st) return st;
+  }
+  return 0;
+}
+
+int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host) {
+  SYM_CHECK(cudaSetDevice(h->device));
+  const int nn = kNodesPerElem[family], dof = family == FEMGPU_TRUSS ? 3 : 6;
+  const int n = nn * dof;
+  uint32_t nodes[4];
+  for (int c = 0; c < nn; ++c) nodes[c] = h->fh[family].conn[c][index];
+  Tmp d_nodes, d_out;
+  SYM_CHECK(d_nodes.alloc(16));
+  SYM_CHECK(d_out.alloc(size_t(n) * n * 8));
+  SYM_CHECK(cudaMemcpyAsync(d_nodes.p, nodes, 16, cudaMemcpyHostToDevice, h->stream));
+  element_slots_kernel<<<div_up(n * n, 128), 128, 0, h->stream>>>(nn, dof, d_nodes.as<uint32_t>(), h->n_blocks,
+                                                                  h->key_bits, h->blk_key.p, h->blk_off.p,
+                                                                  h->node_len.p, h->node_base.p, d_out.as<int64_t>());
+  h->launches++;
+  SYM_CHECK(cudaGetLastError());
+  SYM_CHECK(cudaMemcpyAsync(out_host, d_out.p, size_t(n) * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  SYM_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals) {
+  SYM_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  int64_t nnz = h->nnz;
+  if (nnz == 0) {
+    if (count) *count = 0;
+    return 0;
+  }
+  if (nnz >= (int64_t(1) << 31)) return h->fail(FEMGPU_ERR_LIMIT, "nonzero compaction supports < 2^31 entries");
+  Tmp flag, pos;
+  SYM_CHECK(flag.alloc((size_t(nnz) + 1) * 8));
+  SYM_CHECK(pos.alloc((size_t(nnz) + 1) * 8));
+  SYM_CHECK(cudaMemsetAsync(flag.as<int64_t>() + nnz, 0, 8, s));
+  nz_flag_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, h->values.p, flag.as<int64_t>());
+  h->launches++;
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.as<int64_t>(), pos.as<int64_t>(), int(nnz + 1), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, flag.as<int64_t>(), pos.as<int64_t>(), int(nnz + 1), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  int64_t nz = 0;
+  SYM_CHECK(cudaMemcpy(&nz, pos.as<int64_t>() + nnz, 8, cudaMemcpyDeviceToHost));
+  if (count) *count = nz;
+  if (!rows || !cols || !vals || nz == 0) return 0;
+  Tmp d_rows, d_cols, d_vals;
+  SYM_CHECK(d_rows.alloc(size_t(nz) * 8));
+  SYM_CHECK(d_cols.alloc(size_t(nz) * 8));
+  SYM_CHECK(d_vals.alloc(size_t(nz) * 8));
+  nz_write_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, h->n_rows, h->values.p, pos.as<int64_t>(), h->row_ptr.p,
+                                                   h->col_idx.p, d_rows.as<int64_t>(), d_cols.as<int64_t>(),
+                                                   d_vals.as<double>());
+  h->launches++;
+  SYM_CHECK(cudaGetLastError());
+  SYM_CHECK(cudaMemcpyAsync(rows, d_rows.p, size_t(nz) * 8, cudaMemcpyDeviceToHost, s));
+  SYM_CHECK(cudaMemcpyAsync(cols, d_cols.p, size_t(nz) * 8, cudaMemcpyDeviceToHost, s));
+  SYM_CHECK(cudaMemcpyAsync(vals, d_vals.p, size_t(nz) * 8, cudaMemcpyDeviceToHost, s));
+  SYM_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // namespace femgpu

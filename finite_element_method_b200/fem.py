@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's `FEM<V>` API for the stiffness-assembly path.
+
+Same method names, argument order and error texts as the Rust crate
+(/root/reference/src/fem/fem.rs:34-65,155-202, methods_for_node_data_handle.rs:66-78,
+methods_for_truss_data_handle.rs:49-128, methods_for_beam_data_handle.rs:49-142,
+methods_for_plate_data_handle.rs:62-217), where `Result<(), String>` becomes "returns None or
+raises FemError(str)". Everything is a thin call into the C ABI of include/femgpu.h; all numerics
+run in libfemgpu.so on the GPU. `V = f64` only.
+
+Differences a caller can observe, by design:
+  * add_* record the element and validate it on the device right away, but the stiffness numbers
+    are produced by `assemble()` (symbolic once, numeric re-runnable) instead of inside each call;
+  * bulk variants (`add_nodes`, `add_trusses`, `add_beams`, `add_plates`) take arrays and are
+    prefix-atomic: everything before the first failing element is kept.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+TRUSS, BEAM, PLATE = 0, 1, 2
+
+
+class FemError(Exception):
+    """`Err(String)` of the reference. `.code` is the FEMGPU_E_* / FEMGPU_ERR_* status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = int(code)
+        self.message = message
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class FEM:
+    """`FEM::create(rel_tol, abs_tol, nodes_number)` — fem.rs:34."""
+
+    def __init__(self, rel_tol: float, abs_tol: float, nodes_number: int, device: int = 0):
+        self._L = _lib.load()
+        self._h = _lib.H()
+        st = self._L.femgpu_create(C.byref(self._h), rel_tol, abs_tol, nodes_number, device)
+        if st:
+            msg = self._L.femgpu_last_error(None).decode()
+            self._h = None
+            raise FemError(st, msg)
+        self.rel_tol, self.abs_tol, self.nodes_number, self.device = rel_tol, abs_tol, nodes_number, device
+
+    @classmethod
+    def create(cls, rel_tol: float, abs_tol: float, nodes_number: int, device: int = 0) -> "FEM":
+        return cls(rel_tol, abs_tol, nodes_number, device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.femgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st:
+            raise FemError(st, self._L.femgpu_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self, nodes_number: int) -> None:
+        """fem.rs:155"""
+        self._check(self._L.femgpu_reset(self._h, nodes_number))
+        self.nodes_number = nodes_number
+
+    def add_node(self, number: int, x: float, y: float, z: float) -> None:
+        """methods_for_node_data_handle.rs:66"""
+        self.add_nodes([number], [x], [y], [z])
+
+    def add_truss(self, number, node_1_number, node_2_number, young_modulus, area, optional_area_2=None) -> None:
+        """methods_for_truss_data_handle.rs:49"""
+        self.add_trusses([number], [node_1_number], [node_2_number], [young_modulus], [area],
+                         None if optional_area_2 is None else [optional_area_2])
+        self.validate()
+
+    def add_beam(self, number, node_1_number, node_2_number, young_modulus, poisson_ratio, area, i11, i22, i12,
+                 it, shear_factor, local_axis_1_direction) -> None:
+        """methods_for_beam_data_handle.rs:49"""
+        ax = np.asarray(local_axis_1_direction, np.float64).reshape(3, 1)
+        self.add_beams([number], [node_1_number], [node_2_number], [young_modulus], [poisson_ratio], [area],
+                       [i11], [i22], [i12], [it], [shear_factor], ax)
+        self.validate()
+
+    def add_plate(self, number, node_1_number, node_2_number, node_3_number, node_4_number, young_modulus,
+                  poisson_ratio, thickness, shear_factor) -> None:
+        """methods_for_plate_data_handle.rs:62"""
+        self.add_plates([number], [node_1_number], [node_2_number], [node_3_number], [node_4_number],
+                        [young_modulus], [poisson_ratio], [thickness], [shear_factor])
+        self.validate()
+
+    def get_truss_rotation_matrix_elements(self, number: int):
+        """fem.rs:171"""
+        return self._rotation(TRUSS, number)
+
+    def get_beam_rotation_matrix_elements(self, number: int):
+        """fem.rs:182"""
+        return self._rotation(BEAM, number)
+
+    def get_plate_rotation_matrix_elements(self, number: int):
+        """fem.rs:193"""
+        return self._rotation(PLATE, number)
+
+    def _rotation(self, family, number):
+        out = np.zeros(9)
+        self._check(self._L.femgpu_rotation_elements(self._h, family, number, _p(out, _lib.dp)))
+        return out
+
+    # ------------------------------------------------------------------ bulk API
+    def add_nodes(self, number, x, y, z) -> None:
+        number, x, y, z = _u32(number), _f64(x), _f64(y), _f64(z)
+        self._check(self._L.femgpu_add_nodes(self._h, len(number), _p(number, _lib.u32p), _p(x, _lib.dp),
+                                             _p(y, _lib.dp), _p(z, _lib.dp)))
+
+    def add_trusses(self, number, node_1, node_2, young_modulus, area, area_2=None) -> None:
+        number, n1, n2 = _u32(number), _u32(node_1), _u32(node_2)
+        E, A = _f64(young_modulus), _f64(area)
+        if area_2 is None:
+            a2p = C.cast(None, _lib.dp)
+        else:
+            A2 = _f64([np.nan if v is None else v for v in area_2] if isinstance(area_2, (list, tuple)) else area_2)
+            a2p = _p(A2, _lib.dp)
+        self._check(self._L.femgpu_add_truss(self._h, len(number), _p(number, _lib.u32p), _p(n1, _lib.u32p),
+                                             _p(n2, _lib.u32p), _p(E, _lib.dp), _p(A, _lib.dp), a2p))
+
+    def add_beams(self, number, node_1, node_2, young_modulus, poisson_ratio, area, i11, i22, i12, it,
+                  shear_factor, local_axis_1) -> None:
+        """local_axis_1: array of shape (3, n) — struct of arrays."""
+        number, n1, n2 = _u32(number), _u32(node_1), _u32(node_2)
+        arrs = [_f64(v) for v in (young_modulus, poisson_ratio, area, i11, i22, i12, it, shear_factor)]
+        ax = _f64(np.asarray(local_axis_1, np.float64).reshape(3, -1))
+        if ax.shape[1] != len(number):
+            raise ValueError("local_axis_1 must have shape (3, n)")
+        self._check(self._L.femgpu_add_beam(self._h, len(number), _p(number, _lib.u32p), _p(n1, _lib.u32p),
+                                            _p(n2, _lib.u32p), *[_p(a, _lib.dp) for a in arrs], _p(ax, _lib.dp)))
+
+    def add_plates(self, number, node_1, node_2, node_3, node_4, young_modulus, poisson_ratio, thickness,
+                   shear_factor) -> None:
+        number = _u32(number)
+        ns = [_u32(v) for v in (node_1, node_2, node_3, node_4)]
+        arrs = [_f64(v) for v in (young_modulus, poisson_ratio, thickness, shear_factor)]
+        self._check(self._L.femgpu_add_plate(self._h, len(number), _p(number, _lib.u32p),
+                                             *[_p(a, _lib.u32p) for a in ns], *[_p(a, _lib.dp) for a in arrs]))
+
+    def validate(self) -> None:
+        """Device-side checks of *::create for everything added since the last call."""
+        self._check(self._L.femgpu_validate(self._h, None, None, None))
+
+    def counts(self):
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self._L.femgpu_counts(self._h, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    # ------------------------------------------------------------------ assembly
+    def symbolic(self):
+        """One-time pattern + gather-map construction. Returns (n_rows, nnz)."""
+        nr, nz = C.c_int64(), C.c_int64()
+        self._check(self._L.femgpu_symbolic(self._h, C.byref(nr), C.byref(nz)))
+        self.n_rows, self.nnz = int(nr.value), int(nz.value)
+        return self.n_rows, self.nnz
+
+    def numeric(self) -> None:
+        """Element matrices + deterministic accumulation into the CSR values (asynchronous)."""
+        self._check(self._L.femgpu_numeric(self._h))
+
+    def synchronize(self) -> None:
+        self._check(self._L.femgpu_synchronize(self._h))
+
+    def assemble(self):
+        nr, nz = C.c_int64(), C.c_int64()
+        self._check(self._L.femgpu_assemble(self._h, C.byref(nr), C.byref(nz)))
+        self.n_rows, self.nnz = int(nr.value), int(nz.value)
+        return self.n_rows, self.nnz
+
+    def csr(self, values_only: bool = False, out=None):
+        """Host copy of the assembled matrix on the structural pattern."""
+        n_rows, nnz = self.symbolic()
+        vals = out if out is not None else np.empty(nnz, np.float64)
+        if values_only:
+            self._check(self._L.femgpu_get_csr(self._h, None, None, _p(vals, _lib.dp)))
+            return vals
+        rp = np.empty(n_rows + 1, np.int64)
+        ci = np.empty(nnz, np.int32)
+        self._check(self._L.femgpu_get_csr(self._h, _p(rp, _lib.i64p), _p(ci, _lib.i32p), _p(vals, _lib.dp)))
+        return rp, ci, vals
+
+    def csr_device(self):
+        """(row_ptr, col_idx, values) device addresses and the owned row range — zero-copy hand-off."""
+        p = [C.c_void_p() for _ in range(3)]
+        rb, re = C.c_int64(), C.c_int64()
+        self._check(self._L.femgpu_get_csr_device(self._h, *[C.byref(x) for x in p], C.byref(rb), C.byref(re)))
+        return tuple(x.value for x in p), (int(rb.value), int(re.value))
+
+    def nonzero_coo(self):
+        """The reference's value-dependent pattern: entries != 0.0, sorted by (row, col)."""
+        cnt = C.c_int64()
+        self._check(self._L.femgpu_get_nonzero_coo(self._h, C.byref(cnt), None, None, None))
+        n = int(cnt.value)
+        r = np.empty(n, np.int64); c = np.empty(n, np.int64); v = np.empty(n, np.float64)
+        if n:
+            self._check(self._L.femgpu_get_nonzero_coo(self._h, C.byref(cnt), _p(r, _lib.i64p), _p(c, _lib.i64p),
+                                                       _p(v, _lib.dp)))
+        return r, c, v
+
+    # ------------------------------------------------------------------ hooks
+    def element_matrix(self, family: int, number: int):
+        n = {TRUSS: 6, BEAM: 12, PLATE: 24}[family]
+        out = np.zeros(n * n)
+        self._check(self._L.femgpu_element_matrix(self._h, family, number, _p(out, _lib.dp)))
+        return out.reshape(n, n)
+
+    def element_slots(self, family: int, number: int):
+        n = {TRUSS: 6, BEAM: 12, PLATE: 24}[family]
+        out = np.zeros(n * n, np.int64)
+        self._check(self._L.femgpu_element_slots(self._h, family, number, _p(out, _lib.i64p)))
+        return out.reshape(n, n)
+
+    def launch_count(self, reset: bool = False) -> int:
+        v = C.c_uint64()
+        self._check(self._L.femgpu_launch_count(self._h, int(reset), C.byref(v)))
+        return int(v.value)
+
+    def last_numeric_ms(self):
+        out = np.zeros(4, np.float32)
+        self._check(self._L.femgpu_last_numeric_ms(self._h, _p(out, _lib.fp)))
+        return [float(x) for x in out]
+
+    def device_bytes(self) -> int:
+        v = C.c_uint64()
+        self._check(self._L.femgpu_device_bytes(self._h, C.byref(v)))
+        return int(v.value)
+
+    def stream(self) -> int:
+        v = C.c_void_p()
+        self._check(self._L.femgpu_stream(self._h, C.byref(v)))
+        return int(v.value or 0)
+
+    # ------------------------------------------------------------------ multi-GPU
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        L = _lib.load()
+        buf = (C.c_uint8 * 128)()
+        st = L.femgpu_dist_unique_id(buf)
+        if st:
+            raise FemError(st, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._L.femgpu_dist_init(self._h, rank, world, buf))
+
+    def dist_set_ownership(self, node_index_begin: int, node_index_end: int) -> None:
+        self._check(self._L.femgpu_dist_set_ownership(self._h, node_index_begin, node_index_end))
+
+    def dist_last_exchange_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._L.femgpu_dist_last_exchange_bytes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    # ------------------------------------------------------------------ convenience
+    def load_mesh(self, mesh: dict) -> None:
+        """Bulk-load a mesh dict from finite_element_method_b200.meshes (node number = index + 1;
+        insertion order plates -> beams -> trusses)."""
+        n = len(mesh["x"])
+        first = mesh.get("node_number_offset", 1)
+        self.add_nodes(np.arange(first, first + n, dtype=np.uint32), mesh["x"], mesh["y"], mesh["z"])
+        num = mesh.get("element_number_offset", 1)
+        pn = np.asarray(mesh["p_n"], np.uint32).reshape(4, -1)
+        if pn.shape[1]:
+            pp = np.asarray(mesh["p_props"], np.float64).reshape(4, -1)
+            self.add_plates(np.arange(num, num + pn.shape[1], dtype=np.uint32), pn[0] + first, pn[1] + first,
+                            pn[2] + first, pn[3] + first, pp[0], pp[1], pp[2], pp[3])
+        nb = len(mesh["b_n1"])
+        if nb:
+            bp = np.asarray(mesh["b_props"], np.float64).reshape(8, -1)
+            self.add_beams(np.arange(num, num + nb, dtype=np.uint32), np.asarray(mesh["b_n1"], np.uint32) + first,
+                           np.asarray(mesh["b_n2"], np.uint32) + first, *[bp[i] for i in range(8)], mesh["b_axis"])
+        nt = len(mesh["t_n1"])
+        if nt:
+            self.add_trusses(np.arange(num, num + nt, dtype=np.uint32), np.asarray(mesh["t_n1"], np.uint32) + first,
+                             np.asarray(mesh["t_n2"], np.uint32) + first, mesh["t_E"], mesh["t_A"], mesh.get("t_A2"))

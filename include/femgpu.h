@@ -1,0 +1,218 @@
+/*
+ * femgpu — C ABI of the B200-native structural-FEM stiffness assembly path.
+ *
+ * Drop-in boundary for ONE hot path of RomanShushakov/finite_element_method v0.9.12: per-element
+ * local stiffness (truss / beam / plate) + scatter-assembly into the global FP64 stiffness matrix.
+ * The reference has no FFI of its own; the seam is the inherent-method API of `FEM<V>`. Every entry
+ * point below cites the reference item it replaces (paths relative to /root/reference/src/fem/).
+ * A Rust host binds these with an `extern "C"` block; plain pointers and
+ * sizes only, no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns int32: 0 = ok, >0 = reference-style validation error (FEMGPU_E_*),
+ *     <0 = CUDA / NCCL / usage failure. femgpu_last_error() gives the text; for validation errors
+ *     it is the exact `Err(String)` the reference would return.
+ *   - host arrays are caller-owned and copied during the call; the handle owns all device memory.
+ *   - node / element *numbers* are user labels (u32); node *indices* are 0-based insertion order
+ *     (methods_for_node_data_handle.rs:66-78); global row = 6*index + dof (structs/node.rs:8).
+ *   - batched adds are "prefix-atomic": elements before the first failing one are accepted, the
+ *     failing one and everything after it in the batch are not — what a sequential `add_*?` loop
+ *     over the reference would leave behind.
+ *   - one handle <-> one `FEM` <-> one GPU of one process; not thread-safe (the reference is not
+ *     either). Multi-GPU = one process per GPU, each with a handle, joined by femgpu_dist_init().
+ *   - FP64 only. There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef FEMGPU_H
+#define FEMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct femgpu_handle femgpu_t;
+
+/* pass as `device` to femgpu_create for a staging-only handle: host bookkeeping (numbering,
+ * duplicate checks, error texts) works, every call that needs the GPU returns
+ * FEMGPU_ERR_NO_DEVICE. There is no CPU compute path behind it. */
+#define FEMGPU_DEVICE_NONE (-1)
+
+/* element families */
+#define FEMGPU_TRUSS 0
+#define FEMGPU_BEAM 1
+#define FEMGPU_PLATE 2
+
+/* validation error codes (>0). Texts follow the reference's compose_error_message() functions. */
+enum {
+  FEMGPU_OK = 0,
+  /* methods_for_node_data_handle.rs:16-32 */
+  FEMGPU_E_NODE_NUMBER_EXISTS = 1,
+  FEMGPU_E_NODE_NOT_EXIST = 2,
+  FEMGPU_E_NODE_INDEX_EXISTS = 3,
+  FEMGPU_E_NODE_COORDINATES_EXIST = 4,
+  FEMGPU_E_NODE_LIMIT = 5,
+  /* methods_for_{truss,beam,plate}_data_handle.rs error enums */
+  FEMGPU_E_ELEMENT_NUMBER_EXISTS = 10,
+  FEMGPU_E_ELEMENT_SAME_NODES = 11,
+  FEMGPU_E_ELEMENT_NOT_EXIST = 12,
+  /* structs/truss.rs:23-42, structs/beam.rs:26-61, structs/plate.rs:27-56 */
+  FEMGPU_E_YOUNG_MODULUS = 20,
+  FEMGPU_E_POISSON_RATIO = 21,
+  FEMGPU_E_AREA = 22,
+  FEMGPU_E_AREA2 = 23,
+  FEMGPU_E_I11 = 24,
+  FEMGPU_E_I22 = 25,
+  FEMGPU_E_IT = 26,
+  FEMGPU_E_SHEAR_FACTOR = 27,
+  FEMGPU_E_PARALLEL_LOCAL_AXIS = 28,
+  FEMGPU_E_THICKNESS = 29,
+  FEMGPU_E_NODES_ON_LINE = 30,
+  FEMGPU_E_NODES_NOT_ON_PLANE = 31,
+  FEMGPU_E_NOT_CONVEX = 32
+};
+
+/* failures (<0) */
+enum {
+  FEMGPU_ERR_CUDA = -1,
+  FEMGPU_ERR_USAGE = -2,
+  FEMGPU_ERR_NCCL = -3,
+  FEMGPU_ERR_LIMIT = -4,
+  FEMGPU_ERR_NO_DEVICE = -5
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+
+/* FEM::create(rel_tol, abs_tol, nodes_number)                                   fem.rs:34-65
+ * `device` is the CUDA ordinal this handle computes on. The matrix order is fixed at
+ * 6*nodes_number (fem.rs:37) whether or not that many nodes are ever added. */
+int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t nodes_number,
+                      int32_t device);
+/* FEM::reset(nodes_number): drops nodes, elements, pattern and values            fem.rs:155-169 */
+int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number);
+void femgpu_destroy(femgpu_t* h);
+/* text of the last non-zero status returned on this handle (NULL handle: creation errors) */
+const char* femgpu_last_error(const femgpu_t* h);
+
+/* ---- model definition --------------------------------------------------------------------- */
+
+/* n x FEM::add_node(number, x, y, z), in array order     methods_for_node_data_handle.rs:66-78
+ * Checks, per node and in this order: nodes_number limit, duplicate number, duplicate
+ * coordinates (:42-64). The reference scans all nodes per call; here it is a hash lookup. */
+int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const double* x,
+                         const double* y, const double* z);
+
+/* n x FEM::add_truss(number, node_1, node_2, young_modulus, area, optional_area_2)
+ *                                                    methods_for_truss_data_handle.rs:49-128
+ * area_2 may be NULL (all None); a NaN entry means None for that element. */
+int32_t femgpu_add_truss(femgpu_t* h, size_t n, const uint32_t* number, const uint32_t* node_1,
+                         const uint32_t* node_2, const double* young_modulus, const double* area,
+                         const double* area_2);
+
+/* n x FEM::add_beam(number, node_1, node_2, young_modulus, poisson_ratio, area, i11, i22, i12, it,
+ *                   shear_factor, local_axis_1_direction)   methods_for_beam_data_handle.rs:49-142
+ * local_axis_1 is struct-of-arrays: [3][n] (all x, then all y, then all z). */
+int32_t femgpu_add_beam(femgpu_t* h, size_t n, const uint32_t* number, const uint32_t* node_1,
+                        const uint32_t* node_2, const double* young_modulus,
+                        const double* poisson_ratio, const double* area, const double* i11,
+                        const double* i22, const double* i12, const double* it,
+                        const double* shear_factor, const double* local_axis_1);
+
+/* n x FEM::add_plate(number, node_1..4, young_modulus, poisson_ratio, thickness, shear_factor)
+ *                                                    methods_for_plate_data_handle.rs:62-217 */
+int32_t femgpu_add_plate(femgpu_t* h, size_t n, const uint32_t* number, const uint32_t* node_1,
+                         const uint32_t* node_2, const uint32_t* node_3, const uint32_t* node_4,
+                         const double* young_modulus, const double* poisson_ratio,
+                         const double* thickness, const double* shear_factor);
+
+/* Runs the element-level checks of Truss/Beam/Plate::create (structs/truss.rs:44-64,
+ * structs/beam.rs:63-117, structs/plate.rs:58-158) on the device for every element added since the
+ * last validation. On failure the offending element and everything added after it are rolled
+ * back (prefix semantics) and the reference's message is returned. femgpu_symbolic() calls this
+ * implicitly; the single-element host mirrors call it after each add so errors surface eagerly.
+ * The three out-pointers may be NULL. */
+int32_t femgpu_validate(femgpu_t* h, int32_t* family, uint32_t* number, int32_t* code);
+
+/* counts of accepted entities */
+int32_t femgpu_counts(const femgpu_t* h, uint64_t* nodes, uint64_t* truss, uint64_t* beam,
+                      uint64_t* plate);
+
+/* ---- assembly ----------------------------------------------------------------------------- */
+
+/* One-time symbolic pass: DOF numbering (6*index+dof), node-pair block list, CSR row_ptr/col_idx
+ * on the structural pattern (3x3 per truss-only node pair, 6x6 per beam/plate pair, union when
+ * families share a pair), and the CSR-slot gather map used by the numeric pass. Replaces the
+ * position-keyed `SquareMatrix` of fem.rs:17,37 and the start_positions arithmetic of
+ * methods_for_truss_data_handle.rs:83-109 / ..beam..:96-123 / ..plate..:113-132. */
+int32_t femgpu_symbolic(femgpu_t* h, int64_t* n_rows, int64_t* nnz);
+
+/* Numeric pass (re-runnable): rotation matrices, local stiffness, R^T k R and deterministic
+ * accumulation into the CSR values — what add_truss/add_beam/add_plate do per element
+ * (methods_for_truss_data_handle.rs:64-123, ..beam..:77-137, ..plate..:91-212). Asynchronous on
+ * the handle's stream; femgpu_synchronize() or any copy-out waits for it. */
+int32_t femgpu_numeric(femgpu_t* h);
+int32_t femgpu_synchronize(femgpu_t* h);
+
+/* convenience: validate + symbolic (if stale) + numeric + synchronize */
+int32_t femgpu_assemble(femgpu_t* h, int64_t* n_rows, int64_t* nnz);
+
+/* ---- results ------------------------------------------------------------------------------ */
+
+/* Host copy-out of the CSR on the structural pattern; any pointer may be NULL to skip it.
+ * Read-side contract of the reference (methods_for_separate_stiffness_matrix.rs:223,277-278):
+ * an unordered set of (row, col, value) where an absent entry and a stored 0.0 are equivalent. */
+int32_t femgpu_get_csr(femgpu_t* h, int64_t* row_ptr, int32_t* col_idx, double* values);
+
+/* Device pointers (valid until the next symbolic pass / reset / destroy) for a downstream GPU
+ * consumer. Rows [row_begin, row_end) are the ones this handle owns (all rows on one GPU). */
+int32_t femgpu_get_csr_device(femgpu_t* h, const int64_t** row_ptr, const int32_t** col_idx,
+                              const double** values, int64_t* row_begin, int64_t* row_end);
+
+/* Compacts to the reference's value-dependent pattern (entries that are != 0.0) as sorted COO.
+ * Call with NULL arrays to get the count. */
+int32_t femgpu_get_nonzero_coo(femgpu_t* h, int64_t* count, int64_t* rows, int64_t* cols,
+                               double* values);
+
+/* FEM::get_{truss,beam,plate}_rotation_matrix_elements(number)                 fem.rs:171-202 */
+int32_t femgpu_rotation_elements(femgpu_t* h, int32_t family, uint32_t number, double out[9]);
+
+/* Test hook: the transformed element matrix (R^T k R) of one element, row-major,
+ * 36 | 144 | 576 doubles — `transformed_local_stiffness_matrix` in add_truss/add_beam/add_plate. */
+int32_t femgpu_element_matrix(femgpu_t* h, int32_t family, uint32_t number, double* out);
+
+/* element -> CSR-slot scatter map of one element: for every (local row, local col) of its
+ * transformed matrix the index into `values`, or -1 where the structural pattern has no slot
+ * (never happens for entries the reference would store). 36 | 144 | 576 int64. */
+int32_t femgpu_element_slots(femgpu_t* h, int32_t family, uint32_t number, int64_t* out);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+
+/* kernels launched by this handle since creation / since the last call with reset != 0 */
+int32_t femgpu_launch_count(femgpu_t* h, int32_t reset, uint64_t* launches);
+/* device milliseconds of the last femgpu_numeric() (CUDA events on the handle's stream), split as
+ * [0] total, [1] element-record kernels, [2] assembly kernel, [3] interface exchange */
+int32_t femgpu_last_numeric_ms(femgpu_t* h, float out[4]);
+/* bytes of device memory held by the handle */
+int32_t femgpu_device_bytes(const femgpu_t* h, uint64_t* bytes);
+/* the CUDA stream handle (cudaStream_t) work is issued on, for callers that time with events */
+int32_t femgpu_stream(femgpu_t* h, void** stream);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------------- */
+
+/* Joins `world` handles (one per process/GPU) into one assembly. `nccl_unique_id` is the 128-byte
+ * ncclUniqueId created by rank 0 (femgpu_dist_unique_id) and broadcast by the host. Must be called
+ * before femgpu_symbolic(). Rank g owns the contiguous node-index range given by
+ * femgpu_dist_set_ownership(); each rank is given every node but only the elements whose
+ * lowest-index node it owns. Contributions to rows owned by another rank are summed locally,
+ * exchanged with ncclSend/ncclRecv and added by the owner in (source rank, slot) order. */
+int32_t femgpu_dist_unique_id(uint8_t out[128]);
+int32_t femgpu_dist_init(femgpu_t* h, int32_t rank, int32_t world, const uint8_t nccl_unique_id[128]);
+int32_t femgpu_dist_set_ownership(femgpu_t* h, uint32_t node_index_begin, uint32_t node_index_end);
+/* interface traffic of the last numeric pass: bytes sent / received by this rank */
+int32_t femgpu_dist_last_exchange_bytes(femgpu_t* h, uint64_t* sent, uint64_t* received);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMGPU_H */
