@@ -434,7 +434,8 @@ int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t n
     delete h;
     return FEMGPU_ERR_CUDA;
   }
-  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  for (auto& q : h->ev)
+    for (auto& ev : q) cudaEventCreate(&ev);
   *out = h;
   return 0;
 }
@@ -485,8 +486,9 @@ void femgpu_destroy(femgpu_t* h) {
   cudaStreamSynchronize(h->stream);
   dist_destroy(h);
   free_device(h);
-  for (auto& ev : h->ev)
-    if (ev) cudaEventDestroy(ev);
+  for (auto& q : h->ev)
+    for (auto& ev : q)
+      if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -605,14 +607,16 @@ int32_t femgpu_numeric(femgpu_t* h) {
   if (h->device < 0) return no_device(h);
   if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "femgpu_numeric before femgpu_symbolic");
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
-  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[0], h->stream));
+  cudaEvent_t* ev = h->ev[h->n_numeric % Handle::kEvRing];
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[0], h->stream));
   int32_t st = run_prep(h, /*validate_only=*/false);
   if (st) return st;
-  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[1], h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
   if ((st = run_assembly(h))) return st;
-  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[2], h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[2], h->stream));
   if (h->dist.enabled && (st = dist_numeric_exchange(h))) return st;
-  FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ev[3], h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[3], h->stream));
+  h->n_numeric++;
   return 0;
 }
 
@@ -728,12 +732,21 @@ int32_t femgpu_launch_count(femgpu_t* h, int32_t reset, uint64_t* launches) {
 int32_t femgpu_last_numeric_ms(femgpu_t* h, float out[4]) {
   if (!h || !out) return FEMGPU_ERR_USAGE;
   if (h->device < 0) return no_device(h);
+  return femgpu_numeric_ms_history(h, 0, out);
+}
+
+int32_t femgpu_numeric_ms_history(femgpu_t* h, uint32_t passes_back, float out[4]) {
+  if (!h || !out) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (passes_back >= Handle::kEvRing || passes_back >= h->n_numeric)
+    return h->fail(FEMGPU_ERR_USAGE, "no such numeric pass in the timing history");
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
-  FEMGPU_CUDA_CHECK(h, cudaEventSynchronize(h->ev[3]));
-  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[0], h->ev[0], h->ev[3]));
-  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[1], h->ev[0], h->ev[1]));
-  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[2], h->ev[1], h->ev[2]));
-  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[3], h->ev[2], h->ev[3]));
+  cudaEvent_t* ev = h->ev[(h->n_numeric - 1 - passes_back) % Handle::kEvRing];
+  FEMGPU_CUDA_CHECK(h, cudaEventSynchronize(ev[3]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[0], ev[0], ev[3]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[1], ev[0], ev[1]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[2], ev[1], ev[2]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[3], ev[2], ev[3]));
   return 0;
 }
 

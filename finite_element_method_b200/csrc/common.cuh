@@ -202,7 +202,9 @@ struct Handle {
   uint32_t nodes_number = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kEvRing = 64;  // event quadruples of the last kEvRing numeric passes
+  cudaEvent_t ev[kEvRing][4] = {};
+  uint64_t n_numeric = 0;  // numeric passes issued
   mutable Status last;
   size_t dev_bytes = 0;
   uint64_t launches = 0;

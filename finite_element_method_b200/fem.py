@@ -244,6 +244,11 @@ class FEM:
         self._check(self._L.femgpu_last_numeric_ms(self._h, _p(out, _lib.fp)))
         return [float(x) for x in out]
 
+    def numeric_ms_history(self, passes_back: int = 0):
+        out = np.zeros(4, np.float32)
+        self._check(self._L.femgpu_numeric_ms_history(self._h, passes_back, _p(out, _lib.fp)))
+        return [float(x) for x in out]
+
     def device_bytes(self) -> int:
         v = C.c_uint64()
         self._check(self._L.femgpu_device_bytes(self._h, C.byref(v)))

@@ -193,6 +193,9 @@ int32_t femgpu_launch_count(femgpu_t* h, int32_t reset, uint64_t* launches);
 /* device milliseconds of the last femgpu_numeric() (CUDA events on the handle's stream), split as
  * [0] total, [1] element-record kernels, [2] assembly kernel, [3] interface exchange */
 int32_t femgpu_last_numeric_ms(femgpu_t* h, float out[4]);
+/* same for the pass issued `passes_back` passes before the last one (0 = last; the handle keeps
+ * the events of the most recent 64 passes), so a timed loop needs no sync between passes */
+int32_t femgpu_numeric_ms_history(femgpu_t* h, uint32_t passes_back, float out[4]);
 /* bytes of device memory held by the handle */
 int32_t femgpu_device_bytes(const femgpu_t* h, uint64_t* bytes);
 /* the CUDA stream handle (cudaStream_t) work is issued on, for callers that time with events */

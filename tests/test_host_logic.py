@@ -1,0 +1,109 @@
+"""Host-side bookkeeping of the C ABI on a staging-only handle (no GPU): numbering, duplicate
+checks, prefix semantics and the reference's error texts
+(methods_for_node_data_handle.rs:16-64, methods_for_truss_data_handle.rs:11-62 and siblings)."""
+import numpy as np
+import pytest
+
+from finite_element_method_b200 import FEM, FemError
+
+
+def staged(n=16):
+    return FEM(1e-4, 1e-12, n, device=-1)
+
+
+def raises(code, text, fn, *a, **k):
+    with pytest.raises(FemError) as e:
+        fn(*a, **k)
+    assert e.value.code == code, (e.value.code, str(e.value))
+    assert str(e.value) == text, str(e.value)
+
+
+def test_node_errors_match_reference_texts():
+    f = staged(3)
+    f.add_node(1, 0.0, 0.0, 0.0)
+    f.add_node(2, 30.0, 0.0, 0.0)
+    raises(1, "Node with number 1 already exists!", f.add_node, 1, 5.0, 0.0, 0.0)
+    raises(4, "Node with coordinates x: 30.0, y: 0.0, z: 0.0 already exists!", f.add_node, 3, 30.0, 0.0, 0.0)
+    raises(4, "Node with coordinates x: -0.0, y: 0.0, z: 0.0 already exists!", f.add_node, 3, -0.0, 0.0, 0.0)  # -0.0 == 0.0
+    f.add_node(7, 1.5, -2e-7, 1e20)
+    raises(5, "Nodes number could not be greater than 3!", f.add_node, 9, 1.0, 1.0, 1.0)
+    assert f.counts() == (3, 0, 0, 0)
+
+
+def test_rust_debug_float_formatting():
+    f = staged(8)
+    for i, (v, s) in enumerate([(0.1, "0.1"), (1e16, "1e16"), (123456.0, "123456.0"), (1.5e-5, "1.5e-5"),
+                                (1e-4, "0.0001"), (-2.5, "-2.5"), (1 / 3, "0.3333333333333333")]):
+        f.add_node(10 + i, v, float(i), 0.0)
+        raises(4, f"Node with coordinates x: {s}, y: {float(i)}, z: 0.0 already exists!", f.add_node, 99, v, float(i), 0.0)
+
+
+def test_truss_errors_and_order_of_checks():
+    f = staged()
+    f.add_nodes([1, 2, 3], [0, 1, 2], [0, 0, 0], [0, 0, 0])
+    f.add_trusses([1], [1], [2], [1e6], [2.0])
+    raises(2, "Node with number 9 does not exist!", f.add_trusses, [1], [9], [8], [1e6], [2.0])      # node 1 first
+    raises(2, "Node with number 8 does not exist!", f.add_trusses, [1], [1], [8], [1e6], [2.0])
+    raises(10, "Truss element with number 1 already exists!", f.add_trusses, [1], [2], [3], [1e6], [2.0])
+    raises(11, "Truss element with node number 2 and 1 already exists!", f.add_trusses, [2], [2], [1], [1e6], [2.0])
+    raises(20, "Young's modulus -1.0 is less or equal to zero!", f.add_trusses, [2], [2], [3], [-1.0], [2.0])
+    raises(22, "Area 0.0 is less or equal to zero!", f.add_trusses, [2], [2], [3], [1.0], [0.0])
+    raises(23, "Area2 -0.5 is less or equal to zero!", f.add_trusses, [2], [2], [3], [1.0], [1.0], [-0.5])
+    # a failed add leaves nothing behind: the same number / pair can be used afterwards
+    f.add_trusses([2], [2], [3], [1.0], [1.0], [np.nan])
+    assert f.counts() == (3, 2, 0, 0)
+
+
+def test_beam_and_plate_errors_keep_reference_quirks():
+    f = staged()
+    f.add_nodes([1, 2, 3, 4, 5], [0, 1, 1, 0, 5], [0, 0, 1, 1, 5], [0, 0, 0, 0, 0])
+    ax = np.array([[0.0], [0.0], [1.0]])
+    ok = dict(young_modulus=[2e11], poisson_ratio=[0.3], area=[1e-2], i11=[8e-6], i22=[4e-6], i12=[0.0],
+              it=[1e-5], shear_factor=[5 / 6], local_axis_1=ax)
+    f.add_beams([1], [1], [2], **ok)
+    raises(10, "Beam element with number 1 already exists!", f.add_beams, [1], [2], [3], **ok)
+    raises(11, "Beam element with node number 2 and 1 already exists!", f.add_beams, [2], [2], [1], **ok)
+    # beam.rs:86-87 reports young_modulus inside the Poisson message
+    raises(21, "Poisson's ratio 200000000000.0 is less or equal to zero!", f.add_beams, [2], [2], [3],
+           **{**ok, "poisson_ratio": [0.0]})
+    raises(24, "I11 -1.0 is less or equal to zero!", f.add_beams, [2], [2], [3], **{**ok, "i11": [-1.0]})
+    raises(26, "It 0.0 is less or equal to zero!", f.add_beams, [2], [2], [3], **{**ok, "it": [0.0]})
+    f.add_plates([1], [3], [4], [1], [2], [2e11], [0.3], [0.01], [5 / 6])
+    raises(10, "Plate element with number 1 already exists!", f.add_plates, [1], [3], [4], [1], [5], [2e11], [0.3], [0.01], [5 / 6])
+    raises(11, "Plate element with nodes numbers [1, 2, 3, 4] already exists!", f.add_plates, [2], [1], [2], [3], [4],
+           [2e11], [0.3], [0.01], [5 / 6])
+    # plate.rs:83-84 reports young_modulus inside the Thickness message
+    raises(29, "Thickness 200000000000.0 is less or equal to zero!", f.add_plates, [2], [3], [4], [1], [5],
+           [2e11], [0.3], [0.0], [5 / 6])
+    assert f.counts() == (5, 0, 1, 1)
+
+
+def test_batch_is_prefix_atomic():
+    f = staged()
+    f.add_nodes(np.arange(1, 7), np.arange(6.0), np.zeros(6), np.zeros(6))
+    raises(11, "Truss element with node number 2 and 1 already exists!", f.add_trusses,
+           [1, 2, 3, 4], [1, 2, 2, 3], [2, 3, 1, 4], [1.0] * 4, [1.0] * 4)
+    assert f.counts() == (6, 2, 0, 0)          # elements 1 and 2 kept, 3 (duplicate) and 4 dropped
+    f.add_trusses([3, 4], [3, 4], [4, 5], [1.0, 1.0], [1.0, 1.0])
+    assert f.counts() == (6, 4, 0, 0)
+
+
+def test_reset_drops_everything():
+    f = staged(2)
+    f.add_nodes([1, 2], [0, 1], [0, 0], [0, 0])
+    f.add_trusses([1], [1], [2], [1.0], [1.0])
+    f.reset(4)
+    assert f.counts() == (0, 0, 0, 0)
+    f.add_nodes([1, 2, 3, 4], [0, 1, 2, 3], [0, 0, 0, 0], [0, 0, 0, 0])
+    f.add_trusses([1], [1], [2], [1.0], [1.0])
+    assert f.counts() == (4, 1, 0, 0)
+
+
+def test_compute_calls_fail_loudly_without_device():
+    f = staged(2)
+    f.add_nodes([1, 2], [0, 1], [0, 0], [0, 0])
+    f.add_trusses([1], [1], [2], [1.0], [1.0])
+    for fn in (f.symbolic, f.numeric, f.assemble, f.validate, lambda: f.get_truss_rotation_matrix_elements(1)):
+        with pytest.raises(FemError) as e:
+            fn()
+        assert e.value.code == -5 and "no CPU fallback" in str(e.value)

@@ -1,0 +1,49 @@
+"""The multi-core "fast" CPU baseline agrees with the faithful restatement (CPU only)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from finite_element_method_b200 import meshes
+from oracle import oracle as O
+
+CASES = [
+    lambda: meshes.reference_truss_model(),
+    lambda: meshes.truss_cube(3),
+    lambda: meshes.truss_lattice(6, 10 ** 9, jitter=True),
+    lambda: meshes.beam_frame(5, 10 ** 9),
+    lambda: meshes.beam_frame(5, 10 ** 9, jitter=True),
+    lambda: meshes.plate_grid(6, 5, "flat"),
+    lambda: meshes.plate_grid(6, 5, "jitter"),
+    lambda: meshes.plate_grid(6, 5, "x0"),
+    lambda: meshes.mixed_structure(6, 4),
+]
+
+
+@pytest.mark.parametrize("make", CASES)
+def test_fast_matches_faithful(make):
+    mesh = make()
+    n = 6 * len(mesh["x"])
+    r, c, v = O.faithful_coo(mesh)
+    A = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+    out = O.fast_assemble(mesh, n_threads=2, want_coo=True)
+    fr, fc, fv = out["coo"]
+    B = sp.coo_matrix((fv, (fr, fc)), shape=(n, n)).tocsr()
+    assert out["nnz"] == meshes.algorithmic_bytes(mesh)["nnz"]
+    assert abs(A - B).max() <= 1e-14 * abs(A).max()
+
+
+def test_structural_nnz_closed_form():
+    m = meshes.plate_grid(7, 5)
+    assert meshes.algorithmic_bytes(m)["nnz"] == meshes.grid_nnz_fast(7, 5)
+    m = meshes.mixed_structure(8, 6)
+    assert meshes.algorithmic_bytes(m)["nnz"] == meshes.grid_nnz_fast(8, 6)
+    assert meshes.grid_nnz_fast(2000, 2000) == 1_296_432_036
+
+
+def test_partition_owns_every_element_once():
+    m = meshes.mixed_structure(10, 12)
+    for world in (2, 3, 4):
+        parts = meshes.partition_rows(m, world, 11)
+        assert parts[0][0] == 0 and parts[-1][1] == len(m["x"])
+        tot = sum(meshes.n_elements(meshes.local_part(m, b, e)) for b, e in parts)
+        assert tot == meshes.n_elements(m)
