@@ -170,15 +170,27 @@ struct BlockMeta {
   uint32_t seg0;     // slab-relative offset of the block's first entry in dof rows 0..2
   uint32_t seg3;     // same for dof rows 3..5, 0xFFFFFFFF for a 3x3 (truss-only) block
   uint32_t strides;  // row length of rows 0..2 (low 16 bits) | rows 3..5 (high 16 bits)
-  uint32_t cptr;     // first contribution (thread order); count = next block's cptr - cptr
+  uint32_t count;    // contributions of this block (consecutive in contrib[], thread order)
+};
+
+// One thread's share of a slab: a run of consecutive thread-ordered blocks (and therefore of
+// consecutive contributions). Stored as a dense [n_slabs][kAsmThreads] table so a thread can fetch
+// its item without first reading the slab descriptor.
+struct WorkItem {
+  uint32_t blk_begin;  // first block (thread order)
+  uint32_t blk_count;  // 0 = idle thread
+  uint32_t c_begin;    // first contribution
+  uint32_t c_count;
 };
 
 struct SlabDesc {
-  int64_t val_base;    // first CSR value of the slab
-  uint32_t val_count;  // values in the slab
-  uint32_t blk_begin;  // first block (thread order)
+  int64_t val_base;     // first CSR value of the slab
+  uint32_t val_count;   // values in the slab
+  uint32_t blk_begin;   // first block (thread order)
   uint32_t blk_count;
-  uint32_t flags;      // bit 0: too large for shared memory -> write straight to global
+  uint32_t flags;       // bit 0: too large for shared memory -> write straight to global
+  uint32_t el_begin;    // the slab's distinct elements (elist[]): their records are staged in
+  uint32_t el_count;    // shared memory once per CTA; contrib[] codes index into this list
 };
 
 struct DistState {
@@ -238,6 +250,11 @@ struct Handle {
   DevBuf<uint32_t> contrib;        // family<<30 | pair<<26 | element, thread order
   DevBuf<BlockMeta> blk_meta;      // thread order
   DevBuf<uint32_t> blk_order;      // thread position -> sorted block id
+  DevBuf<WorkItem> items;          // [n_slabs][kAsmThreads] balanced per-thread work lists
+  DevBuf<uint32_t> elist;          // [n_slabs][kElistStride]: family<<26 | element, 0xFFFFFFFF = empty;
+                                   // (compact list when a slab overflows the table: unstaged path)
+  DevBuf<uint32_t> elist_compact;
+  uint32_t slab_smem_bytes = 0;    // dynamic shared memory the assembly kernel is launched with
   DevBuf<uint32_t> node_blk_ptr;   // [n_nodes_total+1]
   DevBuf<int64_t> node_base;       // [n_nodes_total+1] first value of the node's rows
   DevBuf<uint32_t> node_len;       // [2*n_nodes_total] len03, len35
@@ -259,7 +276,7 @@ struct Handle {
       for (auto& p : f.props) tie(p);
       tie(f.cbase); tie(f.rec); tie(f.mat); tie(f.err);
     }
-    tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order);
+    tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
     tie(col_idx); tie(values); tie(scratch); tie(d_flag);
     tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_slot); tie(dist.recv_meta);
@@ -287,10 +304,14 @@ int32_t dist_symbolic_exchange(Handle* h);               // dist.cu
 int32_t dist_numeric_exchange(Handle* h);                // dist.cu
 void dist_destroy(Handle* h);                            // dist.cu
 
-constexpr int kAsmThreads = 128;       // threads per assembly CTA (one node-pair block each)
-constexpr int kSlabQuota = 112;        // node-pair blocks a slab aims for (< kAsmThreads so a
-                                       // trailing node rarely spills into a second round)
-constexpr int kSlabSmemBytes = 72 * 1024;  // staging capacity; larger slabs write straight to HBM
+constexpr int kAsmThreads = 32;            // threads per assembly CTA: one warp, no block barriers
+constexpr int kSlabQuota = 72;             // node-pair blocks a slab aims for (8 plate-grid nodes)
+constexpr int kSlabSmemBytes = 48 * 1024;  // staging capacity (slab image + element records)
+constexpr int kElistStride = 64;           // element slots per slab in the dense elist table; a slab
+                                           // touching more elements takes the unstaged path
+constexpr int kRecStride = 20;             // doubles per staged element record (plate: 16 + 4)
+// relative cost of one contribution, used to balance the per-thread work lists
+constexpr uint32_t kCostTruss = 1, kCostBeam = 8, kCostPlate = 16;
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return uint32_t((a + b - 1) / b); }
 

@@ -26,8 +26,10 @@ namespace {
 struct AsmArgs {
   const SlabDesc* slabs;
   const BlockMeta* meta;
-  const uint32_t* cptr;
   const uint32_t* contrib;
+  const WorkItem* items;
+  const uint32_t* elist;          // dense [n_slabs][kElistStride]
+  const uint32_t* elist_compact;  // compact lists (unstaged fallback only)
   const double4* truss_rec;
   const double* beam_rec;
   const double* plate_rec;
@@ -36,100 +38,211 @@ struct AsmArgs {
   uint32_t n_slabs;
 };
 
-__device__ __forceinline__ void load_rec16(const double* __restrict__ base, uint32_t e, double r[16]) {
-  const double2* p = reinterpret_cast<const double2*>(base + size_t(e) * 16);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    double2 v = __ldg(p + i);
-    r[2 * i] = v.x;
-    r[2 * i + 1] = v.y;
-  }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 
-__device__ __forceinline__ void add_contribution(const AsmArgs& A, uint32_t code, double acc[36]) {
-  const uint32_t family = code >> 30, pair = (code >> 26) & 15u, e = code & 0x03FFFFFFu;
+// global address of 16-byte chunk `chunk` of an element's record (nullptr past its end):
+// plate = 8 chunks of the geometry record + 2 of the material record, beam = 8, truss = 2
+__device__ __forceinline__ const void* record_chunk(const AsmArgs& A, uint32_t fe, uint32_t chunk) {
+  const uint32_t family = fe >> 26, e = fe & 0x03FFFFFFu;
   if (family == FEMGPU_PLATE) {
-    double rec[16], mat[4];
-    load_rec16(A.plate_rec, e, rec);
-    const double2* mp = reinterpret_cast<const double2*>(A.plate_mat + size_t(e) * 4);
-    double2 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-    mat[0] = m0.x; mat[1] = m0.y; mat[2] = m1.x; mat[3] = m1.y;
-    plate_block(rec, mat, int(pair >> 2), int(pair & 3u), acc);
+    if (chunk < 8) return A.plate_rec + size_t(e) * 16 + chunk * 2;
+    return A.plate_mat + size_t(e) * 4 + (chunk - 8) * 2;
+  }
+  if (family == FEMGPU_BEAM) return chunk < 8 ? A.beam_rec + size_t(e) * 16 + chunk * 2 : nullptr;
+  return chunk < 2 ? reinterpret_cast<const double*>(A.truss_rec + e) + chunk * 2 : nullptr;
+}
+
+// evaluate one contribution from a record of kRecStride doubles (shared memory, or registers
+// filled from global in the unstaged fallback)
+__device__ __forceinline__ void add_contribution(const double* __restrict__ rec, uint32_t code,
+                                                 double acc[36]) {
+  const uint32_t family = code >> 30, pair = (code >> 26) & 15u;
+  if (family == FEMGPU_PLATE) {
+    plate_block(rec, rec + 16, int(pair >> 2), int(pair & 3u), acc);
   } else if (family == FEMGPU_BEAM) {
-    double rec[16];
-    load_rec16(A.beam_rec, e, rec);
     beam_block(rec, int(pair >> 1), int(pair & 1u), acc);
   } else {
-    const double2* tp = reinterpret_cast<const double2*>(A.truss_rec + e);
-    double2 t0 = __ldg(tp), t1 = __ldg(tp + 1);
-    truss_block(t0.x, t0.y, t1.x, t1.y, int(pair >> 1), int(pair & 1u), acc);
+    truss_block(rec[0], rec[1], rec[2], rec[3], int(pair >> 1), int(pair & 1u), acc);
   }
 }
 
-// place a 6x6 / 3x3 block into the slab image (shared or global)
-__device__ __forceinline__ void store_block(double* __restrict__ img, const BlockMeta& m,
-                                            const double acc[36]) {
-  const uint32_t s03 = m.strides & 0xFFFFu, s35 = m.strides >> 16;
-  const bool full = m.seg3 != 0xFFFFFFFFu;
+// Place a 6x6 / 3x3 block into the slab image. kShared: image in shared memory (STS) else straight
+// into the CSR values (global). When every row segment is 16-byte aligned (true whenever the node
+// only has 6-wide blocks) the six doubles of a row go out as three 16-byte stores: at the 48-byte
+// lane stride of neighbouring blocks those are bank-conflict free, 8-byte stores are 4-way
+// conflicted.
+template <bool kShared>
+__device__ __forceinline__ void store_block(double* __restrict__ img, const uint4 m,
+                                            const double acc[36], bool base_even) {
+  const uint32_t seg0 = m.x, seg3 = m.y, s03 = m.z & 0xFFFFu, s35 = m.z >> 16;
+  const bool full = seg3 != 0xFFFFFFFFu;
   if (full) {
+    const bool al = base_even && (((seg0 | s03 | seg3 | s35) & 1u) == 0);
+    if (al) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double* r0 = img + m.seg0 + i * s03;
-      double* r3 = img + m.seg3 + i * s35;
+      for (int i = 0; i < 3; ++i) {
+        double2* r0 = reinterpret_cast<double2*>(img + seg0 + i * s03);
+        double2* r3 = reinterpret_cast<double2*>(img + seg3 + i * s35);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        r0[j] = acc[6 * i + j];
-        r3[j] = acc[6 * (i + 3) + j];
+        for (int j = 0; j < 3; ++j) {
+          r0[j] = make_double2(acc[6 * i + 2 * j], acc[6 * i + 2 * j + 1]);
+          r3[j] = make_double2(acc[6 * (i + 3) + 2 * j], acc[6 * (i + 3) + 2 * j + 1]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double* r0 = img + seg0 + i * s03;
+        double* r3 = img + seg3 + i * s35;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          r0[j] = acc[6 * i + j];
+          r3[j] = acc[6 * (i + 3) + j];
+        }
       }
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double* r0 = img + m.seg0 + i * s03;
+      double* r0 = img + seg0 + i * s03;
 #pragma unroll
       for (int j = 0; j < 3; ++j) r0[j] = acc[6 * i + j];
     }
   }
 }
 
-__global__ void __launch_bounds__(kAsmThreads)
-assemble_kernel(const AsmArgs A) {
-  extern __shared__ __align__(16) double slab_img[];
-  for (uint32_t k = blockIdx.x; k < A.n_slabs; k += gridDim.x) {
-    const SlabDesc d = A.slabs[k];
-    if (d.blk_count == 0) continue;
-    const bool direct = d.flags & 1u;
-    double* img = direct ? (A.values + d.val_base) : slab_img;
-    for (uint32_t j = threadIdx.x; j < d.blk_count; j += kAsmThreads) {
-      const uint32_t p = d.blk_begin + j;
-      const BlockMeta m = A.meta[p];
-      const uint32_t c1 = A.cptr[p + 1];
-      double acc[36];
+// One work item = a run of consecutive thread-ordered blocks, hence of consecutive contributions.
+// The loop is flat over contributions (a block boundary is just a predicated store + reset), so
+// lanes whose items are one 4-contribution block and lanes whose items are four 1-contribution
+// blocks stay converged on the expensive part. Codes and block metadata are loaded one step
+// ahead of their use.
+template <bool kShared>
+__device__ __forceinline__ void run_item(const AsmArgs& A, const SlabDesc& d, const WorkItem& w,
+                                         double* img, const double* __restrict__ recs, bool base_even) {
+  // idle lanes (blk_count == 0) run zero iterations but still take part in the warp syncs
+  const uint4* meta = reinterpret_cast<const uint4*>(A.meta);
+  uint32_t p = w.blk_begin;
+  uint4 m = __ldg(meta + p);           // meta[] / contrib[] are padded, index 0 is always valid
+  uint4 m_next = __ldg(meta + p + 1);
+  uint32_t remaining = m.w;
+  uint32_t code = __ldg(A.contrib + w.c_begin);
+  const uint32_t c_end = w.c_begin + w.c_count;
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+  if (kShared) {
+    // the records staged by this warp's cp.async must have landed (and be visible warp-wide)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  for (uint32_t c = w.c_begin; c < c_end; ++c) {
+    const uint32_t next = __ldg(A.contrib + c + 1);  // contrib[] is padded by one entry
+    if (kShared) {
+      add_contribution(recs + (code & 0x03FFFFFFu) * kRecStride, code, acc);
+    } else {
+      // unstaged fallback (a node with thousands of neighbours): gather the record from global
+      double rec[kRecStride];
+      const uint32_t fe = __ldg(A.elist_compact + d.el_begin + (code & 0x03FFFFFFu));
+#pragma unroll
+      for (uint32_t ch = 0; ch < kRecStride / 2; ++ch) {
+        const double2* src = reinterpret_cast<const double2*>(record_chunk(A, fe, ch));
+        double2 v = src ? __ldg(src) : make_double2(0.0, 0.0);
+        rec[2 * ch] = v.x;
+        rec[2 * ch + 1] = v.y;
+      }
+      add_contribution(rec, code, acc);
+    }
+    code = next;
+    if (--remaining == 0) {
+      store_block<kShared>(img, m, acc, base_even);
 #pragma unroll
       for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-      for (uint32_t c = m.cptr; c < c1; ++c) add_contribution(A, __ldg(A.contrib + c), acc);
-      store_block(img, m, acc);
+      ++p;
+      m = m_next;
+      remaining = m.w;
+      m_next = __ldg(meta + p + 1);
     }
-    if (direct) continue;
-    __syncthreads();
-    // stream the slab image out: 16-byte stores on the aligned body, scalars at the ragged ends
-    double* out = A.values + d.val_base;
-    const uint32_t n = d.val_count;
-    const uint32_t head = uint32_t(d.val_base & 1);  // values[] is 16-byte aligned at index 0
-    if (head && threadIdx.x == 0) out[0] = slab_img[0];
-    const uint32_t body = (n - head) >> 1;
-    if (head == 0) {
-      const double2* src = reinterpret_cast<const double2*>(slab_img);
-      double2* dst = reinterpret_cast<double2*>(out);
-      for (uint32_t i = threadIdx.x; i < body; i += kAsmThreads) dst[i] = src[i];
-    } else {
-      double2* dst = reinterpret_cast<double2*>(out + 1);
-      for (uint32_t i = threadIdx.x; i < body; i += kAsmThreads)
-        dst[i] = make_double2(slab_img[1 + 2 * i], slab_img[2 + 2 * i]);
-    }
-    if (((n - head) & 1u) && threadIdx.x == 0) out[n - 1] = slab_img[n - 1];
-    __syncthreads();
   }
+}
+
+// One single-warp CTA per slab; no block barriers anywhere.
+//   trip 1   work item, slab descriptor and the slab's element list are fetched together: all three
+//            are addressable from the slab id alone (dense tables), nothing waits on anything
+//   trip 2   each lane cp.async's the records of "its" elements into shared memory (every record is
+//            fetched once per CTA, all requests in flight together) while it also pulls its first
+//            block metadata and contribution code
+//   compute  each lane evaluates its work item into the shared-memory image of the slab
+//   store    lane 0 hands the image to the TMA engine as one bulk shared->global copy
+__global__ void __maxnreg__(224)
+assemble_kernel(const AsmArgs A) {
+  extern __shared__ __align__(128) double slab_smem[];
+  const uint32_t k = blockIdx.x, lane = threadIdx.x;
+  const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(A.items) + size_t(k) * kAsmThreads + lane);
+  uint32_t fe[kElistStride / kAsmThreads];
+#pragma unroll
+  for (int j = 0; j < kElistStride / kAsmThreads; ++j)
+    fe[j] = __ldg(A.elist + size_t(k) * kElistStride + j * kAsmThreads + lane);
+  const SlabDesc d = A.slabs[k];
+  WorkItem w;
+  w.blk_begin = wraw.x; w.blk_count = wraw.y; w.c_begin = wraw.z; w.c_count = wraw.w;
+  if (d.blk_count == 0) return;
+  if (d.flags & 1u) {  // slab larger than the staging buffer: everything straight from/to HBM
+    run_item<false>(A, d, w, A.values + d.val_base, nullptr, (d.val_base & 1) == 0);
+    return;
+  }
+  double* img = slab_smem;
+  double* recs = slab_smem + ((d.val_count + 1u) & ~1u);
+  {
+    const uint32_t recs_s = smem_u32(recs);
+#pragma unroll
+    for (int j = 0; j < kElistStride / kAsmThreads; ++j) {
+      if (fe[j] != 0xFFFFFFFFu) {
+        const uint32_t slot = j * kAsmThreads + lane;
+#pragma unroll
+        for (uint32_t ch = 0; ch < kRecStride / 2; ++ch) {
+          const void* src = record_chunk(A, fe[j], ch);
+          if (src) cp_async16(recs_s + (slot * (kRecStride / 2) + ch) * 16u, src);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  run_item<true>(A, d, w, img, recs, true);
+  double* out = A.values + d.val_base;
+  const uint32_t n = d.val_count;
+  if (((d.val_base | n) & 1) == 0) {
+    // 16-byte aligned slab: generic-proxy writes -> async proxy, then one TMA bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out),
+                   "r"(smem_u32(img)), "r"(n * 8u)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  __syncwarp();
+  // ragged slab (3-wide truss blocks): coalesced 16-byte stores on the aligned body
+  const uint32_t head = uint32_t(d.val_base & 1);  // values[] is 16-byte aligned at index 0
+  if (head && lane == 0) out[0] = img[0];
+  const uint32_t body = (n - head) >> 1;
+  if (head == 0) {
+    const double2* src = reinterpret_cast<const double2*>(img);
+    double2* dst = reinterpret_cast<double2*>(out);
+    for (uint32_t i = lane; i < body; i += kAsmThreads) dst[i] = src[i];
+  } else {
+    double2* dst = reinterpret_cast<double2*>(out + 1);
+    for (uint32_t i = lane; i < body; i += kAsmThreads)
+      dst[i] = make_double2(img[1 + 2 * i], img[2 + 2 * i]);
+  }
+  if (((n - head) & 1u) && lane == 0) out[n - 1] = img[n - 1];
 }
 
 // test hook: the whole transformed element matrix of one element, built from the same block
@@ -148,9 +261,15 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
   A.beam_rec = beam_rec;
   A.plate_rec = plate_rec;
   A.plate_mat = plate_mat;
+  double rec[kRecStride];
+  for (uint32_t ch = 0; ch < kRecStride / 2; ++ch) {
+    const double* src = reinterpret_cast<const double*>(record_chunk(A, (uint32_t(family) << 26) | e, ch));
+    rec[2 * ch] = src ? src[0] : 0.0;
+    rec[2 * ch + 1] = src ? src[1] : 0.0;
+  }
   double acc[36];
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-  add_contribution(A, (uint32_t(family) << 30) | (uint32_t(pair) << 26) | e, acc);
+  add_contribution(rec, (uint32_t(family) << 30) | (uint32_t(pair) << 26), acc);
   for (int i = 0; i < dof; ++i)
     for (int j = 0; j < dof; ++j) out[(la * dof + i) * n + lb * dof + j] = acc[6 * i + j];
 }
@@ -160,24 +279,26 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
 int32_t run_assembly(Handle* h) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   if (h->n_slabs == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_set_for = -1;
+  if (attr_set_for != h->device) {
     FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               kSlabSmemBytes));
-    attr_set = true;
+    attr_set_for = h->device;
   }
   AsmArgs A;
   A.slabs = h->slabs.p;
   A.meta = h->blk_meta.p;
-  A.cptr = h->blk_cptr.p;
   A.contrib = h->contrib.p;
+  A.items = h->items.p;
+  A.elist = h->elist.p;
+  A.elist_compact = h->elist_compact.p;
   A.truss_rec = reinterpret_cast<const double4*>(h->fd[FEMGPU_TRUSS].rec.p);
   A.beam_rec = h->fd[FEMGPU_BEAM].rec.p;
   A.plate_rec = h->fd[FEMGPU_PLATE].rec.p;
   A.plate_mat = h->fd[FEMGPU_PLATE].mat.p;
   A.values = h->values.p;
   A.n_slabs = h->n_slabs;
-  assemble_kernel<<<h->n_slabs, kAsmThreads, kSlabSmemBytes, h->stream>>>(A);
+  assemble_kernel<<<h->n_slabs, kAsmThreads, h->slab_smem_bytes, h->stream>>>(A);
   h->launches++;
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   return 0;

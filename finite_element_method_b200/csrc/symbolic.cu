@@ -170,30 +170,173 @@ __global__ void slab_kernel(uint32_t n_slabs, uint32_t quota, uint32_t n_nodes,
   d.blk_begin = node_blk_ptr[first];
   d.blk_count = node_blk_ptr[next] - d.blk_begin;
   d.flags = (d.val_count > smem_doubles) ? 1u : 0u;
+  d.el_begin = 0;
+  d.el_count = 0;
   slabs[k] = d;
 }
 
-// sort key for the in-slab thread order: slab id, then descending contribution count
+__device__ __forceinline__ uint32_t block_cost(const uint32_t* __restrict__ cptr,
+                                               const uint32_t* __restrict__ contrib, uint32_t i) {
+  uint32_t cost = 0;
+  for (uint32_t c = cptr[i]; c < cptr[i + 1]; ++c) {
+    uint32_t f = contrib[c] >> 30;
+    cost += (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : kCostTruss);
+  }
+  return min(cost, 65535u);
+}
+
+// sort key for the in-slab thread order: slab id, then descending cost of the block
 __global__ void order_key_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
                                  const uint64_t* __restrict__ blk_key,
                                  const uint32_t* __restrict__ node_blk_ptr,
-                                 const uint32_t* __restrict__ cptr, uint64_t* __restrict__ okey,
+                                 const uint32_t* __restrict__ cptr,
+                                 const uint32_t* __restrict__ contrib, uint64_t* __restrict__ okey,
                                  uint32_t* __restrict__ oval) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_blocks) return;
   uint32_t a = uint32_t(blk_key[i] >> key_bits);
   uint32_t slab = node_blk_ptr[a] / quota;
-  uint32_t cnt = cptr[i + 1] - cptr[i];
-  okey[i] = (uint64_t(slab) << 8) | (255u - min(cnt, 255u));
+  okey[i] = (uint64_t(slab) << 16) | (65535u - block_cost(cptr, contrib, i));
   oval[i] = i;
 }
 
 __global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restrict__ order,
-                                     const uint32_t* __restrict__ cptr, uint32_t* __restrict__ cnt) {
+                                     const uint32_t* __restrict__ cptr,
+                                     const uint32_t* __restrict__ contrib, uint32_t* __restrict__ cnt,
+                                     uint32_t* __restrict__ cost) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_blocks) return;
   uint32_t i = order[p];
   cnt[p] = cptr[i + 1] - cptr[i];
+  cost[p] = block_cost(cptr, contrib, i);
+}
+
+// Work items: consecutive thread-ordered blocks of a slab are grouped greedily (blocks arrive in
+// descending cost) so that every thread of the CTA gets about the same cost. The cap W starts at
+// max(heaviest block, total / threads) and is raised until the slab fits in `threads` items.
+// One thread per slab walks its blocks; items are written to the dense [slab][thread] table.
+__global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, const SlabDesc* __restrict__ slabs,
+                                 const uint32_t* __restrict__ cost, const uint32_t* __restrict__ cptr_ord,
+                                 WorkItem* __restrict__ items) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_slabs) return;
+  const SlabDesc d = slabs[k];
+  const uint32_t b0 = d.blk_begin, b1 = d.blk_begin + d.blk_count;
+  uint64_t total = 0;
+  uint32_t mx = 1;
+  for (uint32_t b = b0; b < b1; ++b) {
+    total += cost[b];
+    mx = max(mx, cost[b]);
+  }
+  uint64_t W = max(uint64_t(mx), (total + threads - 1) / threads);
+  for (;;) {
+    uint32_t n = 0;
+    uint64_t cur = 0;
+    for (uint32_t b = b0; b < b1; ++b) {
+      if (b == b0 || cur + cost[b] > W) {
+        ++n;
+        cur = 0;
+      }
+      cur += cost[b];
+    }
+    if (n <= threads) break;
+    W += max(uint64_t(1), W / 8);
+  }
+  WorkItem* out = items + size_t(k) * threads;
+  uint32_t n = 0;
+  uint64_t cur = 0;
+  uint32_t start = b0;
+  for (uint32_t b = b0; b <= b1; ++b) {
+    bool close = (b == b1) || (b != b0 && cur + cost[b] > W);
+    if (close && b > start) {
+      WorkItem w;
+      w.blk_begin = start;
+      w.blk_count = b - start;
+      w.c_begin = cptr_ord[start];
+      w.c_count = cptr_ord[b] - cptr_ord[start];
+      out[n++] = w;
+      start = b;
+      cur = 0;
+    }
+    if (b < b1) cur += cost[b];
+  }
+  for (; n < threads; ++n) out[n] = WorkItem{0u, 0u, 0u, 0u};
+}
+
+// ---- per-slab element lists -----------------------------------------------------------------
+// key of a contribution: (slab << 28) | family << 26 | element; sorting + unique gives, per slab,
+// the distinct elements whose records the CTA stages in shared memory.
+__global__ void slab_elem_key_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
+                                     const uint32_t* __restrict__ order,
+                                     const uint64_t* __restrict__ blk_key,
+                                     const uint32_t* __restrict__ node_blk_ptr,
+                                     const uint32_t* __restrict__ cptr_ord,
+                                     const uint32_t* __restrict__ contrib_ord,
+                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_blocks) return;
+  uint32_t a = uint32_t(blk_key[order[p]] >> key_bits);
+  uint64_t slab = node_blk_ptr[a] / quota;
+  for (uint32_t c = cptr_ord[p]; c < cptr_ord[p + 1]; ++c) {
+    uint32_t code = contrib_ord[c];
+    uint32_t fe = ((code >> 30) << 26) | (code & 0x03FFFFFFu);
+    keys[c] = (slab << 28) | fe;
+    payload[c] = c;
+  }
+}
+
+__global__ void head_flag_kernel(uint32_t n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// uidx = inclusive scan of the head flags; element u = uidx - 1
+__global__ void elist_kernel(uint32_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flag,
+                             const uint32_t* __restrict__ uidx, uint64_t* __restrict__ ukey,
+                             uint32_t* __restrict__ elist) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  uint32_t u = uidx[i] - 1;
+  ukey[u] = keys[i];
+  elist[u] = uint32_t(keys[i] & 0x0FFFFFFFu);
+}
+
+__global__ void slab_elist_kernel(uint32_t n_slabs, uint32_t n_unique, const uint64_t* __restrict__ ukey,
+                                  SlabDesc* __restrict__ slabs, uint32_t smem_bytes_cap,
+                                  int32_t* __restrict__ flags) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_slabs) return;
+  uint32_t b = lower_bound_u64(ukey, n_unique, uint64_t(k) << 28);
+  uint32_t e = lower_bound_u64(ukey, n_unique, uint64_t(k + 1) << 28);
+  SlabDesc d = slabs[k];
+  d.el_begin = b;
+  d.el_count = e - b;
+  uint64_t need = ((uint64_t(d.val_count) * 8 + 15) & ~uint64_t(15)) + uint64_t(e - b) * kRecStride * 8;
+  if (need > smem_bytes_cap || (e - b) > uint32_t(kElistStride)) d.flags |= 1u;
+  slabs[k] = d;
+  if (!(d.flags & 1u)) atomicMax(flags + 2, int32_t(need));  // largest staged slab (integer max)
+}
+
+// dense [slab][kElistStride] copy of the compact lists: addressable from the slab id alone
+__global__ void elist_table_kernel(uint32_t n_slabs, const SlabDesc* __restrict__ slabs,
+                                   const uint32_t* __restrict__ compact, uint32_t* __restrict__ table) {
+  uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t k = uint32_t(t / kElistStride), e = uint32_t(t % kElistStride);
+  if (k >= n_slabs) return;
+  const SlabDesc d = slabs[k];
+  table[t] = (e < d.el_count && !(d.flags & 1u)) ? compact[d.el_begin + e] : 0xFFFFFFFFu;
+}
+
+// contrib codes become family<<30 | pair<<26 | slab-local element slot
+__global__ void relabel_kernel(uint32_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload,
+                               const uint32_t* __restrict__ uidx, const SlabDesc* __restrict__ slabs,
+                               uint32_t* __restrict__ contrib_ord) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t slab = uint32_t(keys[i] >> 28);
+  uint32_t local = (uidx[i] - 1) - slabs[slab].el_begin;
+  uint32_t c = payload[i];
+  contrib_ord[c] = (contrib_ord[c] & 0xFC000000u) | local;
 }
 
 __global__ void ordered_meta_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
@@ -220,7 +363,7 @@ __global__ void ordered_meta_kernel(uint32_t n_blocks, uint32_t quota, int key_b
   m.seg0 = rel + o03;
   m.seg3 = (o35 == 0xFFFFFFFFu) ? 0xFFFFFFFFu : rel + 3 * l03 + o35;
   m.strides = l03 | (l35 << 16);
-  m.cptr = cptr_ord[p];
+  m.count = cptr_ord[p + 1] - cptr_ord[p];
   meta[p] = m;
   uint32_t src = cptr_sorted[i], n = cptr_sorted[i + 1] - src, dst = cptr_ord[p];
   for (uint32_t c = 0; c < n; ++c) contrib_ord[dst + c] = contrib_sorted[src + c];
@@ -427,12 +570,12 @@ int32_t run_symbolic(Handle* h) {
   SYM_CHECK(oval_a.alloc(size_t(nblk) * 4));
   SYM_CHECK(h->blk_order.reserve(nblk));
   order_key_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_key.p, h->node_blk_ptr.p,
-                                                     cptr_sorted.as<uint32_t>(), okey_a.as<uint64_t>(),
-                                                     oval_a.as<uint32_t>());
+                                                     cptr_sorted.as<uint32_t>(), contrib_sorted,
+                                                     okey_a.as<uint64_t>(), oval_a.as<uint32_t>());
   h->launches++;
   {
-    int sbits = 8;
-    while ((uint64_t(1) << (sbits - 8)) < uint64_t(n_slabs) + 1) ++sbits;
+    int sbits = 16;
+    while ((uint64_t(1) << (sbits - 16)) < uint64_t(n_slabs) + 1) ++sbits;
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, okey_a.as<uint64_t>(), okey_b.as<uint64_t>(),
                                     oval_a.as<uint32_t>(), h->blk_order.p, int(nblk), 0, sbits, s);
@@ -442,11 +585,13 @@ int32_t run_symbolic(Handle* h) {
                                               oval_a.as<uint32_t>(), h->blk_order.p, int(nblk), 0, sbits, s));
     SYM_CHECK(cudaStreamSynchronize(s));
   }
-  Tmp ocnt;
+  Tmp ocnt, ocost;
   SYM_CHECK(ocnt.alloc((size_t(nblk) + 1) * 4));
+  SYM_CHECK(ocost.alloc((size_t(nblk) + 1) * 4));
   SYM_CHECK(cudaMemsetAsync(ocnt.as<uint32_t>() + nblk, 0, 4, s));
   ordered_count_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, h->blk_order.p, cptr_sorted.as<uint32_t>(),
-                                                         ocnt.as<uint32_t>());
+                                                         contrib_sorted, ocnt.as<uint32_t>(),
+                                                         ocost.as<uint32_t>());
   h->launches++;
   SYM_CHECK(h->blk_cptr.reserve(size_t(nblk) + 1));
   {
@@ -457,8 +602,8 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, ocnt.as<uint32_t>(), h->blk_cptr.p, int(nblk + 1), s));
     SYM_CHECK(cudaStreamSynchronize(s));
   }
-  SYM_CHECK(h->contrib.reserve(size_t(NC)));
-  SYM_CHECK(h->blk_meta.reserve(nblk));
+  SYM_CHECK(h->contrib.reserve(size_t(NC) + 1));  // +1: the kernel peeks one code ahead to prefetch
+  SYM_CHECK(h->blk_meta.reserve(size_t(nblk) + 1));  // +1: the kernel loads one block ahead
   ordered_meta_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_order.p, h->blk_key.p,
                                                         h->node_blk_ptr.p, h->blk_off.p, h->node_len.p,
                                                         h->node_base.p, h->slabs.p, cptr_sorted.as<uint32_t>(),
@@ -467,8 +612,69 @@ int32_t run_symbolic(Handle* h) {
   h->launches++;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
-  SYM_CHECK(cudaMemcpy(&overflow, h->d_flag.p, 4, cudaMemcpyDeviceToHost));
-  if (overflow) return h->fail(FEMGPU_ERR_LIMIT, "a slab holds 2^32 or more values");
+  SYM_CHECK(cudaMemsetAsync(h->contrib.p + NC, 0, 4, s));
+  SYM_CHECK(cudaMemsetAsync(h->blk_meta.p + nblk, 0, sizeof(BlockMeta), s));
+  // per-slab element lists; contrib codes are relabelled to slab-local element slots
+  {
+    if (uint64_t(n_slabs) >= (uint64_t(1) << 36)) return h->fail(FEMGPU_ERR_LIMIT, "too many slabs");
+    uint64_t* ekey_a = keys_a.as<uint64_t>();  // the contribution sort buffers are free again
+    uint64_t* ekey_b = uniq.as<uint64_t>();
+    uint32_t* epay_a = vals_a.as<uint32_t>();
+    Tmp epay_b, eflag, euidx;
+    SYM_CHECK(epay_b.alloc(size_t(NC) * 4));
+    SYM_CHECK(eflag.alloc(size_t(NC) * 4));
+    SYM_CHECK(euidx.alloc(size_t(NC) * 4));
+    slab_elem_key_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_order.p, h->blk_key.p,
+                                                           h->node_blk_ptr.p, h->blk_cptr.p, h->contrib.p, ekey_a,
+                                                           epay_a);
+    int ebits = 28;
+    while ((uint64_t(1) << (ebits - 28)) < uint64_t(n_slabs) + 1) ++ebits;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, ekey_a, ekey_b, epay_a, epay_b.as<uint32_t>(), int(NC), 0, ebits, s);
+    {
+      Tmp t;
+      SYM_CHECK(t.alloc(tb));
+      SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, ekey_a, ekey_b, epay_a, epay_b.as<uint32_t>(), int(NC), 0,
+                                                ebits, s));
+      SYM_CHECK(cudaStreamSynchronize(s));
+    }
+    head_flag_kernel<<<div_up(NC, 256), 256, 0, s>>>(uint32_t(NC), ekey_b, eflag.as<uint32_t>());
+    tb = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb, eflag.as<uint32_t>(), euidx.as<uint32_t>(), int(NC), s);
+    {
+      Tmp t;
+      SYM_CHECK(t.alloc(tb));
+      SYM_CHECK(cub::DeviceScan::InclusiveSum(t.p, tb, eflag.as<uint32_t>(), euidx.as<uint32_t>(), int(NC), s));
+      SYM_CHECK(cudaStreamSynchronize(s));
+    }
+    uint32_t n_unique = 0;
+    SYM_CHECK(cudaMemcpy(&n_unique, euidx.as<uint32_t>() + (NC - 1), 4, cudaMemcpyDeviceToHost));
+    SYM_CHECK(h->elist_compact.reserve(n_unique));
+    SYM_CHECK(h->elist.reserve(size_t(n_slabs) * kElistStride));
+    uint64_t* ukey = ekey_a;  // reuse: ekey_a is dead after the sort
+    elist_kernel<<<div_up(NC, 256), 256, 0, s>>>(uint32_t(NC), ekey_b, eflag.as<uint32_t>(), euidx.as<uint32_t>(),
+                                                 ukey, h->elist_compact.p);
+    slab_elist_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, n_unique, ukey, h->slabs.p,
+                                                           uint32_t(kSlabSmemBytes), h->d_flag.p);
+    relabel_kernel<<<div_up(NC, 256), 256, 0, s>>>(uint32_t(NC), ekey_b, epay_b.as<uint32_t>(), euidx.as<uint32_t>(),
+                                                   h->slabs.p, h->contrib.p);
+    elist_table_kernel<<<div_up(uint64_t(n_slabs) * kElistStride, 256), 256, 0, s>>>(n_slabs, h->slabs.p,
+                                                                                  h->elist_compact.p, h->elist.p);
+    h->launches += 6;
+    SYM_CHECK(cudaGetLastError());
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  // balanced per-thread work lists (needs blk_cptr, filled above)
+  SYM_CHECK(h->items.reserve(size_t(n_slabs) * kAsmThreads));
+  work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, kAsmThreads, h->slabs.p, ocost.as<uint32_t>(),
+                                                         h->blk_cptr.p, h->items.p);
+  h->launches++;
+  SYM_CHECK(cudaGetLastError());
+  SYM_CHECK(cudaStreamSynchronize(s));
+  int32_t flags[4] = {0, 0, 0, 0};
+  SYM_CHECK(cudaMemcpy(flags, h->d_flag.p, 16, cudaMemcpyDeviceToHost));
+  if (flags[0]) return h->fail(FEMGPU_ERR_LIMIT, "a slab holds 2^32 or more values");
+  h->slab_smem_bytes = (uint32_t(flags[2]) + 15) & ~15u;
 
   if (h->dist.enabled) {
     int32_t st = dist_symbolic_exchange(h);
