@@ -454,8 +454,8 @@ static void free_device(femgpu_t* h) {
   h->blk_meta.release(); h->blk_order.release(); h->items.release(); h->elist.release(); h->elist_compact.release(); h->node_blk_ptr.release(); h->node_base.release();
   h->node_len.release(); h->blk_off.release(); h->slabs.release(); h->row_ptr.release();
   h->col_idx.release(); h->values.release(); h->scratch.release(); h->d_flag.release();
-  h->dist.send_buf.release(); h->dist.recv_buf.release(); h->dist.recv_slot.release();
-  h->dist.recv_meta.release();
+  h->dist.send_buf.release(); h->dist.recv_buf.release(); h->dist.recv_dst_block.release();
+  h->dist.recv_full.release(); h->dist.remote_keys.release();
 }
 
 int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {

@@ -199,12 +199,14 @@ struct DistState {
   void* comm = nullptr;  // ncclComm_t
   uint32_t own_begin = 0, own_end = 0;
   bool ownership_set = false;
-  // ghost exchange plan (built by the symbolic pass)
-  std::vector<int64_t> send_blocks, recv_blocks;    // per peer: number of node-pair blocks
-  std::vector<int64_t> send_vals, recv_vals;        // per peer: doubles
-  DevBuf<double> send_buf, recv_buf;
-  DevBuf<int64_t> recv_slot;   // per received block: value index of its (row 0, col 0) entry
-  DevBuf<uint32_t> recv_meta;  // per received block: strides / kind to place rows
+  // ghost exchange plan (built by the symbolic pass); all counts are node-pair blocks
+  std::vector<int64_t> send_blocks, recv_blocks;  // per peer
+  std::vector<int64_t> send_off, recv_off;        // per peer: prefix offsets (blocks)
+  std::vector<int64_t> send_first_block;          // per peer: first ghost block in blk_key order
+  DevBuf<uint64_t> remote_keys;   // received ghost block keys, bit 63 = 6x6, grouped by source rank
+  DevBuf<double> send_buf, recv_buf;  // 36 doubles per block
+  DevBuf<uint32_t> recv_dst_block;    // per received block: index of the owner's block
+  DevBuf<uint8_t> recv_full;          // per received block: 1 = 6x6
   uint64_t last_sent = 0, last_recv = 0;
 };
 
@@ -267,6 +269,9 @@ struct Handle {
   DevBuf<int32_t> d_flag;          // small device scalars
 
   DistState dist;
+  struct DistScratch {
+    DevBuf<int64_t> i64;
+  } dist_scratch;
 
   Handle() {
     auto tie = [&](auto& b) { b.tally = &dev_bytes; };
@@ -279,7 +284,8 @@ struct Handle {
     tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
     tie(col_idx); tie(values); tie(scratch); tie(d_flag);
-    tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_slot); tie(dist.recv_meta);
+    tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_dst_block); tie(dist.recv_full);
+    tie(dist.remote_keys); tie(dist_scratch.i64);
   }
 
   int32_t fail(int32_t code, const std::string& text) const {
@@ -300,9 +306,11 @@ int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);  
 int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
 int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host);   // symbolic.cu
 int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals);  // symbolic.cu
-int32_t dist_symbolic_exchange(Handle* h);               // dist.cu
 int32_t dist_numeric_exchange(Handle* h);                // dist.cu
 void dist_destroy(Handle* h);                            // dist.cu
+int32_t dist_allgather_i64(Handle* h, const int64_t* send, int64_t* recv, size_t n);  // dist.cu
+int32_t dist_exchange_8(Handle* h, const void* send, const int64_t* send_offs, const int64_t* send_counts,
+                        void* recv, const int64_t* recv_offs, const int64_t* recv_counts);  // dist.cu
 
 constexpr int kAsmThreads = 32;            // threads per assembly CTA: one warp, no block barriers
 constexpr int kSlabQuota = 72;             // node-pair blocks a slab aims for (8 plate-grid nodes)

@@ -54,6 +54,7 @@ __device__ __forceinline__ const void* record_chunk(const AsmArgs& A, uint32_t f
     return A.plate_mat + size_t(e) * 4 + (chunk - 8) * 2;
   }
   if (family == FEMGPU_BEAM) return chunk < 8 ? A.beam_rec + size_t(e) * 16 + chunk * 2 : nullptr;
+  if (family != FEMGPU_TRUSS) return nullptr;  // family 3: placeholder of a remote contribution
   return chunk < 2 ? reinterpret_cast<const double*>(A.truss_rec + e) + chunk * 2 : nullptr;
 }
 
@@ -66,9 +67,10 @@ __device__ __forceinline__ void add_contribution(const double* __restrict__ rec,
     plate_block(rec, rec + 16, int(pair >> 2), int(pair & 3u), acc);
   } else if (family == FEMGPU_BEAM) {
     beam_block(rec, int(pair >> 1), int(pair & 1u), acc);
-  } else {
+  } else if (family == FEMGPU_TRUSS) {
     truss_block(rec[0], rec[1], rec[2], rec[3], int(pair >> 1), int(pair & 1u), acc);
   }
+  // family 3: slot reserved for another rank's contribution (multi-GPU) — nothing to add here
 }
 
 // Place a 6x6 / 3x3 block into the slab image. kShared: image in shared memory (STS) else straight

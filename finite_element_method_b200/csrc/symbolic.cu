@@ -22,10 +22,15 @@ namespace {
 
 struct Tmp {  // RAII scratch allocation
   void* p = nullptr;
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-  ~Tmp() {
-    if (p) cudaFree(p);
+  cudaError_t alloc(size_t bytes) {
+    release();
+    return cudaMalloc(&p, bytes ? bytes : 16);
   }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  ~Tmp() { release(); }
   template <typename T>
   T* as() {
     return static_cast<T*>(p);
@@ -56,11 +61,14 @@ __global__ void block_kind_kernel(uint32_t n_blocks, const uint32_t* __restrict_
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_blocks) return;
   uint8_t f = 0;
-  for (uint32_t c = cptr[i]; c < cptr[i + 1]; ++c)
-    if ((contrib[c] >> 30) != FEMGPU_TRUSS) {
+  for (uint32_t c = cptr[i]; c < cptr[i + 1]; ++c) {
+    uint32_t fam = contrib[c] >> 30;
+    // family 3 = placeholder for a block another rank contributes to; bit 26 says whether it is 6x6
+    if (fam == FEMGPU_BEAM || fam == FEMGPU_PLATE || (fam == 3u && ((contrib[c] >> 26) & 1u))) {
       f = 1;
       break;
     }
+  }
   full[i] = f;
 }
 
@@ -180,7 +188,7 @@ __device__ __forceinline__ uint32_t block_cost(const uint32_t* __restrict__ cptr
   uint32_t cost = 0;
   for (uint32_t c = cptr[i]; c < cptr[i + 1]; ++c) {
     uint32_t f = contrib[c] >> 30;
-    cost += (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : kCostTruss);
+    cost += (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
   }
   return min(cost, 65535u);
 }
@@ -419,9 +427,238 @@ __global__ void nz_write_kernel(int64_t nnz, int64_t n_rows, const double* __res
   vals[p] = v;
 }
 
+// placeholder contributions for blocks other ranks will add to (multi-GPU): they only create the
+// slot; the assembly kernel skips family 3
+__global__ void remote_contrib_kernel(uint32_t n, const uint64_t* __restrict__ remote_keys, int64_t base,
+                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = remote_keys[i];
+  keys[base + i] = k & ~(uint64_t(1) << 63);
+  vals[base + i] = (3u << 30) | (uint32_t(k >> 63) << 26);
+}
+
+__global__ void ghost_key_kernel(uint32_t n, const uint64_t* __restrict__ blk_key, const uint8_t* __restrict__ full,
+                                 uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = blk_key[i] | (uint64_t(full[i]) << 63);
+}
+
+// bounds[2r], bounds[2r+1] = first / last+1 block whose row node lies in rank r's node range
+__global__ void rank_bounds_kernel(int world, const int64_t* __restrict__ ranges, int key_bits,
+                                   const uint64_t* __restrict__ blk_key, uint32_t n_blocks,
+                                   int64_t* __restrict__ bounds) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * world) return;
+  bounds[t] = lower_bound_u64(blk_key, n_blocks, uint64_t(ranges[t]) << key_bits);
+}
+
+__global__ void ghost_dst_kernel(uint32_t n, const uint64_t* __restrict__ remote_keys,
+                                 const uint64_t* __restrict__ blk_key, uint32_t n_blocks,
+                                 uint32_t* __restrict__ dst, uint8_t* __restrict__ full, int32_t* __restrict__ bad) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = remote_keys[i] & ~(uint64_t(1) << 63);
+  uint32_t b = lower_bound_u64(blk_key, n_blocks, k);
+  if (b >= n_blocks || blk_key[b] != k) *bad = 1;
+  dst[i] = b;
+  full[i] = uint8_t(remote_keys[i] >> 63);
+}
+
+struct BlockBuild {
+  Tmp keys_a, keys_b, vals_a, vals_b, uniq, counts, nruns, cptr_sorted;
+  uint32_t nblk = 0;
+  int64_t total = 0;  // local contributions + remote placeholders
+  void release() {
+    keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release();
+    uniq.release(); counts.release(); nruns.release(); cptr_sorted.release();
+    nblk = 0;
+    total = 0;
+  }
+};
+
 }  // namespace
 
 #define SYM_CHECK(expr) FEMGPU_CUDA_CHECK(h, (expr))
+
+// steps 1-3a: contributions in global insertion order (+ remote placeholders), stable sort by
+// (row node, col node), unique blocks with contribution ranges, block kinds
+static int32_t build_blocks(Handle* h, int64_t n_extra, BlockBuild& bb) {
+  cudaStream_t s = h->stream;
+  const int kb = h->key_bits;
+  const int64_t NC = h->n_contrib;
+  const int64_t T = NC + n_extra;
+  bb.total = T;
+  SYM_CHECK(bb.keys_a.alloc(size_t(T) * 8));
+  SYM_CHECK(bb.keys_b.alloc(size_t(T) * 8));
+  SYM_CHECK(bb.vals_a.alloc(size_t(T) * 4));
+  SYM_CHECK(bb.vals_b.alloc(size_t(T) * 4));
+  for (int f = 0; f < kFamilies; ++f) {
+    FamilyDev& fd = h->fd[f];
+    size_t n = h->fh[f].size();
+    if (!n) continue;
+    uint64_t threads = uint64_t(n) * kPairsPerElem[f];
+    uint32_t grid = div_up(threads, 256);
+    if (f == FEMGPU_PLATE)
+      gen_contrib_kernel<4><<<grid, 256, 0, s>>>(uint32_t(n), f, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p,
+                                                 fd.conn[3].p, fd.cbase.p, kb, bb.keys_a.as<uint64_t>(),
+                                                 bb.vals_a.as<uint32_t>());
+    else
+      gen_contrib_kernel<2><<<grid, 256, 0, s>>>(uint32_t(n), f, fd.conn[0].p, fd.conn[1].p, nullptr, nullptr,
+                                                 fd.cbase.p, kb, bb.keys_a.as<uint64_t>(), bb.vals_a.as<uint32_t>());
+    h->launches++;
+  }
+  if (n_extra) {
+    remote_contrib_kernel<<<div_up(n_extra, 256), 256, 0, s>>>(uint32_t(n_extra), h->dist.remote_keys.p, NC,
+                                                               bb.keys_a.as<uint64_t>(), bb.vals_a.as<uint32_t>());
+    h->launches++;
+  }
+  SYM_CHECK(cudaGetLastError());
+  {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, bb.keys_a.as<uint64_t>(), bb.keys_b.as<uint64_t>(),
+                                    bb.vals_a.as<uint32_t>(), bb.vals_b.as<uint32_t>(), int(T), 0, 2 * kb, s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, bb.keys_a.as<uint64_t>(), bb.keys_b.as<uint64_t>(),
+                                              bb.vals_a.as<uint32_t>(), bb.vals_b.as<uint32_t>(), int(T), 0,
+                                              2 * kb, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  SYM_CHECK(bb.uniq.alloc(size_t(T) * 8));
+  SYM_CHECK(bb.counts.alloc((size_t(T) + 1) * 4));
+  SYM_CHECK(bb.nruns.alloc(16));
+  {
+    size_t tb = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, tb, bb.keys_b.as<uint64_t>(), bb.uniq.as<uint64_t>(),
+                                       bb.counts.as<uint32_t>(), bb.nruns.as<uint32_t>(), int(T), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceRunLengthEncode::Encode(t.p, tb, bb.keys_b.as<uint64_t>(), bb.uniq.as<uint64_t>(),
+                                                 bb.counts.as<uint32_t>(), bb.nruns.as<uint32_t>(), int(T), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  uint32_t nblk = 0;
+  SYM_CHECK(cudaMemcpy(&nblk, bb.nruns.p, 4, cudaMemcpyDeviceToHost));
+  bb.nblk = nblk;
+  h->n_blocks = nblk;
+  SYM_CHECK(h->blk_key.reserve(nblk));
+  SYM_CHECK(cudaMemcpyAsync(h->blk_key.p, bb.uniq.p, size_t(nblk) * 8, cudaMemcpyDeviceToDevice, s));
+  SYM_CHECK(bb.cptr_sorted.alloc((size_t(nblk) + 1) * 4));
+  {
+    // exclusive scan over nblk+1 items (the extra item makes the last entry the total)
+    SYM_CHECK(cudaMemsetAsync(bb.counts.as<uint32_t>() + nblk, 0, 4, s));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, bb.counts.as<uint32_t>(), bb.cptr_sorted.as<uint32_t>(), int(nblk + 1), s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, bb.counts.as<uint32_t>(), bb.cptr_sorted.as<uint32_t>(),
+                                            int(nblk + 1), s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  SYM_CHECK(h->blk_full.reserve(nblk));
+  block_kind_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, bb.cptr_sorted.as<uint32_t>(), bb.vals_b.as<uint32_t>(),
+                                                      h->blk_full.p);
+  h->launches++;
+  SYM_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Multi-GPU, symbolic half (collective): send the keys of the blocks in rows this rank does not own
+// to the owning ranks; what arrives becomes placeholder contributions of the second build.
+static int32_t dist_collect_ghost_keys(Handle* h, const BlockBuild& bb, int64_t* n_extra,
+                                       std::vector<int64_t>& ranges) {
+  DistState& D = h->dist;
+  cudaStream_t s = h->stream;
+  const int W = D.world;
+  if (!D.ownership_set) return h->fail(FEMGPU_ERR_USAGE, "femgpu_dist_set_ownership was not called");
+  // everyone's node ranges
+  int64_t mine[2] = {int64_t(D.own_begin), int64_t(D.own_end)};
+  ranges.assign(size_t(2) * W, 0);
+  int32_t st = dist_allgather_i64(h, mine, ranges.data(), 2);
+  if (st) return st;
+  // per destination rank: the contiguous run of my (sorted) blocks whose row node it owns
+  std::vector<int64_t> bounds(size_t(2) * W, 0);
+  Tmp d_ranges, d_bounds, sendkeys;
+  if (bb.nblk) {
+    SYM_CHECK(d_ranges.alloc(size_t(2) * W * 8));
+    SYM_CHECK(d_bounds.alloc(size_t(2) * W * 8));
+    SYM_CHECK(cudaMemcpyAsync(d_ranges.p, ranges.data(), size_t(2) * W * 8, cudaMemcpyHostToDevice, s));
+    rank_bounds_kernel<<<1, 2 * W, 0, s>>>(W, d_ranges.as<int64_t>(), h->key_bits, h->blk_key.p, bb.nblk,
+                                           d_bounds.as<int64_t>());
+    SYM_CHECK(cudaMemcpyAsync(bounds.data(), d_bounds.p, size_t(2) * W * 8, cudaMemcpyDeviceToHost, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+    SYM_CHECK(sendkeys.alloc(size_t(bb.nblk) * 8));
+    ghost_key_kernel<<<div_up(bb.nblk, 256), 256, 0, s>>>(bb.nblk, h->blk_key.p, h->blk_full.p, sendkeys.as<uint64_t>());
+    h->launches += 2;
+  }
+  std::vector<int64_t> send_counts(W, 0), send_offs(W, 0);
+  for (int r = 0; r < W; ++r) {
+    if (r == D.rank) continue;
+    send_offs[r] = bounds[2 * r];
+    send_counts[r] = bounds[2 * r + 1] - bounds[2 * r];
+  }
+  // count matrix: row = sender
+  std::vector<int64_t> matrix(size_t(W) * W, 0);
+  if ((st = dist_allgather_i64(h, send_counts.data(), matrix.data(), W))) return st;
+  std::vector<int64_t> recv_counts(W, 0), recv_offs(W + 1, 0);
+  for (int r = 0; r < W; ++r) recv_counts[r] = (r == D.rank) ? 0 : matrix[size_t(r) * W + D.rank];
+  for (int r = 0; r < W; ++r) recv_offs[r + 1] = recv_offs[r] + recv_counts[r];
+  const int64_t n_recv = recv_offs[W];
+  SYM_CHECK(D.remote_keys.reserve(size_t(n_recv) + 1));
+  if ((st = dist_exchange_8(h, sendkeys.p, send_offs.data(), send_counts.data(), D.remote_keys.p, recv_offs.data(),
+                            recv_counts.data())))
+    return st;
+  SYM_CHECK(cudaStreamSynchronize(s));
+  D.send_blocks = send_counts;
+  D.recv_blocks = recv_counts;
+  D.recv_off = recv_offs;
+  D.send_off.assign(W + 1, 0);
+  for (int r = 0; r < W; ++r) D.send_off[r + 1] = D.send_off[r] + send_counts[r];
+  *n_extra = n_recv;
+  return 0;
+}
+
+// Multi-GPU, after the final pattern exists: where my ghost blocks sit, where received ones land
+static int32_t dist_finalize_plan(Handle* h, const std::vector<int64_t>& ranges) {
+  DistState& D = h->dist;
+  cudaStream_t s = h->stream;
+  const int W = D.world;
+  std::vector<int64_t> bounds(size_t(2) * W, 0);
+  if (h->n_blocks) {
+    Tmp d_ranges, d_bounds;
+    SYM_CHECK(d_ranges.alloc(size_t(2) * W * 8));
+    SYM_CHECK(d_bounds.alloc(size_t(2) * W * 8));
+    SYM_CHECK(cudaMemcpyAsync(d_ranges.p, ranges.data(), size_t(2) * W * 8, cudaMemcpyHostToDevice, s));
+    rank_bounds_kernel<<<1, 2 * W, 0, s>>>(W, d_ranges.as<int64_t>(), h->key_bits, h->blk_key.p, h->n_blocks,
+                                           d_bounds.as<int64_t>());
+    SYM_CHECK(cudaMemcpyAsync(bounds.data(), d_bounds.p, size_t(2) * W * 8, cudaMemcpyDeviceToHost, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+    h->launches++;
+  }
+  D.send_first_block.assign(W, 0);
+  for (int r = 0; r < W; ++r) {
+    if (r == D.rank) continue;
+    D.send_first_block[r] = bounds[2 * r];
+    if (bounds[2 * r + 1] - bounds[2 * r] != D.send_blocks[r])
+      return h->fail(FEMGPU_ERR_USAGE, "internal: ghost block count changed between the two symbolic builds");
+  }
+  SYM_CHECK(D.send_buf.reserve(size_t(D.send_off[W]) * 36 + 1));
+  SYM_CHECK(D.recv_buf.reserve(size_t(D.recv_off[W]) * 36 + 1));
+  const int64_t n_recv = D.recv_off[W];
+  SYM_CHECK(D.recv_dst_block.reserve(size_t(n_recv) + 1));
+  SYM_CHECK(D.recv_full.reserve(size_t(n_recv) + 1));
+  if (n_recv) {
+    SYM_CHECK(cudaMemsetAsync(h->d_flag.p + 4, 0, 4, s));
+    ghost_dst_kernel<<<div_up(n_recv, 256), 256, 0, s>>>(uint32_t(n_recv), D.remote_keys.p, h->blk_key.p, h->n_blocks,
+                                                         D.recv_dst_block.p, D.recv_full.p, h->d_flag.p + 4);
+    h->launches++;
+    int32_t bad = 0;
+    SYM_CHECK(cudaMemcpy(&bad, h->d_flag.p + 4, 4, cudaMemcpyDeviceToHost));
+    if (bad) return h->fail(FEMGPU_ERR_USAGE, "internal: a received ghost block has no slot in the owner's pattern");
+  }
+  return 0;
+}
 
 int32_t run_symbolic(Handle* h) {
   SYM_CHECK(cudaSetDevice(h->device));
@@ -429,7 +666,6 @@ int32_t run_symbolic(Handle* h) {
   const uint32_t N = h->nodes_number;
   h->n_rows = 6 * int64_t(N);
   const int64_t NC = h->n_contrib;
-  if (NC >= (int64_t(1) << 31)) return h->fail(FEMGPU_ERR_LIMIT, "more than 2^31 node-pair contributions on one device");
   int kb = 1;
   while ((uint64_t(1) << kb) < uint64_t(N)) ++kb;
   h->key_bits = kb;
@@ -441,7 +677,23 @@ int32_t run_symbolic(Handle* h) {
   SYM_CHECK(h->d_flag.reserve(16));
   SYM_CHECK(cudaMemsetAsync(h->d_flag.p, 0, 64, s));
 
-  if (NC == 0) {
+  BlockBuild bb;
+  int64_t n_extra = 0;
+  std::vector<int64_t> ranges;
+  if (h->dist.enabled) {
+    // first build sees local elements only; its ghost-row block keys go to the owning ranks
+    if (NC) {
+      int32_t st = build_blocks(h, 0, bb);
+      if (st) return st;
+    }
+    int32_t st = dist_collect_ghost_keys(h, bb, &n_extra, ranges);
+    if (st) return st;
+    bb.release();
+  }
+  const int64_t NCt = NC + n_extra;
+  if (NCt >= (int64_t(1) << 31)) return h->fail(FEMGPU_ERR_LIMIT, "more than 2^31 node-pair contributions on one device");
+
+  if (NCt == 0) {
     SYM_CHECK(cudaMemsetAsync(h->node_blk_ptr.p, 0, (size_t(N) + 1) * 4, s));
     SYM_CHECK(cudaMemsetAsync(h->node_base.p, 0, (size_t(N) + 1) * 8, s));
     SYM_CHECK(cudaMemsetAsync(h->node_len.p, 0, (2 * size_t(N) + 2) * 4, s));
@@ -449,90 +701,31 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cudaStreamSynchronize(s));
     h->n_blocks = h->n_slabs = 0;
     h->nnz = 0;
+    if (h->dist.enabled) return dist_finalize_plan(h, ranges);
     return 0;
   }
 
-  // ---- 1. contributions in global insertion order, then stable sort by (row node, col node)
-  Tmp keys_a, keys_b, vals_a, vals_b;
-  SYM_CHECK(keys_a.alloc(size_t(NC) * 8));
-  SYM_CHECK(keys_b.alloc(size_t(NC) * 8));
-  SYM_CHECK(vals_a.alloc(size_t(NC) * 4));
-  SYM_CHECK(vals_b.alloc(size_t(NC) * 4));
-  for (int f = 0; f < kFamilies; ++f) {
-    FamilyDev& fd = h->fd[f];
-    size_t n = h->fh[f].size();
-    if (!n) continue;
-    uint64_t threads = uint64_t(n) * kPairsPerElem[f];
-    uint32_t grid = div_up(threads, 256);
-    if (f == FEMGPU_PLATE)
-      gen_contrib_kernel<4><<<grid, 256, 0, s>>>(uint32_t(n), f, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p,
-                                                 fd.conn[3].p, fd.cbase.p, kb, keys_a.as<uint64_t>(),
-                                                 vals_a.as<uint32_t>());
-    else
-      gen_contrib_kernel<2><<<grid, 256, 0, s>>>(uint32_t(n), f, fd.conn[0].p, fd.conn[1].p, nullptr, nullptr,
-                                                 fd.cbase.p, kb, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
-    h->launches++;
-  }
-  SYM_CHECK(cudaGetLastError());
+  // ---- 1-3a. sorted contributions, unique blocks, block kinds
   {
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(),
-                                    vals_a.as<uint32_t>(), vals_b.as<uint32_t>(), int(NC), 0, 2 * kb, s);
-    Tmp t;
-    SYM_CHECK(t.alloc(tb));
-    SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(),
-                                              vals_a.as<uint32_t>(), vals_b.as<uint32_t>(), int(NC), 0,
-                                              2 * kb, s));
-    SYM_CHECK(cudaStreamSynchronize(s));
+    int32_t st = build_blocks(h, n_extra, bb);
+    if (st) return st;
   }
-  uint64_t* keys_sorted = keys_b.as<uint64_t>();
-  uint32_t* contrib_sorted = vals_b.as<uint32_t>();
+  const uint32_t nblk = bb.nblk;
+  Tmp& keys_a = bb.keys_a;
+  Tmp& vals_a = bb.vals_a;
+  Tmp& uniq = bb.uniq;
+  Tmp& cptr_sorted = bb.cptr_sorted;
+  uint32_t* contrib_sorted = bb.vals_b.as<uint32_t>();
 
-  // ---- 2. unique blocks + contribution counts
-  Tmp uniq, counts, nruns;
-  SYM_CHECK(uniq.alloc(size_t(NC) * 8));
-  SYM_CHECK(counts.alloc((size_t(NC) + 1) * 4));
-  SYM_CHECK(nruns.alloc(16));
-  {
-    size_t tb = 0;
-    cub::DeviceRunLengthEncode::Encode(nullptr, tb, keys_sorted, uniq.as<uint64_t>(), counts.as<uint32_t>(),
-                                       nruns.as<uint32_t>(), int(NC), s);
-    Tmp t;
-    SYM_CHECK(t.alloc(tb));
-    SYM_CHECK(cub::DeviceRunLengthEncode::Encode(t.p, tb, keys_sorted, uniq.as<uint64_t>(),
-                                                 counts.as<uint32_t>(), nruns.as<uint32_t>(), int(NC), s));
-    SYM_CHECK(cudaStreamSynchronize(s));
-  }
-  uint32_t nblk = 0;
-  SYM_CHECK(cudaMemcpy(&nblk, nruns.p, 4, cudaMemcpyDeviceToHost));
-  h->n_blocks = nblk;
-  SYM_CHECK(h->blk_key.reserve(nblk));
-  SYM_CHECK(cudaMemcpyAsync(h->blk_key.p, uniq.p, size_t(nblk) * 8, cudaMemcpyDeviceToDevice, s));
-  Tmp cptr_sorted;
-  SYM_CHECK(cptr_sorted.alloc((size_t(nblk) + 1) * 4));
-  {
-    // exclusive scan over nblk+1 items (the extra item makes the last entry the total)
-    SYM_CHECK(cudaMemsetAsync(counts.as<uint32_t>() + nblk, 0, 4, s));
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), cptr_sorted.as<uint32_t>(), int(nblk + 1), s);
-    Tmp t;
-    SYM_CHECK(t.alloc(tb));
-    SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, counts.as<uint32_t>(), cptr_sorted.as<uint32_t>(),
-                                            int(nblk + 1), s));
-    SYM_CHECK(cudaStreamSynchronize(s));
-  }
-
-  // ---- 3. block kinds, node ranges, row layout
-  SYM_CHECK(h->blk_full.reserve(nblk));
+  // ---- 3b. node ranges, row layout
   SYM_CHECK(h->blk_off.reserve(2 * size_t(nblk)));
-  block_kind_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, cptr_sorted.as<uint32_t>(), contrib_sorted, h->blk_full.p);
   node_ptr_kernel<<<div_up(size_t(N) + 1, 256), 256, 0, s>>>(N, nblk, kb, h->blk_key.p, h->node_blk_ptr.p);
   Tmp node_size;
   SYM_CHECK(node_size.alloc((size_t(N) + 1) * 8));
   SYM_CHECK(cudaMemsetAsync(node_size.p, 0, (size_t(N) + 1) * 8, s));
   node_layout_kernel<<<div_up(N, 256), 256, 0, s>>>(N, h->node_blk_ptr.p, h->blk_full.p, h->blk_off.p,
                                                     h->node_len.p, node_size.as<int64_t>(), h->d_flag.p);
-  h->launches += 3;
+  h->launches += 2;
   {
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, node_size.as<int64_t>(), h->node_base.p, int(N + 1), s);
@@ -602,7 +795,7 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, ocnt.as<uint32_t>(), h->blk_cptr.p, int(nblk + 1), s));
     SYM_CHECK(cudaStreamSynchronize(s));
   }
-  SYM_CHECK(h->contrib.reserve(size_t(NC) + 1));  // +1: the kernel peeks one code ahead to prefetch
+  SYM_CHECK(h->contrib.reserve(size_t(NCt) + 1));  // +1: the kernel peeks one code ahead to prefetch
   SYM_CHECK(h->blk_meta.reserve(size_t(nblk) + 1));  // +1: the kernel loads one block ahead
   ordered_meta_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_order.p, h->blk_key.p,
                                                         h->node_blk_ptr.p, h->blk_off.p, h->node_len.p,
@@ -612,7 +805,7 @@ int32_t run_symbolic(Handle* h) {
   h->launches++;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
-  SYM_CHECK(cudaMemsetAsync(h->contrib.p + NC, 0, 4, s));
+  SYM_CHECK(cudaMemsetAsync(h->contrib.p + NCt, 0, 4, s));
   SYM_CHECK(cudaMemsetAsync(h->blk_meta.p + nblk, 0, sizeof(BlockMeta), s));
   // per-slab element lists; contrib codes are relabelled to slab-local element slots
   {
@@ -621,42 +814,42 @@ int32_t run_symbolic(Handle* h) {
     uint64_t* ekey_b = uniq.as<uint64_t>();
     uint32_t* epay_a = vals_a.as<uint32_t>();
     Tmp epay_b, eflag, euidx;
-    SYM_CHECK(epay_b.alloc(size_t(NC) * 4));
-    SYM_CHECK(eflag.alloc(size_t(NC) * 4));
-    SYM_CHECK(euidx.alloc(size_t(NC) * 4));
+    SYM_CHECK(epay_b.alloc(size_t(NCt) * 4));
+    SYM_CHECK(eflag.alloc(size_t(NCt) * 4));
+    SYM_CHECK(euidx.alloc(size_t(NCt) * 4));
     slab_elem_key_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_order.p, h->blk_key.p,
                                                            h->node_blk_ptr.p, h->blk_cptr.p, h->contrib.p, ekey_a,
                                                            epay_a);
     int ebits = 28;
     while ((uint64_t(1) << (ebits - 28)) < uint64_t(n_slabs) + 1) ++ebits;
     size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, ekey_a, ekey_b, epay_a, epay_b.as<uint32_t>(), int(NC), 0, ebits, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, ekey_a, ekey_b, epay_a, epay_b.as<uint32_t>(), int(NCt), 0, ebits, s);
     {
       Tmp t;
       SYM_CHECK(t.alloc(tb));
-      SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, ekey_a, ekey_b, epay_a, epay_b.as<uint32_t>(), int(NC), 0,
+      SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, ekey_a, ekey_b, epay_a, epay_b.as<uint32_t>(), int(NCt), 0,
                                                 ebits, s));
       SYM_CHECK(cudaStreamSynchronize(s));
     }
-    head_flag_kernel<<<div_up(NC, 256), 256, 0, s>>>(uint32_t(NC), ekey_b, eflag.as<uint32_t>());
+    head_flag_kernel<<<div_up(NCt, 256), 256, 0, s>>>(uint32_t(NCt), ekey_b, eflag.as<uint32_t>());
     tb = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, tb, eflag.as<uint32_t>(), euidx.as<uint32_t>(), int(NC), s);
+    cub::DeviceScan::InclusiveSum(nullptr, tb, eflag.as<uint32_t>(), euidx.as<uint32_t>(), int(NCt), s);
     {
       Tmp t;
       SYM_CHECK(t.alloc(tb));
-      SYM_CHECK(cub::DeviceScan::InclusiveSum(t.p, tb, eflag.as<uint32_t>(), euidx.as<uint32_t>(), int(NC), s));
+      SYM_CHECK(cub::DeviceScan::InclusiveSum(t.p, tb, eflag.as<uint32_t>(), euidx.as<uint32_t>(), int(NCt), s));
       SYM_CHECK(cudaStreamSynchronize(s));
     }
     uint32_t n_unique = 0;
-    SYM_CHECK(cudaMemcpy(&n_unique, euidx.as<uint32_t>() + (NC - 1), 4, cudaMemcpyDeviceToHost));
+    SYM_CHECK(cudaMemcpy(&n_unique, euidx.as<uint32_t>() + (NCt - 1), 4, cudaMemcpyDeviceToHost));
     SYM_CHECK(h->elist_compact.reserve(n_unique));
     SYM_CHECK(h->elist.reserve(size_t(n_slabs) * kElistStride));
     uint64_t* ukey = ekey_a;  // reuse: ekey_a is dead after the sort
-    elist_kernel<<<div_up(NC, 256), 256, 0, s>>>(uint32_t(NC), ekey_b, eflag.as<uint32_t>(), euidx.as<uint32_t>(),
+    elist_kernel<<<div_up(NCt, 256), 256, 0, s>>>(uint32_t(NCt), ekey_b, eflag.as<uint32_t>(), euidx.as<uint32_t>(),
                                                  ukey, h->elist_compact.p);
     slab_elist_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, n_unique, ukey, h->slabs.p,
                                                            uint32_t(kSlabSmemBytes), h->d_flag.p);
-    relabel_kernel<<<div_up(NC, 256), 256, 0, s>>>(uint32_t(NC), ekey_b, epay_b.as<uint32_t>(), euidx.as<uint32_t>(),
+    relabel_kernel<<<div_up(NCt, 256), 256, 0, s>>>(uint32_t(NCt), ekey_b, epay_b.as<uint32_t>(), euidx.as<uint32_t>(),
                                                    h->slabs.p, h->contrib.p);
     elist_table_kernel<<<div_up(uint64_t(n_slabs) * kElistStride, 256), 256, 0, s>>>(n_slabs, h->slabs.p,
                                                                                   h->elist_compact.p, h->elist.p);
@@ -677,7 +870,7 @@ int32_t run_symbolic(Handle* h) {
   h->slab_smem_bytes = (uint32_t(flags[2]) + 15) & ~15u;
 
   if (h->dist.enabled) {
-    int32_t st = dist_symbolic_exchange(h);
+    int32_t st = dist_finalize_plan(h, ranges);
     if (st) return st;
   }
   return 0;
