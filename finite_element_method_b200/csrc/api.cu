@@ -3,6 +3,7 @@
 // struct-of-arrays element data into HBM. All numerics run on the device (prep.cu, symbolic.cu,
 // numeric.cu); there is no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -123,6 +124,39 @@ int property_check(int family, const double* p /* props of one element */) {
 
 void invalidate(Handle* h) { h->symbolic_valid = false; }
 
+inline void sort4(uint32_t v[4]) {
+  auto cs = [&](int a, int b) {
+    if (v[a] > v[b]) std::swap(v[a], v[b]);
+  };
+  cs(0, 1); cs(2, 3); cs(0, 2); cs(1, 3); cs(1, 2);
+}
+
+// hash of an element's node-index set (order-insensitive): Truss/Beam::is_nodes_numbers_same accept
+// either orientation (structs/truss.rs:257-260), Plate::is_nodes_numbers_same any permutation
+// (structs/plate.rs:1114-1118)
+inline uint64_t nodeset_hash(int family, const uint32_t nd[4]) {
+  if (family != FEMGPU_PLATE) return mix64((uint64_t(std::min(nd[0], nd[1])) << 32) | std::max(nd[0], nd[1]));
+  uint32_t v[4] = {nd[0], nd[1], nd[2], nd[3]};
+  sort4(v);
+  return mix64(((uint64_t(v[0]) << 32) | v[1]) * 0x9E3779B97F4A7C15ull ^ ((uint64_t(v[2]) << 32) | v[3]));
+}
+
+inline bool nodeset_equal(int family, const uint32_t a[4], const uint32_t b[4]) {
+  if (family != FEMGPU_PLATE)
+    return (a[0] == b[0] && a[1] == b[1]) || (a[0] == b[1] && a[1] == b[0]);
+  uint32_t x[4] = {a[0], a[1], a[2], a[3]}, y[4] = {b[0], b[1], b[2], b[3]};
+  sort4(x);
+  sort4(y);
+  return x[0] == y[0] && x[1] == y[1] && x[2] == y[2] && x[3] == y[3];
+}
+
+inline uint64_t xyz_hash(double x, double y, double z) {
+  uint64_t h = mix64(bits_of(x));
+  h = mix64(h ^ (bits_of(y) + 0x9E3779B97F4A7C15ull));
+  h = mix64(h ^ (bits_of(z) + 0xC2B2AE3D27D4EB4Full));
+  return h;
+}
+
 // Drop every element inserted at or after element `index` of `family` (global insertion order).
 void rollback_to(Handle* h, int family, size_t index) {
   size_t keep[kFamilies] = {0, 0, 0};
@@ -149,17 +183,9 @@ void rollback_to(Handle* h, int family, size_t index) {
     if (keep[f] >= n) continue;
     for (size_t i = keep[f]; i < n; ++i) {
       fh.by_number.erase(fh.number[i]);
-      if (f == FEMGPU_PLATE) {
-        PlateKey k{{fh.conn[0][i], fh.conn[1][i], fh.conn[2][i], fh.conn[3][i]}};
-        std::sort(k.n, k.n + 4);
-        auto it = h->plate_seen.find(k);
-        if (it != h->plate_seen.end() && it->second == i) h->plate_seen.erase(it);
-      } else {
-        uint32_t a = fh.conn[0][i], b = fh.conn[1][i];
-        uint64_t k = (uint64_t(std::min(a, b)) << 32) | std::max(a, b);
-        auto it = h->pair_seen[f].find(k);
-        if (it != h->pair_seen[f].end() && it->second == i) h->pair_seen[f].erase(it);
-      }
+      uint32_t nd[4] = {fh.conn[0][i], fh.conn[1][i], f == FEMGPU_PLATE ? fh.conn[2][i] : 0u,
+                        f == FEMGPU_PLATE ? fh.conn[3][i] : 0u};
+      h->nodeset_seen[f].erase(nodeset_hash(f, nd), uint32_t(i), [](uint32_t) { return true; });
     }
     fh.number.resize(keep[f]);
     for (int c = 0; c < kNodesPerElem[f]; ++c) {
@@ -218,6 +244,10 @@ int32_t fail_after_prefix(Handle* h, int32_t code, const std::string& text) {
   return h->fail(code, text);
 }
 
+// Batched FEM::add_truss / add_beam / add_plate: every check of the reference, in the reference's
+// order per element (node 1..k exist -> element number unused -> node set unused -> property
+// signs), evaluated for the whole batch on all host cores; the batch is accepted up to the first
+// failing element.
 int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
                      const uint32_t* const* nodes, const double* const* props) {
   if (!h) return FEMGPU_ERR_USAGE;
@@ -228,118 +258,173 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
   const size_t start = fh.size();
   if (start + n >= (1u << 26))
     return h->fail(FEMGPU_ERR_LIMIT, "more than 2^26 elements of one family on one device");
-  // reserve
-  fh.number.reserve(start + n);
-  for (int c = 0; c < nn; ++c) {
-    fh.conn[c].reserve(start + n);
-    fh.conn_number[c].reserve(start + n);
-  }
-  for (int p = 0; p < np; ++p) fh.props[p].reserve(start + n);
-  fh.cbase.reserve(start + n);
 
-  size_t accepted = 0;
-  int32_t status = 0;
-  std::string text;
-  for (size_t e = 0; e < n; ++e) {
-    uint32_t idx[4];
-    // check_node_exist, in argument order (methods_for_truss_data_handle.rs:58-59 and siblings)
-    bool ok = true;
-    for (int c = 0; c < nn && ok; ++c) {
-      if (!h->node_by_number.find(nodes[c][e], &idx[c])) {
-        status = FEMGPU_E_NODE_NOT_EXIST;
-        text = "Node with number " + std::to_string(nodes[c][e]) + " does not exist!";
-        ok = false;
+  // A. node numbers -> indices (check_node_exist, argument order), in parallel
+  std::vector<uint32_t> idx[4];
+  for (int c = 0; c < nn; ++c) idx[c].resize(n);
+  std::atomic<size_t> i_node(n);
+  parallel_chunks(n, 8192, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      bool ok = true;
+      for (int c = 0; c < nn; ++c) {
+        uint32_t v = 0;
+        if (!h->node_by_number.find(nodes[c][i], &v)) ok = false;
+        idx[c][i] = v;
+      }
+      if (!ok) {
+        size_t cur = i_node.load();
+        while (i < cur && !i_node.compare_exchange_weak(cur, i)) {
+        }
+        return;  // later elements of this chunk cannot be the first failure
       }
     }
-    if (!ok) break;
-    // check_*_data: duplicate number, then same node set (:32-47)
+  });
+  size_t limit = i_node.load();  // elements at or after this index are never accepted
+
+  // D. property sign checks of *::create, in parallel (geometry checks run on the device)
+  std::atomic<size_t> i_prop(limit);
+  parallel_chunks(limit, 8192, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      double pv[11];
+      for (int p = 0; p < np; ++p) pv[p] = props[p] ? props[p][i] : NAN;
+      if (property_check(family, pv)) {
+        size_t cur = i_prop.load();
+        while (i < cur && !i_prop.compare_exchange_weak(cur, i)) {
+        }
+        return;
+      }
+    }
+  });
+  // a property failure at i still lets the number / node-set checks of element i run first
+  size_t scan_end = std::min(limit, i_prop.load() + 1);
+
+  // B. duplicate element numbers (sequential: dense table updates are a few ns each)
+  size_t i_num = scan_end, inserted_numbers = 0;
+  for (size_t i = 0; i < scan_end; ++i) {
     uint32_t dummy;
-    if (fh.by_number.find(number[e], &dummy)) {
+    if (fh.by_number.find(number[i], &dummy)) {
+      i_num = i;
+      break;
+    }
+    fh.by_number.insert(number[i], uint32_t(start + i));
+    ++inserted_numbers;
+  }
+  scan_end = std::min(scan_end, i_num + 1);
+
+  // C. duplicate node sets, sharded hash index filled by all cores
+  bool degenerate = false;
+  std::vector<uint64_t> hashes(scan_end);
+  parallel_chunks(scan_end, 8192, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      uint32_t nd[4] = {idx[0][i], idx[1][i], nn == 4 ? idx[2][i] : 0u, nn == 4 ? idx[3][i] : 0u};
+      hashes[i] = nodeset_hash(family, nd);
+    }
+  });
+  auto node_set_of = [&](uint32_t id, uint32_t out[4]) {
+    if (id >= start) {
+      size_t i = id - start;
+      for (int c = 0; c < 4; ++c) out[c] = c < nn ? idx[c][i] : 0u;
+    } else {
+      for (int c = 0; c < 4; ++c) out[c] = c < nn ? fh.conn[c][id] : 0u;
+    }
+  };
+  size_t i_set = h->nodeset_seen[family].insert_batch(
+      hashes.data(), scan_end, uint32_t(start), [&](uint32_t existing, size_t i) {
+        uint32_t a[4], b[4];
+        node_set_of(existing, a);
+        node_set_of(uint32_t(start + i), b);
+        return nodeset_equal(family, a, b);
+      });
+  if (family == FEMGPU_PLATE) {
+    // Plate::is_nodes_numbers_same is a subset test; with repeated node numbers in the new element
+    // that is not set equality, so such (degenerate) elements are compared by a scan.
+    for (size_t i = 0; i < std::min(scan_end, i_set + 1) && !degenerate; ++i) {
+      uint32_t v[4] = {idx[0][i], idx[1][i], idx[2][i], idx[3][i]};
+      sort4(v);
+      if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) {
+        degenerate = true;
+        for (size_t j = 0; j < start + i; ++j) {
+          uint32_t o[4];
+          node_set_of(uint32_t(j), o);
+          bool all = true;
+          for (int c = 0; c < 4 && all; ++c) all = (v[c] == o[0] || v[c] == o[1] || v[c] == o[2] || v[c] == o[3]);
+          if (all) {
+            i_set = std::min(i_set, i);
+            break;
+          }
+        }
+      }
+    }
+  }
+
+  // first failing element and, for it, the first failing check in the reference's order
+  size_t e_star = std::min(std::min(limit, i_prop.load()), std::min(i_num, i_set));
+  int32_t status = 0;
+  std::string text;
+  if (e_star < n) {
+    const size_t e = e_star;
+    if (e == i_node.load()) {
+      for (int c = 0; c < nn; ++c) {
+        uint32_t v;
+        if (!h->node_by_number.find(nodes[c][e], &v)) {
+          status = FEMGPU_E_NODE_NOT_EXIST;
+          text = "Node with number " + std::to_string(nodes[c][e]) + " does not exist!";
+          break;
+        }
+      }
+    } else if (e == i_num) {
       status = FEMGPU_E_ELEMENT_NUMBER_EXISTS;
       text = std::string(family_name(family)) + " element with number " + std::to_string(number[e]) +
              " already exists!";
-      break;
-    }
-    const uint32_t self = uint32_t(start + e);
-    if (family == FEMGPU_PLATE) {
-      PlateKey k{{idx[0], idx[1], idx[2], idx[3]}};
-      std::sort(k.n, k.n + 4);
-      bool distinct = k.n[0] != k.n[1] && k.n[1] != k.n[2] && k.n[2] != k.n[3];
-      bool dup = false;
-      if (distinct) {
-        dup = !h->plate_seen.emplace(k, self).second;
-      } else {
-        // Plate::is_nodes_numbers_same (structs/plate.rs:1114-1118) is a subset test; with repeated
-        // node numbers that is not set equality, so fall back to a scan (degenerate input only).
-        for (size_t i = 0; i < fh.size() && !dup; ++i) {
-          bool all = true;
-          for (int c = 0; c < 4 && all; ++c) {
-            bool in = false;
-            for (int d = 0; d < 4; ++d) in |= fh.conn[d][i] == idx[c];
-            all = in;
-          }
-          dup = all;
-        }
-      }
-      if (dup) {
-        status = FEMGPU_E_ELEMENT_SAME_NODES;
+    } else if (e == i_set) {
+      status = FEMGPU_E_ELEMENT_SAME_NODES;
+      if (family == FEMGPU_PLATE)
         text = "Plate element with nodes numbers [" + std::to_string(nodes[0][e]) + ", " +
                std::to_string(nodes[1][e]) + ", " + std::to_string(nodes[2][e]) + ", " +
                std::to_string(nodes[3][e]) + "] already exists!";
-        break;
-      }
-    } else {
-      uint64_t k = (uint64_t(std::min(idx[0], idx[1])) << 32) | std::max(idx[0], idx[1]);
-      if (!h->pair_seen[family].emplace(k, self).second) {
-        status = FEMGPU_E_ELEMENT_SAME_NODES;
-        text = std::string(family_name(family)) + " element with node number " +
-               std::to_string(nodes[0][e]) + " and " + std::to_string(nodes[1][e]) + " already exists!";
-        break;
-      }
+      else
+        text = std::string(family_name(family)) + " element with node number " + std::to_string(nodes[0][e]) +
+               " and " + std::to_string(nodes[1][e]) + " already exists!";
     }
-    // property sign checks of *::create (geometry checks run on the device)
-    double pv[11];
-    for (int p = 0; p < np; ++p) pv[p] = props[p] ? props[p][e] : NAN;
-    fh.number.push_back(number[e]);
-    for (int c = 0; c < nn; ++c) {
-      fh.conn[c].push_back(idx[c]);
-      fh.conn_number[c].push_back(nodes[c][e]);
-    }
-    for (int p = 0; p < np; ++p) fh.props[p].push_back(pv[p]);
-    fh.cbase.push_back(h->n_contrib);
-    int pc = property_check(family, pv);
-    if (pc) {
-      status = pc;
-      text = element_error_text(h, family, fh.size() - 1, pc);
-      // undo the tentative push
-      if (family == FEMGPU_PLATE) {
-        PlateKey k{{idx[0], idx[1], idx[2], idx[3]}};
-        std::sort(k.n, k.n + 4);
-        auto it = h->plate_seen.find(k);
-        if (it != h->plate_seen.end() && it->second == self) h->plate_seen.erase(it);
-      } else {
-        uint64_t k = (uint64_t(std::min(idx[0], idx[1])) << 32) | std::max(idx[0], idx[1]);
-        h->pair_seen[family].erase(k);
-      }
-      fh.number.pop_back();
-      for (int c = 0; c < nn; ++c) {
-        fh.conn[c].pop_back();
-        fh.conn_number[c].pop_back();
-      }
-      for (int p = 0; p < np; ++p) fh.props[p].pop_back();
-      fh.cbase.pop_back();
-      break;
-    }
-    fh.by_number.insert(number[e], self);
-    h->n_contrib += kPairsPerElem[family];
-    ++accepted;
   }
+  // undo index entries of rejected elements
+  const size_t accepted = e_star;
+  for (size_t i = accepted; i < inserted_numbers; ++i) fh.by_number.erase(number[i]);
+  if (accepted < scan_end) h->nodeset_seen[family].erase_batch(hashes.data(), accepted, scan_end, uint32_t(start));
+
+  // append the accepted prefix (bulk copies)
+  fh.number.insert(fh.number.end(), number, number + accepted);
+  for (int c = 0; c < nn; ++c) {
+    fh.conn[c].insert(fh.conn[c].end(), idx[c].begin(), idx[c].begin() + accepted);
+    fh.conn_number[c].insert(fh.conn_number[c].end(), nodes[c], nodes[c] + accepted);
+  }
+  for (int p = 0; p < np; ++p) {
+    if (props[p])
+      fh.props[p].insert(fh.props[p].end(), props[p], props[p] + accepted);
+    else
+      fh.props[p].insert(fh.props[p].end(), accepted, NAN);
+  }
+  fh.cbase.resize(start + accepted);
+  for (size_t i = 0; i < accepted; ++i) fh.cbase[start + i] = h->n_contrib + int64_t(i) * kPairsPerElem[family];
+  h->n_contrib += int64_t(accepted) * kPairsPerElem[family];
   if (accepted) {
     if (!h->journal.empty() && h->journal.back().first == family)
       h->journal.back().second += accepted;
     else
       h->journal.emplace_back(family, accepted);
     invalidate(h);
+  }
+  if (e_star < n && !status) {
+    // property failure: format the message from the caller's arrays (the element was not stored)
+    double pv[11];
+    for (int p = 0; p < np; ++p) pv[p] = props[p] ? props[p][e_star] : NAN;
+    status = property_check(family, pv);
+    // element_error_text reads the host arrays: stage the element temporarily
+    fh.number.push_back(number[e_star]);
+    for (int p = 0; p < np; ++p) fh.props[p].push_back(pv[p]);
+    text = element_error_text(h, family, fh.number.size() - 1, status);
+    fh.number.pop_back();
+    for (int p = 0; p < np; ++p) fh.props[p].pop_back();
   }
   if (status) return fail_after_prefix(h, status, text);
   return 0;
@@ -467,7 +552,7 @@ int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
   h->node_by_number.clear(); h->node_by_xyz.clear();
   h->nodes_uploaded = 0;
   for (auto& f : h->fh) f = FamilyHost();
-  h->pair_seen[0].clear(); h->pair_seen[1].clear(); h->plate_seen.clear();
+  for (auto& x : h->nodeset_seen) x.clear();
   h->n_contrib = 0;
   h->journal.clear();
   h->symbolic_valid = false;
@@ -502,35 +587,57 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
                          const double* y, const double* z) {
   if (!h) return FEMGPU_ERR_USAGE;
   if (n && (!number || !x || !y || !z)) return h->fail(FEMGPU_ERR_USAGE, "null node array");
-  h->node_number.reserve(h->n_nodes() + n);
-  h->nx.reserve(h->n_nodes() + n);
-  h->ny.reserve(h->n_nodes() + n);
-  h->nz.reserve(h->n_nodes() + n);
-  for (size_t i = 0; i < n; ++i) {
-    size_t node_index = h->n_nodes();
-    // methods_for_node_data_handle.rs:42-64: limit, then number, (index,) coordinates
-    if (h->nodes_number == 0 || node_index > size_t(h->nodes_number) - 1)
+  if (n == 0) return 0;
+  const size_t n0 = h->n_nodes();
+  // methods_for_node_data_handle.rs:42-64, per node: limit, then number, (index,) coordinates
+  const size_t room = h->nodes_number > n0 ? size_t(h->nodes_number) - n0 : 0;
+  const size_t i_limit = std::min(n, room);
+  size_t scan_end = std::min(n, i_limit + 0);
+  // duplicate numbers (sequential dense-table pass)
+  size_t i_num = scan_end, inserted = 0;
+  for (size_t i = 0; i < scan_end; ++i) {
+    uint32_t dummy;
+    if (h->node_by_number.find(number[i], &dummy)) {
+      i_num = i;
+      break;
+    }
+    h->node_by_number.insert(number[i], uint32_t(n0 + i));
+    ++inserted;
+  }
+  scan_end = std::min(scan_end, i_num + 1);
+  // duplicate coordinates: sharded hash index, all cores (NaN never compares equal)
+  std::vector<uint64_t> hashes(scan_end);
+  parallel_chunks(scan_end, 8192, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) hashes[i] = xyz_hash(x[i], y[i], z[i]);
+  });
+  size_t i_xyz = h->node_by_xyz.insert_batch(hashes.data(), scan_end, uint32_t(n0), [&](uint32_t existing, size_t i) {
+    double ex, ey, ez;
+    if (existing >= n0) {
+      ex = x[existing - n0]; ey = y[existing - n0]; ez = z[existing - n0];
+    } else {
+      ex = h->nx[existing]; ey = h->ny[existing]; ez = h->nz[existing];
+    }
+    return ex == x[i] && ey == y[i] && ez == z[i];
+  });
+  const size_t accepted = std::min(std::min(i_limit, i_num), i_xyz);
+  for (size_t i = accepted; i < inserted; ++i) h->node_by_number.erase(number[i]);
+  if (accepted < scan_end) h->node_by_xyz.erase_batch(hashes.data(), accepted, scan_end, uint32_t(n0));
+  h->node_number.insert(h->node_number.end(), number, number + accepted);
+  h->nx.insert(h->nx.end(), x, x + accepted);
+  h->ny.insert(h->ny.end(), y, y + accepted);
+  h->nz.insert(h->nz.end(), z, z + accepted);
+  if (accepted) invalidate(h);
+  if (accepted < n) {
+    const size_t e = accepted;
+    if (e == i_limit)
       return h->fail(FEMGPU_E_NODE_LIMIT,
                      "Nodes number could not be greater than " + std::to_string(h->nodes_number) + "!");
-    uint32_t dummy;
-    if (h->node_by_number.find(number[i], &dummy))
-      return h->fail(FEMGPU_E_NODE_NUMBER_EXISTS,
-                     "Node with number " + std::to_string(number[i]) + " already exists!");
-    bool has_nan = std::isnan(x[i]) || std::isnan(y[i]) || std::isnan(z[i]);
-    if (!has_nan) {
-      NodeKey k{bits_of(x[i]), bits_of(y[i]), bits_of(z[i])};
-      if (!h->node_by_xyz.emplace(k, uint32_t(node_index)).second)
-        return h->fail(FEMGPU_E_NODE_COORDINATES_EXIST,
-                       "Node with coordinates x: " + rust_debug_f64(x[i]) + ", y: " + rust_debug_f64(y[i]) +
-                           ", z: " + rust_debug_f64(z[i]) + " already exists!");
-    }
-    h->node_by_number.insert(number[i], uint32_t(node_index));
-    h->node_number.push_back(number[i]);
-    h->nx.push_back(x[i]);
-    h->ny.push_back(y[i]);
-    h->nz.push_back(z[i]);
+    if (e == i_num)
+      return h->fail(FEMGPU_E_NODE_NUMBER_EXISTS, "Node with number " + std::to_string(number[e]) + " already exists!");
+    return h->fail(FEMGPU_E_NODE_COORDINATES_EXIST,
+                   "Node with coordinates x: " + rust_debug_f64(x[e]) + ", y: " + rust_debug_f64(y[e]) +
+                       ", z: " + rust_debug_f64(z[e]) + " already exists!");
   }
-  if (n) invalidate(h);
   return 0;
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/femgpu.h"
+#include "host_index.hpp"
 
 namespace femgpu {
 
@@ -228,15 +229,14 @@ struct Handle {
   std::vector<uint32_t> node_number;
   std::vector<double> nx, ny, nz;
   NumberMap node_by_number;
-  std::unordered_map<NodeKey, uint32_t, NodeKeyHash> node_by_xyz;
+  ShardedIndex node_by_xyz;  // hash of the coordinate bit patterns -> node index
   DevBuf<double> d_x, d_y, d_z;
   size_t nodes_uploaded = 0;
 
   // ---- elements ----
   FamilyHost fh[kFamilies];
   FamilyDev fd[kFamilies];
-  std::unordered_map<uint64_t, uint32_t> pair_seen[2];  // truss, beam: sorted node-index pair
-  std::unordered_map<PlateKey, uint32_t, PlateKeyHash> plate_seen;
+  ShardedIndex nodeset_seen[kFamilies];  // per family: hash of the sorted node-index set -> element
   int64_t n_contrib = 0;  // running contribution counter (global insertion order)
   // insertion journal for prefix rollback: (family, count) runs in global order
   std::vector<std::pair<int, size_t>> journal;

@@ -107,3 +107,47 @@ def test_compute_calls_fail_loudly_without_device():
         with pytest.raises(FemError) as e:
             fn()
         assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+
+
+def test_large_batches_take_the_parallel_path_with_identical_semantics():
+    """>= 32768 keys are indexed by all host cores; the first failing element must still be the one a
+    sequential loop over the reference would hit first."""
+    n = 60000
+    f = staged(n + 5)
+    x = np.arange(n, dtype=np.float64)
+    f.add_nodes(np.arange(1, n + 1), x, np.zeros(n), np.zeros(n))
+    assert f.counts()[0] == n
+    # duplicate coordinates in the middle of a big node batch: prefix kept
+    f2 = staged(n + 5)
+    x2 = x.copy(); x2[41234] = x2[17]
+    raises(4, "Node with coordinates x: 17.0, y: 0.0, z: 0.0 already exists!", f2.add_nodes,
+           np.arange(1, n + 1), x2, np.zeros(n), np.zeros(n))
+    assert f2.counts()[0] == 41234
+    # chain of trusses i -> i+1; element 50000 repeats the node pair of element 123 (reversed)
+    a = np.arange(1, n, dtype=np.uint32); b = a + 1
+    a2, b2 = a.copy(), b.copy()
+    a2[50000], b2[50000] = b[123], a[123]
+    ne = len(a)
+    raises(11, f"Truss element with node number {b[123]} and {a[123]} already exists!", f.add_trusses,
+           np.arange(1, ne + 1), a2, b2, np.ones(ne), np.ones(ne))
+    assert f.counts()[1] == 50000
+    # the rejected tail left no trace: the same numbers / pairs can be added now
+    f.add_trusses(np.arange(50001, ne + 1), a[50000:], b[50000:], np.ones(ne - 50000), np.ones(ne - 50000))
+    assert f.counts()[1] == ne
+    # several failures in one batch: the earliest element wins, and for one element the reference's
+    # check order wins (number before node set before property)
+    f3 = staged(n + 5)
+    f3.add_nodes(np.arange(1, n + 1), x, np.zeros(n), np.zeros(n))
+    num = np.arange(1, ne + 1); num[40000] = 7            # duplicate number at 40000
+    E = np.ones(ne); E[40000] = -1.0; E[45000] = -1.0      # property failures at 40000 and 45000
+    raises(10, "Truss element with number 7 already exists!", f3.add_trusses, num, a, b, E, np.ones(ne))
+    assert f3.counts()[1] == 40000
+
+
+def test_degenerate_plate_uses_subset_rule():
+    f = staged()
+    f.add_nodes([1, 2, 3, 4], [0, 1, 1, 0], [0, 0, 1, 1], [0, 0, 0, 0])
+    f.add_plates([1], [3], [4], [1], [2], [2e11], [0.3], [0.01], [5 / 6])
+    # plate.rs:1114-1118: every node of the new element belongs to plate 1 -> "same nodes"
+    raises(11, "Plate element with nodes numbers [1, 1, 2, 3] already exists!", f.add_plates, [2], [1], [1], [2], [3],
+           [2e11], [0.3], [0.01], [5 / 6])
