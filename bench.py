@@ -322,23 +322,34 @@ def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, 
             fem.dist_init(rank, world, u[0])
             fem.dist_set_ownership(begin, end)
         fem.load_mesh(local)
+        t1 = time.perf_counter()
         n_rows, nnz = fem.symbolic()
+        t2 = time.perf_counter()
         fem.numeric()
+        fem.synchronize()
+        t3 = time.perf_counter()
         if out is None or len(out) != nnz:
+            t_pin = time.perf_counter()
             out = torch.empty(nnz, dtype=torch.float64).pin_memory().numpy()
+            t0 += time.perf_counter() - t_pin      # one-time pinned allocation is not part of a step
+            t1 += time.perf_counter() - t_pin; t2 += time.perf_counter() - t_pin; t3 += time.perf_counter() - t_pin
         fem.csr(values_only=True, out=out)
-        dt = time.perf_counter() - t0
-        d2h = out.nbytes
+        t4 = time.perf_counter()
         fem.close()
+        t5 = time.perf_counter()
+        dt = t5 - t0
+        d2h = out.nbytes
         if it > 0:
             times.append(dt)
+            phases = {"add_nodes_add_elements_s": t1 - t0, "symbolic_s": t2 - t1, "numeric_s": t3 - t2,
+                      "csr_values_d2h_s": t4 - t3, "destroy_s": t5 - t4}
     sec = float(np.mean(times))
     if dist is not None:
         t = torch.tensor([sec], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     return {"value": n_el_total / sec, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec, "steps": steps,
+            "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec, "steps": steps, "phases_last_step": phases,
             "includes": "femgpu_create, add_nodes/add_* host validation + H2D, symbolic pass, numeric pass, D2H of CSR values"}
 
 

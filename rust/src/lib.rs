@@ -1,0 +1,106 @@
+//! `FEM` with the method signatures of `finite_element_method::FEM<f64>` for the stiffness-assembly
+//! path (fem.rs:34,155,171-202; methods_for_{node,truss,beam,plate}_data_handle.rs), backed by the
+//! femgpu C ABI (include/femgpu.h). `Result<(), String>` carries the reference's own messages.
+//! NOT compiled here (no Rust toolchain in the build image).
+use std::ffi::CStr;
+use std::os::raw::c_char;
+
+#[repr(C)]
+pub struct FemGpu { _private: [u8; 0] }
+
+extern "C" {
+    fn femgpu_create(out: *mut *mut FemGpu, rel_tol: f64, abs_tol: f64, nodes_number: u32, device: i32) -> i32;
+    fn femgpu_reset(h: *mut FemGpu, nodes_number: u32) -> i32;
+    fn femgpu_destroy(h: *mut FemGpu);
+    fn femgpu_last_error(h: *const FemGpu) -> *const c_char;
+    fn femgpu_add_nodes(h: *mut FemGpu, n: usize, number: *const u32, x: *const f64, y: *const f64, z: *const f64) -> i32;
+    fn femgpu_add_truss(h: *mut FemGpu, n: usize, number: *const u32, n1: *const u32, n2: *const u32,
+                        e: *const f64, a: *const f64, a2: *const f64) -> i32;
+    fn femgpu_add_beam(h: *mut FemGpu, n: usize, number: *const u32, n1: *const u32, n2: *const u32,
+                       e: *const f64, nu: *const f64, a: *const f64, i11: *const f64, i22: *const f64,
+                       i12: *const f64, it: *const f64, ks: *const f64, axis1: *const f64) -> i32;
+    fn femgpu_add_plate(h: *mut FemGpu, n: usize, number: *const u32, n1: *const u32, n2: *const u32,
+                        n3: *const u32, n4: *const u32, e: *const f64, nu: *const f64, t: *const f64,
+                        ks: *const f64) -> i32;
+    fn femgpu_validate(h: *mut FemGpu, family: *mut i32, number: *mut u32, code: *mut i32) -> i32;
+    fn femgpu_assemble(h: *mut FemGpu, n_rows: *mut i64, nnz: *mut i64) -> i32;
+    fn femgpu_get_csr(h: *mut FemGpu, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
+    fn femgpu_rotation_elements(h: *mut FemGpu, family: i32, number: u32, out: *mut f64) -> i32;
+}
+
+pub struct FEM { h: *mut FemGpu }
+
+impl FEM {
+    fn check(&self, st: i32) -> Result<(), String> {
+        if st == 0 { return Ok(()); }
+        Err(unsafe { CStr::from_ptr(femgpu_last_error(self.h)) }.to_string_lossy().into_owned())
+    }
+    /// fem.rs:34
+    pub fn create(rel_tol: f64, abs_tol: f64, nodes_number: u32) -> Self {
+        let mut h = std::ptr::null_mut();
+        let st = unsafe { femgpu_create(&mut h, rel_tol, abs_tol, nodes_number, 0) };
+        assert!(st == 0, "femgpu_create failed: no CUDA device (there is no CPU fallback)");
+        FEM { h }
+    }
+    /// fem.rs:155
+    pub fn reset(&mut self, nodes_number: u32) { unsafe { femgpu_reset(self.h, nodes_number); } }
+    /// methods_for_node_data_handle.rs:66
+    pub fn add_node(&mut self, number: u32, x: f64, y: f64, z: f64) -> Result<(), String> {
+        self.check(unsafe { femgpu_add_nodes(self.h, 1, &number, &x, &y, &z) })
+    }
+    /// methods_for_truss_data_handle.rs:49
+    pub fn add_truss(&mut self, number: u32, node_1_number: u32, node_2_number: u32, young_modulus: f64,
+                     area: f64, optional_area_2: Option<f64>) -> Result<(), String> {
+        let a2 = optional_area_2.unwrap_or(f64::NAN);
+        self.check(unsafe { femgpu_add_truss(self.h, 1, &number, &node_1_number, &node_2_number,
+                                             &young_modulus, &area, &a2) })?;
+        self.check(unsafe { femgpu_validate(self.h, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })
+    }
+    /// methods_for_beam_data_handle.rs:49
+    #[allow(clippy::too_many_arguments)]
+    pub fn add_beam(&mut self, number: u32, node_1_number: u32, node_2_number: u32, young_modulus: f64,
+                    poisson_ratio: f64, area: f64, i11: f64, i22: f64, i12: f64, it: f64, shear_factor: f64,
+                    local_axis_1_direction: [f64; 3]) -> Result<(), String> {
+        self.check(unsafe { femgpu_add_beam(self.h, 1, &number, &node_1_number, &node_2_number, &young_modulus,
+                                            &poisson_ratio, &area, &i11, &i22, &i12, &it, &shear_factor,
+                                            local_axis_1_direction.as_ptr()) })?;
+        self.check(unsafe { femgpu_validate(self.h, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })
+    }
+    /// methods_for_plate_data_handle.rs:62
+    #[allow(clippy::too_many_arguments)]
+    pub fn add_plate(&mut self, number: u32, node_1_number: u32, node_2_number: u32, node_3_number: u32,
+                     node_4_number: u32, young_modulus: f64, poisson_ratio: f64, thickness: f64,
+                     shear_factor: f64) -> Result<(), String> {
+        self.check(unsafe { femgpu_add_plate(self.h, 1, &number, &node_1_number, &node_2_number, &node_3_number,
+                                             &node_4_number, &young_modulus, &poisson_ratio, &thickness,
+                                             &shear_factor) })?;
+        self.check(unsafe { femgpu_validate(self.h, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })
+    }
+    /// Bulk load: struct-of-arrays slices, prefix-atomic (see include/femgpu.h).
+    pub fn add_plates(&mut self, number: &[u32], n1: &[u32], n2: &[u32], n3: &[u32], n4: &[u32], e: &[f64],
+                      nu: &[f64], t: &[f64], ks: &[f64]) -> Result<(), String> {
+        self.check(unsafe { femgpu_add_plate(self.h, number.len(), number.as_ptr(), n1.as_ptr(), n2.as_ptr(),
+                                             n3.as_ptr(), n4.as_ptr(), e.as_ptr(), nu.as_ptr(), t.as_ptr(), ks.as_ptr()) })
+    }
+    /// fem.rs:171 / :182 / :193 (family 0 = truss, 1 = beam, 2 = plate)
+    pub fn get_rotation_matrix_elements(&self, family: i32, number: u32) -> Result<[f64; 9], String> {
+        let mut out = [0f64; 9];
+        self.check(unsafe { femgpu_rotation_elements(self.h, family, number, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+    /// The assembled global stiffness matrix as CSR on the structural pattern (what
+    /// `self.stiffness_matrix` holds in the reference, fem.rs:17). Stored zeros == absent entries.
+    pub fn assemble_csr(&mut self) -> Result<(Vec<i64>, Vec<i32>, Vec<f64>), String> {
+        let (mut n_rows, mut nnz) = (0i64, 0i64);
+        self.check(unsafe { femgpu_assemble(self.h, &mut n_rows, &mut nnz) })?;
+        let mut rp = vec![0i64; n_rows as usize + 1];
+        let mut ci = vec![0i32; nnz as usize];
+        let mut v = vec![0f64; nnz as usize];
+        self.check(unsafe { femgpu_get_csr(self.h, rp.as_mut_ptr(), ci.as_mut_ptr(), v.as_mut_ptr()) })?;
+        Ok((rp, ci, v))
+    }
+}
+
+impl Drop for FEM {
+    fn drop(&mut self) { unsafe { femgpu_destroy(self.h) } }
+}
