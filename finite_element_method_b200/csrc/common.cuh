@@ -189,7 +189,8 @@ struct SlabDesc {
   uint32_t val_count;   // values in the slab
   uint32_t blk_begin;   // first block (thread order)
   uint32_t blk_count;
-  uint32_t flags;       // bit 0: too large for shared memory -> write straight to global
+  uint32_t flags;       // bit 0: too large for shared memory -> write straight to global;
+                        // staged slabs: trusses << 8 | beams << 20 in the element list
   uint32_t el_begin;    // the slab's distinct elements (elist[]): their records are staged in
   uint32_t el_count;    // shared memory once per CTA; contrib[] codes index into this list
 };
@@ -314,7 +315,12 @@ int32_t dist_exchange_8(Handle* h, const void* send, const int64_t* send_offs, c
 
 constexpr int kAsmThreads = 32;            // threads per assembly CTA: one warp, no block barriers
 constexpr int kSlabQuota = 72;             // node-pair blocks a slab aims for (8 plate-grid nodes)
-constexpr int kSlabSmemBytes = 48 * 1024;  // staging capacity (slab image + element records)
+constexpr int kSlabSmemBytes = 64 * 1024;  // staging capacity (slab image + element records)
+// Record slots in the CTA's shared-memory record area, in doubles. Odd multiples of 16 bytes so that
+// lanes reading the same field of different elements spread over the banks.
+constexpr int kTrussSlotDoubles = 6;       // 4 used
+constexpr int kBeamSlotDoubles = 18;       // 16 used
+constexpr int kPlateSlotDoubles = 66;      // 64 used: the plate's shared form (element_math.cuh)
 constexpr int kElistStride = 64;           // element slots per slab in the dense elist table; a slab
                                            // touching more elements takes the unstaged path
 constexpr int kRecStride = 20;             // doubles per staged element record (plate: 16 + 4)

@@ -601,4 +601,149 @@ __device__ __forceinline__ void plate_block(const double* __restrict__ rec,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Plate, shared form. Everything of a plate element that does not depend on the node pair
+// (Jacobians, 1/det, adj(J)*dh of the four nodes at the four Gauss points, the assumed-strain
+// shear sums, material constants) is evaluated ONCE per element per CTA into a 64-double record in
+// shared memory (plate_shared_record); the node-pair evaluator (plate_block_shared) then only does
+// the pair-specific part. Same quadrature and same f32-rounded abscissa as plate_block above.
+//
+// layout (doubles):
+//    0..31  n[ip][node] = adj(J_ip) * [dh/dr; dh/ds]   as (x, y) pairs
+//   32..35  1/det J_ip
+//   36..38  Cs * sum_ip (1+ea s)(1+eb s) * gamma_rz^2 det  for (ea,eb) = (+,+), (-,-), (+,-)
+//   39..41  same for gamma_sz with (xa,xb) and r
+//   42..49  0.25 * edge vectors e12, e43, e14, e23 (x, y)
+//   50..53  Cm, Cb, nu, (1-nu)/2
+//   54..62  Q (row major)
+//   63      1.0 when Q == I exactly
+// ------------------------------------------------------------------------------------------
+constexpr int kPlateSharedDoubles = 64;
+
+// raw = the prep kernel's record: Q[9], x1, y1, x2, y2, x4, y4, identity flag, Cm, Cb, Cs, nu
+__device__ __forceinline__ void plate_shared_record(const double* __restrict__ raw,
+                                                    double* __restrict__ S) {
+  const double x1 = raw[9], y1 = raw[10], x2 = raw[11], y2 = raw[12], x4 = raw[13], y4 = raw[14];
+  const double Cm = raw[16], Cb = raw[17], Cs = raw[18], nu = raw[19];
+  const double g = 0.57735027779281512;  // sqrt((double)(1.0f / 3.0f)), plate.rs:1066-1091
+  const double e12x = x1 - x2, e12y = y1 - y2;  // edge 1-2 (s = +1)
+  const double e43x = x4, e43y = y4;            // edge 4-3 (s = -1), x3 = y3 = 0
+  const double e14x = x1 - x4, e14y = y1 - y4;  // edge 1-4 (r = +1)
+  const double e23x = x2, e23y = y2;            // edge 2-3 (r = -1)
+  double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int ip = 0; ip < 4; ++ip) {
+    const double r = (ip == 0 || ip == 3) ? g : -g;
+    const double s = (ip < 2) ? g : -g;
+    // J = [[x_r, y_r], [x_s, y_s]]                 quadrilateral_4n_element_functions.rs:252-446
+    const double x_r = 0.25 * (e12x * (1.0 + s) + e43x * (1.0 - s));
+    const double y_r = 0.25 * (e12y * (1.0 + s) + e43y * (1.0 - s));
+    const double x_s = 0.25 * (e14x * (1.0 + r) + e23x * (1.0 - r));
+    const double y_s = 0.25 * (e14y * (1.0 + r) + e23y * (1.0 - r));
+    const double det = x_r * y_s - y_r * x_s;
+    const double rdet = 1.0 / det;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double xa = (a == 0 || a == 3) ? 1.0 : -1.0, ea = (a < 2) ? 1.0 : -1.0;
+      // dh/dr, dh/ds                               quadrilateral_4n_element_functions.rs:505-583
+      const double dar = 0.25 * xa * (1.0 + ea * s), das = 0.25 * ea * (1.0 + xa * r);
+      // adj(J) * dh                                quadrilateral_4n_element_functions.rs:613-653
+      S[(ip * 4 + a) * 2] = y_s * dar - y_r * das;
+      S[(ip * 4 + a) * 2 + 1] = x_r * das - x_s * dar;
+    }
+    S[32 + ip] = rdet;
+    const double q4 = 0.25 * rdet;
+    const double wr = (x_s * x_s + y_s * y_s) * q4;  // gamma_rz^2 * det  (plate.rs:392-511)
+    const double ws = (x_r * x_r + y_r * y_r) * q4;  // gamma_sz^2 * det
+    tr[0] += ((1.0 + s) * (1.0 + s)) * wr;
+    tr[1] += ((1.0 - s) * (1.0 - s)) * wr;
+    tr[2] += ((1.0 + s) * (1.0 - s)) * wr;
+    ts[0] += ((1.0 + r) * (1.0 + r)) * ws;
+    ts[1] += ((1.0 - r) * (1.0 - r)) * ws;
+    ts[2] += ((1.0 + r) * (1.0 - r)) * ws;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    S[36 + i] = Cs * tr[i];
+    S[39 + i] = Cs * ts[i];
+  }
+  S[42] = 0.25 * e12x; S[43] = 0.25 * e12y;
+  S[44] = 0.25 * e43x; S[45] = 0.25 * e43y;
+  S[46] = 0.25 * e14x; S[47] = 0.25 * e14y;
+  S[48] = 0.25 * e23x; S[49] = 0.25 * e23y;
+  S[50] = Cm; S[51] = Cb; S[52] = nu; S[53] = (1.0 - nu) * 0.5;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S[54 + i] = raw[i];
+  S[63] = raw[15];
+}
+
+// acc += block (la, lb) of (R^T k) R of the plate whose shared record is S.
+__device__ __forceinline__ void plate_block_shared(const double* __restrict__ S, int la, int lb,
+                                                   double acc[36]) {
+  const double2* n2 = reinterpret_cast<const double2*>(S);
+  const double2 rd01 = *reinterpret_cast<const double2*>(S + 32);
+  const double2 rd23 = *reinterpret_cast<const double2*>(S + 34);
+  const double rd[4] = {rd01.x, rd01.y, rd23.x, rd23.y};
+  double sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
+#pragma unroll
+  for (int ip = 0; ip < 4; ++ip) {
+    const double2 na = n2[ip * 4 + la], nb = n2[ip * 4 + lb];
+    const double pax = na.x * rd[ip], pay = na.y * rd[ip];
+    sxx += pax * nb.x;
+    sxy += pax * nb.y;
+    syx += pay * nb.x;
+    syy += pay * nb.y;
+  }
+  const double2 c01 = *reinterpret_cast<const double2*>(S + 50);
+  const double2 c23 = *reinterpret_cast<const double2*>(S + 52);
+  const double Cm = c01.x, Cb = c01.y, nu = c23.x, gp = c23.y;
+  const double t1 = sxx + gp * syy, t2 = nu * sxy + gp * syx;
+  const double t3 = nu * syx + gp * sxy, t4 = syy + gp * sxx;
+  const double m00 = Cm * t1, m01 = Cm * t2, m10 = Cm * t3, m11 = Cm * t4;
+  const double b33 = Cb * t4, b34 = -(Cb * t3), b43 = -(Cb * t2), b44 = Cb * t1;
+  // natural-coordinate signs of nodes 1..4: (+,+), (-,+), (-,-), (+,-)
+  const int an = (la ^ (la >> 1)) & 1, bn = (lb ^ (lb >> 1)) & 1;  // 1 when xi = -1
+  const int am = la >> 1, bm = lb >> 1;                            // 1 when eta = -1
+  const double xa = an ? -0.5 : 0.5, ea = am ? -0.5 : 0.5;
+  const double xb = bn ? -0.5 : 0.5, eb = bm ? -0.5 : 0.5;
+  // gamma_rz rows use the node's s-edge (1-2 or 4-3), gamma_sz rows its r-edge (1-4 or 2-3)
+  const double2 era = *reinterpret_cast<const double2*>(S + 42 + 2 * am);
+  const double2 esa = *reinterpret_cast<const double2*>(S + 46 + 2 * an);
+  const double2 erb = *reinterpret_cast<const double2*>(S + 42 + 2 * bm);
+  const double2 esb = *reinterpret_cast<const double2*>(S + 46 + 2 * bn);
+  const double crz = S[36 + ((am == bm) ? am : 2)];
+  const double csz = S[39 + ((an == bn) ? an : 2)];
+  const double arz[3] = {crz * xa, crz * -era.y, crz * era.x};
+  const double asz[3] = {csz * ea, csz * -esa.y, csz * esa.x};
+  const double brz[3] = {xb, -erb.y, erb.x};
+  const double bsz[3] = {eb, -esb.y, esb.x};
+  double sh[9];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sh[3 * p + c] = arz[p] * brz[c] + asz[p] * bsz[c];
+  const double drill = (la == lb) ? 1.0 : 0.0;  // KROT6, plate.rs:25
+  if (S[63] != 0.0) {
+    // Q == I exactly (flat plates in the global xy plane): (R^T k) R == k; only the 14 structural
+    // entries of the local block are touched
+    acc[0] += m00;  acc[1] += m01;  acc[6] += m10;  acc[7] += m11;
+    acc[14] += sh[0]; acc[15] += sh[1]; acc[16] += sh[2];
+    acc[20] += sh[3]; acc[26] += sh[6];
+    acc[21] += b33 + sh[4]; acc[22] += b34 + sh[5];
+    acc[27] += b43 + sh[7]; acc[28] += b44 + sh[8];
+    acc[35] += drill;
+  } else {
+    const double* q = S + 54;
+    const double uu[9] = {m00, m01, 0.0, m10, m11, 0.0, 0.0, 0.0, sh[0]};
+    const double ut[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, sh[1], sh[2], 0.0};
+    const double tu[9] = {0.0, 0.0, sh[3], 0.0, 0.0, sh[6], 0.0, 0.0, 0.0};
+    const double tt[9] = {b33 + sh[4], b34 + sh[5], 0.0, b43 + sh[7], b44 + sh[8], 0.0, 0.0, 0.0, drill};
+    sandwich_full(q, uu, acc, 0, 0);
+    sandwich_full(q, ut, acc, 0, 3);
+    sandwich_full(q, tu, acc, 3, 0);
+    sandwich_full(q, tt, acc, 3, 3);
+  }
+}
+
+
 }  // namespace femgpu

@@ -58,19 +58,33 @@ __device__ __forceinline__ const void* record_chunk(const AsmArgs& A, uint32_t f
   return chunk < 2 ? reinterpret_cast<const double*>(A.truss_rec + e) + chunk * 2 : nullptr;
 }
 
-// evaluate one contribution from a record of kRecStride doubles (shared memory, or registers
-// filled from global in the unstaged fallback)
+// evaluate one contribution. rec = the element's staged record in shared memory: the prep kernel's
+// record for trusses (4 doubles) and beams (16), the per-CTA shared form (element_math.cuh,
+// plate_shared_record) for plates
 __device__ __forceinline__ void add_contribution(const double* __restrict__ rec, uint32_t code,
                                                  double acc[36]) {
   const uint32_t family = code >> 30, pair = (code >> 26) & 15u;
   if (family == FEMGPU_PLATE) {
-    plate_block(rec, rec + 16, int(pair >> 2), int(pair & 3u), acc);
+    plate_block_shared(rec, int(pair >> 2), int(pair & 3u), acc);
   } else if (family == FEMGPU_BEAM) {
     beam_block(rec, int(pair >> 1), int(pair & 1u), acc);
   } else if (family == FEMGPU_TRUSS) {
     truss_block(rec[0], rec[1], rec[2], rec[3], int(pair >> 1), int(pair & 1u), acc);
   }
   // family 3: slot reserved for another rank's contribution (multi-GPU) — nothing to add here
+}
+
+// same from the prep kernel's raw record (unstaged fallback, test hook): plates build their shared
+// form on the spot
+__device__ __forceinline__ void add_contribution_raw(const double* __restrict__ raw, uint32_t code,
+                                                     double acc[36]) {
+  if ((code >> 30) == FEMGPU_PLATE) {
+    double S[kPlateSharedDoubles];
+    plate_shared_record(raw, S);
+    add_contribution(S, code, acc);
+  } else {
+    add_contribution(raw, code, acc);
+  }
 }
 
 // Place a 6x6 / 3x3 block into the slab image. kShared: image in shared memory (STS) else straight
@@ -123,29 +137,39 @@ __device__ __forceinline__ void store_block(double* __restrict__ img, const uint
 // lanes whose items are one 4-contribution block and lanes whose items are four 1-contribution
 // blocks stay converged on the expensive part. Codes and block metadata are loaded one step
 // ahead of their use.
+struct ItemHead {  // first block metadata / contribution code of a work item, fetched early
+  uint4 m, m_next;
+  uint32_t code;
+};
+__device__ __forceinline__ ItemHead load_item_head(const AsmArgs& A, const WorkItem& w) {
+  const uint4* meta = reinterpret_cast<const uint4*>(A.meta);
+  ItemHead h;
+  h.m = __ldg(meta + w.blk_begin);  // meta[] / contrib[] are padded, index 0 is always valid
+  h.m_next = __ldg(meta + w.blk_begin + 1);
+  h.code = __ldg(A.contrib + w.c_begin);
+  return h;
+}
+
 template <bool kShared>
 __device__ __forceinline__ void run_item(const AsmArgs& A, const SlabDesc& d, const WorkItem& w,
-                                         double* img, const double* __restrict__ recs, bool base_even) {
+                                         const ItemHead& head, double* img,
+                                         const double* __restrict__ recs, bool base_even) {
   // idle lanes (blk_count == 0) run zero iterations but still take part in the warp syncs
   const uint4* meta = reinterpret_cast<const uint4*>(A.meta);
   uint32_t p = w.blk_begin;
-  uint4 m = __ldg(meta + p);           // meta[] / contrib[] are padded, index 0 is always valid
-  uint4 m_next = __ldg(meta + p + 1);
+  uint4 m = head.m;
+  uint4 m_next = head.m_next;
   uint32_t remaining = m.w;
-  uint32_t code = __ldg(A.contrib + w.c_begin);
+  uint32_t code = head.code;
   const uint32_t c_end = w.c_begin + w.c_count;
   double acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-  if (kShared) {
-    // the records staged by this warp's cp.async must have landed (and be visible warp-wide)
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-  }
+  if (kShared) __syncwarp();  // phase A's records are visible warp-wide
   for (uint32_t c = w.c_begin; c < c_end; ++c) {
     const uint32_t next = __ldg(A.contrib + c + 1);  // contrib[] is padded by one entry
     if (kShared) {
-      add_contribution(recs + (code & 0x03FFFFFFu) * kRecStride, code, acc);
+      add_contribution(recs + (code & 0x03FFFFFFu) * 2u, code, acc);  // offset in 16-byte units
     } else {
       // unstaged fallback (a node with thousands of neighbours): gather the record from global
       double rec[kRecStride];
@@ -157,7 +181,7 @@ __device__ __forceinline__ void run_item(const AsmArgs& A, const SlabDesc& d, co
         rec[2 * ch] = v.x;
         rec[2 * ch + 1] = v.y;
       }
-      add_contribution(rec, code, acc);
+      add_contribution_raw(rec, code, acc);
     }
     code = next;
     if (--remaining == 0) {
@@ -178,8 +202,13 @@ __device__ __forceinline__ void run_item(const AsmArgs& A, const SlabDesc& d, co
 //   trip 2   each lane cp.async's the records of "its" elements into shared memory (every record is
 //            fetched once per CTA, all requests in flight together) while it also pulls its first
 //            block metadata and contribution code
-//   compute  each lane evaluates its work item into the shared-memory image of the slab
+//   phase A  the lane that fetched a plate record turns it into the element's shared form (Jacobians,
+//            1/det, adj(J) dh, shear sums — everything the element's 16 node-pair blocks share)
+//   phase B  each lane evaluates its work item into the shared-memory image of the slab
 //   store    lane 0 hands the image to the TMA engine as one bulk shared->global copy
+// Record area: the slab's element list is sorted by family, so records sit in three regions
+// [trusses][beams][plates] with slot sizes kTrussSlotDoubles / kBeamSlotDoubles / kPlateSlotDoubles;
+// contribution codes carry the record's offset.
 __global__ void __maxnreg__(224)
 assemble_kernel(const AsmArgs A) {
   extern __shared__ __align__(128) double slab_smem[];
@@ -194,27 +223,52 @@ assemble_kernel(const AsmArgs A) {
   w.blk_begin = wraw.x; w.blk_count = wraw.y; w.c_begin = wraw.z; w.c_count = wraw.w;
   if (d.blk_count == 0) return;
   if (d.flags & 1u) {  // slab larger than the staging buffer: everything straight from/to HBM
-    run_item<false>(A, d, w, A.values + d.val_base, nullptr, (d.val_base & 1) == 0);
+    run_item<false>(A, d, w, load_item_head(A, w), A.values + d.val_base, nullptr, (d.val_base & 1) == 0);
     return;
   }
   double* img = slab_smem;
   double* recs = slab_smem + ((d.val_count + 1u) & ~1u);
+  const uint32_t n_truss = (d.flags >> 8) & 0xFFFu, n_beam = d.flags >> 20;
+  double* my_plate[kElistStride / kAsmThreads];
   {
     const uint32_t recs_s = smem_u32(recs);
 #pragma unroll
     for (int j = 0; j < kElistStride / kAsmThreads; ++j) {
+      my_plate[j] = nullptr;
       if (fe[j] != 0xFFFFFFFFu) {
-        const uint32_t slot = j * kAsmThreads + lane;
-#pragma unroll
-        for (uint32_t ch = 0; ch < kRecStride / 2; ++ch) {
-          const void* src = record_chunk(A, fe[j], ch);
-          if (src) cp_async16(recs_s + (slot * (kRecStride / 2) + ch) * 16u, src);
-        }
+        const uint32_t slot = j * kAsmThreads + lane, family = fe[j] >> 26;
+        // record offset in doubles; the plate's raw 20 doubles land at the start of its slot
+        uint32_t off, chunks;
+        if (family == FEMGPU_TRUSS) { off = slot * kTrussSlotDoubles; chunks = 2; }
+        else if (family == FEMGPU_BEAM) { off = n_truss * kTrussSlotDoubles + (slot - n_truss) * kBeamSlotDoubles; chunks = 8; }
+        else if (family == FEMGPU_PLATE) {
+          off = n_truss * kTrussSlotDoubles + n_beam * kBeamSlotDoubles + (slot - n_truss - n_beam) * kPlateSlotDoubles;
+          chunks = 10;
+          my_plate[j] = recs + off;
+        } else { off = 0; chunks = 0; }  // placeholder of a remote contribution: no record
+        for (uint32_t ch = 0; ch < chunks; ++ch)
+          cp_async16(recs_s + off * 8u + ch * 16u, record_chunk(A, fe[j], ch));
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  run_item<true>(A, d, w, img, recs, true);
+  const ItemHead head = load_item_head(A, w);
+  // phase A (a lane only touches records it fetched itself; the warp sync is in run_item)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < kElistStride / kAsmThreads; ++j) {
+    if (my_plate[j]) {
+      double raw[20];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const double2 v = reinterpret_cast<const double2*>(my_plate[j])[i];
+        raw[2 * i] = v.x;
+        raw[2 * i + 1] = v.y;
+      }
+      plate_shared_record(raw, my_plate[j]);
+    }
+  }
+  run_item<true>(A, d, w, head, img, recs, true);
   double* out = A.values + d.val_base;
   const uint32_t n = d.val_count;
   if (((d.val_base | n) & 1) == 0) {
@@ -232,10 +286,10 @@ assemble_kernel(const AsmArgs A) {
   }
   __syncwarp();
   // ragged slab (3-wide truss blocks): coalesced 16-byte stores on the aligned body
-  const uint32_t head = uint32_t(d.val_base & 1);  // values[] is 16-byte aligned at index 0
-  if (head && lane == 0) out[0] = img[0];
-  const uint32_t body = (n - head) >> 1;
-  if (head == 0) {
+  const uint32_t odd = uint32_t(d.val_base & 1);  // values[] is 16-byte aligned at index 0
+  if (odd && lane == 0) out[0] = img[0];
+  const uint32_t body = (n - odd) >> 1;
+  if (odd == 0) {
     const double2* src = reinterpret_cast<const double2*>(img);
     double2* dst = reinterpret_cast<double2*>(out);
     for (uint32_t i = lane; i < body; i += kAsmThreads) dst[i] = src[i];
@@ -244,7 +298,7 @@ assemble_kernel(const AsmArgs A) {
     for (uint32_t i = lane; i < body; i += kAsmThreads)
       dst[i] = make_double2(img[1 + 2 * i], img[2 + 2 * i]);
   }
-  if (((n - head) & 1u) && lane == 0) out[n - 1] = img[n - 1];
+  if (((n - odd) & 1u) && lane == 0) out[n - 1] = img[n - 1];
 }
 
 // test hook: the whole transformed element matrix of one element, built from the same block
@@ -271,7 +325,7 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
   }
   double acc[36];
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-  add_contribution(rec, (uint32_t(family) << 30) | (uint32_t(pair) << 26), acc);
+  add_contribution_raw(rec, (uint32_t(family) << 30) | (uint32_t(pair) << 26), acc);
   for (int i = 0; i < dof; ++i)
     for (int j = 0; j < dof; ++j) out[(la * dof + i) * n + lb * dof + j] = acc[6 * i + j];
 }

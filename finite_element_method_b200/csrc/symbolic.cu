@@ -314,15 +314,26 @@ __global__ void slab_elist_kernel(uint32_t n_slabs, uint32_t n_unique, const uin
                                   int32_t* __restrict__ flags) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_slabs) return;
+  // the list is sorted by family: [trusses][beams][plates][remote placeholders]
   uint32_t b = lower_bound_u64(ukey, n_unique, uint64_t(k) << 28);
+  uint32_t b1 = lower_bound_u64(ukey, n_unique, (uint64_t(k) << 28) | (uint64_t(FEMGPU_BEAM) << 26));
+  uint32_t b2 = lower_bound_u64(ukey, n_unique, (uint64_t(k) << 28) | (uint64_t(FEMGPU_PLATE) << 26));
+  uint32_t b3 = lower_bound_u64(ukey, n_unique, (uint64_t(k) << 28) | (uint64_t(3) << 26));
   uint32_t e = lower_bound_u64(ukey, n_unique, uint64_t(k + 1) << 28);
   SlabDesc d = slabs[k];
   d.el_begin = b;
   d.el_count = e - b;
-  uint64_t need = ((uint64_t(d.val_count) * 8 + 15) & ~uint64_t(15)) + uint64_t(e - b) * kRecStride * 8;
+  const uint32_t nt = b1 - b, nb = b2 - b1, np = b3 - b2;
+  // record area: [trusses][beams][plates, in their shared form]
+  uint64_t need = ((uint64_t(d.val_count) * 8 + 15) & ~uint64_t(15)) +
+                  (uint64_t(nt) * kTrussSlotDoubles + uint64_t(nb) * kBeamSlotDoubles +
+                   uint64_t(np) * kPlateSlotDoubles) * 8;
   if (need > smem_bytes_cap || (e - b) > uint32_t(kElistStride)) d.flags |= 1u;
+  if (!(d.flags & 1u)) {
+    d.flags |= (nt << 8) | (nb << 20);  // both <= kElistStride
+    atomicMax(flags + 2, int32_t(need));  // largest staged slab (integer max)
+  }
   slabs[k] = d;
-  if (!(d.flags & 1u)) atomicMax(flags + 2, int32_t(need));  // largest staged slab (integer max)
 }
 
 // dense [slab][kElistStride] copy of the compact lists: addressable from the slab id alone
@@ -335,16 +346,27 @@ __global__ void elist_table_kernel(uint32_t n_slabs, const SlabDesc* __restrict_
   table[t] = (e < d.el_count && !(d.flags & 1u)) ? compact[d.el_begin + e] : 0xFFFFFFFFu;
 }
 
-// contrib codes become family<<30 | pair<<26 | slab-local element slot
+// contrib codes become family<<30 | pair<<26 | where the element's record sits: its offset in the
+// CTA's record area in 16-byte units (staged slabs), or its slot in the slab's element list
 __global__ void relabel_kernel(uint32_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload,
                                const uint32_t* __restrict__ uidx, const SlabDesc* __restrict__ slabs,
                                uint32_t* __restrict__ contrib_ord) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t slab = uint32_t(keys[i] >> 28);
-  uint32_t local = (uidx[i] - 1) - slabs[slab].el_begin;
+  const SlabDesc d = slabs[slab];
+  uint32_t local = (uidx[i] - 1) - d.el_begin;
   uint32_t c = payload[i];
-  contrib_ord[c] = (contrib_ord[c] & 0xFC000000u) | local;
+  const uint32_t code = contrib_ord[c], family = code >> 30;
+  if (!(d.flags & 1u)) {
+    const uint32_t nt = (d.flags >> 8) & 0xFFFu, nb = d.flags >> 20;
+    constexpr uint32_t ut = kTrussSlotDoubles / 2, ub = kBeamSlotDoubles / 2, up = kPlateSlotDoubles / 2;
+    if (family == FEMGPU_TRUSS) local = local * ut;
+    else if (family == FEMGPU_BEAM) local = nt * ut + (local - nt) * ub;
+    else if (family == FEMGPU_PLATE) local = nt * ut + nb * ub + (local - nt - nb) * up;
+    else local = 0;
+  }
+  contrib_ord[c] = (code & 0xFC000000u) | local;
 }
 
 __global__ void ordered_meta_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
