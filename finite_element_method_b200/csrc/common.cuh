@@ -179,21 +179,41 @@ struct BlockMeta {
 // its item without first reading the slab descriptor.
 struct WorkItem {
   uint32_t blk_begin;  // first block (thread order)
-  uint32_t blk_count;  // 0 = idle thread
+  uint32_t blk_count;  // low 16 bits: blocks, 0 = idle thread. Bit 24: the item is one chunk of a block
+                       // split over several lanes, bits 16..17 its chunk index; the chunk covers
+                       // c_count contributions (execution order) from c_begin - first contribution of the block
   uint32_t c_begin;    // first contribution
   uint32_t c_count;
 };
 
-struct SlabDesc {
+struct SlabDesc {        // 48 bytes = three 16-byte loads
   int64_t val_base;     // first CSR value of the slab
   uint32_t val_count;   // values in the slab
+  uint32_t flags;       // bit 0: too large for the staged kernel -> assemble_unstaged_kernel;
+                        // bits 8..9: deferred rounds of the slab (max chunk index of a split block);
+                        // bits 16..31: plates in the element list (staged slabs)
   uint32_t blk_begin;   // first block (thread order)
   uint32_t blk_count;
-  uint32_t flags;       // bit 0: too large for shared memory -> write straight to global;
-                        // staged slabs: trusses << 8 | beams << 20 in the element list
-  uint32_t el_begin;    // the slab's distinct elements (elist[]): their records are staged in
-  uint32_t el_count;    // shared memory once per CTA; contrib[] codes index into this list
+  uint32_t c_begin;     // the slab's contribution entries (consecutive, lane-major)
+  uint32_t c_count;
+  uint32_t el_begin;    // the slab's distinct elements in elist_compact[], sorted by family:
+  uint32_t el_count;    // [trusses][beams][plates][placeholders of remote contributions]
+  uint32_t n_truss;
+  uint32_t n_beam;
 };
+
+// Contribution entry of a staged slab (32 bits), in the owning lane's execution order: family-major
+// (placeholders, plates, beams, trusses) over the lane's blocks, insertion order inside a group.
+//   31..30 family   29..26 local node pair   25 group end: flush the accumulator into the block
+//   24 the block already holds an earlier group's sum (read-modify-write)
+//   23..22 deferred round: the block is split over several lanes; chunk j >= 1 is added to the image
+//          after the j-th CTA barrier that follows the evaluation (chunk 0 stores immediately)
+//   21..11 block index inside the slab   10..0 record offset inside the family's record area (16 B units)
+// Unstaged slabs keep family<<30 | pair<<26 | slot in the slab's element list, block-major.
+constexpr uint32_t kEntEnd = 1u << 25, kEntRmw = 1u << 24;
+constexpr int kEntDeferShift = 22, kEntBlkShift = 11;
+constexpr uint32_t kEntBlkMask = 0x7FFu, kEntRecMask = 0x7FFu, kEntDeferMask = 3u;
+constexpr int kMaxChunks = 4;  // a block is split over at most this many lanes
 
 struct DistState {
   bool enabled = false;
@@ -257,7 +277,12 @@ struct Handle {
   DevBuf<uint32_t> elist;          // [n_slabs][kElistStride]: family<<26 | element, 0xFFFFFFFF = empty;
                                    // (compact list when a slab overflows the table: unstaged path)
   DevBuf<uint32_t> elist_compact;
-  uint32_t slab_smem_bytes = 0;    // dynamic shared memory the assembly kernel is launched with
+  // shared-memory regions of the staged assembly kernel (maxima over the staged slabs, bytes)
+  uint32_t smem_img = 0, smem_form = 0, smem_rawp = 0, smem_stage = 0;
+  uint32_t n_unstaged = 0;         // slabs handled by assemble_unstaged_kernel
+  int sm_count = 0;
+  uint32_t asm_smem_set = 0;       // dynamic shared memory assemble_kernel is currently configured for
+  int asm_ctas_per_sm = 0;         // persistent CTAs per SM at that size (occupancy query)
   DevBuf<uint32_t> node_blk_ptr;   // [n_nodes_total+1]
   DevBuf<int64_t> node_base;       // [n_nodes_total+1] first value of the node's rows
   DevBuf<uint32_t> node_len;       // [2*n_nodes_total] len03, len35
@@ -313,9 +338,14 @@ int32_t dist_allgather_i64(Handle* h, const int64_t* send, int64_t* recv, size_t
 int32_t dist_exchange_8(Handle* h, const void* send, const int64_t* send_offs, const int64_t* send_counts,
                         void* recv, const int64_t* recv_offs, const int64_t* recv_counts);  // dist.cu
 
-constexpr int kAsmThreads = 32;            // threads per assembly CTA: one warp, no block barriers
+constexpr int kAsmThreads = 32;            // threads per assembly CTA (32 or 64: one or two warps per slab)
 constexpr int kSlabQuota = 72;             // node-pair blocks a slab aims for (8 plate-grid nodes)
-constexpr int kSlabSmemBytes = 64 * 1024;  // staging capacity (slab image + element records)
+// per-slab capacity of the staged kernel's shared-memory regions; a slab exceeding any of them (a
+// node with hundreds of neighbours) goes to the unstaged kernel
+constexpr int kCapImgBytes = 40 * 1024;    // slab image (CSR values of the slab)
+constexpr int kCapFormBytes = 24 * 1024;   // shared forms of the slab's plates
+constexpr int kCapStageBytes = 12 * 1024;  // block metadata + contribution entries + truss/beam records
+constexpr int kCapBlocks = 2048;           // blocks per staged slab (11-bit index in the entries)
 // Record slots in the CTA's shared-memory record area, in doubles. Odd multiples of 16 bytes so that
 // lanes reading the same field of different elements spread over the banks.
 constexpr int kTrussSlotDoubles = 6;       // 4 used

@@ -677,9 +677,13 @@ __device__ __forceinline__ void plate_shared_record(const double* __restrict__ r
   S[63] = raw[15];
 }
 
-// acc += block (la, lb) of (R^T k) R of the plate whose shared record is S.
+// acc = keep * acc + block (la, lb) of (R^T k) R of the plate whose shared record is S; keep is 1
+// (accumulate) or 0 (first contribution of a block: no separate zeroing of the accumulators).
+// all_flat: every plate of the slab has Q == I exactly (flat plates in the global xy plane), then
+// (R^T k) R == k and only the 14 structural entries of the local block are touched — the other 22
+// accumulators are never written by a flat plate and must already be zero.
 __device__ __forceinline__ void plate_block_shared(const double* __restrict__ S, int la, int lb,
-                                                   double acc[36]) {
+                                                   double keep, bool all_flat, double acc[36]) {
   const double2* n2 = reinterpret_cast<const double2*>(S);
   const double2 rd01 = *reinterpret_cast<const double2*>(S + 32);
   const double2 rd23 = *reinterpret_cast<const double2*>(S + 34);
@@ -723,16 +727,25 @@ __device__ __forceinline__ void plate_block_shared(const double* __restrict__ S,
 #pragma unroll
     for (int c = 0; c < 3; ++c) sh[3 * p + c] = arz[p] * brz[c] + asz[p] * bsz[c];
   const double drill = (la == lb) ? 1.0 : 0.0;  // KROT6, plate.rs:25
-  if (S[63] != 0.0) {
-    // Q == I exactly (flat plates in the global xy plane): (R^T k) R == k; only the 14 structural
-    // entries of the local block are touched
-    acc[0] += m00;  acc[1] += m01;  acc[6] += m10;  acc[7] += m11;
-    acc[14] += sh[0]; acc[15] += sh[1]; acc[16] += sh[2];
-    acc[20] += sh[3]; acc[26] += sh[6];
-    acc[21] += b33 + sh[4]; acc[22] += b34 + sh[5];
-    acc[27] += b43 + sh[7]; acc[28] += b44 + sh[8];
-    acc[35] += drill;
+  if (all_flat) {
+    acc[0] = fma(acc[0], keep, m00);
+    acc[1] = fma(acc[1], keep, m01);
+    acc[6] = fma(acc[6], keep, m10);
+    acc[7] = fma(acc[7], keep, m11);
+    acc[14] = fma(acc[14], keep, sh[0]);
+    acc[15] = fma(acc[15], keep, sh[1]);
+    acc[16] = fma(acc[16], keep, sh[2]);
+    acc[20] = fma(acc[20], keep, sh[3]);
+    acc[26] = fma(acc[26], keep, sh[6]);
+    acc[21] = fma(acc[21], keep, b33 + sh[4]);
+    acc[22] = fma(acc[22], keep, b34 + sh[5]);
+    acc[27] = fma(acc[27], keep, b43 + sh[7]);
+    acc[28] = fma(acc[28], keep, b44 + sh[8]);
+    acc[35] = fma(acc[35], keep, drill);
   } else {
+    // general orientation; for Q == I the sandwich reproduces the local block exactly (1*x + 0*y + 0*z)
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] *= keep;
     const double* q = S + 54;
     const double uu[9] = {m00, m01, 0.0, m10, m11, 0.0, 0.0, 0.0, sh[0]};
     const double ut[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, sh[1], sh[2], 0.0};
@@ -744,6 +757,5 @@ __device__ __forceinline__ void plate_block_shared(const double* __restrict__ S,
     sandwich_full(q, tt, acc, 3, 3);
   }
 }
-
 
 }  // namespace femgpu

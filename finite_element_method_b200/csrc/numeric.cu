@@ -1,21 +1,25 @@
 // Numeric assembly: the hot kernel.
 //
-// Gather formulation — "owner computes": one thread owns one node-pair block (a, b) of the global
-// matrix (6x6, or 3x3 for a truss-only pair). It walks the block's contribution list
-// (family, local pair, element) in global insertion order, evaluates each element's global-frame
-// block T^T k[la,lb] T from the element record (element_math.cuh) and sums into 36 FP64
-// registers. Nothing is ever accumulated through memory: no atomics, no colouring, and the
-// summation order is the order the reference's add_* calls would have used, so the result is
-// deterministic and every CSR value is written exactly once.
+// Gather formulation — "owner computes": one lane owns one node-pair block (a, b) of the global
+// matrix (6x6, or 3x3 for a truss-only pair) at a time. It walks the block's contributions
+// (family, local pair, element), evaluates each element's global-frame block T^T k[la,lb] T from
+// the element record (element_math.cuh) and sums into 36 FP64 registers. Nothing is accumulated
+// through global memory: no atomics, no colouring; the order of summation is fixed by the symbolic
+// pass (family-major, insertion order inside a family), so the result is deterministic and every
+// CSR value is written to HBM exactly once.
 //
-// A CTA owns a "slab": a contiguous range of node rows, hence a contiguous range of CSR values.
-// Threads drop their block into a shared-memory image of the slab (the 6 row segments of a block
-// are 6 doubles wide and a row apart, which would be a poor global store pattern), then the whole
-// CTA streams the image to HBM with fully coalesced 16-byte stores. Blocks inside a slab are
-// pre-sorted by contribution count (symbolic.cu) so the threads of a warp run the same trip count.
+// A warp owns a "slab": a contiguous range of node rows, hence a contiguous range of CSR values.
+// Lanes drop their blocks into a shared-memory image of the slab (the 6 row segments of a block
+// are 6 doubles wide and a row apart, which would be a poor global store pattern) and the image
+// leaves as ONE TMA bulk store.
 //
-// Algorithmic traffic per launch: 8 B x nnz written + element records read (L2-resident re-reads
-// across the 4/16 blocks an element touches). See DESIGN.md for the byte model.
+// The kernel is persistent (single-warp CTAs, a fixed number per SM, slabs dealt round-robin) and
+// software-pipelined: while slab i is evaluated, the element records, block metadata and
+// contribution entries of slab i+1 are in flight (cp.async) and the descriptors of slab i+2 are
+// being loaded into registers; the bulk store of slab i drains while slab i+1 is evaluated. No
+// memory latency sits on the critical path of a warp.
+//
+// Algorithmic traffic per launch: 8 B x nnz written + element records read. See DESIGN.md.
 #include "common.cuh"
 #include "element_math.cuh"
 
@@ -29,13 +33,15 @@ struct AsmArgs {
   const uint32_t* contrib;
   const WorkItem* items;
   const uint32_t* elist;          // dense [n_slabs][kElistStride]
-  const uint32_t* elist_compact;  // compact lists (unstaged fallback only)
+  const uint32_t* elist_compact;  // compact lists (unstaged kernel only)
   const double4* truss_rec;
   const double* beam_rec;
   const double* plate_rec;
   const double* plate_mat;
   double* values;
   uint32_t n_slabs;
+  // shared-memory regions of the staged kernel, bytes: [image][plate forms][raw plates][stage x2]
+  uint32_t smem_img, smem_form, smem_rawp, smem_stage;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -43,6 +49,30 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+// Completion of the cp.async staging is tracked by an mbarrier, not by cp.async groups: the
+// commit/wait_group pair and cp.async.bulk.wait_group share one hardware scoreboard (both compile to
+// DEPBAR.LE SB0), so waiting for the bulk store of the previous slab would also wait for the loads
+// of the next one that were issued a moment earlier.
+__device__ __forceinline__ void mbar_init(uint32_t mbar_s, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s), "r"(count) : "memory");
+}
+// the mbarrier receives this thread's arrival once all its prior cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t mbar_s) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar_s) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_s, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar_s), "r"(parity)
+      : "memory");
 }
 
 // global address of 16-byte chunk `chunk` of an element's record (nullptr past its end):
@@ -58,43 +88,14 @@ __device__ __forceinline__ const void* record_chunk(const AsmArgs& A, uint32_t f
   return chunk < 2 ? reinterpret_cast<const double*>(A.truss_rec + e) + chunk * 2 : nullptr;
 }
 
-// evaluate one contribution. rec = the element's staged record in shared memory: the prep kernel's
-// record for trusses (4 doubles) and beams (16), the per-CTA shared form (element_math.cuh,
-// plate_shared_record) for plates
-__device__ __forceinline__ void add_contribution(const double* __restrict__ rec, uint32_t code,
-                                                 double acc[36]) {
-  const uint32_t family = code >> 30, pair = (code >> 26) & 15u;
-  if (family == FEMGPU_PLATE) {
-    plate_block_shared(rec, int(pair >> 2), int(pair & 3u), acc);
-  } else if (family == FEMGPU_BEAM) {
-    beam_block(rec, int(pair >> 1), int(pair & 1u), acc);
-  } else if (family == FEMGPU_TRUSS) {
-    truss_block(rec[0], rec[1], rec[2], rec[3], int(pair >> 1), int(pair & 1u), acc);
-  }
-  // family 3: slot reserved for another rank's contribution (multi-GPU) — nothing to add here
-}
-
-// same from the prep kernel's raw record (unstaged fallback, test hook): plates build their shared
-// form on the spot
-__device__ __forceinline__ void add_contribution_raw(const double* __restrict__ raw, uint32_t code,
-                                                     double acc[36]) {
-  if ((code >> 30) == FEMGPU_PLATE) {
-    double S[kPlateSharedDoubles];
-    plate_shared_record(raw, S);
-    add_contribution(S, code, acc);
-  } else {
-    add_contribution(raw, code, acc);
-  }
-}
-
-// Place a 6x6 / 3x3 block into the slab image. kShared: image in shared memory (STS) else straight
-// into the CSR values (global). When every row segment is 16-byte aligned (true whenever the node
-// only has 6-wide blocks) the six doubles of a row go out as three 16-byte stores: at the 48-byte
-// lane stride of neighbouring blocks those are bank-conflict free, 8-byte stores are 4-way
-// conflicted.
-template <bool kShared>
-__device__ __forceinline__ void store_block(double* __restrict__ img, const uint4 m,
-                                            const double acc[36], bool base_even) {
+// Place a 6x6 / 3x3 block into the slab image (shared memory) or straight into the CSR values
+// (unstaged kernel). kRmw: the block already holds an earlier group's sum, add it first. When every
+// row segment is 16-byte aligned (true whenever the node only has 6-wide blocks) the six doubles
+// of a row move as three 16-byte accesses: at the 48-byte lane stride of neighbouring blocks those
+// are bank-conflict free, 8-byte accesses are 4-way conflicted.
+template <bool kRmw>
+__device__ __forceinline__ void store_block(double* __restrict__ img, const uint4 m, double acc[36],
+                                            bool base_even) {
   const uint32_t seg0 = m.x, seg3 = m.y, s03 = m.z & 0xFFFFu, s35 = m.z >> 16;
   const bool full = seg3 != 0xFFFFFFFFu;
   if (full) {
@@ -106,8 +107,15 @@ __device__ __forceinline__ void store_block(double* __restrict__ img, const uint
         double2* r3 = reinterpret_cast<double2*>(img + seg3 + i * s35);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          r0[j] = make_double2(acc[6 * i + 2 * j], acc[6 * i + 2 * j + 1]);
-          r3[j] = make_double2(acc[6 * (i + 3) + 2 * j], acc[6 * (i + 3) + 2 * j + 1]);
+          double2 v0 = make_double2(acc[6 * i + 2 * j], acc[6 * i + 2 * j + 1]);
+          double2 v3 = make_double2(acc[6 * (i + 3) + 2 * j], acc[6 * (i + 3) + 2 * j + 1]);
+          if (kRmw) {
+            const double2 o0 = r0[j], o3 = r3[j];
+            v0.x = o0.x + v0.x; v0.y = o0.y + v0.y;
+            v3.x = o3.x + v3.x; v3.y = o3.y + v3.y;
+          }
+          r0[j] = v0;
+          r3[j] = v3;
         }
       }
     } else {
@@ -117,8 +125,8 @@ __device__ __forceinline__ void store_block(double* __restrict__ img, const uint
         double* r3 = img + seg3 + i * s35;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-          r0[j] = acc[6 * i + j];
-          r3[j] = acc[6 * (i + 3) + j];
+          r0[j] = kRmw ? r0[j] + acc[6 * i + j] : acc[6 * i + j];
+          r3[j] = kRmw ? r3[j] + acc[6 * (i + 3) + j] : acc[6 * (i + 3) + j];
         }
       }
     }
@@ -127,178 +135,353 @@ __device__ __forceinline__ void store_block(double* __restrict__ img, const uint
     for (int i = 0; i < 3; ++i) {
       double* r0 = img + seg0 + i * s03;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) r0[j] = acc[6 * i + j];
+      for (int j = 0; j < 3; ++j) r0[j] = kRmw ? r0[j] + acc[6 * i + j] : acc[6 * i + j];
     }
   }
 }
 
-// One work item = a run of consecutive thread-ordered blocks, hence of consecutive contributions.
-// The loop is flat over contributions (a block boundary is just a predicated store + reset), so
-// lanes whose items are one 4-contribution block and lanes whose items are four 1-contribution
-// blocks stay converged on the expensive part. Codes and block metadata are loaded one step
-// ahead of their use.
-struct ItemHead {  // first block metadata / contribution code of a work item, fetched early
-  uint4 m, m_next;
-  uint32_t code;
-};
-__device__ __forceinline__ ItemHead load_item_head(const AsmArgs& A, const WorkItem& w) {
-  const uint4* meta = reinterpret_cast<const uint4*>(A.meta);
-  ItemHead h;
-  h.m = __ldg(meta + w.blk_begin);  // meta[] / contrib[] are padded, index 0 is always valid
-  h.m_next = __ldg(meta + w.blk_begin + 1);
-  h.code = __ldg(A.contrib + w.c_begin);
-  return h;
+// ---- staged, persistent, pipelined kernel --------------------------------------------------------
+
+constexpr int kElistPerLane = kElistStride / kAsmThreads;
+static_assert(kElistStride % kAsmThreads == 0 && (kAsmThreads == 32 || kAsmThreads == 64), "CTA shape");
+
+// CTA-wide barrier / vote: a warp-level sync when the CTA is a single warp
+__device__ __forceinline__ void cta_sync() {
+  if (kAsmThreads == 32) __syncwarp();
+  else __syncthreads();
+}
+__device__ __forceinline__ bool cta_all(bool pred) {
+  if (kAsmThreads == 32) return __all_sync(0xFFFFFFFFu, pred) != 0;
+  return __syncthreads_and(pred) != 0;
 }
 
-template <bool kShared>
-__device__ __forceinline__ void run_item(const AsmArgs& A, const SlabDesc& d, const WorkItem& w,
-                                         const ItemHead& head, double* img,
-                                         const double* __restrict__ recs, bool base_even) {
-  // idle lanes (blk_count == 0) run zero iterations but still take part in the warp syncs
-  const uint4* meta = reinterpret_cast<const uint4*>(A.meta);
-  uint32_t p = w.blk_begin;
-  uint4 m = head.m;
-  uint4 m_next = head.m_next;
-  uint32_t remaining = m.w;
-  uint32_t code = head.code;
-  const uint32_t c_end = w.c_begin + w.c_count;
+// what a thread keeps in registers about a slab that is still to come
+struct SlabRegs {
+  uint4 d0, d1, d2;             // the SlabDesc as three 16-byte words
+  uint32_t fe[kElistPerLane];   // the thread's slots of the slab's element list
+  uint32_t c_begin, c_count;    // the thread's work item
+  __device__ __forceinline__ int64_t val_base() const { return int64_t((uint64_t(d0.y) << 32) | d0.x); }
+  __device__ __forceinline__ uint32_t val_count() const { return d0.z; }
+  __device__ __forceinline__ uint32_t rounds() const { return (d0.w >> 8) & 3u; }
+  __device__ __forceinline__ uint32_t n_plate() const { return d0.w >> 16; }
+  __device__ __forceinline__ uint32_t blk_begin() const { return d1.x; }
+  __device__ __forceinline__ uint32_t blk_count() const { return d1.y; }
+  __device__ __forceinline__ uint32_t slab_c_begin() const { return d1.z; }
+  __device__ __forceinline__ uint32_t slab_c_count() const { return d1.w; }
+  __device__ __forceinline__ uint32_t n_truss() const { return d2.z; }
+  __device__ __forceinline__ uint32_t n_beam() const { return d2.w; }
+  // stage layout (bytes): [block metadata][entries][truss records][beam records]
+  __device__ __forceinline__ uint32_t ent_off() const { return blk_count() * 16u; }
+  __device__ __forceinline__ uint32_t ent_bytes() const {
+    return (((slab_c_begin() & 3u) + slab_c_count() + 1u) * 4u + 15u) & ~15u;
+  }
+  __device__ __forceinline__ uint32_t truss_off() const { return ent_off() + ent_bytes(); }
+  __device__ __forceinline__ uint32_t beam_off() const {
+    return truss_off() + n_truss() * uint32_t(kTrussSlotDoubles * 8);
+  }
+  // an oversized slab is done by the unstaged kernel; here it becomes an empty slab. Called when the
+  // registers are first used, one iteration after the loads were issued.
+  __device__ __forceinline__ void sanitize() {
+    if (d0.w & 1u) {
+      d0.z = 0;
+      d0.w = 1u;
+      d1.y = 0;
+      d1.w = 0;
+      d2.z = d2.w = 0;
+      c_count = 0;
+#pragma unroll
+      for (int j = 0; j < kElistPerLane; ++j) fe[j] = 0xFFFFFFFFu;
+    }
+  }
+};
+
+// Descriptor block of a slab in shared memory: [SlabDesc 48 B][work items kAsmThreads x 16 B][element
+// list kElistStride x 4 B]. Everything is addressable from the slab id alone (dense tables), so it
+// is requested two slabs ahead with cp.async; nothing that is in flight lives in registers.
+constexpr uint32_t kDescItemsOff = 48, kDescElistOff = kDescItemsOff + kAsmThreads * 16;
+constexpr uint32_t kDescBytes = (kDescElistOff + kElistStride * 4 + 127) & ~127u;
+
+__device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_t dbuf_s, uint32_t tid) {
+  cp_async16(dbuf_s + kDescItemsOff + tid * 16u, A.items + size_t(k) * kAsmThreads + tid);
+  if (tid < kElistStride / 4) cp_async16(dbuf_s + kDescElistOff + tid * 16u, A.elist + size_t(k) * kElistStride + tid * 4u);
+  else if (tid < kElistStride / 4 + 3)
+    cp_async16(dbuf_s + (tid - kElistStride / 4) * 16u,
+               reinterpret_cast<const uint4*>(A.slabs + k) + (tid - kElistStride / 4));
+}
+
+__device__ __forceinline__ SlabRegs read_desc(const unsigned char* dbuf, uint32_t tid) {
+  SlabRegs R;
+  const uint4* sp = reinterpret_cast<const uint4*>(dbuf);
+  R.d0 = sp[0];
+  R.d1 = sp[1];
+  R.d2 = sp[2];
+#pragma unroll
+  for (int j = 0; j < kElistPerLane; ++j)
+    R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + kDescElistOff)[j * kAsmThreads + tid];
+  const uint2 w = reinterpret_cast<const uint2*>(dbuf + kDescItemsOff)[tid * 2u + 1u];
+  R.c_begin = w.x;
+  R.c_count = w.y;
+  R.sanitize();
+  return R;
+}
+
+// cp.async everything slab R needs into `stage` (+ its raw plate records into `rawp`): block
+// metadata, contribution entries, and each thread the record of "its" element — every record is
+// fetched once per slab, all requests in flight together
+__device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs& R, uint32_t stage_s,
+                                            uint32_t rawp_s, uint32_t tid) {
+  const uint32_t nb = R.blk_count();
+  for (uint32_t b = tid; b < nb; b += kAsmThreads) cp_async16(stage_s + b * 16u, A.meta + R.blk_begin() + b);
+  const uint32_t c0 = R.slab_c_begin(), first = c0 & ~3u, chunks = R.ent_bytes() >> 4;
+  const uint32_t ent_s = stage_s + R.ent_off();
+  if (R.slab_c_count())
+    for (uint32_t i = tid; i < chunks; i += kAsmThreads) cp_async16(ent_s + i * 16u, A.contrib + first + i * 4u);
+  const uint32_t nt = R.n_truss(), nbm = R.n_beam();
+#pragma unroll
+  for (int j = 0; j < kElistPerLane; ++j) {
+    const uint32_t fe = R.fe[j];
+    if (fe == 0xFFFFFFFFu) continue;
+    const uint32_t slot = j * kAsmThreads + tid, family = fe >> 26, e = fe & 0x03FFFFFFu;
+    if (family == FEMGPU_PLATE) {
+      const uint32_t dst = rawp_s + (slot - nt - nbm) * 160u;
+      const double* rec = A.plate_rec + size_t(e) * 16;
+      const double* mat = A.plate_mat + size_t(e) * 4;
+#pragma unroll
+      for (uint32_t ch = 0; ch < 8; ++ch) cp_async16(dst + ch * 16u, rec + ch * 2);
+      cp_async16(dst + 128u, mat);
+      cp_async16(dst + 144u, mat + 2);
+    } else if (family == FEMGPU_BEAM) {
+      const uint32_t dst = stage_s + R.beam_off() + (slot - nt) * uint32_t(kBeamSlotDoubles * 8);
+      const double* rec = A.beam_rec + size_t(e) * 16;
+#pragma unroll
+      for (uint32_t ch = 0; ch < 8; ++ch) cp_async16(dst + ch * 16u, rec + ch * 2);
+    } else if (family == FEMGPU_TRUSS) {
+      const uint32_t dst = stage_s + R.truss_off() + slot * uint32_t(kTrussSlotDoubles * 8);
+      const double* rec = reinterpret_cast<const double*>(A.truss_rec + e);
+      cp_async16(dst, rec);
+      cp_async16(dst + 16u, rec + 2);
+    }  // family 3: placeholder of a remote contribution, no record
+  }
+}
+
+// phase A: one thread per plate (alternating between the two warps) turns the raw record into the
+// element's shared form (element_math.cuh). Returns whether every plate of the slab has Q == I.
+__device__ __forceinline__ bool phase_a(const SlabRegs& R, const double* __restrict__ rawp,
+                                        double* __restrict__ form, uint32_t tid) {
+  bool flat = true;
+  const uint32_t np = R.n_plate();
+  // plates are dealt to the warps alternately so both carry the same share
+  for (uint32_t idx = (kAsmThreads == 64) ? ((tid & 31u) * 2u + (tid >> 5)) : tid; idx < np; idx += kAsmThreads) {
+    double raw[20];
+    const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const double2 v = src[i];
+      raw[2 * i] = v.x;
+      raw[2 * i + 1] = v.y;
+    }
+    flat = flat && raw[15] != 0.0;
+    plate_shared_record(raw, form + idx * uint32_t(kPlateSlotDoubles));
+  }
+  return cta_all(flat);  // also: forms visible CTA-wide, raw plate records free again
+}
+
+// phase B: the thread runs its contribution entries. The loop is flat over contributions — a group
+// end is a flush of the accumulators into the image, after which `keep` = 0 makes the next
+// contribution overwrite them (no zeroing) — so threads with one long group and threads with
+// several short ones stay converged on the expensive part. A chunk of a split block (deferred
+// round j >= 1) keeps its sum in registers and adds it to the image after the j-th barrier.
+__device__ __forceinline__ void phase_b(const SlabRegs& R, const unsigned char* __restrict__ stage,
+                                        const double* __restrict__ form, double* __restrict__ img,
+                                        bool all_flat) {
+  const uint4* meta = reinterpret_cast<const uint4*>(stage);
+  const uint32_t* ent = reinterpret_cast<const uint32_t*>(stage + R.ent_off()) + (R.slab_c_begin() & 3u);
+  const double* truss = reinterpret_cast<const double*>(stage + R.truss_off());
+  const double* beam = reinterpret_cast<const double*>(stage + R.beam_off());
+  uint32_t i = R.c_begin - R.slab_c_begin();
+  const uint32_t end = i + R.c_count;
   double acc[36];
 #pragma unroll
-  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-  if (kShared) __syncwarp();  // phase A's records are visible warp-wide
-  for (uint32_t c = w.c_begin; c < c_end; ++c) {
-    const uint32_t next = __ldg(A.contrib + c + 1);  // contrib[] is padded by one entry
-    if (kShared) {
-      add_contribution(recs + (code & 0x03FFFFFFu) * 2u, code, acc);  // offset in 16-byte units
-    } else {
-      // unstaged fallback (a node with thousands of neighbours): gather the record from global
-      double rec[kRecStride];
-      const uint32_t fe = __ldg(A.elist_compact + d.el_begin + (code & 0x03FFFFFFu));
+  for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+  double keep = 0.0;
+  uint32_t pending = 0;  // deferred round of the thread's last group
+  uint4 pending_m = make_uint4(0u, 0u, 0u, 0u);
+  if (i < end) {
+    uint32_t code = ent[i];
+    for (; i < end; ++i) {
+      const uint32_t next = ent[i + 1];  // the entry area is padded by one
+      const uint32_t family = code >> 30, pair = (code >> 26) & 15u, rec = (code & kEntRecMask) * 2u;
+      if (family == FEMGPU_PLATE) {
+        plate_block_shared(form + rec, int(pair >> 2), int(pair & 3u), keep, all_flat, acc);
+      } else {
 #pragma unroll
-      for (uint32_t ch = 0; ch < kRecStride / 2; ++ch) {
-        const double2* src = reinterpret_cast<const double2*>(record_chunk(A, fe, ch));
-        double2 v = src ? __ldg(src) : make_double2(0.0, 0.0);
-        rec[2 * ch] = v.x;
-        rec[2 * ch + 1] = v.y;
+        for (int q = 0; q < 36; ++q) acc[q] *= keep;
+        if (family == FEMGPU_BEAM) {
+          beam_block(beam + rec, int(pair >> 1), int(pair & 1u), acc);
+        } else if (family == FEMGPU_TRUSS) {
+          const double* t = truss + rec;
+          truss_block(t[0], t[1], t[2], t[3], int(pair >> 1), int(pair & 1u), acc);
+        }
+        // family 3: slot reserved for another rank's contribution (multi-GPU), contributes zero
       }
-      add_contribution_raw(rec, code, acc);
+      keep = 1.0;
+      if (code & kEntEnd) {
+        const uint4 m = meta[(code >> kEntBlkShift) & kEntBlkMask];
+        const uint32_t defer = (code >> kEntDeferShift) & kEntDeferMask;
+        if (defer) {  // always the thread's last entry
+          pending = defer;
+          pending_m = m;
+        } else if (code & kEntRmw) {
+          store_block<true>(img, m, acc, true);
+        } else {
+          store_block<false>(img, m, acc, true);
+        }
+        keep = 0.0;
+      }
+      code = next;
     }
-    code = next;
-    if (--remaining == 0) {
-      store_block<kShared>(img, m, acc, base_even);
-#pragma unroll
-      for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-      ++p;
-      m = m_next;
-      remaining = m.w;
-      m_next = __ldg(meta + p + 1);
-    }
+  }
+  const uint32_t rounds = R.rounds();
+  for (uint32_t r = 1; r <= rounds; ++r) {
+    cta_sync();
+    if (pending == r) store_block<true>(img, pending_m, acc, true);
   }
 }
 
-// One single-warp CTA per slab; no block barriers anywhere.
-//   trip 1   work item, slab descriptor and the slab's element list are fetched together: all three
-//            are addressable from the slab id alone (dense tables), nothing waits on anything
-//   trip 2   each lane cp.async's the records of "its" elements into shared memory (every record is
-//            fetched once per CTA, all requests in flight together) while it also pulls its first
-//            block metadata and contribution code
-//   phase A  the lane that fetched a plate record turns it into the element's shared form (Jacobians,
-//            1/det, adj(J) dh, shear sums — everything the element's 16 node-pair blocks share)
-//   phase B  each lane evaluates its work item into the shared-memory image of the slab
-//   store    lane 0 hands the image to the TMA engine as one bulk shared->global copy
-// Record area: the slab's element list is sorted by family, so records sit in three regions
-// [trusses][beams][plates] with slot sizes kTrussSlotDoubles / kBeamSlotDoubles / kPlateSlotDoubles;
-// contribution codes carry the record's offset.
-__global__ void __maxnreg__(224)
+__global__ void __maxnreg__(kAsmThreads == 64 ? 200 : 255)
 assemble_kernel(const AsmArgs A) {
-  extern __shared__ __align__(128) double slab_smem[];
-  const uint32_t k = blockIdx.x, lane = threadIdx.x;
-  const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(A.items) + size_t(k) * kAsmThreads + lane);
-  uint32_t fe[kElistStride / kAsmThreads];
-#pragma unroll
-  for (int j = 0; j < kElistStride / kAsmThreads; ++j)
-    fe[j] = __ldg(A.elist + size_t(k) * kElistStride + j * kAsmThreads + lane);
-  const SlabDesc d = A.slabs[k];
-  WorkItem w;
-  w.blk_begin = wraw.x; w.blk_count = wraw.y; w.c_begin = wraw.z; w.c_count = wraw.w;
-  if (d.blk_count == 0) return;
-  if (d.flags & 1u) {  // slab larger than the staging buffer: everything straight from/to HBM
-    run_item<false>(A, d, w, load_item_head(A, w), A.values + d.val_base, nullptr, (d.val_base & 1) == 0);
-    return;
-  }
-  double* img = slab_smem;
-  double* recs = slab_smem + ((d.val_count + 1u) & ~1u);
-  const uint32_t n_truss = (d.flags >> 8) & 0xFFFu, n_beam = d.flags >> 20;
-  double* my_plate[kElistStride / kAsmThreads];
-  {
-    const uint32_t recs_s = smem_u32(recs);
-#pragma unroll
-    for (int j = 0; j < kElistStride / kAsmThreads; ++j) {
-      my_plate[j] = nullptr;
-      if (fe[j] != 0xFFFFFFFFu) {
-        const uint32_t slot = j * kAsmThreads + lane, family = fe[j] >> 26;
-        // record offset in doubles; the plate's raw 20 doubles land at the start of its slot
-        uint32_t off, chunks;
-        if (family == FEMGPU_TRUSS) { off = slot * kTrussSlotDoubles; chunks = 2; }
-        else if (family == FEMGPU_BEAM) { off = n_truss * kTrussSlotDoubles + (slot - n_truss) * kBeamSlotDoubles; chunks = 8; }
-        else if (family == FEMGPU_PLATE) {
-          off = n_truss * kTrussSlotDoubles + n_beam * kBeamSlotDoubles + (slot - n_truss - n_beam) * kPlateSlotDoubles;
-          chunks = 10;
-          my_plate[j] = recs + off;
-        } else { off = 0; chunks = 0; }  // placeholder of a remote contribution: no record
-        for (uint32_t ch = 0; ch < chunks; ++ch)
-          cp_async16(recs_s + off * 8u + ch * 16u, record_chunk(A, fe[j], ch));
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t tid = threadIdx.x, stride = gridDim.x;
+  double* img = reinterpret_cast<double*>(smem);
+  double* form = reinterpret_cast<double*>(smem + A.smem_img);
+  double* rawp = reinterpret_cast<double*>(smem + A.smem_img + A.smem_form);
+  unsigned char* stage0 = smem + A.smem_img + A.smem_form + A.smem_rawp;
+  unsigned char* dbuf0 = stage0 + 2 * A.smem_stage;  // three rotating descriptor blocks
+  const uint32_t rawp_s = smem_u32(rawp), stage0_s = smem_u32(stage0), dbuf0_s = smem_u32(dbuf0);
+
+  uint32_t k = blockIdx.x;
+  if (k >= A.n_slabs) return;
+  const uint32_t mbar_s = dbuf0_s + 3 * kDescBytes;
+  if (tid == 0) mbar_init(mbar_s, kAsmThreads);
+  cta_sync();
+  // prologue: descriptor of the first slab, then its stage and the descriptor of the second
+  issue_desc(A, k, dbuf0_s, tid);
+  cp_async_arrive(mbar_s);
+  mbar_wait(mbar_s, 0);
+  SlabRegs cur = read_desc(dbuf0, tid);
+  issue_stage(A, cur, stage0_s, rawp_s, tid);
+  if (k + stride < A.n_slabs) issue_desc(A, k + stride, dbuf0_s + kDescBytes, tid);
+  cp_async_arrive(mbar_s);
+
+  uint32_t d_cur = 0;  // descriptor block of `cur`
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t buf = it & 1u;
+    const unsigned char* stage = stage0 + buf * A.smem_stage;
+    const uint32_t d_nxt = (d_cur == 2u) ? 0u : d_cur + 1u, d_nn = (d_nxt == 2u) ? 0u : d_nxt + 1u;
+    const bool has_next = k + stride < A.n_slabs;
+    // slab `cur`: its records, metadata and entries (and the next slab's descriptor) were
+    // requested one iteration ago (batch it + 1 of the mbarrier)
+    mbar_wait(mbar_s, (it + 1u) & 1u);
+    cta_sync();
+    const bool all_flat = phase_a(cur, rawp, form, tid);
+    if (has_next) {
+      const SlabRegs nxt = read_desc(dbuf0 + d_nxt * kDescBytes, tid);
+      issue_stage(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, tid);
+      if (k + 2 * stride < A.n_slabs) issue_desc(A, k + 2 * stride, dbuf0_s + d_nn * kDescBytes, tid);
+      cp_async_arrive(mbar_s);
+    }
+    // the image is free once the TMA engine has read the previous slab out of it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    cta_sync();
+    phase_b(cur, stage, form, img, all_flat);
+
+    const uint32_t n = cur.val_count();
+    if (n) {
+      double* out = A.values + cur.val_base();
+      if (((uint32_t(cur.val_base()) | n) & 1u) == 0) {
+        // 16-byte aligned slab: generic-proxy writes -> async proxy, then one TMA bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        cta_sync();
+        if (tid == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out),
+                       "r"(smem_u32(img)), "r"(n * 8u)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        cta_sync();
+        // ragged slab (3-wide truss blocks): coalesced 16-byte stores on the aligned body
+        const uint32_t odd = uint32_t(cur.val_base() & 1);  // values[] is 16-byte aligned at index 0
+        if (odd && tid == 0) out[0] = img[0];
+        const uint32_t body = (n - odd) >> 1;
+        if (odd == 0) {
+          const double2* src = reinterpret_cast<const double2*>(img);
+          double2* dst = reinterpret_cast<double2*>(out);
+          for (uint32_t i = tid; i < body; i += kAsmThreads) dst[i] = src[i];
+        } else {
+          double2* dst = reinterpret_cast<double2*>(out + 1);
+          for (uint32_t i = tid; i < body; i += kAsmThreads)
+            dst[i] = make_double2(img[1 + 2 * i], img[2 + 2 * i]);
+        }
+        if (((n - odd) & 1u) && tid == 0) out[n - 1] = img[n - 1];
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (!has_next) break;
+    k += stride;
+    d_cur = d_nxt;
+    cur = read_desc(dbuf0 + d_cur * kDescBytes, tid);
   }
-  const ItemHead head = load_item_head(A, w);
-  // phase A (a lane only touches records it fetched itself; the warp sync is in run_item)
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- unstaged kernel: slabs too large for shared memory (a node with hundreds of neighbours) ------
+// One warp per oversized slab; records come from global memory per contribution, blocks go straight
+// to the CSR values. Entries are block-major: family<<30 | pair<<26 | slot in the slab's element list.
+__device__ __forceinline__ void add_contribution_raw(const double* __restrict__ raw, uint32_t code,
+                                                     double acc[36]) {
+  const uint32_t family = code >> 30, pair = (code >> 26) & 15u;
+  if (family == FEMGPU_PLATE) {
+    double S[kPlateSharedDoubles];
+    plate_shared_record(raw, S);
+    plate_block_shared(S, int(pair >> 2), int(pair & 3u), 1.0, raw[15] != 0.0, acc);
+  } else if (family == FEMGPU_BEAM) {
+    beam_block(raw, int(pair >> 1), int(pair & 1u), acc);
+  } else if (family == FEMGPU_TRUSS) {
+    truss_block(raw[0], raw[1], raw[2], raw[3], int(pair >> 1), int(pair & 1u), acc);
+  }
+}
+
+__global__ void __launch_bounds__(kAsmThreads)
+assemble_unstaged_kernel(const AsmArgs A) {
+  const uint32_t k = blockIdx.x, lane = threadIdx.x;
+  const SlabDesc d = A.slabs[k];
+  if (!(d.flags & 1u) || d.blk_count == 0) return;
+  const WorkItem w = A.items[size_t(k) * kAsmThreads + lane];
+  const uint4* meta = reinterpret_cast<const uint4*>(A.meta);
+  double* out = A.values + d.val_base;
+  const bool base_even = (d.val_base & 1) == 0;
+  uint32_t c = w.c_begin;
+  for (uint32_t p = w.blk_begin; p < w.blk_begin + (w.blk_count & 0xFFFFu); ++p) {
+    const uint4 m = __ldg(meta + p);
+    double acc[36];
 #pragma unroll
-  for (int j = 0; j < kElistStride / kAsmThreads; ++j) {
-    if (my_plate[j]) {
+    for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+    for (uint32_t j = 0; j < m.w; ++j, ++c) {
+      const uint32_t code = __ldg(A.contrib + c);
+      if ((code >> 30) == 3u) continue;  // remote placeholder
+      const uint32_t fe = __ldg(A.elist_compact + d.el_begin + (code & 0x03FFFFFFu));
       double raw[20];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const double2 v = reinterpret_cast<const double2*>(my_plate[j])[i];
-        raw[2 * i] = v.x;
-        raw[2 * i + 1] = v.y;
+      for (uint32_t ch = 0; ch < 10; ++ch) {
+        const double2* src = reinterpret_cast<const double2*>(record_chunk(A, fe, ch));
+        const double2 v = src ? __ldg(src) : make_double2(0.0, 0.0);
+        raw[2 * ch] = v.x;
+        raw[2 * ch + 1] = v.y;
       }
-      plate_shared_record(raw, my_plate[j]);
+      add_contribution_raw(raw, code, acc);
     }
+    store_block<false>(out, m, acc, base_even);
   }
-  run_item<true>(A, d, w, head, img, recs, true);
-  double* out = A.values + d.val_base;
-  const uint32_t n = d.val_count;
-  if (((d.val_base | n) & 1) == 0) {
-    // 16-byte aligned slab: generic-proxy writes -> async proxy, then one TMA bulk store
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out),
-                   "r"(smem_u32(img)), "r"(n * 8u)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    return;
-  }
-  __syncwarp();
-  // ragged slab (3-wide truss blocks): coalesced 16-byte stores on the aligned body
-  const uint32_t odd = uint32_t(d.val_base & 1);  // values[] is 16-byte aligned at index 0
-  if (odd && lane == 0) out[0] = img[0];
-  const uint32_t body = (n - odd) >> 1;
-  if (odd == 0) {
-    const double2* src = reinterpret_cast<const double2*>(img);
-    double2* dst = reinterpret_cast<double2*>(out);
-    for (uint32_t i = lane; i < body; i += kAsmThreads) dst[i] = src[i];
-  } else {
-    double2* dst = reinterpret_cast<double2*>(out + 1);
-    for (uint32_t i = lane; i < body; i += kAsmThreads)
-      dst[i] = make_double2(img[1 + 2 * i], img[2 + 2 * i]);
-  }
-  if (((n - odd) & 1u) && lane == 0) out[n - 1] = img[n - 1];
 }
 
 // test hook: the whole transformed element matrix of one element, built from the same block
@@ -317,8 +500,8 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
   A.beam_rec = beam_rec;
   A.plate_rec = plate_rec;
   A.plate_mat = plate_mat;
-  double rec[kRecStride];
-  for (uint32_t ch = 0; ch < kRecStride / 2; ++ch) {
+  double rec[20];
+  for (uint32_t ch = 0; ch < 10; ++ch) {
     const double* src = reinterpret_cast<const double*>(record_chunk(A, (uint32_t(family) << 26) | e, ch));
     rec[2 * ch] = src ? src[0] : 0.0;
     rec[2 * ch + 1] = src ? src[1] : 0.0;
@@ -335,12 +518,6 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
 int32_t run_assembly(Handle* h) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   if (h->n_slabs == 0) return 0;
-  static int attr_set_for = -1;
-  if (attr_set_for != h->device) {
-    FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              kSlabSmemBytes));
-    attr_set_for = h->device;
-  }
   AsmArgs A;
   A.slabs = h->slabs.p;
   A.meta = h->blk_meta.p;
@@ -354,9 +531,34 @@ int32_t run_assembly(Handle* h) {
   A.plate_mat = h->fd[FEMGPU_PLATE].mat.p;
   A.values = h->values.p;
   A.n_slabs = h->n_slabs;
-  assemble_kernel<<<h->n_slabs, kAsmThreads, h->slab_smem_bytes, h->stream>>>(A);
-  h->launches++;
-  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
+  A.smem_img = up(h->smem_img);
+  A.smem_form = up(h->smem_form);
+  A.smem_rawp = up(h->smem_rawp);
+  A.smem_stage = up(h->smem_stage);
+  const uint32_t smem = A.smem_img + A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * kDescBytes + 16;
+  if (h->n_unstaged < h->n_slabs) {
+    if (h->asm_smem_set != smem) {
+      FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                int(smem)));
+      int per_sm = 0;
+      FEMGPU_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel, kAsmThreads, smem));
+      if (per_sm < 1) return h->fail(FEMGPU_ERR_CUDA, "assemble_kernel does not fit on an SM");
+      if (h->sm_count == 0)
+        FEMGPU_CUDA_CHECK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+      h->asm_smem_set = smem;
+      h->asm_ctas_per_sm = per_sm;
+    }
+    const uint32_t grid = uint32_t(std::min<uint64_t>(h->n_slabs, uint64_t(h->sm_count) * h->asm_ctas_per_sm));
+    assemble_kernel<<<grid, kAsmThreads, smem, h->stream>>>(A);
+    h->launches++;
+    FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  }
+  if (h->n_unstaged) {
+    assemble_unstaged_kernel<<<h->n_slabs, kAsmThreads, 0, h->stream>>>(A);
+    h->launches++;
+    FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  }
   return 0;
 }
 

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -164,7 +165,7 @@ __global__ void col_idx_kernel(uint32_t n_nodes, int key_bits, const uint64_t* _
 
 __global__ void slab_kernel(uint32_t n_slabs, uint32_t quota, uint32_t n_nodes,
                             const uint32_t* __restrict__ node_blk_ptr,
-                            const int64_t* __restrict__ node_base, uint32_t smem_doubles,
+                            const int64_t* __restrict__ node_base,
                             SlabDesc* __restrict__ slabs, int32_t* __restrict__ overflow) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_slabs) return;
@@ -177,9 +178,10 @@ __global__ void slab_kernel(uint32_t n_slabs, uint32_t quota, uint32_t n_nodes,
   d.val_count = uint32_t(cnt);
   d.blk_begin = node_blk_ptr[first];
   d.blk_count = node_blk_ptr[next] - d.blk_begin;
-  d.flags = (d.val_count > smem_doubles) ? 1u : 0u;
-  d.el_begin = 0;
-  d.el_count = 0;
+  d.flags = 0;
+  d.c_begin = d.c_count = 0;
+  d.el_begin = d.el_count = 0;
+  d.n_truss = d.n_beam = 0;
   slabs[k] = d;
 }
 
@@ -220,55 +222,123 @@ __global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restri
 }
 
 // Work items: consecutive thread-ordered blocks of a slab are grouped greedily (blocks arrive in
-// descending cost) so that every thread of the CTA gets about the same cost. The cap W starts at
-// max(heaviest block, total / threads) and is raised until the slab fits in `threads` items.
-// One thread per slab walks its blocks; items are written to the dense [slab][thread] table.
-__global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, const SlabDesc* __restrict__ slabs,
+// descending cost) so that every thread of the CTA gets about the same cost W. A block heavier
+// than W (the diagonal block of a plate-grid node: 4 plate contributions, twice the per-thread
+// share) is split into up to kMaxChunks chunks of consecutive contributions (execution order), one
+// thread each: chunk 0 stores its partial sum, chunk j >= 1 adds its own after the j-th barrier
+// ("deferred round"). W starts at total / threads and is raised until the slab fits.
+// One thread per slab; items are written to the dense [slab][thread] table.
+__device__ __forceinline__ uint32_t family_cost(uint32_t f) {
+  return (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
+}
+// cost of the first p contributions of a block in execution order (placeholders, plates, beams, trusses)
+__device__ __forceinline__ uint32_t chunk_cum_cost(const uint32_t n[4], uint32_t p) {
+  const uint32_t cost[4] = {0u, kCostPlate, kCostBeam, kCostTruss};
+  uint32_t acc = 0;
+  for (int g = 0; g < 4; ++g) {
+    uint32_t t = min(p, n[g]);
+    acc += t * cost[g];
+    p -= t;
+  }
+  return acc;
+}
+
+__global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* __restrict__ slabs,
                                  const uint32_t* __restrict__ cost, const uint32_t* __restrict__ cptr_ord,
-                                 WorkItem* __restrict__ items) {
+                                 const uint32_t* __restrict__ contrib, WorkItem* __restrict__ items) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_slabs) return;
   const SlabDesc d = slabs[k];
   const uint32_t b0 = d.blk_begin, b1 = d.blk_begin + d.blk_count;
+  const bool staged = !(d.flags & 1u);
   uint64_t total = 0;
   uint32_t mx = 1;
   for (uint32_t b = b0; b < b1; ++b) {
     total += cost[b];
     mx = max(mx, cost[b]);
   }
-  uint64_t W = max(uint64_t(mx), (total + threads - 1) / threads);
+  uint64_t W = max(uint64_t(1), (total + threads - 1) / threads);
+  if (!staged) W = max(W, uint64_t(mx));  // the unstaged kernel takes whole blocks only
   for (;;) {
     uint32_t n = 0;
     uint64_t cur = 0;
+    bool open = false, ok = true;
     for (uint32_t b = b0; b < b1; ++b) {
-      if (b == b0 || cur + cost[b] > W) {
-        ++n;
-        cur = 0;
+      const uint32_t c = cost[b], cnt = cptr_ord[b + 1] - cptr_ord[b];
+      if (staged && c > W && cnt > 1) {
+        const uint64_t kk = min(uint64_t(cnt), (c + W - 1) / W);
+        if (kk > uint64_t(kMaxChunks)) ok = false;
+        n += uint32_t(kk);
+        open = false;
+      } else {
+        if (!open || cur + c > W) {
+          ++n;
+          cur = 0;
+          open = true;
+        }
+        cur += c;
       }
-      cur += cost[b];
     }
-    if (n <= threads) break;
+    if (ok && n <= threads) break;
     W += max(uint64_t(1), W / 8);
   }
   WorkItem* out = items + size_t(k) * threads;
-  uint32_t n = 0;
+  uint32_t n = 0, max_round = 0;
   uint64_t cur = 0;
+  bool open = false;
   uint32_t start = b0;
-  for (uint32_t b = b0; b <= b1; ++b) {
-    bool close = (b == b1) || (b != b0 && cur + cost[b] > W);
-    if (close && b > start) {
+  auto close_run = [&](uint32_t b_end) {
+    if (open && b_end > start) {
       WorkItem w;
       w.blk_begin = start;
-      w.blk_count = b - start;
+      w.blk_count = b_end - start;
       w.c_begin = cptr_ord[start];
-      w.c_count = cptr_ord[b] - cptr_ord[start];
+      w.c_count = cptr_ord[b_end] - cptr_ord[start];
       out[n++] = w;
-      start = b;
-      cur = 0;
     }
-    if (b < b1) cur += cost[b];
+    open = false;
+  };
+  for (uint32_t b = b0; b < b1; ++b) {
+    const uint32_t c = cost[b], c0 = cptr_ord[b], cnt = cptr_ord[b + 1] - c0;
+    if (staged && c > W && cnt > 1) {
+      close_run(b);
+      const uint32_t kk = uint32_t(min(uint64_t(cnt), (c + W - 1) / W));
+      uint32_t nf[4] = {0, 0, 0, 0};  // placeholders, plates, beams, trusses
+      for (uint32_t i = 0; i < cnt; ++i) {
+        const uint32_t f = contrib[c0 + i] >> 30;
+        nf[f == 3u ? 0 : (f == FEMGPU_PLATE ? 1 : (f == FEMGPU_BEAM ? 2 : 3))]++;
+      }
+      uint32_t s_prev = 0;
+      for (uint32_t j = 0; j < kk; ++j) {
+        uint32_t s_next = cnt;
+        if (j + 1 < kk) {
+          const uint32_t target = uint32_t(uint64_t(j + 1) * c / kk);
+          const uint32_t hi = cnt - (kk - 1 - j);  // leave one contribution for every later chunk
+          s_next = s_prev + 1;
+          while (s_next < hi && chunk_cum_cost(nf, s_next + 1) <= target) ++s_next;
+        }
+        WorkItem w;
+        w.blk_begin = b;
+        w.blk_count = 1u | (j << 16) | (1u << 24);
+        w.c_begin = c0 + s_prev;
+        w.c_count = s_next - s_prev;
+        out[n++] = w;
+        max_round = max(max_round, j);
+        s_prev = s_next;
+      }
+    } else {
+      if (!open || cur + c > W) {
+        close_run(b);
+        start = b;
+        cur = 0;
+        open = true;
+      }
+      cur += c;
+    }
   }
+  close_run(b1);
   for (; n < threads; ++n) out[n] = WorkItem{0u, 0u, 0u, 0u};
+  if (max_round) slabs[k].flags = d.flags | (max_round << 8);
 }
 
 // ---- per-slab element lists -----------------------------------------------------------------
@@ -309,8 +379,16 @@ __global__ void elist_kernel(uint32_t n, const uint64_t* __restrict__ keys, cons
   elist[u] = uint32_t(keys[i] & 0x0FFFFFFFu);
 }
 
+// bytes of a slab's double-buffered stage: block metadata, contribution entries (fetched from the
+// 16-byte aligned address below the first one), truss and beam records
+__host__ __device__ inline uint32_t slab_stage_bytes(uint32_t blk_count, uint32_t c_begin, uint32_t c_count,
+                                                     uint32_t nt, uint32_t nb) {
+  uint32_t ent = (((c_begin & 3u) + c_count + 1u) * 4u + 15u) & ~15u;  // +1: the loop peeks one entry ahead
+  return blk_count * 16u + ent + nt * uint32_t(kTrussSlotDoubles * 8) + nb * uint32_t(kBeamSlotDoubles * 8);
+}
+
 __global__ void slab_elist_kernel(uint32_t n_slabs, uint32_t n_unique, const uint64_t* __restrict__ ukey,
-                                  SlabDesc* __restrict__ slabs, uint32_t smem_bytes_cap,
+                                  const uint32_t* __restrict__ cptr_ord, SlabDesc* __restrict__ slabs,
                                   int32_t* __restrict__ flags) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_slabs) return;
@@ -323,15 +401,25 @@ __global__ void slab_elist_kernel(uint32_t n_slabs, uint32_t n_unique, const uin
   SlabDesc d = slabs[k];
   d.el_begin = b;
   d.el_count = e - b;
-  const uint32_t nt = b1 - b, nb = b2 - b1, np = b3 - b2;
-  // record area: [trusses][beams][plates, in their shared form]
-  uint64_t need = ((uint64_t(d.val_count) * 8 + 15) & ~uint64_t(15)) +
-                  (uint64_t(nt) * kTrussSlotDoubles + uint64_t(nb) * kBeamSlotDoubles +
-                   uint64_t(np) * kPlateSlotDoubles) * 8;
-  if (need > smem_bytes_cap || (e - b) > uint32_t(kElistStride)) d.flags |= 1u;
-  if (!(d.flags & 1u)) {
-    d.flags |= (nt << 8) | (nb << 20);  // both <= kElistStride
-    atomicMax(flags + 2, int32_t(need));  // largest staged slab (integer max)
+  d.n_truss = b1 - b;
+  d.n_beam = b2 - b1;
+  const uint32_t np = b3 - b2;
+  d.c_begin = cptr_ord[d.blk_begin];
+  d.c_count = cptr_ord[d.blk_begin + d.blk_count] - d.c_begin;
+  const uint64_t img = (uint64_t(d.val_count) * 8 + 15) & ~uint64_t(15);
+  const uint32_t form = np * uint32_t(kPlateSlotDoubles * 8), rawp = np * 160u;
+  const uint32_t stage = slab_stage_bytes(d.blk_count, d.c_begin, d.c_count, d.n_truss, d.n_beam);
+  if (img > uint64_t(kCapImgBytes) || form > uint32_t(kCapFormBytes) || stage > uint32_t(kCapStageBytes) ||
+      d.el_count > uint32_t(kElistStride) || d.blk_count > uint32_t(kCapBlocks))
+    d.flags |= 1u;
+  if (d.flags & 1u) {
+    atomicAdd(flags + 12, 1);
+  } else {  // integer maxima: order independent
+    d.flags |= np << 16;
+    atomicMax(flags + 8, int32_t(img));
+    atomicMax(flags + 9, int32_t(form));
+    atomicMax(flags + 10, int32_t(rawp));
+    atomicMax(flags + 11, int32_t(stage));
   }
   slabs[k] = d;
 }
@@ -346,8 +434,8 @@ __global__ void elist_table_kernel(uint32_t n_slabs, const SlabDesc* __restrict_
   table[t] = (e < d.el_count && !(d.flags & 1u)) ? compact[d.el_begin + e] : 0xFFFFFFFFu;
 }
 
-// contrib codes become family<<30 | pair<<26 | where the element's record sits: its offset in the
-// CTA's record area in 16-byte units (staged slabs), or its slot in the slab's element list
+// contrib codes become family<<30 | pair<<26 | where the element's record sits: its offset inside
+// the family's record area in 16-byte units (staged slabs), or its slot in the slab's element list
 __global__ void relabel_kernel(uint32_t n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload,
                                const uint32_t* __restrict__ uidx, const SlabDesc* __restrict__ slabs,
                                uint32_t* __restrict__ contrib_ord) {
@@ -359,14 +447,80 @@ __global__ void relabel_kernel(uint32_t n, const uint64_t* __restrict__ keys, co
   uint32_t c = payload[i];
   const uint32_t code = contrib_ord[c], family = code >> 30;
   if (!(d.flags & 1u)) {
-    const uint32_t nt = (d.flags >> 8) & 0xFFFu, nb = d.flags >> 20;
-    constexpr uint32_t ut = kTrussSlotDoubles / 2, ub = kBeamSlotDoubles / 2, up = kPlateSlotDoubles / 2;
-    if (family == FEMGPU_TRUSS) local = local * ut;
-    else if (family == FEMGPU_BEAM) local = nt * ut + (local - nt) * ub;
-    else if (family == FEMGPU_PLATE) local = nt * ut + nb * ub + (local - nt - nb) * up;
+    if (family == FEMGPU_TRUSS) local = local * uint32_t(kTrussSlotDoubles / 2);
+    else if (family == FEMGPU_BEAM) local = (local - d.n_truss) * uint32_t(kBeamSlotDoubles / 2);
+    else if (family == FEMGPU_PLATE) local = (local - d.n_truss - d.n_beam) * uint32_t(kPlateSlotDoubles / 2);
     else local = 0;
   }
   contrib_ord[c] = (code & 0xFC000000u) | local;
+}
+
+// Staged slabs: rewrite each lane's contributions from block-major order into the lane's execution
+// order — family-major (placeholders, plates, beams, trusses) over the lane's blocks, insertion order
+// inside a (block, family) group — and attach the group-end / read-modify-write / deferred-round
+// flags and the block index. One thread per work item; entries stay inside the item's own range.
+__global__ void item_program_kernel(uint32_t n_slabs, const SlabDesc* __restrict__ slabs,
+                                    const WorkItem* __restrict__ items, const uint32_t* __restrict__ cptr_ord,
+                                    const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+  uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t k = uint32_t(t / kAsmThreads);
+  if (k >= n_slabs) return;
+  const WorkItem w = items[t];
+  const uint32_t n_blk = w.blk_count & 0xFFFFu;
+  if (n_blk == 0) return;
+  const SlabDesc d = slabs[k];
+  if (d.flags & 1u) {
+    for (uint32_t c = w.c_begin; c < w.c_begin + w.c_count; ++c) dst[c] = src[c];
+    return;
+  }
+  uint32_t out = w.c_begin;
+  const uint32_t order[4] = {3u, uint32_t(FEMGPU_PLATE), uint32_t(FEMGPU_BEAM), uint32_t(FEMGPU_TRUSS)};
+  if (w.blk_count & (1u << 24)) {
+    // one chunk of a split block: contributions [skip, skip + take) of the block's execution order,
+    // accumulated as a single group
+    const uint32_t p = w.blk_begin, c0 = cptr_ord[p], c1 = cptr_ord[p + 1];
+    const uint32_t skip = w.c_begin - c0, take = w.c_count, round = (w.blk_count >> 16) & 3u;
+    const uint32_t blk = p - d.blk_begin;
+    uint32_t pos = 0, left = take;
+    for (int f = 0; f < 4; ++f)
+      for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t code = src[c];
+        if ((code >> 30) != order[f]) continue;
+        if (pos >= skip && pos < skip + take) {
+          uint32_t e = (code & 0xFC000000u) | (blk << kEntBlkShift) | (code & kEntRecMask);
+          if (--left == 0) e |= kEntEnd | (round << kEntDeferShift) | (round ? kEntRmw : 0u);
+          dst[out++] = e;
+        }
+        ++pos;
+      }
+    return;
+  }
+  for (int f = 0; f < 4; ++f) {
+    const uint32_t fam = order[f];
+    for (uint32_t p = w.blk_begin; p < w.blk_begin + n_blk; ++p) {
+      const uint32_t c0 = cptr_ord[p], c1 = cptr_ord[p + 1];
+      uint32_t in_group = 0, earlier = 0;
+      for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t cf = src[c] >> 30;
+        if (cf == fam) ++in_group;
+        else {
+          int pos = 0;  // does family cf come before fam in the execution order?
+          for (int g = 0; g < 4; ++g) if (order[g] == cf) pos = g;
+          if (pos < f) ++earlier;
+        }
+      }
+      if (!in_group) continue;
+      const uint32_t blk = p - d.blk_begin;
+      uint32_t left = in_group;
+      for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t code = src[c];
+        if ((code >> 30) != fam) continue;
+        uint32_t e = (code & 0xFC000000u) | (blk << kEntBlkShift) | (code & kEntRecMask);
+        if (--left == 0) e |= kEntEnd | (earlier ? kEntRmw : 0u);
+        dst[out++] = e;
+      }
+    }
+  }
 }
 
 __global__ void ordered_meta_kernel(uint32_t n_blocks, uint32_t quota, int key_bits,
@@ -772,12 +926,13 @@ int32_t run_symbolic(Handle* h) {
   h->launches += 2;
 
   // ---- 4. slabs and the in-slab thread order
-  const uint32_t quota = kSlabQuota;
+  uint32_t quota = kSlabQuota;
+  if (const char* q = getenv("FEMGPU_SLAB_QUOTA")) quota = std::max(1, atoi(q));  // tuning knob
   uint32_t n_slabs = div_up(nblk, quota);
   h->n_slabs = n_slabs;
   SYM_CHECK(h->slabs.reserve(n_slabs));
   slab_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, quota, N, h->node_blk_ptr.p, h->node_base.p,
-                                                   uint32_t(kSlabSmemBytes / 8), h->slabs.p, h->d_flag.p);
+                                                   h->slabs.p, h->d_flag.p);
   h->launches++;
   Tmp okey_a, okey_b, oval_a;
   SYM_CHECK(okey_a.alloc(size_t(nblk) * 8));
@@ -817,7 +972,7 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, ocnt.as<uint32_t>(), h->blk_cptr.p, int(nblk + 1), s));
     SYM_CHECK(cudaStreamSynchronize(s));
   }
-  SYM_CHECK(h->contrib.reserve(size_t(NCt) + 1));  // +1: the kernel peeks one code ahead to prefetch
+  SYM_CHECK(h->contrib.reserve(size_t(NCt) + 8));  // +8: entries are fetched in 16-byte chunks, one entry ahead
   SYM_CHECK(h->blk_meta.reserve(size_t(nblk) + 1));  // +1: the kernel loads one block ahead
   ordered_meta_kernel<<<div_up(nblk, 256), 256, 0, s>>>(nblk, quota, kb, h->blk_order.p, h->blk_key.p,
                                                         h->node_blk_ptr.p, h->blk_off.p, h->node_len.p,
@@ -827,7 +982,7 @@ int32_t run_symbolic(Handle* h) {
   h->launches++;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
-  SYM_CHECK(cudaMemsetAsync(h->contrib.p + NCt, 0, 4, s));
+  SYM_CHECK(cudaMemsetAsync(h->contrib.p + NCt, 0, 32, s));
   SYM_CHECK(cudaMemsetAsync(h->blk_meta.p + nblk, 0, sizeof(BlockMeta), s));
   // per-slab element lists; contrib codes are relabelled to slab-local element slots
   {
@@ -869,8 +1024,8 @@ int32_t run_symbolic(Handle* h) {
     uint64_t* ukey = ekey_a;  // reuse: ekey_a is dead after the sort
     elist_kernel<<<div_up(NCt, 256), 256, 0, s>>>(uint32_t(NCt), ekey_b, eflag.as<uint32_t>(), euidx.as<uint32_t>(),
                                                  ukey, h->elist_compact.p);
-    slab_elist_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, n_unique, ukey, h->slabs.p,
-                                                           uint32_t(kSlabSmemBytes), h->d_flag.p);
+    slab_elist_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, n_unique, ukey, h->blk_cptr.p, h->slabs.p,
+                                                           h->d_flag.p);
     relabel_kernel<<<div_up(NCt, 256), 256, 0, s>>>(uint32_t(NCt), ekey_b, epay_b.as<uint32_t>(), euidx.as<uint32_t>(),
                                                    h->slabs.p, h->contrib.p);
     elist_table_kernel<<<div_up(uint64_t(n_slabs) * kElistStride, 256), 256, 0, s>>>(n_slabs, h->slabs.p,
@@ -882,14 +1037,28 @@ int32_t run_symbolic(Handle* h) {
   // balanced per-thread work lists (needs blk_cptr, filled above)
   SYM_CHECK(h->items.reserve(size_t(n_slabs) * kAsmThreads));
   work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, kAsmThreads, h->slabs.p, ocost.as<uint32_t>(),
-                                                         h->blk_cptr.p, h->items.p);
+                                                         h->blk_cptr.p, h->contrib.p, h->items.p);
   h->launches++;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
-  int32_t flags[4] = {0, 0, 0, 0};
-  SYM_CHECK(cudaMemcpy(flags, h->d_flag.p, 16, cudaMemcpyDeviceToHost));
+  {
+    Tmp prog;
+    SYM_CHECK(prog.alloc((size_t(NCt) + 1) * 4));
+    item_program_kernel<<<div_up(uint64_t(n_slabs) * kAsmThreads, 256), 256, 0, s>>>(
+        n_slabs, h->slabs.p, h->items.p, h->blk_cptr.p, h->contrib.p, prog.as<uint32_t>());
+    h->launches++;
+    SYM_CHECK(cudaGetLastError());
+    SYM_CHECK(cudaMemcpyAsync(h->contrib.p, prog.p, size_t(NCt) * 4, cudaMemcpyDeviceToDevice, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+  }
+  int32_t flags[16] = {0};
+  SYM_CHECK(cudaMemcpy(flags, h->d_flag.p, 64, cudaMemcpyDeviceToHost));
   if (flags[0]) return h->fail(FEMGPU_ERR_LIMIT, "a slab holds 2^32 or more values");
-  h->slab_smem_bytes = (uint32_t(flags[2]) + 15) & ~15u;
+  h->smem_img = uint32_t(flags[8]);
+  h->smem_form = uint32_t(flags[9]);
+  h->smem_rawp = uint32_t(flags[10]);
+  h->smem_stage = uint32_t(flags[11]);
+  h->n_unstaged = uint32_t(flags[12]);
 
   if (h->dist.enabled) {
     int32_t st = dist_finalize_plan(h, ranges);

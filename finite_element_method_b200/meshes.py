@@ -263,3 +263,47 @@ def local_part(mesh, begin: int, end: int):
         if mesh.get("t_A2") is not None:
             out["t_A2"] = mesh["t_A2"][k]
     return out
+
+
+def hub_star(n_spokes=700, beams_every=7):
+    """One hub node joined to `n_spokes` rim nodes on a sphere by trusses (every `beams_every`-th spoke
+    also carries a beam). The hub's rows are far larger than a slab image, so this mesh drives the
+    unstaged assembly kernel; the rim nodes go through the staged one."""
+    rng = np.random.default_rng(20240611)
+    n = n_spokes + 1
+    m = _empty(n)
+    v = rng.normal(size=(3, n_spokes))
+    v /= np.linalg.norm(v, axis=0)
+    v *= 1.0 + rng.uniform(0.0, 0.5, n_spokes)
+    v[0] = np.abs(v[0]) + 0.05           # every spoke has a +x component (see the beam note in DESIGN.md)
+    m["x"][1:], m["y"][1:], m["z"][1:] = v[0], v[1], v[2]
+    rim = np.arange(1, n, dtype=np.uint32)
+    m["t_n1"] = np.zeros(n_spokes, np.uint32); m["t_n2"] = rim
+    m["t_E"] = np.full(n_spokes, 2.1e11); m["t_A"] = 1e-4 * (1.0 + rng.uniform(0, 1, n_spokes))
+    bsel = rim[::beams_every]
+    nb = len(bsel)
+    u = rng.uniform(0, 1, nb)
+    m["b_n1"] = np.zeros(nb, np.uint32); m["b_n2"] = bsel.astype(np.uint32)
+    m["b_props"] = np.stack([np.full(nb, 2.1e11), np.full(nb, 0.3), 1e-2 * (1 + u), 8e-6 * (1 + u), 4e-6 * (1 + u),
+                             np.zeros(nb), np.full(nb, 1e-5), np.full(nb, 5.0 / 6.0)])
+    m["b_axis"] = np.tile(np.array([[0.1], [0.2], [1.0]]), (1, nb))
+    m["name"] = f"hub-star-{n_spokes}"
+    return m
+
+
+def folded_plate(nx=12, ny=8):
+    """A plate strip folded along a grid line: rows j < ny/2 lie in the z = 0 plane (Q == I, the
+    flat fast path), the rest in a plane tilted about the x axis (general Q) — slabs along the fold
+    hold both kinds."""
+    m = plate_grid(nx, ny, "flat")
+    w = nx + 1
+    j = np.arange(len(m["x"])) // w
+    fold = ny // 2
+    y0 = m["y"][fold * w]
+    up = j > fold
+    dy = m["y"][up] - y0
+    m["y"] = m["y"].copy(); m["z"] = m["z"].copy()
+    m["y"][up] = y0 + dy * 0.8
+    m["z"][up] = dy * 0.6
+    m["name"] = f"folded-plate-{nx}x{ny}"
+    return m

@@ -1,0 +1,27 @@
+set -x
+mkdir -p gpurun_out
+TAG=${TAG:-r1j}
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for c in P M B T; do
+python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_$c.json 2> gpurun_out/${TAG}_bench_$c.err
+done
+for q in 54 36; do
+FEMGPU_SLAB_QUOTA=$q python bench.py --config P --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_Pq$q.json 2> gpurun_out/${TAG}_bench_Pq$q.err
+FEMGPU_SLAB_QUOTA=$q python bench.py --config M --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_Mq$q.json 2> gpurun_out/${TAG}_bench_Mq$q.err
+done
+python - <<'PY'
+import json,glob,os
+tag=os.environ.get('TAG','r1j')
+for f in sorted(glob.glob(f'gpurun_out/{tag}_bench_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        r=d['roofline']
+        print(f, 'Gelem/s=%.3f step_ms=%.3f asm_ms=%.3f prep_ms=%.3f frac=%.3f'%(d['value']/1e9,d['ms_per_step'],r['kernel_ms'],r['prep_ms'],r['frac']))
+    except Exception as e:
+        print(f,'ERR',e, open(f.replace('.json','.err')).read()[-2000:])
+PY
+if [ -n "$NCU" ]; then
+for c in $NCU; do
+ncu --set full --clock-control none --import-source on -k regex:assemble_kernel -s 1 -c 1 -o gpurun_out/prof_${c}_${TAG} -f python bench.py --config $c --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_${c}_${TAG}.log 2>&1
+done
+fi

@@ -39,6 +39,8 @@ SMALL = {
     "plate-jitter": lambda: meshes.plate_grid(12, 9, "jitter"),
     "plate-x0-plane": lambda: meshes.plate_grid(12, 9, "x0"),
     "mixed": lambda: meshes.mixed_structure(12, 10),
+    "folded-plate-flat-and-tilted": lambda: meshes.folded_plate(12, 8),
+    "hub-star-unstaged-slab": lambda: meshes.hub_star(700, 7),
 }
 
 
