@@ -175,7 +175,7 @@ struct BlockMeta {
 };
 
 // One thread's share of a slab: a run of consecutive thread-ordered blocks (and therefore of
-// consecutive contributions). Stored as a dense [n_slabs][kAsmThreads] table so a thread can fetch
+// consecutive contributions). Stored as a dense [n_slabs][asm_threads] table so a thread can fetch
 // its item without first reading the slab descriptor.
 struct WorkItem {
   uint32_t blk_begin;  // first block (thread order)
@@ -273,7 +273,7 @@ struct Handle {
   DevBuf<uint32_t> contrib;        // family<<30 | pair<<26 | element, thread order
   DevBuf<BlockMeta> blk_meta;      // thread order
   DevBuf<uint32_t> blk_order;      // thread position -> sorted block id
-  DevBuf<WorkItem> items;          // [n_slabs][kAsmThreads] balanced per-thread work lists
+  DevBuf<WorkItem> items;          // [n_slabs][asm_threads] balanced per-thread work lists
   DevBuf<uint32_t> elist;          // [n_slabs][kElistStride]: family<<26 | element, 0xFFFFFFFF = empty;
                                    // (compact list when a slab overflows the table: unstaged path)
   DevBuf<uint32_t> elist_compact;
@@ -281,6 +281,7 @@ struct Handle {
   uint32_t smem_img = 0, smem_form = 0, smem_rawp = 0, smem_stage = 0;
   uint32_t n_unstaged = 0;         // slabs handled by assemble_unstaged_kernel
   int sm_count = 0;
+  int asm_threads = 32;            // 32 or 64, fixed by the symbolic pass
   uint32_t asm_smem_set = 0;       // dynamic shared memory assemble_kernel is currently configured for
   int asm_ctas_per_sm = 0;         // persistent CTAs per SM at that size (occupancy query)
   DevBuf<uint32_t> node_blk_ptr;   // [n_nodes_total+1]
@@ -338,7 +339,11 @@ int32_t dist_allgather_i64(Handle* h, const int64_t* send, int64_t* recv, size_t
 int32_t dist_exchange_8(Handle* h, const void* send, const int64_t* send_offs, const int64_t* send_counts,
                         void* recv, const int64_t* recv_offs, const int64_t* recv_counts);  // dist.cu
 
-constexpr int kAsmThreads = 32;            // threads per assembly CTA (32 or 64: one or two warps per slab)
+// Threads per assembly CTA = lanes that share one slab: 32 or 64, chosen by the symbolic pass
+// (Handle::asm_threads). One warp has the lowest per-slab overhead and wins on single-family plate /
+// truss meshes; two warps double the resident warps per SM at the same shared memory and balance
+// mixed and beam meshes better (measured, see profiles/).
+constexpr int kAsmThreadsMax = 64;
 constexpr int kSlabQuota = 72;             // node-pair blocks a slab aims for (8 plate-grid nodes)
 // per-slab capacity of the staged kernel's shared-memory regions; a slab exceeding any of them (a
 // node with hundreds of neighbours) goes to the unstaged kernel

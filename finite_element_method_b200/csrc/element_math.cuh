@@ -416,16 +416,22 @@ __device__ inline int hull_size4(double px[4], double py[4]) {
   return len;
 }
 
+// kCheck = false builds the record only: the numeric pass runs on elements that already passed
+// validation (femgpu_symbolic validates everything pending), so the validity-only work — collinearity,
+// coplanarity and the Graham scan with its four acos — is not repeated per pass.
+template <bool kCheck = true>
 __device__ inline int plate_record(const double p1[3], const double p2[3], const double p3[3],
                                    const double p4[3], double young_modulus, double poisson_ratio,
                                    double thickness, double shear_factor, double abs_tol,
                                    double rec[16], double mat[4]) {
   // structs/plate.rs:58-158
-  if (young_modulus <= 0.0) return EV_YOUNG;
-  if (poisson_ratio <= 0.0) return EV_POISSON;
-  if (thickness <= 0.0) return EV_THICKNESS;
-  if (shear_factor <= 0.0) return EV_SHEAR_FACTOR;
-  {  // quadrilateral_4n_element_functions.rs:14-86
+  if (kCheck) {
+    if (young_modulus <= 0.0) return EV_YOUNG;
+    if (poisson_ratio <= 0.0) return EV_POISSON;
+    if (thickness <= 0.0) return EV_THICKNESS;
+    if (shear_factor <= 0.0) return EV_SHEAR_FACTOR;
+  }
+  if (kCheck) {  // quadrilateral_4n_element_functions.rs:14-86
     const double* P[4] = {p1, p2, p3, p4};
     const int pr[4][3] = {{0, 1, 3}, {1, 0, 2}, {2, 1, 3}, {3, 2, 0}};
     for (int k = 0; k < 4; ++k) {
@@ -439,7 +445,7 @@ __device__ inline int plate_record(const double p1[3], const double p2[3], const
       if (norm3(cr) == 0.0) return EV_ON_LINE;
     }
   }
-  {  // quadrilateral_4n_element_functions.rs:88-129
+  if (kCheck) {  // quadrilateral_4n_element_functions.rs:88-129
     double v32[3] = {p2[0] - p3[0], p2[1] - p3[1], p2[2] - p3[2]};
     double v34[3] = {p4[0] - p3[0], p4[1] - p3[1], p4[2] - p3[2]};
     double n[3];
@@ -457,7 +463,7 @@ __device__ inline int plate_record(const double p1[3], const double p2[3], const
   mat3_vec(q, d1, t1);  // quadrilateral_4n_element_functions.rs:340-378
   mat3_vec(q, d2, t2);
   mat3_vec(q, d4, t4);
-  {  // quadrilateral_4n_element_functions.rs:173-250 + convex_hull_on_plane.rs
+  if (kCheck) {  // quadrilateral_4n_element_functions.rs:173-250 + convex_hull_on_plane.rs
     double hx[4] = {t1[0], t2[0], 0.0, t4[0]};
     double hy[4] = {t1[1], t2[1], 0.0, t4[1]};
     if (hull_size4(hx, hy) != 4) return EV_NOT_CONVEX;
@@ -677,21 +683,61 @@ __device__ __forceinline__ void plate_shared_record(const double* __restrict__ r
   S[63] = raw[15];
 }
 
+// Everything plate_block_shared derives from the local node pair (la, lb) alone: where the two nodes'
+// entries sit inside the shared record (byte offsets) and the natural-coordinate signs. The staged
+// kernel keeps the 16 possible entries in shared memory so a contribution costs five loads instead
+// of ~40 integer/select instructions.
+struct __align__(16) PlatePair {
+  uint32_t na, nb;      // n[0][la], n[0][lb]                       (stride between Gauss points: 64 B)
+  uint32_t era, esa;    // node a: its s-edge (1-2 or 4-3) for gamma_rz, its r-edge (1-4 or 2-3) for gamma_sz
+  uint32_t erb, esb;    // node b
+  uint32_t crz, csz;    // the (ea, eb) / (xa, xb) sign combination's shear sums
+  double xa, ea, xb, eb;  // +-0.5: half the natural coordinates of the two nodes
+  double drill;           // KROT6 on the diagonal (plate.rs:25)
+  double pad;
+};
+__host__ __device__ inline PlatePair make_plate_pair(int la, int lb) {
+  // natural-coordinate signs of nodes 1..4: (+,+), (-,+), (-,-), (+,-)
+  const int an = (la ^ (la >> 1)) & 1, bn = (lb ^ (lb >> 1)) & 1;  // 1 when xi = -1
+  const int am = la >> 1, bm = lb >> 1;                            // 1 when eta = -1
+  PlatePair t;
+  t.na = uint32_t(la) * 16u;
+  t.nb = uint32_t(lb) * 16u;
+  t.era = uint32_t(42 + 2 * am) * 8u;
+  t.esa = uint32_t(46 + 2 * an) * 8u;
+  t.erb = uint32_t(42 + 2 * bm) * 8u;
+  t.esb = uint32_t(46 + 2 * bn) * 8u;
+  t.crz = uint32_t(36 + ((am == bm) ? am : 2)) * 8u;
+  t.csz = uint32_t(39 + ((an == bn) ? an : 2)) * 8u;
+  t.xa = an ? -0.5 : 0.5;
+  t.ea = am ? -0.5 : 0.5;
+  t.xb = bn ? -0.5 : 0.5;
+  t.eb = bm ? -0.5 : 0.5;
+  t.drill = (la == lb) ? 1.0 : 0.0;
+  t.pad = 0.0;
+  return t;
+}
+
 // acc = keep * acc + block (la, lb) of (R^T k) R of the plate whose shared record is S; keep is 1
 // (accumulate) or 0 (first contribution of a block: no separate zeroing of the accumulators).
 // all_flat: every plate of the slab has Q == I exactly (flat plates in the global xy plane), then
 // (R^T k) R == k and only the 14 structural entries of the local block are touched — the other 22
 // accumulators are never written by a flat plate and must already be zero.
-__device__ __forceinline__ void plate_block_shared(const double* __restrict__ S, int la, int lb,
+__device__ __forceinline__ void plate_block_shared(const double* __restrict__ S, const PlatePair& pt,
                                                    double keep, bool all_flat, double acc[36]) {
-  const double2* n2 = reinterpret_cast<const double2*>(S);
+  const uint4 o0 = *reinterpret_cast<const uint4*>(&pt.na);
+  const uint4 o1 = *reinterpret_cast<const uint4*>(&pt.erb);
+  const double2 sa = *reinterpret_cast<const double2*>(&pt.xa);
+  const double2 sb = *reinterpret_cast<const double2*>(&pt.xb);
+  const char* Sb = reinterpret_cast<const char*>(S);
   const double2 rd01 = *reinterpret_cast<const double2*>(S + 32);
   const double2 rd23 = *reinterpret_cast<const double2*>(S + 34);
   const double rd[4] = {rd01.x, rd01.y, rd23.x, rd23.y};
   double sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
 #pragma unroll
   for (int ip = 0; ip < 4; ++ip) {
-    const double2 na = n2[ip * 4 + la], nb = n2[ip * 4 + lb];
+    const double2 na = *reinterpret_cast<const double2*>(Sb + o0.x + ip * 64);
+    const double2 nb = *reinterpret_cast<const double2*>(Sb + o0.y + ip * 64);
     const double pax = na.x * rd[ip], pay = na.y * rd[ip];
     sxx += pax * nb.x;
     sxy += pax * nb.y;
@@ -705,28 +751,23 @@ __device__ __forceinline__ void plate_block_shared(const double* __restrict__ S,
   const double t3 = nu * syx + gp * sxy, t4 = syy + gp * sxx;
   const double m00 = Cm * t1, m01 = Cm * t2, m10 = Cm * t3, m11 = Cm * t4;
   const double b33 = Cb * t4, b34 = -(Cb * t3), b43 = -(Cb * t2), b44 = Cb * t1;
-  // natural-coordinate signs of nodes 1..4: (+,+), (-,+), (-,-), (+,-)
-  const int an = (la ^ (la >> 1)) & 1, bn = (lb ^ (lb >> 1)) & 1;  // 1 when xi = -1
-  const int am = la >> 1, bm = lb >> 1;                            // 1 when eta = -1
-  const double xa = an ? -0.5 : 0.5, ea = am ? -0.5 : 0.5;
-  const double xb = bn ? -0.5 : 0.5, eb = bm ? -0.5 : 0.5;
   // gamma_rz rows use the node's s-edge (1-2 or 4-3), gamma_sz rows its r-edge (1-4 or 2-3)
-  const double2 era = *reinterpret_cast<const double2*>(S + 42 + 2 * am);
-  const double2 esa = *reinterpret_cast<const double2*>(S + 46 + 2 * an);
-  const double2 erb = *reinterpret_cast<const double2*>(S + 42 + 2 * bm);
-  const double2 esb = *reinterpret_cast<const double2*>(S + 46 + 2 * bn);
-  const double crz = S[36 + ((am == bm) ? am : 2)];
-  const double csz = S[39 + ((an == bn) ? an : 2)];
-  const double arz[3] = {crz * xa, crz * -era.y, crz * era.x};
-  const double asz[3] = {csz * ea, csz * -esa.y, csz * esa.x};
-  const double brz[3] = {xb, -erb.y, erb.x};
-  const double bsz[3] = {eb, -esb.y, esb.x};
+  const double2 era = *reinterpret_cast<const double2*>(Sb + o0.z);
+  const double2 esa = *reinterpret_cast<const double2*>(Sb + o0.w);
+  const double2 erb = *reinterpret_cast<const double2*>(Sb + o1.x);
+  const double2 esb = *reinterpret_cast<const double2*>(Sb + o1.y);
+  const double crz = *reinterpret_cast<const double*>(Sb + o1.z);
+  const double csz = *reinterpret_cast<const double*>(Sb + o1.w);
+  const double arz[3] = {crz * sa.x, crz * -era.y, crz * era.x};
+  const double asz[3] = {csz * sa.y, csz * -esa.y, csz * esa.x};
+  const double brz[3] = {sb.x, -erb.y, erb.x};
+  const double bsz[3] = {sb.y, -esb.y, esb.x};
   double sh[9];
 #pragma unroll
   for (int p = 0; p < 3; ++p)
 #pragma unroll
     for (int c = 0; c < 3; ++c) sh[3 * p + c] = arz[p] * brz[c] + asz[p] * bsz[c];
-  const double drill = (la == lb) ? 1.0 : 0.0;  // KROT6, plate.rs:25
+  const double drill = pt.drill;
   if (all_flat) {
     acc[0] = fma(acc[0], keep, m00);
     acc[1] = fma(acc[1], keep, m01);

@@ -142,21 +142,23 @@ __device__ __forceinline__ void store_block(double* __restrict__ img, const uint
 
 // ---- staged, persistent, pipelined kernel --------------------------------------------------------
 
-constexpr int kElistPerLane = kElistStride / kAsmThreads;
-static_assert(kElistStride % kAsmThreads == 0 && (kAsmThreads == 32 || kAsmThreads == 64), "CTA shape");
-
+// kT = threads per CTA (32 or 64), a template parameter of everything below.
 // CTA-wide barrier / vote: a warp-level sync when the CTA is a single warp
+template <int kT>
 __device__ __forceinline__ void cta_sync() {
-  if (kAsmThreads == 32) __syncwarp();
+  if (kT == 32) __syncwarp();
   else __syncthreads();
 }
+template <int kT>
 __device__ __forceinline__ bool cta_all(bool pred) {
-  if (kAsmThreads == 32) return __all_sync(0xFFFFFFFFu, pred) != 0;
+  if (kT == 32) return __all_sync(0xFFFFFFFFu, pred) != 0;
   return __syncthreads_and(pred) != 0;
 }
 
 // what a thread keeps in registers about a slab that is still to come
+template <int kT>
 struct SlabRegs {
+  static constexpr int kElistPerLane = kElistStride / kT;
   uint4 d0, d1, d2;             // the SlabDesc as three 16-byte words
   uint32_t fe[kElistPerLane];   // the thread's slots of the slab's element list
   uint32_t c_begin, c_count;    // the thread's work item
@@ -195,29 +197,33 @@ struct SlabRegs {
   }
 };
 
-// Descriptor block of a slab in shared memory: [SlabDesc 48 B][work items kAsmThreads x 16 B][element
+// Descriptor block of a slab in shared memory: [SlabDesc 48 B][work items kT x 16 B][element
 // list kElistStride x 4 B]. Everything is addressable from the slab id alone (dense tables), so it
 // is requested two slabs ahead with cp.async; nothing that is in flight lives in registers.
-constexpr uint32_t kDescItemsOff = 48, kDescElistOff = kDescItemsOff + kAsmThreads * 16;
-constexpr uint32_t kDescBytes = (kDescElistOff + kElistStride * 4 + 127) & ~127u;
+constexpr uint32_t kDescItemsOff = 48;
+template <int kT> __host__ __device__ constexpr uint32_t desc_elist_off() { return kDescItemsOff + kT * 16; }
+template <int kT> __host__ __device__ constexpr uint32_t desc_bytes() { return (desc_elist_off<kT>() + kElistStride * 4 + 127) & ~127u; }
 
+template <int kT>
 __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_t dbuf_s, uint32_t tid) {
-  cp_async16(dbuf_s + kDescItemsOff + tid * 16u, A.items + size_t(k) * kAsmThreads + tid);
-  if (tid < kElistStride / 4) cp_async16(dbuf_s + kDescElistOff + tid * 16u, A.elist + size_t(k) * kElistStride + tid * 4u);
+  cp_async16(dbuf_s + kDescItemsOff + tid * 16u, A.items + size_t(k) * kT + tid);
+  if (tid < kElistStride / 4) cp_async16(dbuf_s + desc_elist_off<kT>() + tid * 16u, A.elist + size_t(k) * kElistStride + tid * 4u);
   else if (tid < kElistStride / 4 + 3)
     cp_async16(dbuf_s + (tid - kElistStride / 4) * 16u,
                reinterpret_cast<const uint4*>(A.slabs + k) + (tid - kElistStride / 4));
 }
 
-__device__ __forceinline__ SlabRegs read_desc(const unsigned char* dbuf, uint32_t tid) {
-  SlabRegs R;
+template <int kT>
+__device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uint32_t tid) {
+  SlabRegs<kT> R;
+  constexpr int kElistPerLane = kElistStride / kT;
   const uint4* sp = reinterpret_cast<const uint4*>(dbuf);
   R.d0 = sp[0];
   R.d1 = sp[1];
   R.d2 = sp[2];
 #pragma unroll
   for (int j = 0; j < kElistPerLane; ++j)
-    R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + kDescElistOff)[j * kAsmThreads + tid];
+    R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>())[j * kT + tid];
   const uint2 w = reinterpret_cast<const uint2*>(dbuf + kDescItemsOff)[tid * 2u + 1u];
   R.c_begin = w.x;
   R.c_count = w.y;
@@ -228,20 +234,33 @@ __device__ __forceinline__ SlabRegs read_desc(const unsigned char* dbuf, uint32_
 // cp.async everything slab R needs into `stage` (+ its raw plate records into `rawp`): block
 // metadata, contribution entries, and each thread the record of "its" element — every record is
 // fetched once per slab, all requests in flight together
-__device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs& R, uint32_t stage_s,
-                                            uint32_t rawp_s, uint32_t tid) {
-  const uint32_t nb = R.blk_count();
-  for (uint32_t b = tid; b < nb; b += kAsmThreads) cp_async16(stage_s + b * 16u, A.meta + R.blk_begin() + b);
-  const uint32_t c0 = R.slab_c_begin(), first = c0 & ~3u, chunks = R.ent_bytes() >> 4;
-  const uint32_t ent_s = stage_s + R.ent_off();
-  if (R.slab_c_count())
-    for (uint32_t i = tid; i < chunks; i += kAsmThreads) cp_async16(ent_s + i * 16u, A.contrib + first + i * 4u);
+template <int kT>
+__device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>& R, uint32_t stage_s,
+                                            uint32_t rawp_s, uint32_t mbar_s, uint32_t tid) {
+  // block metadata and contribution entries are contiguous: two TMA bulk loads by one thread,
+  // completing on the same mbarrier as the cp.async record gathers
+  if (tid == 0 && R.blk_count()) {
+    const uint32_t meta_bytes = R.blk_count() * 16u, ent_bytes = R.slab_c_count() ? R.ent_bytes() : 0u;
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mbar_s),
+                 "r"(meta_bytes + ent_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_s),
+        "l"(A.meta + R.blk_begin()), "r"(meta_bytes), "r"(mbar_s)
+        : "memory");
+    if (ent_bytes)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              stage_s + R.ent_off()),
+          "l"(A.contrib + (R.slab_c_begin() & ~3u)), "r"(ent_bytes), "r"(mbar_s)
+          : "memory");
+  }
   const uint32_t nt = R.n_truss(), nbm = R.n_beam();
 #pragma unroll
-  for (int j = 0; j < kElistPerLane; ++j) {
+  for (int j = 0; j < SlabRegs<kT>::kElistPerLane; ++j) {
     const uint32_t fe = R.fe[j];
     if (fe == 0xFFFFFFFFu) continue;
-    const uint32_t slot = j * kAsmThreads + tid, family = fe >> 26, e = fe & 0x03FFFFFFu;
+    const uint32_t slot = j * kT + tid, family = fe >> 26, e = fe & 0x03FFFFFFu;
     if (family == FEMGPU_PLATE) {
       const uint32_t dst = rawp_s + (slot - nt - nbm) * 160u;
       const double* rec = A.plate_rec + size_t(e) * 16;
@@ -266,12 +285,13 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs& R,
 
 // phase A: one thread per plate (alternating between the two warps) turns the raw record into the
 // element's shared form (element_math.cuh). Returns whether every plate of the slab has Q == I.
-__device__ __forceinline__ bool phase_a(const SlabRegs& R, const double* __restrict__ rawp,
+template <int kT>
+__device__ __forceinline__ bool phase_a(const SlabRegs<kT>& R, const double* __restrict__ rawp,
                                         double* __restrict__ form, uint32_t tid) {
   bool flat = true;
   const uint32_t np = R.n_plate();
   // plates are dealt to the warps alternately so both carry the same share
-  for (uint32_t idx = (kAsmThreads == 64) ? ((tid & 31u) * 2u + (tid >> 5)) : tid; idx < np; idx += kAsmThreads) {
+  for (uint32_t idx = (kT == 64) ? ((tid & 31u) * 2u + (tid >> 5)) : tid; idx < np; idx += kT) {
     double raw[20];
     const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
 #pragma unroll
@@ -283,7 +303,7 @@ __device__ __forceinline__ bool phase_a(const SlabRegs& R, const double* __restr
     flat = flat && raw[15] != 0.0;
     plate_shared_record(raw, form + idx * uint32_t(kPlateSlotDoubles));
   }
-  return cta_all(flat);  // also: forms visible CTA-wide, raw plate records free again
+  return cta_all<kT>(flat);  // also: forms visible CTA-wide, raw plate records free again
 }
 
 // phase B: the thread runs its contribution entries. The loop is flat over contributions — a group
@@ -291,9 +311,10 @@ __device__ __forceinline__ bool phase_a(const SlabRegs& R, const double* __restr
 // contribution overwrite them (no zeroing) — so threads with one long group and threads with
 // several short ones stay converged on the expensive part. A chunk of a split block (deferred
 // round j >= 1) keeps its sum in registers and adds it to the image after the j-th barrier.
-__device__ __forceinline__ void phase_b(const SlabRegs& R, const unsigned char* __restrict__ stage,
+template <int kT>
+__device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned char* __restrict__ stage,
                                         const double* __restrict__ form, double* __restrict__ img,
-                                        bool all_flat) {
+                                        const PlatePair* __restrict__ pairs, bool all_flat) {
   const uint4* meta = reinterpret_cast<const uint4*>(stage);
   const uint32_t* ent = reinterpret_cast<const uint32_t*>(stage + R.ent_off()) + (R.slab_c_begin() & 3u);
   const double* truss = reinterpret_cast<const double*>(stage + R.truss_off());
@@ -312,7 +333,7 @@ __device__ __forceinline__ void phase_b(const SlabRegs& R, const unsigned char* 
       const uint32_t next = ent[i + 1];  // the entry area is padded by one
       const uint32_t family = code >> 30, pair = (code >> 26) & 15u, rec = (code & kEntRecMask) * 2u;
       if (family == FEMGPU_PLATE) {
-        plate_block_shared(form + rec, int(pair >> 2), int(pair & 3u), keep, all_flat, acc);
+        plate_block_shared(form + rec, pairs[pair], keep, all_flat, acc);
       } else {
 #pragma unroll
         for (int q = 0; q < 36; ++q) acc[q] *= keep;
@@ -343,12 +364,13 @@ __device__ __forceinline__ void phase_b(const SlabRegs& R, const unsigned char* 
   }
   const uint32_t rounds = R.rounds();
   for (uint32_t r = 1; r <= rounds; ++r) {
-    cta_sync();
+    cta_sync<kT>();
     if (pending == r) store_block<true>(img, pending_m, acc, true);
   }
 }
 
-__global__ void __maxnreg__(kAsmThreads == 64 ? 200 : 255)
+template <int kT>
+__global__ void __maxnreg__(kT == 64 ? 200 : 255)
 assemble_kernel(const AsmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tid = threadIdx.x, stride = gridDim.x;
@@ -361,16 +383,18 @@ assemble_kernel(const AsmArgs A) {
 
   uint32_t k = blockIdx.x;
   if (k >= A.n_slabs) return;
-  const uint32_t mbar_s = dbuf0_s + 3 * kDescBytes;
-  if (tid == 0) mbar_init(mbar_s, kAsmThreads);
-  cta_sync();
+  const uint32_t mbar_s = dbuf0_s + 3 * desc_bytes<kT>();
+  PlatePair* pairs = reinterpret_cast<PlatePair*>(dbuf0 + 3 * desc_bytes<kT>() + 16);
+  if (tid == 0) mbar_init(mbar_s, kT);
+  if (tid < 16) pairs[tid] = make_plate_pair(int(tid >> 2), int(tid & 3u));
+  cta_sync<kT>();
   // prologue: descriptor of the first slab, then its stage and the descriptor of the second
-  issue_desc(A, k, dbuf0_s, tid);
+  issue_desc<kT>(A, k, dbuf0_s, tid);
   cp_async_arrive(mbar_s);
   mbar_wait(mbar_s, 0);
-  SlabRegs cur = read_desc(dbuf0, tid);
-  issue_stage(A, cur, stage0_s, rawp_s, tid);
-  if (k + stride < A.n_slabs) issue_desc(A, k + stride, dbuf0_s + kDescBytes, tid);
+  SlabRegs<kT> cur = read_desc<kT>(dbuf0, tid);
+  issue_stage<kT>(A, cur, stage0_s, rawp_s, mbar_s, tid);
+  if (k + stride < A.n_slabs) issue_desc<kT>(A, k + stride, dbuf0_s + desc_bytes<kT>(), tid);
   cp_async_arrive(mbar_s);
 
   uint32_t d_cur = 0;  // descriptor block of `cur`
@@ -382,18 +406,18 @@ assemble_kernel(const AsmArgs A) {
     // slab `cur`: its records, metadata and entries (and the next slab's descriptor) were
     // requested one iteration ago (batch it + 1 of the mbarrier)
     mbar_wait(mbar_s, (it + 1u) & 1u);
-    cta_sync();
-    const bool all_flat = phase_a(cur, rawp, form, tid);
+    cta_sync<kT>();
+    const bool all_flat = phase_a<kT>(cur, rawp, form, tid);
     if (has_next) {
-      const SlabRegs nxt = read_desc(dbuf0 + d_nxt * kDescBytes, tid);
-      issue_stage(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, tid);
-      if (k + 2 * stride < A.n_slabs) issue_desc(A, k + 2 * stride, dbuf0_s + d_nn * kDescBytes, tid);
+      const SlabRegs<kT> nxt = read_desc<kT>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
+      issue_stage<kT>(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, mbar_s, tid);
+      if (k + 2 * stride < A.n_slabs) issue_desc<kT>(A, k + 2 * stride, dbuf0_s + d_nn * desc_bytes<kT>(), tid);
       cp_async_arrive(mbar_s);
     }
     // the image is free once the TMA engine has read the previous slab out of it
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    cta_sync();
-    phase_b(cur, stage, form, img, all_flat);
+    cta_sync<kT>();
+    phase_b<kT>(cur, stage, form, img, pairs, all_flat);
 
     const uint32_t n = cur.val_count();
     if (n) {
@@ -401,7 +425,7 @@ assemble_kernel(const AsmArgs A) {
       if (((uint32_t(cur.val_base()) | n) & 1u) == 0) {
         // 16-byte aligned slab: generic-proxy writes -> async proxy, then one TMA bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        cta_sync();
+        cta_sync<kT>();
         if (tid == 0) {
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out),
                        "r"(smem_u32(img)), "r"(n * 8u)
@@ -409,7 +433,7 @@ assemble_kernel(const AsmArgs A) {
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       } else {
-        cta_sync();
+        cta_sync<kT>();
         // ragged slab (3-wide truss blocks): coalesced 16-byte stores on the aligned body
         const uint32_t odd = uint32_t(cur.val_base() & 1);  // values[] is 16-byte aligned at index 0
         if (odd && tid == 0) out[0] = img[0];
@@ -417,10 +441,10 @@ assemble_kernel(const AsmArgs A) {
         if (odd == 0) {
           const double2* src = reinterpret_cast<const double2*>(img);
           double2* dst = reinterpret_cast<double2*>(out);
-          for (uint32_t i = tid; i < body; i += kAsmThreads) dst[i] = src[i];
+          for (uint32_t i = tid; i < body; i += kT) dst[i] = src[i];
         } else {
           double2* dst = reinterpret_cast<double2*>(out + 1);
-          for (uint32_t i = tid; i < body; i += kAsmThreads)
+          for (uint32_t i = tid; i < body; i += kT)
             dst[i] = make_double2(img[1 + 2 * i], img[2 + 2 * i]);
         }
         if (((n - odd) & 1u) && tid == 0) out[n - 1] = img[n - 1];
@@ -429,7 +453,7 @@ assemble_kernel(const AsmArgs A) {
     if (!has_next) break;
     k += stride;
     d_cur = d_nxt;
-    cur = read_desc(dbuf0 + d_cur * kDescBytes, tid);
+    cur = read_desc<kT>(dbuf0 + d_cur * desc_bytes<kT>(), tid);
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -443,7 +467,8 @@ __device__ __forceinline__ void add_contribution_raw(const double* __restrict__ 
   if (family == FEMGPU_PLATE) {
     double S[kPlateSharedDoubles];
     plate_shared_record(raw, S);
-    plate_block_shared(S, int(pair >> 2), int(pair & 3u), 1.0, raw[15] != 0.0, acc);
+    const PlatePair pt = make_plate_pair(int(pair >> 2), int(pair & 3u));
+    plate_block_shared(S, pt, 1.0, raw[15] != 0.0, acc);
   } else if (family == FEMGPU_BEAM) {
     beam_block(raw, int(pair >> 1), int(pair & 1u), acc);
   } else if (family == FEMGPU_TRUSS) {
@@ -451,9 +476,9 @@ __device__ __forceinline__ void add_contribution_raw(const double* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(kAsmThreads)
+__global__ void __launch_bounds__(kAsmThreadsMax)
 assemble_unstaged_kernel(const AsmArgs A) {
-  const uint32_t k = blockIdx.x, lane = threadIdx.x;
+  const uint32_t k = blockIdx.x, lane = threadIdx.x, kAsmThreads = blockDim.x;
   const SlabDesc d = A.slabs[k];
   if (!(d.flags & 1u) || d.blk_count == 0) return;
   const WorkItem w = A.items[size_t(k) * kAsmThreads + lane];
@@ -536,26 +561,32 @@ int32_t run_assembly(Handle* h) {
   A.smem_form = up(h->smem_form);
   A.smem_rawp = up(h->smem_rawp);
   A.smem_stage = up(h->smem_stage);
-  const uint32_t smem = A.smem_img + A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * kDescBytes + 16;
+  const int threads = h->asm_threads;
+  const uint32_t desc = threads == 64 ? desc_bytes<64>() : desc_bytes<32>();
+  const uint32_t smem = A.smem_img + A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * desc + 16 +
+                        16 * uint32_t(sizeof(PlatePair));
   if (h->n_unstaged < h->n_slabs) {
-    if (h->asm_smem_set != smem) {
-      FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                int(smem)));
+    const void* fn = threads == 64 ? reinterpret_cast<const void*>(assemble_kernel<64>)
+                                   : reinterpret_cast<const void*>(assemble_kernel<32>);
+    const uint32_t config = smem | (uint32_t(threads) << 24);
+    if (h->asm_smem_set != config) {
+      FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       int per_sm = 0;
-      FEMGPU_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel, kAsmThreads, smem));
+      FEMGPU_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
       if (per_sm < 1) return h->fail(FEMGPU_ERR_CUDA, "assemble_kernel does not fit on an SM");
       if (h->sm_count == 0)
         FEMGPU_CUDA_CHECK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
-      h->asm_smem_set = smem;
+      h->asm_smem_set = config;
       h->asm_ctas_per_sm = per_sm;
     }
     const uint32_t grid = uint32_t(std::min<uint64_t>(h->n_slabs, uint64_t(h->sm_count) * h->asm_ctas_per_sm));
-    assemble_kernel<<<grid, kAsmThreads, smem, h->stream>>>(A);
+    if (threads == 64) assemble_kernel<64><<<grid, 64, smem, h->stream>>>(A);
+    else assemble_kernel<32><<<grid, 32, smem, h->stream>>>(A);
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   }
   if (h->n_unstaged) {
-    assemble_unstaged_kernel<<<h->n_slabs, kAsmThreads, 0, h->stream>>>(A);
+    assemble_unstaged_kernel<<<h->n_slabs, threads, 0, h->stream>>>(A);
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   }

@@ -93,7 +93,7 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
   load_xyz(x, y, z, n2[e], p2);
   load_xyz(x, y, z, n3[e], p3);
   load_xyz(x, y, z, n4[e], p4);
-  int code = plate_record(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m);
+  int code = plate_record<kWriteErr>(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m);
   if (code) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = 0.0;

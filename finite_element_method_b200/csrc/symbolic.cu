@@ -227,6 +227,7 @@ __global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restri
 // share) is split into up to kMaxChunks chunks of consecutive contributions (execution order), one
 // thread each: chunk 0 stores its partial sum, chunk j >= 1 adds its own after the j-th barrier
 // ("deferred round"). W starts at total / threads and is raised until the slab fits.
+// Only blocks at least 25 % heavier than W are split (a split costs a deferred read-modify-write).
 // One thread per slab; items are written to the dense [slab][thread] table.
 __device__ __forceinline__ uint32_t family_cost(uint32_t f) {
   return (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
@@ -265,7 +266,7 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
     bool open = false, ok = true;
     for (uint32_t b = b0; b < b1; ++b) {
       const uint32_t c = cost[b], cnt = cptr_ord[b + 1] - cptr_ord[b];
-      if (staged && c > W && cnt > 1) {
+      if (staged && 4 * uint64_t(c) > 5 * W && cnt > 1) {
         const uint64_t kk = min(uint64_t(cnt), (c + W - 1) / W);
         if (kk > uint64_t(kMaxChunks)) ok = false;
         n += uint32_t(kk);
@@ -300,7 +301,7 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
   };
   for (uint32_t b = b0; b < b1; ++b) {
     const uint32_t c = cost[b], c0 = cptr_ord[b], cnt = cptr_ord[b + 1] - c0;
-    if (staged && c > W && cnt > 1) {
+    if (staged && 4 * uint64_t(c) > 5 * W && cnt > 1) {
       close_run(b);
       const uint32_t kk = uint32_t(min(uint64_t(cnt), (c + W - 1) / W));
       uint32_t nf[4] = {0, 0, 0, 0};  // placeholders, plates, beams, trusses
@@ -459,11 +460,11 @@ __global__ void relabel_kernel(uint32_t n, const uint64_t* __restrict__ keys, co
 // order — family-major (placeholders, plates, beams, trusses) over the lane's blocks, insertion order
 // inside a (block, family) group — and attach the group-end / read-modify-write / deferred-round
 // flags and the block index. One thread per work item; entries stay inside the item's own range.
-__global__ void item_program_kernel(uint32_t n_slabs, const SlabDesc* __restrict__ slabs,
+__global__ void item_program_kernel(uint32_t n_slabs, uint32_t threads, const SlabDesc* __restrict__ slabs,
                                     const WorkItem* __restrict__ items, const uint32_t* __restrict__ cptr_ord,
                                     const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
   uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  uint32_t k = uint32_t(t / kAsmThreads);
+  uint32_t k = uint32_t(t / threads);
   if (k >= n_slabs) return;
   const WorkItem w = items[t];
   const uint32_t n_blk = w.blk_count & 0xFFFFu;
@@ -475,9 +476,10 @@ __global__ void item_program_kernel(uint32_t n_slabs, const SlabDesc* __restrict
   }
   uint32_t out = w.c_begin;
   const uint32_t order[4] = {3u, uint32_t(FEMGPU_PLATE), uint32_t(FEMGPU_BEAM), uint32_t(FEMGPU_TRUSS)};
-  if (w.blk_count & (1u << 24)) {
-    // one chunk of a split block: contributions [skip, skip + take) of the block's execution order,
-    // accumulated as a single group
+  if ((w.blk_count & (1u << 24)) || n_blk == 1) {
+    // one chunk of a split block — or a whole block that is the item's only one: contributions
+    // [skip, skip + take) of the block's execution order, accumulated as a single group (no flush
+    // between the families)
     const uint32_t p = w.blk_begin, c0 = cptr_ord[p], c1 = cptr_ord[p + 1];
     const uint32_t skip = w.c_begin - c0, take = w.c_count, round = (w.blk_count >> 16) & 3u;
     const uint32_t blk = p - d.blk_begin;
@@ -1035,8 +1037,16 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cudaStreamSynchronize(s));
   }
   // balanced per-thread work lists (needs blk_cptr, filled above)
-  SYM_CHECK(h->items.reserve(size_t(n_slabs) * kAsmThreads));
-  work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, kAsmThreads, h->slabs.p, ocost.as<uint32_t>(),
+  {
+    // lanes per slab: two warps for beam and mixed-family meshes, one for plate-only / truss-only
+    const bool has_t = h->fh[FEMGPU_TRUSS].size() != 0, has_b = h->fh[FEMGPU_BEAM].size() != 0,
+               has_p = h->fh[FEMGPU_PLATE].size() != 0;
+    h->asm_threads = (has_b || (has_t && has_p)) ? 64 : 32;
+    if (const char* q = getenv("FEMGPU_ASM_THREADS")) h->asm_threads = (atoi(q) == 64) ? 64 : 32;  // tuning knob
+  }
+  const uint32_t threads = uint32_t(h->asm_threads);
+  SYM_CHECK(h->items.reserve(size_t(n_slabs) * threads));
+  work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, threads, h->slabs.p, ocost.as<uint32_t>(),
                                                          h->blk_cptr.p, h->contrib.p, h->items.p);
   h->launches++;
   SYM_CHECK(cudaGetLastError());
@@ -1044,8 +1054,8 @@ int32_t run_symbolic(Handle* h) {
   {
     Tmp prog;
     SYM_CHECK(prog.alloc((size_t(NCt) + 1) * 4));
-    item_program_kernel<<<div_up(uint64_t(n_slabs) * kAsmThreads, 256), 256, 0, s>>>(
-        n_slabs, h->slabs.p, h->items.p, h->blk_cptr.p, h->contrib.p, prog.as<uint32_t>());
+    item_program_kernel<<<div_up(uint64_t(n_slabs) * threads, 256), 256, 0, s>>>(
+        n_slabs, threads, h->slabs.p, h->items.p, h->blk_cptr.p, h->contrib.p, prog.as<uint32_t>());
     h->launches++;
     SYM_CHECK(cudaGetLastError());
     SYM_CHECK(cudaMemcpyAsync(h->contrib.p, prog.p, size_t(NCt) * 4, cudaMemcpyDeviceToDevice, s));
