@@ -110,32 +110,47 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+SAMPLE = {"M": (300, 200), "P": (300, 200), "B": (34, None), "T": (40, None)}   # bounded CPU samples
+
+
+def _cpu_sample(config: str):
+    from finite_element_method_b200 import meshes
+    nx, ny = SAMPLE[config]
+    mesh, _ = build_mesh(config, 1, nx, ny)
+    return mesh, meshes.n_elements(mesh)
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the crate itself is Rust and
-    cannot be built here) on all host cores, on a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU algorithm for this path. The crate is Rust (no
+    rustc/cargo in the image, un-vendored dependencies), so this times the oracle port: the faithful
+    restatement of FEM::add_plate / add_beam / add_truss — dense R^T k R per element, accumulation into
+    a position-keyed map — which is single-threaded like the crate (FEM<V> has no parallelism at all,
+    so "all the host threads it can use" is one). Each step is one pass over a bounded sample of the
+    configured workload. The multi-core optimised CPU port (not the reference's algorithm) is
+    reported next to it for context."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from finite_element_method_b200 import meshes
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
-    nx, ny = {"M": (500, 400), "P": (500, 400), "B": (40, None), "T": (50, None)}[args.config]
-    mesh, _ = build_mesh(args.config, 1, nx, ny)
-    n_el = meshes.n_elements(mesh)
-    for _ in range(max(1, args.warmup) if args.warmup else 0):
-        O.fast_assemble(mesh, n_threads=cores, repeats=1)
-    t = []
-    for _ in range(args.steps):
-        t.append(O.fast_assemble(mesh, n_threads=cores, repeats=1)["seconds"])
+    mesh, n_el = _cpu_sample(args.config)
+    for _ in range(min(args.warmup, 1)):
+        O.faithful_time(mesh)
+    t = [O.faithful_time(mesh) for _ in range(args.steps)]
     sec = float(np.mean(t))
     val = n_el / sec
-    sample = f"{mesh['name']}: {n_el} elements per step (bounded sample of config {args.config}), oracle fast path, OpenMP"
+    cores = os.cpu_count() or 1
+    fast = O.fast_assemble(mesh, n_threads=cores, repeats=3)["seconds"]
+    sample = (f"{mesh['name']}: {n_el} elements per step (bounded sample of config {args.config}); faithful "
+              f"operation-by-operation port of the crate's add_* path, 1 thread (the crate is single-threaded), "
+              f"duplicate scans disabled")
     line = {
         "impl": "reference", "metric": "elements assembled/s (FP64)", "value": val, "unit": "elements/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": CONFIGS[args.config], "config": args.config, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample,
+                         "optimized_multicore_port": {"value": n_el / fast, "unit": "elements/s", "cores": cores,
+                                                      "note": "owner-computes OpenMP port, not the reference's algorithm"}},
         "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -143,22 +158,21 @@ def run_reference(args):
 
 
 def cpu_baseline(config: str):
-    """Bounded CPU sample (≈10-30 s): faithful single-thread restatement (the reference is
-    single-threaded) and the multi-core fast path, both on the same smaller mesh of the same shape."""
-    from finite_element_method_b200 import meshes
+    """Bounded CPU sample (about 10-30 s): the faithful single-thread port (the reference's algorithm; the crate
+    is single-threaded) is the baseline value; the multi-core optimised port is reported next to it."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    nx, ny = {"M": (300, 200), "P": (300, 200), "B": (40, None), "T": (50, None)}[config]
-    mesh, _ = build_mesh(config, 1, nx, ny)
-    n_el = meshes.n_elements(mesh)
-    t_faithful = O.faithful_time(mesh)
-    fast = O.fast_assemble(mesh, n_threads=cores, repeats=2)["seconds"]
+    mesh, n_el = _cpu_sample(config)
+    reps = 3 if config in ("M", "P") else 2
+    t_faithful = float(np.mean([O.faithful_time(mesh) for _ in range(reps)]))
+    fast = O.fast_assemble(mesh, n_threads=cores, repeats=3)["seconds"]
     return {
-        "value": n_el / fast, "unit": "elements/s", "cores": cores, "kind": "port",
-        "sample": f"{mesh['name']} ({n_el} elements, same shape as config {config}); oracle fast path on {cores} threads",
-        "faithful_single_thread": {"value": n_el / t_faithful, "unit": "elements/s", "cores": 1,
-                                   "seconds": t_faithful,
-                                   "note": "operation-by-operation restatement, hash-map global K, duplicate scans disabled"},
+        "value": n_el / t_faithful, "unit": "elements/s", "cores": 1, "kind": "port",
+        "sample": f"{mesh['name']} ({n_el} elements, same shape as config {config}), {reps} passes; faithful "
+                  f"operation-by-operation port of the crate's add_* path (dense R^T k R, position-keyed global K, "
+                  f"duplicate scans disabled), single thread like the crate",
+        "optimized_multicore_port": {"value": n_el / fast, "unit": "elements/s", "cores": cores,
+                                     "note": "owner-computes OpenMP port, not the reference's algorithm"},
     }
 
 
