@@ -626,41 +626,48 @@ __device__ __forceinline__ void plate_block(const double* __restrict__ rec,
 // ------------------------------------------------------------------------------------------
 constexpr int kPlateSharedDoubles = 64;
 
+// One Gauss point (r, s) of a plate with edge vectors e12, e43, e14, e23: writes n[node] = adj(J) dh
+// (8 doubles) and 1/det, returns the two shear weights gamma_rz^2 det and gamma_sz^2 det.
+__device__ __forceinline__ void plate_gauss_point(const double e[8], double r, double s,
+                                                  double* __restrict__ n_out, double* rdet_out,
+                                                  double* wr, double* ws) {
+  // J = [[x_r, y_r], [x_s, y_s]]                 quadrilateral_4n_element_functions.rs:252-446
+  const double x_r = 0.25 * (e[0] * (1.0 + s) + e[2] * (1.0 - s));
+  const double y_r = 0.25 * (e[1] * (1.0 + s) + e[3] * (1.0 - s));
+  const double x_s = 0.25 * (e[4] * (1.0 + r) + e[6] * (1.0 - r));
+  const double y_s = 0.25 * (e[5] * (1.0 + r) + e[7] * (1.0 - r));
+  const double det = x_r * y_s - y_r * x_s;
+  const double rdet = 1.0 / det;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double xa = (a == 0 || a == 3) ? 1.0 : -1.0, ea = (a < 2) ? 1.0 : -1.0;
+    // dh/dr, dh/ds                               quadrilateral_4n_element_functions.rs:505-583
+    const double dar = 0.25 * xa * (1.0 + ea * s), das = 0.25 * ea * (1.0 + xa * r);
+    // adj(J) * dh                                quadrilateral_4n_element_functions.rs:613-653
+    n_out[2 * a] = y_s * dar - y_r * das;
+    n_out[2 * a + 1] = x_r * das - x_s * dar;
+  }
+  *rdet_out = rdet;
+  const double q4 = 0.25 * rdet;
+  *wr = (x_s * x_s + y_s * y_s) * q4;  // gamma_rz^2 * det  (plate.rs:392-511)
+  *ws = (x_r * x_r + y_r * y_r) * q4;  // gamma_sz^2 * det
+}
+
 // raw = the prep kernel's record: Q[9], x1, y1, x2, y2, x4, y4, identity flag, Cm, Cb, Cs, nu
 __device__ __forceinline__ void plate_shared_record(const double* __restrict__ raw,
                                                     double* __restrict__ S) {
   const double x1 = raw[9], y1 = raw[10], x2 = raw[11], y2 = raw[12], x4 = raw[13], y4 = raw[14];
   const double Cm = raw[16], Cb = raw[17], Cs = raw[18], nu = raw[19];
   const double g = 0.57735027779281512;  // sqrt((double)(1.0f / 3.0f)), plate.rs:1066-1091
-  const double e12x = x1 - x2, e12y = y1 - y2;  // edge 1-2 (s = +1)
-  const double e43x = x4, e43y = y4;            // edge 4-3 (s = -1), x3 = y3 = 0
-  const double e14x = x1 - x4, e14y = y1 - y4;  // edge 1-4 (r = +1)
-  const double e23x = x2, e23y = y2;            // edge 2-3 (r = -1)
+  // edges 1-2 (s = +1), 4-3 (s = -1), 1-4 (r = +1), 2-3 (r = -1); x3 = y3 = 0
+  const double e[8] = {x1 - x2, y1 - y2, x4, y4, x1 - x4, y1 - y4, x2, y2};
   double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int ip = 0; ip < 4; ++ip) {
     const double r = (ip == 0 || ip == 3) ? g : -g;
     const double s = (ip < 2) ? g : -g;
-    // J = [[x_r, y_r], [x_s, y_s]]                 quadrilateral_4n_element_functions.rs:252-446
-    const double x_r = 0.25 * (e12x * (1.0 + s) + e43x * (1.0 - s));
-    const double y_r = 0.25 * (e12y * (1.0 + s) + e43y * (1.0 - s));
-    const double x_s = 0.25 * (e14x * (1.0 + r) + e23x * (1.0 - r));
-    const double y_s = 0.25 * (e14y * (1.0 + r) + e23y * (1.0 - r));
-    const double det = x_r * y_s - y_r * x_s;
-    const double rdet = 1.0 / det;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double xa = (a == 0 || a == 3) ? 1.0 : -1.0, ea = (a < 2) ? 1.0 : -1.0;
-      // dh/dr, dh/ds                               quadrilateral_4n_element_functions.rs:505-583
-      const double dar = 0.25 * xa * (1.0 + ea * s), das = 0.25 * ea * (1.0 + xa * r);
-      // adj(J) * dh                                quadrilateral_4n_element_functions.rs:613-653
-      S[(ip * 4 + a) * 2] = y_s * dar - y_r * das;
-      S[(ip * 4 + a) * 2 + 1] = x_r * das - x_s * dar;
-    }
-    S[32 + ip] = rdet;
-    const double q4 = 0.25 * rdet;
-    const double wr = (x_s * x_s + y_s * y_s) * q4;  // gamma_rz^2 * det  (plate.rs:392-511)
-    const double ws = (x_r * x_r + y_r * y_r) * q4;  // gamma_sz^2 * det
+    double wr, ws;
+    plate_gauss_point(e, r, s, S + ip * 8, S + 32 + ip, &wr, &ws);
     tr[0] += ((1.0 + s) * (1.0 + s)) * wr;
     tr[1] += ((1.0 - s) * (1.0 - s)) * wr;
     tr[2] += ((1.0 + s) * (1.0 - s)) * wr;
@@ -673,14 +680,57 @@ __device__ __forceinline__ void plate_shared_record(const double* __restrict__ r
     S[36 + i] = Cs * tr[i];
     S[39 + i] = Cs * ts[i];
   }
-  S[42] = 0.25 * e12x; S[43] = 0.25 * e12y;
-  S[44] = 0.25 * e43x; S[45] = 0.25 * e43y;
-  S[46] = 0.25 * e14x; S[47] = 0.25 * e14y;
-  S[48] = 0.25 * e23x; S[49] = 0.25 * e23y;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) S[42 + i] = 0.25 * e[i];
   S[50] = Cm; S[51] = Cb; S[52] = nu; S[53] = (1.0 - nu) * 0.5;
 #pragma unroll
   for (int i = 0; i < 9; ++i) S[54 + i] = raw[i];
   S[63] = raw[15];
+}
+
+// The same record built by TWO adjacent lanes (half = lane & 1): each takes two Gauss points
+// (half 0: s = +g, half 1: s = -g), the shear sums are combined with one shuffle exchange, and the
+// point-independent fields are shared out between the two. Must be called by both lanes of a pair.
+__device__ __forceinline__ void plate_shared_record_half(const double* __restrict__ raw,
+                                                         double* __restrict__ S, int half,
+                                                         uint32_t pair_mask) {
+  const double x1 = raw[9], y1 = raw[10], x2 = raw[11], y2 = raw[12], x4 = raw[13], y4 = raw[14];
+  const double g = 0.57735027779281512;
+  const double e[8] = {x1 - x2, y1 - y2, x4, y4, x1 - x4, y1 - y4, x2, y2};
+  const double s = half ? -g : g;
+  double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    // Gauss points 0:(+,+) 1:(-,+) | 2:(-,-) 3:(+,-)
+    const int ip = 2 * half + q;
+    const double r = ((q == 0) != (half != 0)) ? g : -g;
+    double wr, ws;
+    plate_gauss_point(e, r, s, S + ip * 8, S + 32 + ip, &wr, &ws);
+    tr[0] += ((1.0 + s) * (1.0 + s)) * wr;
+    tr[1] += ((1.0 - s) * (1.0 - s)) * wr;
+    tr[2] += ((1.0 + s) * (1.0 - s)) * wr;
+    ts[0] += ((1.0 + r) * (1.0 + r)) * ws;
+    ts[1] += ((1.0 - r) * (1.0 - r)) * ws;
+    ts[2] += ((1.0 + r) * (1.0 - r)) * ws;
+  }
+  // half 0 finishes the gamma_rz sums, half 1 the gamma_sz sums (fixed order: half 0 + half 1)
+  const double Cs = raw[18];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double mine = half ? ts[i] : tr[i], give = half ? tr[i] : ts[i];
+    const double got = __shfl_xor_sync(pair_mask, give, 1);
+    const double sum = half ? got + mine : mine + got;
+    S[(half ? 39 : 36) + i] = Cs * sum;
+  }
+  if (half == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[42 + i] = 0.25 * e[i];
+    S[50] = raw[16]; S[51] = raw[17]; S[52] = raw[19]; S[53] = (1.0 - raw[19]) * 0.5;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S[54 + i] = raw[i];
+    S[63] = raw[15];
+  }
 }
 
 // Everything plate_block_shared derives from the local node pair (la, lb) alone: where the two nodes'

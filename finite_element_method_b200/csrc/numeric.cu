@@ -290,18 +290,38 @@ __device__ __forceinline__ bool phase_a(const SlabRegs<kT>& R, const double* __r
                                         double* __restrict__ form, uint32_t tid) {
   bool flat = true;
   const uint32_t np = R.n_plate();
-  // plates are dealt to the warps alternately so both carry the same share
-  for (uint32_t idx = (kT == 64) ? ((tid & 31u) * 2u + (tid >> 5)) : tid; idx < np; idx += kT) {
-    double raw[20];
-    const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
+  if (kT == 64) {
+    // two adjacent lanes per plate, two Gauss points each: up to 32 plates in one pass
+    for (uint32_t idx = tid >> 1; idx < ((np + 31u) & ~31u); idx += kT / 2) {
+      const uint32_t pair_mask = __activemask();
+      if (idx < np) {
+        double raw[20];
+        const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const double2 v = src[i];
-      raw[2 * i] = v.x;
-      raw[2 * i + 1] = v.y;
+        for (int i = 0; i < 10; ++i) {
+          const double2 v = src[i];
+          raw[2 * i] = v.x;
+          raw[2 * i + 1] = v.y;
+        }
+        flat = flat && raw[15] != 0.0;
+        plate_shared_record_half(raw, form + idx * uint32_t(kPlateSlotDoubles), int(tid & 1u),
+                                 3u << (tid & 30u));
+      }
+      (void)pair_mask;
     }
-    flat = flat && raw[15] != 0.0;
-    plate_shared_record(raw, form + idx * uint32_t(kPlateSlotDoubles));
+  } else {
+    for (uint32_t idx = tid; idx < np; idx += kT) {
+      double raw[20];
+      const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const double2 v = src[i];
+        raw[2 * i] = v.x;
+        raw[2 * i + 1] = v.y;
+      }
+      flat = flat && raw[15] != 0.0;
+      plate_shared_record(raw, form + idx * uint32_t(kPlateSlotDoubles));
+    }
   }
   return cta_all<kT>(flat);  // also: forms visible CTA-wide, raw plate records free again
 }
@@ -405,8 +425,11 @@ assemble_kernel(const AsmArgs A) {
     const bool has_next = k + stride < A.n_slabs;
     // slab `cur`: its records, metadata and entries (and the next slab's descriptor) were
     // requested one iteration ago (batch it + 1 of the mbarrier)
+    // (each thread waits on the mbarrier itself; the previous slab's phase B ended with a CTA barrier)
     mbar_wait(mbar_s, (it + 1u) & 1u);
-    cta_sync<kT>();
+    // the image is free once the TMA engine has read the previous slab out of it; phase A's closing
+    // barrier publishes that to the CTA together with the forms
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     const bool all_flat = phase_a<kT>(cur, rawp, form, tid);
     if (has_next) {
       const SlabRegs<kT> nxt = read_desc<kT>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
@@ -414,9 +437,6 @@ assemble_kernel(const AsmArgs A) {
       if (k + 2 * stride < A.n_slabs) issue_desc<kT>(A, k + 2 * stride, dbuf0_s + d_nn * desc_bytes<kT>(), tid);
       cp_async_arrive(mbar_s);
     }
-    // the image is free once the TMA engine has read the previous slab out of it
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    cta_sync<kT>();
     phase_b<kT>(cur, stage, form, img, pairs, all_flat);
 
     const uint32_t n = cur.val_count();
