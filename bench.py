@@ -283,8 +283,14 @@ def main():
         ab = {"nnz": nnz_local, "total_bytes": 24 * nt + 96 * nb + 48 * npl + 24 * (end - begin) + 8 * nnz_local}
     peak, peak_src = measured_peaks()
     achieved = ab["total_bytes"] / (asm_ms * 1e-3) / 1e9
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.config, {}).get("dram_bytes_per_launch") if world == 1 and not (args.nx or args.ny) else None
+    except OSError:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "assemble_kernel", "kernel_ms": asm_ms, "prep_ms": prep_ms,
+                "traffic": traffic, "kernel": "assemble_kernel", "kernel_ms": asm_ms, "prep_ms": prep_ms,
                 "exchange_ms": xchg_ms, "algorithmic_bytes_per_launch": ab["total_bytes"], "peak_source": peak_src,
                 "whole_step_frac": ab["total_bytes"] / (ms_step * 1e-3) / 1e9 / peak}
 

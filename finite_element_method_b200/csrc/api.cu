@@ -8,6 +8,10 @@
 #include <cstdio>
 #include <cstring>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace femgpu;
@@ -697,12 +701,23 @@ int32_t femgpu_counts(const femgpu_t* h, uint64_t* nodes, uint64_t* truss, uint6
 int32_t femgpu_symbolic(femgpu_t* h, int64_t* n_rows, int64_t* nnz) {
   if (!h) return FEMGPU_ERR_USAGE;
   if (h->device < 0) return no_device(h);
+  const bool timing = getenv("FEMGPU_SYM_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(h->stream);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[femgpu symbolic] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+    t0 = now;
+  };
   int32_t st = validate_pending(h, nullptr, nullptr, nullptr);
   if (st) return st;
+  lap("upload + device validation");
   if (!h->symbolic_valid) {
     if ((st = upload_pending(h))) return st;
     if ((st = run_symbolic(h))) return st;
     h->symbolic_valid = true;
+    lap("run_symbolic total");
   }
   if (n_rows) *n_rows = h->n_rows;
   if (nnz) *nnz = h->nnz;

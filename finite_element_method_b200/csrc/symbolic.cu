@@ -13,6 +13,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -841,6 +843,16 @@ static int32_t dist_finalize_plan(Handle* h, const std::vector<int64_t>& ranges)
 int32_t run_symbolic(Handle* h) {
   SYM_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  const bool timing = getenv("FEMGPU_SYM_TIMING") != nullptr;  // per-stage wall clock to stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[femgpu symbolic] %-28s %8.2f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   const uint32_t N = h->nodes_number;
   h->n_rows = 6 * int64_t(N);
   const int64_t NC = h->n_contrib;
@@ -855,6 +867,7 @@ int32_t run_symbolic(Handle* h) {
   SYM_CHECK(h->d_flag.reserve(16));
   SYM_CHECK(cudaMemsetAsync(h->d_flag.p, 0, 64, s));
 
+  mark("reserve node arrays");
   BlockBuild bb;
   int64_t n_extra = 0;
   std::vector<int64_t> ranges;
@@ -888,6 +901,7 @@ int32_t run_symbolic(Handle* h) {
     int32_t st = build_blocks(h, n_extra, bb);
     if (st) return st;
   }
+  mark("sort + unique blocks");
   const uint32_t nblk = bb.nblk;
   Tmp& keys_a = bb.keys_a;
   Tmp& vals_a = bb.vals_a;
@@ -921,12 +935,14 @@ int32_t run_symbolic(Handle* h) {
 
   SYM_CHECK(h->col_idx.reserve(size_t(nnz)));
   SYM_CHECK(h->values.reserve(size_t(nnz)));
+  mark("node layout + alloc col_idx/values");
   row_ptr_kernel<<<div_up(size_t(N) + 1, 256), 256, 0, s>>>(N, h->node_base.p, h->node_len.p, h->row_ptr.p);
   col_idx_kernel<<<div_up(uint64_t(N) * 32, 256), 256, 0, s>>>(N, kb, h->blk_key.p, h->node_blk_ptr.p, h->blk_full.p,
                                                               h->blk_off.p, h->node_len.p, h->node_base.p,
                                                               h->col_idx.p);
   h->launches += 2;
 
+  mark("row layout, row_ptr, col_idx");
   // ---- 4. slabs and the in-slab thread order
   uint32_t quota = kSlabQuota;
   if (const char* q = getenv("FEMGPU_SLAB_QUOTA")) quota = std::max(1, atoi(q));  // tuning knob
@@ -986,6 +1002,7 @@ int32_t run_symbolic(Handle* h) {
   SYM_CHECK(cudaStreamSynchronize(s));
   SYM_CHECK(cudaMemsetAsync(h->contrib.p + NCt, 0, 32, s));
   SYM_CHECK(cudaMemsetAsync(h->blk_meta.p + nblk, 0, sizeof(BlockMeta), s));
+  mark("slabs, thread order, meta");
   // per-slab element lists; contrib codes are relabelled to slab-local element slots
   {
     if (uint64_t(n_slabs) >= (uint64_t(1) << 36)) return h->fail(FEMGPU_ERR_LIMIT, "too many slabs");
@@ -1036,6 +1053,7 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cudaGetLastError());
     SYM_CHECK(cudaStreamSynchronize(s));
   }
+  mark("element lists, relabel");
   // balanced per-thread work lists (needs blk_cptr, filled above)
   {
     // lanes per slab: two warps for beam and mixed-family meshes, one for plate-only / truss-only
@@ -1051,6 +1069,7 @@ int32_t run_symbolic(Handle* h) {
   h->launches++;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
+  mark("work items");
   {
     Tmp prog;
     SYM_CHECK(prog.alloc((size_t(NCt) + 1) * 4));
@@ -1061,6 +1080,7 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cudaMemcpyAsync(h->contrib.p, prog.p, size_t(NCt) * 4, cudaMemcpyDeviceToDevice, s));
     SYM_CHECK(cudaStreamSynchronize(s));
   }
+  mark("item programs");
   int32_t flags[16] = {0};
   SYM_CHECK(cudaMemcpy(flags, h->d_flag.p, 64, cudaMemcpyDeviceToHost));
   if (flags[0]) return h->fail(FEMGPU_ERR_LIMIT, "a slab holds 2^32 or more values");

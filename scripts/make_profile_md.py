@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Summarise an ncu report (gpurun_out/*.ncu-rep) into a markdown table under profiles/.
+usage: make_profile_md.py <report.ncu-rep> <out.md> "<title>" "<command>" """
+import csv, subprocess, sys, json, os
+rep, out, title, cmd = sys.argv[1:5]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_st.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
+lines = [f"# {title}", "", f"`{cmd}`", ""]
+summary = {}
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+    lines += [f"## {name}", "", "| metric | unit | value |", "|---|---|---|"]
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            lines.append(f"| {k} | {units[i]} | {r[i]} |")
+            summary.setdefault(name, {})[k] = (r[i], units[i])
+    lines.append("")
+open(out, "w").write("\n".join(lines) + "\n")
+print(json.dumps(summary, indent=1)[:3000])
