@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfemgpu.so")
+# FEMGPU_LIB selects another build of the same library (the profiling variant, `make prof`)
+LIB_PATH = os.environ.get("FEMGPU_LIB") or os.path.join(HERE, "libfemgpu.so")
 
 u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)

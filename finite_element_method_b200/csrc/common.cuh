@@ -349,7 +349,7 @@ constexpr int kSlabQuota = 72;             // node-pair blocks a slab aims for (
 // node with hundreds of neighbours) goes to the unstaged kernel
 constexpr int kCapImgBytes = 40 * 1024;    // slab image (CSR values of the slab)
 constexpr int kCapFormBytes = 24 * 1024;   // shared forms of the slab's plates
-constexpr int kCapStageBytes = 12 * 1024;  // block metadata + contribution entries + truss/beam records
+constexpr int kCapStageBytes = 20 * 1024;  // block metadata + contribution entries + truss/beam records
 constexpr int kCapBlocks = 2048;           // blocks per staged slab (11-bit index in the entries)
 // Record slots in the CTA's shared-memory record area, in doubles. Odd multiples of 16 bytes so that
 // lanes reading the same field of different elements spread over the banks.

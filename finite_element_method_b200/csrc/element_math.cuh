@@ -733,39 +733,32 @@ __device__ __forceinline__ void plate_shared_record_half(const double* __restric
   }
 }
 
-// Everything plate_block_shared derives from the local node pair (la, lb) alone: where the two nodes'
-// entries sit inside the shared record (byte offsets) and the natural-coordinate signs. The staged
-// kernel keeps the 16 possible entries in shared memory so a contribution costs five loads instead
-// of ~40 integer/select instructions.
-struct __align__(16) PlatePair {
-  uint32_t na, nb;      // n[0][la], n[0][lb]                       (stride between Gauss points: 64 B)
-  uint32_t era, esa;    // node a: its s-edge (1-2 or 4-3) for gamma_rz, its r-edge (1-4 or 2-3) for gamma_sz
-  uint32_t erb, esb;    // node b
-  uint32_t crz, csz;    // the (ea, eb) / (xa, xb) sign combination's shear sums
-  double xa, ea, xb, eb;  // +-0.5: half the natural coordinates of the two nodes
-  double drill;           // KROT6 on the diagonal (plate.rs:25)
-  double pad;
-};
+// Everything plate_block_shared derives from the local node pair (la, lb) alone, packed into 16 bytes:
+// where the two nodes' entries sit inside the shared record (byte offsets < 512) and the signs of
+// their natural coordinates. The staged kernel keeps the 16 possible entries in shared memory and
+// fetches the entry of the NEXT contribution one loop trip ahead, so a contribution starts with its
+// addresses in registers instead of a dependent chain of loads.
+//   x: n[0][la] | n[0][lb] << 16                              (stride between Gauss points: 64 B)
+//   y: node a's s-edge (1-2 or 4-3, for gamma_rz) | its r-edge (1-4 or 2-3, for gamma_sz) << 16
+//   z: the same two for node b
+//   w: shear sum of the (ea, eb) combination | of the (xa, xb) combination << 10
+//      | bits 27..31: diagonal pair (KROT6, plate.rs:25), xi_a < 0, eta_a < 0, xi_b < 0, eta_b < 0
+typedef uint4 PlatePair;
 __host__ __device__ inline PlatePair make_plate_pair(int la, int lb) {
   // natural-coordinate signs of nodes 1..4: (+,+), (-,+), (-,-), (+,-)
-  const int an = (la ^ (la >> 1)) & 1, bn = (lb ^ (lb >> 1)) & 1;  // 1 when xi = -1
-  const int am = la >> 1, bm = lb >> 1;                            // 1 when eta = -1
+  const uint32_t an = (la ^ (la >> 1)) & 1, bn = (lb ^ (lb >> 1)) & 1;  // 1 when xi = -1
+  const uint32_t am = la >> 1, bm = lb >> 1;                            // 1 when eta = -1
   PlatePair t;
-  t.na = uint32_t(la) * 16u;
-  t.nb = uint32_t(lb) * 16u;
-  t.era = uint32_t(42 + 2 * am) * 8u;
-  t.esa = uint32_t(46 + 2 * an) * 8u;
-  t.erb = uint32_t(42 + 2 * bm) * 8u;
-  t.esb = uint32_t(46 + 2 * bn) * 8u;
-  t.crz = uint32_t(36 + ((am == bm) ? am : 2)) * 8u;
-  t.csz = uint32_t(39 + ((an == bn) ? an : 2)) * 8u;
-  t.xa = an ? -0.5 : 0.5;
-  t.ea = am ? -0.5 : 0.5;
-  t.xb = bn ? -0.5 : 0.5;
-  t.eb = bm ? -0.5 : 0.5;
-  t.drill = (la == lb) ? 1.0 : 0.0;
-  t.pad = 0.0;
+  t.x = uint32_t(la) * 16u | (uint32_t(lb) * 16u) << 16;
+  t.y = (42u + 2u * am) * 8u | ((46u + 2u * an) * 8u) << 16;
+  t.z = (42u + 2u * bm) * 8u | ((46u + 2u * bn) * 8u) << 16;
+  t.w = (36u + ((am == bm) ? am : 2u)) * 8u | ((39u + ((an == bn) ? an : 2u)) * 8u) << 10 |
+        (la == lb ? 1u << 27 : 0u) | an << 28 | am << 29 | bn << 30 | bm << 31;
   return t;
+}
+// +-0.5 with the sign taken from bit `bit` of w
+__device__ __forceinline__ double plate_half_sign(uint32_t w, int bit) {
+  return __hiloint2double(int(0x3FE00000u | ((w << (31 - bit)) & 0x80000000u)), 0);
 }
 
 // acc = keep * acc + block (la, lb) of (R^T k) R of the plate whose shared record is S; keep is 1
@@ -773,12 +766,12 @@ __host__ __device__ inline PlatePair make_plate_pair(int la, int lb) {
 // all_flat: every plate of the slab has Q == I exactly (flat plates in the global xy plane), then
 // (R^T k) R == k and only the 14 structural entries of the local block are touched — the other 22
 // accumulators are never written by a flat plate and must already be zero.
-__device__ __forceinline__ void plate_block_shared(const double* __restrict__ S, const PlatePair& pt,
+__device__ __forceinline__ void plate_block_shared(const double* __restrict__ S, const PlatePair pt,
                                                    double keep, bool all_flat, double acc[36]) {
-  const uint4 o0 = *reinterpret_cast<const uint4*>(&pt.na);
-  const uint4 o1 = *reinterpret_cast<const uint4*>(&pt.erb);
-  const double2 sa = *reinterpret_cast<const double2*>(&pt.xa);
-  const double2 sb = *reinterpret_cast<const double2*>(&pt.xb);
+  const uint4 o0 = make_uint4(pt.x & 0xFFFFu, pt.x >> 16, pt.y & 0xFFFFu, pt.y >> 16);
+  const uint4 o1 = make_uint4(pt.z & 0xFFFFu, pt.z >> 16, pt.w & 0x3FFu, (pt.w >> 10) & 0x3FFu);
+  const double2 sa = make_double2(plate_half_sign(pt.w, 28), plate_half_sign(pt.w, 29));
+  const double2 sb = make_double2(plate_half_sign(pt.w, 30), plate_half_sign(pt.w, 31));
   const char* Sb = reinterpret_cast<const char*>(S);
   const double2 rd01 = *reinterpret_cast<const double2*>(S + 32);
   const double2 rd23 = *reinterpret_cast<const double2*>(S + 34);
@@ -817,7 +810,7 @@ __device__ __forceinline__ void plate_block_shared(const double* __restrict__ S,
   for (int p = 0; p < 3; ++p)
 #pragma unroll
     for (int c = 0; c < 3; ++c) sh[3 * p + c] = arz[p] * brz[c] + asz[p] * bsz[c];
-  const double drill = pt.drill;
+  const double drill = (pt.w & (1u << 27)) ? 1.0 : 0.0;
   if (all_flat) {
     acc[0] = fma(acc[0], keep, m00);
     acc[1] = fma(acc[1], keep, m01);

@@ -44,6 +44,18 @@ struct AsmArgs {
   uint32_t smem_img, smem_form, smem_rawp, smem_stage;
 };
 
+// Per-phase cycle accounting of the staged kernel (profiling builds only: make prof). Warp leaders
+// accumulate clock() deltas per phase and add them to g_phase at the end of the kernel.
+#ifdef FEMGPU_PHASE_CLOCKS
+constexpr int kPhases = 12;
+__device__ unsigned long long g_phase[kPhases + 4];
+#define PHASE_DECL uint32_t ph_acc[kPhases] = {}; uint32_t ph_last = clock(); uint32_t ph_iters = 0, ph_work = 0, ph_slabs = 0;
+#define PHASE_MARK(i) { const uint32_t ph_now = clock(); ph_acc[i] += ph_now - ph_last; ph_last = ph_now; }
+#else
+#define PHASE_DECL
+#define PHASE_MARK(i)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -81,7 +93,7 @@ __device__ __forceinline__ const void* record_chunk(const AsmArgs& A, uint32_t f
   const uint32_t family = fe >> 26, e = fe & 0x03FFFFFFu;
   if (family == FEMGPU_PLATE) {
     if (chunk < 8) return A.plate_rec + size_t(e) * 16 + chunk * 2;
-    return A.plate_mat + size_t(e) * 4 + (chunk - 8) * 2;
+    return chunk < 10 ? A.plate_mat + size_t(e) * 4 + (chunk - 8) * 2 : nullptr;
   }
   if (family == FEMGPU_BEAM) return chunk < 8 ? A.beam_rec + size_t(e) * 16 + chunk * 2 : nullptr;
   if (family != FEMGPU_TRUSS) return nullptr;  // family 3: placeholder of a remote contribution
@@ -323,6 +335,9 @@ __device__ __forceinline__ bool phase_a(const SlabRegs<kT>& R, const double* __r
       plate_shared_record(raw, form + idx * uint32_t(kPlateSlotDoubles));
     }
   }
+  // two-warp shape: the image is free once the TMA engine has read the previous slab out of it; the
+  // closing barrier publishes that to the CTA together with the forms
+  if (kT == 64 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   return cta_all<kT>(flat);  // also: forms visible CTA-wide, raw plate records free again
 }
 
@@ -334,7 +349,11 @@ __device__ __forceinline__ bool phase_a(const SlabRegs<kT>& R, const double* __r
 template <int kT>
 __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned char* __restrict__ stage,
                                         const double* __restrict__ form, double* __restrict__ img,
-                                        const PlatePair* __restrict__ pairs, bool all_flat) {
+                                        const PlatePair* __restrict__ pairs, bool all_flat
+#ifdef FEMGPU_PHASE_CLOCKS
+                                        , uint32_t* ph_acc, uint32_t& ph_last, uint32_t& ph_iters, uint32_t& ph_work
+#endif
+                                        ) {
   const uint4* meta = reinterpret_cast<const uint4*>(stage);
   const uint32_t* ent = reinterpret_cast<const uint32_t*>(stage + R.ent_off()) + (R.slab_c_begin() & 3u);
   const double* truss = reinterpret_cast<const double*>(stage + R.truss_off());
@@ -349,11 +368,16 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
   uint4 pending_m = make_uint4(0u, 0u, 0u, 0u);
   if (i < end) {
     uint32_t code = ent[i];
+    PlatePair pt = pairs[(code >> 26) & 15u];
     for (; i < end; ++i) {
       const uint32_t next = ent[i + 1];  // the entry area is padded by one
+      // the next contribution's pair entry and this one's block metadata are requested now, a whole
+      // contribution before they are needed
+      const PlatePair pt_next = pairs[(next >> 26) & 15u];
+      const uint4 m = meta[(code >> kEntBlkShift) & kEntBlkMask];
       const uint32_t family = code >> 30, pair = (code >> 26) & 15u, rec = (code & kEntRecMask) * 2u;
       if (family == FEMGPU_PLATE) {
-        plate_block_shared(form + rec, pairs[pair], keep, all_flat, acc);
+        plate_block_shared(form + rec, pt, keep, all_flat, acc);
       } else {
 #pragma unroll
         for (int q = 0; q < 36; ++q) acc[q] *= keep;
@@ -367,7 +391,6 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
       }
       keep = 1.0;
       if (code & kEntEnd) {
-        const uint4 m = meta[(code >> kEntBlkShift) & kEntBlkMask];
         const uint32_t defer = (code >> kEntDeferShift) & kEntDeferMask;
         if (defer) {  // always the thread's last entry
           pending = defer;
@@ -380,8 +403,14 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
         keep = 0.0;
       }
       code = next;
+      pt = pt_next;
     }
   }
+#ifdef FEMGPU_PHASE_CLOCKS
+  ph_iters += __reduce_max_sync(0xFFFFFFFFu, R.c_count);
+  ph_work += __reduce_add_sync(0xFFFFFFFFu, R.c_count);
+#endif
+  PHASE_MARK(5)
   const uint32_t rounds = R.rounds();
   for (uint32_t r = 1; r <= rounds; ++r) {
     cta_sync<kT>();
@@ -417,8 +446,10 @@ assemble_kernel(const AsmArgs A) {
   if (k + stride < A.n_slabs) issue_desc<kT>(A, k + stride, dbuf0_s + desc_bytes<kT>(), tid);
   cp_async_arrive(mbar_s);
 
+  PHASE_DECL
   uint32_t d_cur = 0;  // descriptor block of `cur`
   for (uint32_t it = 0;; ++it) {
+    PHASE_MARK(0)
     const uint32_t buf = it & 1u;
     const unsigned char* stage = stage0 + buf * A.smem_stage;
     const uint32_t d_nxt = (d_cur == 2u) ? 0u : d_cur + 1u, d_nn = (d_nxt == 2u) ? 0u : d_nxt + 1u;
@@ -427,17 +458,30 @@ assemble_kernel(const AsmArgs A) {
     // requested one iteration ago (batch it + 1 of the mbarrier)
     // (each thread waits on the mbarrier itself; the previous slab's phase B ended with a CTA barrier)
     mbar_wait(mbar_s, (it + 1u) & 1u);
-    // the image is free once the TMA engine has read the previous slab out of it; phase A's closing
-    // barrier publishes that to the CTA together with the forms
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    PHASE_MARK(1)
+    PHASE_MARK(2)
     const bool all_flat = phase_a<kT>(cur, rawp, form, tid);
+    PHASE_MARK(3)
     if (has_next) {
       const SlabRegs<kT> nxt = read_desc<kT>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
       issue_stage<kT>(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, mbar_s, tid);
       if (k + 2 * stride < A.n_slabs) issue_desc<kT>(A, k + 2 * stride, dbuf0_s + d_nn * desc_bytes<kT>(), tid);
       cp_async_arrive(mbar_s);
     }
+    // one-warp shape: wait for the previous slab's bulk store to have left the image as late as
+    // possible — phase A and the staging above do not touch it
+    if (kT == 32) {
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+    PHASE_MARK(4)
+#ifdef FEMGPU_PHASE_CLOCKS
+    phase_b<kT>(cur, stage, form, img, pairs, all_flat, ph_acc, ph_last, ph_iters, ph_work);
+    ++ph_slabs;
+#else
     phase_b<kT>(cur, stage, form, img, pairs, all_flat);
+#endif
+    PHASE_MARK(6)
 
     const uint32_t n = cur.val_count();
     if (n) {
@@ -470,17 +514,29 @@ assemble_kernel(const AsmArgs A) {
         if (((n - odd) & 1u) && tid == 0) out[n - 1] = img[n - 1];
       }
     }
+    PHASE_MARK(7)
     if (!has_next) break;
     k += stride;
     d_cur = d_nxt;
     cur = read_desc<kT>(dbuf0 + d_cur * desc_bytes<kT>(), tid);
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef FEMGPU_PHASE_CLOCKS
+  PHASE_MARK(8)
+  if ((tid & 31u) == 0) {
+    for (int i = 0; i < kPhases; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph_acc[i]);
+    atomicAdd(&g_phase[kPhases], (unsigned long long)ph_iters);
+    atomicAdd(&g_phase[kPhases + 1], (unsigned long long)ph_work);
+    atomicAdd(&g_phase[kPhases + 2], (unsigned long long)ph_slabs);
+    atomicAdd(&g_phase[kPhases + 3], 1ull);
+  }
+#endif
 }
 
 // ---- unstaged kernel: slabs too large for shared memory (a node with hundreds of neighbours) ------
 // One warp per oversized slab; records come from global memory per contribution, blocks go straight
 // to the CSR values. Entries are block-major: family<<30 | pair<<26 | slot in the slab's element list.
+constexpr int kRawDoubles = 20;
 __device__ __forceinline__ void add_contribution_raw(const double* __restrict__ raw, uint32_t code,
                                                      double acc[36]) {
   const uint32_t family = code >> 30, pair = (code >> 26) & 15u;
@@ -515,9 +571,9 @@ assemble_unstaged_kernel(const AsmArgs A) {
       const uint32_t code = __ldg(A.contrib + c);
       if ((code >> 30) == 3u) continue;  // remote placeholder
       const uint32_t fe = __ldg(A.elist_compact + d.el_begin + (code & 0x03FFFFFFu));
-      double raw[20];
+      double raw[kRawDoubles];
 #pragma unroll
-      for (uint32_t ch = 0; ch < 10; ++ch) {
+      for (uint32_t ch = 0; ch < uint32_t(kRawDoubles / 2); ++ch) {
         const double2* src = reinterpret_cast<const double2*>(record_chunk(A, fe, ch));
         const double2 v = src ? __ldg(src) : make_double2(0.0, 0.0);
         raw[2 * ch] = v.x;
@@ -529,6 +585,7 @@ assemble_unstaged_kernel(const AsmArgs A) {
   }
 }
 
+// (kRawDoubles: the largest per-element record read from global memory: plate 16 + 4)
 // test hook: the whole transformed element matrix of one element, built from the same block
 // evaluators the assembly uses
 __global__ void element_matrix_kernel(int family, uint32_t e, const double4* truss_rec,
@@ -545,8 +602,8 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
   A.beam_rec = beam_rec;
   A.plate_rec = plate_rec;
   A.plate_mat = plate_mat;
-  double rec[20];
-  for (uint32_t ch = 0; ch < 10; ++ch) {
+  double rec[kRawDoubles];
+  for (uint32_t ch = 0; ch < uint32_t(kRawDoubles / 2); ++ch) {
     const double* src = reinterpret_cast<const double*>(record_chunk(A, (uint32_t(family) << 26) | e, ch));
     rec[2 * ch] = src ? src[0] : 0.0;
     rec[2 * ch + 1] = src ? src[1] : 0.0;
@@ -604,6 +661,27 @@ int32_t run_assembly(Handle* h) {
     else assemble_kernel<32><<<grid, 32, smem, h->stream>>>(A);
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+#ifdef FEMGPU_PHASE_CLOCKS
+    if (getenv("FEMGPU_PHASE_DUMP")) {
+      unsigned long long ph[kPhases + 4];
+      FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+      FEMGPU_CUDA_CHECK(h, cudaMemcpyFromSymbol(ph, g_phase, sizeof ph));
+      unsigned long long zero[kPhases + 4] = {};
+      FEMGPU_CUDA_CHECK(h, cudaMemcpyToSymbol(g_phase, zero, sizeof zero));
+      const double ws = double(ph[kPhases + 2]);  // warp-slabs
+      static const char* names[kPhases] = {"loop top", "wait stage (mbarrier)", "wait image free", "phase A", "issue next stage",
+                                           "phase B loop", "deferred rounds", "store issue", "tail", "-", "-", "-"};
+      fprintf(stderr, "[femgpu phases] T=%d grid=%u warps=%llu slabs/warp=%.1f\n", threads, grid, ph[kPhases + 3],
+              ws / double(ph[kPhases + 3]));
+      double tot = 0;
+      for (int i = 0; i < 9; ++i) tot += double(ph[i]);
+      for (int i = 0; i < 9; ++i)
+        fprintf(stderr, "[femgpu phases] %-24s %9.1f cycles/slab  %5.1f %%\n", names[i], double(ph[i]) / ws, 100.0 * double(ph[i]) / tot);
+      fprintf(stderr, "[femgpu phases] total %.1f cycles/slab; phase-B trips/slab %.2f, lane work/slab %.2f, lane efficiency %.3f\n",
+              tot / ws, double(ph[kPhases]) / ws, double(ph[kPhases + 1]) / ws,
+              double(ph[kPhases + 1]) / (32.0 * double(ph[kPhases])));
+    }
+#endif
   }
   if (h->n_unstaged) {
     assemble_unstaged_kernel<<<h->n_slabs, threads, 0, h->stream>>>(A);

@@ -1,0 +1,24 @@
+# per-phase cycle accounting of assemble_kernel (profiling build) on M and P in both CTA shapes
+set -x
+mkdir -p gpurun_out
+TAG=${TAG:-r1s3b}
+export FEMGPU_LIB=$PWD/finite_element_method_b200/libfemgpu_prof.so
+for c in M P; do for t in 32 64; do
+FEMGPU_PHASE_DUMP=1 FEMGPU_ASM_THREADS=$t python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_phase_${c}$t.json 2> gpurun_out/${TAG}_phase_${c}$t.err
+grep "femgpu phases" gpurun_out/${TAG}_phase_${c}$t.err | tail -11
+done; done
+unset FEMGPU_LIB
+for c in M P; do for t in 32 64; do
+FEMGPU_ASM_THREADS=$t python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_${c}$t.json 2> gpurun_out/${TAG}_bench_${c}$t.err
+done; done
+python - <<'PY'
+import json,glob,os
+tag=os.environ.get('TAG','r1s3b')
+for f in sorted(glob.glob(f'gpurun_out/{tag}_bench_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        r=d['roofline']
+        print(f, 'Gelem/s=%.3f step_ms=%.3f asm_ms=%.3f prep_ms=%.3f frac=%.3f'%(d['value']/1e9,d['ms_per_step'],r['kernel_ms'],r['prep_ms'],r['frac']))
+    except Exception as e:
+        print(f,'ERR',e, open(f.replace('.json','.err')).read()[-2000:])
+PY
