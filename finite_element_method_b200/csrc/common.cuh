@@ -300,6 +300,15 @@ struct Handle {
     DevBuf<int64_t> i64;
   } dist_scratch;
 
+  // Pinned bounce buffers of the bulk host->device path (api.cu h2d_staged): the host staging vectors
+  // are pageable, so large uploads are copied chunk-wise into pinned memory by several host threads
+  // while the previous chunk is on its way over PCIe.
+  static constexpr size_t kPinChunk = size_t(16) << 20;
+  void* pin_buf[2] = {nullptr, nullptr};
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  bool pin_busy[2] = {false, false};
+  int pin_next = 0;
+
   Handle() {
     auto tie = [&](auto& b) { b.tally = &dev_bytes; };
     tie(d_x); tie(d_y); tie(d_z);

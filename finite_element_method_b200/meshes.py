@@ -142,10 +142,12 @@ def _plate_conn(nx, ny, j0=0, j1=None):
     return np.stack([n3 + 1 + w, n3 + w, n3, n3 + 1]).astype(np.uint32)
 
 
-def plate_grid(nx=2000, ny=2000, variant="flat", dx=1.0, dy=0.75):
+def plate_grid(nx=2000, ny=2000, variant="flat", dx=1.0, dy=0.75, rows=None):
     """Config 4 (P): (nx+1)x(ny+1) nodes at (i*dx, j*dy, 0); E=2.1e11, nu=0.3, t=0.01(1+u), ks=5/6
     (seed 20240605). variant: "flat" | "jitter" (in-plane U(-0.1,0.1)*h, seed 20240606) |
-    "x0" (the same mesh in the x=0 plane, Q != I)."""
+    "x0" (the same mesh in the x=0 plane, Q != I).
+    rows=(j0, j1): all nodes, but only the elements of grid rows j0 <= j < j1 — what one rank of a
+    row-strip partition owns (identical to local_part() of the whole mesh, without building it)."""
     w, h = nx + 1, ny + 1
     j, i = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
     x = (i.ravel() * dx).astype(np.float64); y = (j.ravel() * dy).astype(np.float64); z = np.zeros(w * h)
@@ -156,33 +158,36 @@ def plate_grid(nx=2000, ny=2000, variant="flat", dx=1.0, dy=0.75):
         x, y, z = np.zeros(w * h), x, y  # plane x = 0: (0, i*dx, j*dy); normal is +x
     m = _empty(w * h)
     m["x"], m["y"], m["z"] = x, y, z
-    m["p_n"] = _plate_conn(nx, ny)
-    ne = nx * ny
-    u = np.random.default_rng(20240605).random(ne)
+    j0, j1 = (0, ny) if rows is None else (max(0, rows[0]), min(ny, rows[1]))
+    m["p_n"] = _plate_conn(nx, ny, j0, j1)
+    u = np.random.default_rng(20240605).random(nx * ny)[j0 * nx:j1 * nx]
+    ne = len(u)
     m["p_props"] = np.stack([np.full(ne, 2.1e11), np.full(ne, 0.3), 0.01 * (1 + u), np.full(ne, 5.0 / 6.0)])
     m["name"] = f"plate-grid-{nx}x{ny}-{variant}"
     return m
 
 
-def mixed_structure(nx=2000, ny=2000):
+def mixed_structure(nx=2000, ny=2000, rows=None):
     """Config 5 (M): the P node set; nx*ny plates; beams on every +x grid edge of rows j=0..ny-1
     (props as B, axis1=(0,0,1)); trusses on +y grid edges of even columns i=0,2,..,nx-2 (props as T).
-    2000x2000 -> 4M plates + 4M beams + 2M trusses = 10M elements."""
-    m = plate_grid(nx, ny, "flat")
+    2000x2000 -> 4M plates + 4M beams + 2M trusses = 10M elements. rows: see plate_grid."""
+    m = plate_grid(nx, ny, "flat", rows=rows)
     w = nx + 1
-    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    j0, j1 = (0, ny) if rows is None else (max(0, rows[0]), min(ny, rows[1]))
+    jj, ii = np.meshgrid(np.arange(j0, j1), np.arange(nx), indexing="ij")
     a = (ii + w * jj).ravel().astype(np.uint32)
     nb = len(a)
-    u = np.random.default_rng(20240603).random(nb)
+    u = np.random.default_rng(20240603).random(nx * ny)[j0 * nx:j1 * nx]
     m["b_n1"], m["b_n2"] = a, a + 1
     m["b_props"] = np.stack([np.full(nb, 2.1e11), np.full(nb, 0.3), 1e-2 * (1 + u), 8e-6 * (1 + u),
                              4e-6 * (1 + u), np.zeros(nb), np.full(nb, 1e-5), np.full(nb, 5.0 / 6.0)])
     ax = np.zeros((3, nb)); ax[2] = 1.0
     m["b_axis"] = ax
-    jj, ii = np.meshgrid(np.arange(ny), np.arange(0, nx, 2), indexing="ij")
+    jj, ii = np.meshgrid(np.arange(j0, j1), np.arange(0, nx, 2), indexing="ij")
     t = (ii + w * jj).ravel().astype(np.uint32)
     nt = len(t)
-    ut = np.random.default_rng(20240601).random(nt)
+    ncol = len(range(0, nx, 2))
+    ut = np.random.default_rng(20240601).random(ncol * ny)[j0 * ncol:j1 * ncol]
     m["t_n1"], m["t_n2"] = t, (t + w).astype(np.uint32)
     m["t_E"] = np.full(nt, 2.1e11); m["t_A"] = 1e-4 * (1 + ut)
     m["name"] = f"mixed-{nx}x{ny}"

@@ -40,6 +40,12 @@ def main():
     fem.numeric(); fem.synchronize()
     assert np.array_equal(v1, fem.csr(values_only=True)), "dist re-assembly is not bit-identical"
     sent, recv = fem.dist_last_exchange_bytes()
+    # FEM::reset keeps the communicator: the same handle assembles the model again from scratch
+    fem.reset(n)
+    fem.dist_set_ownership(begin, end)
+    fem.load_mesh(part)
+    assert fem.assemble() == (n_rows, nnz)
+    assert np.array_equal(v1, fem.csr(values_only=True)), "assembly after reset differs"
 
     ref = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=local)
     ref.load_mesh(mesh)

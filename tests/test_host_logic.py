@@ -151,3 +151,22 @@ def test_degenerate_plate_uses_subset_rule():
     # plate.rs:1114-1118: every node of the new element belongs to plate 1 -> "same nodes"
     raises(11, "Plate element with nodes numbers [1, 1, 2, 3] already exists!", f.add_plates, [2], [1], [1], [2], [3],
            [2e11], [0.3], [0.01], [5 / 6])
+
+
+def test_row_strip_generators_match_local_part():
+    """meshes.*(rows=...) — what bench.py builds per rank — is exactly local_part() of the whole mesh."""
+    import numpy as np
+    from finite_element_method_b200 import meshes
+    for world in (2, 3, 8):
+        full = meshes.mixed_structure(24, 19)
+        for b, e in meshes.partition_rows(full, world, 25):
+            a = meshes.local_part(full, b, e)
+            c = meshes.mixed_structure(24, 19, rows=(b // 25, e // 25))
+            for k in ("x", "p_n", "p_props", "b_n1", "b_n2", "b_props", "b_axis", "t_n1", "t_n2", "t_E", "t_A"):
+                assert np.array_equal(np.asarray(a[k]), np.asarray(c[k])), (world, b, e, k)
+        full = meshes.plate_grid(17, 11, "flat")
+        for b, e in meshes.partition_rows(full, world, 18):
+            a = meshes.local_part(full, b, e)
+            c = meshes.plate_grid(17, 11, "flat", rows=(b // 18, e // 18))
+            for k in ("p_n", "p_props"):
+                assert np.array_equal(np.asarray(a[k]), np.asarray(c[k])), (world, b, e, k)
