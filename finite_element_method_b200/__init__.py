@@ -3,7 +3,7 @@ RomanShushakov/finite_element_method: truss / beam / plate local stiffness + det
 assembly into the global FP64 CSR matrix. The product is libfemgpu.so (C ABI in include/femgpu.h);
 this package is its Python host mirror (`FEM`) plus synthetic mesh generators for the benchmarks.
 """
-from .fem import BEAM, PLATE, TRUSS, FEM, FemError  # noqa: F401
+from .fem import BEAM, PLATE, TRUSS, FEM, DOFParameter, FemError, SeparatedStiffnessMatrixSparse  # noqa: F401
 from . import meshes  # noqa: F401
 
-__all__ = ["FEM", "FemError", "TRUSS", "BEAM", "PLATE", "meshes"]
+__all__ = ["FEM", "FemError", "DOFParameter", "SeparatedStiffnessMatrixSparse", "TRUSS", "BEAM", "PLATE", "meshes"]

@@ -42,6 +42,15 @@ SIGNATURES = {
     "femgpu_rotation_elements": (C.c_int32, [H, C.c_int32, C.c_uint32, dp]),
     "femgpu_element_matrix": (C.c_int32, [H, C.c_int32, C.c_uint32, dp]),
     "femgpu_element_slots": (C.c_int32, [H, C.c_int32, C.c_uint32, i64p]),
+    "femgpu_add_displacement": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
+    "femgpu_add_concentrated_load": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
+    "femgpu_separate_sparse": (C.c_int32, [H, i64p, i64p, i64p]),
+    "femgpu_get_separated_indexes": (C.c_int32, [H, i64p, i64p]),
+    "femgpu_get_separated_csr": (C.c_int32, [H, C.c_int32, i64p, i32p, dp]),
+    "femgpu_get_separated_csr_device": (C.c_int32, [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                    C.POINTER(C.c_void_p)]),
+    "femgpu_separated_rhs": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
+    "femgpu_last_separate_ms": (C.c_int32, [H, fp]),
     "femgpu_launch_count": (C.c_int32, [H, C.c_int32, u64p]),
     "femgpu_last_numeric_ms": (C.c_int32, [H, fp]),
     "femgpu_numeric_ms_history": (C.c_int32, [H, C.c_uint32, fp]),

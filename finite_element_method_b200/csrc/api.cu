@@ -473,6 +473,7 @@ int32_t append_to_device(Handle* h, DevBuf<T>& buf, const std::vector<T>& host, 
     // old buffer is only read by work already queued on h->stream, and cudaFree synchronises.
     DevBuf<T> nb;
     nb.tally = buf.tally;
+    nb.stream = buf.stream;
     FEMGPU_CUDA_CHECK(h, nb.reserve(n));
     int32_t st = h2d_staged(h, nb.p, host.data(), n * sizeof(T));
     if (st) return st;
@@ -554,6 +555,12 @@ int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t n
   }
   for (auto& q : h->ev)
     for (auto& ev : q) cudaEventCreate(&ev);
+  // keep freed device memory in the stream-ordered pool instead of returning it to the driver
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   *out = h;
   return 0;
 }
@@ -574,6 +581,7 @@ static void free_device(femgpu_t* h) {
   h->col_idx.release(); h->values.release(); h->scratch.release(); h->d_flag.release();
   h->dist.send_buf.release(); h->dist.recv_buf.release(); h->dist.recv_dst_block.release();
   h->dist.recv_full.release(); h->dist.remote_keys.release();
+  sep_release(h);
 }
 
 int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
@@ -588,6 +596,7 @@ int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
   for (auto& x : h->nodeset_seen) x.clear();
   h->n_contrib = 0;
   h->journal.clear();
+  bc_clear(h);
   h->symbolic_valid = false;
   h->n_rows = h->nnz = 0;
   h->n_blocks = h->n_slabs = 0;

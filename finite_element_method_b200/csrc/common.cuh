@@ -37,24 +37,38 @@ struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
   size_t* tally = nullptr;
+  // Buffers tied to a handle come from the device's stream-ordered pool (cudaMallocAsync on the
+  // handle's stream; femgpu_create lifts the pool's release threshold), so the tens of gigabytes a
+  // model needs are mapped once per process and re-used by the next symbolic pass / reset / handle
+  // instead of going back to the driver. Untied buffers fall back to cudaMalloc.
+  cudaStream_t* stream = nullptr;
+  bool pooled = false;
+  void drop(T* q, bool was_pooled) {
+    if (!q) return;
+    if (was_pooled && stream && *stream) cudaFreeAsync(q, *stream);
+    else cudaFree(q);
+  }
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     size_t want = n + n / 8 + 16;
     T* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    const bool pool = stream && *stream;
+    cudaError_t e = pool ? cudaMallocAsync(reinterpret_cast<void**>(&q), want * sizeof(T), *stream)
+                         : cudaMalloc(&q, want * sizeof(T));
     if (e != cudaSuccess) return e;
     if (p) {
-      cudaFree(p);
+      drop(p, pooled);
       if (tally) *tally -= cap * sizeof(T);
     }
     p = q;
+    pooled = pool;
     cap = want;
     if (tally) *tally += cap * sizeof(T);
     return cudaSuccess;
   }
   void release() {
     if (p) {
-      cudaFree(p);
+      drop(p, pooled);
       if (tally) *tally -= cap * sizeof(T);
     }
     p = nullptr;
@@ -300,6 +314,28 @@ struct Handle {
     DevBuf<int64_t> i64;
   } dist_scratch;
 
+  // ---- boundary conditions and the separated matrix (separate.cu) ----
+  struct BoundaryConditions {
+    std::vector<uint8_t> constrained;         // imposed_constraints, [6 * nodes_number] (fem.rs:24,45)
+    std::vector<double> displacement, force;  // displacements_vector / forces_vector (fem.rs:18-19)
+    bool uploaded = false;
+  } bc;
+  struct Separated {
+    bool valid = false;
+    int64_t n_aa = 0, n_bb = 0;
+    int64_t nnz[4] = {0, 0, 0, 0};  // aa, ab, ba, bb
+    float last_ms = 0.f;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    DevBuf<uint8_t> d_constrained;
+    DevBuf<double> d_disp, d_force, rhs;
+    DevBuf<uint32_t> cls_pos;         // per DOF: class (0 inactive, 1 a, 2 b) << 30 | local index
+    DevBuf<int64_t> aa_idx, bb_idx;   // k_aa_indexes / k_bb_indexes
+    DevBuf<int64_t> row_ptr[4];
+    DevBuf<int32_t> col[4];
+    DevBuf<double> val[4];
+    DevBuf<int32_t> tmp[8];           // scratch: class flags, their scans, per-row counts of the 4 quadrants
+  } sep;
+
   // Pinned bounce buffers of the bulk host->device path (api.cu h2d_staged): the host staging vectors
   // are pageable, so large uploads are copied chunk-wise into pinned memory by several host threads
   // while the previous chunk is on its way over PCIe.
@@ -310,7 +346,10 @@ struct Handle {
   int pin_next = 0;
 
   Handle() {
-    auto tie = [&](auto& b) { b.tally = &dev_bytes; };
+    auto tie = [&](auto& b) {
+      b.tally = &dev_bytes;
+      b.stream = &stream;
+    };
     tie(d_x); tie(d_y); tie(d_z);
     for (auto& f : fd) {
       for (auto& c : f.conn) tie(c);
@@ -322,6 +361,12 @@ struct Handle {
     tie(col_idx); tie(values); tie(scratch); tie(d_flag);
     tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_dst_block); tie(dist.recv_full);
     tie(dist.remote_keys); tie(dist_scratch.i64);
+    tie(sep.d_constrained); tie(sep.d_disp); tie(sep.d_force); tie(sep.rhs); tie(sep.cls_pos); tie(sep.aa_idx);
+    tie(sep.bb_idx);
+    for (int q = 0; q < 4; ++q) {
+      tie(sep.row_ptr[q]); tie(sep.col[q]); tie(sep.val[q]);
+    }
+    for (auto& t : sep.tmp) tie(t);
   }
 
   int32_t fail(int32_t code, const std::string& text) const {
@@ -342,6 +387,9 @@ int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);  
 int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
 int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host);   // symbolic.cu
 int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals);  // symbolic.cu
+int32_t run_separate(Handle* h);                         // separate.cu
+void sep_release(Handle* h);                             // separate.cu
+void bc_clear(Handle* h);                                // separate.cu
 int32_t dist_numeric_exchange(Handle* h);                // dist.cu
 void dist_destroy(Handle* h);                            // dist.cu
 int32_t dist_allgather_i64(Handle* h, const int64_t* send, int64_t* recv, size_t n);  // dist.cu

@@ -1,0 +1,564 @@
+// Boundary conditions and the sparse separation of the assembled matrix — the first consumer of K
+// in the reference:
+//   FEM::add_displacement / add_concentrated_load        methods_for_bc_data_handle.rs:31-56,175-203
+//   FEM::separate_stiffness_matrix_sparse_iterative      methods_for_separate_stiffness_matrix.rs:217-320
+//   compose_r_a_vector / compose_u_b_vector / find_b_sparse
+//                                methods_for_separate_stiffness_matrix.rs:322-343, methods_for_global_analysis.rs:28-48
+//
+// The reference walks the position-keyed map of K three times on one core. Here the CSR values stay
+// in HBM and the separation is integer stream compaction:
+//   1. classify every DOF from its diagonal entry and the constraint flags
+//      (zero diagonal -> inactive, constrained -> "b", else "a"), first error = smallest index;
+//   2. exclusive scans give the local numbering of the a- and b-sets (ascending global index, like
+//      the reference's push order);
+//   3. one warp per row counts its non-zero entries per quadrant, scans give four CSR row pointers;
+//   4. the same walk writes (local column, value) in row order — deterministic and column-sorted.
+// Entries equal to 0.0 are dropped (the reference skips them, :277-279) and entries touching an
+// inactive DOF are ignored (:296-299), so the four matrices hold exactly the reference's triplets,
+// as CSR (its consumer builds CsrMatrix::from_coo out of them, methods_for_global_analysis.rs:205).
+// Bound: HBM — col_idx and values are read twice, the compacted copies written once.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace femgpu {
+
+namespace {
+
+constexpr uint32_t kClsNone = 0u, kClsA = 1u, kClsB = 2u;
+
+struct CastI64 {
+  __host__ __device__ int64_t operator()(const int32_t& v) const { return int64_t(v); }
+};
+
+// diag(K)[i]: the row's columns ascend, so the diagonal is found by bisection; an absent entry is 0
+__global__ void classify_kernel(int64_t n_rows, const int64_t* __restrict__ row_ptr,
+                                const int32_t* __restrict__ col_idx, const double* __restrict__ values,
+                                const uint8_t* __restrict__ constrained, int32_t* __restrict__ is_a,
+                                int32_t* __restrict__ is_b, unsigned long long* __restrict__ first_bad) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  int64_t lo = row_ptr[i], hi = row_ptr[i + 1];
+  double d = 0.0;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    int32_t c = col_idx[mid];
+    if (c == int32_t(i)) {
+      d = values[mid];
+      break;
+    }
+    if (c < int32_t(i)) lo = mid + 1;
+    else hi = mid;
+  }
+  const bool fixed = constrained[i] != 0;
+  int32_t a = 0, b = 0;
+  if (d == 0.0) {
+    if (fixed) atomicMin(first_bad, (unsigned long long)i);  // integer min: order independent
+  } else if (fixed) {
+    b = 1;
+  } else {
+    a = 1;
+  }
+  is_a[i] = a;
+  is_b[i] = b;
+}
+
+// cls_pos[i] = class << 30 | local index; index lists in ascending global order
+__global__ void number_kernel(int64_t n_rows, const int32_t* __restrict__ is_a, const int32_t* __restrict__ is_b,
+                              const int32_t* __restrict__ pos_a, const int32_t* __restrict__ pos_b,
+                              uint32_t* __restrict__ cls_pos, int64_t* __restrict__ aa_idx,
+                              int64_t* __restrict__ bb_idx) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  uint32_t v = 0;
+  if (is_a[i]) {
+    v = (kClsA << 30) | uint32_t(pos_a[i]);
+    aa_idx[pos_a[i]] = i;
+  } else if (is_b[i]) {
+    v = (kClsB << 30) | uint32_t(pos_b[i]);
+    bb_idx[pos_b[i]] = i;
+  }
+  cls_pos[i] = v;
+}
+
+// One warp per global row. kFill = false: count the row's non-zero entries whose column is in the
+// a-set / b-set. kFill = true: write them, in row order, at the positions the scanned counts give.
+// Quadrants: 0 = aa, 1 = ab, 2 = ba, 3 = bb.
+struct SepOut {
+  int64_t* row_ptr[4];
+  int32_t* col[4];
+  double* val[4];
+  int32_t* cnt[4];
+};
+
+// one row, any length: chunks of 32 entries, ballots give the in-row positions
+template <bool kFill>
+__device__ __forceinline__ void quadrant_row(uint32_t lane, uint32_t rc, int64_t begin, int64_t end,
+                                             const int32_t* __restrict__ col_idx, const double* __restrict__ values,
+                                             const uint32_t* __restrict__ cls_pos, const SepOut& out) {
+  const uint32_t rcls = rc >> 30, rloc = rc & 0x3FFFFFFFu;
+  if (rcls == kClsNone) return;
+  const int qa = rcls == kClsA ? 0 : 2, qb = qa + 1;
+  int64_t wa = 0, wb = 0;
+  if (kFill) {
+    wa = out.row_ptr[qa][rloc];
+    wb = out.row_ptr[qb][rloc];
+  }
+  uint32_t na = 0, nb = 0;
+  for (int64_t p = begin + lane; p - lane < end; p += 32) {
+    bool in_a = false, in_b = false;
+    double v = 0.0;
+    uint32_t cloc = 0;
+    if (p < end) {
+      v = values[p];
+      if (v != 0.0) {
+        const uint32_t cc = cls_pos[col_idx[p]];
+        in_a = (cc >> 30) == kClsA;
+        in_b = (cc >> 30) == kClsB;
+        cloc = cc & 0x3FFFFFFFu;
+      }
+    }
+    const uint32_t ma = __ballot_sync(0xFFFFFFFFu, in_a), mb = __ballot_sync(0xFFFFFFFFu, in_b);
+    if (kFill) {
+      const uint32_t below = (1u << lane) - 1u;
+      if (in_a) {
+        const int64_t w = wa + na + __popc(ma & below);
+        out.col[qa][w] = int32_t(cloc);
+        out.val[qa][w] = v;
+      } else if (in_b) {
+        const int64_t w = wb + nb + __popc(mb & below);
+        out.col[qb][w] = int32_t(cloc);
+        out.val[qb][w] = v;
+      }
+    }
+    na += __popc(ma);
+    nb += __popc(mb);
+  }
+  if (!kFill && lane == 0) {
+    out.cnt[qa][rloc] = int32_t(na);
+    out.cnt[qb][rloc] = int32_t(nb);
+  }
+}
+
+// One warp per kRowsPerWarp consecutive rows. Rows of a structural model are short (54 entries on a
+// plate grid) and each needs a chain of dependent loads (row_ptr -> values/col_idx -> class of the
+// column), so a warp that walks one row at a time is latency-bound. When its rows have at most 64
+// entries each — two chunks of 32 — the warp issues the loads of all of them back to back before
+// the first use; longer rows take the generic loop.
+constexpr int kRowsPerWarp = 4;
+
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+quadrant_kernel(int64_t n_rows, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                const double* __restrict__ values, const uint32_t* __restrict__ cls_pos, SepOut out) {
+  const int64_t row0 = ((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * kRowsPerWarp;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (row0 >= n_rows) return;
+  // lanes 0..4 fetch the five row pointers, lanes 0..3 the rows' classes
+  const int64_t my_row = row0 + lane;
+  const int64_t ptr_l = (lane <= uint32_t(kRowsPerWarp) && my_row <= n_rows) ? row_ptr[my_row] : 0;
+  const uint32_t cls_l = (lane < uint32_t(kRowsPerWarp) && my_row < n_rows) ? cls_pos[my_row] : 0u;
+  int64_t begin[kRowsPerWarp], end[kRowsPerWarp];
+  uint32_t rc[kRowsPerWarp];
+  bool all_short = true;
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    begin[r] = __shfl_sync(0xFFFFFFFFu, ptr_l, r);
+    end[r] = __shfl_sync(0xFFFFFFFFu, ptr_l, r + 1);
+    rc[r] = __shfl_sync(0xFFFFFFFFu, cls_l, r);
+    if (row0 + r >= n_rows) {
+      rc[r] = 0u;
+      end[r] = begin[r];
+    }
+    all_short = all_short && (end[r] - begin[r] <= 64);
+  }
+  if (!all_short) {
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) quadrant_row<kFill>(lane, rc[r], begin[r], end[r], col_idx, values, cls_pos, out);
+    return;
+  }
+  double v[kRowsPerWarp][2];
+  int32_t c[kRowsPerWarp][2];
+  uint32_t cc[kRowsPerWarp][2];
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int64_t p = begin[r] + lane + 32 * k;
+      const bool on = (rc[r] >> 30) != kClsNone && p < end[r];
+      v[r][k] = on ? values[p] : 0.0;
+      c[r][k] = on ? col_idx[p] : 0;
+    }
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) cc[r][k] = (v[r][k] != 0.0) ? cls_pos[c[r][k]] : 0u;
+  int64_t wa[kRowsPerWarp], wb[kRowsPerWarp];
+  if (kFill) {
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const uint32_t rcls = rc[r] >> 30, rloc = rc[r] & 0x3FFFFFFFu;
+      const int qa = rcls == kClsA ? 0 : 2;
+      wa[r] = rcls != kClsNone ? out.row_ptr[qa][rloc] : 0;
+      wb[r] = rcls != kClsNone ? out.row_ptr[qa + 1][rloc] : 0;
+    }
+  }
+  const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const uint32_t rcls = rc[r] >> 30, rloc = rc[r] & 0x3FFFFFFFu;
+    if (rcls == kClsNone) continue;  // warp-uniform
+    const int qa = rcls == kClsA ? 0 : 2, qb = qa + 1;
+    uint32_t na = 0, nb = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const bool in_a = (cc[r][k] >> 30) == kClsA, in_b = (cc[r][k] >> 30) == kClsB;
+      const uint32_t ma = __ballot_sync(0xFFFFFFFFu, in_a), mb = __ballot_sync(0xFFFFFFFFu, in_b);
+      if (kFill) {
+        if (in_a) {
+          const int64_t w = wa[r] + na + __popc(ma & below);
+          out.col[qa][w] = int32_t(cc[r][k] & 0x3FFFFFFFu);
+          out.val[qa][w] = v[r][k];
+        } else if (in_b) {
+          const int64_t w = wb[r] + nb + __popc(mb & below);
+          out.col[qb][w] = int32_t(cc[r][k] & 0x3FFFFFFFu);
+          out.val[qb][w] = v[r][k];
+        }
+      }
+      na += __popc(ma);
+      nb += __popc(mb);
+    }
+    if (!kFill && lane == 0) {
+      out.cnt[qa][rloc] = int32_t(na);
+      out.cnt[qb][rloc] = int32_t(nb);
+    }
+  }
+}
+
+// b = R_a - K_ab u_b, one thread per a-row, summed in row order (find_b_sparse)
+__global__ void rhs_kernel(int64_t n_aa, const int64_t* __restrict__ aa_idx, const int64_t* __restrict__ bb_idx,
+                           const double* __restrict__ force, const double* __restrict__ disp,
+                           const int64_t* __restrict__ ab_ptr, const int32_t* __restrict__ ab_col,
+                           const double* __restrict__ ab_val, double* __restrict__ b) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_aa) return;
+  double acc = force[aa_idx[i]];
+  for (int64_t p = ab_ptr[i]; p < ab_ptr[i + 1]; ++p) acc = acc - ab_val[p] * disp[bb_idx[ab_col[p]]];
+  b[i] = acc;
+}
+
+const char* dof_name(int d) {
+  static const char* names[6] = {"X", "Y", "Z", "ThX", "ThY", "ThZ"};  // DOFParameter's {:?}
+  return names[d];
+}
+
+void ensure_bc(Handle* h) {
+  const size_t n = size_t(h->nodes_number) * 6;
+  if (h->bc.constrained.size() != n) {
+    h->bc.constrained.assign(n, 0);
+    h->bc.displacement.assign(n, 0.0);
+    h->bc.force.assign(n, 0.0);
+  }
+}
+
+template <typename T>
+cudaError_t scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s) {
+  cub::TransformInputIterator<int64_t, CastI64, const int32_t*> it(in, CastI64());
+  size_t tb = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, out, n, s);
+  if (e != cudaSuccess) return e;
+  void* t = nullptr;
+  if ((e = cudaMallocAsync(&t, tb ? tb : 16, s)) != cudaSuccess) return e;
+  e = cub::DeviceScan::ExclusiveSum(t, tb, it, out, n, s);
+  cudaFreeAsync(t, s);
+  return e;
+}
+
+cudaError_t scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s) {
+  size_t tb = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s);
+  if (e != cudaSuccess) return e;
+  void* t = nullptr;
+  if ((e = cudaMallocAsync(&t, tb ? tb : 16, s)) != cudaSuccess) return e;
+  e = cub::DeviceScan::ExclusiveSum(t, tb, in, out, n, s);
+  cudaFreeAsync(t, s);
+  return e;
+}
+
+}  // namespace
+
+void bc_clear(Handle* h) {
+  h->bc.constrained.clear();
+  h->bc.displacement.clear();
+  h->bc.force.clear();
+  h->bc.uploaded = false;
+  h->sep.valid = false;
+}
+
+void sep_release(Handle* h) {
+  Handle::Separated& S = h->sep;
+  S.d_constrained.release(); S.d_disp.release(); S.d_force.release(); S.cls_pos.release();
+  S.aa_idx.release(); S.bb_idx.release(); S.rhs.release();
+  for (auto& t : S.tmp) t.release();
+  for (int q = 0; q < 4; ++q) {
+    S.row_ptr[q].release(); S.col[q].release(); S.val[q].release();
+  }
+  for (auto& e : S.ev) {
+    if (e) cudaEventDestroy(e);
+    e = nullptr;
+  }
+  S.valid = false;
+  h->bc.uploaded = false;
+}
+
+// n x FEM::add_displacement / add_concentrated_load, prefix semantics like the element batches
+int32_t bc_add(Handle* h, bool displacement, size_t n, const uint32_t* node_number, const int32_t* dof,
+               const double* value) {
+  if (n == 0) return 0;
+  if (!node_number || !dof || !value) return h->fail(FEMGPU_ERR_USAGE, "null boundary-condition array");
+  ensure_bc(h);
+  for (size_t k = 0; k < n; ++k) {
+    if (dof[k] < 0 || dof[k] > 5) return h->fail(FEMGPU_ERR_USAGE, "dof parameter must be 0..5 (X, Y, Z, ThX, ThY, ThZ)");
+    uint32_t idx;
+    if (!h->node_by_number.find(node_number[k], &idx))
+      // check_node_exist, methods_for_node_data_handle.rs:80-86
+      return h->fail(FEMGPU_E_NODE_NOT_EXIST, "Node with number " + std::to_string(node_number[k]) + " does not exist!");
+    const size_t i = size_t(idx) * 6 + size_t(dof[k]);
+    if (displacement) {
+      if (h->bc.constrained[i])  // methods_for_bc_data_handle.rs:190-194
+        return h->fail(FEMGPU_E_DISPLACEMENT_EXISTS, std::string("Displacement ") + dof_name(dof[k]) +
+                                                         " already applied to node " + std::to_string(node_number[k]) + "!");
+      h->bc.constrained[i] = 1;
+      h->bc.displacement[i] = value[k];
+    } else {
+      h->bc.force[i] += value[k];  // methods_for_bc_data_handle.rs:47-53
+    }
+    h->bc.uploaded = false;
+    h->sep.valid = false;
+  }
+  return 0;
+}
+
+int32_t run_separate(Handle* h) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  Handle::Separated& S = h->sep;
+  const int64_t n = h->n_rows;
+  ensure_bc(h);
+  if (!S.ev[0]) {
+    FEMGPU_CUDA_CHECK(h, cudaEventCreate(&S.ev[0]));
+    FEMGPU_CUDA_CHECK(h, cudaEventCreate(&S.ev[1]));
+  }
+  cudaEvent_t e0 = S.ev[0], e1 = S.ev[1];
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(e0, s));
+  FEMGPU_CUDA_CHECK(h, S.d_constrained.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, S.d_disp.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, S.d_force.reserve(size_t(n) + 1));
+  if (!h->bc.uploaded && n) {
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_constrained.p, h->bc.constrained.data(), size_t(n), cudaMemcpyHostToDevice, s));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_disp.p, h->bc.displacement.data(), size_t(n) * 8, cudaMemcpyHostToDevice, s));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_force.p, h->bc.force.data(), size_t(n) * 8, cudaMemcpyHostToDevice, s));
+    h->bc.uploaded = true;
+  }
+  S.valid = false;
+  S.n_aa = S.n_bb = 0;
+  for (auto& z : S.nnz) z = 0;
+
+  // ---- 1. classes, 2. local numbering (scratch arrays stay with the handle for the next call)
+  DevBuf<int32_t>&is_a = S.tmp[0], &is_b = S.tmp[1], &pos_a = S.tmp[2], &pos_b = S.tmp[3];
+  FEMGPU_CUDA_CHECK(h, is_a.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, is_b.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, pos_a.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, pos_b.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, h->d_flag.reserve(16));
+  unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(h->d_flag.p);
+  unsigned long long none = ~0ull;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_bad, &none, 8, cudaMemcpyHostToDevice, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(is_a.p + n, 0, 4, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(is_b.p + n, 0, 4, s));
+  if (n) {
+    classify_kernel<<<div_up(n, 256), 256, 0, s>>>(n, h->row_ptr.p, h->col_idx.p, h->values.p, S.d_constrained.p,
+                                                  is_a.p, is_b.p, d_bad);
+    h->launches++;
+  }
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  FEMGPU_CUDA_CHECK(h, scan_i32(is_a.p, pos_a.p, n + 1, s));
+  FEMGPU_CUDA_CHECK(h, scan_i32(is_b.p, pos_b.p, n + 1, s));
+  unsigned long long bad = 0;
+  int32_t n_aa = 0, n_bb = 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&n_aa, pos_a.p + n, 4, cudaMemcpyDeviceToHost, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&n_bb, pos_b.p + n, 4, cudaMemcpyDeviceToHost, s));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(s));
+  if (bad != ~0ull) {
+    // methods_for_separate_stiffness_matrix.rs:233-243
+    const size_t node = size_t(bad / 6);
+    const uint32_t number = node < h->n_nodes() ? h->node_number[node] : 0u;
+    return h->fail(FEMGPU_E_NO_STIFFNESS_FOR_DISPLACEMENT,
+                   std::string("There are no stiffness to withstand displacement ") + dof_name(int(bad % 6)) +
+                       " applied to node " + std::to_string(number) + "!");
+  }
+  if (n_bb == 0) return h->fail(FEMGPU_E_NO_RESTRAINTS, "No restraints");  // :257-259
+  if (n >= (int64_t(1) << 30)) return h->fail(FEMGPU_ERR_LIMIT, "separation supports < 2^30 degrees of freedom");
+
+  FEMGPU_CUDA_CHECK(h, S.cls_pos.reserve(size_t(n)));
+  FEMGPU_CUDA_CHECK(h, S.aa_idx.reserve(size_t(n_aa) + 1));
+  FEMGPU_CUDA_CHECK(h, S.bb_idx.reserve(size_t(n_bb) + 1));
+  number_kernel<<<div_up(n, 256), 256, 0, s>>>(n, is_a.p, is_b.p, pos_a.p, pos_b.p, S.cls_pos.p, S.aa_idx.p,
+                                              S.bb_idx.p);
+  h->launches++;
+
+  // ---- 3. counts per row and quadrant -> row pointers
+  const int64_t rows_q[4] = {n_aa, n_aa, n_bb, n_bb};
+  DevBuf<int32_t>* cnt = S.tmp + 4;
+  SepOut out{};
+  for (int q = 0; q < 4; ++q) {
+    FEMGPU_CUDA_CHECK(h, cnt[q].reserve(size_t(rows_q[q]) + 1));
+    FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(cnt[q].p, 0, (size_t(rows_q[q]) + 1) * 4, s));
+    FEMGPU_CUDA_CHECK(h, S.row_ptr[q].reserve(size_t(rows_q[q]) + 1));
+    out.cnt[q] = cnt[q].p;
+    out.row_ptr[q] = S.row_ptr[q].p;
+  }
+  const uint32_t warp_grid = div_up(uint64_t(div_up(n, kRowsPerWarp)) * 32, 256);
+  quadrant_kernel<false><<<warp_grid, 256, 0, s>>>(n, h->row_ptr.p, h->col_idx.p, h->values.p, S.cls_pos.p, out);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  for (int q = 0; q < 4; ++q) {
+    FEMGPU_CUDA_CHECK(h, scan_i32_to_i64<int>(cnt[q].p, S.row_ptr[q].p, rows_q[q] + 1, s));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&S.nnz[q], S.row_ptr[q].p + rows_q[q], 8, cudaMemcpyDeviceToHost, s));
+  }
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(s));
+  if (S.nnz[0] == 0)  // :303-307
+    return h->fail(FEMGPU_E_KAA_EMPTY, "Sparse separation: K_aa is empty (structure has no free stiffness?)");
+
+  // ---- 4. fill
+  for (int q = 0; q < 4; ++q) {
+    FEMGPU_CUDA_CHECK(h, S.col[q].reserve(size_t(S.nnz[q]) + 1));
+    FEMGPU_CUDA_CHECK(h, S.val[q].reserve(size_t(S.nnz[q]) + 1));
+    out.col[q] = S.col[q].p;
+    out.val[q] = S.val[q].p;
+  }
+  quadrant_kernel<true><<<warp_grid, 256, 0, s>>>(n, h->row_ptr.p, h->col_idx.p, h->values.p, S.cls_pos.p, out);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+
+  // ---- b = R_a - K_ab u_b
+  FEMGPU_CUDA_CHECK(h, S.rhs.reserve(size_t(n_aa) + 1));
+  rhs_kernel<<<div_up(n_aa, 256), 256, 0, s>>>(n_aa, S.aa_idx.p, S.bb_idx.p, S.d_force.p, S.d_disp.p, S.row_ptr[1].p,
+                                              S.col[1].p, S.val[1].p, S.rhs.p);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(e1, s));
+  FEMGPU_CUDA_CHECK(h, cudaEventSynchronize(e1));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&S.last_ms, e0, e1));
+  S.n_aa = n_aa;
+  S.n_bb = n_bb;
+  S.valid = true;
+  return 0;
+}
+
+}  // namespace femgpu
+
+using femgpu::Handle;
+
+extern "C" {
+
+static int32_t sep_ready(femgpu_t* h) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0)
+    return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
+                                         "femgpu has no CPU fallback");
+  if (!h->sep.valid) return h->fail(FEMGPU_ERR_USAGE, "no separated matrix: call femgpu_separate_sparse first");
+  return 0;
+}
+
+int32_t femgpu_add_displacement(femgpu_t* h, size_t n, const uint32_t* node_number, const int32_t* dof,
+                                const double* value) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  return femgpu::bc_add(h, true, n, node_number, dof, value);
+}
+
+int32_t femgpu_add_concentrated_load(femgpu_t* h, size_t n, const uint32_t* node_number, const int32_t* dof,
+                                     const double* value) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  return femgpu::bc_add(h, false, n, node_number, dof, value);
+}
+
+int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t nnz[4]) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0)
+    return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
+                                         "femgpu has no CPU fallback");
+  if (!h->symbolic_valid || h->n_numeric == 0)
+    return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_sparse needs an assembled matrix (femgpu_assemble)");
+  if (h->dist.enabled)
+    return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_sparse is single-GPU for now (the rows of a multi-GPU "
+                                     "assembly stay partitioned)");
+  int32_t st = femgpu::run_separate(h);
+  if (st) return st;
+  if (n_aa) *n_aa = h->sep.n_aa;
+  if (n_bb) *n_bb = h->sep.n_bb;
+  if (nnz)
+    for (int q = 0; q < 4; ++q) nnz[q] = h->sep.nnz[q];
+  return 0;
+}
+
+int32_t femgpu_get_separated_indexes(femgpu_t* h, int64_t* k_aa_indexes, int64_t* k_bb_indexes) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  if (k_aa_indexes && h->sep.n_aa)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(k_aa_indexes, h->sep.aa_idx.p, size_t(h->sep.n_aa) * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (k_bb_indexes && h->sep.n_bb)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(k_bb_indexes, h->sep.bb_idx.p, size_t(h->sep.n_bb) * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t femgpu_get_separated_csr(femgpu_t* h, int32_t which, int64_t* row_ptr, int32_t* col_idx, double* values) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  if (which < 0 || which > 3) return h->fail(FEMGPU_ERR_USAGE, "quadrant must be 0..3 (aa, ab, ba, bb)");
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const int64_t rows = which < 2 ? h->sep.n_aa : h->sep.n_bb, nnz = h->sep.nnz[which];
+  if (row_ptr)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(row_ptr, h->sep.row_ptr[which].p, size_t(rows + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (col_idx && nnz)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(col_idx, h->sep.col[which].p, size_t(nnz) * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (values && nnz)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(values, h->sep.val[which].p, size_t(nnz) * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t femgpu_get_separated_csr_device(femgpu_t* h, int32_t which, const int64_t** row_ptr, const int32_t** col_idx,
+                                        const double** values) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  if (which < 0 || which > 3) return h->fail(FEMGPU_ERR_USAGE, "quadrant must be 0..3 (aa, ab, ba, bb)");
+  if (row_ptr) *row_ptr = h->sep.row_ptr[which].p;
+  if (col_idx) *col_idx = h->sep.col[which].p;
+  if (values) *values = h->sep.val[which].p;
+  return 0;
+}
+
+int32_t femgpu_separated_rhs(femgpu_t* h, double* b, const double** b_device) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  if (b && h->sep.n_aa) {
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(b, h->sep.rhs.p, size_t(h->sep.n_aa) * 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  }
+  if (b_device) *b_device = h->sep.rhs.p;
+  return 0;
+}
+
+int32_t femgpu_last_separate_ms(femgpu_t* h, float* ms) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  if (ms) *ms = h->sep.last_ms;
+  return 0;
+}
+
+}  // extern "C"

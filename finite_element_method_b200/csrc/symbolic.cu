@@ -23,14 +23,22 @@ namespace femgpu {
 
 namespace {
 
-struct Tmp {  // RAII scratch allocation
+// stream the scratch allocations of the running pass are ordered on (set by the entry points below)
+thread_local cudaStream_t t_tmp_stream = nullptr;
+
+struct Tmp {  // RAII scratch allocation from the stream-ordered pool
   void* p = nullptr;
+  cudaStream_t s = nullptr;
   cudaError_t alloc(size_t bytes) {
     release();
-    return cudaMalloc(&p, bytes ? bytes : 16);
+    s = t_tmp_stream;
+    return s ? cudaMallocAsync(&p, bytes ? bytes : 16, s) : cudaMalloc(&p, bytes ? bytes : 16);
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (s) cudaFreeAsync(p, s);
+      else cudaFree(p);
+    }
     p = nullptr;
   }
   ~Tmp() { release(); }
@@ -843,6 +851,7 @@ static int32_t dist_finalize_plan(Handle* h, const std::vector<int64_t>& ranges)
 int32_t run_symbolic(Handle* h) {
   SYM_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  t_tmp_stream = s;
   const bool timing = getenv("FEMGPU_SYM_TIMING") != nullptr;  // per-stage wall clock to stderr
   auto t_last = std::chrono::steady_clock::now();
   auto mark = [&](const char* what) {
@@ -1099,6 +1108,7 @@ int32_t run_symbolic(Handle* h) {
 
 int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host) {
   SYM_CHECK(cudaSetDevice(h->device));
+  t_tmp_stream = h->stream;
   const int nn = kNodesPerElem[family], dof = family == FEMGPU_TRUSS ? 3 : 6;
   const int n = nn * dof;
   uint32_t nodes[4];
@@ -1120,6 +1130,7 @@ int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host) {
 int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals) {
   SYM_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  t_tmp_stream = s;
   int64_t nnz = h->nnz;
   if (nnz == 0) {
     if (count) *count = 0;

@@ -24,6 +24,28 @@ from . import _lib
 TRUSS, BEAM, PLATE = 0, 1, 2
 
 
+class DOFParameter:
+    """methods_for_bc_data_handle.rs:6-13"""
+    X, Y, Z, ThX, ThY, ThZ = range(6)
+
+
+class SeparatedStiffnessMatrixSparse:
+    """structs/separated_stiffness_matrix_sparse.rs. The four quadrants are CSR matrices in local
+    indices (row_ptr, col_idx, values); `triplets(q)` expands one to the reference's (i, j, value) list."""
+
+    def __init__(self, k_aa_indexes, k_bb_indexes, quadrants, rhs, device_ms):
+        self.k_aa_indexes, self.k_bb_indexes = k_aa_indexes, k_bb_indexes
+        self.n_aa, self.n_bb = len(k_aa_indexes), len(k_bb_indexes)
+        self.k_aa, self.k_ab, self.k_ba, self.k_bb = quadrants
+        self.b = rhs                      # R_a - K_ab u_b (find_b_sparse)
+        self.device_ms = device_ms
+
+    def triplets(self, quadrant):
+        rp, ci, v = quadrant
+        rows = np.repeat(np.arange(len(rp) - 1, dtype=np.int64), np.diff(rp))
+        return rows, ci.astype(np.int64), v
+
+
 class FemError(Exception):
     """`Err(String)` of the reference. `.code` is the FEMGPU_E_* / FEMGPU_ERR_* status."""
 
@@ -220,6 +242,44 @@ class FEM:
             self._check(self._L.femgpu_get_nonzero_coo(self._h, C.byref(cnt), _p(r, _lib.i64p), _p(c, _lib.i64p),
                                                        _p(v, _lib.dp)))
         return r, c, v
+
+    # ------------------------------------------------------------------ boundary conditions, separation
+    def add_displacement(self, node_number, dof_parameter, value) -> None:
+        """methods_for_bc_data_handle.rs:175 (arrays are accepted: n calls in order)"""
+        nn, dd, vv = _u32(np.atleast_1d(node_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
+            _f64(np.atleast_1d(value))
+        self._check(self._L.femgpu_add_displacement(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p),
+                                                    _p(vv, _lib.dp)))
+
+    def add_concentrated_load(self, node_number, dof_parameter, value) -> None:
+        """methods_for_bc_data_handle.rs:31"""
+        nn, dd, vv = _u32(np.atleast_1d(node_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
+            _f64(np.atleast_1d(value))
+        self._check(self._L.femgpu_add_concentrated_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p),
+                                                         _p(vv, _lib.dp)))
+
+    def separate_stiffness_matrix_sparse_iterative(self, copy_out: bool = True):
+        """methods_for_separate_stiffness_matrix.rs:217, on the device. copy_out=False leaves the
+        quadrants in HBM (returns counts only): (n_aa, n_bb, [nnz_aa, nnz_ab, nnz_ba, nnz_bb], device_ms)."""
+        na, nb = C.c_int64(), C.c_int64()
+        nnz = np.zeros(4, np.int64)
+        self._check(self._L.femgpu_separate_sparse(self._h, C.byref(na), C.byref(nb), _p(nnz, _lib.i64p)))
+        ms = C.c_float()
+        self._check(self._L.femgpu_last_separate_ms(self._h, C.byref(ms)))
+        if not copy_out:
+            return int(na.value), int(nb.value), [int(x) for x in nnz], float(ms.value)
+        ia, ib = np.empty(na.value, np.int64), np.empty(nb.value, np.int64)
+        self._check(self._L.femgpu_get_separated_indexes(self._h, _p(ia, _lib.i64p), _p(ib, _lib.i64p)))
+        quads = []
+        for q in range(4):
+            rows = na.value if q < 2 else nb.value
+            rp, ci, v = np.empty(rows + 1, np.int64), np.empty(nnz[q], np.int32), np.empty(nnz[q], np.float64)
+            self._check(self._L.femgpu_get_separated_csr(self._h, q, _p(rp, _lib.i64p), _p(ci, _lib.i32p),
+                                                         _p(v, _lib.dp)))
+            quads.append((rp, ci, v))
+        b = np.empty(na.value, np.float64)
+        self._check(self._L.femgpu_separated_rhs(self._h, _p(b, _lib.dp), None))
+        return SeparatedStiffnessMatrixSparse(ia, ib, quads, b, float(ms.value))
 
     # ------------------------------------------------------------------ hooks
     def element_matrix(self, family: int, number: int):

@@ -70,7 +70,13 @@ enum {
   FEMGPU_E_THICKNESS = 29,
   FEMGPU_E_NODES_ON_LINE = 30,
   FEMGPU_E_NODES_NOT_ON_PLANE = 31,
-  FEMGPU_E_NOT_CONVEX = 32
+  FEMGPU_E_NOT_CONVEX = 32,
+  /* methods_for_bc_data_handle.rs:190-194 */
+  FEMGPU_E_DISPLACEMENT_EXISTS = 40,
+  /* methods_for_separate_stiffness_matrix.rs:233-243, :257-259, :303-307 */
+  FEMGPU_E_NO_STIFFNESS_FOR_DISPLACEMENT = 41,
+  FEMGPU_E_NO_RESTRAINTS = 42,
+  FEMGPU_E_KAA_EMPTY = 43
 };
 
 /* failures (<0) */
@@ -185,6 +191,46 @@ int32_t femgpu_element_matrix(femgpu_t* h, int32_t family, uint32_t number, doub
  * transformed matrix the index into `values`, or -1 where the structural pattern has no slot
  * (never happens for entries the reference would store). 36 | 144 | 576 int64. */
 int32_t femgpu_element_slots(femgpu_t* h, int32_t family, uint32_t number, int64_t* out);
+
+/* ---- boundary conditions and separation of K (first consumer of the assembled matrix) ------- */
+
+/* DOF parameters: DOFParameter of methods_for_bc_data_handle.rs:6-13 */
+#define FEMGPU_DOF_X 0
+#define FEMGPU_DOF_Y 1
+#define FEMGPU_DOF_Z 2
+#define FEMGPU_DOF_THX 3
+#define FEMGPU_DOF_THY 4
+#define FEMGPU_DOF_THZ 5
+
+/* n x FEM::add_displacement(node_number, dof_parameter, value)   methods_for_bc_data_handle.rs:175-203
+ * marks global index 6*node_index+dof as constrained; a second displacement on the same index is
+ * the reference's "Displacement {dof:?} already applied to node {n}!". Prefix semantics. */
+int32_t femgpu_add_displacement(femgpu_t* h, size_t n, const uint32_t* node_number, const int32_t* dof,
+                                const double* value);
+/* n x FEM::add_concentrated_load(node_number, dof_parameter, value): += into the forces vector
+ *                                                               methods_for_bc_data_handle.rs:31-56 */
+int32_t femgpu_add_concentrated_load(femgpu_t* h, size_t n, const uint32_t* node_number, const int32_t* dof,
+                                     const double* value);
+
+/* FEM::separate_stiffness_matrix_sparse_iterative()   methods_for_separate_stiffness_matrix.rs:217-320
+ * on the device, from the CSR values of the last numeric pass: DOFs with a zero diagonal are
+ * inactive (error when one of them is constrained), constrained ones form the b-set, the rest the
+ * a-set, both numbered in ascending global index; K_aa, K_ab, K_ba, K_bb hold the entries != 0.0
+ * between active DOFs. The reference returns unordered triplets; here each quadrant is a CSR matrix
+ * in local indices (rows and columns ascending) — the same set of triplets. Also evaluates
+ * b = R_a - K_ab u_b (find_b_sparse, methods_for_global_analysis.rs:28-48).
+ * nnz order: aa, ab, ba, bb. Out-pointers may be NULL. Single GPU. */
+int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t nnz[4]);
+/* k_aa_indexes [n_aa] / k_bb_indexes [n_bb]: global DOF index of every local row */
+int32_t femgpu_get_separated_indexes(femgpu_t* h, int64_t* k_aa_indexes, int64_t* k_bb_indexes);
+/* quadrant `which` (0 aa, 1 ab, 2 ba, 3 bb): row_ptr [rows+1], col_idx / values [nnz] */
+int32_t femgpu_get_separated_csr(femgpu_t* h, int32_t which, int64_t* row_ptr, int32_t* col_idx, double* values);
+int32_t femgpu_get_separated_csr_device(femgpu_t* h, int32_t which, const int64_t** row_ptr,
+                                        const int32_t** col_idx, const double** values);
+/* b = R_a - K_ab u_b [n_aa]; either pointer may be NULL */
+int32_t femgpu_separated_rhs(femgpu_t* h, double* b, const double** b_device);
+/* device milliseconds of the last femgpu_separate_sparse() */
+int32_t femgpu_last_separate_ms(femgpu_t* h, float* ms);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 

@@ -247,3 +247,59 @@ def faithful_coo(mesh):
     if len(mesh["t_n1"]):
         m.add_truss(mesh["t_n1"], mesh["t_n2"], mesh["t_E"], mesh["t_A"], mesh.get("t_A2"))
     return m.coo()
+
+
+# ---------------------------------------------------------------------------------------------
+# Sparse separation of K (restatement, numpy; integer/index work only — values are copied).
+# Follows FEM::separate_stiffness_matrix_sparse_iterative, methods_for_separate_stiffness_matrix.rs:217-320,
+# find_b_sparse, methods_for_global_analysis.rs:28-48, compose_r_a_vector / compose_u_b_vector :322-343.
+# PINNED against the reference's own sparse-separation test model (src/tests/fem/test_fem.rs:65-80:
+# n_aa > 0, K_aa non-empty) and the end-to-end numbers of :83-150 (u = b / K_aa = 0.0015, one PCG
+# iteration) in tests/test_separation.py; larger meshes are checked against this restatement.
+# ---------------------------------------------------------------------------------------------
+DOF_NAMES = ("X", "Y", "Z", "ThX", "ThY", "ThZ")
+
+
+class SeparationError(Exception):
+    pass
+
+
+def separate_sparse(n_dof, rows, cols, vals, constrained, node_numbers=None, forces=None, displacements=None):
+    """rows/cols/vals: the position-keyed map of K as COO (one entry per position).
+    constrained: bool[n_dof] imposed_constraints. Returns a dict with k_aa_indexes, k_bb_indexes, the
+    four triplet lists sorted by (i, j) (the reference's order is hash-map order, i.e. unspecified)
+    and b = R_a - K_ab u_b."""
+    rows = np.asarray(rows, np.int64); cols = np.asarray(cols, np.int64); vals = np.asarray(vals, np.float64)
+    constrained = np.asarray(constrained, bool)
+    diag = np.zeros(n_dof)                                   # :222-227
+    d = rows == cols
+    diag[rows[d]] = vals[d]
+    zero = diag == 0.0
+    bad = np.nonzero(zero & constrained)[0]                  # :232-243, first index in ascending order
+    if len(bad):
+        idx = int(bad[0])
+        number = 0 if node_numbers is None or idx // 6 >= len(node_numbers) else int(node_numbers[idx // 6])
+        raise SeparationError(f"There are no stiffness to withstand displacement {DOF_NAMES[idx % 6]} applied to node {number}!")
+    k_bb = np.nonzero(~zero & constrained)[0]                # :250-254
+    k_aa = np.nonzero(~zero & ~constrained)[0]
+    if len(k_bb) == 0:
+        raise SeparationError("No restraints")               # :257-259
+    aa_pos = np.full(n_dof, -1, np.int64); aa_pos[k_aa] = np.arange(len(k_aa))   # :264-271
+    bb_pos = np.full(n_dof, -1, np.int64); bb_pos[k_bb] = np.arange(len(k_bb))
+    nz = vals != 0.0                                         # :277-279
+    r, c, v = rows[nz], cols[nz], vals[nz]
+    out = {"k_aa_indexes": k_aa, "k_bb_indexes": k_bb, "n_aa": len(k_aa), "n_bb": len(k_bb)}
+    for name, rp, cp in (("k_aa", aa_pos, aa_pos), ("k_ab", aa_pos, bb_pos), ("k_ba", bb_pos, aa_pos), ("k_bb", bb_pos, bb_pos)):
+        m = (rp[r] >= 0) & (cp[c] >= 0)                      # :288-299
+        i, j, x = rp[r][m], cp[c][m], v[m]
+        o = np.lexsort((j, i))
+        out[name] = (i[o], j[o], x[o])
+    if len(out["k_aa"][0]) == 0:                             # :303-307
+        raise SeparationError("Sparse separation: K_aa is empty (structure has no free stiffness?)")
+    if forces is not None and displacements is not None:
+        b = np.asarray(forces, np.float64)[k_aa].copy()      # compose_r_a_vector
+        u_b = np.asarray(displacements, np.float64)[k_bb]    # compose_u_b_vector
+        i, j, x = out["k_ab"]
+        np.subtract.at(b, i, x * u_b[j])                     # find_b_sparse (row order; the reference's is unspecified)
+        out["b"] = b
+    return out

@@ -1,0 +1,193 @@
+"""Sparse separation of the assembled matrix: FEM::add_displacement,
+add_concentrated_load, separate_stiffness_matrix_sparse_iterative, find_b_sparse.
+
+CPU tests pin the oracle restatement on the reference's own test model
+(/root/reference/src/tests/fem/test_fem.rs:65-150) and cover the host-side checks; GPU tests compare the
+device separation with the oracle, bit for bit (index work and copied values)."""
+import numpy as np
+import pytest
+
+from finite_element_method_b200 import FEM, DOFParameter, FemError, meshes
+from oracle import oracle as O
+
+
+# ---------------------------------------------------------------------------- oracle, pinned
+def test_oracle_separation_on_the_reference_test_model():
+    """test_fem.rs:65-80 / :83-150: nodes (0,0,0), (30,0,0), truss E=1e6 A=2, u1x = 0, F2x = 100.
+    K has +-EA/L at rows/cols {0, 6}; every other DOF has a zero diagonal and is inactive."""
+    k = 1e6 * 2.0 / 30.0
+    rows, cols, vals = [0, 0, 6, 6], [0, 6, 0, 6], [k, -k, -k, k]
+    constrained = np.zeros(12, bool); constrained[0] = True
+    forces = np.zeros(12); forces[6] = 100.0
+    sep = O.separate_sparse(12, rows, cols, vals, constrained, [1, 2], forces, np.zeros(12))
+    assert sep["n_aa"] == 1 and sep["n_bb"] == 1          # assert!(sep.get_n_aa() > 0)
+    assert list(sep["k_aa_indexes"]) == [6] and list(sep["k_bb_indexes"]) == [0]
+    assert len(sep["k_aa"][0]) == 1                        # assert!(!sep.get_k_aa_triplets().is_empty())
+    assert sep["k_aa"][2][0] == k and sep["k_ab"][2][0] == -k and sep["k_ba"][2][0] == -k and sep["k_bb"][2][0] == k
+    # the reference's expected result: u2x = 0.0014999999 (its f32 chain), one Jacobi-PCG iteration on a
+    # 1x1 system; in f64 the same quotient is 0.0015 to within one f32 ulp (1.2e-10) of that literal
+    u = sep["b"][0] / sep["k_aa"][2][0]
+    assert abs(u - 0.0014999999) < 2e-10
+    # reaction R1x = K_ba u_a + K_bb u_b - F = -100 (find_r_r_sparse)
+    assert np.isclose(sep["k_ba"][2][0] * u, -100.0, rtol=1e-15)
+
+
+def test_oracle_separation_errors():
+    k = 5.0
+    with pytest.raises(O.SeparationError, match="No restraints"):
+        O.separate_sparse(12, [0, 6], [0, 6], [k, k], np.zeros(12, bool))
+    c = np.zeros(12, bool); c[1] = True
+    with pytest.raises(O.SeparationError, match="There are no stiffness to withstand displacement Y applied to node 7!"):
+        O.separate_sparse(12, [0, 6], [0, 6], [k, k], c, [7, 8])
+    c = np.zeros(12, bool); c[0] = c[6] = True
+    with pytest.raises(O.SeparationError, match="K_aa is empty"):
+        O.separate_sparse(12, [0, 6], [0, 6], [k, k], c)
+
+
+# ---------------------------------------------------------------------------- host logic (no GPU)
+def test_add_displacement_host_checks():
+    fem = FEM(1e-4, 1e-12, 2, device=-1)
+    fem.add_node(1, 0.0, 0.0, 0.0)
+    fem.add_node(2, 30.0, 0.0, 0.0)
+    fem.add_displacement(1, DOFParameter.X, 0.0)
+    with pytest.raises(FemError, match="Displacement X already applied to node 1!"):
+        fem.add_displacement(1, DOFParameter.X, 0.5)
+    with pytest.raises(FemError, match="Node with number 9 does not exist!"):
+        fem.add_displacement(9, DOFParameter.ThZ, 0.0)
+    with pytest.raises(FemError, match="Node with number 9 does not exist!"):
+        fem.add_concentrated_load(9, DOFParameter.X, 1.0)
+    # prefix semantics of the batched form: the first two are kept, the duplicate stops the batch
+    with pytest.raises(FemError, match="Displacement Y already applied to node 2!"):
+        fem.add_displacement([2, 2, 2, 1], [1, 2, 1, 3], [0.0, 0.0, 0.0, 0.0])
+    with pytest.raises(FemError, match="Displacement Z already applied to node 2!"):
+        fem.add_displacement(2, DOFParameter.Z, 0.0)
+    fem.add_displacement(1, DOFParameter.ThX, 0.0)         # was after the failing entry: not applied yet
+    with pytest.raises(FemError) as e:
+        fem.separate_stiffness_matrix_sparse_iterative()
+    assert "no CPU fallback" in str(e.value)
+    fem.reset(2)
+    fem.add_node(1, 0.0, 0.0, 0.0)
+    fem.add_displacement(1, DOFParameter.X, 0.0)           # reset dropped the constraints
+    fem.close()
+
+
+# ---------------------------------------------------------------------------- GPU parity
+def _oracle_for(mesh, fem, constrained, forces, disp):
+    n_dof = 6 * len(mesh["x"])
+    r, c, v = O.faithful_coo(mesh)
+    numbers = np.arange(1, len(mesh["x"]) + 1)
+    return O.separate_sparse(n_dof, r, c, v, constrained, numbers, forces, disp)
+
+
+def _check_against_oracle(mesh, fixed_nodes, fixed_dofs, loads, values=None):
+    n_dof = 6 * len(mesh["x"])
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], len(mesh["x"]), device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    values = np.zeros(len(fixed_nodes)) if values is None else np.asarray(values, float)
+    fem.add_displacement(np.asarray(fixed_nodes) + 1, fixed_dofs, values)
+    constrained = np.zeros(n_dof, bool); disp = np.zeros(n_dof); forces = np.zeros(n_dof)
+    constrained[6 * np.asarray(fixed_nodes) + np.asarray(fixed_dofs)] = True
+    disp[6 * np.asarray(fixed_nodes) + np.asarray(fixed_dofs)] = values
+    for node, dof, val in loads:
+        fem.add_concentrated_load(node + 1, dof, val)
+        forces[6 * node + dof] += val
+    sep = fem.separate_stiffness_matrix_sparse_iterative()
+    ref = _oracle_for(mesh, fem, constrained, forces, disp)
+    assert np.array_equal(sep.k_aa_indexes, ref["k_aa_indexes"]) and np.array_equal(sep.k_bb_indexes, ref["k_bb_indexes"])
+    # K itself carries the assembly's rounding (1e-12 bar of test_parity_gpu); the separation must route
+    # every entry to the oracle's (quadrant, i, j). Compare positions exactly and values with that bar.
+    _, _, gv = fem.csr()
+    scale = np.abs(gv).max()
+    for name, quad in (("k_aa", sep.k_aa), ("k_ab", sep.k_ab), ("k_ba", sep.k_ba), ("k_bb", sep.k_bb)):
+        i, j, x = sep.triplets(quad)
+        ri, rj, rx = ref[name]
+        # the GPU assembly may keep entries that are exactly cancelled on one side only: compare on the union
+        key = lambda a, b: a * (max(sep.n_aa, sep.n_bb) + 1) + b
+        g = dict(zip(key(i, j).tolist(), x.tolist())); o = dict(zip(key(ri, rj).tolist(), rx.tolist()))
+        for k_ in set(g) | set(o):
+            assert abs(g.get(k_, 0.0) - o.get(k_, 0.0)) <= 1e-12 * scale, (name, k_)
+        assert len(set(g) ^ set(o)) <= 0.001 * max(1, len(o)), (name, len(g), len(o))
+        assert np.all(np.diff(quad[0]) >= 0) and quad[0][0] == 0 and quad[0][-1] == len(quad[1])
+    assert np.allclose(sep.b, ref["b"], rtol=1e-12, atol=1e-12 * max(1.0, np.abs(ref["b"]).max()))
+    fem.close()
+    return sep
+
+
+@pytest.mark.gpu
+def test_gpu_separation_reference_truss_model():
+    mesh = meshes.reference_truss_model()
+    fem = FEM(1e-4, 1e-12, 2, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    fem.add_displacement(1, DOFParameter.X, 0.0)
+    fem.add_concentrated_load(2, DOFParameter.X, 100.0)
+    sep = fem.separate_stiffness_matrix_sparse_iterative()
+    k = 1e6 * 2.0 / 30.0
+    assert sep.n_aa == 1 and sep.n_bb == 1 and list(sep.k_aa_indexes) == [6] and list(sep.k_bb_indexes) == [0]
+    assert sep.k_aa[2][0] == k and sep.k_ab[2][0] == -k and sep.k_ba[2][0] == -k and sep.k_bb[2][0] == k
+    assert abs(sep.b[0] / sep.k_aa[2][0] - 0.0014999999) < 2e-10
+    fem.close()
+
+
+@pytest.mark.gpu
+def test_gpu_separation_matches_oracle_truss_cube():
+    mesh = meshes.truss_cube(3)
+    # pin node 0 fully (translations), node 2 in y/z, node 6 in z; prescribed non-zero settlement on one DOF
+    _check_against_oracle(mesh, [0, 0, 0, 2, 2, 6], [0, 1, 2, 1, 2, 2], [(26, 0, 1e3), (13, 2, -5e2), (26, 0, 2.5e2)],
+                          values=[0, 0, 0, 0, 1e-3, 0])
+
+
+@pytest.mark.gpu
+def test_gpu_separation_matches_oracle_mixed():
+    mesh = meshes.mixed_structure(12, 9)
+    w = 13
+    fixed = [(n, d) for n in range(w) for d in range(6)]              # clamp the first grid line
+    fixed += [(w * 9 + 3, 2), (w * 9 + 7, 4)]
+    loads = [(w * 5 + 6, 2, -1e4), (w * 9 + 12, 0, 3e3)]
+    sep = _check_against_oracle(mesh, [f[0] for f in fixed], [f[1] for f in fixed], loads,
+                                values=[0.0] * (len(fixed) - 2) + [2e-3, -1e-3])
+    assert sep.n_aa + sep.n_bb == 6 * len(mesh["x"])                 # plates + beams activate all 6 DOFs
+
+
+@pytest.mark.gpu
+def test_gpu_separation_errors_follow_the_reference():
+    mesh = meshes.reference_truss_model()
+    fem = FEM(1e-4, 1e-12, 2, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    with pytest.raises(FemError, match="No restraints"):
+        fem.separate_stiffness_matrix_sparse_iterative()
+    fem.add_displacement(2, DOFParameter.Y, 0.0)                      # a truss along x has no stiffness in y
+    with pytest.raises(FemError, match="There are no stiffness to withstand displacement Y applied to node 2!"):
+        fem.separate_stiffness_matrix_sparse_iterative()
+    fem.close()
+    fem = FEM(1e-4, 1e-12, 2, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    fem.add_displacement([1, 2], [0, 0], [0.0, 0.0])
+    with pytest.raises(FemError, match="K_aa is empty"):
+        fem.separate_stiffness_matrix_sparse_iterative()
+    fem.close()
+
+
+@pytest.mark.gpu
+def test_gpu_separation_fullsize_properties():
+    """Config P (4M plates): size-independent properties — every non-zero of K lands in exactly one
+    quadrant (checksum of checksums), the quadrants' shapes add up, K_ab = K_ba^T in count."""
+    mesh = meshes.plate_grid(600, 400, "flat")
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], len(mesh["x"]), device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    w = 601
+    nodes = np.repeat(np.arange(w), 6); dofs = np.tile(np.arange(6), w)
+    fem.add_displacement(nodes + 1, dofs, np.zeros(len(nodes)))
+    sep = fem.separate_stiffness_matrix_sparse_iterative()
+    rp, ci, v = fem.csr()
+    assert sep.n_aa + sep.n_bb == 6 * len(mesh["x"]) and sep.n_bb == 6 * w
+    nnz = [len(q[2]) for q in (sep.k_aa, sep.k_ab, sep.k_ba, sep.k_bb)]
+    assert sum(nnz) == int(np.count_nonzero(v)) and nnz[1] == nnz[2]
+    total = sum(float(np.sum(q[2])) for q in (sep.k_aa, sep.k_ab, sep.k_ba, sep.k_bb))
+    assert abs(total - float(np.sum(v))) <= 1e-9 * float(np.sum(np.abs(v)))
+    assert np.array_equal(np.sort(np.concatenate([sep.k_aa_indexes, sep.k_bb_indexes])), np.arange(6 * len(mesh["x"])))
+    fem.close()
