@@ -26,6 +26,25 @@ extern "C" {
     fn femgpu_assemble(h: *mut FemGpu, n_rows: *mut i64, nnz: *mut i64) -> i32;
     fn femgpu_get_csr(h: *mut FemGpu, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_rotation_elements(h: *mut FemGpu, family: i32, number: u32, out: *mut f64) -> i32;
+    fn femgpu_add_displacement(h: *mut FemGpu, n: usize, node: *const u32, dof: *const i32, value: *const f64) -> i32;
+    fn femgpu_add_concentrated_load(h: *mut FemGpu, n: usize, node: *const u32, dof: *const i32, value: *const f64) -> i32;
+    fn femgpu_separate_sparse(h: *mut FemGpu, n_aa: *mut i64, n_bb: *mut i64, nnz: *mut i64) -> i32;
+    fn femgpu_get_separated_indexes(h: *mut FemGpu, k_aa_indexes: *mut i64, k_bb_indexes: *mut i64) -> i32;
+    fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
+    fn femgpu_separated_rhs(h: *mut FemGpu, b: *mut f64, b_device: *mut *const f64) -> i32;
+}
+
+/// methods_for_bc_data_handle.rs:6-13
+#[derive(Debug, Clone, Copy, PartialEq, Eq, PartialOrd, Ord)]
+pub enum DOFParameter { X = 0, Y = 1, Z = 2, ThX = 3, ThY = 4, ThZ = 5 }
+
+/// structs/separated_stiffness_matrix_sparse.rs, with each quadrant as CSR in local indices
+/// (row_ptr, col_idx, values) instead of an unordered triplet list, plus b = R_a - K_ab u_b.
+pub struct SeparatedStiffnessMatrixSparse {
+    pub k_aa_indexes: Vec<i64>,
+    pub k_bb_indexes: Vec<i64>,
+    pub quadrants: [(Vec<i64>, Vec<i32>, Vec<f64>); 4], // aa, ab, ba, bb
+    pub b: Vec<f64>,
 }
 
 pub struct FEM { h: *mut FemGpu }
@@ -98,6 +117,37 @@ impl FEM {
         let mut v = vec![0f64; nnz as usize];
         self.check(unsafe { femgpu_get_csr(self.h, rp.as_mut_ptr(), ci.as_mut_ptr(), v.as_mut_ptr()) })?;
         Ok((rp, ci, v))
+    }
+}
+
+impl FEM {
+    /// methods_for_bc_data_handle.rs:175
+    pub fn add_displacement(&mut self, node_number: u32, dof_parameter: DOFParameter, value: f64) -> Result<(), String> {
+        let dof = dof_parameter as i32;
+        self.check(unsafe { femgpu_add_displacement(self.h, 1, &node_number, &dof, &value) })
+    }
+    /// methods_for_bc_data_handle.rs:31
+    pub fn add_concentrated_load(&mut self, node_number: u32, dof_parameter: DOFParameter, value: f64) -> Result<(), String> {
+        let dof = dof_parameter as i32;
+        self.check(unsafe { femgpu_add_concentrated_load(self.h, 1, &node_number, &dof, &value) })
+    }
+    /// methods_for_separate_stiffness_matrix.rs:217 — runs on the device on the assembled CSR values
+    pub fn separate_stiffness_matrix_sparse_iterative(&mut self) -> Result<SeparatedStiffnessMatrixSparse, String> {
+        let (mut n_aa, mut n_bb, mut nnz) = (0i64, 0i64, [0i64; 4]);
+        self.check(unsafe { femgpu_separate_sparse(self.h, &mut n_aa, &mut n_bb, nnz.as_mut_ptr()) })?;
+        let mut ia = vec![0i64; n_aa as usize];
+        let mut ib = vec![0i64; n_bb as usize];
+        self.check(unsafe { femgpu_get_separated_indexes(self.h, ia.as_mut_ptr(), ib.as_mut_ptr()) })?;
+        let mut quadrants: [(Vec<i64>, Vec<i32>, Vec<f64>); 4] = Default::default();
+        for q in 0..4 {
+            let rows = if q < 2 { n_aa } else { n_bb } as usize;
+            let (mut rp, mut ci, mut v) = (vec![0i64; rows + 1], vec![0i32; nnz[q] as usize], vec![0f64; nnz[q] as usize]);
+            self.check(unsafe { femgpu_get_separated_csr(self.h, q as i32, rp.as_mut_ptr(), ci.as_mut_ptr(), v.as_mut_ptr()) })?;
+            quadrants[q] = (rp, ci, v);
+        }
+        let mut b = vec![0f64; n_aa as usize];
+        self.check(unsafe { femgpu_separated_rhs(self.h, b.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok(SeparatedStiffnessMatrixSparse { k_aa_indexes: ia, k_bb_indexes: ib, quadrants, b })
     }
 }
 
