@@ -626,10 +626,10 @@ __device__ __forceinline__ void plate_block(const double* __restrict__ rec,
 // ------------------------------------------------------------------------------------------
 constexpr int kPlateSharedDoubles = 64;
 
-// One Gauss point (r, s) of a plate with edge vectors e12, e43, e14, e23: writes n[node] = adj(J) dh
-// (8 doubles) and 1/det, returns the two shear weights gamma_rz^2 det and gamma_sz^2 det.
+// One Gauss point (r, s) of a plate with edge vectors e12, e43, e14, e23: n[node] = adj(J) dh
+// (8 doubles) and 1/det into registers, returns the two shear weights gamma_rz^2 det and gamma_sz^2 det.
 __device__ __forceinline__ void plate_gauss_point(const double e[8], double r, double s,
-                                                  double* __restrict__ n_out, double* rdet_out,
+                                                  double n_out[8], double* rdet_out,
                                                   double* wr, double* ws) {
   // J = [[x_r, y_r], [x_s, y_s]]                 quadrilateral_4n_element_functions.rs:252-446
   const double x_r = 0.25 * (e[0] * (1.0 + s) + e[2] * (1.0 - s));
@@ -653,6 +653,13 @@ __device__ __forceinline__ void plate_gauss_point(const double e[8], double r, d
   *ws = (x_r * x_r + y_r * y_r) * q4;  // gamma_sz^2 * det
 }
 
+// 16-byte store of two consecutive record fields (S is 16-byte aligned, i even): the shared-memory
+// data pipe is the assembly kernel's busiest unit, and a 16-byte store costs the same wavefronts as
+// an 8-byte one
+__device__ __forceinline__ void store2(double* __restrict__ S, int i, double a, double b) {
+  *reinterpret_cast<double2*>(S + i) = make_double2(a, b);
+}
+
 // raw = the prep kernel's record: Q[9], x1, y1, x2, y2, x4, y4, identity flag, Cm, Cb, Cs, nu
 __device__ __forceinline__ void plate_shared_record(const double* __restrict__ raw,
                                                     double* __restrict__ S) {
@@ -661,13 +668,15 @@ __device__ __forceinline__ void plate_shared_record(const double* __restrict__ r
   const double g = 0.57735027779281512;  // sqrt((double)(1.0f / 3.0f)), plate.rs:1066-1091
   // edges 1-2 (s = +1), 4-3 (s = -1), 1-4 (r = +1), 2-3 (r = -1); x3 = y3 = 0
   const double e[8] = {x1 - x2, y1 - y2, x4, y4, x1 - x4, y1 - y4, x2, y2};
-  double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0};
+  double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0}, rd[4];
 #pragma unroll
   for (int ip = 0; ip < 4; ++ip) {
     const double r = (ip == 0 || ip == 3) ? g : -g;
     const double s = (ip < 2) ? g : -g;
-    double wr, ws;
-    plate_gauss_point(e, r, s, S + ip * 8, S + 32 + ip, &wr, &ws);
+    double wr, ws, n[8];
+    plate_gauss_point(e, r, s, n, &rd[ip], &wr, &ws);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) store2(S, ip * 8 + 2 * a, n[2 * a], n[2 * a + 1]);
     tr[0] += ((1.0 + s) * (1.0 + s)) * wr;
     tr[1] += ((1.0 - s) * (1.0 - s)) * wr;
     tr[2] += ((1.0 + s) * (1.0 - s)) * wr;
@@ -675,17 +684,18 @@ __device__ __forceinline__ void plate_shared_record(const double* __restrict__ r
     ts[1] += ((1.0 - r) * (1.0 - r)) * ws;
     ts[2] += ((1.0 + r) * (1.0 - r)) * ws;
   }
+  store2(S, 32, rd[0], rd[1]);
+  store2(S, 34, rd[2], rd[3]);
+  store2(S, 36, Cs * tr[0], Cs * tr[1]);
+  store2(S, 38, Cs * tr[2], Cs * ts[0]);
+  store2(S, 40, Cs * ts[1], Cs * ts[2]);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    S[36 + i] = Cs * tr[i];
-    S[39 + i] = Cs * ts[i];
-  }
+  for (int i = 0; i < 4; ++i) store2(S, 42 + 2 * i, 0.25 * e[2 * i], 0.25 * e[2 * i + 1]);
+  store2(S, 50, Cm, Cb);
+  store2(S, 52, nu, (1.0 - nu) * 0.5);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) S[42 + i] = 0.25 * e[i];
-  S[50] = Cm; S[51] = Cb; S[52] = nu; S[53] = (1.0 - nu) * 0.5;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) S[54 + i] = raw[i];
-  S[63] = raw[15];
+  for (int i = 0; i < 4; ++i) store2(S, 54 + 2 * i, raw[2 * i], raw[2 * i + 1]);
+  store2(S, 62, raw[8], raw[15]);
 }
 
 // The same record built by TWO adjacent lanes (half = lane & 1): each takes two Gauss points
@@ -698,14 +708,16 @@ __device__ __forceinline__ void plate_shared_record_half(const double* __restric
   const double g = 0.57735027779281512;
   const double e[8] = {x1 - x2, y1 - y2, x4, y4, x1 - x4, y1 - y4, x2, y2};
   const double s = half ? -g : g;
-  double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0};
+  double tr[3] = {0.0, 0.0, 0.0}, ts[3] = {0.0, 0.0, 0.0}, rd[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     // Gauss points 0:(+,+) 1:(-,+) | 2:(-,-) 3:(+,-)
     const int ip = 2 * half + q;
     const double r = ((q == 0) != (half != 0)) ? g : -g;
-    double wr, ws;
-    plate_gauss_point(e, r, s, S + ip * 8, S + 32 + ip, &wr, &ws);
+    double wr, ws, n[8];
+    plate_gauss_point(e, r, s, n, &rd[q], &wr, &ws);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) store2(S, ip * 8 + 2 * a, n[2 * a], n[2 * a + 1]);
     tr[0] += ((1.0 + s) * (1.0 + s)) * wr;
     tr[1] += ((1.0 - s) * (1.0 - s)) * wr;
     tr[2] += ((1.0 + s) * (1.0 - s)) * wr;
@@ -713,6 +725,7 @@ __device__ __forceinline__ void plate_shared_record_half(const double* __restric
     ts[1] += ((1.0 - r) * (1.0 - r)) * ws;
     ts[2] += ((1.0 + r) * (1.0 - r)) * ws;
   }
+  store2(S, 32 + 2 * half, rd[0], rd[1]);
   // half 0 finishes the gamma_rz sums, half 1 the gamma_sz sums (fixed order: half 0 + half 1)
   const double Cs = raw[18];
 #pragma unroll
@@ -724,12 +737,13 @@ __device__ __forceinline__ void plate_shared_record_half(const double* __restric
   }
   if (half == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) S[42 + i] = 0.25 * e[i];
-    S[50] = raw[16]; S[51] = raw[17]; S[52] = raw[19]; S[53] = (1.0 - raw[19]) * 0.5;
+    for (int i = 0; i < 4; ++i) store2(S, 42 + 2 * i, 0.25 * e[2 * i], 0.25 * e[2 * i + 1]);
+    store2(S, 50, raw[16], raw[17]);
+    store2(S, 52, raw[19], (1.0 - raw[19]) * 0.5);
   } else {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) S[54 + i] = raw[i];
-    S[63] = raw[15];
+    for (int i = 0; i < 4; ++i) store2(S, 54 + 2 * i, raw[2 * i], raw[2 * i + 1]);
+    store2(S, 62, raw[8], raw[15]);
   }
 }
 

@@ -170,9 +170,12 @@ __device__ __forceinline__ bool cta_all(bool pred) {
 // what a thread keeps in registers about a slab that is still to come
 template <int kT>
 struct SlabRegs {
-  static constexpr int kElistPerLane = kElistStride / kT;
+  // Two adjacent lanes share an element slot and copy alternate 16-byte chunks of its record, so
+  // both halves of every 32-byte sector land in shared memory in one wavefront (an LDGSTS costs one
+  // wavefront of the shared-memory data pipe per sector it touches).
+  static constexpr int kElistPerPair = kElistStride / (kT / 2);
   uint4 d0, d1, d2;             // the SlabDesc as three 16-byte words
-  uint32_t fe[kElistPerLane];   // the thread's slots of the slab's element list
+  uint32_t fe[kElistPerPair];   // the lane pair's slots of the slab's element list
   uint32_t c_begin, c_count;    // the thread's work item
   __device__ __forceinline__ int64_t val_base() const { return int64_t((uint64_t(d0.y) << 32) | d0.x); }
   __device__ __forceinline__ uint32_t val_count() const { return d0.z; }
@@ -204,7 +207,7 @@ struct SlabRegs {
       d2.z = d2.w = 0;
       c_count = 0;
 #pragma unroll
-      for (int j = 0; j < kElistPerLane; ++j) fe[j] = 0xFFFFFFFFu;
+      for (int j = 0; j < kElistPerPair; ++j) fe[j] = 0xFFFFFFFFu;
     }
   }
 };
@@ -228,14 +231,13 @@ __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_
 template <int kT>
 __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uint32_t tid) {
   SlabRegs<kT> R;
-  constexpr int kElistPerLane = kElistStride / kT;
   const uint4* sp = reinterpret_cast<const uint4*>(dbuf);
   R.d0 = sp[0];
   R.d1 = sp[1];
   R.d2 = sp[2];
 #pragma unroll
-  for (int j = 0; j < kElistPerLane; ++j)
-    R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>())[j * kT + tid];
+  for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j)
+    R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>())[j * (kT / 2) + (tid >> 1)];
   const uint2 w = reinterpret_cast<const uint2*>(dbuf + kDescItemsOff)[tid * 2u + 1u];
   R.c_begin = w.x;
   R.c_count = w.y;
@@ -244,8 +246,8 @@ __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uin
 }
 
 // cp.async everything slab R needs into `stage` (+ its raw plate records into `rawp`): block
-// metadata, contribution entries, and each thread the record of "its" element — every record is
-// fetched once per slab, all requests in flight together
+// metadata, contribution entries, and each lane pair the records of "its" elements — every record
+// is fetched once per slab, all requests in flight together
 template <int kT>
 __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>& R, uint32_t stage_s,
                                             uint32_t rawp_s, uint32_t mbar_s, uint32_t tid) {
@@ -267,30 +269,28 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
           "l"(A.contrib + (R.slab_c_begin() & ~3u)), "r"(ent_bytes), "r"(mbar_s)
           : "memory");
   }
-  const uint32_t nt = R.n_truss(), nbm = R.n_beam();
+  const uint32_t nt = R.n_truss(), nbm = R.n_beam(), half = tid & 1u;
 #pragma unroll
-  for (int j = 0; j < SlabRegs<kT>::kElistPerLane; ++j) {
+  for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
     const uint32_t fe = R.fe[j];
     if (fe == 0xFFFFFFFFu) continue;
-    const uint32_t slot = j * kT + tid, family = fe >> 26, e = fe & 0x03FFFFFFu;
+    const uint32_t slot = j * (kT / 2) + (tid >> 1), family = fe >> 26, e = fe & 0x03FFFFFFu;
     if (family == FEMGPU_PLATE) {
-      const uint32_t dst = rawp_s + (slot - nt - nbm) * 160u;
-      const double* rec = A.plate_rec + size_t(e) * 16;
-      const double* mat = A.plate_mat + size_t(e) * 4;
+      // chunks 0..7 = geometry record, 8..9 = material record; this lane takes every other one
+      const uint32_t dst = rawp_s + (slot - nt - nbm) * 160u + half * 16u;
+      const double* rec = A.plate_rec + size_t(e) * 16 + half * 2;
+      const double* mat = A.plate_mat + size_t(e) * 4 + half * 2;
 #pragma unroll
-      for (uint32_t ch = 0; ch < 8; ++ch) cp_async16(dst + ch * 16u, rec + ch * 2);
+      for (uint32_t ch = 0; ch < 4; ++ch) cp_async16(dst + ch * 32u, rec + ch * 4);
       cp_async16(dst + 128u, mat);
-      cp_async16(dst + 144u, mat + 2);
     } else if (family == FEMGPU_BEAM) {
-      const uint32_t dst = stage_s + R.beam_off() + (slot - nt) * uint32_t(kBeamSlotDoubles * 8);
-      const double* rec = A.beam_rec + size_t(e) * 16;
+      const uint32_t dst = stage_s + R.beam_off() + (slot - nt) * uint32_t(kBeamSlotDoubles * 8) + half * 16u;
+      const double* rec = A.beam_rec + size_t(e) * 16 + half * 2;
 #pragma unroll
-      for (uint32_t ch = 0; ch < 8; ++ch) cp_async16(dst + ch * 16u, rec + ch * 2);
+      for (uint32_t ch = 0; ch < 4; ++ch) cp_async16(dst + ch * 32u, rec + ch * 4);
     } else if (family == FEMGPU_TRUSS) {
-      const uint32_t dst = stage_s + R.truss_off() + slot * uint32_t(kTrussSlotDoubles * 8);
-      const double* rec = reinterpret_cast<const double*>(A.truss_rec + e);
-      cp_async16(dst, rec);
-      cp_async16(dst + 16u, rec + 2);
+      const uint32_t dst = stage_s + R.truss_off() + slot * uint32_t(kTrussSlotDoubles * 8) + half * 16u;
+      cp_async16(dst, reinterpret_cast<const double*>(A.truss_rec + e) + half * 2);
     }  // family 3: placeholder of a remote contribution, no record
   }
 }
@@ -541,7 +541,7 @@ __device__ __forceinline__ void add_contribution_raw(const double* __restrict__ 
                                                      double acc[36]) {
   const uint32_t family = code >> 30, pair = (code >> 26) & 15u;
   if (family == FEMGPU_PLATE) {
-    double S[kPlateSharedDoubles];
+    __align__(16) double S[kPlateSharedDoubles];
     plate_shared_record(raw, S);
     const PlatePair pt = make_plate_pair(int(pair >> 2), int(pair & 3u));
     plate_block_shared(S, pt, 1.0, raw[15] != 0.0, acc);
