@@ -227,7 +227,10 @@ struct SlabDesc {        // 48 bytes = three 16-byte loads
 constexpr uint32_t kEntEnd = 1u << 25, kEntRmw = 1u << 24;
 constexpr int kEntDeferShift = 22, kEntBlkShift = 11;
 constexpr uint32_t kEntBlkMask = 0x7FFu, kEntRecMask = 0x7FFu, kEntDeferMask = 3u;
-constexpr int kMaxChunks = 4;  // a block is split over at most this many lanes
+#ifndef FEMGPU_MAX_CHUNKS
+#define FEMGPU_MAX_CHUNKS 4
+#endif
+constexpr int kMaxChunks = FEMGPU_MAX_CHUNKS;  // a block is split over at most this many lanes
 
 struct DistState {
   bool enabled = false;
@@ -417,7 +420,16 @@ constexpr int kElistStride = 64;           // element slots per slab in the dens
                                            // touching more elements takes the unstaged path
 constexpr int kRecStride = 20;             // doubles per staged element record (plate: 16 + 4)
 // relative cost of one contribution, used to balance the per-thread work lists
-constexpr uint32_t kCostTruss = 1, kCostBeam = 8, kCostPlate = 16;
+#ifndef FEMGPU_COST_T
+#define FEMGPU_COST_T 1
+#endif
+#ifndef FEMGPU_COST_B
+#define FEMGPU_COST_B 8
+#endif
+#ifndef FEMGPU_COST_P
+#define FEMGPU_COST_P 16
+#endif
+constexpr uint32_t kCostTruss = FEMGPU_COST_T, kCostBeam = FEMGPU_COST_B, kCostPlate = FEMGPU_COST_P;
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return uint32_t((a + b - 1) / b); }
 
