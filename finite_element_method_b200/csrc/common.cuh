@@ -204,7 +204,7 @@ struct SlabDesc {        // 48 bytes = three 16-byte loads
   int64_t val_base;     // first CSR value of the slab
   uint32_t val_count;   // values in the slab
   uint32_t flags;       // bit 0: too large for the staged kernel -> assemble_unstaged_kernel;
-                        // bits 8..9: deferred rounds of the slab (max chunk index of a split block);
+                        // bits 8..9: merge rounds of the slab (max chunk index of a split block);
                         // bits 16..31: plates in the element list (staged slabs)
   uint32_t blk_begin;   // first block (thread order)
   uint32_t blk_count;
@@ -219,9 +219,11 @@ struct SlabDesc {        // 48 bytes = three 16-byte loads
 // Contribution entry of a staged slab (32 bits), in the owning lane's execution order: family-major
 // (placeholders, plates, beams, trusses) over the lane's blocks, insertion order inside a group.
 //   31..30 family   29..26 local node pair   25 group end: flush the accumulator into the block
-//   24 the block already holds an earlier group's sum (read-modify-write)
-//   23..22 deferred round: the block is split over several lanes; chunk j >= 1 is added to the image
-//          after the j-th CTA barrier that follows the evaluation (chunk 0 stores immediately)
+//   24 the block already holds an earlier group's sum (read-modify-write); on a chunk of a split
+//      block: this lane is a sender
+//   23..22 merge round: the block is split over several adjacent lanes of one warp. Chunk j >= 1 (bit 24
+//          set) hands its partial sum to the lane of chunk 0 in round j (warp shuffle); chunk 0 (bit 24
+//          clear) carries the number of rounds it receives and stores the block after the last one
 //   21..11 block index inside the slab   10..0 record offset inside the family's record area (16 B units)
 // Unstaged slabs keep family<<30 | pair<<26 | slot in the slab's element list, block-major.
 constexpr uint32_t kEntEnd = 1u << 25, kEntRmw = 1u << 24;
@@ -299,6 +301,7 @@ struct Handle {
   uint32_t n_unstaged = 0;         // slabs handled by assemble_unstaged_kernel
   int sm_count = 0;
   int asm_threads = 32;            // 32 or 64, fixed by the symbolic pass
+  bool asm_split = false;          // some slab splits a block over several lanes (kernel variant with merge rounds)
   uint32_t asm_smem_set = 0;       // dynamic shared memory assemble_kernel is currently configured for
   int asm_ctas_per_sm = 0;         // persistent CTAs per SM at that size (occupancy query)
   DevBuf<uint32_t> node_blk_ptr;   // [n_nodes_total+1]

@@ -344,9 +344,11 @@ __device__ __forceinline__ bool phase_a(const SlabRegs<kT>& R, const double* __r
 // phase B: the thread runs its contribution entries. The loop is flat over contributions — a group
 // end is a flush of the accumulators into the image, after which `keep` = 0 makes the next
 // contribution overwrite them (no zeroing) — so threads with one long group and threads with
-// several short ones stay converged on the expensive part. A chunk of a split block (deferred
-// round j >= 1) keeps its sum in registers and adds it to the image after the j-th barrier.
-template <int kT>
+// several short ones stay converged on the expensive part. The chunks of a split block keep their
+// sums in registers and are merged with warp shuffles after the loop.
+// kSplit = false: the model has no split block anywhere (decided by the symbolic pass), the merge-round
+// code is compiled out.
+template <int kT, bool kSplit>
 __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned char* __restrict__ stage,
                                         const double* __restrict__ form, double* __restrict__ img,
                                         const PlatePair* __restrict__ pairs, bool all_flat
@@ -364,7 +366,8 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
 #pragma unroll
   for (int q = 0; q < 36; ++q) acc[q] = 0.0;
   double keep = 0.0;
-  uint32_t pending = 0;  // deferred round of the thread's last group
+  uint32_t pending = 0;  // merge rounds of the thread's last group (a chunk of a split block)
+  bool sender = false;
   uint4 pending_m = make_uint4(0u, 0u, 0u, 0u);
   if (i < end) {
     uint32_t code = ent[i];
@@ -392,8 +395,9 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
       keep = 1.0;
       if (code & kEntEnd) {
         const uint32_t defer = (code >> kEntDeferShift) & kEntDeferMask;
-        if (defer) {  // always the thread's last entry
+        if (kSplit && defer) {  // a chunk of a split block: always the thread's last entry
           pending = defer;
+          sender = (code & kEntRmw) != 0;
           pending_m = m;
         } else if (code & kEntRmw) {
           store_block<true>(img, m, acc, true);
@@ -411,14 +415,25 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
   ph_work += __reduce_add_sync(0xFFFFFFFFu, R.c_count);
 #endif
   PHASE_MARK(5)
-  const uint32_t rounds = R.rounds();
-  for (uint32_t r = 1; r <= rounds; ++r) {
-    cta_sync<kT>();
-    if (pending == r) store_block<true>(img, pending_m, acc, true);
+  // Merge rounds: the lane of chunk 0 collects the partial sums of the block's other chunks from the
+  // lanes right above it, in chunk order (so the sum is (chunk 0 + chunk 1) + chunk 2 ...), and stores
+  // the block once. No barrier and no read-modify-write through the image.
+  const uint32_t rounds = kSplit ? R.rounds() : 0u;  // CTA-uniform
+  if (kSplit && rounds) {
+    const uint32_t recv = sender ? 0u : pending;
+    for (uint32_t r = 1; r <= rounds; ++r) {
+      if (!__any_sync(0xFFFFFFFFu, recv >= r)) continue;  // warp-uniform
+#pragma unroll
+      for (int q = 0; q < 36; ++q) {
+        const double t = __shfl_down_sync(0xFFFFFFFFu, acc[q], r);
+        if (recv >= r) acc[q] += t;
+      }
+    }
+    if (recv) store_block<false>(img, pending_m, acc, true);
   }
 }
 
-template <int kT>
+template <int kT, bool kSplit>
 __global__ void __maxnreg__(kT == 64 ? 200 : 255)
 assemble_kernel(const AsmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -476,10 +491,10 @@ assemble_kernel(const AsmArgs A) {
     }
     PHASE_MARK(4)
 #ifdef FEMGPU_PHASE_CLOCKS
-    phase_b<kT>(cur, stage, form, img, pairs, all_flat, ph_acc, ph_last, ph_iters, ph_work);
+    phase_b<kT, kSplit>(cur, stage, form, img, pairs, all_flat, ph_acc, ph_last, ph_iters, ph_work);
     ++ph_slabs;
 #else
-    phase_b<kT>(cur, stage, form, img, pairs, all_flat);
+    phase_b<kT, kSplit>(cur, stage, form, img, pairs, all_flat);
 #endif
     PHASE_MARK(6)
 
@@ -643,9 +658,12 @@ int32_t run_assembly(Handle* h) {
   const uint32_t smem = A.smem_img + A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * desc + 16 +
                         16 * uint32_t(sizeof(PlatePair));
   if (h->n_unstaged < h->n_slabs) {
-    const void* fn = threads == 64 ? reinterpret_cast<const void*>(assemble_kernel<64>)
-                                   : reinterpret_cast<const void*>(assemble_kernel<32>);
-    const uint32_t config = smem | (uint32_t(threads) << 24);
+    const bool split = h->asm_split;
+    const void* fn = threads == 64 ? (split ? reinterpret_cast<const void*>(assemble_kernel<64, true>)
+                                            : reinterpret_cast<const void*>(assemble_kernel<64, false>))
+                                   : (split ? reinterpret_cast<const void*>(assemble_kernel<32, true>)
+                                            : reinterpret_cast<const void*>(assemble_kernel<32, false>));
+    const uint32_t config = smem | (uint32_t(threads) << 24) | (split ? 1u << 31 : 0u);
     if (h->asm_smem_set != config) {
       FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       int per_sm = 0;
@@ -657,8 +675,13 @@ int32_t run_assembly(Handle* h) {
       h->asm_ctas_per_sm = per_sm;
     }
     const uint32_t grid = uint32_t(std::min<uint64_t>(h->n_slabs, uint64_t(h->sm_count) * h->asm_ctas_per_sm));
-    if (threads == 64) assemble_kernel<64><<<grid, 64, smem, h->stream>>>(A);
-    else assemble_kernel<32><<<grid, 32, smem, h->stream>>>(A);
+    if (threads == 64) {
+      if (split) assemble_kernel<64, true><<<grid, 64, smem, h->stream>>>(A);
+      else assemble_kernel<64, false><<<grid, 64, smem, h->stream>>>(A);
+    } else {
+      if (split) assemble_kernel<32, true><<<grid, 32, smem, h->stream>>>(A);
+      else assemble_kernel<32, false><<<grid, 32, smem, h->stream>>>(A);
+    }
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
 #ifdef FEMGPU_PHASE_CLOCKS
@@ -670,7 +693,7 @@ int32_t run_assembly(Handle* h) {
       FEMGPU_CUDA_CHECK(h, cudaMemcpyToSymbol(g_phase, zero, sizeof zero));
       const double ws = double(ph[kPhases + 2]);  // warp-slabs
       static const char* names[kPhases] = {"loop top", "wait stage (mbarrier)", "wait image free", "phase A", "issue next stage",
-                                           "phase B loop", "deferred rounds", "store issue", "tail", "-", "-", "-"};
+                                           "phase B loop", "merge rounds", "store issue", "tail", "-", "-", "-"};
       fprintf(stderr, "[femgpu phases] T=%d grid=%u warps=%llu slabs/warp=%.1f\n", threads, grid, ph[kPhases + 3],
               ws / double(ph[kPhases + 3]));
       double tot = 0;

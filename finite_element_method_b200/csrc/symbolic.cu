@@ -235,9 +235,10 @@ __global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restri
 // descending cost) so that every thread of the CTA gets about the same cost W. A block heavier
 // than W (the diagonal block of a plate-grid node: 4 plate contributions, twice the per-thread
 // share) is split into up to kMaxChunks chunks of consecutive contributions (execution order), one
-// thread each: chunk 0 stores its partial sum, chunk j >= 1 adds its own after the j-th barrier
-// ("deferred round"). W starts at total / threads and is raised until the slab fits.
-// Only blocks at least 25 % heavier than W are split (a split costs a deferred read-modify-write).
+// thread each, in adjacent lanes of one warp: after the contribution loop the lane of chunk 0 collects the
+// partial sums of chunks 1, 2, .. with warp shuffles, in that order ("merge round" j), and stores the
+// block. W starts at total / threads and is raised until the slab fits.
+// Only blocks at least 25 % heavier than W are split (a split costs a merge round: 72 shuffles).
 // One thread per slab; items are written to the dense [slab][thread] table.
 __device__ __forceinline__ uint32_t family_cost(uint32_t f) {
   return (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
@@ -256,7 +257,8 @@ __device__ __forceinline__ uint32_t chunk_cum_cost(const uint32_t n[4], uint32_t
 
 __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* __restrict__ slabs,
                                  const uint32_t* __restrict__ cost, const uint32_t* __restrict__ cptr_ord,
-                                 const uint32_t* __restrict__ contrib, WorkItem* __restrict__ items) {
+                                 const uint32_t* __restrict__ contrib, WorkItem* __restrict__ items,
+                                 int32_t* __restrict__ flags) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_slabs) return;
   const SlabDesc d = slabs[k];
@@ -279,6 +281,7 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
       if (staged && 4 * uint64_t(c) > 5 * W && cnt > 1) {
         const uint64_t kk = min(uint64_t(cnt), (c + W - 1) / W);
         if (kk > uint64_t(kMaxChunks)) ok = false;
+        if ((n & 31u) + uint32_t(kk) > 32u) n = (n + 31u) & ~31u;  // chunks of a block stay inside one warp
         n += uint32_t(kk);
         open = false;
       } else {
@@ -314,6 +317,9 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
     if (staged && 4 * uint64_t(c) > 5 * W && cnt > 1) {
       close_run(b);
       const uint32_t kk = uint32_t(min(uint64_t(cnt), (c + W - 1) / W));
+      // the chunks are merged with warp shuffles (lane of chunk 0 <- lane + j): keep them in one warp
+      if ((n & 31u) + kk > 32u)
+        while (n & 31u) out[n++] = WorkItem{0u, 0u, 0u, 0u};
       uint32_t nf[4] = {0, 0, 0, 0};  // placeholders, plates, beams, trusses
       for (uint32_t i = 0; i < cnt; ++i) {
         const uint32_t f = contrib[c0 + i] >> 30;
@@ -330,7 +336,7 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
         }
         WorkItem w;
         w.blk_begin = b;
-        w.blk_count = 1u | (j << 16) | (1u << 24);
+        w.blk_count = 1u | (j << 16) | ((kk - 1u) << 20) | (1u << 24);
         w.c_begin = c0 + s_prev;
         w.c_count = s_next - s_prev;
         out[n++] = w;
@@ -349,7 +355,10 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
   }
   close_run(b1);
   for (; n < threads; ++n) out[n] = WorkItem{0u, 0u, 0u, 0u};
-  if (max_round) slabs[k].flags = d.flags | (max_round << 8);
+  if (max_round) {
+    slabs[k].flags = d.flags | (max_round << 8);
+    atomicMax(flags + 13, 1);  // some staged slab splits a block: the kernel variant with merge rounds is needed
+  }
 }
 
 // ---- per-slab element lists -----------------------------------------------------------------
@@ -468,7 +477,7 @@ __global__ void relabel_kernel(uint32_t n, const uint64_t* __restrict__ keys, co
 
 // Staged slabs: rewrite each lane's contributions from block-major order into the lane's execution
 // order — family-major (placeholders, plates, beams, trusses) over the lane's blocks, insertion order
-// inside a (block, family) group — and attach the group-end / read-modify-write / deferred-round
+// inside a (block, family) group — and attach the group-end / read-modify-write / merge-round
 // flags and the block index. One thread per work item; entries stay inside the item's own range.
 __global__ void item_program_kernel(uint32_t n_slabs, uint32_t threads, const SlabDesc* __restrict__ slabs,
                                     const WorkItem* __restrict__ items, const uint32_t* __restrict__ cptr_ord,
@@ -492,6 +501,7 @@ __global__ void item_program_kernel(uint32_t n_slabs, uint32_t threads, const Sl
     // between the families)
     const uint32_t p = w.blk_begin, c0 = cptr_ord[p], c1 = cptr_ord[p + 1];
     const uint32_t skip = w.c_begin - c0, take = w.c_count, round = (w.blk_count >> 16) & 3u;
+    const uint32_t more = (w.blk_count & (1u << 24)) ? (w.blk_count >> 20) & 3u : 0u;  // chunks after chunk 0
     const uint32_t blk = p - d.blk_begin;
     uint32_t pos = 0, left = take;
     for (int f = 0; f < 4; ++f)
@@ -500,7 +510,8 @@ __global__ void item_program_kernel(uint32_t n_slabs, uint32_t threads, const Sl
         if ((code >> 30) != order[f]) continue;
         if (pos >= skip && pos < skip + take) {
           uint32_t e = (code & 0xFC000000u) | (blk << kEntBlkShift) | (code & kEntRecMask);
-          if (--left == 0) e |= kEntEnd | (round << kEntDeferShift) | (round ? kEntRmw : 0u);
+          // chunk j >= 1: sender of merge round j; chunk 0: holds its flush and receives `more` rounds
+          if (--left == 0) e |= kEntEnd | ((round ? round : more) << kEntDeferShift) | (round ? kEntRmw : 0u);
           dst[out++] = e;
         }
         ++pos;
@@ -1074,7 +1085,7 @@ int32_t run_symbolic(Handle* h) {
   const uint32_t threads = uint32_t(h->asm_threads);
   SYM_CHECK(h->items.reserve(size_t(n_slabs) * threads));
   work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, threads, h->slabs.p, ocost.as<uint32_t>(),
-                                                         h->blk_cptr.p, h->contrib.p, h->items.p);
+                                                         h->blk_cptr.p, h->contrib.p, h->items.p, h->d_flag.p);
   h->launches++;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
@@ -1098,6 +1109,7 @@ int32_t run_symbolic(Handle* h) {
   h->smem_rawp = uint32_t(flags[10]);
   h->smem_stage = uint32_t(flags[11]);
   h->n_unstaged = uint32_t(flags[12]);
+  h->asm_split = flags[13] != 0;
 
   if (h->dist.enabled) {
     int32_t st = dist_finalize_plan(h, ranges);
