@@ -329,13 +329,31 @@ def main():
         nodes = np.repeat(np.arange(1, 65, dtype=np.uint32), ndof)
         fem.add_displacement(nodes, np.tile(np.arange(ndof, dtype=np.int32), 64), np.zeros(len(nodes)))
         fem.add_concentrated_load(n_nodes, 0, 1.0e3)
+        # §8f rank 2: a uniform load on every beam and every plate -> nodal loads, evaluated on the device
+        n_pl = np.asarray(local["p_n"]).reshape(4, -1).shape[1]
+        n_bm = len(local["b_n1"])
+        loads = None
+        if n_pl + n_bm:
+            if n_bm:
+                fem.add_uniformly_distributed_line_load(np.arange(1, n_bm + 1, dtype=np.uint32),
+                                                        np.full(n_bm, 2, np.int32), np.full(n_bm, -2.0e3))
+            if n_pl:
+                fem.add_uniformly_distributed_surface_load(np.arange(1, n_pl + 1, dtype=np.uint32),
+                                                           np.full(n_pl, 2, np.int32), np.full(n_pl, -1.0e3))
+            fem.synchronize()
+            t0 = time.perf_counter()
+            fem.forces_vector(copy_out=False)
+            fem.synchronize()
+            loads = {"op": "uniformly distributed line/surface loads -> forces vector, on the device (upload of the load "
+                           "list, nodal loads, stable sort by DOF, in-order sums)", "n_loads": int(n_pl + n_bm),
+                     "ms_wall": (time.perf_counter() - t0) * 1e3}
         fem.separate_stiffness_matrix_sparse_iterative(copy_out=False)          # warm-up (allocations)
         n_aa, n_bb, q_nnz, sep_ms = fem.separate_stiffness_matrix_sparse_iterative(copy_out=False)
         sep_bytes = 12 * nnz_local + 12 * sum(q_nnz)      # col_idx + values read once, compacted copies written once
         separation = {"op": "separate_stiffness_matrix_sparse_iterative + b = R_a - K_ab u_b, on the device",
                       "ms": sep_ms, "n_aa": n_aa, "n_bb": n_bb, "nnz_aa_ab_ba_bb": q_nnz,
                       "algorithmic_bytes": sep_bytes, "achieved_GBps": sep_bytes / (sep_ms * 1e-3) / 1e9,
-                      "frac_of_hbm_peak": sep_bytes / (sep_ms * 1e-3) / 1e9 / peak}
+                      "frac_of_hbm_peak": sep_bytes / (sep_ms * 1e-3) / 1e9 / peak, "distributed_loads": loads}
 
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.config)

@@ -44,6 +44,9 @@ SIGNATURES = {
     "femgpu_element_slots": (C.c_int32, [H, C.c_int32, C.c_uint32, i64p]),
     "femgpu_add_displacement": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
     "femgpu_add_concentrated_load": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
+    "femgpu_add_line_load": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
+    "femgpu_add_surface_load": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
+    "femgpu_get_forces": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_separate_sparse": (C.c_int32, [H, i64p, i64p, i64p]),
     "femgpu_get_separated_indexes": (C.c_int32, [H, i64p, i64p]),
     "femgpu_get_separated_csr": (C.c_int32, [H, C.c_int32, i64p, i32p, dp]),

@@ -323,7 +323,13 @@ struct Handle {
   // ---- boundary conditions and the separated matrix (separate.cu) ----
   struct BoundaryConditions {
     std::vector<uint8_t> constrained;         // imposed_constraints, [6 * nodes_number] (fem.rs:24,45)
-    std::vector<double> displacement, force;  // displacements_vector / forces_vector (fem.rs:18-19)
+    std::vector<double> displacement, force;  // displacements_vector / forces_vector (fem.rs:18-19);
+                                              // `force` holds the concentrated loads only
+    // uniformly distributed line / surface loads in call order (family, element index, dof, value): their
+    // nodal equivalents are evaluated on the device and added to the forces vector at the next flush
+    std::vector<int32_t> load_family, load_dof;
+    std::vector<uint32_t> load_elem;
+    std::vector<double> load_value;
     bool uploaded = false;
   } bc;
   struct Separated {
@@ -393,6 +399,9 @@ int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);  
 int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
 int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host);   // symbolic.cu
 int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals);  // symbolic.cu
+int32_t run_load_kernel(Handle* h, uint32_t n, const int32_t* d_family, const uint32_t* d_elem, const int32_t* d_dof,
+                        const double* d_value, uint32_t* d_key, double* d_val);  // prep.cu
+int32_t forces_flush(Handle* h);                         // separate.cu: bc -> sep.d_constrained / d_disp / d_force
 int32_t run_separate(Handle* h);                         // separate.cu
 void sep_release(Handle* h);                             // separate.cu
 void bc_clear(Handle* h);                                // separate.cu

@@ -106,6 +106,76 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
   if (kWriteErr) err[e] = code;
 }
 
+// Uniformly distributed loads -> nodal loads, one thread per load:
+//   Beam::convert_uniformly_distributed_line_load_to_nodal_loads    structs/beam.rs:775-797
+//       over the beam's integration points [(r = 0, alpha = 2)] (:729): f_a = (h_a(r) q)(det J alpha)
+//   Plate::convert_uniformly_distributed_surface_load_to_nodal_loads structs/plate.rs:1145-1185
+//       over the four Gauss points of :1066-1091: f_a += (h_a(r, s) q)(det J(r, s) alpha_r alpha_s)
+// Each load writes four (global DOF index, value) contributions (a beam's last two are padding with
+// the key 0xFFFFFFFF); the caller sorts them by key and sums every run in insertion order.
+__global__ void __launch_bounds__(kPrepThreads)
+load_kernel(uint32_t n, const int32_t* __restrict__ family, const uint32_t* __restrict__ elem,
+            const int32_t* __restrict__ dof, const double* __restrict__ value,
+            const uint32_t* __restrict__ b1, const uint32_t* __restrict__ b2,
+            const uint32_t* __restrict__ q1, const uint32_t* __restrict__ q2,
+            const uint32_t* __restrict__ q3, const uint32_t* __restrict__ q4,
+            const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+            double abs_tol, uint32_t* __restrict__ key, double* __restrict__ val) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t e = elem[k];
+  const double q = value[k];
+  uint32_t node[4] = {0u, 0u, 0u, 0u};
+  double f[4] = {0.0, 0.0, 0.0, 0.0};
+  int nn;
+  if (family[k] == FEMGPU_BEAM) {
+    nn = 2;
+    node[0] = b1[e];
+    node[1] = b2[e];
+    double p1[3], p2[3];
+    load_xyz(x, y, z, node[0], p1);
+    load_xyz(x, y, z, node[1], p2);
+    const double v[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+    const double det = bar_jacobian(norm3(v)), r = 0.0, alpha = 2.0;
+    f[0] = 0.0 + ((0.5 * (1.0 - r)) * q) * (det * alpha);
+    f[1] = 0.0 + ((0.5 * (1.0 + r)) * q) * (det * alpha);
+  } else {
+    nn = 4;
+    node[0] = q1[e];
+    node[1] = q2[e];
+    node[2] = q3[e];
+    node[3] = q4[e];
+    double p1[3], p2[3], p3[3], p4[3], rec[16], mat[4];
+    load_xyz(x, y, z, node[0], p1);
+    load_xyz(x, y, z, node[1], p2);
+    load_xyz(x, y, z, node[2], p3);
+    load_xyz(x, y, z, node[3], p4);
+    plate_record<false>(p1, p2, p3, p4, 1.0, 0.5, 1.0, 1.0, abs_tol, rec, mat);
+    const double x1 = rec[9], y1 = rec[10], x2 = rec[11], y2 = rec[12], x4 = rec[13], y4 = rec[14];
+    const double g = 0.57735027779281512;  // sqrt((double)(1.0f / 3.0f)), plate.rs:1066-1091
+#pragma unroll
+    for (int ip = 0; ip < 4; ++ip) {
+      const double r = (ip == 0 || ip == 3) ? g : -g;
+      const double s = (ip < 2) ? g : -g;
+      // J of quadrilateral_4n_element_functions.rs:252-446 with node 3 at the local origin
+      const double x_r = 0.25 * ((x1 - x2) * (1.0 + s) + x4 * (1.0 - s));
+      const double y_r = 0.25 * ((y1 - y2) * (1.0 + s) + y4 * (1.0 - s));
+      const double x_s = 0.25 * ((x1 - x4) * (1.0 + r) + x2 * (1.0 - r));
+      const double y_s = 0.25 * ((y1 - y4) * (1.0 + r) + y2 * (1.0 - r));
+      const double scale = (x_r * y_s - y_r * x_s) * 1.0 * 1.0;
+      const double h[4] = {0.25 * (1.0 + r) * (1.0 + s), 0.25 * (1.0 - r) * (1.0 + s),
+                           0.25 * (1.0 - r) * (1.0 - s), 0.25 * (1.0 + r) * (1.0 - s)};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) f[a] = f[a] + (h[a] * q) * scale;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    key[4 * size_t(k) + a] = a < nn ? 6u * node[a] + uint32_t(dof[k]) : 0xFFFFFFFFu;
+    val[4 * size_t(k) + a] = f[a];
+  }
+}
+
 // smallest insertion position (cbase) among failing elements; family in the low 2 bits
 __global__ void first_error_kernel(uint32_t from, uint32_t n, int family,
                                    const int32_t* __restrict__ err,
@@ -199,6 +269,20 @@ int32_t run_prep(Handle* h, bool validate_only) {
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   }
+  return 0;
+}
+
+int32_t run_load_kernel(Handle* h, uint32_t n, const int32_t* d_family, const uint32_t* d_elem,
+                        const int32_t* d_dof, const double* d_value, uint32_t* d_key, double* d_val) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  if (n == 0) return 0;
+  const FamilyDev& fb = h->fd[FEMGPU_BEAM];
+  const FamilyDev& fp = h->fd[FEMGPU_PLATE];
+  load_kernel<<<div_up(n, kPrepThreads), kPrepThreads, 0, h->stream>>>(
+      n, d_family, d_elem, d_dof, d_value, fb.conn[0].p, fb.conn[1].p, fp.conn[0].p, fp.conn[1].p, fp.conn[2].p,
+      fp.conn[3].p, h->d_x.p, h->d_y.p, h->d_z.p, h->abs_tol, d_key, d_val);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   return 0;
 }
 

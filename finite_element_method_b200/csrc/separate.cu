@@ -19,6 +19,8 @@
 // Bound: HBM — col_idx and values are read twice, the compacted copies written once.
 #include <cub/cub.cuh>
 
+#include <functional>
+
 #include "common.cuh"
 
 namespace femgpu {
@@ -247,6 +249,25 @@ __global__ void rhs_kernel(int64_t n_aa, const int64_t* __restrict__ aa_idx, con
   b[i] = acc;
 }
 
+__global__ void iota_kernel(uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+// contributions sorted by global DOF index (stable: insertion order inside a run); the thread at the
+// head of a run adds the run to the forces vector one value after the other, like the reference's
+// sequence of `+=` (methods_for_bc_data_handle.rs:79-101,126-172)
+__global__ void run_sum_kernel(uint32_t m, const uint32_t* __restrict__ key, const uint32_t* __restrict__ pos,
+                               const double* __restrict__ val, double* __restrict__ force) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m) return;
+  const uint32_t k = key[p];
+  if (k == 0xFFFFFFFFu || (p > 0 && key[p - 1] == k)) return;
+  double acc = force[k];
+  for (uint32_t q = p; q < m && key[q] == k; ++q) acc += val[pos[q]];
+  force[k] = acc;
+}
+
 const char* dof_name(int d) {
   static const char* names[6] = {"X", "Y", "Z", "ThX", "ThY", "ThZ"};  // DOFParameter's {:?}
   return names[d];
@@ -291,6 +312,10 @@ void bc_clear(Handle* h) {
   h->bc.constrained.clear();
   h->bc.displacement.clear();
   h->bc.force.clear();
+  h->bc.load_family.clear();
+  h->bc.load_dof.clear();
+  h->bc.load_elem.clear();
+  h->bc.load_value.clear();
   h->bc.uploaded = false;
   h->sep.valid = false;
 }
@@ -339,6 +364,94 @@ int32_t bc_add(Handle* h, bool displacement, size_t n, const uint32_t* node_numb
   return 0;
 }
 
+// n x FEM::add_uniformly_distributed_line_load / add_uniformly_distributed_surface_load
+// (methods_for_bc_data_handle.rs:58-102, :104-173): recorded on the host, evaluated at the next flush
+int32_t load_add(Handle* h, int family, size_t n, const uint32_t* number, const int32_t* dof, const double* value) {
+  if (n == 0) return 0;
+  if (!number || !dof || !value) return h->fail(FEMGPU_ERR_USAGE, "null load array");
+  for (size_t k = 0; k < n; ++k) {
+    if (dof[k] < 0 || dof[k] > 5) return h->fail(FEMGPU_ERR_USAGE, "dof parameter must be 0..5 (X, Y, Z, ThX, ThY, ThZ)");
+    uint32_t idx;
+    if (!h->fh[family].by_number.find(number[k], &idx))
+      // check_beam_element_exist / check_plate_element_exist
+      return h->fail(FEMGPU_E_ELEMENT_NOT_EXIST, std::string(family == FEMGPU_BEAM ? "Beam" : "Plate") +
+                                                     " element with number " + std::to_string(number[k]) + " does not exist!");
+    h->bc.load_family.push_back(family);
+    h->bc.load_elem.push_back(idx);
+    h->bc.load_dof.push_back(dof[k]);
+    h->bc.load_value.push_back(value[k]);
+    h->bc.uploaded = false;
+    h->sep.valid = false;
+  }
+  return 0;
+}
+
+// host boundary-condition state -> device: constraint flags, displacements, and the forces vector =
+// concentrated loads + the nodal equivalents of the distributed loads (evaluated here, on the device)
+int32_t forces_flush(Handle* h) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  Handle::Separated& S = h->sep;
+  const int64_t n = 6 * int64_t(h->nodes_number);
+  ensure_bc(h);
+  FEMGPU_CUDA_CHECK(h, S.d_constrained.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, S.d_disp.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, S.d_force.reserve(size_t(n) + 1));
+  if (h->bc.uploaded || n == 0) return 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_constrained.p, h->bc.constrained.data(), size_t(n), cudaMemcpyHostToDevice, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_disp.p, h->bc.displacement.data(), size_t(n) * 8, cudaMemcpyHostToDevice, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_force.p, h->bc.force.data(), size_t(n) * 8, cudaMemcpyHostToDevice, s));
+  const size_t nl = h->bc.load_family.size();
+  if (nl) {
+    if (4 * nl >= (size_t(1) << 32) || uint64_t(n) >= 0xFFFFFFFFull)
+      return h->fail(FEMGPU_ERR_LIMIT, "too many distributed loads / degrees of freedom for 32-bit load keys");
+    int32_t st = upload_pending(h);  // the loaded elements' connectivity and the nodes must be on the device
+    if (st) return st;
+    const uint32_t m = uint32_t(4 * nl);
+    DevBuf<int32_t> d_fam, d_dof;
+    DevBuf<uint32_t> d_elem, key_a, key_b, pos_a, pos_b;
+    DevBuf<double> d_value, val;
+    DevBuf<uint8_t> tmp;
+    auto tie = [&](auto& b) { b.stream = &h->stream; };
+    tie(d_fam); tie(d_dof); tie(d_elem); tie(key_a); tie(key_b); tie(pos_a); tie(pos_b); tie(d_value); tie(val); tie(tmp);
+    struct Guard {
+      std::function<void()> f;
+      ~Guard() { f(); }
+    } guard{[&] {
+      d_fam.release(); d_dof.release(); d_elem.release(); key_a.release(); key_b.release(); pos_a.release();
+      pos_b.release(); d_value.release(); val.release(); tmp.release();
+    }};
+    FEMGPU_CUDA_CHECK(h, d_fam.reserve(nl));
+    FEMGPU_CUDA_CHECK(h, d_dof.reserve(nl));
+    FEMGPU_CUDA_CHECK(h, d_elem.reserve(nl));
+    FEMGPU_CUDA_CHECK(h, d_value.reserve(nl));
+    FEMGPU_CUDA_CHECK(h, key_a.reserve(m));
+    FEMGPU_CUDA_CHECK(h, key_b.reserve(m));
+    FEMGPU_CUDA_CHECK(h, pos_a.reserve(m));
+    FEMGPU_CUDA_CHECK(h, pos_b.reserve(m));
+    FEMGPU_CUDA_CHECK(h, val.reserve(m));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_fam.p, h->bc.load_family.data(), nl * 4, cudaMemcpyHostToDevice, s));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_dof.p, h->bc.load_dof.data(), nl * 4, cudaMemcpyHostToDevice, s));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_elem.p, h->bc.load_elem.data(), nl * 4, cudaMemcpyHostToDevice, s));
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_value.p, h->bc.load_value.data(), nl * 8, cudaMemcpyHostToDevice, s));
+    if ((st = run_load_kernel(h, uint32_t(nl), d_fam.p, d_elem.p, d_dof.p, d_value.p, key_a.p, val.p))) return st;
+    iota_kernel<<<div_up(m, 256), 256, 0, s>>>(m, pos_a.p);
+    int bits = 1;
+    while (bits < 32 && (uint64_t(1) << bits) <= uint64_t(n)) ++bits;
+    bits = 32;  // the padding key 0xFFFFFFFF must sort last
+    size_t tb = 0;
+    FEMGPU_CUDA_CHECK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, key_a.p, key_b.p, pos_a.p, pos_b.p, int(m), 0, bits, s));
+    FEMGPU_CUDA_CHECK(h, tmp.reserve(tb + 16));
+    FEMGPU_CUDA_CHECK(h, cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_a.p, key_b.p, pos_a.p, pos_b.p, int(m), 0, bits, s));
+    run_sum_kernel<<<div_up(m, 256), 256, 0, s>>>(m, key_b.p, pos_b.p, val.p, S.d_force.p);
+    h->launches += 3;
+    FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+    FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(s));
+  }
+  h->bc.uploaded = true;
+  return 0;
+}
+
 int32_t run_separate(Handle* h) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
@@ -351,14 +464,9 @@ int32_t run_separate(Handle* h) {
   }
   cudaEvent_t e0 = S.ev[0], e1 = S.ev[1];
   FEMGPU_CUDA_CHECK(h, cudaEventRecord(e0, s));
-  FEMGPU_CUDA_CHECK(h, S.d_constrained.reserve(size_t(n) + 1));
-  FEMGPU_CUDA_CHECK(h, S.d_disp.reserve(size_t(n) + 1));
-  FEMGPU_CUDA_CHECK(h, S.d_force.reserve(size_t(n) + 1));
-  if (!h->bc.uploaded && n) {
-    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_constrained.p, h->bc.constrained.data(), size_t(n), cudaMemcpyHostToDevice, s));
-    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_disp.p, h->bc.displacement.data(), size_t(n) * 8, cudaMemcpyHostToDevice, s));
-    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(S.d_force.p, h->bc.force.data(), size_t(n) * 8, cudaMemcpyHostToDevice, s));
-    h->bc.uploaded = true;
+  {
+    int32_t st = forces_flush(h);
+    if (st) return st;
   }
   S.valid = false;
   S.n_aa = S.n_bb = 0;
@@ -482,6 +590,43 @@ int32_t femgpu_add_concentrated_load(femgpu_t* h, size_t n, const uint32_t* node
                                      const double* value) {
   if (!h) return FEMGPU_ERR_USAGE;
   return femgpu::bc_add(h, false, n, node_number, dof, value);
+}
+
+// the reference only accepts loads on elements that passed *::create: settle pending validation first
+static int32_t settle_validation(femgpu_t* h) {
+  return h->device >= 0 ? femgpu_validate(h, nullptr, nullptr, nullptr) : 0;
+}
+
+int32_t femgpu_add_line_load(femgpu_t* h, size_t n, const uint32_t* beam_number, const int32_t* dof,
+                             const double* value) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  int32_t st = settle_validation(h);
+  if (st) return st;
+  return femgpu::load_add(h, FEMGPU_BEAM, n, beam_number, dof, value);
+}
+
+int32_t femgpu_add_surface_load(femgpu_t* h, size_t n, const uint32_t* plate_number, const int32_t* dof,
+                                const double* value) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  int32_t st = settle_validation(h);
+  if (st) return st;
+  return femgpu::load_add(h, FEMGPU_PLATE, n, plate_number, dof, value);
+}
+
+int32_t femgpu_get_forces(femgpu_t* h, double* forces, const double** forces_device) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0)
+    return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
+                                         "femgpu has no CPU fallback");
+  int32_t st = femgpu::forces_flush(h);
+  if (st) return st;
+  const size_t n = size_t(h->nodes_number) * 6;
+  if (forces && n) {
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(forces, h->sep.d_force.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  }
+  if (forces_device) *forces_device = h->sep.d_force.p;
+  return 0;
 }
 
 int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t nnz[4]) {

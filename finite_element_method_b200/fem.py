@@ -258,6 +258,29 @@ class FEM:
         self._check(self._L.femgpu_add_concentrated_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p),
                                                          _p(vv, _lib.dp)))
 
+    def add_uniformly_distributed_line_load(self, beam_element_number, dof_parameter, value) -> None:
+        """methods_for_bc_data_handle.rs:58 (arrays are accepted: n calls in order)"""
+        nn, dd, vv = _u32(np.atleast_1d(beam_element_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
+            _f64(np.atleast_1d(value))
+        self._check(self._L.femgpu_add_line_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p), _p(vv, _lib.dp)))
+
+    def add_uniformly_distributed_surface_load(self, plate_element_number, dof_parameter, value) -> None:
+        """methods_for_bc_data_handle.rs:104"""
+        nn, dd, vv = _u32(np.atleast_1d(plate_element_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
+            _f64(np.atleast_1d(value))
+        self._check(self._L.femgpu_add_surface_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p), _p(vv, _lib.dp)))
+
+    def forces_vector(self, copy_out: bool = True):
+        """forces_vector of fem.rs:19: concentrated loads + nodal equivalents of the distributed loads.
+        copy_out=False evaluates it on the device only and returns its device address."""
+        if not copy_out:
+            dev = C.c_void_p()
+            self._check(self._L.femgpu_get_forces(self._h, None, C.byref(dev)))
+            return int(dev.value or 0)
+        out = np.zeros(6 * self.nodes_number, np.float64)
+        self._check(self._L.femgpu_get_forces(self._h, _p(out, _lib.dp), None))
+        return out
+
     def separate_stiffness_matrix_sparse_iterative(self, copy_out: bool = True):
         """methods_for_separate_stiffness_matrix.rs:217, on the device. copy_out=False leaves the
         quadrants in HBM (returns counts only): (n_aa, n_bb, [nnz_aa, nnz_ab, nnz_ba, nnz_bb], device_ms)."""

@@ -212,6 +212,20 @@ int32_t femgpu_add_displacement(femgpu_t* h, size_t n, const uint32_t* node_numb
 int32_t femgpu_add_concentrated_load(femgpu_t* h, size_t n, const uint32_t* node_number, const int32_t* dof,
                                      const double* value);
 
+/* n x FEM::add_uniformly_distributed_line_load(beam_element_number, dof_parameter, value)
+ *                                                              methods_for_bc_data_handle.rs:58-102
+ * n x FEM::add_uniformly_distributed_surface_load(plate_element_number, dof_parameter, value)    :104-173
+ * The nodal equivalents (Beam::convert_uniformly_distributed_line_load_to_nodal_loads structs/beam.rs:775-797,
+ * Plate::convert_uniformly_distributed_surface_load_to_nodal_loads structs/plate.rs:1145-1185) are
+ * evaluated on the device and added to the forces vector, per DOF in call order, when the forces are
+ * next needed (femgpu_get_forces, femgpu_separate_sparse). */
+int32_t femgpu_add_line_load(femgpu_t* h, size_t n, const uint32_t* beam_number, const int32_t* dof,
+                             const double* value);
+int32_t femgpu_add_surface_load(femgpu_t* h, size_t n, const uint32_t* plate_number, const int32_t* dof,
+                                const double* value);
+/* forces vector [6 * nodes_number] = concentrated + distributed loads (fem.rs:19); either pointer may be NULL */
+int32_t femgpu_get_forces(femgpu_t* h, double* forces, const double** forces_device);
+
 /* FEM::separate_stiffness_matrix_sparse_iterative()   methods_for_separate_stiffness_matrix.rs:217-320
  * on the device, from the CSR values of the last numeric pass: DOFs with a zero diagonal are
  * inactive (error when one of them is constrained), constrained ones form the b-set, the rest the

@@ -966,6 +966,48 @@ inline int plate_element(const V p1[3], const V p2[3], const V p3[3], const V p4
 }
 
 // --------------------------------------------------------------------------
+// Uniformly distributed loads -> nodal loads
+// --------------------------------------------------------------------------
+
+// Beam::convert_uniformly_distributed_line_load_to_nodal_loads (beam.rs:775-797) over the beam's
+// integration points [(r = 0, alpha = 2)] (beam.rs:729): f += (h(r) * q) * (det J(r) * alpha)
+template <typename V>
+inline void beam_line_load_nodal(const V p1[3], const V p2[3], V q, V f[2]) {
+  f[0] = f[1] = V(0.0f);
+  const V r = V(0.0f), alpha = V(2.0f);
+  const V det = bar_determinant_of_jacobian_at_r(p1, p2, r);
+  f[0] = f[0] + (h1_r(r) * q) * (det * alpha);
+  f[1] = f[1] + (h2_r(r) * q) * (det * alpha);
+}
+
+// Plate::convert_uniformly_distributed_surface_load_to_nodal_loads (plate.rs:1145-1185) over the four
+// Gauss points of plate.rs:1066-1091: f += (h_a(r, s) * q) * (det J(r, s) * alpha_r * alpha_s),
+// h_a = quadrilateral_4n_element_functions.rs:585-611, det J = :477-503
+template <typename V>
+inline void plate_surface_load_nodal(const V p1[3], const V p2[3], const V p3[3], const V p4[3], V q,
+                                     V rel_tol, V abs_tol, V f[4]) {
+  PlateGeom<V> g;
+  find_rotation_matrix_elements_of_quadrilateral(p2, p3, p4, rel_tol, abs_tol, g.q);
+  extract_transformed_directions_of_nodes(p1, p2, p3, p4, g);
+  V gp = std::sqrt(V(1.0f / 3.0f));
+  const V one = V(1.0f), m1 = V(-1.0f), quarter = V(0.25f);
+  V ips[4][4] = {{gp * one, gp * one, one, one},
+                 {gp * m1, gp * one, one, one},
+                 {gp * m1, gp * m1, one, one},
+                 {gp * one, gp * m1, one, one}};
+  for (int a = 0; a < 4; ++a) f[a] = V(0.0f);
+  for (auto& ip : ips) {
+    const V r = ip[0], s = ip[1];
+    V j[4];
+    quad_jacobian_at_r_s(g, r, s, j);
+    const V scale = quad_determinant_of_jacobian(j) * ip[2] * ip[3];
+    const V h[4] = {quarter * (one + r) * (one + s), quarter * (one - r) * (one + s),
+                    quarter * (one - r) * (one - s), quarter * (one + r) * (one - s)};
+    for (int a = 0; a < 4; ++a) f[a] = f[a] + (h[a] * q) * scale;
+  }
+}
+
+// --------------------------------------------------------------------------
 // Global matrix: position-keyed map + the zero-skip block scatter
 // (methods_for_truss_data_handle.rs:93-123, methods_for_beam_data_handle.rs:107-137,
 //  methods_for_plate_data_handle.rs:134-212; add_value = entry(pos).or_insert(0) += v)

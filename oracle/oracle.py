@@ -116,6 +116,21 @@ def plate(p1, p2, p3, p4, E, nu, t, ks, rel_tol=1e-4, abs_tol=1e-12):
     return q.reshape(3, 3), kl.reshape(24, 24), kg.reshape(24, 24)
 
 
+def beam_line_load(p1, p2, q):
+    """Beam::convert_uniformly_distributed_line_load_to_nodal_loads (beam.rs:775-797) -> f[2]"""
+    f = np.zeros(2)
+    lib().oracle_beam_line_load_f64(_d(p1)[1], _d(p2)[1], C.c_double(q), f.ctypes.data_as(_dp))
+    return f
+
+
+def plate_surface_load(p1, p2, p3, p4, q, rel_tol=1e-4, abs_tol=1e-12):
+    """Plate::convert_uniformly_distributed_surface_load_to_nodal_loads (plate.rs:1145-1185) -> f[4]"""
+    f = np.zeros(4)
+    lib().oracle_plate_surface_load_f64(*[_d(p)[1] for p in (p1, p2, p3, p4)], C.c_double(q),
+                                        C.c_double(rel_tol), C.c_double(abs_tol), f.ctypes.data_as(_dp))
+    return f
+
+
 def reference_truss_test_f32():
     """Replays the reference's own f32 test model; returns (k00, u2x, r1x, force_r) as float32."""
     v = [C.c_float() for _ in range(4)]

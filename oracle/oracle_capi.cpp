@@ -84,6 +84,15 @@ int oracle_plate_f64(const double* p1, const double* p2, const double* p3, const
   return OK;
 }
 
+void oracle_beam_line_load_f64(const double* p1, const double* p2, double q, double* f) {
+  beam_line_load_nodal<double>(p1, p2, q, f);
+}
+
+void oracle_plate_surface_load_f64(const double* p1, const double* p2, const double* p3, const double* p4,
+                                   double q, double rel_tol, double abs_tol, double* f) {
+  plate_surface_load_nodal<double>(p1, p2, p3, p4, q, rel_tol, abs_tol, f);
+}
+
 // The reference's only test model, replayed in f32 end to end
 // (tests/fem/test_fem.rs:5-64): 2 nodes (0,0,0),(30,0,0); truss E=1e6, A=2; u1x=0; F2x=100.
 // K_aa is 1x1, so colsol's LDL^T solve is u = r / k; the reaction is K_ba*u_a + K_bb*u_b - R_b

@@ -191,3 +191,86 @@ def test_gpu_separation_fullsize_properties():
     assert abs(total - float(np.sum(v))) <= 1e-9 * float(np.sum(np.abs(v)))
     assert np.array_equal(np.sort(np.concatenate([sep.k_aa_indexes, sep.k_bb_indexes])), np.arange(6 * len(mesh["x"])))
     fem.close()
+
+
+# ---------------------------------------------------------------------------- distributed loads (§8f rank 2)
+def test_oracle_distributed_loads_analytic():
+    """beam.rs:775-797 / plate.rs:1145-1185: a uniform load q on a straight member of length L gives
+    qL/2 per node; on a quadrilateral of area A the four nodal loads add up to qA (and are qA/4 each on
+    a rectangle)."""
+    assert np.allclose(O.beam_line_load([0, 0, 0], [3, 4, 0], 10.0), [25.0, 25.0], rtol=1e-15)
+    assert np.allclose(O.plate_surface_load([2, 1.5, 0], [0, 1.5, 0], [0, 0, 0], [2, 0, 0], 4.0), 3.0, rtol=1e-15)
+    p = [[2.2, 1.4, 0.3], [0.1, 1.6, 0.3], [0, 0, 0.3], [2.0, -0.1, 0.3]]
+    x, y = np.array([q[0] for q in p]), np.array([q[1] for q in p])
+    area = 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+    f = O.plate_surface_load(*p, 4.0)
+    assert abs(f.sum() - 4.0 * area) < 1e-13 and f.min() > 0
+
+
+def test_distributed_load_host_checks():
+    fem = FEM(1e-4, 1e-12, 4, device=-1)
+    for i, (x, y) in enumerate([(1, 1), (0, 1), (0, 0), (1, 0)]):
+        fem.add_node(i + 1, float(x), float(y), 0.0)
+    with pytest.raises(FemError, match="Beam element with number 3 does not exist!"):
+        fem.add_uniformly_distributed_line_load(3, DOFParameter.Y, 1.0)
+    with pytest.raises(FemError, match="Plate element with number 1 does not exist!"):
+        fem.add_uniformly_distributed_surface_load(1, DOFParameter.Z, 1.0)
+    fem.close()
+
+
+def _expected_forces(mesh, line, surface, point):
+    """The reference's sequence of `+=` into the forces vector, with the oracle's nodal loads."""
+    F = np.zeros(6 * len(mesh["x"]))
+    P = np.stack([mesh["x"], mesh["y"], mesh["z"]], axis=1)
+    for node, dof, val in point:
+        F[6 * node + dof] += val
+    for e, dof, q in line:
+        a, b = int(mesh["b_n1"][e]), int(mesh["b_n2"][e])
+        f = O.beam_line_load(P[a], P[b], q)
+        F[6 * a + dof] += f[0]; F[6 * b + dof] += f[1]
+    pn = np.asarray(mesh["p_n"]).reshape(4, -1)
+    for e, dof, q in surface:
+        n = [int(pn[k][e]) for k in range(4)]
+        f = O.plate_surface_load(*[P[k] for k in n], q, mesh["rel_tol"], mesh["abs_tol"])
+        for k in range(4):
+            F[6 * n[k] + dof] += f[k]
+    return F
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["mixed", "jitter", "x0"])
+def test_gpu_distributed_loads_match_oracle(which):
+    rng = np.random.default_rng(7)
+    if which == "mixed":
+        mesh = meshes.mixed_structure(10, 8)
+    else:
+        mesh = meshes.plate_grid(9, 7, which)
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], len(mesh["x"]), device=0)
+    fem.load_mesh(mesh)
+    npl = np.asarray(mesh["p_n"]).reshape(4, -1).shape[1]
+    nb = len(mesh["b_n1"])
+    # every plate gets a pressure, a third of them a second (in-plane) load; every other beam a line load
+    surface = [(e, 2, float(rng.uniform(-5e3, 5e3))) for e in range(npl)] + \
+              [(e, 0, float(rng.uniform(-1e3, 1e3))) for e in range(0, npl, 3)]
+    line = [(e, int(rng.integers(0, 6)), float(rng.uniform(-2e3, 2e3))) for e in range(0, nb, 2)]
+    point = [(3, 1, 750.0), (len(mesh["x"]) - 1, 2, -125.0), (3, 1, 250.0)]
+    first_plate = 1                              # load_mesh numbers every family from 1
+    for node, dof, val in point:
+        fem.add_concentrated_load(node + 1, dof, val)
+    if line:
+        fem.add_uniformly_distributed_line_load([e + 1 for e, _, _ in line], [d for _, d, _ in line], [q for _, _, q in line])
+    fem.add_uniformly_distributed_surface_load([e + first_plate for e, _, _ in surface], [d for _, d, _ in surface],
+                                               [q for _, _, q in surface])
+    F = fem.forces_vector()
+    ref = _expected_forces(mesh, line, surface, point)
+    scale = np.abs(ref).max()
+    assert np.abs(F - ref).max() <= 1e-12 * scale, np.abs(F - ref).max() / scale
+    assert np.array_equal(F, fem.forces_vector())                     # re-evaluation is bit-identical
+    # the distributed loads reach the right-hand side of the separated system
+    fem.assemble()
+    w = int(round(mesh["x"].max())) + 1 if which != "x0" else 10
+    fixed = np.repeat(np.arange(w), 6)
+    fem.add_displacement(fixed + 1, np.tile(np.arange(6), w), np.zeros(len(fixed)))
+    sep = fem.separate_stiffness_matrix_sparse_iterative()
+    assert np.abs(sep.b - ref[sep.k_aa_indexes]).max() <= 1e-12 * scale   # u_b = 0: b = R_a
+    fem.close()
