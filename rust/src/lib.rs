@@ -28,6 +28,8 @@ extern "C" {
     fn femgpu_rotation_elements(h: *mut FemGpu, family: i32, number: u32, out: *mut f64) -> i32;
     fn femgpu_add_displacement(h: *mut FemGpu, n: usize, node: *const u32, dof: *const i32, value: *const f64) -> i32;
     fn femgpu_add_concentrated_load(h: *mut FemGpu, n: usize, node: *const u32, dof: *const i32, value: *const f64) -> i32;
+    fn femgpu_add_line_load(h: *mut FemGpu, n: usize, beam: *const u32, dof: *const i32, value: *const f64) -> i32;
+    fn femgpu_add_surface_load(h: *mut FemGpu, n: usize, plate: *const u32, dof: *const i32, value: *const f64) -> i32;
     fn femgpu_separate_sparse(h: *mut FemGpu, n_aa: *mut i64, n_bb: *mut i64, nnz: *mut i64) -> i32;
     fn femgpu_get_separated_indexes(h: *mut FemGpu, k_aa_indexes: *mut i64, k_bb_indexes: *mut i64) -> i32;
     fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
@@ -130,6 +132,18 @@ impl FEM {
     pub fn add_concentrated_load(&mut self, node_number: u32, dof_parameter: DOFParameter, value: f64) -> Result<(), String> {
         let dof = dof_parameter as i32;
         self.check(unsafe { femgpu_add_concentrated_load(self.h, 1, &node_number, &dof, &value) })
+    }
+    /// methods_for_bc_data_handle.rs:58
+    pub fn add_uniformly_distributed_line_load(&mut self, beam_element_number: u32, dof_parameter: DOFParameter,
+                                               value: f64) -> Result<(), String> {
+        let dof = dof_parameter as i32;
+        self.check(unsafe { femgpu_add_line_load(self.h, 1, &beam_element_number, &dof, &value) })
+    }
+    /// methods_for_bc_data_handle.rs:104
+    pub fn add_uniformly_distributed_surface_load(&mut self, plate_element_number: u32, dof_parameter: DOFParameter,
+                                                  value: f64) -> Result<(), String> {
+        let dof = dof_parameter as i32;
+        self.check(unsafe { femgpu_add_surface_load(self.h, 1, &plate_element_number, &dof, &value) })
     }
     /// methods_for_separate_stiffness_matrix.rs:217 — runs on the device on the assembled CSR values
     pub fn separate_stiffness_matrix_sparse_iterative(&mut self) -> Result<SeparatedStiffnessMatrixSparse, String> {
