@@ -293,6 +293,8 @@ struct Handle {
   DevBuf<BlockMeta> blk_meta;      // thread order
   DevBuf<uint32_t> blk_order;      // thread position -> sorted block id
   DevBuf<WorkItem> items;          // [n_slabs][asm_threads] balanced per-thread work lists
+  DevBuf<uint32_t> items_c;        // the same table as the staged kernel reads it: (first entry - the slab's
+                                   // first entry) | entries << 16
   DevBuf<uint32_t> elist;          // [n_slabs][kElistStride]: family<<26 | element, 0xFFFFFFFF = empty;
                                    // (compact list when a slab overflows the table: unstaged path)
   DevBuf<uint32_t> elist_compact;

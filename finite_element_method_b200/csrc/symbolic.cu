@@ -243,16 +243,39 @@ __global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restri
 __device__ __forceinline__ uint32_t family_cost(uint32_t f) {
   return (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
 }
-// cost of the first p contributions of a block in execution order (placeholders, plates, beams, trusses)
-__device__ __forceinline__ uint32_t chunk_cum_cost(const uint32_t n[4], uint32_t p) {
+// How the contributions of a block split over kk lanes are dealt to its chunks: every family
+// (execution order: placeholders, plates, beams, trusses) is spread evenly, chunk j taking a
+// consecutive run of the family's contributions — n / kk each, the n % kk left over going one by
+// one to the chunks that are lightest so far (cost, then count, then index). The lanes of a warp
+// run their entries family by family, so a warp's time is the sum over the families of the LARGEST
+// per-lane count: a chunk holding "the second half" of a mixed block (2 plates + 2 beams + 2
+// trusses) costs its warp six loop trips, two chunks of (2 plates + beam + truss) cost it four.
+// cnt[g][j] = contributions of family group g in chunk j. Every chunk is non-empty when kk <= total.
+__device__ __forceinline__ void chunk_family_counts(const uint32_t n[4], uint32_t kk, uint32_t cnt[4][kMaxChunks]) {
   const uint32_t cost[4] = {0u, kCostPlate, kCostBeam, kCostTruss};
-  uint32_t acc = 0;
+  uint32_t load[kMaxChunks], items[kMaxChunks];
+  for (uint32_t j = 0; j < uint32_t(kMaxChunks); ++j) load[j] = items[j] = 0;
   for (int g = 0; g < 4; ++g) {
-    uint32_t t = min(p, n[g]);
-    acc += t * cost[g];
-    p -= t;
+    const uint32_t base = n[g] / kk, extra = n[g] % kk;
+    uint32_t got = 0;  // bit j: chunk j already has one of this family's left-over contributions
+    for (uint32_t j = 0; j < uint32_t(kMaxChunks); ++j) cnt[g][j] = j < kk ? base : 0u;
+    for (uint32_t e = 0; e < extra; ++e) {
+      uint32_t best = kk;
+      for (uint32_t j = 0; j < kk; ++j) {
+        if (got & (1u << j)) continue;
+        if (best == kk || load[j] < load[best] || (load[j] == load[best] && items[j] < items[best])) best = j;
+      }
+      got |= 1u << best;
+      cnt[g][best]++;
+    }
+    for (uint32_t j = 0; j < kk; ++j) {
+      load[j] += cnt[g][j] * cost[g];
+      items[j] += cnt[g][j];
+    }
   }
-  return acc;
+}
+__device__ __forceinline__ int family_group(uint32_t f) {
+  return f == 3u ? 0 : (f == uint32_t(FEMGPU_PLATE) ? 1 : (f == uint32_t(FEMGPU_BEAM) ? 2 : 3));
 }
 
 __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* __restrict__ slabs,
@@ -321,27 +344,20 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
       if ((n & 31u) + kk > 32u)
         while (n & 31u) out[n++] = WorkItem{0u, 0u, 0u, 0u};
       uint32_t nf[4] = {0, 0, 0, 0};  // placeholders, plates, beams, trusses
-      for (uint32_t i = 0; i < cnt; ++i) {
-        const uint32_t f = contrib[c0 + i] >> 30;
-        nf[f == 3u ? 0 : (f == FEMGPU_PLATE ? 1 : (f == FEMGPU_BEAM ? 2 : 3))]++;
-      }
+      for (uint32_t i = 0; i < cnt; ++i) nf[family_group(contrib[c0 + i] >> 30)]++;
+      uint32_t fc[4][kMaxChunks];
+      chunk_family_counts(nf, kk, fc);
       uint32_t s_prev = 0;
       for (uint32_t j = 0; j < kk; ++j) {
-        uint32_t s_next = cnt;
-        if (j + 1 < kk) {
-          const uint32_t target = uint32_t(uint64_t(j + 1) * c / kk);
-          const uint32_t hi = cnt - (kk - 1 - j);  // leave one contribution for every later chunk
-          s_next = s_prev + 1;
-          while (s_next < hi && chunk_cum_cost(nf, s_next + 1) <= target) ++s_next;
-        }
+        const uint32_t take = fc[0][j] + fc[1][j] + fc[2][j] + fc[3][j];
         WorkItem w;
         w.blk_begin = b;
         w.blk_count = 1u | (j << 16) | ((kk - 1u) << 20) | (1u << 24);
-        w.c_begin = c0 + s_prev;
-        w.c_count = s_next - s_prev;
+        w.c_begin = c0 + s_prev;  // where the chunk's entries go; WHICH contributions: chunk_family_counts
+        w.c_count = take;
         out[n++] = w;
         max_round = max(max_round, j);
-        s_prev = s_next;
+        s_prev += take;
       }
     } else {
       if (!open || cur + c > W) {
@@ -359,6 +375,18 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
     slabs[k].flags = d.flags | (max_round << 8);
     atomicMax(flags + 13, 1);  // some staged slab splits a block: the kernel variant with merge rounds is needed
   }
+}
+
+// the work items as the staged kernel stages them: 4 bytes per lane
+__global__ void compact_items_kernel(uint32_t n_slabs, uint32_t threads, const SlabDesc* __restrict__ slabs,
+                                     const WorkItem* __restrict__ items, uint32_t* __restrict__ out) {
+  uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t k = uint32_t(t / threads);
+  if (k >= n_slabs) return;
+  const WorkItem w = items[t];
+  const SlabDesc d = slabs[k];
+  const bool live = (w.blk_count & 0xFFFFu) != 0 && !(d.flags & 1u);  // staged slabs: < 2^16 entries (stage cap)
+  out[t] = live ? ((w.c_begin - d.c_begin) & 0xFFFFu) | (w.c_count << 16) : 0u;
 }
 
 // ---- per-slab element lists -----------------------------------------------------------------
@@ -496,19 +524,28 @@ __global__ void item_program_kernel(uint32_t n_slabs, uint32_t threads, const Sl
   uint32_t out = w.c_begin;
   const uint32_t order[4] = {3u, uint32_t(FEMGPU_PLATE), uint32_t(FEMGPU_BEAM), uint32_t(FEMGPU_TRUSS)};
   if ((w.blk_count & (1u << 24)) || n_blk == 1) {
-    // one chunk of a split block — or a whole block that is the item's only one: contributions
-    // [skip, skip + take) of the block's execution order, accumulated as a single group (no flush
-    // between the families)
+    // one chunk of a split block — or a whole block that is the item's only one (= the single chunk
+    // of an unsplit block): its share of every family (chunk_family_counts), accumulated as a single
+    // group (no flush between the families)
     const uint32_t p = w.blk_begin, c0 = cptr_ord[p], c1 = cptr_ord[p + 1];
-    const uint32_t skip = w.c_begin - c0, take = w.c_count, round = (w.blk_count >> 16) & 3u;
-    const uint32_t more = (w.blk_count & (1u << 24)) ? (w.blk_count >> 20) & 3u : 0u;  // chunks after chunk 0
+    const bool is_chunk = (w.blk_count & (1u << 24)) != 0;
+    const uint32_t round = is_chunk ? (w.blk_count >> 16) & 3u : 0u;
+    const uint32_t more = is_chunk ? (w.blk_count >> 20) & 3u : 0u;  // chunks after chunk 0
     const uint32_t blk = p - d.blk_begin;
-    uint32_t pos = 0, left = take;
-    for (int f = 0; f < 4; ++f)
+    uint32_t nf[4] = {0, 0, 0, 0};
+    for (uint32_t c = c0; c < c1; ++c) nf[family_group(src[c] >> 30)]++;
+    uint32_t fc[4][kMaxChunks];
+    chunk_family_counts(nf, more + 1u, fc);
+    uint32_t left = w.c_count;
+    for (int f = 0; f < 4; ++f) {
+      uint32_t lo = 0;
+      for (uint32_t j = 0; j < round; ++j) lo += fc[f][j];
+      const uint32_t hi = lo + fc[f][round];
+      uint32_t pos = 0;
       for (uint32_t c = c0; c < c1; ++c) {
         const uint32_t code = src[c];
         if ((code >> 30) != order[f]) continue;
-        if (pos >= skip && pos < skip + take) {
+        if (pos >= lo && pos < hi) {
           uint32_t e = (code & 0xFC000000u) | (blk << kEntBlkShift) | (code & kEntRecMask);
           // chunk j >= 1: sender of merge round j; chunk 0: holds its flush and receives `more` rounds
           if (--left == 0) e |= kEntEnd | ((round ? round : more) << kEntDeferShift) | (round ? kEntRmw : 0u);
@@ -516,6 +553,7 @@ __global__ void item_program_kernel(uint32_t n_slabs, uint32_t threads, const Sl
         }
         ++pos;
       }
+    }
     return;
   }
   for (int f = 0; f < 4; ++f) {
@@ -1086,7 +1124,10 @@ int32_t run_symbolic(Handle* h) {
   SYM_CHECK(h->items.reserve(size_t(n_slabs) * threads));
   work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, threads, h->slabs.p, ocost.as<uint32_t>(),
                                                          h->blk_cptr.p, h->contrib.p, h->items.p, h->d_flag.p);
-  h->launches++;
+  SYM_CHECK(h->items_c.reserve(size_t(n_slabs) * threads));
+  compact_items_kernel<<<div_up(uint64_t(n_slabs) * threads, 256), 256, 0, s>>>(n_slabs, threads, h->slabs.p,
+                                                                                h->items.p, h->items_c.p);
+  h->launches += 2;
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaStreamSynchronize(s));
   mark("work items");
