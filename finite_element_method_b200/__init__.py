@@ -3,7 +3,9 @@ RomanShushakov/finite_element_method: truss / beam / plate local stiffness + det
 assembly into the global FP64 CSR matrix. The product is libfemgpu.so (C ABI in include/femgpu.h);
 this package is its Python host mirror (`FEM`) plus synthetic mesh generators for the benchmarks.
 """
-from .fem import BEAM, PLATE, TRUSS, FEM, DOFParameter, FemError, SeparatedStiffnessMatrixSparse  # noqa: F401
+from .fem import (BEAM, ELEMENT_RESULT_COMPONENTS, PLATE, TRUSS, FEM, DOFParameter, FemError,  # noqa: F401
+                  SeparatedStiffnessMatrixSparse)
 from . import meshes  # noqa: F401
 
-__all__ = ["FEM", "FemError", "DOFParameter", "SeparatedStiffnessMatrixSparse", "TRUSS", "BEAM", "PLATE", "meshes"]
+__all__ = ["FEM", "FemError", "DOFParameter", "SeparatedStiffnessMatrixSparse", "TRUSS", "BEAM", "PLATE",
+           "ELEMENT_RESULT_COMPONENTS", "meshes"]

@@ -31,6 +31,7 @@ SIGNATURES = {
     "femgpu_add_plate": (C.c_int32, [H, C.c_size_t, u32p, u32p, u32p, u32p, u32p, dp, dp, dp, dp]),
     "femgpu_validate": (C.c_int32, [H, i32p, u32p, i32p]),
     "femgpu_counts": (C.c_int32, [H, u64p, u64p, u64p, u64p]),
+    "femgpu_get_numbers": (C.c_int32, [H, C.c_int32, u32p]),
     "femgpu_symbolic": (C.c_int32, [H, i64p, i64p]),
     "femgpu_numeric": (C.c_int32, [H]),
     "femgpu_synchronize": (C.c_int32, [H]),
@@ -54,6 +55,15 @@ SIGNATURES = {
                                                     C.POINTER(C.c_void_p)]),
     "femgpu_separated_rhs": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_last_separate_ms": (C.c_int32, [H, fp]),
+    "femgpu_solve_pcg": (C.c_int32, [H, C.c_int32, C.c_int64, i64p]),
+    "femgpu_get_ua": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
+    "femgpu_set_ua": (C.c_int32, [H, dp]),
+    "femgpu_solve_info": (C.c_int32, [H, i64p, dp, fp]),
+    "femgpu_global_analysis": (C.c_int32, [H]),
+    "femgpu_get_reactions": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
+    "femgpu_get_global_result": (C.c_int32, [H, dp, dp]),
+    "femgpu_set_displacements": (C.c_int32, [H, dp]),
+    "femgpu_element_results": (C.c_int32, [H, C.c_int32, dp, C.POINTER(C.c_void_p)]),
     "femgpu_launch_count": (C.c_int32, [H, C.c_int32, u64p]),
     "femgpu_last_numeric_ms": (C.c_int32, [H, fp]),
     "femgpu_numeric_ms_history": (C.c_int32, [H, C.c_uint32, fp]),

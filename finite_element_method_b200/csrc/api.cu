@@ -582,6 +582,7 @@ static void free_device(femgpu_t* h) {
   h->dist.send_buf.release(); h->dist.recv_buf.release(); h->dist.recv_dst_block.release();
   h->dist.recv_full.release(); h->dist.remote_keys.release();
   sep_release(h);
+  sol_release(h);
 }
 
 int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
@@ -737,6 +738,14 @@ int32_t femgpu_counts(const femgpu_t* h, uint64_t* nodes, uint64_t* truss, uint6
   if (truss) *truss = h->fh[0].size();
   if (beam) *beam = h->fh[1].size();
   if (plate) *plate = h->fh[2].size();
+  return 0;
+}
+
+int32_t femgpu_get_numbers(const femgpu_t* h, int32_t family, uint32_t* out) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (family < -1 || family >= femgpu::kFamilies) return h->fail(FEMGPU_ERR_USAGE, "family must be -1 (nodes), 0, 1 or 2");
+  const std::vector<uint32_t>& v = family < 0 ? h->node_number : h->fh[family].number;
+  if (out && !v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(uint32_t));
   return 0;
 }
 

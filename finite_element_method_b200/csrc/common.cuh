@@ -350,6 +350,21 @@ struct Handle {
     DevBuf<int32_t> tmp[8];           // scratch: class flags, their scans, per-row counts of the 4 quadrants
   } sep;
 
+  // ---- global analysis (solve.cu): u_a, reactions, composed vectors, element results (results.cu) ----
+  struct Solution {
+    bool ua_valid = false, composed = false, disp_valid = false;
+    int64_t iterations = 0;
+    double residual = 0.0;
+    float last_ms = 0.f;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    DevBuf<double> u_a, r_r;          // [n_aa], [n_bb]
+    DevBuf<double> r, z, p, ap, minv; // PCG work vectors; minv: 1/diag, or 6 doubles per row (block Jacobi)
+    DevBuf<uint32_t> blk;             // block Jacobi: first row of the row's block | size << 28
+    DevBuf<double> partial, scal;     // reduction partials, device scalars
+    DevBuf<double> disp, force;       // [6 * nodes_number] displacements / forces after compose
+    DevBuf<double> res[kFamilies];    // element results
+  } sol;
+
   // Pinned bounce buffers of the bulk host->device path (api.cu h2d_staged): the host staging vectors
   // are pageable, so large uploads are copied chunk-wise into pinned memory by several host threads
   // while the previous chunk is on its way over PCIe.
@@ -370,7 +385,7 @@ struct Handle {
       for (auto& p : f.props) tie(p);
       tie(f.cbase); tie(f.rec); tie(f.mat); tie(f.err);
     }
-    tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(elist); tie(elist_compact);
+    tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(items_c); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
     tie(col_idx); tie(values); tie(scratch); tie(d_flag);
     tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_dst_block); tie(dist.recv_full);
@@ -381,6 +396,9 @@ struct Handle {
       tie(sep.row_ptr[q]); tie(sep.col[q]); tie(sep.val[q]);
     }
     for (auto& t : sep.tmp) tie(t);
+    tie(sol.u_a); tie(sol.r_r); tie(sol.r); tie(sol.z); tie(sol.p); tie(sol.ap); tie(sol.minv); tie(sol.blk);
+    tie(sol.partial); tie(sol.scal); tie(sol.disp); tie(sol.force);
+    for (auto& r : sol.res) tie(r);
   }
 
   int32_t fail(int32_t code, const std::string& text) const {
@@ -407,6 +425,9 @@ int32_t forces_flush(Handle* h);                         // separate.cu: bc -> s
 int32_t run_separate(Handle* h);                         // separate.cu
 void sep_release(Handle* h);                             // separate.cu
 void bc_clear(Handle* h);                                // separate.cu
+int32_t run_element_results(Handle* h, int family, const double* d_u, double* d_out);  // results.cu
+void sol_release(Handle* h);                             // solve.cu
+void sol_invalidate(Handle* h);                          // solve.cu
 int32_t dist_numeric_exchange(Handle* h);                // dist.cu
 void dist_destroy(Handle* h);                            // dist.cu
 int32_t dist_allgather_i64(Handle* h, const int64_t* send, int64_t* recv, size_t n);  // dist.cu

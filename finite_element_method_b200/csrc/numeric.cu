@@ -213,22 +213,22 @@ struct SlabRegs {
   }
 };
 
-// Descriptor block of a slab in shared memory: [SlabDesc 48 B][work items kT x 16 B][element
+// Descriptor block of a slab in shared memory: [SlabDesc 48 B][work items kT x 4 B][element
 // list kElistStride x 4 B]. Everything is addressable from the slab id alone (dense tables), so it
 // is requested two slabs ahead with cp.async; nothing that is in flight lives in registers.
 constexpr uint32_t kDescItemsOff = 48;
-#ifdef FEMGPU_COMPACT_ITEMS
+// alignment of the shared-memory regions after the image (TMA bulk copies and cp.async need 16 bytes)
+#ifndef FEMGPU_SMEM_ALIGN
+#define FEMGPU_SMEM_ALIGN 16u
+#endif
+constexpr uint32_t kSmemAlign = FEMGPU_SMEM_ALIGN;
 // a lane only needs where its entries start and how many they are: 4 bytes per lane
 constexpr uint32_t kDescItemBytes = 4;
-#else
-constexpr uint32_t kDescItemBytes = 16;
-#endif
 template <int kT> __host__ __device__ constexpr uint32_t desc_elist_off() { return kDescItemsOff + kT * kDescItemBytes; }
-template <int kT> __host__ __device__ constexpr uint32_t desc_bytes() { return (desc_elist_off<kT>() + kElistStride * 4 + 127) & ~127u; }
+template <int kT> __host__ __device__ constexpr uint32_t desc_bytes() { return (desc_elist_off<kT>() + kElistStride * 4 + kSmemAlign - 1) & ~(kSmemAlign - 1); }
 
 template <int kT>
 __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_t dbuf_s, uint32_t tid) {
-#ifdef FEMGPU_COMPACT_ITEMS
   constexpr uint32_t kItemLanes = kT / 4, kElistLanes = kElistStride / 4;
   if (tid < kItemLanes) cp_async16(dbuf_s + kDescItemsOff + tid * 16u, A.items_c + size_t(k) * kT + tid * 4u);
   else if (tid < kItemLanes + kElistLanes)
@@ -237,13 +237,6 @@ __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_
   else if (tid < kItemLanes + kElistLanes + 3)
     cp_async16(dbuf_s + (tid - kItemLanes - kElistLanes) * 16u,
                reinterpret_cast<const uint4*>(A.slabs + k) + (tid - kItemLanes - kElistLanes));
-#else
-  cp_async16(dbuf_s + kDescItemsOff + tid * 16u, A.items + size_t(k) * kT + tid);
-  if (tid < kElistStride / 4) cp_async16(dbuf_s + desc_elist_off<kT>() + tid * 16u, A.elist + size_t(k) * kElistStride + tid * 4u);
-  else if (tid < kElistStride / 4 + 3)
-    cp_async16(dbuf_s + (tid - kElistStride / 4) * 16u,
-               reinterpret_cast<const uint4*>(A.slabs + k) + (tid - kElistStride / 4));
-#endif
 }
 
 template <int kT>
@@ -256,15 +249,9 @@ __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uin
 #pragma unroll
   for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j)
     R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>())[j * (kT / 2) + (tid >> 1)];
-#ifdef FEMGPU_COMPACT_ITEMS
   const uint32_t w = reinterpret_cast<const uint32_t*>(dbuf + kDescItemsOff)[tid];
   R.c_begin = R.slab_c_begin() + (w & 0xFFFFu);
   R.c_count = w >> 16;
-#else
-  const uint2 w = reinterpret_cast<const uint2*>(dbuf + kDescItemsOff)[tid * 2u + 1u];
-  R.c_begin = w.x;
-  R.c_count = w.y;
-#endif
   R.sanitize();
   return R;
 }
@@ -279,13 +266,8 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
   // completing on the same mbarrier as the cp.async record gathers
   if (tid == 0 && R.blk_count()) {
     const uint32_t meta_bytes = R.blk_count() * 16u, ent_bytes = R.slab_c_count() ? R.ent_bytes() : 0u;
-#ifdef FEMGPU_BULK_RECORDS
-    const uint32_t rec_bytes = R.n_truss() * 32u + R.n_beam() * 128u + R.n_plate() * 160u;
-#else
-    const uint32_t rec_bytes = 0u;
-#endif
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mbar_s),
-                 "r"(meta_bytes + ent_bytes + rec_bytes)
+                 "r"(meta_bytes + ent_bytes)
                  : "memory");
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_s),
@@ -299,37 +281,6 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
           : "memory");
   }
   const uint32_t nt = R.n_truss(), nbm = R.n_beam(), half = tid & 1u;
-#ifdef FEMGPU_BULK_RECORDS
-  // every record is contiguous and 16-byte aligned in global memory and in its slot: one TMA bulk copy
-  // per lane (the two lanes of a pair take the two parts of a record) instead of five LDGSTS, none of
-  // which goes through the LSU data pipe. The bytes are announced by thread 0 (expect_tx above).
-#pragma unroll
-  for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
-    const uint32_t fe = R.fe[j];
-    if (fe == 0xFFFFFFFFu) continue;
-    const uint32_t slot = j * (kT / 2) + (tid >> 1), family = fe >> 26, e = fe & 0x03FFFFFFu;
-    uint32_t dst = 0, bytes = 0;
-    const void* src = nullptr;
-    if (family == FEMGPU_PLATE) {
-      dst = rawp_s + (slot - nt - nbm) * 160u + half * 128u;
-      src = half ? static_cast<const void*>(A.plate_mat + size_t(e) * 4) : static_cast<const void*>(A.plate_rec + size_t(e) * 16);
-      bytes = half ? 32u : 128u;
-    } else if (family == FEMGPU_BEAM) {
-      dst = stage_s + R.beam_off() + (slot - nt) * uint32_t(kBeamSlotDoubles * 8) + half * 64u;
-      src = A.beam_rec + size_t(e) * 16 + half * 8;
-      bytes = 64u;
-    } else if (family == FEMGPU_TRUSS) {
-      dst = stage_s + R.truss_off() + slot * uint32_t(kTrussSlotDoubles * 8) + half * 16u;
-      src = reinterpret_cast<const double*>(A.truss_rec + e) + half * 2;
-      bytes = 16u;
-    }
-    if (bytes)
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-          "l"(src), "r"(bytes), "r"(mbar_s)
-          : "memory");
-  }
-#else
 #pragma unroll
   for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
     const uint32_t fe = R.fe[j];
@@ -353,7 +304,6 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
       cp_async16(dst, reinterpret_cast<const double*>(A.truss_rec + e) + half * 2);
     }  // family 3: placeholder of a remote contribution, no record
   }
-#endif
 }
 
 // phase A: one thread per plate (alternating between the two warps) turns the raw record into the
@@ -494,8 +444,13 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
   }
 }
 
+// registers per thread of the two-warp shape: 168 = three warps per SM sub-partition (5-6 CTAs per SM when
+// shared memory allows; 12 bytes of spill), 200 = two (4 CTAs per SM)
+#ifndef FEMGPU_MAXNREG64
+#define FEMGPU_MAXNREG64 168
+#endif
 template <int kT, bool kSplit>
-__global__ void __maxnreg__(kT == 64 ? 200 : 255)
+__global__ void __maxnreg__(kT == 64 ? FEMGPU_MAXNREG64 : 255)
 assemble_kernel(const AsmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tid = threadIdx.x, stride = gridDim.x;
@@ -710,7 +665,7 @@ int32_t run_assembly(Handle* h) {
   A.plate_mat = h->fd[FEMGPU_PLATE].mat.p;
   A.values = h->values.p;
   A.n_slabs = h->n_slabs;
-  auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
+  auto up = [](uint32_t b) { return (b + kSmemAlign - 1u) & ~(kSmemAlign - 1u); };
   A.smem_img = up(h->smem_img);
   A.smem_form = up(h->smem_form);
   A.smem_rawp = up(h->smem_rawp);

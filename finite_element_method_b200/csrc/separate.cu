@@ -318,6 +318,7 @@ void bc_clear(Handle* h) {
   h->bc.load_value.clear();
   h->bc.uploaded = false;
   h->sep.valid = false;
+  sol_invalidate(h);
 }
 
 void sep_release(Handle* h) {
@@ -360,6 +361,7 @@ int32_t bc_add(Handle* h, bool displacement, size_t n, const uint32_t* node_numb
     }
     h->bc.uploaded = false;
     h->sep.valid = false;
+    sol_invalidate(h);
   }
   return 0;
 }
@@ -382,6 +384,7 @@ int32_t load_add(Handle* h, int family, size_t n, const uint32_t* number, const 
     h->bc.load_value.push_back(value[k]);
     h->bc.uploaded = false;
     h->sep.valid = false;
+    sol_invalidate(h);
   }
   return 0;
 }
@@ -469,6 +472,7 @@ int32_t run_separate(Handle* h) {
     if (st) return st;
   }
   S.valid = false;
+  sol_invalidate(h);
   S.n_aa = S.n_bb = 0;
   for (auto& z : S.nnz) z = 0;
 

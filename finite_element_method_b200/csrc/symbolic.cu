@@ -281,7 +281,7 @@ __device__ __forceinline__ int family_group(uint32_t f) {
 __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* __restrict__ slabs,
                                  const uint32_t* __restrict__ cost, const uint32_t* __restrict__ cptr_ord,
                                  const uint32_t* __restrict__ contrib, WorkItem* __restrict__ items,
-                                 int32_t* __restrict__ flags) {
+                                 int32_t* __restrict__ flags, const BlockMeta* __restrict__ meta, int spread_banks) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_slabs) return;
   const SlabDesc d = slabs[k];
@@ -371,6 +371,67 @@ __global__ void work_item_kernel(uint32_t n_slabs, uint32_t threads, SlabDesc* _
   }
   close_run(b1);
   for (; n < threads; ++n) out[n] = WorkItem{0u, 0u, 0u, 0u};
+  // Lane order inside a warp. A block is flushed into the slab image with 16-byte stores, which the
+  // shared-memory pipe serves a quarter-warp (8 lanes) at a time: conflict-free when the eight blocks start in
+  // eight different 16-byte bank groups. Which group a block starts in is fixed by its place in the CSR rows
+  // ((seg0 / 2) mod 8; the rows of a block shift every lane alike), and blocks of equal cost sit in
+  // neighbouring lanes whatever their group: the diagonal blocks of eight grid nodes occupy four groups, two
+  // each. The warp's time only depends on WHICH items it holds, not on their lanes, so the items are dealt to
+  // the four quarter-warps greedily, each to the quarter where the fewest lanes flush the same group at the
+  // same loop trip. The chunks of a split block stay in adjacent lanes (they are merged with shuffles).
+  if (spread_banks && staged) {
+    for (uint32_t w0 = 0; w0 < threads; w0 += 32) {
+      WorkItem tmp[32];
+      unsigned char seen[4][16][8];
+      unsigned char slot_of[32], q_used[4] = {0, 0, 0, 0};
+      for (int q = 0; q < 4; ++q)
+        for (int t = 0; t < 16; ++t)
+          for (int g = 0; g < 8; ++g) seen[q][t][g] = 0;
+      bool ok = true;
+      for (uint32_t l = 0; l < 32; ++l) tmp[l] = out[w0 + l];
+      for (uint32_t l = 0; l < 32 && ok;) {
+        const WorkItem w = tmp[l];
+        const uint32_t n_blk = w.blk_count & 0xFFFFu;
+        const bool chunk = (w.blk_count & (1u << 24)) != 0;
+        const uint32_t len = chunk ? ((w.blk_count >> 20) & 3u) + 1u : 1u;
+        // flush events of the unit: (loop trip, bank group)
+        uint32_t ev_t[16], ev_g[16], n_ev = 0;
+        if (chunk) {
+          ev_t[0] = 15u;  // stored after the merge rounds, together with the other split blocks of the warp
+          ev_g[0] = (meta[w.blk_begin].seg0 >> 1) & 7u;
+          n_ev = 1;
+        } else {
+          for (uint32_t p = w.blk_begin; p < w.blk_begin + n_blk && n_ev < 16u; ++p) {
+            ev_t[n_ev] = min(14u, cptr_ord[p + 1] - cptr_ord[w.blk_begin]);
+            ev_g[n_ev] = (meta[p].seg0 >> 1) & 7u;
+            ++n_ev;
+          }
+        }
+        int best = -1;
+        uint32_t best_cost = 0xFFFFFFFFu;
+        for (int q = 0; q < 4; ++q) {
+          if (q_used[q] + len > 8u) continue;
+          uint32_t c = 0;
+          for (uint32_t e = 0; e < n_ev; ++e) c += seen[q][ev_t[e]][ev_g[e]];
+          if (c < best_cost || (c == best_cost && q_used[q] < q_used[best])) {
+            best = q;
+            best_cost = c;
+          }
+        }
+        if (best < 0) {
+          ok = false;
+          break;
+        }
+        for (uint32_t e = 0; e < n_ev; ++e) seen[best][ev_t[e]][ev_g[e]]++;
+        for (uint32_t j = 0; j < len; ++j) slot_of[l + j] = (unsigned char)(8u * best + q_used[best] + j);
+        q_used[best] = (unsigned char)(q_used[best] + len);
+        l += len;
+      }
+      if (!ok) continue;  // a split block did not fit any quarter: keep the order of this warp
+      for (uint32_t l = 0; l < 32; ++l) out[w0 + l] = WorkItem{0u, 0u, 0u, 0u};
+      for (uint32_t l = 0; l < 32; ++l) out[w0 + slot_of[l]] = tmp[l];
+    }
+  }
   if (max_round) {
     slabs[k].flags = d.flags | (max_round << 8);
     atomicMax(flags + 13, 1);  // some staged slab splits a block: the kernel variant with merge rounds is needed
@@ -1122,8 +1183,11 @@ int32_t run_symbolic(Handle* h) {
   }
   const uint32_t threads = uint32_t(h->asm_threads);
   SYM_CHECK(h->items.reserve(size_t(n_slabs) * threads));
+  int spread_banks = 0;
+  if (const char* q = getenv("FEMGPU_SPREAD_BANKS")) spread_banks = atoi(q);  // tuning knob
   work_item_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, threads, h->slabs.p, ocost.as<uint32_t>(),
-                                                         h->blk_cptr.p, h->contrib.p, h->items.p, h->d_flag.p);
+                                                         h->blk_cptr.p, h->contrib.p, h->items.p, h->d_flag.p,
+                                                         h->blk_meta.p, spread_banks);
   SYM_CHECK(h->items_c.reserve(size_t(n_slabs) * threads));
   compact_items_kernel<<<div_up(uint64_t(n_slabs) * threads, 256), 256, 0, s>>>(n_slabs, threads, h->slabs.p,
                                                                                 h->items.p, h->items_c.p);

@@ -23,6 +23,15 @@ from . import _lib
 
 TRUSS, BEAM, PLATE = 0, 1, 2
 
+# ElementForceComponent (methods_for_element_analysis.rs:5-21) of every value extract_elements_analysis_result
+# returns per element: truss.rs:325-328, beam.rs:967-987, plate.rs:1368-1401
+ELEMENT_RESULT_COMPONENTS = {
+    TRUSS: ("ForceR",),
+    BEAM: ("ForceR", "ForceS", "ForceT", "MomentR", "MomentS", "MomentS", "MomentS", "MomentT", "MomentT", "MomentT"),
+    PLATE: ("MembraneForceR", "MembraneForceS", "MembraneForceRS", "BendingMomentR", "BendingMomentS",
+            "BendingMomentRS", "ShearForceRT", "ShearForceST"),
+}
+
 
 class DOFParameter:
     """methods_for_bc_data_handle.rs:6-13"""
@@ -192,6 +201,17 @@ class FEM:
         self._check(self._L.femgpu_counts(self._h, *[C.byref(x) for x in v]))
         return tuple(int(x.value) for x in v)
 
+    def node_numbers(self):
+        """user labels of the nodes, index = insertion order"""
+        out = np.empty(self.counts()[0], np.uint32)
+        self._check(self._L.femgpu_get_numbers(self._h, -1, _p(out, _lib.u32p) if len(out) else None))
+        return out
+
+    def element_numbers(self, family: int):
+        out = np.empty(self.counts()[1 + family], np.uint32)
+        self._check(self._L.femgpu_get_numbers(self._h, family, _p(out, _lib.u32p) if len(out) else None))
+        return out
+
     # ------------------------------------------------------------------ assembly
     def symbolic(self):
         """One-time pattern + gather-map construction. Returns (n_rows, nnz)."""
@@ -289,6 +309,7 @@ class FEM:
         self._check(self._L.femgpu_separate_sparse(self._h, C.byref(na), C.byref(nb), _p(nnz, _lib.i64p)))
         ms = C.c_float()
         self._check(self._L.femgpu_last_separate_ms(self._h, C.byref(ms)))
+        self._sep_counts = (int(na.value), int(nb.value))
         if not copy_out:
             return int(na.value), int(nb.value), [int(x) for x in nnz], float(ms.value)
         ia, ib = np.empty(na.value, np.int64), np.empty(nb.value, np.int64)
@@ -303,6 +324,102 @@ class FEM:
         b = np.empty(na.value, np.float64)
         self._check(self._L.femgpu_separated_rhs(self._h, _p(b, _lib.dp), None))
         return SeparatedStiffnessMatrixSparse(ia, ib, quads, b, float(ms.value))
+
+    # ------------------------------------------------------------------ global analysis, element results
+    def _solve(self, preconditioner: int, max_iter: int, copy_out: bool):
+        it = C.c_int64()
+        self._check(self._L.femgpu_solve_pcg(self._h, preconditioner, int(max_iter), C.byref(it)))
+        if not copy_out:
+            return None, int(it.value)
+        return self.u_a_vector(), int(it.value)
+
+    def find_ua_vector_iterative_pcg_jacobi_sparse(self, max_iter: int, copy_out: bool = True):
+        """methods_for_global_analysis.rs:189-233 on the separated matrix the handle holds (the reference passes
+        it back in together with r_a / u_b; here they never left the device). Returns (u_a, iterations)."""
+        return self._solve(0, max_iter, copy_out)
+
+    def find_ua_vector_iterative_pcg_block_jacobi_sparse(self, max_iter: int, copy_out: bool = True):
+        """methods_for_global_analysis.rs:235-275 (blocks = the rows of one node, :121-147)"""
+        return self._solve(1, max_iter, copy_out)
+
+    def u_a_vector(self):
+        n = self._n_aa_bb()[0]
+        out = np.empty(n, np.float64)
+        self._check(self._L.femgpu_get_ua(self._h, _p(out, _lib.dp), None))
+        return out
+
+    def set_u_a_vector(self, u_a) -> None:
+        """install the solution of an external solver (e.g. a direct solve of K_aa) as u_a"""
+        u = _f64(u_a)
+        if len(u) != self._n_aa_bb()[0]:
+            raise ValueError("u_a has the wrong length")
+        self._check(self._L.femgpu_set_ua(self._h, _p(u, _lib.dp)))
+
+    def _n_aa_bb(self):
+        if getattr(self, "_sep_counts", None) is None:
+            raise FemError(-2, "no separated matrix: call separate_stiffness_matrix_sparse_iterative first")
+        return self._sep_counts
+
+    def solve_info(self):
+        it, res, ms = C.c_int64(), C.c_double(), C.c_float()
+        self._check(self._L.femgpu_solve_info(self._h, C.byref(it), C.byref(res), C.byref(ms)))
+        return int(it.value), float(res.value), float(ms.value)
+
+    def find_r_r_vector_sparse(self, copy_out: bool = True):
+        """methods_for_global_analysis.rs:334-360 (+ compose_global_analysis_result, :362-385, in the same call)"""
+        self._check(self._L.femgpu_global_analysis(self._h))
+        if not copy_out:
+            return None
+        out = np.empty(self._n_aa_bb()[1], np.float64)
+        self._check(self._L.femgpu_get_reactions(self._h, _p(out, _lib.dp), None))
+        return out
+
+    def compose_global_analysis_result(self) -> None:
+        """methods_for_global_analysis.rs:362-385: displacements[k_aa_indexes] = u_a, forces[k_bb_indexes] = r_r"""
+        self._check(self._L.femgpu_global_analysis(self._h))
+
+    def global_analysis_vectors(self):
+        """(displacements, forces), each [6 * nodes_number], after compose_global_analysis_result"""
+        n = 6 * self.nodes_number
+        d, f = np.empty(n, np.float64), np.empty(n, np.float64)
+        self._check(self._L.femgpu_get_global_result(self._h, _p(d, _lib.dp), _p(f, _lib.dp)))
+        return d, f
+
+    def extract_global_analysis_result(self):
+        """methods_for_global_analysis.rs:387-...: [(node_number, dof_parameter, displacement, load)], sorted by
+        (node insertion order, dof) — the reference iterates a HashMap, its order is unspecified"""
+        d, f = self.global_analysis_vectors()
+        out = []
+        for i, number in enumerate(self.node_numbers()):
+            for k in range(6):
+                out.append((int(number), k, float(d[6 * i + k]), float(f[6 * i + k])))
+        return out
+
+    def set_displacements_vector(self, displacements) -> None:
+        u = _f64(displacements)
+        if len(u) != 6 * self.nodes_number:
+            raise ValueError("displacements must hold 6 * nodes_number values")
+        self._check(self._L.femgpu_set_displacements(self._h, _p(u, _lib.dp)))
+
+    def element_results(self, family: int):
+        """rows = elements of `family` in insertion order, columns = the reference's components:
+        truss [n, 1], beam [n, 10], plate [n, 8]"""
+        n = self.counts()[1 + family]
+        k = ELEMENT_RESULT_COMPONENTS[family]
+        out = np.empty((n, len(k)), np.float64)
+        self._check(self._L.femgpu_element_results(self._h, family, _p(out, _lib.dp) if n else None, None))
+        return out
+
+    def extract_elements_analysis_result(self):
+        """methods_for_element_analysis.rs:27-58: [(element_number, [(component, value), ...])], trusses, then
+        beams, then plates, each family in insertion order"""
+        out = []
+        for family in (TRUSS, BEAM, PLATE):
+            vals = self.element_results(family)
+            names = ELEMENT_RESULT_COMPONENTS[family]
+            for number, row in zip(self.element_numbers(family), vals):
+                out.append((int(number), [(c, float(v)) for c, v in zip(names, row)]))
+        return out
 
     # ------------------------------------------------------------------ hooks
     def element_matrix(self, family: int, number: int):

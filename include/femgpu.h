@@ -76,7 +76,9 @@ enum {
   /* methods_for_separate_stiffness_matrix.rs:233-243, :257-259, :303-307 */
   FEMGPU_E_NO_STIFFNESS_FOR_DISPLACEMENT = 41,
   FEMGPU_E_NO_RESTRAINTS = 42,
-  FEMGPU_E_KAA_EMPTY = 43
+  FEMGPU_E_KAA_EMPTY = 43,
+  /* find_ua_vector_iterative_*: "PCG failed" (methods_for_global_analysis.rs:228,272) */
+  FEMGPU_E_SOLVER = 50
 };
 
 /* failures (<0) */
@@ -143,6 +145,9 @@ int32_t femgpu_validate(femgpu_t* h, int32_t* family, uint32_t* number, int32_t*
 /* counts of accepted entities */
 int32_t femgpu_counts(const femgpu_t* h, uint64_t* nodes, uint64_t* truss, uint64_t* beam,
                       uint64_t* plate);
+/* user labels in insertion order (index i = the i-th node / element added): family -1 = nodes
+ * [nodes], 0 / 1 / 2 = truss / beam / plate element numbers. Host bookkeeping only. */
+int32_t femgpu_get_numbers(const femgpu_t* h, int32_t family, uint32_t* out);
 
 /* ---- assembly ----------------------------------------------------------------------------- */
 
@@ -245,6 +250,48 @@ int32_t femgpu_get_separated_csr_device(femgpu_t* h, int32_t which, const int64_
 int32_t femgpu_separated_rhs(femgpu_t* h, double* b, const double** b_device);
 /* device milliseconds of the last femgpu_separate_sparse() */
 int32_t femgpu_last_separate_ms(femgpu_t* h, float* ms);
+
+/* ---- global analysis and element results (downstream of the separated matrix, all in HBM) ---- */
+
+#define FEMGPU_PCG_JACOBI 0
+#define FEMGPU_PCG_BLOCK_JACOBI 1
+
+/* FEM::find_ua_vector_iterative_pcg_jacobi_sparse / ..._pcg_block_jacobi_sparse
+ *                                                        methods_for_global_analysis.rs:189-275
+ * K_aa u_a = b (b = R_a - K_ab u_b of the last femgpu_separate_sparse), preconditioned conjugate
+ * gradients from u_a = 0 on the device CSR; block Jacobi groups the rows of one node
+ * (build_block_starts_from_k_aa_indexes, :121-147). Stops when ||r||_2 <= max(rel_tol ||b||_2, abs_tol);
+ * `iterations` = search directions used. The reference's arithmetic lives in the un-vendored crate
+ * iterative_solvers_smpl: parity is pinned on the reference's own test only (one iteration, u = 0.0015).
+ * Deterministic (fixed reduction trees, no atomics). FEMGPU_E_SOLVER when it does not converge. */
+int32_t femgpu_solve_pcg(femgpu_t* h, int32_t preconditioner, int64_t max_iter, int64_t* iterations);
+/* u_a [n_aa] of the last solve; femgpu_set_ua installs the result of an external solver instead */
+int32_t femgpu_get_ua(femgpu_t* h, double* u_a, const double** u_a_device);
+int32_t femgpu_set_ua(femgpu_t* h, const double* u_a);
+/* iterations, final ||r||_2 and device milliseconds of the last femgpu_solve_pcg (pointers may be NULL) */
+int32_t femgpu_solve_info(femgpu_t* h, int64_t* iterations, double* residual, float* ms);
+
+/* FEM::find_r_r_vector_sparse (r_r = K_ba u_a + K_bb u_b - R_b, methods_for_global_analysis.rs:100-137,
+ * :334-360) followed by FEM::compose_global_analysis_result (:362-385): displacements[k_aa_indexes] = u_a,
+ * forces[k_bb_indexes] = r_r. */
+int32_t femgpu_global_analysis(femgpu_t* h);
+/* r_r [n_bb]; either pointer may be NULL */
+int32_t femgpu_get_reactions(femgpu_t* h, double* r_r, const double** r_r_device);
+/* FEM::extract_global_analysis_result (:387-...): displacements / forces vectors [6 * nodes_number]
+ * (row 6 * node_index + dof); either pointer may be NULL */
+int32_t femgpu_get_global_result(femgpu_t* h, double* displacements, double* forces);
+/* installs a displacements vector [6 * nodes_number] from elsewhere (an external solver, a test) */
+int32_t femgpu_set_displacements(femgpu_t* h, const double* displacements);
+
+/* FEM::extract_elements_analysis_result            methods_for_element_analysis.rs:27-58
+ * for every element of `family`, in insertion order, from the displacements vector:
+ *   truss  1 value : ForceR                                              structs/truss.rs:281-333
+ *   beam  10 values: ForceR, ForceS, ForceT, MomentR, MomentS (node 1, average, node 2),
+ *                    MomentT (node 1, average, node 2)                   structs/beam.rs:803-993
+ *   plate  8 values: MembraneForceR, MembraneForceS, MembraneForceRS, BendingMomentR, BendingMomentS,
+ *                    BendingMomentRS, ShearForceRT, ShearForceST        structs/plate.rs:1196-1409
+ * out [n_elements][values] (element-major); either pointer may be NULL. */
+int32_t femgpu_element_results(femgpu_t* h, int32_t family, double* out, const double** out_device);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 

@@ -8,6 +8,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "femgpu.h"
@@ -73,6 +74,47 @@ class FEM {
     check(femgpu_get_csr(h_, m.row_ptr.data(), m.col_idx.data(), m.values.data()));
     return m;
   }
+  // ---- boundary conditions, separation, solve, results: the reference's sparse-iterative flow (tests/fem/test_fem.rs:83-225)
+  void add_displacement(uint32_t node_number, int dof_parameter, double value) {       // methods_for_bc_data_handle.rs:175
+    check(femgpu_add_displacement(h_, 1, &node_number, &dof_parameter, &value));
+  }
+  void add_concentrated_load(uint32_t node_number, int dof_parameter, double value) {  // methods_for_bc_data_handle.rs:31
+    check(femgpu_add_concentrated_load(h_, 1, &node_number, &dof_parameter, &value));
+  }
+  struct Separated {
+    int64_t n_aa = 0, n_bb = 0, nnz[4] = {0, 0, 0, 0};
+  };
+  // methods_for_separate_stiffness_matrix.rs:217; the quadrants stay in HBM (femgpu_get_separated_csr copies them out)
+  Separated separate_stiffness_matrix_sparse_iterative() {
+    Separated s;
+    check(femgpu_separate_sparse(h_, &s.n_aa, &s.n_bb, s.nnz));
+    sep_ = s;
+    return s;
+  }
+  // methods_for_global_analysis.rs:189 / :235 -> (u_a, iterations)
+  std::pair<std::vector<double>, int64_t> find_ua_vector_iterative_pcg_jacobi_sparse(int64_t max_iter) {
+    return solve(FEMGPU_PCG_JACOBI, max_iter);
+  }
+  std::pair<std::vector<double>, int64_t> find_ua_vector_iterative_pcg_block_jacobi_sparse(int64_t max_iter) {
+    return solve(FEMGPU_PCG_BLOCK_JACOBI, max_iter);
+  }
+  // find_r_r_vector_sparse (:334) + compose_global_analysis_result (:362)
+  std::vector<double> find_r_r_vector_sparse() {
+    check(femgpu_global_analysis(h_));
+    std::vector<double> r(size_t(sep_.n_bb));
+    check(femgpu_get_reactions(h_, r.data(), nullptr));
+    return r;
+  }
+  // extract_elements_analysis_result (methods_for_element_analysis.rs:27): values of one family, element-major
+  // (1 / 10 / 8 per element, component order of femgpu.h)
+  std::vector<double> element_results(int family) {
+    uint64_t n[4] = {0, 0, 0, 0};
+    check(femgpu_counts(h_, &n[0], &n[1], &n[2], &n[3]));
+    static const size_t comps[3] = {1, 10, 8};
+    std::vector<double> out(size_t(n[1 + family]) * comps[family]);
+    check(femgpu_element_results(h_, family, out.data(), nullptr));
+    return out;
+  }
   femgpu_t* handle() { return h_; }
 
  private:
@@ -85,7 +127,15 @@ class FEM {
     check(femgpu_rotation_elements(h_, family, number, out.data()));
     return out;
   }
+  std::pair<std::vector<double>, int64_t> solve(int preconditioner, int64_t max_iter) {
+    int64_t it = 0;
+    check(femgpu_solve_pcg(h_, preconditioner, max_iter, &it));
+    std::vector<double> u(size_t(sep_.n_aa));
+    check(femgpu_get_ua(h_, u.data(), nullptr));
+    return {std::move(u), it};
+  }
   femgpu_t* h_ = nullptr;
+  Separated sep_;
 };
 
 }  // namespace femgpu

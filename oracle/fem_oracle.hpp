@@ -1008,6 +1008,124 @@ inline void plate_surface_load_nodal(const V p1[3], const V p2[3], const V p3[3]
 }
 
 // --------------------------------------------------------------------------
+// Element result recovery: forces / moments from the nodal displacements.
+// `u` below is the element's slice of the global displacement vector, node by node, as the
+// reference gathers it (displacements[node_index * NODE_DOF + i]).
+// --------------------------------------------------------------------------
+
+// Truss::extract_element_analysis_result (truss.rs:281-333): u = [u1 (3), u2 (3)] -> ForceR
+template <typename V>
+inline V truss_element_result(const V p1[3], const V p2[3], V young_modulus, V area, bool has_area_2,
+                              V area_2, V rel_tol, V abs_tol, const V u[6]) {
+  V q[9];
+  truss_find_rotation_matrix_elements(p1, p2, rel_tol, abs_tol, q);  // stored at creation, truss.rs:238
+  Mat<V> ug(6, 1);
+  for (int i = 0; i < 6; ++i) ug.at(i, 0) = u[i];
+  Mat<V> ul = compose_rotation_matrix_3dof(q, 2).multiply(ug);
+  const V ips[1][2] = {{V(0.0f), V(2.0f)}};  // truss.rs:244
+  Mat<V> b(1, 6);
+  V area_sum = V(0.0f);
+  for (auto& ip : ips) {
+    b = b.add(truss_strain_displacement_matrix_at_r(p1, p2, ip[0]));
+    area_sum += truss_area_at_r(area, has_area_2, area_2, ip[0]);
+  }
+  Mat<V> strain = b.multiply(ul);
+  Mat<V> force = strain.multiply_by_scalar(young_modulus * area_sum / V(1.0f));  // / n_ip
+  return force.at(0, 0);
+}
+
+// Beam::extract_element_analysis_result (beam.rs:803-993): u = [node 1 (6), node 2 (6)] ->
+// ForceR, ForceS, ForceT, MomentR, MomentS (node 1, average, node 2), MomentT (node 1, average, node 2)
+template <typename V>
+inline void beam_element_result(const V p1[3], const V p2[3], V young_modulus, V poisson_ratio, V area,
+                                V i11, V i22, V i12, V it, V shear_factor, const V axis1[3], V rel_tol,
+                                V abs_tol, const V u[12], V out[10]) {
+  V i11_p, i22_p, angle, q[9];
+  find_principal_moments_of_inertia(i11, i22, i12, rel_tol, i11_p, i22_p, angle);  // beam.rs:711
+  beam_find_rotation_matrix_elements(p1, p2, axis1, angle, rel_tol, abs_tol, q);
+  Mat<V> ug(12, 1);
+  for (int i = 0; i < 12; ++i) ug.at(i, 0) = u[i];
+  Mat<V> ul = compose_rotation_matrix_6dof(q, 2).multiply(ug);
+  const V ips[1][2] = {{V(0.0f), V(2.0f)}};  // beam.rs:729
+  const V n_ip = V(1.0f);
+  V shear_modulus = young_modulus / (V(2.0f) * (V(1.0f) + poisson_ratio));
+  const V cs[6] = {young_modulus * area / n_ip,
+                   shear_modulus * area * shear_factor / n_ip,
+                   shear_modulus * area * shear_factor / n_ip,
+                   shear_modulus * it / n_ip,
+                   young_modulus * i22_p / n_ip,
+                   young_modulus * i11_p / n_ip};
+  V f[6];
+  for (int w = 0; w < 6; ++w) {
+    Mat<V> b(1, 12);
+    for (auto& ip : ips) b = b.add(beam_b_row(p1, p2, ip[0], w));
+    f[w] = b.multiply(ul).multiply_by_scalar(cs[w]).at(0, 0);
+  }
+  V len = v3_norm(find_2n_element_vector(p1, p2));
+  const V force_s = f[1], force_t = f[2], moment_s_average = f[4], moment_t_average = f[5];
+  out[0] = f[0];
+  out[1] = force_s;
+  out[2] = force_t;
+  out[3] = f[3];
+  out[4] = moment_s_average + len * force_t / V(2.0f);
+  out[5] = moment_s_average;
+  out[6] = moment_s_average - len * force_t / V(2.0f);
+  out[7] = moment_t_average + len * force_s / V(2.0f);
+  out[8] = moment_t_average;
+  out[9] = moment_t_average - len * force_s / V(2.0f);
+}
+
+// Plate::extract_element_analysis_result (plate.rs:1196-1409): u = 4 nodes x 6 ->
+// MembraneForceR, MembraneForceS, MembraneForceRS, BendingMomentR, BendingMomentS, BendingMomentRS,
+// ShearForceRT, ShearForceST. The strain-displacement matrices are summed over the four NODES
+// (r, s = +-1), not the Gauss points.
+template <typename V>
+inline void plate_element_result(const V p1[3], const V p2[3], const V p3[3], const V p4[3],
+                                 V young_modulus, V poisson_ratio, V thickness, V shear_factor, V rel_tol,
+                                 V abs_tol, const V u[24], V out[8]) {
+  PlateGeom<V> g;
+  find_rotation_matrix_elements_of_quadrilateral(p2, p3, p4, rel_tol, abs_tol, g.q);
+  extract_transformed_directions_of_nodes(p1, p2, p3, p4, g);
+  Mat<V> ug(24, 1);
+  for (int i = 0; i < 24; ++i) ug.at(i, 0) = u[i];
+  Mat<V> ul = compose_rotation_matrix_6dof(g.q, 4).multiply(ug);
+  const V one = V(1.0f), two = V(2.0f), zero = V(0.0f), m1 = V(-1.0f);
+  const V rs[4][2] = {{one, one}, {m1, one}, {m1, m1}, {one, m1}};
+  const V n_nodes = V(4.0f);
+
+  V c_multiplier_mem = young_modulus / (one - poisson_ratio * poisson_ratio);
+  Mat<V> c_mem = Mat<V>(3, 3, {one, poisson_ratio, zero, poisson_ratio, one, zero, zero, zero,
+                               (one - poisson_ratio) / two})
+                     .multiply_by_scalar(c_multiplier_mem);
+  Mat<V> b_mem(3, 24);
+  for (auto& n : rs) b_mem = b_mem.add(plate_b_mem(g, n[0], n[1]));
+  Mat<V> f_mem = c_mem.multiply(b_mem.multiply(ul)).multiply_by_scalar(thickness / n_nodes);
+
+  V c_multiplier_bend = young_modulus * thickness / (two * (one - poisson_ratio * poisson_ratio));
+  Mat<V> c_bend = Mat<V>(3, 3, {one, poisson_ratio, zero, poisson_ratio, one, zero, zero, zero,
+                                (one - poisson_ratio) / two})
+                      .multiply_by_scalar(c_multiplier_bend);
+  Mat<V> b_bend(3, 24);
+  for (auto& n : rs) b_bend = b_bend.add(plate_b_bend(g, n[0], n[1]));
+  Mat<V> f_bend = c_bend.multiply(b_bend.multiply(ul)).multiply_by_scalar(thickness * thickness / V(24.0f));
+
+  V c_multiplier_shear = young_modulus / (two * (one + poisson_ratio));
+  Mat<V> c_shear = Mat<V>(2, 2, {one, zero, zero, one}).multiply_by_scalar(c_multiplier_shear);
+  Mat<V> b_shear(2, 24);
+  for (auto& n : rs) b_shear = b_shear.add(plate_b_shear(g, n[0], n[1]));
+  Mat<V> f_shear = c_shear.multiply(b_shear.multiply(ul)).multiply_by_scalar(thickness * shear_factor / n_nodes);
+
+  out[0] = f_mem.at(0, 0);
+  out[1] = f_mem.at(1, 0);
+  out[2] = f_mem.at(2, 0);
+  out[3] = f_bend.at(1, 0);  // BendingMomentR takes row 1, BendingMomentS row 0 (plate.rs:1384-1391)
+  out[4] = f_bend.at(0, 0);
+  out[5] = f_bend.at(2, 0);
+  out[6] = f_shear.at(0, 0);
+  out[7] = f_shear.at(1, 0);
+}
+
+// --------------------------------------------------------------------------
 // Global matrix: position-keyed map + the zero-skip block scatter
 // (methods_for_truss_data_handle.rs:93-123, methods_for_beam_data_handle.rs:107-137,
 //  methods_for_plate_data_handle.rs:134-212; add_value = entry(pos).or_insert(0) += v)

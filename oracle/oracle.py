@@ -243,6 +243,19 @@ def fast_assemble(mesh, n_threads=0, repeats=1, want_coo=False):
     return out
 
 
+def element_results(mesh, u):
+    """extract_elements_analysis_result (methods_for_element_analysis.rs:27-58) of a mesh dict for the global
+    displacement vector u (6 per node): (truss [nt], beam [nb, 10], plate [np, 8]) in the reference's
+    component order (truss.rs:325-328, beam.rs:967-987, plate.rs:1368-1401)."""
+    args, keep = _mesh_args(mesh)
+    nt, nb = len(mesh["t_n1"]), len(mesh["b_n1"])
+    npl = len(mesh["p_n"][0]) if len(mesh["p_n"]) else 0
+    u, pu = _d(u)
+    ot = np.zeros(nt); ob = np.zeros((nb, 10)); op = np.zeros((npl, 8))
+    lib().oracle_element_results(*args, pu, ot.ctypes.data_as(_dp), ob.ctypes.data_as(_dp), op.ctypes.data_as(_dp))
+    return ot, ob, op
+
+
 def faithful_time(mesh):
     """Seconds for the single-thread faithful add_* loop over the whole mesh (plates, beams, trusses)."""
     args, keep = _mesh_args(mesh)
@@ -318,3 +331,91 @@ def separate_sparse(n_dof, rows, cols, vals, constrained, node_numbers=None, for
         np.subtract.at(b, i, x * u_b[j])                     # find_b_sparse (row order; the reference's is unspecified)
         out["b"] = b
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Global analysis downstream of the separation (restatement, numpy): the iterative solve, the reactions
+# and the composed result vectors.
+#   find_ua_vector_iterative_pcg_jacobi_sparse / ..._block_jacobi_sparse  methods_for_global_analysis.rs:189-275
+#   build_block_starts_from_k_aa_indexes :121-147, find_r_r_sparse :100-137, compose_global_analysis_result :362-385
+# The PCG arithmetic itself lives in the un-vendored crate iterative_solvers_smpl 0.1.5: what is restated is
+# the textbook preconditioned conjugate gradient from x0 = 0, stopping when ||r||_2 <= max(rel_tol ||b||_2,
+# abs_tol), the count being the number of search directions used. PARITY UNPINNED beyond the reference's own
+# test model (iterations == 1, u = 0.0015; src/tests/fem/test_fem.rs:83-225), which tests/ check.
+# ---------------------------------------------------------------------------------------------
+def block_starts_from_k_aa_indexes(k_aa_indexes):
+    """methods_for_global_analysis.rs:121-147: local row where the rows of the next node begin"""
+    starts = []
+    current = None
+    for i, g in enumerate(k_aa_indexes):
+        node = int(g) // 6
+        if node != current:
+            starts.append(i)
+            current = node
+    return starts
+
+
+def pcg(n, k_aa, b, max_iter, rel_tol, abs_tol, block_starts=None):
+    """k_aa = (i, j, value) triplets of K_aa. Returns (u_a, iterations). Jacobi when block_starts is None."""
+    import scipy.sparse as sp
+    i, j, v = k_aa
+    A = sp.csr_matrix((np.asarray(v, np.float64), (np.asarray(i), np.asarray(j))), shape=(n, n))
+    b = np.asarray(b, np.float64)
+    if block_starts is None:
+        dinv = 1.0 / A.diagonal()
+
+        def minv(r):
+            return dinv * r
+    else:
+        Ad = A.toarray() if n <= 4096 else None
+        bounds = list(block_starts) + [n]
+        invs = []
+        for s, e in zip(bounds[:-1], bounds[1:]):
+            blk = Ad[s:e, s:e] if Ad is not None else A[s:e, s:e].toarray()
+            invs.append((s, e, np.linalg.inv(blk)))
+
+        def minv(r):
+            z = np.empty_like(r)
+            for s, e, m in invs:
+                z[s:e] = m @ r[s:e]
+            return z
+    x = np.zeros(n)
+    r = b.copy()
+    tol = max(rel_tol * np.sqrt(b @ b), abs_tol)
+    if np.sqrt(r @ r) <= tol:
+        return x, 0
+    z = minv(r)
+    p = z.copy()
+    rz = r @ z
+    for k in range(max_iter):
+        ap = A @ p
+        alpha = rz / (p @ ap)
+        x = x + alpha * p
+        r = r - alpha * ap
+        if np.sqrt(r @ r) <= tol:
+            return x, k + 1
+        z = minv(r)
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    raise SeparationError(f"PCG did not converge in {max_iter} iterations")
+
+
+def reactions(sep, u_a, forces, displacements):
+    """find_r_r_sparse: r_r = K_ba u_a + K_bb u_b - R_b (each product summed in (row, column) order)"""
+    n_bb = sep["n_bb"]
+    u_b = np.asarray(displacements, np.float64)[sep["k_bb_indexes"]]
+    y_ba = np.zeros(n_bb); y_bb = np.zeros(n_bb)
+    i, j, x = sep["k_ba"]
+    np.add.at(y_ba, i, x * np.asarray(u_a)[j])
+    i, j, x = sep["k_bb"]
+    np.add.at(y_bb, i, x * u_b[j])
+    return y_ba + y_bb - np.asarray(forces, np.float64)[sep["k_bb_indexes"]]
+
+
+def compose_global_analysis_result(sep, u_a, r_r, forces, displacements):
+    d = np.asarray(displacements, np.float64).copy()
+    f = np.asarray(forces, np.float64).copy()
+    d[sep["k_aa_indexes"]] = u_a
+    f[sep["k_bb_indexes"]] = r_r
+    return d, f

@@ -110,20 +110,14 @@ int oracle_reference_truss_test_f32(float* k00, float* u2x, float* r1x, float* f
   float ra = 100.0f;
   float ua = ra / kaa;           // 1x1 LDL^T
   float rr = kba * ua;           // u_b = 0, R_b = 0
-  // truss.rs:281-333: local displacements = R * [u1; u2], strain = B * u_local, force = E*A*strain
-  Mat<float> rm = compose_rotation_matrix_3dof(o.q, 2);
-  Mat<float> ug(6, 1);
-  ug.at(3, 0) = ua;
-  Mat<float> ul = rm.multiply(ug);
-  Mat<float> b = Mat<float>(1, 6).add(truss_strain_displacement_matrix_at_r(p1, p2, 0.0f));
-  float area = 0.0f;
-  area += truss_area_at_r(2.0f, false, 0.0f, 0.0f);
-  Mat<float> strain = b.multiply(ul);
-  Mat<float> force = strain.multiply_by_scalar(1e6f * area / 1.0f);
+  // truss.rs:281-333 (truss_element_result): local displacements = R * [u1; u2], strain = B * u_local,
+  // force = E * A * strain
+  const float ue[6] = {0.0f, 0.0f, 0.0f, ua, 0.0f, 0.0f};
+  const float force_value = truss_element_result<float>(p1, p2, 1e6f, 2.0f, false, 0.0f, 1e-4f, 1e-12f, ue);
   *k00 = kaa;
   *u2x = ua;
   *r1x = rr;
-  *force_r = force.at(0, 0);
+  *force_r = force_value;
   return OK;
 }
 
@@ -243,6 +237,56 @@ void oracle_model_get_coo(void* h, int64_t* rows, int64_t* cols, double* vals) {
     rows[i] = int64_t(v[i].first >> 32);
     cols[i] = int64_t(v[i].first & 0xffffffffu);
     vals[i] = v[i].second;
+  }
+}
+
+// ---------------------------------------------------------------- element result recovery
+// extract_elements_analysis_result (methods_for_element_analysis.rs:27-58) over a whole mesh: `u` is the
+// global displacement vector (6 per node, node index order). out_t [n_truss], out_b [n_beam][10],
+// out_p [n_plate][8] in the component order of truss.rs:325-328, beam.rs:967-987, plate.rs:1368-1401.
+void oracle_element_results(int64_t n_nodes, const double* x, const double* y, const double* z,
+                            int64_t n_truss, const uint32_t* t_n1, const uint32_t* t_n2,
+                            const double* t_E, const double* t_A, const double* t_A2,
+                            int64_t n_beam, const uint32_t* b_n1, const uint32_t* b_n2,
+                            const double* b_props, const double* b_axis, int64_t n_plate,
+                            const uint32_t* p_n, const double* p_props, double rel_tol,
+                            double abs_tol, const double* u, double* out_t, double* out_b, double* out_p) {
+  auto xyz = [&](uint32_t i, double p[3]) { p[0] = x[i]; p[1] = y[i]; p[2] = z[i]; };
+  for (int64_t e = 0; e < n_truss; ++e) {
+    double p1[3], p2[3], ue[6];
+    xyz(t_n1[e], p1);
+    xyz(t_n2[e], p2);
+    for (int i = 0; i < 3; ++i) {
+      ue[i] = u[size_t(t_n1[e]) * NODE_DOF + i];
+      ue[3 + i] = u[size_t(t_n2[e]) * NODE_DOF + i];
+    }
+    const bool has2 = t_A2 && !std::isnan(t_A2[e]);
+    out_t[e] = truss_element_result<double>(p1, p2, t_E[e], t_A[e], has2, has2 ? t_A2[e] : 0.0, rel_tol, abs_tol, ue);
+  }
+  for (int64_t e = 0; e < n_beam; ++e) {
+    double p1[3], p2[3], ue[12];
+    xyz(b_n1[e], p1);
+    xyz(b_n2[e], p2);
+    for (int i = 0; i < 6; ++i) {
+      ue[i] = u[size_t(b_n1[e]) * NODE_DOF + i];
+      ue[6 + i] = u[size_t(b_n2[e]) * NODE_DOF + i];
+    }
+    const double ax[3] = {b_axis[e], b_axis[n_beam + e], b_axis[2 * n_beam + e]};
+    const double* bp = b_props;
+    beam_element_result<double>(p1, p2, bp[e], bp[n_beam + e], bp[2 * n_beam + e], bp[3 * n_beam + e],
+                                bp[4 * n_beam + e], bp[5 * n_beam + e], bp[6 * n_beam + e], bp[7 * n_beam + e],
+                                ax, rel_tol, abs_tol, ue, out_b + 10 * e);
+  }
+  for (int64_t e = 0; e < n_plate; ++e) {
+    double p[4][3], ue[24];
+    for (int a = 0; a < 4; ++a) {
+      const uint32_t n = p_n[a * n_plate + e];
+      xyz(n, p[a]);
+      for (int i = 0; i < 6; ++i) ue[6 * a + i] = u[size_t(n) * NODE_DOF + i];
+    }
+    plate_element_result<double>(p[0], p[1], p[2], p[3], p_props[e], p_props[n_plate + e],
+                                 p_props[2 * n_plate + e], p_props[3 * n_plate + e], rel_tol, abs_tol, ue,
+                                 out_p + 8 * e);
   }
 }
 

@@ -8,7 +8,8 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
     for (file, extra) in [("api.cu", None), ("prep.cu", Some("-fmad=false")), ("symbolic.cu", None),
-                          ("numeric.cu", None), ("dist.cu", None), ("separate.cu", None)] {
+                          ("numeric.cu", None), ("dist.cu", None), ("separate.cu", None),
+                          ("results.cu", Some("-fmad=false")), ("solve.cu", None)] {
         let obj = out.join(file).with_extension("o");
         let mut c = Command::new(&nvcc);
         c.args(["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -34,7 +34,31 @@ extern "C" {
     fn femgpu_get_separated_indexes(h: *mut FemGpu, k_aa_indexes: *mut i64, k_bb_indexes: *mut i64) -> i32;
     fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_separated_rhs(h: *mut FemGpu, b: *mut f64, b_device: *mut *const f64) -> i32;
+    fn femgpu_counts(h: *const FemGpu, nodes: *mut u64, truss: *mut u64, beam: *mut u64, plate: *mut u64) -> i32;
+    fn femgpu_get_numbers(h: *const FemGpu, family: i32, out: *mut u32) -> i32;
+    fn femgpu_solve_pcg(h: *mut FemGpu, preconditioner: i32, max_iter: i64, iterations: *mut i64) -> i32;
+    fn femgpu_get_ua(h: *mut FemGpu, u_a: *mut f64, u_a_device: *mut *const f64) -> i32;
+    fn femgpu_global_analysis(h: *mut FemGpu) -> i32;
+    fn femgpu_get_reactions(h: *mut FemGpu, r_r: *mut f64, r_r_device: *mut *const f64) -> i32;
+    fn femgpu_get_global_result(h: *mut FemGpu, displacements: *mut f64, forces: *mut f64) -> i32;
+    fn femgpu_element_results(h: *mut FemGpu, family: i32, out: *mut f64, out_device: *mut *const f64) -> i32;
 }
+
+/// methods_for_element_analysis.rs:5-21
+#[derive(Debug, Clone, Copy, PartialEq, Eq, PartialOrd, Ord)]
+pub enum ElementForceComponent {
+    ForceR, ForceS, ForceT, MembraneForceR, MembraneForceS, MembraneForceRS, ShearForceRT, ShearForceST,
+    MomentR, MomentS, MomentT, BendingMomentR, BendingMomentS, BendingMomentRS,
+}
+use ElementForceComponent::*;
+/// component of every value femgpu_element_results returns per element (truss.rs:325-328, beam.rs:967-987,
+/// plate.rs:1368-1401)
+const COMPONENTS: [&[ElementForceComponent]; 3] = [
+    &[ForceR],
+    &[ForceR, ForceS, ForceT, MomentR, MomentS, MomentS, MomentS, MomentT, MomentT, MomentT],
+    &[MembraneForceR, MembraneForceS, MembraneForceRS, BendingMomentR, BendingMomentS, BendingMomentRS,
+      ShearForceRT, ShearForceST],
+];
 
 /// methods_for_bc_data_handle.rs:6-13
 #[derive(Debug, Clone, Copy, PartialEq, Eq, PartialOrd, Ord)]
@@ -49,7 +73,7 @@ pub struct SeparatedStiffnessMatrixSparse {
     pub b: Vec<f64>,
 }
 
-pub struct FEM { h: *mut FemGpu }
+pub struct FEM { h: *mut FemGpu, nodes_number: u32 }
 
 impl FEM {
     fn check(&self, st: i32) -> Result<(), String> {
@@ -61,10 +85,10 @@ impl FEM {
         let mut h = std::ptr::null_mut();
         let st = unsafe { femgpu_create(&mut h, rel_tol, abs_tol, nodes_number, 0) };
         assert!(st == 0, "femgpu_create failed: no CUDA device (there is no CPU fallback)");
-        FEM { h }
+        FEM { h, nodes_number }
     }
     /// fem.rs:155
-    pub fn reset(&mut self, nodes_number: u32) { unsafe { femgpu_reset(self.h, nodes_number); } }
+    pub fn reset(&mut self, nodes_number: u32) { unsafe { femgpu_reset(self.h, nodes_number); } self.nodes_number = nodes_number; }
     /// methods_for_node_data_handle.rs:66
     pub fn add_node(&mut self, number: u32, x: f64, y: f64, z: f64) -> Result<(), String> {
         self.check(unsafe { femgpu_add_nodes(self.h, 1, &number, &x, &y, &z) })
@@ -162,6 +186,65 @@ impl FEM {
         let mut b = vec![0f64; n_aa as usize];
         self.check(unsafe { femgpu_separated_rhs(self.h, b.as_mut_ptr(), std::ptr::null_mut()) })?;
         Ok(SeparatedStiffnessMatrixSparse { k_aa_indexes: ia, k_bb_indexes: ib, quadrants, b })
+    }
+}
+
+impl FEM {
+    /// methods_for_global_analysis.rs:189 / :235 — K_aa, r_a and u_b never left the device, so the three
+    /// arguments of the reference collapse into the handle. Returns (u_a, iterations).
+    pub fn find_ua_vector_iterative_pcg_jacobi_sparse(&mut self, n_aa: usize, max_iter: usize) -> Result<(Vec<f64>, usize), String> {
+        self.solve(0, n_aa, max_iter)
+    }
+    pub fn find_ua_vector_iterative_pcg_block_jacobi_sparse(&mut self, n_aa: usize, max_iter: usize) -> Result<(Vec<f64>, usize), String> {
+        self.solve(1, n_aa, max_iter)
+    }
+    fn solve(&mut self, preconditioner: i32, n_aa: usize, max_iter: usize) -> Result<(Vec<f64>, usize), String> {
+        let mut it = 0i64;
+        self.check(unsafe { femgpu_solve_pcg(self.h, preconditioner, max_iter as i64, &mut it) })?;
+        let mut u_a = vec![0f64; n_aa];
+        self.check(unsafe { femgpu_get_ua(self.h, u_a.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok((u_a, it as usize))
+    }
+    /// methods_for_global_analysis.rs:334 (find_r_r_vector_sparse) + :362 (compose_global_analysis_result)
+    pub fn find_r_r_vector_sparse(&mut self, n_bb: usize) -> Result<Vec<f64>, String> {
+        self.check(unsafe { femgpu_global_analysis(self.h) })?;
+        let mut r_r = vec![0f64; n_bb];
+        self.check(unsafe { femgpu_get_reactions(self.h, r_r.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok(r_r)
+    }
+    /// methods_for_global_analysis.rs:387 — (node_number, dof, displacement, load) per node and DOF
+    pub fn extract_global_analysis_result(&mut self) -> Result<Vec<(u32, DOFParameter, f64, f64)>, String> {
+        let mut n = [0u64; 4];
+        self.check(unsafe { femgpu_counts(self.h, &mut n[0], &mut n[1], &mut n[2], &mut n[3]) })?;
+        let mut numbers = vec![0u32; n[0] as usize];
+        self.check(unsafe { femgpu_get_numbers(self.h, -1, numbers.as_mut_ptr()) })?;
+        let rows = 6 * self.nodes_number as usize;
+        let (mut d, mut f) = (vec![0f64; rows], vec![0f64; rows]);
+        self.check(unsafe { femgpu_get_global_result(self.h, d.as_mut_ptr(), f.as_mut_ptr()) })?;
+        const DOFS: [DOFParameter; 6] = [DOFParameter::X, DOFParameter::Y, DOFParameter::Z, DOFParameter::ThX,
+                                         DOFParameter::ThY, DOFParameter::ThZ];
+        let mut out = Vec::with_capacity(6 * numbers.len());
+        for (i, number) in numbers.iter().enumerate() {
+            for k in 0..6 { out.push((*number, DOFS[k], d[6 * i + k], f[6 * i + k])); }
+        }
+        Ok(out)
+    }
+    /// methods_for_element_analysis.rs:27 — trusses, beams, plates; each family in insertion order
+    pub fn extract_elements_analysis_result(&mut self) -> Result<Vec<(u32, Vec<(ElementForceComponent, f64)>)>, String> {
+        let mut n = [0u64; 4];
+        self.check(unsafe { femgpu_counts(self.h, &mut n[0], &mut n[1], &mut n[2], &mut n[3]) })?;
+        let mut out = Vec::new();
+        for family in 0..3usize {
+            let (count, comps) = (n[1 + family] as usize, COMPONENTS[family]);
+            let mut numbers = vec![0u32; count];
+            let mut vals = vec![0f64; count * comps.len()];
+            self.check(unsafe { femgpu_get_numbers(self.h, family as i32, numbers.as_mut_ptr()) })?;
+            self.check(unsafe { femgpu_element_results(self.h, family as i32, vals.as_mut_ptr(), std::ptr::null_mut()) })?;
+            for (e, number) in numbers.iter().enumerate() {
+                out.push((*number, comps.iter().cloned().zip(vals[e * comps.len()..(e + 1) * comps.len()].iter().cloned()).collect()));
+            }
+        }
+        Ok(out)
     }
 }
 

@@ -141,3 +141,99 @@ def test_validation_codes():
     with pytest.raises(O.OracleError) as e:
         O.plate([0.2, 0.2, 0], *flat[1:], 1, .3, 1, 1)                      # re-entrant corner
     assert e.value.code == 13
+
+
+# ---- element result recovery and the iterative solve -------------------------------
+def _mesh_one(kind, p, props, axis=None):
+    from finite_element_method_b200 import meshes  # noqa: F401  (mesh dict layout)
+    p = np.asarray(p, float)
+    m = {"name": kind, "rel_tol": 1e-4, "abs_tol": 1e-12, "x": p[:, 0], "y": p[:, 1], "z": p[:, 2],
+         "t_n1": np.zeros(0, np.uint32), "t_n2": np.zeros(0, np.uint32), "t_E": np.zeros(0), "t_A": np.zeros(0),
+         "b_n1": np.zeros(0, np.uint32), "b_n2": np.zeros(0, np.uint32), "b_props": np.zeros((8, 0)),
+         "b_axis": np.zeros((3, 0)), "p_n": np.zeros((4, 0), np.uint32), "p_props": np.zeros((4, 0))}
+    if kind == "truss":
+        m.update(t_n1=np.array([0], np.uint32), t_n2=np.array([1], np.uint32), t_E=np.array([props[0]]),
+                 t_A=np.array([props[1]]))
+        if len(props) > 2:
+            m["t_A2"] = np.array([props[2]])
+    elif kind == "beam":
+        m.update(b_n1=np.array([0], np.uint32), b_n2=np.array([1], np.uint32),
+                 b_props=np.asarray(props, float).reshape(8, 1), b_axis=np.asarray(axis, float).reshape(3, 1))
+    else:
+        m.update(p_n=np.arange(4, dtype=np.uint32).reshape(4, 1), p_props=np.asarray(props, float).reshape(4, 1))
+    return m
+
+
+def test_truss_result_is_axial_force():
+    # truss.rs:281-333: N = E A (u2 - u1).n / L for any orientation (tapered: area at r = 0)
+    rng = np.random.default_rng(5)
+    for tapered in (False, True):
+        p = rng.normal(size=(2, 3))
+        u = rng.normal(size=12) * 1e-3
+        props = (2.1e11, 1e-4, 2e-4) if tapered else (2.1e11, 1e-4)
+        ft, _, _ = O.element_results(_mesh_one("truss", p, props), u)
+        L = np.linalg.norm(p[1] - p[0]); n = (p[1] - p[0]) / L
+        ref = 2.1e11 * (1.5e-4 if tapered else 1e-4) * ((u[6:9] - u[0:3]) @ n) / L
+        assert abs(ft[0] - ref) <= 1e-12 * abs(ref) * 10
+
+
+def test_beam_result_cantilever_tip_load():
+    # solve the one-element cantilever for a tip load P along local v and recover the section forces:
+    # ForceS = P (constant shear), MomentT (average) = P L / 2 = the moment at mid-span, node values +- P L / 2
+    E, nu, A, I11, I22, It, ks, L, P = 2.1e11, 0.3, 1e-2, 8e-6, 4e-6, 1e-5, 5 / 6, 2.0, 1000.0
+    props = [E, nu, A, I11, I22, 0.0, It, ks]
+    q, pr, kl, kg = O.beam([0, 0, 0], [L, 0, 0], *props, [0, 0, 1])
+    f = np.zeros(6); f[1] = P
+    u = np.zeros(12); u[6:] = np.linalg.solve(kg[6:, 6:], f)
+    _, fb, _ = O.element_results(_mesh_one("beam", [[0, 0, 0], [L, 0, 0]], props, [0, 0, 1]), u)
+    fb = fb[0]
+    assert abs(fb[0]) < 1e-6 * P and abs(abs(fb[1]) - P) < 1e-9 * P and abs(fb[2]) < 1e-6 * P
+    assert abs(abs(fb[8]) - P * L / 2) < 1e-9 * P * L                 # MomentT average
+    assert abs(fb[7] - fb[9]) == pytest.approx(abs(L * fb[1]), rel=1e-12)   # node 1 / node 2 differ by L * ForceS
+    assert min(abs(fb[7]), abs(fb[9])) < 1e-9 * P * L                 # free end carries no moment
+
+
+def test_plate_result_constant_membrane_strain():
+    # u = eps_x * x on a skewed flat quad: N_x = E t eps / (1 - nu^2), N_y = nu N_x, N_xy = 0, no bending/shear
+    rng = np.random.default_rng(6)
+    p = np.array([[1, 0.75, 0], [0, 0.75, 0], [0, 0, 0], [1, 0, 0]], float)
+    p[:, :2] += rng.uniform(-0.1, 0.1, (4, 2))
+    E, nu, t, eps = 2.1e11, 0.3, 0.01, 1e-4
+    u = np.zeros(24); u[0::6] = eps * p[:, 0]
+    _, _, fp = O.element_results(_mesh_one("plate", p, [E, nu, t, 5 / 6]), u)
+    nx = E * t * eps / (1 - nu * nu)
+    assert abs(fp[0, 0] - nx) < 1e-10 * nx and abs(fp[0, 1] - nu * nx) < 1e-10 * nx
+    assert np.all(np.abs(fp[0, 2:]) < 1e-9 * nx)
+
+
+def test_plate_result_constant_curvature():
+    # theta_y = -kappa * x (w = kappa x^2 / 2 would add shear; a pure rotation field gives curvature kappa_x and
+    # transverse shear -theta): BendingMoment rows follow plate.rs:1294-1332 with c_bend = E t / (2 (1 - nu^2)), * t^2 / 24
+    p = np.array([[1, 0.75, 0], [0, 0.75, 0], [0, 0, 0], [1, 0, 0]], float)
+    E, nu, t, kappa = 2.1e11, 0.3, 0.01, 1e-3
+    u = np.zeros(24); u[4::6] = -kappa * p[:, 0]
+    _, _, fp = O.element_results(_mesh_one("plate", p, [E, nu, t, 5 / 6]), u)
+    # c_bend * t^2 / 24 = E t^3 / (48 (1 - nu^2)), times the SUM over the four nodes = the textbook D = E t^3 / (12 (1 - nu^2))
+    d = E * t * t * t / (12 * (1 - nu * nu))
+    assert abs(abs(fp[0, 4]) - d * kappa) < 1e-10 * d * kappa          # BendingMomentS takes row 0 (kappa_x)
+    assert abs(abs(fp[0, 3]) - nu * d * kappa) < 1e-10 * d * kappa     # BendingMomentR takes row 1
+
+
+def test_pcg_reference_model_one_iteration():
+    # src/tests/fem/test_fem.rs:83-225 in f64: K_aa = [66666.67], b = [100] -> one iteration, u = 0.0015, R = -100
+    for starts in (None, [0]):
+        u, it = O.pcg(1, ([0], [0], [66666.66666666667]), [100.0], 1000, 1e-4, 1e-12, starts)
+        assert it == 1 and u[0] == 100.0 / 66666.66666666667
+    sep = {"n_bb": 1, "k_bb_indexes": np.array([0]), "k_aa_indexes": np.array([6]),
+           "k_ba": (np.array([0]), np.array([0]), np.array([-66666.66666666667])),
+           "k_bb": (np.array([0]), np.array([0]), np.array([66666.66666666667]))}
+    forces = np.zeros(12); forces[6] = 100.0
+    rr = O.reactions(sep, u, forces, np.zeros(12))
+    assert abs(rr[0] + 100.0) < 1e-12
+    d, f = O.compose_global_analysis_result(sep, u, rr, forces, np.zeros(12))
+    assert d[6] == u[0] and f[0] == rr[0] and f[6] == 100.0
+
+
+def test_block_starts():
+    assert O.block_starts_from_k_aa_indexes([6, 7, 8, 12, 14, 18]) == [0, 3, 5]
+    assert O.block_starts_from_k_aa_indexes([]) == []
