@@ -354,6 +354,38 @@ def main():
                       "ms": sep_ms, "n_aa": n_aa, "n_bb": n_bb, "nnz_aa_ab_ba_bb": q_nnz,
                       "algorithmic_bytes": sep_bytes, "achieved_GBps": sep_bytes / (sep_ms * 1e-3) / 1e9,
                       "frac_of_hbm_peak": sep_bytes / (sep_ms * 1e-3) / 1e9 / peak, "distributed_loads": loads}
+        # §8f ranks 3-4: a fixed number of PCG iterations on K_aa (the model is far from converged after that:
+        # only the per-iteration cost is reported) and the element result recovery from a displacement vector
+        from finite_element_method_b200 import FemError
+        analysis = {}
+        for name, solve in (("pcg_jacobi", fem.find_ua_vector_iterative_pcg_jacobi_sparse),
+                            ("pcg_block_jacobi", fem.find_ua_vector_iterative_pcg_block_jacobi_sparse)):
+            iters = 0
+            for max_iter in (3, 25):          # the first call allocates the work vectors
+                try:
+                    iters = solve(max_iter, copy_out=False)[1]
+                except FemError:
+                    iters = fem.solve_info()[0]
+            it_ms = fem.solve_info()[2] / max(1, iters)
+            it_bytes = 12 * q_nnz[0] + 8 * n_aa * (14 if name == "pcg_jacobi" else 22)   # K_aa once + ~14 (22) vector passes of 8 B per row
+            analysis[name] = {"iterations_timed": iters, "ms_per_iteration": it_ms, "algorithmic_bytes_per_iteration": it_bytes,
+                              "achieved_GBps": it_bytes / (it_ms * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": it_bytes / (it_ms * 1e-3) / 1e9 / peak}
+        fem.set_displacements_vector(np.random.default_rng(7).normal(size=6 * n_nodes) * 1e-3)
+        res_ms = {}
+        for fam, fname, n_f, comps, rec in ((0, "truss", len(local["t_n1"]), 1, 24), (1, "beam", n_bm, 10, 96), (2, "plate", n_pl, 8, 48)):
+            if not n_f:
+                continue
+            fem.element_results(fam, copy_out=False)
+            fem.synchronize()
+            t0 = time.perf_counter()
+            fem.element_results(fam, copy_out=False)
+            dt = (time.perf_counter() - t0) * 1e3
+            nn = 4 if fam == 2 else 2
+            b = n_f * (rec + 8 * comps + nn * (24 + 48))      # record + results + gathered coordinates / displacements
+            res_ms[fname] = {"elements": int(n_f), "ms_wall": dt, "algorithmic_GBps": b / (dt * 1e-3) / 1e9}
+        analysis["element_results"] = res_ms
+        separation["analysis"] = analysis
 
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.config)

@@ -572,7 +572,7 @@ static void free_device(femgpu_t* h) {
   for (auto& f : h->fd) {
     for (auto& c : f.conn) c.release();
     for (auto& p : f.props) p.release();
-    f.cbase.release(); f.rec.release(); f.mat.release(); f.err.release();
+    f.cbase.release(); f.rec.release(); f.err.release();
     f.uploaded = f.validated = 0;
   }
   h->blk_key.release(); h->blk_full.release(); h->blk_cptr.release(); h->contrib.release();

@@ -156,7 +156,13 @@ constexpr int kFamilies = 3;
 constexpr int kNodesPerElem[kFamilies] = {2, 2, 4};
 constexpr int kPairsPerElem[kFamilies] = {4, 4, 16};
 constexpr int kPropsPerElem[kFamilies] = {3, 11, 4};  // truss: E,A,A2; beam: 8 props + axis[3]; plate: 4
-constexpr int kRecDoubles[kFamilies] = {4, 16, 16};   // per-element record written by the prep kernels
+// per-element record written by the prep kernels, laid out like its shared-memory slot in the assembly kernel
+// (kTrussSlotDoubles / kBeamSlotDoubles / 16 + 4 for a plate: geometry + material), so a run of consecutive
+// elements is one contiguous TMA bulk copy: truss 4 used of 6, beam 16 used of 18, plate 20
+constexpr int kTrussSlotDoubles = 6;       // 4 used
+constexpr int kBeamSlotDoubles = 18;       // 16 used
+constexpr int kPlateRawDoubles = 20;       // geometry record 16 + material 4
+constexpr int kRecDoubles[kFamilies] = {kTrussSlotDoubles, kBeamSlotDoubles, kPlateRawDoubles};
 
 struct FamilyHost {
   std::vector<uint32_t> number;       // user label
@@ -174,7 +180,6 @@ struct FamilyDev {
   DevBuf<double> props[11];
   DevBuf<int64_t> cbase;
   DevBuf<double> rec;    // kRecDoubles per element
-  DevBuf<double> mat;    // plates only: Cm, Cb, Cs, nu
   DevBuf<int32_t> err;   // per-element validation code
   size_t uploaded = 0;   // elements already on the device
   size_t validated = 0;  // elements already checked by the prep kernel
@@ -304,6 +309,7 @@ struct Handle {
   int sm_count = 0;
   int asm_threads = 32;            // 32 or 64, fixed by the symbolic pass
   bool asm_split = false;          // some slab splits a block over several lanes (kernel variant with merge rounds)
+  bool asm_bulk = false;           // element records are staged run-wise with TMA bulk copies (consecutive numbering)
   uint32_t asm_smem_set = 0;       // dynamic shared memory assemble_kernel is currently configured for
   int asm_ctas_per_sm = 0;         // persistent CTAs per SM at that size (occupancy query)
   DevBuf<uint32_t> node_blk_ptr;   // [n_nodes_total+1]
@@ -383,7 +389,7 @@ struct Handle {
     for (auto& f : fd) {
       for (auto& c : f.conn) tie(c);
       for (auto& p : f.props) tie(p);
-      tie(f.cbase); tie(f.rec); tie(f.mat); tie(f.err);
+      tie(f.cbase); tie(f.rec); tie(f.err);
     }
     tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(items_c); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
@@ -448,8 +454,6 @@ constexpr int kCapStageBytes = 20 * 1024;  // block metadata + contribution entr
 constexpr int kCapBlocks = 2048;           // blocks per staged slab (11-bit index in the entries)
 // Record slots in the CTA's shared-memory record area, in doubles. Odd multiples of 16 bytes so that
 // lanes reading the same field of different elements spread over the banks.
-constexpr int kTrussSlotDoubles = 6;       // 4 used
-constexpr int kBeamSlotDoubles = 18;       // 16 used
 constexpr int kPlateSlotDoubles = 66;      // 64 used: the plate's shared form (element_math.cuh)
 constexpr int kElistStride = 64;           // element slots per slab in the dense elist table; a slab
                                            // touching more elements takes the unstaged path

@@ -35,10 +35,9 @@ struct AsmArgs {
   const uint32_t* items_c;        // staged kernel: [n_slabs][kT] packed (first entry - slab's first) | count << 16
   const uint32_t* elist;          // dense [n_slabs][kElistStride]
   const uint32_t* elist_compact;  // compact lists (unstaged kernel only)
-  const double4* truss_rec;
+  const double* truss_rec;        // records at the stride of their shared-memory slots (kRecDoubles)
   const double* beam_rec;
-  const double* plate_rec;
-  const double* plate_mat;
+  const double* plate_rec;        // geometry (16) + material (4)
   double* values;
   uint32_t n_slabs;
   // shared-memory regions of the staged kernel, bytes: [image][plate forms][raw plates][stage x2]
@@ -89,16 +88,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar_s, uint32_t parity) {
 }
 
 // global address of 16-byte chunk `chunk` of an element's record (nullptr past its end):
-// plate = 8 chunks of the geometry record + 2 of the material record, beam = 8, truss = 2
+// plate = 8 chunks of geometry + 2 of material, beam = 8, truss = 2
 __device__ __forceinline__ const void* record_chunk(const AsmArgs& A, uint32_t fe, uint32_t chunk) {
   const uint32_t family = fe >> 26, e = fe & 0x03FFFFFFu;
-  if (family == FEMGPU_PLATE) {
-    if (chunk < 8) return A.plate_rec + size_t(e) * 16 + chunk * 2;
-    return chunk < 10 ? A.plate_mat + size_t(e) * 4 + (chunk - 8) * 2 : nullptr;
-  }
-  if (family == FEMGPU_BEAM) return chunk < 8 ? A.beam_rec + size_t(e) * 16 + chunk * 2 : nullptr;
+  if (family == FEMGPU_PLATE) return chunk < 10 ? A.plate_rec + size_t(e) * kPlateRawDoubles + chunk * 2 : nullptr;
+  if (family == FEMGPU_BEAM) return chunk < 8 ? A.beam_rec + size_t(e) * kBeamSlotDoubles + chunk * 2 : nullptr;
   if (family != FEMGPU_TRUSS) return nullptr;  // family 3: placeholder of a remote contribution
-  return chunk < 2 ? reinterpret_cast<const double*>(A.truss_rec + e) + chunk * 2 : nullptr;
+  return chunk < 2 ? A.truss_rec + size_t(e) * kTrussSlotDoubles + chunk * 2 : nullptr;
 }
 
 // Place a 6x6 / 3x3 block into the slab image (shared memory) or straight into the CSR values
@@ -239,16 +235,21 @@ __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_
                reinterpret_cast<const uint4*>(A.slabs + k) + (tid - kItemLanes - kElistLanes));
 }
 
-template <int kT>
+// kBulk: a lane holds the element slots j * kT + tid (it heads the run-wise bulk copies); otherwise two
+// adjacent lanes share the slots j * kT / 2 + tid / 2 (they copy alternate 16-byte chunks of a record)
+template <int kT, bool kBulk>
 __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uint32_t tid) {
   SlabRegs<kT> R;
   const uint4* sp = reinterpret_cast<const uint4*>(dbuf);
   R.d0 = sp[0];
   R.d1 = sp[1];
   R.d2 = sp[2];
+  const uint32_t* el = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>());
 #pragma unroll
-  for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j)
-    R.fe[j] = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>())[j * (kT / 2) + (tid >> 1)];
+  for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
+    if (kBulk) R.fe[j] = j < kElistStride / kT ? el[j * kT + tid] : 0xFFFFFFFFu;
+    else R.fe[j] = el[j * (kT / 2) + (tid >> 1)];
+  }
   const uint32_t w = reinterpret_cast<const uint32_t*>(dbuf + kDescItemsOff)[tid];
   R.c_begin = R.slab_c_begin() + (w & 0xFFFFu);
   R.c_count = w >> 16;
@@ -259,15 +260,19 @@ __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uin
 // cp.async everything slab R needs into `stage` (+ its raw plate records into `rawp`): block
 // metadata, contribution entries, and each lane pair the records of "its" elements — every record
 // is fetched once per slab, all requests in flight together
-template <int kT>
+template <int kT, bool kBulk>
 __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>& R, uint32_t stage_s,
                                             uint32_t rawp_s, uint32_t mbar_s, uint32_t tid) {
   // block metadata and contribution entries are contiguous: two TMA bulk loads by one thread,
-  // completing on the same mbarrier as the cp.async record gathers
+  // completing on the same mbarrier as the record copies
+  const uint32_t nt = R.n_truss(), nbm = R.n_beam();
   if (tid == 0 && R.blk_count()) {
     const uint32_t meta_bytes = R.blk_count() * 16u, ent_bytes = R.slab_c_count() ? R.ent_bytes() : 0u;
+    const uint32_t rec_bytes = kBulk ? nt * uint32_t(kTrussSlotDoubles * 8) + nbm * uint32_t(kBeamSlotDoubles * 8) +
+                                           R.n_plate() * uint32_t(kPlateRawDoubles * 8)
+                                     : 0u;
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mbar_s),
-                 "r"(meta_bytes + ent_bytes)
+                 "r"(meta_bytes + ent_bytes + rec_bytes)
                  : "memory");
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_s),
@@ -280,28 +285,70 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
           "l"(A.contrib + (R.slab_c_begin() & ~3u)), "r"(ent_bytes), "r"(mbar_s)
           : "memory");
   }
-  const uint32_t nt = R.n_truss(), nbm = R.n_beam(), half = tid & 1u;
+  if (kBulk) {
+    // The slab's element list is sorted by (family, element) and the records lie in global memory exactly as in
+    // their shared-memory slots, so a run of consecutively numbered elements — the rule in a mesh numbered along
+    // its grid lines — is ONE contiguous TMA bulk copy: a slab of the plate grid needs 2 copies of 9 plate
+    // records instead of 180 LDGSTS, none of which passes through the LSU data pipe. The lane at the head of a
+    // run (found with a shuffle and two ballots) issues the copy. The symbolic pass selects this variant only
+    // when the runs are long enough on average (Handle::asm_bulk): a bulk copy per element is slower than LDGSTS.
+    const uint32_t lane = tid & 31u;
+#pragma unroll
+    for (int j = 0; j < kElistStride / kT; ++j) {
+      const uint32_t fe = R.fe[j], family = fe >> 26, e = fe & 0x03FFFFFFu;
+      const bool copy = fe != 0xFFFFFFFFu && family < 3u;
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, fe, 1);
+      const bool head = copy && (lane == 0u || fe != prev + 1u || (prev >> 26) != family);
+      const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head), copies = __ballot_sync(0xFFFFFFFFu, copy);
+      if (head) {
+        const uint32_t after = lane == 31u ? 0u : heads >> (lane + 1u);
+        uint32_t len = after ? uint32_t(__ffs(int(after))) : 32u - lane;
+        const uint32_t stop = (~copies) >> lane;  // bit 0 = this lane
+        if (stop) len = min(len, uint32_t(__ffs(int(stop))) - 1u);
+        const uint32_t slot = uint32_t(j) * kT + tid;
+        uint32_t dst, bytes;
+        const double* src;
+        if (family == FEMGPU_PLATE) {
+          dst = rawp_s + (slot - nt - nbm) * uint32_t(kPlateRawDoubles * 8);
+          src = A.plate_rec + size_t(e) * kPlateRawDoubles;
+          bytes = len * uint32_t(kPlateRawDoubles * 8);
+        } else if (family == FEMGPU_BEAM) {
+          dst = stage_s + R.beam_off() + (slot - nt) * uint32_t(kBeamSlotDoubles * 8);
+          src = A.beam_rec + size_t(e) * kBeamSlotDoubles;
+          bytes = len * uint32_t(kBeamSlotDoubles * 8);
+        } else {
+          dst = stage_s + R.truss_off() + slot * uint32_t(kTrussSlotDoubles * 8);
+          src = A.truss_rec + size_t(e) * kTrussSlotDoubles;
+          bytes = len * uint32_t(kTrussSlotDoubles * 8);
+        }
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(src), "r"(bytes), "r"(mbar_s)
+            : "memory");
+      }
+    }
+    return;
+  }
+  const uint32_t half = tid & 1u;
 #pragma unroll
   for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
     const uint32_t fe = R.fe[j];
     if (fe == 0xFFFFFFFFu) continue;
     const uint32_t slot = j * (kT / 2) + (tid >> 1), family = fe >> 26, e = fe & 0x03FFFFFFu;
     if (family == FEMGPU_PLATE) {
-      // chunks 0..7 = geometry record, 8..9 = material record; this lane takes every other one
-      const uint32_t dst = rawp_s + (slot - nt - nbm) * 160u + half * 16u;
-      const double* rec = A.plate_rec + size_t(e) * 16 + half * 2;
-      const double* mat = A.plate_mat + size_t(e) * 4 + half * 2;
+      // chunks 0..7 = geometry, 8..9 = material; this lane takes every other one
+      const uint32_t dst = rawp_s + (slot - nt - nbm) * uint32_t(kPlateRawDoubles * 8) + half * 16u;
+      const double* rec = A.plate_rec + size_t(e) * kPlateRawDoubles + half * 2;
 #pragma unroll
-      for (uint32_t ch = 0; ch < 4; ++ch) cp_async16(dst + ch * 32u, rec + ch * 4);
-      cp_async16(dst + 128u, mat);
+      for (uint32_t ch = 0; ch < 5; ++ch) cp_async16(dst + ch * 32u, rec + ch * 4);
     } else if (family == FEMGPU_BEAM) {
       const uint32_t dst = stage_s + R.beam_off() + (slot - nt) * uint32_t(kBeamSlotDoubles * 8) + half * 16u;
-      const double* rec = A.beam_rec + size_t(e) * 16 + half * 2;
+      const double* rec = A.beam_rec + size_t(e) * kBeamSlotDoubles + half * 2;
 #pragma unroll
       for (uint32_t ch = 0; ch < 4; ++ch) cp_async16(dst + ch * 32u, rec + ch * 4);
     } else if (family == FEMGPU_TRUSS) {
       const uint32_t dst = stage_s + R.truss_off() + slot * uint32_t(kTrussSlotDoubles * 8) + half * 16u;
-      cp_async16(dst, reinterpret_cast<const double*>(A.truss_rec + e) + half * 2);
+      cp_async16(dst, A.truss_rec + size_t(e) * kTrussSlotDoubles + half * 2);
     }  // family 3: placeholder of a remote contribution, no record
   }
 }
@@ -449,7 +496,7 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
 #ifndef FEMGPU_MAXNREG64
 #define FEMGPU_MAXNREG64 168
 #endif
-template <int kT, bool kSplit>
+template <int kT, bool kSplit, bool kBulk>
 __global__ void __maxnreg__(kT == 64 ? FEMGPU_MAXNREG64 : 255)
 assemble_kernel(const AsmArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -472,8 +519,8 @@ assemble_kernel(const AsmArgs A) {
   issue_desc<kT>(A, k, dbuf0_s, tid);
   cp_async_arrive(mbar_s);
   mbar_wait(mbar_s, 0);
-  SlabRegs<kT> cur = read_desc<kT>(dbuf0, tid);
-  issue_stage<kT>(A, cur, stage0_s, rawp_s, mbar_s, tid);
+  SlabRegs<kT> cur = read_desc<kT, kBulk>(dbuf0, tid);
+  issue_stage<kT, kBulk>(A, cur, stage0_s, rawp_s, mbar_s, tid);
   if (k + stride < A.n_slabs) issue_desc<kT>(A, k + stride, dbuf0_s + desc_bytes<kT>(), tid);
   cp_async_arrive(mbar_s);
 
@@ -494,8 +541,8 @@ assemble_kernel(const AsmArgs A) {
     const bool all_flat = phase_a<kT>(cur, rawp, form, tid);
     PHASE_MARK(3)
     if (has_next) {
-      const SlabRegs<kT> nxt = read_desc<kT>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
-      issue_stage<kT>(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, mbar_s, tid);
+      const SlabRegs<kT> nxt = read_desc<kT, kBulk>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
+      issue_stage<kT, kBulk>(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, mbar_s, tid);
       if (k + 2 * stride < A.n_slabs) issue_desc<kT>(A, k + 2 * stride, dbuf0_s + d_nn * desc_bytes<kT>(), tid);
       cp_async_arrive(mbar_s);
     }
@@ -549,7 +596,7 @@ assemble_kernel(const AsmArgs A) {
     if (!has_next) break;
     k += stride;
     d_cur = d_nxt;
-    cur = read_desc<kT>(dbuf0 + d_cur * desc_bytes<kT>(), tid);
+    cur = read_desc<kT, kBulk>(dbuf0 + d_cur * desc_bytes<kT>(), tid);
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef FEMGPU_PHASE_CLOCKS
@@ -619,9 +666,8 @@ assemble_unstaged_kernel(const AsmArgs A) {
 // (kRawDoubles: the largest per-element record read from global memory: plate 16 + 4)
 // test hook: the whole transformed element matrix of one element, built from the same block
 // evaluators the assembly uses
-__global__ void element_matrix_kernel(int family, uint32_t e, const double4* truss_rec,
-                                      const double* beam_rec, const double* plate_rec,
-                                      const double* plate_mat, double* out) {
+__global__ void element_matrix_kernel(int family, uint32_t e, const double* truss_rec,
+                                      const double* beam_rec, const double* plate_rec, double* out) {
   const int nn = (family == FEMGPU_PLATE) ? 4 : 2;
   const int dof = (family == FEMGPU_TRUSS) ? 3 : 6;
   const int n = nn * dof;
@@ -632,7 +678,6 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double4* tru
   A.truss_rec = truss_rec;
   A.beam_rec = beam_rec;
   A.plate_rec = plate_rec;
-  A.plate_mat = plate_mat;
   double rec[kRawDoubles];
   for (uint32_t ch = 0; ch < uint32_t(kRawDoubles / 2); ++ch) {
     const double* src = reinterpret_cast<const double*>(record_chunk(A, (uint32_t(family) << 26) | e, ch));
@@ -659,10 +704,9 @@ int32_t run_assembly(Handle* h) {
   A.items_c = h->items_c.p;
   A.elist = h->elist.p;
   A.elist_compact = h->elist_compact.p;
-  A.truss_rec = reinterpret_cast<const double4*>(h->fd[FEMGPU_TRUSS].rec.p);
+  A.truss_rec = h->fd[FEMGPU_TRUSS].rec.p;
   A.beam_rec = h->fd[FEMGPU_BEAM].rec.p;
   A.plate_rec = h->fd[FEMGPU_PLATE].rec.p;
-  A.plate_mat = h->fd[FEMGPU_PLATE].mat.p;
   A.values = h->values.p;
   A.n_slabs = h->n_slabs;
   auto up = [](uint32_t b) { return (b + kSmemAlign - 1u) & ~(kSmemAlign - 1u); };
@@ -675,12 +719,16 @@ int32_t run_assembly(Handle* h) {
   const uint32_t smem = A.smem_img + A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * desc + 16 +
                         16 * uint32_t(sizeof(PlatePair));
   if (h->n_unstaged < h->n_slabs) {
-    const bool split = h->asm_split;
-    const void* fn = threads == 64 ? (split ? reinterpret_cast<const void*>(assemble_kernel<64, true>)
-                                            : reinterpret_cast<const void*>(assemble_kernel<64, false>))
-                                   : (split ? reinterpret_cast<const void*>(assemble_kernel<32, true>)
-                                            : reinterpret_cast<const void*>(assemble_kernel<32, false>));
-    const uint32_t config = smem | (uint32_t(threads) << 24) | (split ? 1u << 31 : 0u);
+    const bool split = h->asm_split, bulk = h->asm_bulk;
+    using Kernel = void (*)(const AsmArgs);
+    static const Kernel table[2][2][2] = {
+        {{assemble_kernel<32, false, false>, assemble_kernel<32, false, true>},
+         {assemble_kernel<32, true, false>, assemble_kernel<32, true, true>}},
+        {{assemble_kernel<64, false, false>, assemble_kernel<64, false, true>},
+         {assemble_kernel<64, true, false>, assemble_kernel<64, true, true>}}};
+    const Kernel kernel = table[threads == 64][split][bulk];
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    const uint32_t config = smem | (threads == 64 ? 1u << 28 : 0u) | (bulk ? 1u << 29 : 0u) | (split ? 1u << 30 : 0u);
     if (h->asm_smem_set != config) {
       FEMGPU_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       int per_sm = 0;
@@ -691,17 +739,11 @@ int32_t run_assembly(Handle* h) {
       h->asm_smem_set = config;
       h->asm_ctas_per_sm = per_sm;
       if (getenv("FEMGPU_ASM_INFO"))  // shared-memory budget of the staged kernel, to stderr
-        fprintf(stderr, "[femgpu asm] T=%d split=%d smem=%u B (image %u, forms %u, raw plates %u, stage 2 x %u, descriptors 3 x %u) -> %d CTAs/SM, %u slabs (%u unstaged)\n",
-                threads, int(split), smem, A.smem_img, A.smem_form, A.smem_rawp, A.smem_stage, desc, per_sm, h->n_slabs, h->n_unstaged);
+        fprintf(stderr, "[femgpu asm] T=%d split=%d bulk=%d smem=%u B (image %u, forms %u, raw plates %u, stage 2 x %u, descriptors 3 x %u) -> %d CTAs/SM, %u slabs (%u unstaged)\n",
+                threads, int(split), int(bulk), smem, A.smem_img, A.smem_form, A.smem_rawp, A.smem_stage, desc, per_sm, h->n_slabs, h->n_unstaged);
     }
     const uint32_t grid = uint32_t(std::min<uint64_t>(h->n_slabs, uint64_t(h->sm_count) * h->asm_ctas_per_sm));
-    if (threads == 64) {
-      if (split) assemble_kernel<64, true><<<grid, 64, smem, h->stream>>>(A);
-      else assemble_kernel<64, false><<<grid, 64, smem, h->stream>>>(A);
-    } else {
-      if (split) assemble_kernel<32, true><<<grid, 32, smem, h->stream>>>(A);
-      else assemble_kernel<32, false><<<grid, 32, smem, h->stream>>>(A);
-    }
+    kernel<<<grid, threads, smem, h->stream>>>(A);
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
 #ifdef FEMGPU_PHASE_CLOCKS
@@ -742,9 +784,8 @@ int32_t element_matrix(Handle* h, int family, size_t index, double* out_host) {
   const int nn = kNodesPerElem[family], dof = family == FEMGPU_TRUSS ? 3 : 6, n = nn * dof;
   FEMGPU_CUDA_CHECK(h, h->scratch.reserve(size_t(n) * n * 8 + 64));
   double* d_out = reinterpret_cast<double*>(h->scratch.p);
-  element_matrix_kernel<<<1, 32, 0, h->stream>>>(
-      family, uint32_t(index), reinterpret_cast<const double4*>(h->fd[FEMGPU_TRUSS].rec.p),
-      h->fd[FEMGPU_BEAM].rec.p, h->fd[FEMGPU_PLATE].rec.p, h->fd[FEMGPU_PLATE].mat.p, d_out);
+  element_matrix_kernel<<<1, 32, 0, h->stream>>>(family, uint32_t(index), h->fd[FEMGPU_TRUSS].rec.p,
+                                                 h->fd[FEMGPU_BEAM].rec.p, h->fd[FEMGPU_PLATE].rec.p, d_out);
   h->launches++;
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(out_host, d_out, size_t(n) * n * 8, cudaMemcpyDeviceToHost, h->stream));

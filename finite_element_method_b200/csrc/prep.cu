@@ -1,7 +1,8 @@
 // Element-record kernels: one thread per element computes everything that needs transcendental
 // functions or the abs_tol clipping (rotation matrices, principal inertia, Jacobian scalars) and
 // the element-level validity checks of Truss/Beam/Plate::create, and writes a compact record the
-// assembly kernel reads (truss 32 B, beam 128 B, plate 128 B + 32 B material).
+// assembly kernel reads (truss 32 B, beam 128 B, plate 128 B + 32 B material; stored at the stride of the
+// kernel's shared-memory slots, kRecDoubles).
 //
 // Compiled with -fmad=false: this file follows the reference's operation order, and Rust does not
 // contract a*b+c.
@@ -31,7 +32,7 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
                   const uint32_t* __restrict__ n2, const double* __restrict__ E,
                   const double* __restrict__ A, const double* __restrict__ A2,
                   const double* __restrict__ x, const double* __restrict__ y,
-                  const double* __restrict__ z, double abs_tol, double4* __restrict__ rec,
+                  const double* __restrict__ z, double abs_tol, double* __restrict__ rec,
                   int32_t* __restrict__ err) {
   uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
@@ -43,7 +44,10 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
     q[0] = q[1] = q[2] = 0.0;
     k00 = 0.0;
   }
-  rec[e] = make_double4(q[0], q[1], q[2], k00);
+  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kTrussSlotDoubles);
+  out[0] = make_double2(q[0], q[1]);
+  out[1] = make_double2(q[2], k00);
+  out[2] = make_double2(0.0, 0.0);
   if (kWriteErr) err[e] = code;
 }
 
@@ -71,9 +75,10 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = 0.0;
   }
-  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * 16);
+  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kBeamSlotDoubles);
 #pragma unroll
   for (int i = 0; i < 8; ++i) out[i] = make_double2(r[2 * i], r[2 * i + 1]);
+  out[8] = make_double2(0.0, 0.0);
   if (kWriteErr) err[e] = code;
 }
 
@@ -85,7 +90,7 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
                   const double* __restrict__ nu, const double* __restrict__ t,
                   const double* __restrict__ ks, const double* __restrict__ x,
                   const double* __restrict__ y, const double* __restrict__ z, double abs_tol,
-                  double* __restrict__ rec, double4* __restrict__ mat, int32_t* __restrict__ err) {
+                  double* __restrict__ rec, int32_t* __restrict__ err) {
   uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   double p1[3], p2[3], p3[3], p4[3], r[16], m[4];
@@ -99,10 +104,11 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
     for (int i = 0; i < 16; ++i) r[i] = 0.0;
     m[0] = m[1] = m[2] = m[3] = 0.0;
   }
-  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * 16);
+  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kPlateRawDoubles);
 #pragma unroll
   for (int i = 0; i < 8; ++i) out[i] = make_double2(r[2 * i], r[2 * i + 1]);
-  mat[e] = make_double4(m[0], m[1], m[2], m[3]);
+  out[8] = make_double2(m[0], m[1]);
+  out[9] = make_double2(m[2], m[3]);
   if (kWriteErr) err[e] = code;
 }
 
@@ -227,7 +233,6 @@ int32_t run_prep(Handle* h, bool validate_only) {
     // records are needed for every element either way (the buffers may have been reallocated)
     size_t before = fd.rec.cap;
     FEMGPU_CUDA_CHECK(h, fd.rec.reserve(n * size_t(kRecDoubles[f])));
-    if (f == FEMGPU_PLATE) FEMGPU_CUDA_CHECK(h, fd.mat.reserve(n * 4));
     FEMGPU_CUDA_CHECK(h, fd.err.reserve(n));
     if (fd.rec.cap != before) from = validate_only ? fd.validated : 0;
     if (from >= n) continue;
@@ -240,11 +245,11 @@ int32_t run_prep(Handle* h, bool validate_only) {
       if (validate_only)
         truss_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
-            h->abs_tol, reinterpret_cast<double4*>(fd.rec.p), fd.err.p);
+            h->abs_tol, fd.rec.p, fd.err.p);
       else
         truss_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
-            h->abs_tol, reinterpret_cast<double4*>(fd.rec.p), fd.err.p);
+            h->abs_tol, fd.rec.p, fd.err.p);
     } else if (f == FEMGPU_BEAM) {
       if (validate_only)
         beam_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
@@ -258,13 +263,11 @@ int32_t run_prep(Handle* h, bool validate_only) {
       if (validate_only)
         plate_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
-            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p,
-            reinterpret_cast<double4*>(fd.mat.p), fd.err.p);
+            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
       else
         plate_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
-            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p,
-            reinterpret_cast<double4*>(fd.mat.p), fd.err.p);
+            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
     }
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());

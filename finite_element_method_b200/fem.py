@@ -401,11 +401,15 @@ class FEM:
             raise ValueError("displacements must hold 6 * nodes_number values")
         self._check(self._L.femgpu_set_displacements(self._h, _p(u, _lib.dp)))
 
-    def element_results(self, family: int):
+    def element_results(self, family: int, copy_out: bool = True):
         """rows = elements of `family` in insertion order, columns = the reference's components:
-        truss [n, 1], beam [n, 10], plate [n, 8]"""
+        truss [n, 1], beam [n, 10], plate [n, 8]. copy_out=False leaves them in HBM (returns the device address)."""
         n = self.counts()[1 + family]
         k = ELEMENT_RESULT_COMPONENTS[family]
+        if not copy_out:
+            dev = C.c_void_p()
+            self._check(self._L.femgpu_element_results(self._h, family, None, C.byref(dev)))
+            return int(dev.value or 0)
         out = np.empty((n, len(k)), np.float64)
         self._check(self._L.femgpu_element_results(self._h, family, _p(out, _lib.dp) if n else None, None))
         return out
