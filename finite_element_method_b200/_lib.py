@@ -49,6 +49,8 @@ SIGNATURES = {
     "femgpu_add_surface_load": (C.c_int32, [H, C.c_size_t, u32p, i32p, dp]),
     "femgpu_get_forces": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_separate_sparse": (C.c_int32, [H, i64p, i64p, i64p]),
+    "femgpu_separate_direct": (C.c_int32, [H, i64p, i64p, i64p]),
+    "femgpu_get_skyline": (C.c_int32, [H, i64p, dp, i64p]),
     "femgpu_get_separated_indexes": (C.c_int32, [H, i64p, i64p]),
     "femgpu_get_separated_csr": (C.c_int32, [H, C.c_int32, i64p, i32p, dp]),
     "femgpu_get_separated_csr_device": (C.c_int32, [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -618,6 +618,11 @@ void femgpu_destroy(femgpu_t* h) {
     for (auto& ev : q)
       if (ev) cudaEventDestroy(ev);
   for (int b = 0; b < 2; ++b) {
+    if (h->side_stream[b]) cudaStreamDestroy(h->side_stream[b]);
+    if (h->join_ev[b]) cudaEventDestroy(h->join_ev[b]);
+  }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  for (int b = 0; b < 2; ++b) {
     if (h->pin_ev[b]) cudaEventDestroy(h->pin_ev[b]);
     if (h->pin_buf[b]) cudaFreeHost(h->pin_buf[b]);
   }

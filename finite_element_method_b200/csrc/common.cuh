@@ -354,6 +354,12 @@ struct Handle {
     DevBuf<int32_t> col[4];
     DevBuf<double> val[4];
     DevBuf<int32_t> tmp[8];           // scratch: class flags, their scans, per-row counts of the 4 quadrants
+    // direct separation: k_aa_skyline and K_aa in the compacted column form (a, maxa) of the skyline solver
+    bool sky_valid = false;
+    int64_t sky_total = 0;
+    DevBuf<int32_t> sky;
+    DevBuf<int64_t> maxa;
+    DevBuf<double> sky_a;
   } sep;
 
   // ---- global analysis (solve.cu): u_a, reactions, composed vectors, element results (results.cu) ----
@@ -370,6 +376,11 @@ struct Handle {
     DevBuf<double> disp, force;       // [6 * nodes_number] displacements / forces after compose
     DevBuf<double> res[kFamilies];    // element results
   } sol;
+
+  // side streams of the numeric pass: the element-record kernels of the three families are independent and
+  // each is bound by gather latency at a third of the SM's warp slots, so they run side by side (prep.cu)
+  cudaStream_t side_stream[2] = {nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
 
   // Pinned bounce buffers of the bulk host->device path (api.cu h2d_staged): the host staging vectors
   // are pageable, so large uploads are copied chunk-wise into pinned memory by several host threads
@@ -402,6 +413,7 @@ struct Handle {
       tie(sep.row_ptr[q]); tie(sep.col[q]); tie(sep.val[q]);
     }
     for (auto& t : sep.tmp) tie(t);
+    tie(sep.sky); tie(sep.maxa); tie(sep.sky_a);
     tie(sol.u_a); tie(sol.r_r); tie(sol.r); tie(sol.z); tie(sol.p); tie(sol.ap); tie(sol.minv); tie(sol.blk);
     tie(sol.partial); tie(sol.scal); tie(sol.disp); tie(sol.force);
     for (auto& r : sol.res) tie(r);
@@ -428,7 +440,8 @@ int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, dou
 int32_t run_load_kernel(Handle* h, uint32_t n, const int32_t* d_family, const uint32_t* d_elem, const int32_t* d_dof,
                         const double* d_value, uint32_t* d_key, double* d_val);  // prep.cu
 int32_t forces_flush(Handle* h);                         // separate.cu: bc -> sep.d_constrained / d_disp / d_force
-int32_t run_separate(Handle* h);                         // separate.cu
+int32_t run_separate(Handle* h, bool direct);            // separate.cu
+int32_t run_skyline(Handle* h);                          // separate.cu
 void sep_release(Handle* h);                             // separate.cu
 void bc_clear(Handle* h);                                // separate.cu
 int32_t run_element_results(Handle* h, int family, const double* d_u, double* d_out);  // results.cu

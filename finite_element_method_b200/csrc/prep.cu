@@ -225,17 +225,43 @@ __global__ void rotation_kernel(int family, uint32_t e, const uint32_t* n1, cons
 
 int32_t run_prep(Handle* h, bool validate_only) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  // buffers first (stream-ordered allocations on the handle's stream), then the kernels
+  size_t from_of[kFamilies] = {0, 0, 0};
+  int n_live = 0;
   for (int f = 0; f < kFamilies; ++f) {
     FamilyDev& fd = h->fd[f];
-    size_t n = h->fh[f].size();
-    size_t from = validate_only ? fd.validated : 0;
+    const size_t n = h->fh[f].size();
+    from_of[f] = validate_only ? fd.validated : 0;
     if (n == 0) continue;
     // records are needed for every element either way (the buffers may have been reallocated)
-    size_t before = fd.rec.cap;
+    const size_t before = fd.rec.cap;
     FEMGPU_CUDA_CHECK(h, fd.rec.reserve(n * size_t(kRecDoubles[f])));
     FEMGPU_CUDA_CHECK(h, fd.err.reserve(n));
-    if (fd.rec.cap != before) from = validate_only ? fd.validated : 0;
-    if (from >= n) continue;
+    if (fd.rec.cap != before) from_of[f] = validate_only ? fd.validated : 0;
+    if (from_of[f] < n) ++n_live;
+  }
+  // numeric pass with several families: fork the kernels onto side streams, join before returning
+  const bool fork = !validate_only && n_live > 1;
+  if (fork) {
+    if (!h->fork_ev) {
+      FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+      for (int b = 0; b < 2; ++b) {
+        FEMGPU_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->side_stream[b], cudaStreamNonBlocking));
+        FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->join_ev[b], cudaEventDisableTiming));
+      }
+    }
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->fork_ev, h->stream));
+  }
+  int lane = 0;  // 0 = the handle's stream, 1 / 2 = side streams
+  for (int f = kFamilies - 1; f >= 0; --f) {  // plates and beams (the long ones) first
+    FamilyDev& fd = h->fd[f];
+    const size_t n = h->fh[f].size(), from = from_of[f];
+    if (n == 0 || from >= n) continue;
+    cudaStream_t st = h->stream;
+    if (fork && lane > 0) {
+      st = h->side_stream[lane - 1];
+      FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->fork_ev, 0));
+    }
     uint32_t grid = div_up(n - from, kPrepThreads);
     const double* x = h->d_x.p;
     const double* y = h->d_y.p;
@@ -243,34 +269,39 @@ int32_t run_prep(Handle* h, bool validate_only) {
     auto P = [&](int k) { return (const double*)fd.props[k].p; };
     if (f == FEMGPU_TRUSS) {
       if (validate_only)
-        truss_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
+        truss_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
             h->abs_tol, fd.rec.p, fd.err.p);
       else
-        truss_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
+        truss_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
             h->abs_tol, fd.rec.p, fd.err.p);
     } else if (f == FEMGPU_BEAM) {
       if (validate_only)
-        beam_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
+        beam_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
             P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
       else
-        beam_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
+        beam_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
             P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
     } else {
       if (validate_only)
-        plate_prep_kernel<true><<<grid, kPrepThreads, 0, h->stream>>>(
+        plate_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
             P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
       else
-        plate_prep_kernel<false><<<grid, kPrepThreads, 0, h->stream>>>(
+        plate_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
             P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
     }
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+    if (fork && lane > 0) {
+      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->join_ev[lane - 1], st));
+      FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->join_ev[lane - 1], 0));
+    }
+    ++lane;
   }
   return 0;
 }

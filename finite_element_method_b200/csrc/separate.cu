@@ -36,8 +36,9 @@ struct CastI64 {
 // diag(K)[i]: the row's columns ascend, so the diagonal is found by bisection; an absent entry is 0
 __global__ void classify_kernel(int64_t n_rows, const int64_t* __restrict__ row_ptr,
                                 const int32_t* __restrict__ col_idx, const double* __restrict__ values,
-                                const uint8_t* __restrict__ constrained, int32_t* __restrict__ is_a,
-                                int32_t* __restrict__ is_b, unsigned long long* __restrict__ first_bad) {
+                                const uint8_t* __restrict__ constrained, const double* __restrict__ force,
+                                int32_t* __restrict__ is_a, int32_t* __restrict__ is_b,
+                                unsigned long long* __restrict__ first_bad) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
   int64_t lo = row_ptr[i], hi = row_ptr[i + 1];
@@ -55,7 +56,9 @@ __global__ void classify_kernel(int64_t n_rows, const int64_t* __restrict__ row_
   const bool fixed = constrained[i] != 0;
   int32_t a = 0, b = 0;
   if (d == 0.0) {
-    if (fixed) atomicMin(first_bad, (unsigned long long)i);  // integer min: order independent
+    // check_excluded_index of the direct separation (methods_for_separate_stiffness_matrix.rs:36-61) also rejects
+    // a load on a DOF without stiffness; the sparse separation only looks at the constraints (force == nullptr)
+    if (fixed || (force && force[i] != 0.0)) atomicMin(first_bad, (unsigned long long)i);  // integer min: order independent
   } else if (fixed) {
     b = 1;
   } else {
@@ -324,7 +327,8 @@ void bc_clear(Handle* h) {
 void sep_release(Handle* h) {
   Handle::Separated& S = h->sep;
   S.d_constrained.release(); S.d_disp.release(); S.d_force.release(); S.cls_pos.release();
-  S.aa_idx.release(); S.bb_idx.release(); S.rhs.release();
+  S.aa_idx.release(); S.bb_idx.release(); S.rhs.release(); S.sky.release(); S.maxa.release(); S.sky_a.release();
+  S.sky_valid = false;
   for (auto& t : S.tmp) t.release();
   for (int q = 0; q < 4; ++q) {
     S.row_ptr[q].release(); S.col[q].release(); S.val[q].release();
@@ -455,7 +459,7 @@ int32_t forces_flush(Handle* h) {
   return 0;
 }
 
-int32_t run_separate(Handle* h) {
+int32_t run_separate(Handle* h, bool direct) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   Handle::Separated& S = h->sep;
@@ -490,7 +494,7 @@ int32_t run_separate(Handle* h) {
   FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(is_b.p + n, 0, 4, s));
   if (n) {
     classify_kernel<<<div_up(n, 256), 256, 0, s>>>(n, h->row_ptr.p, h->col_idx.p, h->values.p, S.d_constrained.p,
-                                                  is_a.p, is_b.p, d_bad);
+                                                  direct ? S.d_force.p : nullptr, is_a.p, is_b.p, d_bad);
     h->launches++;
   }
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
@@ -506,11 +510,16 @@ int32_t run_separate(Handle* h) {
     // methods_for_separate_stiffness_matrix.rs:233-243
     const size_t node = size_t(bad / 6);
     const uint32_t number = node < h->n_nodes() ? h->node_number[node] : 0u;
+    if (direct && !h->bc.constrained[size_t(bad)])  // :49-58
+      return h->fail(FEMGPU_E_NO_STIFFNESS_FOR_LOAD, std::string("There are no stiffness to withstand load ") +
+                                                         dof_name(int(bad % 6)) + " applied to node " +
+                                                         std::to_string(number) + "!");
     return h->fail(FEMGPU_E_NO_STIFFNESS_FOR_DISPLACEMENT,
                    std::string("There are no stiffness to withstand displacement ") + dof_name(int(bad % 6)) +
                        " applied to node " + std::to_string(number) + "!");
   }
-  if (n_bb == 0) return h->fail(FEMGPU_E_NO_RESTRAINTS, "No restraints");  // :257-259
+  if (n_bb == 0)  // :257-259 ("No restraints"), :87-89 ("There are no restraints applied!")
+    return h->fail(FEMGPU_E_NO_RESTRAINTS, direct ? "There are no restraints applied!" : "No restraints");
   if (n >= (int64_t(1) << 30)) return h->fail(FEMGPU_ERR_LIMIT, "separation supports < 2^30 degrees of freedom");
 
   FEMGPU_CUDA_CHECK(h, S.cls_pos.reserve(size_t(n)));
@@ -566,6 +575,75 @@ int32_t run_separate(Handle* h) {
   S.n_aa = n_aa;
   S.n_bb = n_bb;
   S.valid = true;
+  return 0;
+}
+
+// ---- direct separation: skyline of K_aa ---------------------------------------------------------------
+// FEM::separate_stiffness_matrix_direct (methods_for_separate_stiffness_matrix.rs:63-215) walks a DENSE copy of
+// K to build k_aa_skyline[j] = the largest j - i with K_aa[i, j] != 0 (i < j) and dense quadrants; its only
+// consumer, find_ua_vector_direct (methods_for_global_analysis.rs:161-187), turns K_aa into the compacted
+// column form (a, maxa) of convert_k_aa_into_compacted_form (:50-80): column j holds K_aa[j, j], K_aa[j-1, j],
+// ..., K_aa[j - skyline[j], j] from maxa[j]. Here both come straight from the CSR quadrant, no dense detour.
+namespace {
+
+// one thread per K_aa row i: every stored entry (i, j), j > i, is != 0 by construction
+__global__ void skyline_height_kernel(int64_t n_aa, const int64_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                                      int32_t* __restrict__ sky) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_aa) return;
+  for (int64_t p = rp[i]; p < rp[i + 1]; ++p) {
+    const int32_t j = ci[p];
+    if (j > int32_t(i)) atomicMax(sky + j, j - int32_t(i));  // integer max: order independent
+  }
+}
+
+__global__ void skyline_len_kernel(int64_t n_aa, const int32_t* __restrict__ sky, int32_t* __restrict__ len) {
+  int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j <= n_aa) len[j] = j < n_aa ? sky[j] + 1 : 0;
+}
+
+__global__ void skyline_fill_kernel(int64_t n_aa, const int64_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                                    const double* __restrict__ va, const int64_t* __restrict__ maxa,
+                                    double* __restrict__ a) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_aa) return;
+  for (int64_t p = rp[i]; p < rp[i + 1]; ++p) {
+    const int32_t j = ci[p];
+    if (j >= int32_t(i)) a[maxa[j] + (j - int32_t(i))] = va[p];
+  }
+}
+
+}  // namespace
+
+int32_t run_skyline(Handle* h) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  Handle::Separated& S = h->sep;
+  const int64_t n = S.n_aa;
+  S.sky_valid = false;
+  FEMGPU_CUDA_CHECK(h, S.sky.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, S.maxa.reserve(size_t(n) + 2));
+  DevBuf<int32_t>& len = S.tmp[0];  // the class flags of run_separate are no longer needed
+  FEMGPU_CUDA_CHECK(h, len.reserve(size_t(n) + 2));
+  FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(S.sky.p, 0, (size_t(n) + 1) * 4, s));
+  skyline_height_kernel<<<div_up(n, 256), 256, 0, s>>>(n, S.row_ptr[0].p, S.col[0].p, S.sky.p);
+  skyline_len_kernel<<<div_up(n + 1, 256), 256, 0, s>>>(n, S.sky.p, len.p);
+  FEMGPU_CUDA_CHECK(h, scan_i32_to_i64<int>(len.p, S.maxa.p, n + 1, s));
+  int64_t total = 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&total, S.maxa.p + n, 8, cudaMemcpyDeviceToHost, s));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(s));
+  size_t free_b = 0, total_b = 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemGetInfo(&free_b, &total_b));
+  if (uint64_t(total) * 8 > uint64_t(free_b) + S.sky_a.cap * 8)
+    return h->fail(FEMGPU_ERR_LIMIT, "the skyline of K_aa holds " + std::to_string(total) +
+                                         " values: too large for the device (use the sparse separation)");
+  FEMGPU_CUDA_CHECK(h, S.sky_a.reserve(size_t(total) + 1));
+  FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(S.sky_a.p, 0, size_t(total) * 8, s));
+  skyline_fill_kernel<<<div_up(n, 256), 256, 0, s>>>(n, S.row_ptr[0].p, S.col[0].p, S.val[0].p, S.maxa.p, S.sky_a.p);
+  h->launches += 3;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  S.sky_total = total;
+  S.sky_valid = true;
   return 0;
 }
 
@@ -643,12 +721,49 @@ int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_
   if (h->dist.enabled)
     return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_sparse is single-GPU for now (the rows of a multi-GPU "
                                      "assembly stay partitioned)");
-  int32_t st = femgpu::run_separate(h);
+  int32_t st = femgpu::run_separate(h, false);
   if (st) return st;
   if (n_aa) *n_aa = h->sep.n_aa;
   if (n_bb) *n_bb = h->sep.n_bb;
   if (nnz)
     for (int q = 0; q < 4; ++q) nnz[q] = h->sep.nnz[q];
+  return 0;
+}
+
+int32_t femgpu_separate_direct(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t* skyline_values) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0)
+    return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
+                                         "femgpu has no CPU fallback");
+  if (!h->symbolic_valid || h->n_numeric == 0)
+    return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_direct needs an assembled matrix (femgpu_assemble)");
+  if (h->dist.enabled)
+    return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_direct is single-GPU (the rows of a multi-GPU assembly stay partitioned)");
+  int32_t st = femgpu::run_separate(h, true);
+  if (st) return st;
+  if ((st = femgpu::run_skyline(h))) return st;
+  if (n_aa) *n_aa = h->sep.n_aa;
+  if (n_bb) *n_bb = h->sep.n_bb;
+  if (skyline_values) *skyline_values = h->sep.sky_total;
+  return 0;
+}
+
+int32_t femgpu_get_skyline(femgpu_t* h, int64_t* k_aa_skyline, double* a, int64_t* maxa) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  if (!h->sep.sky_valid) return h->fail(FEMGPU_ERR_USAGE, "no skyline: call femgpu_separate_direct first");
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const size_t n = size_t(h->sep.n_aa);
+  if (k_aa_skyline && n) {  // widened on the host: the reference's Vec<usize>
+    std::vector<int32_t> tmp(n);
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(tmp.data(), h->sep.sky.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i) k_aa_skyline[i] = tmp[i];
+  }
+  if (a && h->sep.sky_total)
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(a, h->sep.sky_a.p, size_t(h->sep.sky_total) * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (maxa) FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(maxa, h->sep.maxa.p, (n + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -325,6 +325,20 @@ class FEM:
         self._check(self._L.femgpu_separated_rhs(self._h, _p(b, _lib.dp), None))
         return SeparatedStiffnessMatrixSparse(ia, ib, quads, b, float(ms.value))
 
+    def separate_stiffness_matrix_direct(self):
+        """methods_for_separate_stiffness_matrix.rs:63-215 without the dense detour: (k_aa_indexes, k_bb_indexes,
+        k_aa_skyline, a, maxa) with K_aa in the compacted column form of the skyline solver
+        (convert_k_aa_into_compacted_form, methods_for_global_analysis.rs:50-80). K_ab / K_ba / K_bb stay
+        available as the CSR quadrants of the handle."""
+        na, nb, nv = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._L.femgpu_separate_direct(self._h, C.byref(na), C.byref(nb), C.byref(nv)))
+        self._sep_counts = (int(na.value), int(nb.value))
+        ia, ib = np.empty(na.value, np.int64), np.empty(nb.value, np.int64)
+        self._check(self._L.femgpu_get_separated_indexes(self._h, _p(ia, _lib.i64p), _p(ib, _lib.i64p)))
+        sky, a, maxa = np.empty(na.value, np.int64), np.empty(nv.value, np.float64), np.empty(na.value + 1, np.int64)
+        self._check(self._L.femgpu_get_skyline(self._h, _p(sky, _lib.i64p), _p(a, _lib.dp), _p(maxa, _lib.i64p)))
+        return ia, ib, sky, a, maxa
+
     # ------------------------------------------------------------------ global analysis, element results
     def _solve(self, preconditioner: int, max_iter: int, copy_out: bool):
         it = C.c_int64()

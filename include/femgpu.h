@@ -77,6 +77,8 @@ enum {
   FEMGPU_E_NO_STIFFNESS_FOR_DISPLACEMENT = 41,
   FEMGPU_E_NO_RESTRAINTS = 42,
   FEMGPU_E_KAA_EMPTY = 43,
+  /* methods_for_separate_stiffness_matrix.rs:49-58 (direct separation only) */
+  FEMGPU_E_NO_STIFFNESS_FOR_LOAD = 44,
   /* find_ua_vector_iterative_*: "PCG failed" (methods_for_global_analysis.rs:228,272) */
   FEMGPU_E_SOLVER = 50
 };
@@ -240,6 +242,17 @@ int32_t femgpu_get_forces(femgpu_t* h, double* forces, const double** forces_dev
  * b = R_a - K_ab u_b (find_b_sparse, methods_for_global_analysis.rs:28-48).
  * nnz order: aa, ab, ba, bb. Out-pointers may be NULL. Single GPU. */
 int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t nnz[4]);
+/* FEM::separate_stiffness_matrix_direct()              methods_for_separate_stiffness_matrix.rs:63-215
+ * Same classification as the sparse separation plus the direct variant's extra check (a load on a DOF without
+ * stiffness: "There are no stiffness to withstand load ..."; no restraints: "There are no restraints applied!").
+ * The reference makes K dense to collect k_aa_skyline and dense quadrants whose only consumer turns K_aa into the
+ * compacted column form of its skyline solver (convert_k_aa_into_compacted_form, methods_for_global_analysis.rs:50-80);
+ * here k_aa_skyline and (a, maxa) are built straight from the CSR quadrant on the device, and K_ab / K_ba / K_bb
+ * stay available as the CSR quadrants of femgpu_get_separated_csr. skyline_values = length of `a`. */
+int32_t femgpu_separate_direct(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t* skyline_values);
+/* k_aa_skyline [n_aa], a [skyline_values], maxa [n_aa + 1]: column j of K_aa = a[maxa[j]] (diagonal),
+ * a[maxa[j] + k] = K_aa[j - k, j] for k <= k_aa_skyline[j]. Pointers may be NULL. */
+int32_t femgpu_get_skyline(femgpu_t* h, int64_t* k_aa_skyline, double* a, int64_t* maxa);
 /* k_aa_indexes [n_aa] / k_bb_indexes [n_bb]: global DOF index of every local row */
 int32_t femgpu_get_separated_indexes(femgpu_t* h, int64_t* k_aa_indexes, int64_t* k_bb_indexes);
 /* quadrant `which` (0 aa, 1 ab, 2 ba, 3 bb): row_ptr [rows+1], col_idx / values [nnz] */

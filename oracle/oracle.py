@@ -419,3 +419,45 @@ def compose_global_analysis_result(sep, u_a, r_r, forces, displacements):
     d[sep["k_aa_indexes"]] = u_a
     f[sep["k_bb_indexes"]] = r_r
     return d, f
+
+
+# ---------------------------------------------------------------------------------------------
+# Direct separation (restatement, numpy; index work and copied values).
+# FEM::separate_stiffness_matrix_direct, methods_for_separate_stiffness_matrix.rs:63-215, with check_excluded_index
+# :36-61, and the compacted column form its consumer builds (convert_k_aa_into_compacted_form,
+# methods_for_global_analysis.rs:50-80). Pinned on the reference's direct test model (src/tests/fem/test_fem.rs:5-64:
+# one free DOF, K_aa = [EA/L], skyline [0]) in tests/test_separation.py.
+# ---------------------------------------------------------------------------------------------
+def separate_direct(n_dof, rows, cols, vals, constrained, node_numbers=None, forces=None):
+    rows = np.asarray(rows, np.int64); cols = np.asarray(cols, np.int64); vals = np.asarray(vals, np.float64)
+    constrained = np.asarray(constrained, bool)
+    forces = np.zeros(n_dof) if forces is None else np.asarray(forces, np.float64)
+    diag = np.zeros(n_dof)
+    d = rows == cols
+    diag[rows[d]] = vals[d]
+    k_aa, k_bb = [], []
+    for index in range(n_dof):                                   # :70-86, ascending
+        if diag[index] == 0.0:
+            number = 0 if node_numbers is None or index // 6 >= len(node_numbers) else int(node_numbers[index // 6])
+            if constrained[index]:                               # check_excluded_index :43-48
+                raise SeparationError(f"There are no stiffness to withstand displacement {DOF_NAMES[index % 6]} applied to node {number}!")
+            if forces[index] != 0.0:                             # :50-58
+                raise SeparationError(f"There are no stiffness to withstand load {DOF_NAMES[index % 6]} applied to node {number}!")
+        elif constrained[index]:
+            k_bb.append(index)
+        else:
+            k_aa.append(index)
+    if not k_bb:
+        raise SeparationError("There are no restraints applied!")  # :88-90
+    k_aa = np.asarray(k_aa, np.int64); k_bb = np.asarray(k_bb, np.int64)
+    pos = np.full(n_dof, -1, np.int64); pos[k_aa] = np.arange(len(k_aa))
+    m = (pos[rows] >= 0) & (pos[cols] >= 0) & (vals != 0.0)
+    i, j, v = pos[rows][m], pos[cols][m], vals[m]
+    skyline = np.zeros(len(k_aa), np.int64)                      # :117-129: j - i over the non-zero entries above the diagonal
+    up = j > i
+    np.maximum.at(skyline, j[up], (j - i)[up])
+    maxa = np.concatenate([[0], np.cumsum(skyline + 1)])         # methods_for_global_analysis.rs:50-80
+    a = np.zeros(int(maxa[-1]))
+    on = j >= i
+    a[maxa[j[on]] + (j - i)[on]] = v[on]
+    return {"k_aa_indexes": k_aa, "k_bb_indexes": k_bb, "k_aa_skyline": skyline, "a": a, "maxa": maxa}

@@ -274,3 +274,76 @@ def test_gpu_distributed_loads_match_oracle(which):
     sep = fem.separate_stiffness_matrix_sparse_iterative()
     assert np.abs(sep.b - ref[sep.k_aa_indexes]).max() <= 1e-12 * scale   # u_b = 0: b = R_a
     fem.close()
+
+
+# ---------------------------------------------------------------------------- direct separation (skyline)
+def test_oracle_direct_separation_on_the_reference_test_model():
+    """test_fem.rs:5-64 (the direct path): one free DOF -> K_aa = [EA/L], skyline [0], a = [EA/L], maxa = [0, 1]"""
+    k = 1e6 * 2.0 / 30.0
+    c = np.zeros(12, bool); c[0] = True
+    f = np.zeros(12); f[6] = 100.0
+    d = O.separate_direct(12, [0, 0, 6, 6], [0, 6, 0, 6], [k, -k, -k, k], c, [1, 2], f)
+    assert list(d["k_aa_indexes"]) == [6] and list(d["k_bb_indexes"]) == [0]
+    assert list(d["k_aa_skyline"]) == [0] and list(d["a"]) == [k] and list(d["maxa"]) == [0, 1]
+    assert d["a"][0] and 100.0 / d["a"][0] == 0.0014999999999999998        # colsol on a 1 x 1 system
+    f[7] = 1.0                                                               # a load on a DOF without stiffness
+    with pytest.raises(O.SeparationError, match="There are no stiffness to withstand load Y applied to node 2!"):
+        O.separate_direct(12, [0, 0, 6, 6], [0, 6, 0, 6], [k, -k, -k, k], c, [1, 2], f)
+    with pytest.raises(O.SeparationError, match="There are no restraints applied!"):
+        O.separate_direct(12, [0, 0, 6, 6], [0, 6, 0, 6], [k, -k, -k, k], np.zeros(12, bool), [1, 2])
+
+
+def test_oracle_skyline_form():
+    # 4 free DOFs, entries (0,2) and (1,3) above the diagonal -> heights [0, 0, 2, 2]
+    r = [0, 1, 2, 3, 0, 2, 1, 3, 4]; c_ = [0, 1, 2, 3, 2, 0, 3, 1, 4]; v = [4., 5., 6., 7., 1., 1., 2., 2., 9.]
+    con = np.zeros(5, bool); con[4] = True
+    d = O.separate_direct(5, r, c_, v, con)
+    assert list(d["k_aa_skyline"]) == [0, 0, 2, 2]
+    assert list(d["maxa"]) == [0, 1, 2, 5, 8]
+    assert list(d["a"]) == [4., 5., 6., 0., 1., 7., 0., 2.]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["reference", "mixed", "beams"])
+def test_direct_separation_matches_oracle(which):
+    if which == "reference":
+        mesh = meshes.reference_truss_model()
+        fixed_nodes, fixed_dofs = [0], [0]
+    else:
+        mesh = meshes.mixed_structure(7, 5) if which == "mixed" else meshes.beam_frame(4, 10**9)
+        y0 = np.flatnonzero(np.asarray(mesh["y"]) == np.min(mesh["y"]))
+        fixed_nodes, fixed_dofs = np.repeat(y0, 6), np.tile(np.arange(6), len(y0))
+    n = len(mesh["x"])
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    fem.add_displacement(np.asarray(fixed_nodes) + 1, fixed_dofs, np.zeros(len(fixed_nodes)))
+    fem.add_concentrated_load(n, DOFParameter.X, 100.0)
+    ia, ib, sky, a, maxa = fem.separate_stiffness_matrix_direct()
+    rp, ci, v = fem.csr()
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    con = np.zeros(6 * n, bool); con[6 * np.asarray(fixed_nodes) + np.asarray(fixed_dofs)] = True
+    f = np.zeros(6 * n); f[6 * (n - 1)] = 100.0
+    ref = O.separate_direct(6 * n, rows, ci, v, con, np.arange(1, n + 1), f)       # same K: bit-for-bit
+    assert np.array_equal(ia, ref["k_aa_indexes"]) and np.array_equal(ib, ref["k_bb_indexes"])
+    assert np.array_equal(sky, ref["k_aa_skyline"]) and np.array_equal(maxa, ref["maxa"])
+    assert np.array_equal(a, ref["a"])
+    if which == "reference":
+        assert list(sky) == [0] and a[0] == 66666.66666666667
+    fem.close()
+
+
+@pytest.mark.gpu
+def test_direct_separation_errors():
+    mesh = meshes.reference_truss_model()
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], 2, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    with pytest.raises(FemError, match="There are no restraints applied!"):
+        fem.separate_stiffness_matrix_direct()
+    fem.add_displacement(1, DOFParameter.X, 0.0)
+    fem.add_concentrated_load(2, DOFParameter.Y, 5.0)        # the truss has no stiffness in y
+    with pytest.raises(FemError, match="There are no stiffness to withstand load Y applied to node 2!"):
+        fem.separate_stiffness_matrix_direct()
+    fem.separate_stiffness_matrix_sparse_iterative()         # the sparse variant does not look at the loads
+    fem.close()
