@@ -149,6 +149,37 @@ __device__ __forceinline__ void store_block(double* __restrict__ img, const uint
   }
 }
 
+// One half of a block: dof rows 0..2 (half 0: acc[0..17]) or 3..5 (half 1: acc[18..35]). Used when the two
+// chunks of a split block each finish one half (phase B, pair merge). A 3x3 block only has a half 0.
+__device__ __forceinline__ void store_half(double* __restrict__ img, const uint4 m, const double acc[36], int half) {
+  const uint32_t seg0 = m.x, seg3 = m.y, s03 = m.z & 0xFFFFu, s35 = m.z >> 16;
+  const bool full = seg3 != 0xFFFFFFFFu;
+  if (full) {
+    const uint32_t seg = half ? seg3 : seg0, st = half ? s35 : s03;
+    const bool al = ((seg | st) & 1u) == 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double* r = img + seg + i * st;
+      if (al) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          reinterpret_cast<double2*>(r)[j] = half ? make_double2(acc[18 + 6 * i + 2 * j], acc[18 + 6 * i + 2 * j + 1])
+                                                  : make_double2(acc[6 * i + 2 * j], acc[6 * i + 2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) r[j] = half ? acc[18 + 6 * i + j] : acc[6 * i + j];
+      }
+    }
+  } else if (half == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double* r0 = img + seg0 + i * s03;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) r0[j] = acc[6 * i + j];
+    }
+  }
+}
+
 // ---- staged, persistent, pipelined kernel --------------------------------------------------------
 
 // kT = threads per CTA (32 or 64), a template parameter of everything below.
@@ -477,7 +508,24 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
   // lanes right above it, in chunk order (so the sum is (chunk 0 + chunk 1) + chunk 2 ...), and stores
   // the block once. No barrier and no read-modify-write through the image.
   const uint32_t rounds = kSplit ? R.rounds() : 0u;  // CTA-uniform
-  if (kSplit && rounds) {
+  if (kSplit && rounds == 1u) {
+    // Every split block of the slab has two chunks, in lanes l and l + 1. Instead of handing all 36 partial sums
+    // to lane l, the two lanes swap halves — l gives its rows 3..5 and gets the partner's rows 0..2, in the same
+    // shuffle — and each finishes and stores one half: 18 shuffles and 9 stores per lane instead of 36 and 18 on
+    // one. a + b == b + a exactly, so the block is the same (chunk 0) + (chunk 1) as in the general path below.
+    const bool part = pending != 0u;
+    if (__any_sync(0xFFFFFFFFu, part)) {  // warp-uniform
+      const uint32_t lane = threadIdx.x & 31u, partner = part ? (sender ? lane - 1u : lane + 1u) : lane;
+#pragma unroll
+      for (int q = 0; q < 18; ++q) {
+        const double give = sender ? acc[q] : acc[q + 18];
+        const double t = __shfl_sync(0xFFFFFFFFu, give, partner);
+        if (sender) acc[q + 18] += t;
+        else if (part) acc[q] += t;
+      }
+      if (part) store_half(img, pending_m, acc, sender ? 1 : 0);
+    }
+  } else if (kSplit && rounds) {
     const uint32_t recv = sender ? 0u : pending;
     for (uint32_t r = 1; r <= rounds; ++r) {
       if (!__any_sync(0xFFFFFFFFu, recv >= r)) continue;  // warp-uniform
@@ -491,20 +539,28 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
   }
 }
 
+// Two-warp shape: warp 1 finishes its loop trips earlier than warp 0 (which carries the beam trips and the
+// merges), so it builds the plate forms of the NEXT slab in that time (the forms are double-buffered) and phase A
+// leaves the critical path of the CTA. 0 = both warps build the current slab's forms at the top of the iteration.
+#ifndef FEMGPU_AHEAD
+#define FEMGPU_AHEAD 1
+#endif
 // registers per thread of the two-warp shape: 168 = three warps per SM sub-partition (5-6 CTAs per SM when
-// shared memory allows; 12 bytes of spill), 200 = two (4 CTAs per SM)
+// shared memory allows; a few bytes of spill), 200 = two (4 CTAs per SM)
 #ifndef FEMGPU_MAXNREG64
 #define FEMGPU_MAXNREG64 168
 #endif
 template <int kT, bool kSplit, bool kBulk>
 __global__ void __maxnreg__(kT == 64 ? FEMGPU_MAXNREG64 : 255)
 assemble_kernel(const AsmArgs A) {
+  constexpr bool kAhead = kT == 64 && FEMGPU_AHEAD != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t tid = threadIdx.x, stride = gridDim.x;
   double* img = reinterpret_cast<double*>(smem);
-  double* form = reinterpret_cast<double*>(smem + A.smem_img);
-  double* rawp = reinterpret_cast<double*>(smem + A.smem_img + A.smem_form);
-  unsigned char* stage0 = smem + A.smem_img + A.smem_form + A.smem_rawp;
+  double* form0 = reinterpret_cast<double*>(smem + A.smem_img);
+  const uint32_t form_all = (kAhead ? 2u : 1u) * A.smem_form;
+  double* rawp = reinterpret_cast<double*>(smem + A.smem_img + form_all);
+  unsigned char* stage0 = smem + A.smem_img + form_all + A.smem_rawp;
   unsigned char* dbuf0 = stage0 + 2 * A.smem_stage;  // three rotating descriptor blocks
   const uint32_t rawp_s = smem_u32(rawp), stage0_s = smem_u32(stage0), dbuf0_s = smem_u32(dbuf0);
 
@@ -512,6 +568,7 @@ assemble_kernel(const AsmArgs A) {
   if (k >= A.n_slabs) return;
   const uint32_t mbar_s = dbuf0_s + 3 * desc_bytes<kT>();
   PlatePair* pairs = reinterpret_cast<PlatePair*>(dbuf0 + 3 * desc_bytes<kT>() + 16);
+  volatile uint32_t* flat_flag = reinterpret_cast<volatile uint32_t*>(dbuf0 + 3 * desc_bytes<kT>() + 8);  // [2], kAhead
   if (tid == 0) mbar_init(mbar_s, kT);
   if (tid < 16) pairs[tid] = make_plate_pair(int(tid >> 2), int(tid & 3u));
   cta_sync<kT>();
@@ -523,6 +580,11 @@ assemble_kernel(const AsmArgs A) {
   issue_stage<kT, kBulk>(A, cur, stage0_s, rawp_s, mbar_s, tid);
   if (k + stride < A.n_slabs) issue_desc<kT>(A, k + stride, dbuf0_s + desc_bytes<kT>(), tid);
   cp_async_arrive(mbar_s);
+  if (kAhead) {  // the first slab's forms: both warps, like the classic phase A
+    mbar_wait(mbar_s, 1u);
+    const bool flat0 = phase_a<kT>(cur, rawp, form0, tid);
+    if (tid == 0) flat_flag[0] = flat0 ? 1u : 0u;
+  }
 
   PHASE_DECL
   uint32_t d_cur = 0;  // descriptor block of `cur`
@@ -530,6 +592,7 @@ assemble_kernel(const AsmArgs A) {
     PHASE_MARK(0)
     const uint32_t buf = it & 1u;
     const unsigned char* stage = stage0 + buf * A.smem_stage;
+    double* form = kAhead ? form0 + buf * (A.smem_form / 8u) : form0;
     const uint32_t d_nxt = (d_cur == 2u) ? 0u : d_cur + 1u, d_nn = (d_nxt == 2u) ? 0u : d_nxt + 1u;
     const bool has_next = k + stride < A.n_slabs;
     // slab `cur`: its records, metadata and entries (and the next slab's descriptor) were
@@ -538,10 +601,21 @@ assemble_kernel(const AsmArgs A) {
     mbar_wait(mbar_s, (it + 1u) & 1u);
     PHASE_MARK(1)
     PHASE_MARK(2)
-    const bool all_flat = phase_a<kT>(cur, rawp, form, tid);
+    bool all_flat;
+    if (kAhead) {
+      // forms[buf] and their flag were finished before the barrier that closed the previous slab (or in the
+      // prologue); this barrier publishes that the TMA engine has read the previous slab out of the image
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      cta_sync<kT>();
+      all_flat = flat_flag[buf] != 0u;
+    } else {
+      all_flat = phase_a<kT>(cur, rawp, form, tid);
+    }
     PHASE_MARK(3)
+    uint32_t np_next = 0;
     if (has_next) {
       const SlabRegs<kT> nxt = read_desc<kT, kBulk>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
+      np_next = nxt.n_plate();
       issue_stage<kT, kBulk>(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, mbar_s, tid);
       if (k + 2 * stride < A.n_slabs) issue_desc<kT>(A, k + 2 * stride, dbuf0_s + d_nn * desc_bytes<kT>(), tid);
       cp_async_arrive(mbar_s);
@@ -560,8 +634,29 @@ assemble_kernel(const AsmArgs A) {
     phase_b<kT, kSplit>(cur, stage, form, img, pairs, all_flat);
 #endif
     PHASE_MARK(6)
+    if (kAhead && has_next && tid >= 32u) {
+      // warp 1: the next slab's records have been on their way since the top of this iteration
+      mbar_wait(mbar_s, it & 1u);  // batch it + 2
+      double* form_next = form0 + (buf ^ 1u) * (A.smem_form / 8u);
+      bool flat = true;
+      for (uint32_t idx = tid - 32u; idx < np_next; idx += 32u) {
+        double raw[20];
+        const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const double2 v = src[i];
+          raw[2 * i] = v.x;
+          raw[2 * i + 1] = v.y;
+        }
+        flat = flat && raw[15] != 0.0;
+        plate_shared_record(raw, form_next + idx * uint32_t(kPlateSlotDoubles));
+      }
+      flat = __all_sync(0xFFFFFFFFu, flat) != 0;
+      if (tid == 32u) flat_flag[buf ^ 1u] = flat ? 1u : 0u;
+    }
 
     const uint32_t n = cur.val_count();
+    if (kAhead && !n) cta_sync<kT>();  // the barrier below is what orders warp 1's forms before their use
     if (n) {
       double* out = A.values + cur.val_base();
       if (((uint32_t(cur.val_base()) | n) & 1u) == 0) {
@@ -716,7 +811,8 @@ int32_t run_assembly(Handle* h) {
   A.smem_stage = up(h->smem_stage);
   const int threads = h->asm_threads;
   const uint32_t desc = threads == 64 ? desc_bytes<64>() : desc_bytes<32>();
-  const uint32_t smem = A.smem_img + A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * desc + 16 +
+  const uint32_t form_bufs = (threads == 64 && FEMGPU_AHEAD != 0) ? 2u : 1u;  // kAhead of assemble_kernel
+  const uint32_t smem = A.smem_img + form_bufs * A.smem_form + A.smem_rawp + 2 * A.smem_stage + 3 * desc + 16 +
                         16 * uint32_t(sizeof(PlatePair));
   if (h->n_unstaged < h->n_slabs) {
     const bool split = h->asm_split, bulk = h->asm_bulk;

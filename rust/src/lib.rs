@@ -34,6 +34,8 @@ extern "C" {
     fn femgpu_get_separated_indexes(h: *mut FemGpu, k_aa_indexes: *mut i64, k_bb_indexes: *mut i64) -> i32;
     fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_separated_rhs(h: *mut FemGpu, b: *mut f64, b_device: *mut *const f64) -> i32;
+    fn femgpu_separate_direct(h: *mut FemGpu, n_aa: *mut i64, n_bb: *mut i64, skyline_values: *mut i64) -> i32;
+    fn femgpu_get_skyline(h: *mut FemGpu, k_aa_skyline: *mut i64, a: *mut f64, maxa: *mut i64) -> i32;
     fn femgpu_counts(h: *const FemGpu, nodes: *mut u64, truss: *mut u64, beam: *mut u64, plate: *mut u64) -> i32;
     fn femgpu_get_numbers(h: *const FemGpu, family: i32, out: *mut u32) -> i32;
     fn femgpu_solve_pcg(h: *mut FemGpu, preconditioner: i32, max_iter: i64, iterations: *mut i64) -> i32;
@@ -190,6 +192,18 @@ impl FEM {
 }
 
 impl FEM {
+    /// methods_for_separate_stiffness_matrix.rs:63 without the dense detour: (k_aa_indexes, k_bb_indexes,
+    /// k_aa_skyline, a, maxa) — K_aa already in the compacted column form colsol::factorization takes
+    /// (methods_for_global_analysis.rs:50-80, :183)
+    pub fn separate_stiffness_matrix_direct(&mut self) -> Result<(Vec<i64>, Vec<i64>, Vec<i64>, Vec<f64>, Vec<i64>), String> {
+        let (mut n_aa, mut n_bb, mut n_val) = (0i64, 0i64, 0i64);
+        self.check(unsafe { femgpu_separate_direct(self.h, &mut n_aa, &mut n_bb, &mut n_val) })?;
+        let (mut ia, mut ib) = (vec![0i64; n_aa as usize], vec![0i64; n_bb as usize]);
+        self.check(unsafe { femgpu_get_separated_indexes(self.h, ia.as_mut_ptr(), ib.as_mut_ptr()) })?;
+        let (mut sky, mut a, mut maxa) = (vec![0i64; n_aa as usize], vec![0f64; n_val as usize], vec![0i64; n_aa as usize + 1]);
+        self.check(unsafe { femgpu_get_skyline(self.h, sky.as_mut_ptr(), a.as_mut_ptr(), maxa.as_mut_ptr()) })?;
+        Ok((ia, ib, sky, a, maxa))
+    }
     /// methods_for_global_analysis.rs:189 / :235 — K_aa, r_a and u_b never left the device, so the three
     /// arguments of the reference collapse into the handle. Returns (u_a, iterations).
     pub fn find_ua_vector_iterative_pcg_jacobi_sparse(&mut self, n_aa: usize, max_iter: usize) -> Result<(Vec<f64>, usize), String> {
