@@ -266,8 +266,15 @@ __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_
                reinterpret_cast<const uint4*>(A.slabs + k) + (tid - kItemLanes - kElistLanes));
 }
 
-// kBulk: a lane holds the element slots j * kT + tid (it heads the run-wise bulk copies); otherwise two
-// adjacent lanes share the slots j * kT / 2 + tid / 2 (they copy alternate 16-byte chunks of a record)
+// Issuing a TMA bulk copy stalls the issuing warp for a few hundred cycles, and a slab needs five to eight of
+// them. In the two-warp shape warp 0 is the critical one (it carries the beam trips and the merges), so warp 1
+// issues the metadata / entry loads (its lane 0 = thread kStageThread) and heads the element slots 0..31, where
+// the trusses, the beams and most plates of a slab sit; warp 0 keeps the slots 32..63.
+template <int kT> __device__ __forceinline__ uint32_t bulk_slot_lane(uint32_t tid) { return kT == 64 ? tid ^ 32u : tid; }
+template <int kT> __device__ __forceinline__ uint32_t stage_thread() { return kT == 64 ? 32u : 0u; }
+
+// kBulk: a lane holds the element slots j * kT + bulk_slot_lane(tid) (it heads the run-wise bulk copies); otherwise
+// two adjacent lanes share the slots j * kT / 2 + tid / 2 (they copy alternate 16-byte chunks of a record)
 template <int kT, bool kBulk>
 __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uint32_t tid) {
   SlabRegs<kT> R;
@@ -278,7 +285,7 @@ __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uin
   const uint32_t* el = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>());
 #pragma unroll
   for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
-    if (kBulk) R.fe[j] = j < kElistStride / kT ? el[j * kT + tid] : 0xFFFFFFFFu;
+    if (kBulk) R.fe[j] = j < kElistStride / kT ? el[j * kT + bulk_slot_lane<kT>(tid)] : 0xFFFFFFFFu;
     else R.fe[j] = el[j * (kT / 2) + (tid >> 1)];
   }
   const uint32_t w = reinterpret_cast<const uint32_t*>(dbuf + kDescItemsOff)[tid];
@@ -297,7 +304,7 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
   // block metadata and contribution entries are contiguous: two TMA bulk loads by one thread,
   // completing on the same mbarrier as the record copies
   const uint32_t nt = R.n_truss(), nbm = R.n_beam();
-  if (tid == 0 && R.blk_count()) {
+  if (tid == (kBulk ? stage_thread<kT>() : 0u) && R.blk_count()) {
     const uint32_t meta_bytes = R.blk_count() * 16u, ent_bytes = R.slab_c_count() ? R.ent_bytes() : 0u;
     const uint32_t rec_bytes = kBulk ? nt * uint32_t(kTrussSlotDoubles * 8) + nbm * uint32_t(kBeamSlotDoubles * 8) +
                                            R.n_plate() * uint32_t(kPlateRawDoubles * 8)
@@ -336,7 +343,7 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
         uint32_t len = after ? uint32_t(__ffs(int(after))) : 32u - lane;
         const uint32_t stop = (~copies) >> lane;  // bit 0 = this lane
         if (stop) len = min(len, uint32_t(__ffs(int(stop))) - 1u);
-        const uint32_t slot = uint32_t(j) * kT + tid;
+        const uint32_t slot = uint32_t(j) * kT + bulk_slot_lane<kT>(tid);
         uint32_t dst, bytes;
         const double* src;
         if (family == FEMGPU_PLATE) {
