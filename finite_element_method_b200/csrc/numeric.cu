@@ -267,11 +267,14 @@ __device__ __forceinline__ void issue_desc(const AsmArgs& A, uint32_t k, uint32_
 }
 
 // Issuing a TMA bulk copy stalls the issuing warp for a few hundred cycles, and a slab needs five to eight of
-// them. In the two-warp shape warp 0 is the critical one (it carries the beam trips and the merges), so warp 1
-// issues the metadata / entry loads (its lane 0 = thread kStageThread) and heads the element slots 0..31, where
-// the trusses, the beams and most plates of a slab sit; warp 0 keeps the slots 32..63.
-template <int kT> __device__ __forceinline__ uint32_t bulk_slot_lane(uint32_t tid) { return kT == 64 ? tid ^ 32u : tid; }
-template <int kT> __device__ __forceinline__ uint32_t stage_thread() { return kT == 64 ? 32u : 0u; }
+// them. In the two-warp shape the warp that is NOT the critical one should issue them: in a slab without plates
+// that is warp 1 (warp 0 carries the split blocks and their merges) — it issues the metadata / entry loads and
+// heads the element slots 0..31, where most records of a slab sit (B: 0.437 -> 0.430 ms); in a slab with plates
+// warp 1 already builds the next slab's forms, and warp 0 keeps the issue work (M: 3.25 ms, against 3.36 the
+// other way round). `flip` is uniform over the CTA (it comes from the slab descriptor).
+template <int kT> __device__ __forceinline__ uint32_t bulk_slot_lane(uint32_t tid, bool flip) {
+  return kT == 64 && flip ? tid ^ 32u : tid;
+}
 
 // kBulk: a lane holds the element slots j * kT + bulk_slot_lane(tid) (it heads the run-wise bulk copies); otherwise
 // two adjacent lanes share the slots j * kT / 2 + tid / 2 (they copy alternate 16-byte chunks of a record)
@@ -285,7 +288,7 @@ __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uin
   const uint32_t* el = reinterpret_cast<const uint32_t*>(dbuf + desc_elist_off<kT>());
 #pragma unroll
   for (int j = 0; j < SlabRegs<kT>::kElistPerPair; ++j) {
-    if (kBulk) R.fe[j] = j < kElistStride / kT ? el[j * kT + bulk_slot_lane<kT>(tid)] : 0xFFFFFFFFu;
+    if (kBulk) R.fe[j] = j < kElistStride / kT ? el[j * kT + bulk_slot_lane<kT>(tid, R.n_plate() == 0u)] : 0xFFFFFFFFu;
     else R.fe[j] = el[j * (kT / 2) + (tid >> 1)];
   }
   const uint32_t w = reinterpret_cast<const uint32_t*>(dbuf + kDescItemsOff)[tid];
@@ -304,7 +307,10 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
   // block metadata and contribution entries are contiguous: two TMA bulk loads by one thread,
   // completing on the same mbarrier as the record copies
   const uint32_t nt = R.n_truss(), nbm = R.n_beam();
-  if (tid == (kBulk ? stage_thread<kT>() : 0u) && R.blk_count()) {
+  const bool flip = kBulk && kT == 64 && R.n_plate() == 0u;
+  // the metadata / entry loads always go out from warp 1 in the two-warp bulk shape: in a slab with plates that
+  // splits the issue work about evenly (warp 0 heads five record runs, warp 1 one + these two)
+  if (tid == (kBulk && kT == 64 ? 32u : 0u) && R.blk_count()) {
     const uint32_t meta_bytes = R.blk_count() * 16u, ent_bytes = R.slab_c_count() ? R.ent_bytes() : 0u;
     const uint32_t rec_bytes = kBulk ? nt * uint32_t(kTrussSlotDoubles * 8) + nbm * uint32_t(kBeamSlotDoubles * 8) +
                                            R.n_plate() * uint32_t(kPlateRawDoubles * 8)
@@ -343,7 +349,7 @@ __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>
         uint32_t len = after ? uint32_t(__ffs(int(after))) : 32u - lane;
         const uint32_t stop = (~copies) >> lane;  // bit 0 = this lane
         if (stop) len = min(len, uint32_t(__ffs(int(stop))) - 1u);
-        const uint32_t slot = uint32_t(j) * kT + bulk_slot_lane<kT>(tid);
+        const uint32_t slot = uint32_t(j) * kT + bulk_slot_lane<kT>(tid, flip);
         uint32_t dst, bytes;
         const double* src;
         if (family == FEMGPU_PLATE) {
