@@ -74,6 +74,45 @@ def test_both_cta_shapes_match_oracle(name, threads, O, monkeypatch):
     fem.close()
 
 
+@pytest.mark.parametrize("threads", [32, 64])
+@pytest.mark.parametrize("name", ["plate-jitter", "mixed", "beam-frame", "truss-lattice-jitter"])
+def test_record_staging_variants_agree_bit_for_bit(name, threads, monkeypatch):
+    """Element records reach shared memory either run-wise with TMA bulk copies (consecutively numbered meshes) or
+    per element with cp.async (the symbolic pass measures the runs and picks one); same records, same arithmetic:
+    the matrices must be identical. Also with the bank-spreading lane order, which only permutes lanes."""
+    mesh = SMALL[name]()
+    monkeypatch.setenv("FEMGPU_ASM_THREADS", str(threads))
+    vals = []
+    for bulk, spread in (("0", "0"), ("1", "0"), ("1", "1")):
+        monkeypatch.setenv("FEMGPU_ASM_BULK", bulk)
+        monkeypatch.setenv("FEMGPU_SPREAD_BANKS", spread)
+        fem, n_rows, nnz = assemble(mesh)
+        vals.append(fem.csr(values_only=True).copy())
+        fem.close()
+    assert np.array_equal(vals[0], vals[1]) and np.array_equal(vals[0], vals[2])
+
+
+def test_shuffled_numbering_takes_the_per_element_staging(O, monkeypatch):
+    """a mesh whose elements are inserted in random order has no runs: the symbolic pass must still give the
+    oracle's matrix (accumulation order = insertion order) through the cp.async staging it selects"""
+    mesh = meshes.mixed_structure(12, 9)
+    rng = np.random.default_rng(3)
+    pp = rng.permutation(len(mesh["p_n"][0])); pb = rng.permutation(len(mesh["b_n1"])); pt = rng.permutation(len(mesh["t_n1"]))
+    mesh["p_n"] = np.asarray(mesh["p_n"]).reshape(4, -1)[:, pp]
+    mesh["p_props"] = np.asarray(mesh["p_props"]).reshape(4, -1)[:, pp]
+    mesh["b_n1"], mesh["b_n2"] = np.asarray(mesh["b_n1"])[pb], np.asarray(mesh["b_n2"])[pb]
+    mesh["b_props"] = np.asarray(mesh["b_props"]).reshape(8, -1)[:, pb]
+    mesh["b_axis"] = np.asarray(mesh["b_axis"]).reshape(3, -1)[:, pb]
+    mesh["t_n1"], mesh["t_n2"] = np.asarray(mesh["t_n1"])[pt], np.asarray(mesh["t_n2"])[pt]
+    mesh["t_E"], mesh["t_A"] = np.asarray(mesh["t_E"])[pt], np.asarray(mesh["t_A"])[pt]
+    if mesh.get("t_A2") is not None:
+        mesh["t_A2"] = np.asarray(mesh["t_A2"])[pt]
+    fem, n_rows, nnz = assemble(mesh)
+    rep = parity_report(n_rows, fem.csr(), O.faithful_coo(mesh), RTOL)
+    assert rep["n_fail"] == 0, rep
+    fem.close()
+
+
 def test_reference_model_known_answer():
     """config 1(i): K entries +-66666.66666666667 at rows/cols {0, 6}, nothing else."""
     fem, n_rows, nnz = assemble(meshes.reference_truss_model())
