@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 
 #include <chrono>
 #include <cstdio>
@@ -263,8 +264,16 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
   if (start + n >= (1u << 26))
     return h->fail(FEMGPU_ERR_LIMIT, "more than 2^26 elements of one family on one device");
 
+  static const bool timing = getenv("FEMGPU_HOST_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[femgpu add %d] %-22s %7.2f ms\n", family, what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   // A. node numbers -> indices (check_node_exist, argument order), in parallel
-  std::vector<uint32_t> idx[4];
+  std::vector<uint32_t>* idx = h->add_idx;  // scratch kept by the handle: no fresh pages per batch
   for (int c = 0; c < nn; ++c) idx[c].resize(n);
   std::atomic<size_t> i_node(n);
   parallel_chunks(n, 8192, [&](size_t b, size_t e) {
@@ -284,6 +293,7 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
     }
   });
   size_t limit = i_node.load();  // elements at or after this index are never accepted
+  lap("node lookup");
 
   // D. property sign checks of *::create, in parallel (geometry checks run on the device)
   std::atomic<size_t> i_prop(limit);
@@ -299,6 +309,7 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
       }
     }
   });
+  lap("property checks");
   // a property failure at i still lets the number / node-set checks of element i run first
   size_t scan_end = std::min(limit, i_prop.load() + 1);
 
@@ -314,10 +325,12 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
     ++inserted_numbers;
   }
   scan_end = std::min(scan_end, i_num + 1);
+  lap("element numbers");
 
   // C. duplicate node sets, sharded hash index filled by all cores
   bool degenerate = false;
-  std::vector<uint64_t> hashes(scan_end);
+  std::vector<uint64_t>& hashes = h->add_hash;
+  hashes.resize(scan_end);
   parallel_chunks(scan_end, 8192, [&](size_t b, size_t e) {
     for (size_t i = b; i < e; ++i) {
       uint32_t nd[4] = {idx[0][i], idx[1][i], nn == 4 ? idx[2][i] : 0u, nn == 4 ? idx[3][i] : 0u};
@@ -339,6 +352,7 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
         node_set_of(uint32_t(start + i), b);
         return nodeset_equal(family, a, b);
       });
+  lap("node-set index");
   if (family == FEMGPU_PLATE) {
     // Plate::is_nodes_numbers_same is a subset test; with repeated node numbers in the new element
     // that is not set equality, so such (degenerate) elements are compared by a scan.
@@ -361,6 +375,7 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
     }
   }
 
+  lap("degenerate scan");
   // first failing element and, for it, the first failing check in the reference's order
   size_t e_star = std::min(std::min(limit, i_prop.load()), std::min(i_num, i_set));
   int32_t status = 0;
@@ -396,21 +411,32 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
   for (size_t i = accepted; i < inserted_numbers; ++i) fh.by_number.erase(number[i]);
   if (accepted < scan_end) h->nodeset_seen[family].erase_batch(hashes.data(), accepted, scan_end, uint32_t(start));
 
-  // append the accepted prefix (bulk copies)
-  fh.number.insert(fh.number.end(), number, number + accepted);
-  for (int c = 0; c < nn; ++c) {
-    fh.conn[c].insert(fh.conn[c].end(), idx[c].begin(), idx[c].begin() + accepted);
-    fh.conn_number[c].insert(fh.conn_number[c].end(), nodes[c], nodes[c] + accepted);
+  // append the accepted prefix: one bulk copy per array, the arrays spread over the host cores
+  {
+    std::vector<std::function<void()>> jobs;
+    jobs.emplace_back([&] { fh.number.insert(fh.number.end(), number, number + accepted); });
+    for (int c = 0; c < nn; ++c) {
+      jobs.emplace_back([&, c] { fh.conn[c].insert(fh.conn[c].end(), idx[c].begin(), idx[c].begin() + accepted); });
+      jobs.emplace_back([&, c] { fh.conn_number[c].insert(fh.conn_number[c].end(), nodes[c], nodes[c] + accepted); });
+    }
+    for (int p = 0; p < np; ++p)
+      jobs.emplace_back([&, p] {
+        if (props[p]) fh.props[p].insert(fh.props[p].end(), props[p], props[p] + accepted);
+        else fh.props[p].insert(fh.props[p].end(), accepted, NAN);
+      });
+    const unsigned T = accepted >= 65536 ? std::min<unsigned>(host_threads(), unsigned(jobs.size())) : 1u;
+    std::atomic<size_t> next(0);
+    parallel_run(T, [&](unsigned, unsigned) {
+      for (size_t j = next.fetch_add(1); j < jobs.size(); j = next.fetch_add(1)) jobs[j]();
+    });
   }
-  for (int p = 0; p < np; ++p) {
-    if (props[p])
-      fh.props[p].insert(fh.props[p].end(), props[p], props[p] + accepted);
-    else
-      fh.props[p].insert(fh.props[p].end(), accepted, NAN);
-  }
+  lap("appends");
   fh.cbase.resize(start + accepted);
-  for (size_t i = 0; i < accepted; ++i) fh.cbase[start + i] = h->n_contrib + int64_t(i) * kPairsPerElem[family];
+  parallel_chunks(accepted, 65536, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) fh.cbase[start + i] = h->n_contrib + int64_t(i) * kPairsPerElem[family];
+  });
   h->n_contrib += int64_t(accepted) * kPairsPerElem[family];
+  lap("cbase");
   if (accepted) {
     if (!h->journal.empty() && h->journal.back().first == family)
       h->journal.back().second += accepted;
@@ -593,7 +619,7 @@ int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
   h->node_number.clear(); h->nx.clear(); h->ny.clear(); h->nz.clear();
   h->node_by_number.clear(); h->node_by_xyz.clear();
   h->nodes_uploaded = 0;
-  for (auto& f : h->fh) f = FamilyHost();
+  for (auto& f : h->fh) f.clear();
   for (auto& x : h->nodeset_seen) x.clear();
   h->n_contrib = 0;
   h->journal.clear();
@@ -658,7 +684,8 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
   }
   scan_end = std::min(scan_end, i_num + 1);
   // duplicate coordinates: sharded hash index, all cores (NaN never compares equal)
-  std::vector<uint64_t> hashes(scan_end);
+  std::vector<uint64_t>& hashes = h->add_hash;
+  hashes.resize(scan_end);
   parallel_chunks(scan_end, 8192, [&](size_t b, size_t e) {
     for (size_t i = b; i < e; ++i) hashes[i] = xyz_hash(x[i], y[i], z[i]);
   });
@@ -674,10 +701,14 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
   const size_t accepted = std::min(std::min(i_limit, i_num), i_xyz);
   for (size_t i = accepted; i < inserted; ++i) h->node_by_number.erase(number[i]);
   if (accepted < scan_end) h->node_by_xyz.erase_batch(hashes.data(), accepted, scan_end, uint32_t(n0));
-  h->node_number.insert(h->node_number.end(), number, number + accepted);
-  h->nx.insert(h->nx.end(), x, x + accepted);
-  h->ny.insert(h->ny.end(), y, y + accepted);
-  h->nz.insert(h->nz.end(), z, z + accepted);
+  parallel_run(accepted >= 65536 ? std::min(4u, host_threads()) : 1u, [&](unsigned t, unsigned nt) {
+    for (unsigned j = t; j < 4u; j += nt) {
+      if (j == 0) h->node_number.insert(h->node_number.end(), number, number + accepted);
+      if (j == 1) h->nx.insert(h->nx.end(), x, x + accepted);
+      if (j == 2) h->ny.insert(h->ny.end(), y, y + accepted);
+      if (j == 3) h->nz.insert(h->nz.end(), z, z + accepted);
+    }
+  });
   if (accepted) invalidate(h);
   if (accepted < n) {
     const size_t e = accepted;

@@ -173,6 +173,16 @@ struct FamilyHost {
                                       // insertion order (= accumulation order of the reference)
   NumberMap by_number;
   size_t size() const { return number.size(); }
+  // FEM::reset: forget the elements, keep the storage (a re-used instance re-fills the same pages instead of
+  // faulting in half a gigabyte of fresh ones)
+  void clear() {
+    number.clear();
+    for (auto& v : conn) v.clear();
+    for (auto& v : conn_number) v.clear();
+    for (auto& v : props) v.clear();
+    cbase.clear();
+    by_number.clear();
+  }
 };
 
 struct FamilyDev {
@@ -285,6 +295,10 @@ struct Handle {
   int64_t n_contrib = 0;  // running contribution counter (global insertion order)
   // insertion journal for prefix rollback: (family, count) runs in global order
   std::vector<std::pair<int, size_t>> journal;
+
+  // scratch of the batched adds (node indices of the batch, hashes), kept between calls
+  std::vector<uint32_t> add_idx[4];
+  std::vector<uint64_t> add_hash;
 
   // ---- symbolic products ----
   bool symbolic_valid = false;

@@ -58,8 +58,15 @@ class ShardedIndex {
   static constexpr unsigned kShards = 256;
   static constexpr uint32_t kEmpty = 0xFFFFFFFFu, kDead = 0xFFFFFFFEu;
 
+  // forget the entries, keep the tables (FEM::reset of a re-used instance: no fresh pages to fault in)
   void clear() {
-    for (auto& s : shards_) s = Shard();
+    parallel_run(std::min(host_threads(), 8u), [&](unsigned t, unsigned nt) {
+      for (unsigned sh = t; sh < kShards; sh += nt) {
+        Shard& s = shards_[sh];
+        if (s.used) std::fill(s.id.begin(), s.id.end(), kEmpty);
+        s.used = 0;
+      }
+    });
   }
 
   // Looks for an entry equal to (hash, probe) under `same(existing_id)`; returns its id or kEmpty.
