@@ -4,7 +4,7 @@ checks, prefix semantics and the reference's error texts
 import numpy as np
 import pytest
 
-from finite_element_method_b200 import FEM, FemError
+from finite_element_method_b200 import FEM, PLATE, FemError, meshes
 
 
 def staged(n=16):
@@ -170,3 +170,34 @@ def test_row_strip_generators_match_local_part():
             c = meshes.plate_grid(17, 11, "flat", rows=(b // 18, e // 18))
             for k in ("p_n", "p_props"):
                 assert np.array_equal(np.asarray(a[k]), np.asarray(c[k])), (world, b, e, k)
+
+
+def test_reset_reuses_storage_but_forgets_everything():
+    """FEM::reset (fem.rs:155-169) on a re-used instance keeps the staging vectors and hash tables allocated but must
+    forget every node, element, number and node set: the same model loads again, twice, and duplicates are still
+    caught afterwards (both through the per-call path and the batched, multi-threaded one)."""
+    mesh = meshes.mixed_structure(60, 40)             # > 32768 keys per batch: the sharded multi-thread inserts
+    n = len(mesh["x"])
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n + 2, device=-1)   # room for the two probes (the limit is checked first)
+    for _ in range(3):
+        fem.load_mesh(mesh)
+        assert fem.counts() == (n, len(mesh["t_n1"]), len(mesh["b_n1"]), len(mesh["p_n"][0]))
+        assert list(fem.node_numbers()[:3]) == [1, 2, 3] and len(fem.element_numbers(PLATE)) == len(mesh["p_n"][0])
+        with pytest.raises(FemError, match="Node with number 1 already exists!"):
+            fem.add_node(1, -5.0, -5.0, -5.0)
+        with pytest.raises(FemError, match="already exists!"):
+            fem.add_node(10 ** 6, float(mesh["x"][7]), float(mesh["y"][7]), float(mesh["z"][7]))   # same coordinates
+        with pytest.raises(FemError, match="Plate element with nodes numbers"):
+            pn = np.asarray(mesh["p_n"]).reshape(4, -1)[:, 5] + 1
+            fem.add_plate(10 ** 6, int(pn[2]), int(pn[3]), int(pn[0]), int(pn[1]), 2.1e11, 0.3, 0.01, 5 / 6)      # same node set, rotated
+        fem.reset(n + 2)
+        assert fem.counts() == (0, 0, 0, 0)
+    # a smaller model after a larger one: nothing of the old one may be found
+    fem.reset(2)
+    fem.add_node(1, 0.0, 0.0, 0.0)
+    fem.add_node(2, 30.0, 0.0, 0.0)
+    fem.add_trusses([1], [1], [2], [1e6], [2.0])         # the batched form: no device validation on a staging-only handle
+    assert fem.counts() == (2, 1, 0, 0)
+    with pytest.raises(FemError, match="Node with number 3 does not exist!"):
+        fem.add_trusses([2], [1], [3], [1e6], [2.0])
+    fem.close()
