@@ -58,6 +58,7 @@ SIGNATURES = {
     "femgpu_separated_rhs": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_last_separate_ms": (C.c_int32, [H, fp]),
     "femgpu_solve_pcg": (C.c_int32, [H, C.c_int32, C.c_int64, i64p]),
+    "femgpu_solve_direct": (C.c_int32, [H]),
     "femgpu_get_ua": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_set_ua": (C.c_int32, [H, dp]),
     "femgpu_solve_info": (C.c_int32, [H, i64p, dp, fp]),

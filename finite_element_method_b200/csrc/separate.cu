@@ -476,6 +476,7 @@ int32_t run_separate(Handle* h, bool direct) {
     if (st) return st;
   }
   S.valid = false;
+  S.sky_valid = false;
   sol_invalidate(h);
   S.n_aa = S.n_bb = 0;
   for (auto& z : S.nnz) z = 0;

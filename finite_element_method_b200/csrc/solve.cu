@@ -295,6 +295,83 @@ __global__ void scatter_kernel(int64_t n, const int64_t* __restrict__ idx, const
   if (i < n) dst[idx[i]] = src[i];
 }
 
+// ---- direct solve: active-column (skyline) LDL^T, FEM::find_ua_vector_direct --------------------------
+// methods_for_global_analysis.rs:161-187 hands (a, maxa) to the un-vendored crate colsol 1.0.1
+// (`factorization`, `find_unknown`), i.e. Bathe's COLSOL: column by column, every entry of a column is reduced by
+// the dot product of the rows above it with the matching column of L (top to bottom), then the column is divided
+// by the pivots and the diagonal reduced; forward reduction, division by D and back-substitution follow. The
+// columns — and the entries inside a column — depend on each other, so ONE warp walks them in COLSOL's order and
+// only the dot products are spread over its lanes (fixed shuffle tree: deterministic, but not the sequential
+// summation order of the scalar code — parity unpinned beyond the reference's 1 x 1 test). This is the path for
+// the model sizes the reference's dense separation could handle; large models take the PCG.
+// status: 0 ok, n + 1 = "stiffness matrix not positive definite" at column n.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(32)
+colsol_kernel(int64_t nn, const int64_t* __restrict__ maxa, double* a, double* v, int64_t* __restrict__ status) {
+  const int lane = threadIdx.x;
+  // factorisation (COLSOL, KKK = 1)
+  for (int64_t n = 0; n < nn; ++n) {
+    const int64_t kn = maxa[n], kl = kn + 1, ku = maxa[n + 1] - 1, kh = ku - kl;
+    if (kh > 0) {
+      int64_t k = n - kh, klt = ku;
+      for (int64_t ic = 1; ic <= kh; ++ic, ++k) {
+        --klt;
+        const int64_t ki = maxa[k], nd = maxa[k + 1] - ki - 1;
+        if (nd > 0) {
+          const int64_t kk = ic < nd ? ic : nd;
+          double c = 0.0;
+          for (int64_t l = 1 + lane; l <= kk; l += 32) c += a[ki + l] * a[klt + l];
+          c = warp_sum(c);
+          if (lane == 0) a[klt] -= c;
+          __syncwarp();
+        }
+      }
+    }
+    if (kh >= 0) {
+      double b = 0.0;
+      for (int64_t kk = kl + lane; kk <= ku; kk += 32) {
+        const int64_t k = n - 1 - (kk - kl);
+        const double c = a[kk] / a[maxa[k]];
+        b += c * a[kk];
+        a[kk] = c;
+      }
+      b = warp_sum(b);
+      if (lane == 0) a[kn] -= b;
+      __syncwarp();
+    }
+    if (!(a[kn] > 0.0)) {
+      if (lane == 0) *status = n + 1;
+      return;
+    }
+  }
+  // forward reduction of the right-hand side (KKK = 2)
+  for (int64_t n = 0; n < nn; ++n) {
+    const int64_t kl = maxa[n] + 1, ku = maxa[n + 1] - 1;
+    if (ku - kl >= 0) {
+      double c = 0.0;
+      for (int64_t kk = kl + lane; kk <= ku; kk += 32) c += a[kk] * v[n - 1 - (kk - kl)];
+      c = warp_sum(c);
+      if (lane == 0) v[n] -= c;
+      __syncwarp();
+    }
+  }
+  for (int64_t n = lane; n < nn; n += 32) v[n] = v[n] / a[maxa[n]];
+  __syncwarp();
+  // back-substitution
+  for (int64_t n = nn - 1; n >= 1; --n) {
+    const int64_t kl = maxa[n] + 1, ku = maxa[n + 1] - 1;
+    const double vn = v[n];
+    for (int64_t kk = kl + lane; kk <= ku; kk += 32) v[n - 1 - (kk - kl)] -= a[kk] * vn;
+    __syncwarp();
+  }
+  if (lane == 0) *status = 0;
+}
+
 int grid_for(int64_t n, int per_cta, int sm_count) {
   const int64_t want = (n + per_cta - 1) / per_cta;
   const int64_t cap = std::min<int64_t>(kMaxPartials, int64_t(sm_count > 0 ? sm_count : 148) * 8);
@@ -441,6 +518,42 @@ int32_t run_global_analysis(Handle* h) {
   return 0;
 }
 
+// K_aa u_a = b by the skyline LDL^T on copies of (a, b): u_a replaces any earlier solution
+int32_t run_colsol(Handle* h) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  Handle::Separated& S = h->sep;
+  Handle::Solution& Z = h->sol;
+  const int64_t n = S.n_aa;
+  Z.ua_valid = Z.composed = false;
+  if (!Z.ev[0]) {
+    FEMGPU_CUDA_CHECK(h, cudaEventCreate(&Z.ev[0]));
+    FEMGPU_CUDA_CHECK(h, cudaEventCreate(&Z.ev[1]));
+  }
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(Z.ev[0], s));
+  FEMGPU_CUDA_CHECK(h, Z.u_a.reserve(size_t(n) + 1));
+  FEMGPU_CUDA_CHECK(h, Z.ap.reserve(size_t(S.sky_total) + 1));  // the factor overwrites a copy of `a`
+  FEMGPU_CUDA_CHECK(h, h->d_flag.reserve(16));
+  int64_t* d_status = reinterpret_cast<int64_t*>(h->d_flag.p);
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(Z.ap.p, S.sky_a.p, size_t(S.sky_total) * 8, cudaMemcpyDeviceToDevice, s));
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(Z.u_a.p, S.rhs.p, size_t(n) * 8, cudaMemcpyDeviceToDevice, s));
+  colsol_kernel<<<1, 32, 0, s>>>(n, S.maxa.p, Z.ap.p, Z.u_a.p, d_status);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  int64_t status = -1;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&status, d_status, 8, cudaMemcpyDeviceToHost, s));
+  FEMGPU_CUDA_CHECK(h, cudaEventRecord(Z.ev[1], s));
+  FEMGPU_CUDA_CHECK(h, cudaEventSynchronize(Z.ev[1]));
+  FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&Z.last_ms, Z.ev[0], Z.ev[1]));
+  Z.iterations = 0;
+  Z.residual = 0.0;
+  if (status != 0)
+    return h->fail(FEMGPU_E_SOLVER, "Direct solve: stiffness matrix is not positive definite (pivot of equation " +
+                                        std::to_string(status) + " is not positive)");
+  Z.ua_valid = true;
+  return 0;
+}
+
 }  // namespace femgpu
 
 using femgpu::Handle;
@@ -455,6 +568,14 @@ int32_t femgpu_solve_pcg(femgpu_t* h, int32_t preconditioner, int64_t max_iter, 
     return h->fail(FEMGPU_ERR_USAGE, "preconditioner must be 0 (Jacobi) or 1 (block Jacobi)");
   if (max_iter < 0) return h->fail(FEMGPU_ERR_USAGE, "max_iter must be >= 0");
   return femgpu::run_pcg(h, preconditioner, max_iter, iterations);
+}
+
+int32_t femgpu_solve_direct(femgpu_t* h) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  int32_t st = femgpu::need_sep(h);
+  if (st) return st;
+  if (!h->sep.sky_valid) return h->fail(FEMGPU_ERR_USAGE, "no skyline: call femgpu_separate_direct first");
+  return femgpu::run_colsol(h);
 }
 
 int32_t femgpu_set_ua(femgpu_t* h, const double* u_a) {

@@ -356,6 +356,17 @@ class FEM:
         """methods_for_global_analysis.rs:235-275 (blocks = the rows of one node, :121-147)"""
         return self._solve(1, max_iter, copy_out)
 
+    def find_ua_vector_direct(self, copy_out: bool = True):
+        """methods_for_global_analysis.rs:161-187: skyline LDL^T (COLSOL) on the form separate_stiffness_matrix_direct
+        left on the device. Returns u_a."""
+        self._check(self._L.femgpu_solve_direct(self._h))
+        return self.u_a_vector() if copy_out else None
+
+    def find_r_r_vector(self, copy_out: bool = True):
+        """methods_for_global_analysis.rs:277-309 (the direct flow's name for the reactions): the same sums as the
+        sparse variant, on the CSR quadrants"""
+        return self.find_r_r_vector_sparse(copy_out)
+
     def u_a_vector(self):
         n = self._n_aa_bb()[0]
         out = np.empty(n, np.float64)

@@ -278,6 +278,12 @@ int32_t femgpu_last_separate_ms(femgpu_t* h, float* ms);
  * iterative_solvers_smpl: parity is pinned on the reference's own test only (one iteration, u = 0.0015).
  * Deterministic (fixed reduction trees, no atomics). FEMGPU_E_SOLVER when it does not converge. */
 int32_t femgpu_solve_pcg(femgpu_t* h, int32_t preconditioner, int64_t max_iter, int64_t* iterations);
+/* FEM::find_ua_vector_direct                              methods_for_global_analysis.rs:161-187
+ * K_aa u_a = b by the active-column LDL^T of the skyline form femgpu_separate_direct left on the device (the
+ * reference hands (a, maxa) to colsol::factorization / find_unknown, i.e. Bathe's COLSOL). One warp walks the
+ * columns in COLSOL's order, its lanes share the dot products: meant for the model sizes the reference's dense
+ * separation could handle. FEMGPU_E_SOLVER when a pivot is not positive. */
+int32_t femgpu_solve_direct(femgpu_t* h);
 /* u_a [n_aa] of the last solve; femgpu_set_ua installs the result of an external solver instead */
 int32_t femgpu_get_ua(femgpu_t* h, double* u_a, const double** u_a_device);
 int32_t femgpu_set_ua(femgpu_t* h, const double* u_a);

@@ -461,3 +461,43 @@ def separate_direct(n_dof, rows, cols, vals, constrained, node_numbers=None, for
     on = j >= i
     a[maxa[j[on]] + (j - i)[on]] = v[on]
     return {"k_aa_indexes": k_aa, "k_bb_indexes": k_bb, "k_aa_skyline": skyline, "a": a, "maxa": maxa}
+
+
+# ---------------------------------------------------------------------------------------------
+# Direct solve (restatement, numpy): FEM::find_ua_vector_direct, methods_for_global_analysis.rs:161-187, hands the
+# compacted column form (a, maxa) to the un-vendored crate colsol 1.0.1 (`factorization`, `find_unknown`) — Bathe's
+# COLSOL active-column LDL^T, restated here column by column in its order (the dot products through numpy).
+# Pinned on the reference's direct test model (src/tests/fem/test_fem.rs:5-64: a = [EA/L], b = [100] -> u = 0.0015);
+# PARITY UNPINNED beyond that (the crate's source is not available).
+# ---------------------------------------------------------------------------------------------
+def colsol(a, maxa, b):
+    a = np.array(a, np.float64); v = np.array(b, np.float64); maxa = np.asarray(maxa, np.int64)
+    nn = len(maxa) - 1
+    for n in range(nn):                                   # factorisation: K = L D L^T
+        kn = maxa[n]; kl = kn + 1; ku = maxa[n + 1] - 1; kh = ku - kl
+        if kh > 0:
+            k = n - kh; klt = ku
+            for ic in range(1, kh + 1):
+                klt -= 1
+                ki = maxa[k]; nd = maxa[k + 1] - ki - 1
+                if nd > 0:
+                    kk = min(ic, nd)
+                    a[klt] -= a[ki + 1:ki + kk + 1] @ a[klt + 1:klt + kk + 1]
+                k += 1
+        if kh >= 0:
+            rows = n - 1 - np.arange(ku - kl + 1)
+            c = a[kl:ku + 1] / a[maxa[rows]]
+            a[kn] -= c @ a[kl:ku + 1]
+            a[kl:ku + 1] = c
+        if not a[kn] > 0.0:
+            raise SeparationError(f"stiffness matrix not positive definite (equation {n + 1})")
+    for n in range(nn):                                   # forward reduction
+        kl = maxa[n] + 1; ku = maxa[n + 1] - 1
+        if ku - kl >= 0:
+            v[n] -= a[kl:ku + 1] @ v[n - 1 - np.arange(ku - kl + 1)]
+    v /= a[maxa[:-1]]
+    for n in range(nn - 1, 0, -1):                        # back-substitution
+        kl = maxa[n] + 1; ku = maxa[n + 1] - 1
+        if ku - kl >= 0:
+            v[n - 1 - np.arange(ku - kl + 1)] -= a[kl:ku + 1] * v[n]
+    return v

@@ -35,6 +35,7 @@ extern "C" {
     fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_separated_rhs(h: *mut FemGpu, b: *mut f64, b_device: *mut *const f64) -> i32;
     fn femgpu_separate_direct(h: *mut FemGpu, n_aa: *mut i64, n_bb: *mut i64, skyline_values: *mut i64) -> i32;
+    fn femgpu_solve_direct(h: *mut FemGpu) -> i32;
     fn femgpu_get_skyline(h: *mut FemGpu, k_aa_skyline: *mut i64, a: *mut f64, maxa: *mut i64) -> i32;
     fn femgpu_counts(h: *const FemGpu, nodes: *mut u64, truss: *mut u64, beam: *mut u64, plate: *mut u64) -> i32;
     fn femgpu_get_numbers(h: *const FemGpu, family: i32, out: *mut u32) -> i32;
@@ -203,6 +204,13 @@ impl FEM {
         let (mut sky, mut a, mut maxa) = (vec![0i64; n_aa as usize], vec![0f64; n_val as usize], vec![0i64; n_aa as usize + 1]);
         self.check(unsafe { femgpu_get_skyline(self.h, sky.as_mut_ptr(), a.as_mut_ptr(), maxa.as_mut_ptr()) })?;
         Ok((ia, ib, sky, a, maxa))
+    }
+    /// methods_for_global_analysis.rs:161 — skyline LDL^T on the form separate_stiffness_matrix_direct left on the device
+    pub fn find_ua_vector_direct(&mut self, n_aa: usize) -> Result<Vec<f64>, String> {
+        self.check(unsafe { femgpu_solve_direct(self.h) })?;
+        let mut u_a = vec![0f64; n_aa];
+        self.check(unsafe { femgpu_get_ua(self.h, u_a.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok(u_a)
     }
     /// methods_for_global_analysis.rs:189 / :235 — K_aa, r_a and u_b never left the device, so the three
     /// arguments of the reference collapse into the handle. Returns (u_a, iterations).

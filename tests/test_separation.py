@@ -347,3 +347,63 @@ def test_direct_separation_errors():
         fem.separate_stiffness_matrix_direct()
     fem.separate_stiffness_matrix_sparse_iterative()         # the sparse variant does not look at the loads
     fem.close()
+
+
+# ---------------------------------------------------------------------------- direct solve (skyline LDL^T)
+def test_oracle_colsol():
+    """the reference's direct test (test_fem.rs:5-64) is a 1 x 1 system; larger ones against a dense solve"""
+    k = 66666.66666666667
+    assert O.colsol([k], [0, 1], [100.0])[0] == 100.0 / k == 0.0014999999999999998
+    rng = np.random.default_rng(11)
+    n = 40
+    A = np.zeros((n, n))
+    for i in range(n):
+        for j in range(max(0, i - rng.integers(0, 6)), i):
+            A[i, j] = A[j, i] = rng.normal()
+    A += np.diag(np.abs(A).sum(axis=1) + 1.0)              # SPD, variable column heights
+    sky = np.array([max([j - i for i in range(j) if A[i, j] != 0.0] + [0]) for j in range(n)])
+    maxa = np.concatenate([[0], np.cumsum(sky + 1)])
+    a = np.concatenate([[A[j - m, j] for m in range(sky[j] + 1)] for j in range(n)])
+    b = rng.normal(size=n)
+    u = O.colsol(a, maxa, b)
+    assert np.linalg.norm(u - np.linalg.solve(A, b)) <= 1e-12 * np.linalg.norm(u)
+    with pytest.raises(O.SeparationError, match="not positive definite"):
+        O.colsol([1.0, 1.0, 2.0], [0, 1, 3], [1.0, 1.0])   # [[1, 2], [2, 1]]: column 1 = (diagonal 1, above it 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["reference", "mixed", "beams"])
+def test_direct_solve_matches_oracle_and_dense(which):
+    """the reference's direct flow (test_fem.rs:5-64): separate_stiffness_matrix_direct -> find_ua_vector_direct ->
+    find_r_r_vector -> compose_global_analysis_result"""
+    if which == "reference":
+        mesh = meshes.reference_truss_model()
+        fixed_nodes, fixed_dofs = [0], [0]
+    else:
+        mesh = meshes.mixed_structure(7, 5) if which == "mixed" else meshes.beam_frame(4, 10**9)
+        y0 = np.flatnonzero(np.asarray(mesh["y"]) == np.min(mesh["y"]))
+        fixed_nodes, fixed_dofs = np.repeat(y0, 6), np.tile(np.arange(6), len(y0))
+    n = len(mesh["x"])
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    fem.add_displacement(np.asarray(fixed_nodes) + 1, fixed_dofs, np.zeros(len(fixed_nodes)))
+    fem.add_concentrated_load(n, DOFParameter.X, 100.0)
+    ia, ib, sky, a, maxa = fem.separate_stiffness_matrix_direct()
+    sep = fem.separate_stiffness_matrix_sparse_iterative()    # the same quadrants, for b and a dense check
+    fem.separate_stiffness_matrix_direct()
+    u = fem.find_ua_vector_direct()
+    u_ref = O.colsol(a, maxa, sep.b)
+    assert np.linalg.norm(u - u_ref) <= 1e-9 * np.linalg.norm(u_ref)          # same algorithm, other dot order
+    i, j, v = sep.triplets(sep.k_aa)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((v, (i, j)), shape=(sep.n_aa, sep.n_aa))
+    assert np.linalg.norm(A @ u - sep.b) <= 1e-9 * np.linalg.norm(sep.b)
+    assert np.array_equal(u, fem.find_ua_vector_direct())                     # deterministic
+    r_r = fem.find_r_r_vector()
+    d, f = fem.global_analysis_vectors()
+    assert abs(f[0::6].sum()) <= 1e-7 * 100.0 and np.array_equal(d[ia], u)
+    if which == "reference":
+        assert u[0] == 100.0 / 66666.66666666667 and abs(r_r[0] + 100.0) < 1e-12   # 0.0015, -100 (test_fem.rs:40-58)
+        assert abs(fem.extract_elements_analysis_result()[0][1][0][1] - 100.0) < 1e-11
+    fem.close()
