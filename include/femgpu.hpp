@@ -91,6 +91,28 @@ class FEM {
     sep_ = s;
     return s;
   }
+  struct Skyline {
+    std::vector<int64_t> k_aa_skyline, maxa;
+    std::vector<double> a;
+  };
+  // methods_for_separate_stiffness_matrix.rs:63 without the dense detour: K_aa as (a, maxa), the compacted column form
+  // of methods_for_global_analysis.rs:50-80
+  Skyline separate_stiffness_matrix_direct() {
+    Separated s;
+    int64_t n_val = 0;
+    check(femgpu_separate_direct(h_, &s.n_aa, &s.n_bb, &n_val));
+    sep_ = s;
+    Skyline k{std::vector<int64_t>(size_t(s.n_aa)), std::vector<int64_t>(size_t(s.n_aa) + 1), std::vector<double>(size_t(n_val))};
+    check(femgpu_get_skyline(h_, k.k_aa_skyline.data(), k.a.data(), k.maxa.data()));
+    return k;
+  }
+  // methods_for_global_analysis.rs:161 (skyline LDL^T, COLSOL)
+  std::vector<double> find_ua_vector_direct() {
+    check(femgpu_solve_direct(h_));
+    std::vector<double> u(size_t(sep_.n_aa));
+    check(femgpu_get_ua(h_, u.data(), nullptr));
+    return u;
+  }
   // methods_for_global_analysis.rs:189 / :235 -> (u_a, iterations)
   std::pair<std::vector<double>, int64_t> find_ua_vector_iterative_pcg_jacobi_sparse(int64_t max_iter) {
     return solve(FEMGPU_PCG_JACOBI, max_iter);
