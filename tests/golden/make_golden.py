@@ -46,3 +46,16 @@ for i in range(6):
 with open(os.path.join(os.path.dirname(__file__), "element_golden.json"), "w") as f:
     json.dump(gold, f)
 print("written")
+
+# ---- element result recovery: oracle outputs for fixed displacement vectors ----------------
+from finite_element_method_b200 import meshes  # noqa: E402
+
+res = {}
+for name, mesh in (("truss_cube", meshes.truss_cube(3)), ("beam_frame_jitter", meshes.beam_frame(3, 10 ** 9, jitter=True)),
+                   ("plate_x0", meshes.plate_grid(3, 2, "x0")), ("mixed", meshes.mixed_structure(3, 2))):
+    u = np.random.default_rng(20241018).normal(size=6 * len(mesh["x"])) * 1e-3
+    ot, ob, op = O.element_results(mesh, u)
+    res[name] = {"truss": ot.tolist(), "beam": ob.tolist(), "plate": op.tolist()}
+with open(os.path.join(os.path.dirname(__file__), "element_results_golden.json"), "w") as f:
+    json.dump(res, f)
+print("element results written")

@@ -237,3 +237,19 @@ def test_pcg_reference_model_one_iteration():
 def test_block_starts():
     assert O.block_starts_from_k_aa_indexes([6, 7, 8, 12, 14, 18]) == [0, 3, 5]
     assert O.block_starts_from_k_aa_indexes([]) == []
+
+
+def test_element_results_golden_fixture():
+    """tests/golden/element_results_golden.json (generator: make_golden.py) pins the oracle's element results bit
+    for bit across machines / compilers (-ffp-contract=off); the GPU path is compared with the oracle in
+    tests/test_analysis.py"""
+    from finite_element_method_b200 import meshes
+    with open(os.path.join(GOLD, "element_results_golden.json")) as f:
+        gold = json.load(f)
+    for name, mesh in (("truss_cube", meshes.truss_cube(3)), ("beam_frame_jitter", meshes.beam_frame(3, 10 ** 9, jitter=True)),
+                       ("plate_x0", meshes.plate_grid(3, 2, "x0")), ("mixed", meshes.mixed_structure(3, 2))):
+        u = np.random.default_rng(20241018).normal(size=6 * len(mesh["x"])) * 1e-3
+        ot, ob, op = O.element_results(mesh, u)
+        assert np.array_equal(ot, np.array(gold[name]["truss"]))
+        assert np.array_equal(ob, np.array(gold[name]["beam"]).reshape(ob.shape))
+        assert np.array_equal(op, np.array(gold[name]["plate"]).reshape(op.shape))
