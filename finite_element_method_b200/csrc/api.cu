@@ -614,7 +614,17 @@ static void free_device(femgpu_t* h) {
 int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
   if (!h) return FEMGPU_ERR_USAGE;
   if (h->device >= 0) cudaStreamSynchronize(h->stream);
-  free_device(h);
+  // FEM::reset of a re-used instance: the device buffers stay with the handle (every one of them is rewritten before
+  // it is read again — uploads restart at element 0, the symbolic products are rebuilt), like the host staging does.
+  // Handing ~20 GB back to the stream-ordered pool and asking for it again cost 0.04 s on most boxes and 0.7-0.9 s
+  // on some (profiles/README.md); femgpu_destroy frees everything. FEMGPU_RESET_FREES=1 restores the old behaviour.
+  static const bool reset_frees = getenv("FEMGPU_RESET_FREES") != nullptr;
+  if (reset_frees) {
+    free_device(h);
+  } else if (h->device >= 0) {
+    for (auto& f : h->fd) f.uploaded = f.validated = 0;
+    sol_invalidate(h);
+  }
   h->nodes_number = nodes_number;
   h->node_number.clear(); h->nx.clear(); h->ny.clear(); h->nz.clear();
   h->node_by_number.clear(); h->node_by_xyz.clear();

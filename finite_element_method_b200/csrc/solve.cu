@@ -26,7 +26,10 @@ namespace femgpu {
 namespace {
 
 constexpr int kVecThreads = 256;
-constexpr int kLanesPerRow = 8;   // rows of a structural K_aa hold ~54 entries
+#ifndef FEMGPU_SPMV_LANES
+#define FEMGPU_SPMV_LANES 4
+#endif
+constexpr int kLanesPerRow = FEMGPU_SPMV_LANES;   // rows of a structural K_aa hold ~20-54 entries
 constexpr int kMaxPartials = 2048;
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -54,19 +57,26 @@ spmv_dot_kernel(int64_t n, const int64_t* __restrict__ rp, const int32_t* __rest
   const int sub = threadIdx.x % kLanesPerRow;
   const int64_t rows_per_cta = kVecThreads / kLanesPerRow;
   double dot = 0.0;
-  for (int64_t base = int64_t(blockIdx.x) * rows_per_cta; base < n; base += int64_t(gridDim.x) * rows_per_cta) {
-    const int64_t i = base + threadIdx.x / kLanesPerRow;
+  const int64_t step = int64_t(gridDim.x) * rows_per_cta;
+  int64_t i = int64_t(blockIdx.x) * rows_per_cta + threadIdx.x / kLanesPerRow;
+  // the row pointers of the NEXT row are requested before this row's entries are summed: one dependent
+  // round trip (row_ptr -> entries -> x) less on the critical path of a thread
+  int64_t b = i < n ? rp[i] : 0, e = i < n ? rp[i + 1] : 0;
+  for (int64_t base = int64_t(blockIdx.x) * rows_per_cta; base < n; base += step) {
+    const int64_t i_next = i + step;
+    const int64_t b_next = i_next < n ? rp[i_next] : 0, e_next = i_next < n ? rp[i_next + 1] : 0;
     double acc = 0.0;
-    if (i < n) {
-      const int64_t b = rp[i], e = rp[i + 1];
+    if (i < n)
       for (int64_t p = b + sub; p < e; p += kLanesPerRow) acc += va[p] * __ldg(x + ci[p]);
-    }
 #pragma unroll
     for (int o = kLanesPerRow / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o, kLanesPerRow);
     if (sub == 0 && i < n) {
       y[i] = acc;
       dot += __ldg(x + i) * acc;
     }
+    i = i_next;
+    b = b_next;
+    e = e_next;
   }
   const double t = block_sum(dot, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;

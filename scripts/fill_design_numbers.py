@@ -22,7 +22,9 @@ for n in (2, 4, 8):
     L.append(f"| M, {n} × B200 (weak){note} | {d['config']['elements'] / 1e6:.1f} M | {d['ms_per_step']:.3f} | {d['value'] / 1e9:.2f} | {r['kernel_ms']:.3f} | "
              f"{r['achieved']:.0f} | {100 * r['frac']:.1f} % | {e.get('value', 0) / 1e6:.1f} M elem/s | — |")
 d2 = load("r1_bench_M_n2.json")
-M = load("r1_bench_M.json"); an = M["separation"]["analysis"]; er = an["element_results"]
+M = load("r1_bench_M.json"); er = M["separation"]["analysis"]["element_results"]
+# the PCG leg was re-measured after the last change to its SpMV (four lanes per row): r1_bench_M_spmv4.json
+an = load("r1_bench_M_spmv4.json")["separation"]["analysis"]
 ref = load("r1_bench_reference.json"); cpu = M["cpu_baseline"]; e = M["e2e"]; ph = e["phases_last_step"]
 L += ["",
       f"Start of session 4: M 4.95 ms / 2.02 G elem/s / 40.4 %; B 0.700 ms / 52.4 %. Two GPUs (final kernel): {100 * d2['value'] / (2 * one):.1f} % of twice the "
@@ -33,8 +35,8 @@ L += ["",
       f"{M['separation']['nnz_aa_ab_ba_bb'][0] / 1e6:.0f} M stored entries):",
       "",
       "| step | time | algorithmic GB/s | of measured copy peak |", "|---|---|---|---|",
-      f"| Jacobi PCG, one iteration (`spmv_dot_kernel` is 1.76 ms of it; ncu: 6.4 GB read) | {an['pcg_jacobi']['ms_per_iteration']:.2f} ms | {an['pcg_jacobi']['achieved_GBps']:.0f} | {100 * an['pcg_jacobi']['frac_of_hbm_peak']:.1f} % |",
-      f"| block-Jacobi PCG, one iteration | {an['pcg_block_jacobi']['ms_per_iteration']:.2f} ms | {an['pcg_block_jacobi']['achieved_GBps']:.0f} | {100 * an['pcg_block_jacobi']['frac_of_hbm_peak']:.1f} % |",
+      f"| Jacobi PCG, one iteration (`r1_bench_M_spmv4.json`; with eight lanes per row: 2.12 ms, `spmv_dot_kernel` 1.76 ms of it, ncu 6.4 GB read) | {an['pcg_jacobi']['ms_per_iteration']:.2f} ms | {an['pcg_jacobi']['achieved_GBps']:.0f} | {100 * an['pcg_jacobi']['frac_of_hbm_peak']:.1f} % |",
+      f"| block-Jacobi PCG, one iteration (eight lanes: 2.64 ms) | {an['pcg_block_jacobi']['ms_per_iteration']:.2f} ms | {an['pcg_block_jacobi']['achieved_GBps']:.0f} | {100 * an['pcg_block_jacobi']['frac_of_hbm_peak']:.1f} % |",
       f"| element results, {er['truss']['elements'] / 1e6:.0f} M trusses / {er['beam']['elements'] / 1e6:.0f} M beams / {er['plate']['elements'] / 1e6:.0f} M plates | "
       f"{er['truss']['ms_wall']:.2f} / {er['beam']['ms_wall']:.2f} / {er['plate']['ms_wall']:.2f} ms | {er['truss']['algorithmic_GBps']:.0f} / {er['beam']['algorithmic_GBps']:.0f} / {er['plate']['algorithmic_GBps']:.0f} | — |",
       "",
