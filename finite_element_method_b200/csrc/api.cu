@@ -356,7 +356,22 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
   if (family == FEMGPU_PLATE) {
     // Plate::is_nodes_numbers_same is a subset test; with repeated node numbers in the new element
     // that is not set equality, so such (degenerate) elements are compared by a scan.
-    for (size_t i = 0; i < std::min(scan_end, i_set + 1) && !degenerate; ++i) {
+    // first element with a repeated node, found on all cores; the scan below only runs for that rare element
+    const size_t deg_end = std::min(scan_end, i_set + 1);
+    std::atomic<size_t> first_deg(deg_end);
+    parallel_chunks(deg_end, 65536, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; ++i) {
+        uint32_t v[4] = {idx[0][i], idx[1][i], idx[2][i], idx[3][i]};
+        sort4(v);
+        if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) {
+          size_t cur = first_deg.load();
+          while (i < cur && !first_deg.compare_exchange_weak(cur, i)) {
+          }
+          return;
+        }
+      }
+    });
+    for (size_t i = first_deg.load(); i < deg_end && !degenerate; ++i) {
       uint32_t v[4] = {idx[0][i], idx[1][i], idx[2][i], idx[3][i]};
       sort4(v);
       if (v[0] == v[1] || v[1] == v[2] || v[2] == v[3]) {
