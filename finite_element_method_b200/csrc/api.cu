@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <mutex>
 
 #include <chrono>
 #include <cstdio>
@@ -127,7 +128,15 @@ int property_check(int family, const double* p /* props of one element */) {
   }
 }
 
-void invalidate(Handle* h) { h->symbolic_valid = false; }
+// the model changed: everything derived from the old one is stale — the pattern, the assembled values, the
+// separated matrix and whatever was solved / recovered from it
+void invalidate(Handle* h) {
+  h->symbolic_valid = false;
+  h->values_valid = false;
+  h->sep.valid = false;
+  h->sep.sky_valid = false;
+  sol_invalidate(h);
+}
 
 inline void sort4(uint32_t v[4]) {
   auto cs = [&](int a, int b) {
@@ -549,6 +558,33 @@ int32_t upload_pending(Handle* h) {
   return 0;
 }
 
+// The library's private stream-ordered pool, one per device, created on first use and kept for the life of the
+// process (freed memory stays mapped: release threshold lifted). The default pool of the device is not touched.
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t s) {
+  static cudaMemPool_t pools[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaMallocAsync(p, bytes, s);
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if ((e = cudaMemPoolCreate(&pools[dev], &props)) != cudaSuccess) return e;
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool = pools[dev];
+  }
+  return cudaMallocFromPoolAsync(p, bytes, pool, s);
+}
+
 }  // namespace femgpu
 
 extern "C" {
@@ -596,12 +632,6 @@ int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t n
   }
   for (auto& q : h->ev)
     for (auto& ev : q) cudaEventCreate(&ev);
-  // keep freed device memory in the stream-ordered pool instead of returning it to the driver
-  cudaMemPool_t pool = nullptr;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-    uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
   *out = h;
   return 0;
 }
@@ -649,7 +679,7 @@ int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
   h->n_contrib = 0;
   h->journal.clear();
   bc_clear(h);
-  h->symbolic_valid = false;
+  invalidate(h);
   h->n_rows = h->nnz = 0;
   h->n_blocks = h->n_slabs = 0;
   return 0;
@@ -826,6 +856,7 @@ int32_t femgpu_symbolic(femgpu_t* h, int64_t* n_rows, int64_t* nnz) {
   if (st) return st;
   lap("upload + device validation");
   if (!h->symbolic_valid) {
+    h->values_valid = false;  // the value array is re-laid-out: nothing assembled yet on the new pattern
     if ((st = upload_pending(h))) return st;
     if ((st = run_symbolic(h))) return st;
     h->symbolic_valid = true;
@@ -851,6 +882,7 @@ int32_t femgpu_numeric(femgpu_t* h) {
   if (h->dist.enabled && (st = dist_numeric_exchange(h))) return st;
   FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[3], h->stream));
   h->n_numeric++;
+  h->values_valid = true;
   return 0;
 }
 

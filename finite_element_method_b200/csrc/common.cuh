@@ -32,15 +32,18 @@ struct Status {
 // Grow-only typed device allocation. The handle owns every byte it allocates; sizes are tracked so
 // femgpu_device_bytes() is exact.
 struct Handle;
+// Stream-ordered allocation from the library's PRIVATE memory pool of the current device (api.cu). The pool keeps
+// what is freed (release threshold lifted) so the tens of gigabytes a model needs are mapped once per process; the
+// device's default pool — which other cudaMallocAsync users of the process share, PyTorch among them — is left alone.
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t s);
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
   size_t* tally = nullptr;
-  // Buffers tied to a handle come from the device's stream-ordered pool (cudaMallocAsync on the
-  // handle's stream; femgpu_create lifts the pool's release threshold), so the tens of gigabytes a
-  // model needs are mapped once per process and re-used by the next symbolic pass / reset / handle
-  // instead of going back to the driver. Untied buffers fall back to cudaMalloc.
+  // Buffers tied to a handle come from the library's private stream-ordered pool (pool_malloc on the
+  // handle's stream), so the tens of gigabytes a model needs are mapped once per process and re-used by the
+  // next symbolic pass / reset / handle instead of going back to the driver. Untied buffers fall back to cudaMalloc.
   cudaStream_t* stream = nullptr;
   bool pooled = false;
   void drop(T* q, bool was_pooled) {
@@ -53,7 +56,7 @@ struct DevBuf {
     size_t want = n + n / 8 + 16;
     T* q = nullptr;
     const bool pool = stream && *stream;
-    cudaError_t e = pool ? cudaMallocAsync(reinterpret_cast<void**>(&q), want * sizeof(T), *stream)
+    cudaError_t e = pool ? pool_malloc(reinterpret_cast<void**>(&q), want * sizeof(T), *stream)
                          : cudaMalloc(&q, want * sizeof(T));
     if (e != cudaSuccess) return e;
     if (p) {
@@ -99,6 +102,9 @@ struct NumberMap {
   std::unordered_map<uint32_t, uint32_t> sparse;
   size_t count = 0;
   static constexpr uint32_t kDenseLimit = 1u << 28;
+  // A label may sit in `sparse` although it is below dense.size(): it was inserted while the dense table was
+  // still short (labels added out of order, e.g. 100000 before 1..70000) and the table grew past it later. So a
+  // miss in the dense table always falls through to `sparse` (empty in the common 1..n case: one branch).
   bool find(uint32_t number, uint32_t* idx) const {
     if (number < dense.size()) {
       uint32_t v = dense[number];
@@ -106,8 +112,8 @@ struct NumberMap {
         *idx = v - 1;
         return true;
       }
-      return false;
     }
+    if (sparse.empty()) return false;
     auto it = sparse.find(number);
     if (it == sparse.end()) return false;
     *idx = it->second;
@@ -117,8 +123,10 @@ struct NumberMap {
     if (number < kDenseLimit && number <= 8 * (count + 1024)) {
       if (number >= dense.size()) dense.resize(std::max<size_t>(size_t(number) + 1, dense.size() * 2), 0);
       dense[number] = idx + 1;
+      if (!sparse.empty()) sparse.erase(number);  // never two homes for one label
     } else {
       sparse[number] = idx;
+      if (number < dense.size()) dense[number] = 0;
     }
     ++count;
   }
@@ -128,7 +136,7 @@ struct NumberMap {
       --count;
       return;
     }
-    if (sparse.erase(number)) --count;
+    if (!sparse.empty() && sparse.erase(number)) --count;
   }
   void clear() {
     dense.clear();
@@ -302,6 +310,8 @@ struct Handle {
 
   // ---- symbolic products ----
   bool symbolic_valid = false;
+  bool values_valid = false;  // `values` holds a finished numeric pass of the CURRENT model (set by femgpu_numeric,
+                              // cleared by every add_*, reset and symbolic rebuild)
   int64_t n_rows = 0, nnz = 0;
   uint32_t n_blocks = 0, n_slabs = 0;
   int key_bits = 1;

@@ -256,6 +256,7 @@ int32_t femgpu_dist_init(femgpu_t* h, int32_t rank, int32_t world, const uint8_t
   D.recv_off.assign(world + 1, 0);
   D.send_first_block.assign(world, 0);
   h->symbolic_valid = false;
+  h->values_valid = false;
   return 0;
 }
 
@@ -267,6 +268,7 @@ int32_t femgpu_dist_set_ownership(femgpu_t* h, uint32_t node_index_begin, uint32
   h->dist.own_end = node_index_end;
   h->dist.ownership_set = true;
   h->symbolic_valid = false;
+  h->values_valid = false;
   return 0;
 }
 

@@ -118,7 +118,8 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
 //   Plate::convert_uniformly_distributed_surface_load_to_nodal_loads structs/plate.rs:1145-1185
 //       over the four Gauss points of :1066-1091: f_a += (h_a(r, s) q)(det J(r, s) alpha_r alpha_s)
 // Each load writes four (global DOF index, value) contributions (a beam's last two are padding with
-// the key 0xFFFFFFFF); the caller sorts them by key and sums every run in insertion order.
+// the key 0xFFFFFFFF; kind 3 = a concentrated load recorded after distributed ones: one contribution);
+// the caller sorts them by key and sums every run in insertion order.
 __global__ void __launch_bounds__(kPrepThreads)
 load_kernel(uint32_t n, const int32_t* __restrict__ family, const uint32_t* __restrict__ elem,
             const int32_t* __restrict__ dof, const double* __restrict__ value,
@@ -134,7 +135,11 @@ load_kernel(uint32_t n, const int32_t* __restrict__ family, const uint32_t* __re
   uint32_t node[4] = {0u, 0u, 0u, 0u};
   double f[4] = {0.0, 0.0, 0.0, 0.0};
   int nn;
-  if (family[k] == FEMGPU_BEAM) {
+  if (family[k] == 3) {  // a concentrated load queued behind distributed ones (separate.cu bc_add): elem = node index
+    nn = 1;
+    node[0] = e;
+    f[0] = q;
+  } else if (family[k] == FEMGPU_BEAM) {
     nn = 2;
     node[0] = b1[e];
     node[1] = b2[e];

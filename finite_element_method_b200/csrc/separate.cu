@@ -292,7 +292,7 @@ cudaError_t scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStre
   cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, out, n, s);
   if (e != cudaSuccess) return e;
   void* t = nullptr;
-  if ((e = cudaMallocAsync(&t, tb ? tb : 16, s)) != cudaSuccess) return e;
+  if ((e = pool_malloc(&t, tb ? tb : 16, s)) != cudaSuccess) return e;
   e = cub::DeviceScan::ExclusiveSum(t, tb, it, out, n, s);
   cudaFreeAsync(t, s);
   return e;
@@ -303,7 +303,7 @@ cudaError_t scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s)
   cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s);
   if (e != cudaSuccess) return e;
   void* t = nullptr;
-  if ((e = cudaMallocAsync(&t, tb ? tb : 16, s)) != cudaSuccess) return e;
+  if ((e = pool_malloc(&t, tb ? tb : 16, s)) != cudaSuccess) return e;
   e = cub::DeviceScan::ExclusiveSum(t, tb, in, out, n, s);
   cudaFreeAsync(t, s);
   return e;
@@ -360,8 +360,15 @@ int32_t bc_add(Handle* h, bool displacement, size_t n, const uint32_t* node_numb
                                                          " already applied to node " + std::to_string(node_number[k]) + "!");
       h->bc.constrained[i] = 1;
       h->bc.displacement[i] = value[k];
-    } else {
+    } else if (h->bc.load_family.empty()) {
       h->bc.force[i] += value[k];  // methods_for_bc_data_handle.rs:47-53
+    } else {
+      // distributed loads were recorded before this call: keep the reference's `+=` sequence per DOF by
+      // queueing the concentrated load behind them in the same ordered list (kind 3: elem = node index)
+      h->bc.load_family.push_back(3);
+      h->bc.load_elem.push_back(idx);
+      h->bc.load_dof.push_back(dof[k]);
+      h->bc.load_value.push_back(value[k]);
     }
     h->bc.uploaded = false;
     h->sep.valid = false;
@@ -550,7 +557,7 @@ int32_t run_separate(Handle* h, bool direct) {
     FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&S.nnz[q], S.row_ptr[q].p + rows_q[q], 8, cudaMemcpyDeviceToHost, s));
   }
   FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(s));
-  if (S.nnz[0] == 0)  // :303-307
+  if (!direct && S.nnz[0] == 0)  // :303-307 (the direct variant, :63-215, has no such check)
     return h->fail(FEMGPU_E_KAA_EMPTY, "Sparse separation: K_aa is empty (structure has no free stiffness?)");
 
   // ---- 4. fill
@@ -717,7 +724,7 @@ int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_
   if (h->device < 0)
     return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
                                          "femgpu has no CPU fallback");
-  if (!h->symbolic_valid || h->n_numeric == 0)
+  if (!h->symbolic_valid || !h->values_valid)
     return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_sparse needs an assembled matrix (femgpu_assemble)");
   if (h->dist.enabled)
     return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_sparse is single-GPU for now (the rows of a multi-GPU "
@@ -736,7 +743,7 @@ int32_t femgpu_separate_direct(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_
   if (h->device < 0)
     return h->fail(FEMGPU_ERR_NO_DEVICE, "this handle was created without a CUDA device (staging only); "
                                          "femgpu has no CPU fallback");
-  if (!h->symbolic_valid || h->n_numeric == 0)
+  if (!h->symbolic_valid || !h->values_valid)
     return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_direct needs an assembled matrix (femgpu_assemble)");
   if (h->dist.enabled)
     return h->fail(FEMGPU_ERR_USAGE, "femgpu_separate_direct is single-GPU (the rows of a multi-GPU assembly stay partitioned)");

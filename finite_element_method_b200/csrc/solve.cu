@@ -427,6 +427,8 @@ int32_t run_pcg(Handle* h, int preconditioner, int64_t max_iter, int64_t* iterat
   FEMGPU_CUDA_CHECK(h, cudaEventRecord(Z.ev[0], s));
   Z.ua_valid = Z.composed = false;
   const bool block = preconditioner == 1;
+  if (block && n >= (int64_t(1) << 28))  // Z.blk packs (first row of the block | size << 28) into 32 bits
+    return h->fail(FEMGPU_ERR_LIMIT, "block-Jacobi PCG supports fewer than 2^28 free degrees of freedom");
   FEMGPU_CUDA_CHECK(h, Z.u_a.reserve(size_t(n) + 1));
   FEMGPU_CUDA_CHECK(h, Z.r.reserve(size_t(n) + 1));
   FEMGPU_CUDA_CHECK(h, Z.z.reserve(size_t(n) + 1));

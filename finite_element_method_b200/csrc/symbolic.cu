@@ -32,7 +32,7 @@ struct Tmp {  // RAII scratch allocation from the stream-ordered pool
   cudaError_t alloc(size_t bytes) {
     release();
     s = t_tmp_stream;
-    return s ? cudaMallocAsync(&p, bytes ? bytes : 16, s) : cudaMalloc(&p, bytes ? bytes : 16);
+    return s ? pool_malloc(&p, bytes ? bytes : 16, s) : cudaMalloc(&p, bytes ? bytes : 16);
   }
   void release() {
     if (p) {

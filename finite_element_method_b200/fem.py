@@ -76,6 +76,13 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
+def _same_length(what, n, **arrays):
+    """The C ABI takes one count for all arrays of a batch: a short array would be read past its end."""
+    for name, a in arrays.items():
+        if a is not None and len(a) != n:
+            raise ValueError(f"{what}: `{name}` has {len(a)} entries, expected {n}")
+
+
 class FEM:
     """`FEM::create(rel_tol, abs_tol, nodes_number)` — fem.rs:34."""
 
@@ -159,17 +166,20 @@ class FEM:
     # ------------------------------------------------------------------ bulk API
     def add_nodes(self, number, x, y, z) -> None:
         number, x, y, z = _u32(number), _f64(x), _f64(y), _f64(z)
+        _same_length("add_nodes", len(number), x=x, y=y, z=z)
         self._check(self._L.femgpu_add_nodes(self._h, len(number), _p(number, _lib.u32p), _p(x, _lib.dp),
                                              _p(y, _lib.dp), _p(z, _lib.dp)))
 
     def add_trusses(self, number, node_1, node_2, young_modulus, area, area_2=None) -> None:
         number, n1, n2 = _u32(number), _u32(node_1), _u32(node_2)
         E, A = _f64(young_modulus), _f64(area)
+        A2 = None
         if area_2 is None:
             a2p = C.cast(None, _lib.dp)
         else:
             A2 = _f64([np.nan if v is None else v for v in area_2] if isinstance(area_2, (list, tuple)) else area_2)
             a2p = _p(A2, _lib.dp)
+        _same_length("add_trusses", len(number), node_1=n1, node_2=n2, young_modulus=E, area=A, area_2=A2)
         self._check(self._L.femgpu_add_truss(self._h, len(number), _p(number, _lib.u32p), _p(n1, _lib.u32p),
                                              _p(n2, _lib.u32p), _p(E, _lib.dp), _p(A, _lib.dp), a2p))
 
@@ -181,6 +191,8 @@ class FEM:
         ax = _f64(np.asarray(local_axis_1, np.float64).reshape(3, -1))
         if ax.shape[1] != len(number):
             raise ValueError("local_axis_1 must have shape (3, n)")
+        _same_length("add_beams", len(number), node_1=n1, node_2=n2,
+                     **dict(zip(("young_modulus", "poisson_ratio", "area", "i11", "i22", "i12", "it", "shear_factor"), arrs)))
         self._check(self._L.femgpu_add_beam(self._h, len(number), _p(number, _lib.u32p), _p(n1, _lib.u32p),
                                             _p(n2, _lib.u32p), *[_p(a, _lib.dp) for a in arrs], _p(ax, _lib.dp)))
 
@@ -189,6 +201,8 @@ class FEM:
         number = _u32(number)
         ns = [_u32(v) for v in (node_1, node_2, node_3, node_4)]
         arrs = [_f64(v) for v in (young_modulus, poisson_ratio, thickness, shear_factor)]
+        _same_length("add_plates", len(number), **dict(zip(("node_1", "node_2", "node_3", "node_4"), ns)),
+                     **dict(zip(("young_modulus", "poisson_ratio", "thickness", "shear_factor"), arrs)))
         self._check(self._L.femgpu_add_plate(self._h, len(number), _p(number, _lib.u32p),
                                              *[_p(a, _lib.u32p) for a in ns], *[_p(a, _lib.dp) for a in arrs]))
 
@@ -268,6 +282,7 @@ class FEM:
         """methods_for_bc_data_handle.rs:175 (arrays are accepted: n calls in order)"""
         nn, dd, vv = _u32(np.atleast_1d(node_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
             _f64(np.atleast_1d(value))
+        _same_length("add_displacement", len(nn), dof_parameter=dd, value=vv)
         self._check(self._L.femgpu_add_displacement(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p),
                                                     _p(vv, _lib.dp)))
 
@@ -275,6 +290,7 @@ class FEM:
         """methods_for_bc_data_handle.rs:31"""
         nn, dd, vv = _u32(np.atleast_1d(node_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
             _f64(np.atleast_1d(value))
+        _same_length("add_concentrated_load", len(nn), dof_parameter=dd, value=vv)
         self._check(self._L.femgpu_add_concentrated_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p),
                                                          _p(vv, _lib.dp)))
 
@@ -282,12 +298,14 @@ class FEM:
         """methods_for_bc_data_handle.rs:58 (arrays are accepted: n calls in order)"""
         nn, dd, vv = _u32(np.atleast_1d(beam_element_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
             _f64(np.atleast_1d(value))
+        _same_length("add_uniformly_distributed_line_load", len(nn), dof_parameter=dd, value=vv)
         self._check(self._L.femgpu_add_line_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p), _p(vv, _lib.dp)))
 
     def add_uniformly_distributed_surface_load(self, plate_element_number, dof_parameter, value) -> None:
         """methods_for_bc_data_handle.rs:104"""
         nn, dd, vv = _u32(np.atleast_1d(plate_element_number)), np.ascontiguousarray(np.atleast_1d(dof_parameter), np.int32), \
             _f64(np.atleast_1d(value))
+        _same_length("add_uniformly_distributed_surface_load", len(nn), dof_parameter=dd, value=vv)
         self._check(self._L.femgpu_add_surface_load(self._h, len(nn), _p(nn, _lib.u32p), _p(dd, _lib.i32p), _p(vv, _lib.dp)))
 
     def forces_vector(self, copy_out: bool = True):

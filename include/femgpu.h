@@ -224,8 +224,9 @@ int32_t femgpu_add_concentrated_load(femgpu_t* h, size_t n, const uint32_t* node
  * n x FEM::add_uniformly_distributed_surface_load(plate_element_number, dof_parameter, value)    :104-173
  * The nodal equivalents (Beam::convert_uniformly_distributed_line_load_to_nodal_loads structs/beam.rs:775-797,
  * Plate::convert_uniformly_distributed_surface_load_to_nodal_loads structs/plate.rs:1145-1185) are
- * evaluated on the device and added to the forces vector, per DOF in call order, when the forces are
- * next needed (femgpu_get_forces, femgpu_separate_sparse). */
+ * evaluated on the device and added to the forces vector, per DOF in call order — across all three load kinds:
+ * a concentrated load added after distributed ones is queued behind them — when the forces are next needed
+ * (femgpu_get_forces, femgpu_separate_sparse). */
 int32_t femgpu_add_line_load(femgpu_t* h, size_t n, const uint32_t* beam_number, const int32_t* dof,
                              const double* value);
 int32_t femgpu_add_surface_load(femgpu_t* h, size_t n, const uint32_t* plate_number, const int32_t* dof,
@@ -276,7 +277,10 @@ int32_t femgpu_last_separate_ms(femgpu_t* h, float* ms);
  * (build_block_starts_from_k_aa_indexes, :121-147). Stops when ||r||_2 <= max(rel_tol ||b||_2, abs_tol);
  * `iterations` = search directions used. The reference's arithmetic lives in the un-vendored crate
  * iterative_solvers_smpl: parity is pinned on the reference's own test only (one iteration, u = 0.0015).
- * Deterministic (fixed reduction trees, no atomics). FEMGPU_E_SOLVER when it does not converge. */
+ * Deterministic (fixed reduction trees, no atomics). When max_iter search directions did not reach the stopping
+ * test the call returns FEMGPU_E_SOLVER (the reference crate's behaviour in that case is not pinned: its solver is
+ * un-vendored); `iterations`, femgpu_solve_info and femgpu_get_ua still report the last iterate. Block Jacobi is
+ * limited to n_aa < 2^28 (FEMGPU_ERR_LIMIT). */
 int32_t femgpu_solve_pcg(femgpu_t* h, int32_t preconditioner, int64_t max_iter, int64_t* iterations);
 /* FEM::find_ua_vector_direct                              methods_for_global_analysis.rs:161-187
  * K_aa u_a = b by the active-column LDL^T of the skyline form femgpu_separate_direct left on the device (the

@@ -127,6 +127,11 @@ impl FEM {
     /// Bulk load: struct-of-arrays slices, prefix-atomic (see include/femgpu.h).
     pub fn add_plates(&mut self, number: &[u32], n1: &[u32], n2: &[u32], n3: &[u32], n4: &[u32], e: &[f64],
                       nu: &[f64], t: &[f64], ks: &[f64]) -> Result<(), String> {
+        // the C ABI takes ONE count for all nine arrays: a shorter slice would be read past its end
+        let n = number.len();
+        if [n1.len(), n2.len(), n3.len(), n4.len(), e.len(), nu.len(), t.len(), ks.len()].iter().any(|&l| l != n) {
+            return Err(format!("add_plates: every slice must hold {} entries", n));
+        }
         self.check(unsafe { femgpu_add_plate(self.h, number.len(), number.as_ptr(), n1.as_ptr(), n2.as_ptr(),
                                              n3.as_ptr(), n4.as_ptr(), e.as_ptr(), nu.as_ptr(), t.as_ptr(), ks.as_ptr()) })
     }

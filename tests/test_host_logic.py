@@ -201,3 +201,53 @@ def test_reset_reuses_storage_but_forgets_everything():
     with pytest.raises(FemError, match="Node with number 3 does not exist!"):
         fem.add_trusses([2], [1], [3], [1e6], [2.0])
     fem.close()
+
+
+def test_labels_added_out_of_order_are_all_found():
+    """a label inserted while the dense number table was still short went to the
+    sparse map; once the dense table grew past it, lookups missed it. Label 100000 before 1..70000."""
+    n = 70001
+    f = staged(n + 8)
+    f.add_node(100000, -1.0, 0.0, 0.0)
+    k = np.arange(1, n, dtype=np.uint32)
+    f.add_nodes(k, k.astype(np.float64), np.zeros(n - 1), np.zeros(n - 1))
+    # the early label is still known: as a duplicate ...
+    raises(1, "Node with number 100000 already exists!", f.add_node, 100000, -2.0, 0.0, 0.0)
+    # ... and as an element node
+    f.add_trusses([1], [100000], [1], [1e6], [2.0])
+    f.add_trusses([2], [70000], [100000], [1e6], [2.0])
+    assert f.counts() == (n, 2, 0, 0)
+    # element labels go through the same map
+    g = staged(16)
+    g.add_nodes(np.arange(1, 11), np.arange(10.0), np.zeros(10), np.zeros(10))
+    g.add_trusses([500000], [1], [2], [1e6], [2.0])
+    lab = np.arange(1, 9, dtype=np.uint32)
+    g.add_trusses(lab, lab + 1, lab + 2, np.full(8, 1e6), np.full(8, 2.0))
+    raises(10, "Truss element with number 500000 already exists!", g.add_trusses, [500000], [9], [10], [1e6], [2.0])
+    # a rolled-back batch forgets its labels again, wherever they lived
+    h = staged(4)
+    raises(5, "Nodes number could not be greater than 4!", h.add_nodes, [900000, 1, 2, 3, 4], np.arange(5.0),
+           np.zeros(5), np.zeros(5))
+    h2 = staged(8)
+    h2.add_node(1, 0.0, 0.0, 0.0)
+    # the batch fails at its FIRST node (coordinates exist): the labels 900000 and 5 it had already entered are forgotten
+    raises(4, "Node with coordinates x: 0.0, y: 0.0, z: 0.0 already exists!", h2.add_nodes, [900000, 5], [0.0, 1.0],
+           np.zeros(2), np.zeros(2))
+    h2.add_nodes([5, 900000], [5.0, 6.0], np.zeros(2), np.zeros(2))
+    raises(1, "Node with number 900000 already exists!", h2.add_node, 900000, 9.0, 0.0, 0.0)
+    assert h2.counts()[0] == 3
+
+
+def test_bulk_wrappers_reject_ragged_arrays():
+    f = staged(8)
+    with pytest.raises(ValueError):
+        f.add_nodes([1, 2, 3], [0.0, 1.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+    f.add_nodes([1, 2, 3, 4], [0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0], np.zeros(4))
+    with pytest.raises(ValueError):
+        f.add_trusses([1, 2], [1, 2], [2], [1e6, 1e6], [2.0, 2.0])
+    with pytest.raises(ValueError):
+        f.add_plates([1], [3], [4], [1], [2], [2.1e11, 1.0], [0.3], [0.01], [5 / 6])
+    with pytest.raises(ValueError):
+        f.add_beams([1, 2], [1, 2], [2, 3], [1.0, 1.0], [0.3], [1.0, 1.0], [1.0, 1.0], [1.0, 1.0], [0.0, 0.0],
+                    [1.0, 1.0], [1.0, 1.0], np.zeros((3, 2)))
+    assert f.counts() == (4, 0, 0, 0)
