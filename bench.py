@@ -5,8 +5,9 @@
 
 A "step" is one numeric pass (element records + deterministic assembly into the prebuilt CSR) over
 the whole synthetic mesh. Default workload: config M, the 10M-element mixed truss/beam/plate
-structure of BASELINE.json on one B200; with N GPUs (torchrun, one rank per GPU) each rank gets a
-strip of the same shape (weak scaling) unless --scaling strong.
+structure of BASELINE.json on one B200; with N GPUs (torchrun, one rank per GPU) that ONE mesh is
+partitioned into N contiguous row strips (strong scaling — BASELINE.json configs 4 and 5); the weak-scaling
+figure (every rank a strip of the full size) is measured in the same run and reported under the key "weak".
 
 Prints ONE JSON line (rank 0). Keys beyond the base contract:
   roofline      dominant kernel (assemble_kernel) against the measured HBM copy peak
@@ -176,94 +177,98 @@ def cpu_baseline(config: str):
     }
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="M", choices=list(CONFIGS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-separation", action="store_true")
-    ap.add_argument("--nx", type=int, default=None, help="override grid size (testing)")
-    ap.add_argument("--ny", type=int, default=None)
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = max(args.warmup, 1)
+_T0 = time.perf_counter()
 
-    if args.impl == "reference":
-        run_reference(args)
-        return
 
+def log(msg: str) -> None:
+    """Per-phase progress on stderr (flushed), so that a run that stops somewhere says where."""
+    rank = os.environ.get("RANK", "0")
+    print(f"[bench rank {rank} +{time.perf_counter() - _T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def watchdog(seconds: int) -> None:
+    """(Re-)arm the hang watchdog: if the process is still in the same phase after `seconds`, dump every thread's
+    stack to stderr and exit — a stuck rank must not spin on its GPU until the launcher's own timeout."""
+    import faulthandler
+    faulthandler.cancel_dump_traceback_later()
+    if seconds > 0:
+        faulthandler.dump_traceback_later(seconds, exit=True)
+
+
+def workload(args, scaling, rank, world):
+    """(local mesh of this rank, whole-mesh name, n_nodes, n_el_total, begin, end): with several ranks only
+    this rank's strip of elements is built (identical to local_part() of the whole mesh, tests/test_host_logic.py)."""
+    from finite_element_method_b200 import meshes
+    variant = args.variant
+    if args.config in ("M", "P"):
+        nx = args.nx or 2000
+        ny = (args.ny or 2000) * (world if scaling == "weak" else 1)
+        grid_w, n_nodes = nx + 1, (nx + 1) * (ny + 1)
+        begin, end = meshes.partition_rows({"x": np.empty(n_nodes, np.uint8)}, world, grid_w)[rank]
+        rows = (begin // grid_w, end // grid_w) if world > 1 else None
+        local = (meshes.mixed_structure(nx, ny, rows=rows, variant=variant) if args.config == "M"
+                 else meshes.plate_grid(nx, ny, variant, rows=rows))
+        n_el_total = nx * ny * (1 if args.config == "P" else 2) + (len(range(0, nx, 2)) * ny if args.config == "M" else 0)
+        return local, local["name"], n_nodes, n_el_total, begin, end
+    jitter = variant == "jitter"
+    if args.config == "B":
+        mesh = meshes.beam_frame(args.nx or 88, 2_000_000 if args.nx is None else 10 ** 9, jitter=jitter)
+    else:
+        mesh = meshes.truss_lattice(args.nx or 64, 1_000_000 if args.nx is None else 10 ** 9, jitter=jitter)
+    n_nodes = len(mesh["x"])
+    begin, end = meshes.partition_rows(mesh, world, None)[rank]
+    local = meshes.local_part(mesh, begin, end) if world > 1 else mesh
+    return local, mesh["name"], n_nodes, meshes.n_elements(mesh), begin, end
+
+
+def measure_numeric(args, scaling, ctx, sample_clocks):
+    """Build this rank's part of the workload, run W warm-up + K timed numeric passes; returns the numbers of the
+    JSON line that depend on the scaling mode. Collective over the ranks."""
     import torch
     from finite_element_method_b200 import FEM, meshes
+    rank, world, local_rank, dist = ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dist"]
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (femgpu has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def barrier():
+        # this handle's stream first: the torch collective must never be in flight together with work of the
+        # library's own communicator / peer windows
+        fem.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
 
-    # ---------------------------------------------------------------- workload
-    scale_y = world if (args.scaling == "weak" and args.config in ("M", "P")) else 1
-    if world > 1 and args.config in ("M", "P"):
-        # every rank needs every node but only its own strip of elements: build just that
-        # (identical to local_part() of the whole mesh, tests/test_host_logic.py)
-        nx, ny = args.nx or 2000, (args.ny or 2000) * scale_y
-        grid_w, n_nodes = nx + 1, (nx + 1) * (ny + 1)
-        parts = meshes.partition_rows({"x": np.empty(n_nodes, np.uint8)}, world, grid_w)
-        begin, end = parts[rank]
-        rows = (begin // grid_w, end // grid_w)
-        local = (meshes.mixed_structure(nx, ny, rows=rows) if args.config == "M"
-                 else meshes.plate_grid(nx, ny, "flat", rows=rows))
-        mesh = local
-        n_el_total = nx * ny * (1 if args.config == "P" else 2) + (len(range(0, nx, 2)) * ny if args.config == "M" else 0)
-    else:
-        mesh, grid_w = build_mesh(args.config, scale_y, args.nx, args.ny)
-        n_nodes = len(mesh["x"])
-        parts = meshes.partition_rows(mesh, world, grid_w)
-        begin, end = parts[rank]
-        local = meshes.local_part(mesh, begin, end) if world > 1 else mesh
-        n_el_total = meshes.n_elements(mesh)
+    log(f"{scaling}: building the mesh")
+    local, mesh_name, n_nodes, n_el_total, begin, end = workload(args, scaling, rank, world)
     n_el_local = meshes.n_elements(local)
-
-    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n_nodes, device=local_rank)
+    fem = FEM(local["rel_tol"], local["abs_tol"], n_nodes, device=local_rank)
     if world > 1:
         uid = [FEM.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         fem.dist_init(rank, world, uid[0])
         fem.dist_set_ownership(begin, end)
+    log(f"{scaling}: add_* ({n_el_local} elements, {n_nodes} nodes)")
     t0 = time.perf_counter()
     fem.load_mesh(local)
     t_load = time.perf_counter() - t0
+    log(f"{scaling}: symbolic")
     t0 = time.perf_counter()
     n_rows, nnz_local = fem.symbolic()
     t_sym = time.perf_counter() - t0
-
     stream = torch.cuda.ExternalStream(fem.stream(), device=torch.device("cuda", local_rank))
+    p2p = fem.dist_info()[0] if world > 1 else None
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------------------------------------------------------- timed region
+    log(f"{scaling}: warm-up ({args.warmup} passes)")
     fem.launch_count(reset=True)
     for _ in range(args.warmup):
         fem.numeric()
     barrier()
-    launches_warm = fem.launch_count(reset=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    fem.launch_count(reset=True)
+    sampler = ClockSampler(local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    log(f"{scaling}: timed region ({args.steps} passes)")
     ev0.record(stream)
     for _ in range(args.steps):
         fem.numeric()
@@ -272,27 +277,35 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     launches = fem.launch_count()
     hist = [fem.numeric_ms_history(i) for i in range(min(args.steps, 64))]   # the timed passes
-    # the timed region lasts ~0.1 s, shorter than nvidia-smi's polling period: keep the identical load
-    # running (untimed) for about a second more so the clock sample covers several polls under load
-    t_end = time.perf_counter() + 1.0
-    while time.perf_counter() < t_end:
-        for _ in range(10):
-            fem.numeric()
-        fem.synchronize()
-    clocks = sampler.stop()
-    clocks["window"] = "timed steps + ~1 s of the same passes, untimed (nvidia-smi polls every 100 ms)"
-    asm_ms = float(np.mean([h[2] for h in hist]))
-    prep_ms = float(np.mean([h[1] for h in hist]))
-    xchg_ms = float(np.mean([h[3] for h in hist]))
     if dist is not None:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         cnt = torch.tensor([float(n_el_local), float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt)
+        torch.cuda.synchronize()
         assert int(cnt[0].item()) == n_el_total, "partition lost or duplicated elements"
         launches = int(cnt[1].item())
     ms_step = ms_total / args.steps
+    clocks = None
+    if sampler:
+        # The timed region lasts ~0.1 s, shorter than nvidia-smi's polling period: keep the identical load running
+        # (untimed) for about a second more so the clock sample covers several polls under load. The number of
+        # extra passes is derived from the all-reduced step time — the SAME on every rank (the passes exchange
+        # ghost rows between neighbours: a rank-local wall-clock bound would leave the ranks with unequal pass
+        # counts, i.e. an exchange that never completes).
+        extra = int(min(2000, max(10, 1000.0 / max(ms_step, 0.05))))
+        log(f"{scaling}: {extra} more passes under the clock sampler")
+        for i in range(extra):
+            fem.numeric()
+            if i % 16 == 15:
+                fem.synchronize()
+        barrier()
+        clocks = sampler.stop()
+        clocks["window"] = f"timed steps + {extra} more of the same passes, untimed (nvidia-smi polls every 100 ms)"
+    asm_ms = float(np.mean([h[2] for h in hist]))
+    prep_ms = float(np.mean([h[1] for h in hist]))
+    xchg_ms = float(np.mean([h[3] for h in hist]))
     value = n_el_total / (ms_step * 1e-3)
 
     # ---------------------------------------------------------------- roofline (dominant kernel)
@@ -306,105 +319,239 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = ab["total_bytes"] / (asm_ms * 1e-3) / 1e9
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)
+    traffic_src = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.config, {}).get("dram_bytes_per_launch") if world == 1 and not (args.nx or args.ny) else None
+            tj = json.load(f)
+        key = args.config if args.variant == "flat" else f"{args.config}-{args.variant}"
+        if world == 1 and not (args.nx or args.ny) and key in tj:
+            traffic = tj[key].get("dram_bytes_per_launch")
+            traffic_src = "profiles/traffic.json (" + tj[key].get("source", "ncu --set full capture") + "), not measured in this run"
     except OSError:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "assemble_kernel", "kernel_ms": asm_ms, "prep_ms": prep_ms,
-                "exchange_ms": xchg_ms, "algorithmic_bytes_per_launch": ab["total_bytes"], "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "assemble_kernel", "kernel_ms": asm_ms,
+                "prep_ms": prep_ms, "exchange_ms": xchg_ms, "algorithmic_bytes_per_launch": ab["total_bytes"],
+                "peak_source": peak_src, "per": "rank 0",
                 "whole_step_frac": ab["total_bytes"] / (ms_step * 1e-3) / 1e9 / peak}
+    out = {"value": value, "ms_per_step": ms_step, "launches": launches, "roofline": roofline, "clocks": clocks,
+           "mesh_name": mesh_name, "n_el_total": n_el_total, "n_el_local": n_el_local, "n_nodes": n_nodes,
+           "nnz_local": nnz_local, "symbolic_s": t_sym, "load_s": t_load, "begin": begin, "end": end,
+           "exchange": None if world == 1 else ("peer windows over NVLink (CUDA IPC), flags in HBM" if p2p
+                                                else "ncclSend/ncclRecv")}
+    return fem, local, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="M", choices=list(CONFIGS))
+    ap.add_argument("--variant", default="flat", choices=["flat", "jitter", "x0"],
+                    help="P / M: flat (Q == I), jitter (in-plane), x0 (the mesh in the x = 0 plane, Q != I); B / T: jitter")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = ONE mesh of the configured size split over the ranks (BASELINE.json configs 4-5, "
+                         "default); weak = every rank a strip of the configured size")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the additional weak-scaling measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-separation", action="store_true")
+    ap.add_argument("--nx", type=int, default=None, help="override grid size (testing)")
+    ap.add_argument("--ny", type=int, default=None)
+    ap.add_argument("--phase-timeout", type=int, default=420, help="seconds a phase may take before the run aborts")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.variant == "x0" and args.config in ("B", "T"):
+        ap.error("--variant x0 applies to the plate configurations")
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    watchdog(args.phase_timeout)
+    import datetime
+
+    import torch
+    from finite_element_method_b200 import meshes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (femgpu has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        log("init_process_group")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
+    ctx = {"rank": rank, "world": world, "local_rank": local_rank, "dist": dist}
+    scaling = args.scaling if world > 1 else "strong"
+
+    fem, local, m = measure_numeric(args, scaling, ctx, sample_clocks=True)
+    n_nodes, n_el_total, n_el_local = m["n_nodes"], m["n_el_total"], m["n_el_local"]
+    roofline, peak = m["roofline"], m["roofline"]["peak"]
+    nnz_local = m["nnz_local"]
+
+    # ---------------------------------------------------------------- FP64 pipe, N = 1
+    fp64 = None
+    if world == 1:
+        watchdog(args.phase_timeout)
+        log("FP64 FMA micro-benchmark")
+        peak_tf = fem.fp64_fma_peak()
+        # FP64 operations of one assemble_kernel launch: thread-level DFMA (x2) + DMUL + DADD instruction counts of the
+        # ncu capture named in profiles/traffic.json (exact for this workload: the kernel's work does not vary)
+        flops = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            key = args.config if args.variant == "flat" else f"{args.config}-{args.variant}"
+            if not (args.nx or args.ny):
+                flops = tj.get(key, {}).get("fp64_flops_per_launch")
+        except OSError:
+            pass
+        kms = roofline["kernel_ms"] * 1e-3
+        fp64 = {"measured_peak_TFLOPs": peak_tf,
+                "how": "femgpu_fp64_fma_peak: 8 independent DFMA chains per thread, 8 x 256 threads per SM, best of 5",
+                "kernel_flops_per_launch": flops,
+                "flops_source": "ncu smsp__sass_thread_inst_executed_op_{dfma x2, dmul, dadd}_pred_on of the capture in profiles/traffic.json",
+                "achieved_TFLOPs": None if flops is None else flops / kms / 1e12,
+                "fp64_pipe_frac": None if flops is None else flops / kms / 1e12 / peak_tf,
+                "ridge_flop_per_byte": peak_tf * 1e3 / peak,
+                "arithmetic_intensity_flop_per_byte": None if flops is None else flops / roofline["algorithmic_bytes_per_launch"]}
+        roofline["fp64_pipe_frac"] = fp64["fp64_pipe_frac"]
+
+    # ---------------------------------------------------------------- next row (SURVEY §8f), reported aside
+    separation = None
+    if world == 1 and not args.no_separation:
+        watchdog(args.phase_timeout)
+        log("separation / PCG / element results")
+        separation = measure_downstream(args, fem, local, n_nodes, nnz_local, peak)
+    if dist is not None:
+        fem.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+    fem.close()          # one library communicator at a time: the next measurement creates its own
+
+    # ---------------------------------------------------------------- the other scaling mode (N > 1)
+    other = None
+    if world > 1 and not args.no_weak and args.config in ("M", "P"):
+        watchdog(args.phase_timeout)
+        mode2 = "weak" if scaling == "strong" else "strong"
+        fem2, _, m2 = measure_numeric(args, mode2, ctx, sample_clocks=False)
+        fem2.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        fem2.close()
+        other = {"scaling": mode2, "value": m2["value"], "unit": "elements/s", "ms_per_step": m2["ms_per_step"],
+                 "elements": m2["n_el_total"], "mesh": m2["mesh_name"], "kernel_ms": m2["roofline"]["kernel_ms"],
+                 "prep_ms": m2["roofline"]["prep_ms"], "exchange_ms": m2["roofline"]["exchange_ms"],
+                 "frac": m2["roofline"]["frac"], "whole_step_frac": m2["roofline"]["whole_step_frac"]}
 
     # ---------------------------------------------------------------- e2e through the public API
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, rank, world, begin, end)
+        watchdog(args.phase_timeout)
+        log("e2e")
+        e2e = measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, rank, world, m["begin"], m["end"])
 
-    # ---------------------------------------------------------------- next row (SURVEY §8f rank 1), reported aside
-    separation = None
-    if world == 1 and not args.no_separation:
-        # clamp the first 64 nodes (translations only for the truss lattice: it has no rotational stiffness)
-        ndof = 3 if args.config == "T" else 6
-        nodes = np.repeat(np.arange(1, 65, dtype=np.uint32), ndof)
-        fem.add_displacement(nodes, np.tile(np.arange(ndof, dtype=np.int32), 64), np.zeros(len(nodes)))
-        fem.add_concentrated_load(n_nodes, 0, 1.0e3)
-        # §8f rank 2: a uniform load on every beam and every plate -> nodal loads, evaluated on the device
-        n_pl = np.asarray(local["p_n"]).reshape(4, -1).shape[1]
-        n_bm = len(local["b_n1"])
-        loads = None
-        if n_pl + n_bm:
-            if n_bm:
-                fem.add_uniformly_distributed_line_load(np.arange(1, n_bm + 1, dtype=np.uint32),
-                                                        np.full(n_bm, 2, np.int32), np.full(n_bm, -2.0e3))
-            if n_pl:
-                fem.add_uniformly_distributed_surface_load(np.arange(1, n_pl + 1, dtype=np.uint32),
-                                                           np.full(n_pl, 2, np.int32), np.full(n_pl, -1.0e3))
-            fem.synchronize()
-            t0 = time.perf_counter()
-            fem.forces_vector(copy_out=False)
-            fem.synchronize()
-            loads = {"op": "uniformly distributed line/surface loads -> forces vector, on the device (upload of the load "
-                           "list, nodal loads, stable sort by DOF, in-order sums)", "n_loads": int(n_pl + n_bm),
-                     "ms_wall": (time.perf_counter() - t0) * 1e3}
-        fem.separate_stiffness_matrix_sparse_iterative(copy_out=False)          # warm-up (allocations)
-        n_aa, n_bb, q_nnz, sep_ms = fem.separate_stiffness_matrix_sparse_iterative(copy_out=False)
-        sep_bytes = 12 * nnz_local + 12 * sum(q_nnz)      # col_idx + values read once, compacted copies written once
-        separation = {"op": "separate_stiffness_matrix_sparse_iterative + b = R_a - K_ab u_b, on the device",
-                      "ms": sep_ms, "n_aa": n_aa, "n_bb": n_bb, "nnz_aa_ab_ba_bb": q_nnz,
-                      "algorithmic_bytes": sep_bytes, "achieved_GBps": sep_bytes / (sep_ms * 1e-3) / 1e9,
-                      "frac_of_hbm_peak": sep_bytes / (sep_ms * 1e-3) / 1e9 / peak, "distributed_loads": loads}
-        # §8f ranks 3-4: a fixed number of PCG iterations on K_aa (the model is far from converged after that:
-        # only the per-iteration cost is reported) and the element result recovery from a displacement vector
-        from finite_element_method_b200 import FemError
-        analysis = {}
-        for name, solve in (("pcg_jacobi", fem.find_ua_vector_iterative_pcg_jacobi_sparse),
-                            ("pcg_block_jacobi", fem.find_ua_vector_iterative_pcg_block_jacobi_sparse)):
-            iters = 0
-            for max_iter in (3, 25):          # the first call allocates the work vectors
-                try:
-                    iters = solve(max_iter, copy_out=False)[1]
-                except FemError:
-                    iters = fem.solve_info()[0]
-            it_ms = fem.solve_info()[2] / max(1, iters)
-            it_bytes = 12 * q_nnz[0] + 8 * n_aa * (14 if name == "pcg_jacobi" else 22)   # K_aa once + ~14 (22) vector passes of 8 B per row
-            analysis[name] = {"iterations_timed": iters, "ms_per_iteration": it_ms, "algorithmic_bytes_per_iteration": it_bytes,
-                              "achieved_GBps": it_bytes / (it_ms * 1e-3) / 1e9,
-                              "frac_of_hbm_peak": it_bytes / (it_ms * 1e-3) / 1e9 / peak}
-        fem.set_displacements_vector(np.random.default_rng(7).normal(size=6 * n_nodes) * 1e-3)
-        res_ms = {}
-        for fam, fname, n_f, comps, rec in ((0, "truss", len(local["t_n1"]), 1, 24), (1, "beam", n_bm, 10, 96), (2, "plate", n_pl, 8, 48)):
-            if not n_f:
-                continue
-            fem.element_results(fam, copy_out=False)
-            fem.synchronize()
-            t0 = time.perf_counter()
-            fem.element_results(fam, copy_out=False)
-            dt = (time.perf_counter() - t0) * 1e3
-            nn = 4 if fam == 2 else 2
-            b = n_f * (rec + 8 * comps + nn * (24 + 48))      # record + results + gathered coordinates / displacements
-            res_ms[fname] = {"elements": int(n_f), "ms_wall": dt, "algorithmic_GBps": b / (dt * 1e-3) / 1e9}
-        analysis["element_results"] = res_ms
-        separation["analysis"] = analysis
-
+    watchdog(args.phase_timeout)
     if rank == 0:
+        log("cpu baseline")
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.config)
         line = {
-            "metric": "elements assembled/s (FP64)", "value": value, "unit": "elements/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config], "config": args.config, "mesh": mesh["name"],
-                       "elements": n_el_total, "nodes": n_nodes, "nnz_rank0": nnz_local,
-                       "parallelism": f"row-strips x{world}" if world > 1 else "single GPU",
+            "metric": "elements assembled/s (FP64)", "value": m["value"], "unit": "elements/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config], "config": args.config, "variant": args.variant,
+                       "mesh": m["mesh_name"], "elements": n_el_total, "nodes": n_nodes, "nnz_rank0": nnz_local,
+                       "parallelism": (f"{world} contiguous row strips of one mesh, ghost rows exchanged through "
+                                       f"{m['exchange']}" if world > 1 and scaling == "strong" else
+                                       f"row-strips x{world} ({m['exchange']})" if world > 1 else "single GPU"),
                        "l2": "working set (>= 0.2 GB of CSR values rewritten per step) is larger than the 126 MB L2; no flush needed",
-                       "symbolic_s": t_sym, "load_s": t_load},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "separation": separation,
+                       "symbolic_s": m["symbolic_s"], "load_s": m["load_s"]},
+            "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": m["launches"],
+            "clocks": m["clocks"], "separation": separation,
         }
+        if other is not None:
+            line[other["scaling"]] = other
         print(json.dumps(line), flush=True)
-    fem.close()
+    watchdog(0)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_downstream(args, fem, local, n_nodes, nnz_local, peak):
+    """SURVEY §8f on the assembled matrix of the timed handle (N = 1): distributed loads, K separation, a fixed number
+    of PCG iterations, element results."""
+    # clamp the first 64 nodes (translations only for the truss lattice: it has no rotational stiffness)
+    ndof = 3 if args.config == "T" else 6
+    nodes = np.repeat(np.arange(1, 65, dtype=np.uint32), ndof)
+    fem.add_displacement(nodes, np.tile(np.arange(ndof, dtype=np.int32), 64), np.zeros(len(nodes)))
+    fem.add_concentrated_load(n_nodes, 0, 1.0e3)
+    # §8f rank 2: a uniform load on every beam and every plate -> nodal loads, evaluated on the device
+    n_pl = np.asarray(local["p_n"]).reshape(4, -1).shape[1]
+    n_bm = len(local["b_n1"])
+    loads = None
+    if n_pl + n_bm:
+        if n_bm:
+            fem.add_uniformly_distributed_line_load(np.arange(1, n_bm + 1, dtype=np.uint32),
+                                                    np.full(n_bm, 2, np.int32), np.full(n_bm, -2.0e3))
+        if n_pl:
+            fem.add_uniformly_distributed_surface_load(np.arange(1, n_pl + 1, dtype=np.uint32),
+                                                       np.full(n_pl, 2, np.int32), np.full(n_pl, -1.0e3))
+        fem.synchronize()
+        t0 = time.perf_counter()
+        fem.forces_vector(copy_out=False)
+        fem.synchronize()
+        loads = {"op": "uniformly distributed line/surface loads -> forces vector, on the device (upload of the load "
+                       "list, nodal loads, stable sort by DOF, in-order sums)", "n_loads": int(n_pl + n_bm),
+                 "ms_wall": (time.perf_counter() - t0) * 1e3}
+    fem.separate_stiffness_matrix_sparse_iterative(copy_out=False)          # warm-up (allocations)
+    n_aa, n_bb, q_nnz, sep_ms = fem.separate_stiffness_matrix_sparse_iterative(copy_out=False)
+    sep_bytes = 12 * nnz_local + 12 * sum(q_nnz)      # col_idx + values read once, compacted copies written once
+    separation = {"op": "separate_stiffness_matrix_sparse_iterative + b = R_a - K_ab u_b, on the device",
+                  "ms": sep_ms, "n_aa": n_aa, "n_bb": n_bb, "nnz_aa_ab_ba_bb": q_nnz,
+                  "algorithmic_bytes": sep_bytes, "achieved_GBps": sep_bytes / (sep_ms * 1e-3) / 1e9,
+                  "frac_of_hbm_peak": sep_bytes / (sep_ms * 1e-3) / 1e9 / peak, "distributed_loads": loads}
+    # §8f ranks 3-4: a fixed number of PCG iterations on K_aa (the model is far from converged after that:
+    # only the per-iteration cost is reported) and the element result recovery from a displacement vector
+    from finite_element_method_b200 import FemError
+    analysis = {}
+    for name, solve in (("pcg_jacobi", fem.find_ua_vector_iterative_pcg_jacobi_sparse),
+                        ("pcg_block_jacobi", fem.find_ua_vector_iterative_pcg_block_jacobi_sparse)):
+        iters = 0
+        for max_iter in (3, 25):          # the first call allocates the work vectors
+            try:
+                iters = solve(max_iter, copy_out=False)[1]
+            except FemError:
+                iters = fem.solve_info()[0]
+        it_ms = fem.solve_info()[2] / max(1, iters)
+        it_bytes = 12 * q_nnz[0] + 8 * n_aa * (14 if name == "pcg_jacobi" else 22)   # K_aa once + ~14 (22) vector passes of 8 B per row
+        analysis[name] = {"iterations_timed": iters, "ms_per_iteration": it_ms, "algorithmic_bytes_per_iteration": it_bytes,
+                          "achieved_GBps": it_bytes / (it_ms * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": it_bytes / (it_ms * 1e-3) / 1e9 / peak}
+    fem.set_displacements_vector(np.random.default_rng(7).normal(size=6 * n_nodes) * 1e-3)
+    res_ms = {}
+    for fam, fname, n_f, comps, rec in ((0, "truss", len(local["t_n1"]), 1, 24), (1, "beam", n_bm, 10, 96), (2, "plate", n_pl, 8, 48)):
+        if not n_f:
+            continue
+        fem.element_results(fam, copy_out=False)
+        fem.synchronize()
+        t0 = time.perf_counter()
+        fem.element_results(fam, copy_out=False)
+        dt = (time.perf_counter() - t0) * 1e3
+        nn = 4 if fam == 2 else 2
+        b = n_f * (rec + 8 * comps + nn * (24 + 48))      # record + results + gathered coordinates / displacements
+        res_ms[fname] = {"elements": int(n_f), "ms_wall": dt, "algorithmic_GBps": b / (dt * 1e-3) / 1e9}
+    analysis["element_results"] = res_ms
+    separation["analysis"] = analysis
+    return separation
 
 
 def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, rank, world, begin, end):
@@ -427,9 +574,12 @@ def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, 
         dist.broadcast_object_list(u, src=0)
         fem.dist_init(rank, world, u[0])
     for it in range(steps + 1):
+        log(f"e2e: step {it} of {steps} (+1 warm-up)")
+        fem.synchronize()
+        torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         fem.reset(n_nodes)                      # frees the previous step's device buffers
         if world > 1:
@@ -454,6 +604,10 @@ def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, 
             times.append(dt)
             phases = {"reset_add_nodes_add_elements_s": t1 - t0, "symbolic_s": t2 - t1, "numeric_s": t3 - t2,
                       "csr_values_d2h_s": t4 - t3 - t_pin}
+    fem.synchronize()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()      # no rank may still be in a pass when the joined handles go
     fem.close()
     sec = float(np.mean(times))
     if dist is not None:

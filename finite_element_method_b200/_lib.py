@@ -72,10 +72,12 @@ SIGNATURES = {
     "femgpu_numeric_ms_history": (C.c_int32, [H, C.c_uint32, fp]),
     "femgpu_device_bytes": (C.c_int32, [H, u64p]),
     "femgpu_stream": (C.c_int32, [H, C.POINTER(C.c_void_p)]),
+    "femgpu_fp64_fma_peak": (C.c_int32, [H, dp]),
     "femgpu_dist_unique_id": (C.c_int32, [u8p]),
     "femgpu_dist_init": (C.c_int32, [H, C.c_int32, C.c_int32, u8p]),
     "femgpu_dist_set_ownership": (C.c_int32, [H, C.c_uint32, C.c_uint32]),
     "femgpu_dist_last_exchange_bytes": (C.c_int32, [H, u64p, u64p]),
+    "femgpu_dist_info": (C.c_int32, [H, i32p, u64p]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp")) or f == "Makefile"]
     srcs.append(os.path.join(HERE, "..", "include", "femgpu.h"))
     return any(os.path.getmtime(s) > t for s in srcs)
 

@@ -891,7 +891,7 @@ int32_t femgpu_synchronize(femgpu_t* h) {
   if (h->device < 0) return no_device(h);
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-  return 0;
+  return dist_check(h);
 }
 
 int32_t femgpu_assemble(femgpu_t* h, int64_t* n_rows, int64_t* nnz) {
@@ -916,7 +916,7 @@ int32_t femgpu_get_csr(femgpu_t* h, int64_t* row_ptr, int32_t* col_idx, double* 
     FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(values, h->values.p, size_t(h->nnz) * 8,
                                          cudaMemcpyDeviceToHost, h->stream));
   FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-  return 0;
+  return dist_check(h);
 }
 
 int32_t femgpu_get_csr_device(femgpu_t* h, const int64_t** row_ptr, const int32_t** col_idx,

@@ -272,6 +272,23 @@ struct DistState {
   DevBuf<uint32_t> recv_dst_block;    // per received block: index of the owner's block
   DevBuf<uint8_t> recv_full;          // per received block: 1 = 6x6
   uint64_t last_sent = 0, last_recv = 0;
+  std::vector<int64_t> count_matrix;  // [world][world] ghost blocks sender -> owner (the symbolic pass gathers it)
+  // Peer-to-peer exchange (dist.cu): every rank exposes one cudaMalloc'ed "window" through CUDA IPC,
+  //   [arrived[world] | consumed[world]] (64-byte slots) [ring slot 0] [ring slot 1], a slot = this rank's whole
+  // receive area (36 doubles per block, grouped by source rank). The pack kernel of a sender stores its ghost
+  // blocks straight into the owner's window over NVLink and then raises arrived[sender] there; the owner's apply
+  // kernel waits for that flag (in its own memory), adds the blocks and raises consumed[owner] in the sender's
+  // window, which frees the ring slot for the sender's pass after next. No NCCL call in a numeric pass.
+  static constexpr int kRing = 2;
+  bool p2p = false;
+  unsigned char* win = nullptr;
+  std::vector<unsigned char*> peer_win;  // peers' windows mapped into this process (nullptr: no traffic with that rank)
+  size_t win_slot_bytes = 0, win_bytes = 0;
+  std::vector<int64_t> peer_recv_off;    // first block of my run in peer r's receive area
+  uint64_t epoch = 0;                    // numeric passes since the plan was built (the same on every rank)
+  uint32_t* done_count = nullptr;        // device: per-peer "last CTA" counters of the pack / apply kernels
+  volatile uint32_t* h_err = nullptr;    // mapped pinned host word: a kernel timed out waiting for a peer
+  uint32_t* d_err = nullptr;
 };
 
 struct Handle {
@@ -472,6 +489,8 @@ int32_t run_element_results(Handle* h, int family, const double* d_u, double* d_
 void sol_release(Handle* h);                             // solve.cu
 void sol_invalidate(Handle* h);                          // solve.cu
 int32_t dist_numeric_exchange(Handle* h);                // dist.cu
+int32_t dist_setup_p2p(Handle* h);                       // dist.cu: collective, called when the exchange plan is final
+int32_t dist_check(Handle* h);                           // dist.cu: after a stream sync — did an exchange time out?
 void dist_destroy(Handle* h);                            // dist.cu
 int32_t dist_allgather_i64(Handle* h, const int64_t* send, int64_t* recv, size_t n);  // dist.cu
 int32_t dist_exchange_8(Handle* h, const void* send, const int64_t* send_offs, const int64_t* send_counts,

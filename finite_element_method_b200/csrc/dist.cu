@@ -6,12 +6,19 @@
 // not own ("ghost rows", contiguous in its local CSR because rows are ordered by node index).
 //   symbolic  the ghost node-pair block keys are sent to the owning ranks (ncclSend/ncclRecv), which
 //             merge them into their pattern so every remote contribution has a slot
-//   numeric   ghost blocks are packed (36 doubles each) and exchanged with one grouped
-//             ncclSend/ncclRecv per neighbour on the handle's stream; the owner adds the received
-//             partials one source rank at a time, in rank order -> deterministic
-// NCCL is loaded with dlopen at femgpu_dist_init() so the library has no link-time dependency on it
-// (and shares the copy a host framework such as PyTorch may already have loaded).
+//   numeric   ghost blocks are packed (36 doubles each) by a kernel that stores them STRAIGHT INTO THE
+//             OWNER'S HBM over NVLink (peer memory mapped with CUDA IPC) and then raises a flag there;
+//             the owner's apply kernel waits for the flag and adds the partials one source rank at a
+//             time, in rank order -> deterministic. No NCCL call, no host synchronisation and no
+//             matched send/recv pair inside a numeric pass: a rank that runs a pass its neighbour never
+//             runs gets FEMGPU_ERR_NCCL ("timed out") from the next synchronising call instead of a hung GPU.
+//             When the peers cannot be mapped (no P2P, one process driving several handles) the
+//             exchange falls back to one grouped ncclSend/ncclRecv per neighbour (FEMGPU_DIST_P2P=0 forces it).
+// NCCL (symbolic-pass collectives, fallback exchange) is loaded with dlopen at femgpu_dist_init() so the
+// library has no link-time dependency on it (and shares the copy a host framework such as PyTorch may
+// already have loaded).
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstring>
 
@@ -125,6 +132,110 @@ __global__ void apply_ghost_kernel(uint32_t n, const uint32_t* __restrict__ dst_
         values[base + 3 * int64_t(l03) + int64_t(i) * l35 + o35 + j] += p[6 * (i + 3) + j];
 }
 
+
+// ---- peer-to-peer exchange --------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// thread 0 of the CTA waits until *flag >= want (a flag in THIS device's memory, raised by a peer); gives up
+// after timeout_ns and records `code` in the mapped host word so that the next synchronising call can report it
+__device__ __forceinline__ void wait_flag(const uint64_t* flag, uint64_t want, uint64_t timeout_ns, uint32_t code,
+                                          uint32_t* err) {
+  if (threadIdx.x == 0 && ld_acquire_sys(flag) < want) {
+    const uint64_t t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < want) {
+      __nanosleep(200);
+      if (global_timer_ns() - t0 > timeout_ns) {
+        atomicCAS(err, 0u, code);
+        __threadfence_system();
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+// the last CTA of the launch to get here raises the peer's flag (after every CTA's peer accesses are fenced)
+__device__ __forceinline__ void signal_when_all_done(uint32_t* counter, uint64_t* peer_flag, uint64_t value) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(counter, 1u) == gridDim.x - 1u) {
+      *counter = 0u;  // ready for the next launch (stream-ordered after this one)
+      __threadfence_system();
+      st_release_sys(peer_flag, value);
+    }
+  }
+}
+
+// pack_ghost_kernel, writing into the owner's window: waits until the owner has consumed the pass that last
+// used this ring slot, stores the blocks over NVLink, raises arrived[me] = epoch in the owner's window
+__global__ void __launch_bounds__(128)
+pack_ghost_p2p_kernel(uint32_t n, uint32_t first_block, int key_bits, const uint64_t* __restrict__ blk_key,
+                      const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ node_len,
+                      const int64_t* __restrict__ node_base, const double* __restrict__ values,
+                      double* __restrict__ peer_out, const uint64_t* consumed_flag, uint64_t need_consumed,
+                      uint64_t* peer_arrived_flag, uint64_t epoch, uint32_t* counter, uint64_t timeout_ns,
+                      uint32_t err_code, uint32_t* err) {
+  if (need_consumed) wait_flag(consumed_flag, need_consumed, timeout_ns, err_code, err);
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    uint32_t blk = first_block + t;
+    uint32_t a = uint32_t(blk_key[blk] >> key_bits);
+    uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+    uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
+    bool full = o35 != 0xFFFFFFFFu;
+    int64_t base = node_base[a];
+    double2* o = reinterpret_cast<double2*>(peer_out + size_t(t) * 36);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 6; j += 2) {
+        const double* r0 = values + base + int64_t(i) * l03 + o03 + j;
+        const double* r3 = values + base + 3 * int64_t(l03) + int64_t(i) * l35 + o35 + j;
+        o[3 * i + j / 2] = make_double2((full || j < 3) ? r0[0] : 0.0, (full || j + 1 < 3) ? r0[1] : 0.0);
+        o[3 * (i + 3) + j / 2] = full ? make_double2(r3[0], r3[1]) : make_double2(0.0, 0.0);
+      }
+  }
+  signal_when_all_done(counter, peer_arrived_flag, epoch);
+}
+
+// apply_ghost_kernel on the ring slot the sender filled: waits for arrived[src] >= epoch (my memory), adds the
+// partial blocks, raises consumed[me] = epoch in the sender's window
+__global__ void __launch_bounds__(128)
+apply_ghost_p2p_kernel(uint32_t n, const uint32_t* __restrict__ dst_block, const uint8_t* __restrict__ src_full,
+                       int key_bits, const uint64_t* __restrict__ blk_key, const uint32_t* __restrict__ blk_off,
+                       const uint32_t* __restrict__ node_len, const int64_t* __restrict__ node_base,
+                       const double* in, double* __restrict__ values, const uint64_t* arrived_flag, uint64_t epoch,
+                       uint64_t* peer_consumed_flag, uint32_t* counter, uint64_t timeout_ns, uint32_t err_code,
+                       uint32_t* err) {
+  wait_flag(arrived_flag, epoch, timeout_ns, err_code, err);
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    uint32_t blk = dst_block[t];
+    uint32_t a = uint32_t(blk_key[blk] >> key_bits);
+    uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+    uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
+    bool full = src_full[t] != 0;  // the owner's block is full whenever any source's is
+    int64_t base = node_base[a];
+    const double* p = in + size_t(t) * 36;  // written by the peer: read through L2 (never a stale L1 line)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < (full ? 6 : 3); ++j) values[base + int64_t(i) * l03 + o03 + j] += __ldcg(p + 6 * i + j);
+    if (full)
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 6; ++j)
+          values[base + 3 * int64_t(l03) + int64_t(i) * l35 + o35 + j] += __ldcg(p + 6 * (i + 3) + j);
+  }
+  signal_when_all_done(counter, peer_consumed_flag, epoch);
+}
+
 }  // namespace
 
 // ---- helpers used by symbolic.cu ------------------------------------------------------------------
@@ -161,11 +272,185 @@ int32_t dist_exchange_8(Handle* h, const void* send, const int64_t* send_offs, c
   return 0;
 }
 
+constexpr size_t kFlagStride = 64;  // bytes between two flags of a window
+static inline uint64_t* win_arrived(unsigned char* win, int src) { return reinterpret_cast<uint64_t*>(win + kFlagStride * size_t(src)); }
+static inline uint64_t* win_consumed(unsigned char* win, int world, int dst) {
+  return reinterpret_cast<uint64_t*>(win + kFlagStride * size_t(world + dst));
+}
+static inline size_t win_flag_bytes(int world) { return (2 * kFlagStride * size_t(world) + 255) & ~size_t(255); }
+
+static uint64_t p2p_timeout_ns() {
+  static const uint64_t ns = [] {
+    const char* q = getenv("FEMGPU_P2P_TIMEOUT_MS");
+    const double ms = q ? atof(q) : 20000.0;
+    return uint64_t((ms > 1.0 ? ms : 1.0) * 1e6);
+  }();
+  return ns;
+}
+
+static int32_t p2p_numeric_exchange(Handle* h) {
+  DistState& D = h->dist;
+  const int W = D.world;
+  const uint64_t epoch = ++D.epoch;
+  const uint32_t slot = uint32_t((epoch - 1) % DistState::kRing);
+  const size_t flag_bytes = win_flag_bytes(W);
+  for (int r = 0; r < W; ++r) {  // my ghost blocks -> the owner's window
+    if (r == D.rank || D.send_blocks[r] == 0) continue;
+    const uint32_t n = uint32_t(D.send_blocks[r]);
+    double* out = reinterpret_cast<double*>(D.peer_win[r] + flag_bytes + size_t(slot) * D.win_slot_bytes) +
+                  size_t(D.peer_recv_off[r]) * 36;
+    const uint64_t need = epoch > uint64_t(DistState::kRing) ? epoch - DistState::kRing : 0;
+    pack_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(
+        n, uint32_t(D.send_first_block[r]), h->key_bits, h->blk_key.p, h->blk_off.p, h->node_len.p, h->node_base.p,
+        h->values.p, out, win_consumed(D.win, W, r), need, win_arrived(D.peer_win[r], D.rank), epoch,
+        D.done_count + r, p2p_timeout_ns(), 0x100u + uint32_t(r), D.d_err);
+    h->launches++;
+    D.last_sent += uint64_t(n) * 36 * 8;
+  }
+  for (int r = 0; r < W; ++r) {  // partials of the other ranks, in rank order (fixed order of the sums)
+    if (r == D.rank || D.recv_blocks[r] == 0) continue;
+    const uint32_t n = uint32_t(D.recv_blocks[r]);
+    const double* in = reinterpret_cast<const double*>(D.win + flag_bytes + size_t(slot) * D.win_slot_bytes) +
+                       size_t(D.recv_off[r]) * 36;
+    apply_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(
+        n, D.recv_dst_block.p + D.recv_off[r], D.recv_full.p + D.recv_off[r], h->key_bits, h->blk_key.p, h->blk_off.p,
+        h->node_len.p, h->node_base.p, in, h->values.p, win_arrived(D.win, r), epoch,
+        win_consumed(D.peer_win[r], W, D.rank), D.done_count + W + r, p2p_timeout_ns(), 0x200u + uint32_t(r), D.d_err);
+    h->launches++;
+    D.last_recv += uint64_t(n) * 36 * 8;
+  }
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+static void p2p_close_peers(Handle* h) {
+  for (auto& w : h->dist.peer_win) {
+    if (w) cudaIpcCloseMemHandle(w);
+    w = nullptr;
+  }
+  h->dist.p2p = false;
+}
+// An exported window may only be freed once no importer has it mapped any more: callers put a collective
+// between p2p_close_peers() on every rank and this (dist_setup_p2p), or have synchronised the ranks themselves
+// (femgpu_destroy: no rank may still be running numeric passes when a joined handle is destroyed).
+static void p2p_free_window(unsigned char* win, uint32_t* done_count) {
+  if (win) cudaFree(win);
+  if (done_count) cudaFree(done_count);
+}
+static void p2p_release(Handle* h) {
+  DistState& D = h->dist;
+  p2p_close_peers(h);
+  p2p_free_window(D.win, D.done_count);
+  D.win = nullptr;
+  D.done_count = nullptr;
+}
+
+// Collective (every rank calls it once the exchange plan of a symbolic pass is final): allocate and zero the
+// window, trade IPC handles over the NCCL communicator, map the neighbours. All-or-nothing across the ranks.
+int32_t dist_setup_p2p(Handle* h) {
+  DistState& D = h->dist;
+  const int W = D.world;
+  // every rank has been through the collectives of this symbolic pass, i.e. its stream is past the last numeric
+  // pass that touched the old windows: unmap the peers now, free the own old window after the next collective
+  p2p_close_peers(h);
+  unsigned char* old_win = D.win;
+  uint32_t* old_count = D.done_count;
+  D.win = nullptr;
+  D.done_count = nullptr;
+  D.epoch = 0;
+  if (!D.h_err) {
+    void* hp = nullptr;
+    FEMGPU_CUDA_CHECK(h, cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+    std::memset(hp, 0, 64);
+    D.h_err = static_cast<volatile uint32_t*>(hp);
+    FEMGPU_CUDA_CHECK(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&D.d_err), hp, 0));
+  }
+  *D.h_err = 0;
+  bool want = true;
+  if (const char* q = getenv("FEMGPU_DIST_P2P")) want = atoi(q) != 0;
+  const int64_t n_recv = D.recv_off[W];
+  D.win_slot_bytes = (size_t(n_recv) * 36 * 8 + 255) & ~size_t(255);
+  D.win_bytes = win_flag_bytes(W) + DistState::kRing * D.win_slot_bytes;
+  bool ok = want;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof mine);
+  if (ok) {
+    ok = cudaMalloc(reinterpret_cast<void**>(&D.win), D.win_bytes) == cudaSuccess &&
+         cudaMalloc(reinterpret_cast<void**>(&D.done_count), size_t(2 * W) * 4) == cudaSuccess &&
+         cudaMemsetAsync(D.win, 0, D.win_bytes, h->stream) == cudaSuccess &&
+         cudaMemsetAsync(D.done_count, 0, size_t(2 * W) * 4, h->stream) == cudaSuccess &&
+         cudaStreamSynchronize(h->stream) == cudaSuccess && cudaIpcGetMemHandle(&mine, D.win) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
+  // [ok, pid, handle (8 words)] from everyone; the gather is also the barrier "all windows are zeroed"
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::vector<int64_t> send(10, 0), all(size_t(10) * W, 0);
+  send[0] = ok ? 1 : 0;
+  send[1] = int64_t(getpid());
+  std::memcpy(&send[2], &mine, 64);
+  int32_t st = dist_allgather_i64(h, send.data(), all.data(), 10);
+  p2p_free_window(old_win, old_count);  // every importer unmapped it before entering the gather
+  if (st) return st;
+  for (int r = 0; r < W; ++r)
+    if (!all[size_t(10) * r] || (r != D.rank && all[size_t(10) * r + 1] == int64_t(getpid()))) ok = false;
+  D.peer_win.assign(W, nullptr);
+  D.peer_recv_off.assign(W, 0);
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      if (r == D.rank || (D.send_blocks[r] == 0 && D.recv_blocks[r] == 0)) continue;
+      cudaIpcMemHandle_t hd;
+      std::memcpy(&hd, &all[size_t(10) * r + 2], 64);
+      void* mapped = nullptr;
+      if (cudaIpcOpenMemHandle(&mapped, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      D.peer_win[r] = static_cast<unsigned char*>(mapped);
+      // my run inside rank r's receive area starts after the runs of the lower source ranks
+      int64_t off = 0;
+      for (int q = 0; q < D.rank; ++q)
+        if (q != r) off += D.count_matrix[size_t(q) * W + r];
+      D.peer_recv_off[r] = off;
+    }
+  }
+  // second round: did every rank map all its neighbours?
+  int64_t mine_ok = ok ? 1 : 0;
+  std::vector<int64_t> oks(W, 0);
+  if ((st = dist_allgather_i64(h, &mine_ok, oks.data(), 1))) return st;
+  for (int r = 0; r < W; ++r) ok = ok && oks[r] != 0;
+  if (!ok) {
+    p2p_release(h);  // NCCL send / recv exchange
+    if (getenv("FEMGPU_DIST_INFO")) fprintf(stderr, "[femgpu dist] rank %d: peer-to-peer windows unavailable, using ncclSend/ncclRecv\n", D.rank);
+    return 0;
+  }
+  D.p2p = true;
+  if (getenv("FEMGPU_DIST_INFO"))
+    fprintf(stderr, "[femgpu dist] rank %d/%d: p2p window %.2f MB (%lld blocks in, %lld out)\n", D.rank, W,
+            double(D.win_bytes) / 1e6, (long long)n_recv, (long long)D.send_off[W]);
+  return 0;
+}
+
+int32_t dist_check(Handle* h) {
+  DistState& D = h->dist;
+  if (!D.h_err) return 0;
+  const uint32_t code = *D.h_err;
+  if (!code) return 0;
+  *D.h_err = 0;
+  const int peer = int(code & 0xFFu);
+  return h->fail(FEMGPU_ERR_NCCL,
+                 std::string("ghost-row exchange timed out on rank ") + std::to_string(D.rank) + " in numeric pass " +
+                     std::to_string(D.epoch) + ((code & 0x200u) ? ": the blocks of rank " : ": the ring slot of rank ") +
+                     std::to_string(peer) + ((code & 0x200u) ? " never arrived" : " was never consumed") +
+                     " (did every rank run the same number of femgpu_numeric passes?)");
+}
+
 int32_t dist_numeric_exchange(Handle* h) {
   DistState& D = h->dist;
   if (!D.enabled) return 0;
   const int W = D.world;
   D.last_sent = D.last_recv = 0;
+  if (D.p2p) return p2p_numeric_exchange(h);
   // pack ghost blocks, one dense run per destination rank
   for (int r = 0; r < W; ++r) {
     if (r == D.rank || D.send_blocks[r] == 0) continue;
@@ -206,6 +491,10 @@ int32_t dist_numeric_exchange(Handle* h) {
 }
 
 void dist_destroy(Handle* h) {
+  p2p_release(h);
+  if (h->dist.h_err) cudaFreeHost(const_cast<uint32_t*>(h->dist.h_err));
+  h->dist.h_err = nullptr;
+  h->dist.d_err = nullptr;
   if (h->dist.comm && nccl()->CommDestroy) nccl()->CommDestroy((ncclComm_t)h->dist.comm);
   h->dist.comm = nullptr;
   h->dist.enabled = false;
@@ -276,6 +565,13 @@ int32_t femgpu_dist_last_exchange_bytes(femgpu_t* h, uint64_t* sent, uint64_t* r
   if (!h) return FEMGPU_ERR_USAGE;
   if (sent) *sent = h->dist.last_sent;
   if (received) *received = h->dist.last_recv;
+  return 0;
+}
+
+int32_t femgpu_dist_info(femgpu_t* h, int32_t* p2p, uint64_t* passes) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (p2p) *p2p = h->dist.p2p ? 1 : 0;
+  if (passes) *passes = h->dist.epoch;
   return 0;
 }
 

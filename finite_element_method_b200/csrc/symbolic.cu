@@ -964,6 +964,7 @@ static int32_t dist_collect_ghost_keys(Handle* h, const BlockBuild& bb, int64_t*
                             recv_counts.data())))
     return st;
   SYM_CHECK(cudaStreamSynchronize(s));
+  D.count_matrix = matrix;
   D.send_blocks = send_counts;
   D.recv_blocks = recv_counts;
   D.recv_off = recv_offs;
@@ -1011,7 +1012,7 @@ static int32_t dist_finalize_plan(Handle* h, const std::vector<int64_t>& ranges)
     SYM_CHECK(cudaMemcpy(&bad, h->d_flag.p + 4, 4, cudaMemcpyDeviceToHost));
     if (bad) return h->fail(FEMGPU_ERR_USAGE, "internal: a received ghost block has no slot in the owner's pattern");
   }
-  return 0;
+  return dist_setup_p2p(h);
 }
 
 int32_t run_symbolic(Handle* h) {

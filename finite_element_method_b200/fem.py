@@ -501,6 +501,12 @@ class FEM:
         self._check(self._L.femgpu_device_bytes(self._h, C.byref(v)))
         return int(v.value)
 
+    def fp64_fma_peak(self) -> float:
+        """measured FP64 FMA throughput of the device, TFLOP/s (micro-benchmark)"""
+        v = C.c_double()
+        self._check(self._L.femgpu_fp64_fma_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     def stream(self) -> int:
         v = C.c_void_p()
         self._check(self._L.femgpu_stream(self._h, C.byref(v)))
@@ -526,6 +532,13 @@ class FEM:
     def dist_last_exchange_bytes(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._L.femgpu_dist_last_exchange_bytes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def dist_info(self):
+        """(p2p, passes): 1 when ghost rows travel through peer windows over NVLink (0: ncclSend/ncclRecv), and the
+        numeric passes issued since the last symbolic pass"""
+        a, b = C.c_int32(), C.c_uint64()
+        self._check(self._L.femgpu_dist_info(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
     # ------------------------------------------------------------------ convenience

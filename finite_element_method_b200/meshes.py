@@ -167,11 +167,12 @@ def plate_grid(nx=2000, ny=2000, variant="flat", dx=1.0, dy=0.75, rows=None):
     return m
 
 
-def mixed_structure(nx=2000, ny=2000, rows=None):
+def mixed_structure(nx=2000, ny=2000, rows=None, variant="flat"):
     """Config 5 (M): the P node set; nx*ny plates; beams on every +x grid edge of rows j=0..ny-1
     (props as B, axis1=(0,0,1)); trusses on +y grid edges of even columns i=0,2,..,nx-2 (props as T).
-    2000x2000 -> 4M plates + 4M beams + 2M trusses = 10M elements. rows: see plate_grid."""
-    m = plate_grid(nx, ny, "flat", rows=rows)
+    2000x2000 -> 4M plates + 4M beams + 2M trusses = 10M elements. rows, variant: see plate_grid (in the
+    "x0" variant the grid lies in the x = 0 plane: beams run along +y with axis1 = (1, 0, 0), trusses along +z)."""
+    m = plate_grid(nx, ny, variant, rows=rows)
     w = nx + 1
     j0, j1 = (0, ny) if rows is None else (max(0, rows[0]), min(ny, rows[1]))
     jj, ii = np.meshgrid(np.arange(j0, j1), np.arange(nx), indexing="ij")
@@ -181,7 +182,7 @@ def mixed_structure(nx=2000, ny=2000, rows=None):
     m["b_n1"], m["b_n2"] = a, a + 1
     m["b_props"] = np.stack([np.full(nb, 2.1e11), np.full(nb, 0.3), 1e-2 * (1 + u), 8e-6 * (1 + u),
                              4e-6 * (1 + u), np.zeros(nb), np.full(nb, 1e-5), np.full(nb, 5.0 / 6.0)])
-    ax = np.zeros((3, nb)); ax[2] = 1.0
+    ax = np.zeros((3, nb)); ax[0 if variant == "x0" else 2] = 1.0
     m["b_axis"] = ax
     jj, ii = np.meshgrid(np.arange(j0, j1), np.arange(0, nx, 2), indexing="ij")
     t = (ii + w * jj).ravel().astype(np.uint32)
@@ -190,7 +191,7 @@ def mixed_structure(nx=2000, ny=2000, rows=None):
     ut = np.random.default_rng(20240601).random(ncol * ny)[j0 * ncol:j1 * ncol]
     m["t_n1"], m["t_n2"] = t, (t + w).astype(np.uint32)
     m["t_E"] = np.full(nt, 2.1e11); m["t_A"] = 1e-4 * (1 + ut)
-    m["name"] = f"mixed-{nx}x{ny}"
+    m["name"] = f"mixed-{nx}x{ny}" + ("" if variant == "flat" else f"-{variant}")
     return m
 
 

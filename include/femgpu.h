@@ -331,19 +331,31 @@ int32_t femgpu_device_bytes(const femgpu_t* h, uint64_t* bytes);
 /* the CUDA stream handle (cudaStream_t) work is issued on, for callers that time with events */
 int32_t femgpu_stream(femgpu_t* h, void** stream);
 
+/* measured FP64 FMA throughput of the handle's device in TFLOP/s (micro-benchmark, ~10 ms): the denominator of
+ * the FP64-pipe fraction bench.py reports next to the HBM roofline (no reference counterpart) */
+int32_t femgpu_fp64_fma_peak(femgpu_t* h, double* tflops);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------- */
 
 /* Joins `world` handles (one per process/GPU) into one assembly. `nccl_unique_id` is the 128-byte
  * ncclUniqueId created by rank 0 (femgpu_dist_unique_id) and broadcast by the host. Must be called
  * before femgpu_symbolic(). Rank g owns the contiguous node-index range given by
  * femgpu_dist_set_ownership(); each rank is given every node but only the elements whose
- * lowest-index node it owns. Contributions to rows owned by another rank are summed locally,
- * exchanged with ncclSend/ncclRecv and added by the owner in (source rank, slot) order. */
+ * lowest-index node it owns. femgpu_symbolic() is collective (NCCL all-gathers and a key exchange; it also maps
+ * the neighbours' receive windows with CUDA IPC). femgpu_numeric() is NOT a host-level collective: contributions
+ * to rows owned by another rank are summed locally, stored into the owner's HBM over NVLink by the sender's pack
+ * kernel and added by the owner in (source rank, slot) order once the sender's flag is up; every rank must run the
+ * same number of passes, and a rank that waits in vain for 20 s (FEMGPU_P2P_TIMEOUT_MS) reports FEMGPU_ERR_NCCL
+ * "timed out" from femgpu_synchronize / femgpu_get_csr instead of hanging. Without peer access the exchange is one
+ * grouped ncclSend/ncclRecv per neighbour. No rank may still be running passes when a joined handle is destroyed. */
 int32_t femgpu_dist_unique_id(uint8_t out[128]);
 int32_t femgpu_dist_init(femgpu_t* h, int32_t rank, int32_t world, const uint8_t nccl_unique_id[128]);
 int32_t femgpu_dist_set_ownership(femgpu_t* h, uint32_t node_index_begin, uint32_t node_index_end);
 /* interface traffic of the last numeric pass: bytes sent / received by this rank */
 int32_t femgpu_dist_last_exchange_bytes(femgpu_t* h, uint64_t* sent, uint64_t* received);
+/* how the last symbolic pass set the exchange up: *p2p = 1 peer windows over NVLink, 0 ncclSend/ncclRecv;
+ * *passes = numeric passes issued since (pointers may be NULL) */
+int32_t femgpu_dist_info(femgpu_t* h, int32_t* p2p, uint64_t* passes);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     which = sys.argv[1] if len(sys.argv) > 1 else "mixed"
-    if which == "mixed":
+    if which in ("mixed", "mismatch"):
         mesh, width = meshes.mixed_structure(40, 36), 41
     elif which == "plate":
         mesh, width = meshes.plate_grid(50, 31, "jitter"), 51
@@ -40,6 +40,30 @@ def main():
     fem.numeric(); fem.synchronize()
     assert np.array_equal(v1, fem.csr(values_only=True)), "dist re-assembly is not bit-identical"
     sent, recv = fem.dist_last_exchange_bytes()
+    p2p, passes = fem.dist_info()
+    assert passes == 2, passes
+    if which == "mismatch":
+        # A rank that runs passes its neighbours never run must get an error, not a hung GPU (the
+        # 8-GPU bench hung in an unmatched ncclSend). Rank 0 only sends; its ring of two slots is full after two
+        # unanswered passes and the third one times out (FEMGPU_P2P_TIMEOUT_MS is set short by the test).
+        from finite_element_method_b200 import FemError
+        msg = "ncclSend/ncclRecv exchange (no peer access): nothing to test"
+        if p2p and rank == 0 and world > 1:
+            for _ in range(3):
+                fem.numeric()
+            try:
+                fem.synchronize()
+                raise AssertionError("three unanswered passes did not time out")
+            except FemError as e:
+                assert e.code == -3 and "timed out" in str(e), (e.code, str(e))
+                msg = str(e)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            print(f"DIST_OK world={world} p2p={p2p} mismatch -> {msg}")
+        fem.close()
+        dist.destroy_process_group()
+        return
     # FEM::reset keeps the communicator: the same handle assembles the model again from scratch
     fem.reset(n)
     fem.dist_set_ownership(begin, end)
@@ -63,7 +87,9 @@ def main():
     if rank == 0:
         assert int(tot[0].item()) == meshes.n_elements(mesh)
         assert tot[1].item() == tot[2].item() and (world == 1 or tot[1].item() > 0)
-        print(f"DIST_OK world={world} mesh={mesh['name']} max_err={err:.2e} exchanged_bytes={int(tot[1].item())}")
+        print(f"DIST_OK world={world} p2p={p2p} mesh={mesh['name']} max_err={err:.2e} exchanged_bytes={int(tot[1].item())}")
+    torch.cuda.synchronize()
+    dist.barrier()
     fem.close(); ref.close()
     dist.destroy_process_group()
 
