@@ -357,5 +357,141 @@ inline double assemble(const Mesh& m, int n_threads, int repeats, int64_t* nnz_o
   return best;
 }
 
+// ---- sampled block rows at full size ---------------------------------------------------------------
+// For each node in `sample` (any order, no duplicates): every node-pair block (a, b) of its six rows, computed
+// from scratch — adjacency from a scan over all elements, element matrices by the functions above — and summed
+// in the reference's accumulation order for a model loaded family by family (plates, beams, trusses; insertion
+// order inside a family: methods_for_*_data_handle.rs add_value loops). This is how tests/ compare the GPU
+// matrix with the oracle at BASELINE.json's full sizes without holding 18 GB of element matrices.
+// Output, per sampled node i: blocks [blk_ptr[i], blk_ptr[i+1]) sorted by column node; blk_col[], blk_full[]
+// (1 = 6x6 beam/plate pair, 0 = 3x3 truss-only pair), blk_val[36 per block] row-major 6x6 (3x3 zero-padded).
+struct SampledRows {
+  std::vector<int64_t> blk_ptr;
+  std::vector<uint32_t> blk_col;
+  std::vector<uint8_t> blk_full;
+  std::vector<double> blk_val;
+};
+
+// faithful = true: element matrices by the operation-by-operation restatement (truss_element / beam_element /
+// plate_element of fem_oracle.hpp: dense (R^T k) R on Mat), i.e. the definition of parity; false: the fast ones above.
+inline int element_kg(const Mesh& m, int order, int64_t e, bool faithful, double* kg) {
+  if (!faithful) return order == 0 ? plate_kg(m, e, kg, false) : order == 1 ? beam_kg(m, e, kg) : truss_kg(m, e, kg);
+  double p[4][3];
+  if (order == 0) {
+    const int64_t n = m.n_plate;
+    for (int a = 0; a < 4; ++a) xyz(m, m.p_n[a * n + e], p[a]);
+    PlateOut<double> o;
+    const double* P = m.p_props;
+    int err = plate_element<double>(p[0], p[1], p[2], p[3], P[e], P[n + e], P[2 * n + e], P[3 * n + e], m.rel_tol,
+                                    m.abs_tol, o);
+    if (err) return err;
+    for (int i = 0; i < 24; ++i)
+      for (int j = 0; j < 24; ++j) kg[24 * i + j] = o.k_global.at(i, j);
+    return 0;
+  }
+  if (order == 1) {
+    const int64_t n = m.n_beam;
+    xyz(m, m.b_n1[e], p[0]);
+    xyz(m, m.b_n2[e], p[1]);
+    const double* P = m.b_props;
+    const double ax[3] = {m.b_axis[e], m.b_axis[n + e], m.b_axis[2 * n + e]};
+    BeamOut<double> o;
+    int err = beam_element<double>(p[0], p[1], P[e], P[n + e], P[2 * n + e], P[3 * n + e], P[4 * n + e], P[5 * n + e],
+                                   P[6 * n + e], P[7 * n + e], ax, m.rel_tol, m.abs_tol, o);
+    if (err) return err;
+    for (int i = 0; i < 12; ++i)
+      for (int j = 0; j < 12; ++j) kg[12 * i + j] = o.k_global.at(i, j);
+    return 0;
+  }
+  xyz(m, m.t_n1[e], p[0]);
+  xyz(m, m.t_n2[e], p[1]);
+  const bool has2 = m.t_A2 && !std::isnan(m.t_A2[e]);
+  TrussOut<double> o;
+  int err = truss_element<double>(p[0], p[1], m.t_E[e], m.t_A[e], has2, has2 ? m.t_A2[e] : 0.0, m.rel_tol, m.abs_tol, o);
+  if (err) return err;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) kg[6 * i + j] = o.k_global.at(i, j);
+  return 0;
+}
+
+inline int sample_rows(const Mesh& m, const uint32_t* sample, int64_t n_sample, int n_threads, bool faithful,
+                       SampledRows& out) {
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+  std::vector<int32_t> slot(size_t(m.n_nodes), -1);
+  for (int64_t i = 0; i < n_sample; ++i) slot[sample[i]] = int32_t(i);
+  struct C {
+    uint32_t col;
+    uint32_t order;  // family-major rank: plates 0, beams 1, trusses 2
+    int64_t elem;
+    int pair;
+  };
+  std::vector<std::vector<C>> lists;
+  lists.resize(static_cast<size_t>(n_sample));
+  auto push = [&](uint32_t order, int64_t e, const uint32_t* nd, int nn) {
+    for (int a = 0; a < nn; ++a) {
+      const int32_t s = slot[nd[a]];
+      if (s < 0) continue;
+      for (int b = 0; b < nn; ++b) lists[size_t(s)].push_back({nd[b], order, e, a * nn + b});
+    }
+  };
+  for (int64_t e = 0; e < m.n_plate; ++e) {
+    uint32_t nd[4] = {m.p_n[e], m.p_n[m.n_plate + e], m.p_n[2 * m.n_plate + e], m.p_n[3 * m.n_plate + e]};
+    push(0, e, nd, 4);
+  }
+  for (int64_t e = 0; e < m.n_beam; ++e) {
+    uint32_t nd[2] = {m.b_n1[e], m.b_n2[e]};
+    push(1, e, nd, 2);
+  }
+  for (int64_t e = 0; e < m.n_truss; ++e) {
+    uint32_t nd[2] = {m.t_n1[e], m.t_n2[e]};
+    push(2, e, nd, 2);
+  }
+  out.blk_ptr.assign(size_t(n_sample) + 1, 0);
+  for (int64_t i = 0; i < n_sample; ++i) {
+    auto& L = lists[size_t(i)];
+    std::stable_sort(L.begin(), L.end(), [](const C& a, const C& b) { return a.col < b.col; });  // keeps plates, beams, trusses / insertion order
+    int64_t nb = 0;
+    for (size_t k = 0; k < L.size(); ++k)
+      if (k == 0 || L[k].col != L[k - 1].col) ++nb;
+    out.blk_ptr[size_t(i) + 1] = out.blk_ptr[size_t(i)] + nb;
+  }
+  const int64_t total = out.blk_ptr[size_t(n_sample)];
+  out.blk_col.assign(size_t(total), 0);
+  out.blk_full.assign(size_t(total), 0);
+  out.blk_val.assign(size_t(total) * 36, 0.0);
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t i = 0; i < n_sample; ++i) {
+    const auto& L = lists[size_t(i)];
+    int64_t blk = out.blk_ptr[size_t(i)] - 1;
+    std::vector<double> kg(576);
+    for (size_t k = 0; k < L.size(); ++k) {
+      if (k == 0 || L[k].col != L[k - 1].col) {
+        ++blk;
+        out.blk_col[size_t(blk)] = L[k].col;
+      }
+      double* acc = &out.blk_val[size_t(blk) * 36];
+      const C& c = L[k];
+      if (element_kg(m, int(c.order), c.elem, faithful, kg.data())) bad = 1;
+      if (c.order == 0) {
+        const int la = c.pair / 4, lb = c.pair % 4;
+        for (int r = 0; r < 6; ++r)
+          for (int q = 0; q < 6; ++q) acc[6 * r + q] += kg[size_t((6 * la + r) * 24 + 6 * lb + q)];
+        out.blk_full[size_t(blk)] = 1;
+      } else if (c.order == 1) {
+        const int la = c.pair / 2, lb = c.pair % 2;
+        for (int r = 0; r < 6; ++r)
+          for (int q = 0; q < 6; ++q) acc[6 * r + q] += kg[size_t((6 * la + r) * 12 + 6 * lb + q)];
+        out.blk_full[size_t(blk)] = 1;
+      } else {
+        const int la = c.pair / 2, lb = c.pair % 2;
+        for (int r = 0; r < 3; ++r)
+          for (int q = 0; q < 3; ++q) acc[6 * r + q] += kg[size_t((3 * la + r) * 6 + 3 * lb + q)];
+      }
+    }
+  }
+  return bad ? -1 : 0;
+}
+
 }  // namespace fast
 }  // namespace oracle

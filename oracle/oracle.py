@@ -243,6 +243,29 @@ def fast_assemble(mesh, n_threads=0, repeats=1, want_coo=False):
     return out
 
 
+def sample_rows(mesh, nodes, n_threads=0, faithful=True):
+    """Block rows of the sampled nodes, computed from scratch at any mesh size (fem_oracle_fast.hpp sample_rows):
+    returns (blk_ptr [n+1], blk_col, blk_full, blk_val [nblk, 6, 6]); blocks of a node sorted by column node,
+    contributions summed plates -> beams -> trusses in insertion order (the reference's add_value sequence for a
+    model loaded family by family). faithful=True: element matrices by the operation-by-operation restatement
+    (dense (R^T k) R on Mat, fem_oracle.hpp); False: the multi-core baseline's block-wise ones."""
+    args, keep = _mesh_args(mesh)
+    nodes = np.ascontiguousarray(nodes, np.uint32)
+    assert len(np.unique(nodes)) == len(nodes)
+    ptr = np.zeros(len(nodes) + 1, np.int64)
+    f = lib().oracle_sample_rows
+    f.restype = C.c_int64
+    u8p = C.POINTER(C.c_uint8)
+    nb = f(*args, C.c_int(n_threads), C.c_int(int(faithful)), C.c_int64(len(nodes)), nodes.ctypes.data_as(_u32p), ptr.ctypes.data_as(_i64p),
+           C.cast(None, _u32p), C.cast(None, u8p), C.cast(None, _dp))
+    if nb < 0:
+        raise OracleError(-1)
+    col = np.zeros(nb, np.uint32); full = np.zeros(nb, np.uint8); val = np.zeros((nb, 6, 6))
+    f(*args, C.c_int(n_threads), C.c_int(int(faithful)), C.c_int64(len(nodes)), nodes.ctypes.data_as(_u32p), ptr.ctypes.data_as(_i64p),
+      col.ctypes.data_as(_u32p), full.ctypes.data_as(u8p), val.ctypes.data_as(_dp))
+    return ptr, col, full, val
+
+
 def element_results(mesh, u):
     """extract_elements_analysis_result (methods_for_element_analysis.rs:27-58) of a mesh dict for the global
     displacement vector u (6 per node): (truss [nt], beam [nb, 10], plate [np, 8]) in the reference's

@@ -310,6 +310,34 @@ double oracle_fast_assemble(int64_t n_nodes, const double* x, const double* y, c
   return fast::assemble(mesh, n_threads, repeats, nnz_out, checksum_out, coo_rows, coo_cols, coo_vals);
 }
 
+
+// Sampled block rows of the global matrix at any mesh size (fem_oracle_fast.hpp sample_rows). Two calls: with
+// blk_col == nullptr it returns the number of blocks (and fills blk_ptr [n_sample + 1]); the second call fills
+// blk_col / blk_full / blk_val (36 per block). Returns < 0 when an element is invalid.
+int64_t oracle_sample_rows(int64_t n_nodes, const double* x, const double* y, const double* z,
+                           int64_t n_truss, const uint32_t* t_n1, const uint32_t* t_n2,
+                           const double* t_E, const double* t_A, const double* t_A2,
+                           int64_t n_beam, const uint32_t* b_n1, const uint32_t* b_n2,
+                           const double* b_props, const double* b_axis, int64_t n_plate,
+                           const uint32_t* p_n, const double* p_props, double rel_tol, double abs_tol,
+                           int n_threads, int faithful, int64_t n_sample, const uint32_t* sample, int64_t* blk_ptr,
+                           uint32_t* blk_col, uint8_t* blk_full, double* blk_val) {
+  fast::Mesh mesh{n_nodes, x, y, z, n_truss, t_n1, t_n2, t_E, t_A, t_A2, n_beam, b_n1, b_n2,
+                  b_props, b_axis, n_plate, p_n, p_props, rel_tol, abs_tol};
+  static thread_local fast::SampledRows cache;  // the second call returns what the first one computed
+  if (!blk_col) {
+    if (fast::sample_rows(mesh, sample, n_sample, n_threads, faithful != 0, cache)) return -1;
+    std::memcpy(blk_ptr, cache.blk_ptr.data(), cache.blk_ptr.size() * sizeof(int64_t));
+    return int64_t(cache.blk_col.size());
+  }
+  std::memcpy(blk_col, cache.blk_col.data(), cache.blk_col.size() * sizeof(uint32_t));
+  std::memcpy(blk_full, cache.blk_full.data(), cache.blk_full.size());
+  std::memcpy(blk_val, cache.blk_val.data(), cache.blk_val.size() * sizeof(double));
+  const int64_t n = int64_t(cache.blk_col.size());
+  cache = fast::SampledRows();
+  return n;
+}
+
 // single-thread faithful timing on the same arrays: seconds for `add_*` of everything
 double oracle_faithful_time(int64_t n_nodes, const double* x, const double* y, const double* z,
                             int64_t n_truss, const uint32_t* t_n1, const uint32_t* t_n2,

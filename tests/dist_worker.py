@@ -18,6 +18,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     which = sys.argv[1] if len(sys.argv) > 1 else "mixed"
+    if which == "fullsize":
+        return fullsize(rank, world, local, dist, torch)
     if which in ("mixed", "mismatch"):
         mesh, width = meshes.mixed_structure(40, 36), 41
     elif which == "plate":
@@ -91,6 +93,43 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     fem.close(); ref.close()
+    dist.destroy_process_group()
+
+
+def fullsize(rank, world, local, dist, torch):
+    """BASELINE.json config 5 as the north star states it: ONE 10M-element mixed mesh partitioned into `world`
+    contiguous row strips. Every rank compares sampled rows of the strip it owns — among them its first grid line
+    (which received the lower neighbour's ghost contributions) and its last one — with the oracle."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from finite_element_method_b200 import FEM, meshes
+    from fullsize_common import compare_sampled_rows, sample_nodes
+    nx = ny = 2000
+    w = nx + 1
+    mesh = meshes.mixed_structure(nx, ny)
+    n = len(mesh["x"])
+    begin, end = meshes.partition_rows(mesh, world, w)[rank]
+    part = meshes.mixed_structure(nx, ny, rows=(begin // w, end // w))
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=local)
+    uid = [FEM.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    fem.dist_init(rank, world, uid[0])
+    fem.dist_set_ownership(begin, end)
+    fem.load_mesh(part)
+    fem.assemble()
+    j0, j1 = begin // w, end // w
+    nodes = sample_nodes(n, w, lo=begin, hi=end, n_random=max(2000, 10_000 // world), lines=(j0, j0 + 1, j1 - 1))
+    rep = compare_sampled_rows(fem, mesh, nodes, rtol=1e-12, faithful=True, device=f"cuda:{local}")
+    assert rep["n_fail"] == 0 and rep["max_block_rel"] <= 1e-12, (rank, rep)
+    tot = torch.tensor([float(rep["nodes"]), float(rep["entries"]), rep["max_block_rel"]], device="cuda", dtype=torch.float64)
+    mx = tot.clone()
+    dist.all_reduce(tot)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST_OK world={world} p2p={fem.dist_info()[0]} mesh={mesh['name']} strips: sampled nodes={int(tot[0].item())} "
+              f"entries={int(tot[1].item())} max_block_rel={mx[2].item():.2e}")
+    fem.close()
     dist.destroy_process_group()
 
 

@@ -46,3 +46,11 @@ def test_unmatched_passes_time_out_instead_of_hanging():
         pytest.skip("needs 2 GPUs")
     out = _run("mismatch", 2, {"FEMGPU_P2P_TIMEOUT_MS": "300"}, port=29513)
     assert "timed out" in out or "nothing to test" in out
+
+
+def test_full_size_mixed_mesh_in_strips_matches_oracle():
+    """config 5: the 10M-element mesh split over every GPU of the box (>= 2), sampled rows vs the oracle"""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _run("fullsize", min(8, _n_gpus()), port=29514)
+    assert "sampled nodes" in out

@@ -47,3 +47,32 @@ def test_partition_owns_every_element_once():
         assert parts[0][0] == 0 and parts[-1][1] == len(m["x"])
         tot = sum(meshes.n_elements(meshes.local_part(m, b, e)) for b, e in parts)
         assert tot == meshes.n_elements(m)
+
+
+@pytest.mark.parametrize("make", [lambda: meshes.mixed_structure(9, 7), lambda: meshes.truss_cube(4),
+                                  lambda: meshes.plate_grid(6, 5, "x0")])
+def test_sampled_rows_harness_on_cpu(make):
+    """The full-size GPU parity tests compare sampled block rows (tests/fullsize_common.py). Here the same harness
+    runs on CPU tensors: the fast baseline's structural CSR against the faithful sampled rows, and a corrupted
+    copy must be caught."""
+    import sys, os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fullsize_common import compare_sampled_rows, sample_nodes
+    mesh = make()
+    n = len(mesh["x"])
+    out = O.fast_assemble(mesh, n_threads=2, want_coo=True)
+    r, c, v = out["coo"]                       # structural layout order = CSR order
+    assert np.all(np.diff(r) >= 0)
+    rp = np.zeros(6 * n + 1, np.int64)
+    np.add.at(rp, r + 1, 1)
+    rp = np.cumsum(rp)
+    csr = (torch.as_tensor(rp), torch.as_tensor(c.astype(np.int32)), torch.as_tensor(v.copy()))
+    nodes = sample_nodes(n, n_random=50)
+    rep = compare_sampled_rows(None, mesh, nodes, device="cpu", csr=csr)
+    assert rep["n_fail"] == 0 and rep["entries"] > 0 and rep["max_block_rel"] < 1e-13, rep
+    bad = v.copy()
+    k = int(rp[6 * int(nodes[len(nodes) // 2])])
+    bad[k] = bad[k] * (1 + 1e-9) + 1e-3
+    rep = compare_sampled_rows(None, mesh, nodes, device="cpu", csr=(csr[0], csr[1], torch.as_tensor(bad)))
+    assert rep["n_fail"] == 1, rep
