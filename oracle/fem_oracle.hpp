@@ -30,6 +30,10 @@
 //       - 2x2 inverse / determinant   : closed form
 //     Beam and plate element matrices are therefore "parity unpinned"
 //     (the reference has no beam/plate test); analytic checks in tests/ back them.
+//     `Variants` below switches the two restatement choices that could matter (the anti-parallel
+//     branch of the Rodrigues rotation, the 2x2 inverse); tests/test_oracle_variants.py shows which
+//     results do not depend on them (trusses always; plates and beams unless a normal / member is
+//     EXACTLY anti-parallel to its target axis) and quantifies the ones that do.
 //
 // Build: g++ -O2 -ffp-contract=off (Rust never contracts a*b+c into an FMA).
 #pragma once
@@ -42,6 +46,30 @@
 #include <vector>
 
 namespace oracle {
+
+// --------------------------------------------------------------------------
+// Variants of the two places where the un-vendored extended_matrix crate could plausibly differ from the
+// restatement below (tests/test_oracle_variants.py runs every family through all of them to show which
+// results depend on the unknown and which do not). Test-only switches; the defaults are the restatement.
+//   antiparallel: what rotation_matrix_to_align_with_vector(a, b) returns when a x b == 0 and a.b < 0
+//     0  the same guard as the parallel case: zero axis, c = -1  ->  Q = -I          (default)
+//     1  rotation by pi about the y axis   diag(-1, 1, -1)
+//     2  rotation by pi about the z axis   diag(-1, -1, 1)
+//     3  identity (the guard returns before the formula)
+//   inverse2: SquareMatrix::inverse / determinant of the 2x2 Jacobian (quadrilateral...rs:448-503)
+//     0  closed form (adjugate / determinant)                                        (default)
+//     1  LU (Doolittle, no pivoting): forward / back substitution per column, det = u11 u22
+//     2  Gauss-Jordan with partial pivoting
+// --------------------------------------------------------------------------
+struct Variants {
+  int antiparallel = 0;
+  int inverse2 = 0;
+  long antiparallel_hits = 0;  // how often the anti-parallel branch was taken since the last reset
+};
+inline Variants& variants() {
+  static Variants v;
+  return v;
+}
 
 // --------------------------------------------------------------------------
 // math_functions.rs
@@ -130,6 +158,20 @@ inline void rotation_matrix_to_align_with_vector(const Vec3<V>& a, const Vec3<V>
     x = axis.c[0] / n;
     y = axis.c[1] / n;
     z = axis.c[2] / n;
+  }
+  if (n == V(0.0f) && cosv < V(0.0f)) {  // anti-parallel: the one input class whose result is not pinned
+#pragma omp atomic
+    variants().antiparallel_hits++;
+    const int mode = variants().antiparallel;
+    if (mode != 0) {
+      const V one = V(1.0f), m1 = V(-1.0f), z0 = V(0.0f);
+      const V d[3][3] = {{m1, one, m1}, {m1, m1, one}, {one, one, one}};
+      for (int i = 0; i < 9; ++i) q[i] = z0;
+      q[0] = d[mode - 1][0];
+      q[4] = d[mode - 1][1];
+      q[8] = d[mode - 1][2];
+      return;
+    }
   }
   V c = compare_with_tolerance(std::cos(angle), abs_tol);
   V s = compare_with_tolerance(std::sin(angle), abs_tol);
@@ -732,10 +774,40 @@ inline void quad_jacobian_at_r_s(const PlateGeom<V>& g, V r, V s, V j[4]) {
 }
 // :477-503 (closed-form 2x2; extended_matrix's determinant(rel_tol) assumed equivalent)
 template <typename V>
-inline V quad_determinant_of_jacobian(const V j[4]) { return j[0] * j[3] - j[1] * j[2]; }
-// :448-475 (closed-form 2x2 inverse)
+inline V quad_determinant_of_jacobian(const V j[4]) {
+  const int mode = variants().inverse2;
+  if (mode == 1) {  // LU without pivoting: det = u11 * u22
+    const V l21 = j[2] / j[0];
+    return j[0] * (j[3] - l21 * j[1]);
+  }
+  if (mode == 2) {  // partial pivoting: a row swap flips the sign
+    const bool swap = std::fabs(j[2]) > std::fabs(j[0]);
+    const V a = swap ? j[2] : j[0], b = swap ? j[3] : j[1], c = swap ? j[0] : j[2], d = swap ? j[1] : j[3];
+    const V det = a * (d - (c / a) * b);
+    return swap ? V(-1.0f) * det : det;
+  }
+  return j[0] * j[3] - j[1] * j[2];
+}
+// :448-475 (closed-form 2x2 inverse; variants: see the top of the file)
 template <typename V>
 inline void quad_inverse_jacobian(const V j[4], V inv[4]) {
+  const int mode = variants().inverse2;
+  if (mode == 1 || mode == 2) {
+    // solve J x = e_k for k = 0, 1 by elimination (mode 2 picks the larger first-column entry as pivot)
+    const bool swap = mode == 2 && std::fabs(j[2]) > std::fabs(j[0]);
+    const V a = swap ? j[2] : j[0], b = swap ? j[3] : j[1], c = swap ? j[0] : j[2], d = swap ? j[1] : j[3];
+    const V l = c / a, u22 = d - l * b;
+    for (int k = 0; k < 2; ++k) {
+      V r0 = (k == 0) ? V(1.0f) : V(0.0f), r1 = (k == 1) ? V(1.0f) : V(0.0f);
+      if (swap) std::swap(r0, r1);
+      const V y1 = r1 - l * r0;
+      const V x1 = y1 / u22;
+      const V x0 = (r0 - b * x1) / a;
+      inv[k] = x0;
+      inv[2 + k] = x1;
+    }
+    return;
+  }
   V det = quad_determinant_of_jacobian(j);
   inv[0] = j[3] / det;
   inv[1] = V(-1.0f) * j[1] / det;

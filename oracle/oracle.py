@@ -52,6 +52,15 @@ def lib():
     return _lib
 
 
+def set_variants(antiparallel=-1, inverse2=-1, reset_hits=False):
+    """Test-only switches of the restatement (fem_oracle.hpp `Variants`): antiparallel 0 zero axis (Q = -I, default) /
+    1 pi about y / 2 pi about z / 3 identity; inverse2 0 closed form (default) / 1 LU / 2 pivoted elimination.
+    -1 leaves a switch alone. Returns how often the anti-parallel branch has been taken so far."""
+    f = lib().oracle_set_variants
+    f.restype = C.c_long
+    return int(f(C.c_int(antiparallel), C.c_int(inverse2), C.c_int(int(reset_hits))))
+
+
 def _d(a):
     a = np.ascontiguousarray(a, dtype=np.float64)
     return a, a.ctypes.data_as(_dp)

@@ -31,6 +31,16 @@ const char* oracle_error_text(int code) {
   }
 }
 
+// test-only switches of the restatement (fem_oracle.hpp Variants); returns the anti-parallel branch hits so far
+long oracle_set_variants(int antiparallel, int inverse2, int reset_hits) {
+  Variants& v = variants();
+  if (antiparallel >= 0) v.antiparallel = antiparallel;
+  if (inverse2 >= 0) v.inverse2 = inverse2;
+  long hits = v.antiparallel_hits;
+  if (reset_hits) v.antiparallel_hits = 0;
+  return hits;
+}
+
 // ---------------------------------------------------------------- element level
 int oracle_truss_f64(const double* p1, const double* p2, double E, double A, double A2,
                      double rel_tol, double abs_tol, double* q, double* k_local, double* k_global) {
