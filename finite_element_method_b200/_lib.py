@@ -70,6 +70,7 @@ SIGNATURES = {
     "femgpu_launch_count": (C.c_int32, [H, C.c_int32, u64p]),
     "femgpu_last_numeric_ms": (C.c_int32, [H, fp]),
     "femgpu_numeric_ms_history": (C.c_int32, [H, C.c_uint32, fp]),
+    "femgpu_numeric_kernel_ms": (C.c_int32, [H, C.c_uint32, fp, i32p]),
     "femgpu_device_bytes": (C.c_int32, [H, u64p]),
     "femgpu_stream": (C.c_int32, [H, C.POINTER(C.c_void_p)]),
     "femgpu_fp64_fma_peak": (C.c_int32, [H, dp]),

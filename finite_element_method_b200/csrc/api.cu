@@ -623,8 +623,12 @@ int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t n
   h->abs_tol = abs_tol;
   h->nodes_number = nodes_number;
   h->device = device;
+  // the handle's stream gets the highest priority: when the element-record kernels of the next slab range share the
+  // device with the assembly kernel (femgpu_numeric), freed SM resources go to the assembly CTAs first
+  int prio_least = 0, prio_greatest = 0;
   if (cudaSetDevice(device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
     g_create_status.code = FEMGPU_ERR_CUDA;
     g_create_status.text = "could not create a CUDA stream";
     delete h;
@@ -703,6 +707,15 @@ void femgpu_destroy(femgpu_t* h) {
     if (h->join_ev[b]) cudaEventDestroy(h->join_ev[b]);
   }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
+  for (auto& e : h->range_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& q : h->range_t0)
+    for (auto& e : q)
+      if (e) cudaEventDestroy(e);
+  for (auto& q : h->range_t1)
+    for (auto& e : q)
+      if (e) cudaEventDestroy(e);
   for (int b = 0; b < 2; ++b) {
     if (h->pin_ev[b]) cudaEventDestroy(h->pin_ev[b]);
     if (h->pin_buf[b]) cudaFreeHost(h->pin_buf[b]);
@@ -872,12 +885,50 @@ int32_t femgpu_numeric(femgpu_t* h) {
   if (h->device < 0) return no_device(h);
   if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "femgpu_numeric before femgpu_symbolic");
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
-  cudaEvent_t* ev = h->ev[h->n_numeric % Handle::kEvRing];
+  const uint32_t slot = uint32_t(h->n_numeric % Handle::kEvRing);
+  cudaEvent_t* ev = h->ev[slot];
   FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[0], h->stream));
-  int32_t st = run_prep(h, /*validate_only=*/false);
-  if (st) return st;
-  FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
-  if ((st = run_assembly(h))) return st;
+  int32_t st = 0;
+  const int R = h->n_ranges;
+  h->range_count[slot] = 0;
+  if (R <= 1) {
+    if ((st = run_prep(h, /*validate_only=*/false))) return st;
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
+    if ((st = run_assembly(h, 0, h->n_slabs))) return st;
+  } else {
+    // Software pipeline over slab ranges: the element records range r + 1 needs are computed on a low-priority stream
+    // while the (high-priority) assembly kernel works on range r; only range 0's records are on the critical path.
+    if (!h->prep_stream) {
+      int least = 0, greatest = 0;
+      FEMGPU_CUDA_CHECK(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      FEMGPU_CUDA_CHECK(h, cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, least));
+      if (!h->fork_ev) FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+      for (auto& e : h->range_ev) FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& q : h->range_t0)
+        for (auto& e : q) FEMGPU_CUDA_CHECK(h, cudaEventCreate(&e));
+      for (auto& q : h->range_t1)
+        for (auto& e : q) FEMGPU_CUDA_CHECK(h, cudaEventCreate(&e));
+    }
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->fork_ev, h->stream));  // after the previous pass: its kernels read the records
+    FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->prep_stream, h->fork_ev, 0));
+    auto prep = [&](int r) -> int32_t {
+      int32_t e = run_prep_range(h, r, h->prep_stream);
+      if (e) return e;
+      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_ev[r], h->prep_stream));
+      return 0;
+    };
+    if ((st = prep(0))) return st;
+    for (int r = 0; r < R; ++r) {
+      if (r + 1 < R && (st = prep(r + 1))) return st;
+      FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->range_ev[r], 0));
+      if (r == 0) FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
+      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t0[slot][r], h->stream));
+      if ((st = run_assembly(h, r ? h->range_slab_end[r - 1] : 0u, h->range_slab_end[r]))) return st;
+      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t1[slot][r], h->stream));
+    }
+    h->range_count[slot] = R;
+  }
+  if ((st = run_assembly_unstaged(h))) return st;
   FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[2], h->stream));
   if (h->dist.enabled && (st = dist_numeric_exchange(h))) return st;
   FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[3], h->stream));
@@ -1013,6 +1064,31 @@ int32_t femgpu_numeric_ms_history(femgpu_t* h, uint32_t passes_back, float out[4
   FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[1], ev[0], ev[1]));
   FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[2], ev[1], ev[2]));
   FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&out[3], ev[2], ev[3]));
+  return 0;
+}
+
+int32_t femgpu_numeric_kernel_ms(femgpu_t* h, uint32_t passes_back, float* assemble_ms, int32_t* launches) {
+  if (!h || !assemble_ms) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (passes_back >= Handle::kEvRing || passes_back >= h->n_numeric)
+    return h->fail(FEMGPU_ERR_USAGE, "no such numeric pass in the timing history");
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const uint32_t slot = uint32_t((h->n_numeric - 1 - passes_back) % Handle::kEvRing);
+  cudaEvent_t* ev = h->ev[slot];
+  FEMGPU_CUDA_CHECK(h, cudaEventSynchronize(ev[3]));
+  const int R = h->range_count[slot];
+  float total = 0.f;
+  if (R == 0) {
+    FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&total, ev[1], ev[2]));
+  } else {
+    for (int r = 0; r < R; ++r) {
+      float ms = 0.f;
+      FEMGPU_CUDA_CHECK(h, cudaEventElapsedTime(&ms, h->range_t0[slot][r], h->range_t1[slot][r]));
+      total += ms;
+    }
+  }
+  *assemble_ms = total;
+  if (launches) *launches = R ? R : 1;
   return 0;
 }
 

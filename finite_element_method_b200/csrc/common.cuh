@@ -418,6 +418,20 @@ struct Handle {
     DevBuf<double> res[kFamilies];    // element results
   } sol;
 
+  // Range plan of the numeric pass (symbolic.cu build_range_plan): the slabs are cut into n_ranges consecutive
+  // ranges, and every family's elements are listed by the first range that needs their record (prep_order, with
+  // range_elem_end[f][r] = end of range r's share of the list). The record kernels of range r + 1 run on a low-priority
+  // stream while the assembly kernel works on range r, so only the first range's records sit on the critical path.
+  static constexpr int kMaxRanges = 16;
+  int n_ranges = 1;
+  uint32_t range_slab_end[kMaxRanges] = {};
+  uint32_t range_elem_end[kFamilies][kMaxRanges] = {};
+  DevBuf<uint32_t> prep_order[kFamilies];
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t range_ev[kMaxRanges] = {};
+  cudaEvent_t range_t0[kEvRing][kMaxRanges] = {}, range_t1[kEvRing][kMaxRanges] = {};  // per-range assembly launch times
+  int range_count[kEvRing] = {};  // ranges of the pass in that ring slot (0: one launch between ev[1] and ev[2])
+
   // side streams of the numeric pass: the element-record kernels of the three families are independent and
   // each is bound by gather latency at a third of the SM's warp slots, so they run side by side (prep.cu)
   cudaStream_t side_stream[2] = {nullptr, nullptr};
@@ -446,6 +460,7 @@ struct Handle {
     tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(items_c); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
     tie(col_idx); tie(values); tie(scratch); tie(d_flag);
+    for (auto& o : prep_order) tie(o);
     tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_dst_block); tie(dist.recv_full);
     tie(dist.remote_keys); tie(dist_scratch.i64);
     tie(sep.d_constrained); tie(sep.d_disp); tie(sep.d_force); tie(sep.rhs); tie(sep.cls_pos); tie(sep.aa_idx);
@@ -471,9 +486,11 @@ struct Handle {
 // ---- kernels' host entry points (one per translation unit) -------------------------------------
 int32_t upload_pending(Handle* h);                       // api.cu
 int32_t run_prep(Handle* h, bool validate_only);         // prep.cu
+int32_t run_prep_range(Handle* h, int range, cudaStream_t st);  // prep.cu: records of the elements first needed by `range`
 int32_t first_error(Handle* h, int* family, size_t* index, int* code);  // prep.cu
 int32_t run_symbolic(Handle* h);                         // symbolic.cu
-int32_t run_assembly(Handle* h);                         // numeric.cu
+int32_t run_assembly(Handle* h, uint32_t slab_begin, uint32_t slab_end);  // numeric.cu: staged slabs of [begin, end)
+int32_t run_assembly_unstaged(Handle* h);                // numeric.cu: the oversized slabs
 int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);   // numeric.cu
 int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
 int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host);   // symbolic.cu

@@ -39,6 +39,7 @@ struct AsmArgs {
   const double* beam_rec;
   const double* plate_rec;        // geometry (16) + material (4)
   double* values;
+  uint32_t slab_begin;  // this launch works on the slabs [slab_begin, n_slabs)
   uint32_t n_slabs;
   // shared-memory regions of the staged kernel, bytes: [image][plate forms][raw plates][stage x2]
   uint32_t smem_img, smem_form, smem_rawp, smem_stage;
@@ -577,7 +578,7 @@ assemble_kernel(const AsmArgs A) {
   unsigned char* dbuf0 = stage0 + 2 * A.smem_stage;  // three rotating descriptor blocks
   const uint32_t rawp_s = smem_u32(rawp), stage0_s = smem_u32(stage0), dbuf0_s = smem_u32(dbuf0);
 
-  uint32_t k = blockIdx.x;
+  uint32_t k = A.slab_begin + blockIdx.x;
   if (k >= A.n_slabs) return;
   const uint32_t mbar_s = dbuf0_s + 3 * desc_bytes<kT>();
   PlatePair* pairs = reinterpret_cast<PlatePair*>(dbuf0 + 3 * desc_bytes<kT>() + 16);
@@ -801,9 +802,7 @@ __global__ void element_matrix_kernel(int family, uint32_t e, const double* trus
 
 }  // namespace
 
-int32_t run_assembly(Handle* h) {
-  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
-  if (h->n_slabs == 0) return 0;
+static AsmArgs asm_args(Handle* h) {
   AsmArgs A;
   A.slabs = h->slabs.p;
   A.meta = h->blk_meta.p;
@@ -816,12 +815,31 @@ int32_t run_assembly(Handle* h) {
   A.beam_rec = h->fd[FEMGPU_BEAM].rec.p;
   A.plate_rec = h->fd[FEMGPU_PLATE].rec.p;
   A.values = h->values.p;
+  A.slab_begin = 0;
   A.n_slabs = h->n_slabs;
   auto up = [](uint32_t b) { return (b + kSmemAlign - 1u) & ~(kSmemAlign - 1u); };
   A.smem_img = up(h->smem_img);
   A.smem_form = up(h->smem_form);
   A.smem_rawp = up(h->smem_rawp);
   A.smem_stage = up(h->smem_stage);
+  return A;
+}
+
+int32_t run_assembly_unstaged(Handle* h) {
+  if (h->n_slabs == 0 || h->n_unstaged == 0) return 0;
+  const AsmArgs A = asm_args(h);
+  assemble_unstaged_kernel<<<h->n_slabs, h->asm_threads, 0, h->stream>>>(A);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+int32_t run_assembly(Handle* h, uint32_t slab_begin, uint32_t slab_end) {
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  if (h->n_slabs == 0 || slab_end <= slab_begin) return 0;
+  AsmArgs A = asm_args(h);
+  A.slab_begin = slab_begin;
+  A.n_slabs = slab_end;
   const int threads = h->asm_threads;
   const uint32_t desc = threads == 64 ? desc_bytes<64>() : desc_bytes<32>();
   const uint32_t form_bufs = (threads == 64 && FEMGPU_AHEAD != 0) ? 2u : 1u;  // kAhead of assemble_kernel
@@ -851,7 +869,7 @@ int32_t run_assembly(Handle* h) {
         fprintf(stderr, "[femgpu asm] T=%d split=%d bulk=%d smem=%u B (image %u, forms %u, raw plates %u, stage 2 x %u, descriptors 3 x %u) -> %d CTAs/SM, %u slabs (%u unstaged)\n",
                 threads, int(split), int(bulk), smem, A.smem_img, A.smem_form, A.smem_rawp, A.smem_stage, desc, per_sm, h->n_slabs, h->n_unstaged);
     }
-    const uint32_t grid = uint32_t(std::min<uint64_t>(h->n_slabs, uint64_t(h->sm_count) * h->asm_ctas_per_sm));
+    const uint32_t grid = uint32_t(std::min<uint64_t>(slab_end - slab_begin, uint64_t(h->sm_count) * h->asm_ctas_per_sm));
     kernel<<<grid, threads, smem, h->stream>>>(A);
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
@@ -876,11 +894,6 @@ int32_t run_assembly(Handle* h) {
               double(ph[kPhases + 1]) / (32.0 * double(ph[kPhases])));
     }
 #endif
-  }
-  if (h->n_unstaged) {
-    assemble_unstaged_kernel<<<h->n_slabs, threads, 0, h->stream>>>(A);
-    h->launches++;
-    FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   }
   return 0;
 }

@@ -28,7 +28,7 @@ __device__ __forceinline__ void load_xyz(const double* __restrict__ x, const dou
 
 template <bool kWriteErr>
 __global__ void __launch_bounds__(kPrepThreads)
-truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
+truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ n1,
                   const uint32_t* __restrict__ n2, const double* __restrict__ E,
                   const double* __restrict__ A, const double* __restrict__ A2,
                   const double* __restrict__ x, const double* __restrict__ y,
@@ -36,6 +36,7 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
                   int32_t* __restrict__ err) {
   uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  if (order) e = order[e];  // positions [from, n) of the range plan's list (Handle::prep_order)
   double p1[3], p2[3], q[9], k00 = 0.0;
   load_xyz(x, y, z, n1[e], p1);
   load_xyz(x, y, z, n2[e], p2);
@@ -53,7 +54,7 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
 
 template <bool kWriteErr>
 __global__ void __launch_bounds__(kPrepThreads)
-beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
+beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ n1,
                  const uint32_t* __restrict__ n2, const double* __restrict__ E,
                  const double* __restrict__ nu, const double* __restrict__ A,
                  const double* __restrict__ I11, const double* __restrict__ I22,
@@ -65,6 +66,7 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
                  double* __restrict__ rec, int32_t* __restrict__ err) {
   uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  if (order) e = order[e];
   double p1[3], p2[3], r[16];
   load_xyz(x, y, z, n1[e], p1);
   load_xyz(x, y, z, n2[e], p2);
@@ -84,7 +86,7 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
 
 template <bool kWriteErr>
 __global__ void __launch_bounds__(kPrepThreads)
-plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
+plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ n1,
                   const uint32_t* __restrict__ n2, const uint32_t* __restrict__ n3,
                   const uint32_t* __restrict__ n4, const double* __restrict__ E,
                   const double* __restrict__ nu, const double* __restrict__ t,
@@ -93,6 +95,7 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ n1,
                   double* __restrict__ rec, int32_t* __restrict__ err) {
   uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  if (order) e = order[e];
   double p1[3], p2[3], p3[3], p4[3], r[16], m[4];
   load_xyz(x, y, z, n1[e], p1);
   load_xyz(x, y, z, n2[e], p2);
@@ -275,29 +278,29 @@ int32_t run_prep(Handle* h, bool validate_only) {
     if (f == FEMGPU_TRUSS) {
       if (validate_only)
         truss_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
-            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
+            uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
             h->abs_tol, fd.rec.p, fd.err.p);
       else
         truss_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
-            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
+            uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
             h->abs_tol, fd.rec.p, fd.err.p);
     } else if (f == FEMGPU_BEAM) {
       if (validate_only)
         beam_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
-            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
+            uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
             P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
       else
         beam_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
-            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
+            uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
             P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
     } else {
       if (validate_only)
         plate_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
-            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
+            uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
             P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
       else
         plate_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
-            uint32_t(from), uint32_t(n), fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
+            uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
             P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
     }
     h->launches++;
@@ -307,6 +310,39 @@ int32_t run_prep(Handle* h, bool validate_only) {
       FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->join_ev[lane - 1], 0));
     }
     ++lane;
+  }
+  return 0;
+}
+
+// Numeric pass with a range plan: the records of the elements `range` is the first to need, the three families one
+// after the other on stream `st` (the low-priority stream of api.cu femgpu_numeric; the buffers exist: the symbolic
+// call validated, i.e. ran the record kernels over, every element).
+int32_t run_prep_range(Handle* h, int range, cudaStream_t st) {
+  const double* x = h->d_x.p;
+  const double* y = h->d_y.p;
+  const double* z = h->d_z.p;
+  for (int f = kFamilies - 1; f >= 0; --f) {
+    FamilyDev& fd = h->fd[f];
+    const uint32_t from = range ? h->range_elem_end[f][range - 1] : 0u, to = h->range_elem_end[f][range];
+    if (to <= from) continue;
+    FEMGPU_CUDA_CHECK(h, fd.rec.reserve(h->fh[f].size() * size_t(kRecDoubles[f])));
+    FEMGPU_CUDA_CHECK(h, fd.err.reserve(h->fh[f].size()));
+    const uint32_t grid = div_up(to - from, kPrepThreads);
+    const uint32_t* order = h->prep_order[f].p;
+    auto P = [&](int k) { return (const double*)fd.props[k].p; };
+    if (f == FEMGPU_TRUSS)
+      truss_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(from, to, order, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2),
+                                                             x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
+    else if (f == FEMGPU_BEAM)
+      beam_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(from, to, order, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2),
+                                                            P(3), P(4), P(5), P(6), P(7), P(8), P(9), P(10), x, y, z,
+                                                            h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
+    else
+      plate_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(from, to, order, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p,
+                                                             fd.conn[3].p, P(0), P(1), P(2), P(3), x, y, z, h->abs_tol,
+                                                             fd.rec.p, fd.err.p);
+    h->launches++;
+    FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   }
   return 0;
 }

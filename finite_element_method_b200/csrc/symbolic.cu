@@ -731,6 +731,40 @@ __global__ void ordered_meta_kernel(uint32_t n_blocks, uint32_t quota, int key_b
   for (uint32_t c = 0; c < n; ++c) contrib_ord[dst + c] = contrib_sorted[src + c];
 }
 
+// ---- range plan (see Handle::n_ranges) ----
+// first range whose slabs list the element; one thread per slab walks its compact element list
+__global__ void first_range_kernel(uint32_t n_slabs, uint32_t slabs_per_range, const SlabDesc* __restrict__ slabs,
+                                   const uint32_t* __restrict__ elist_compact, uint32_t* __restrict__ first_t,
+                                   uint32_t* __restrict__ first_b, uint32_t* __restrict__ first_p) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_slabs) return;
+  const SlabDesc d = slabs[k];
+  const uint32_t r = k / slabs_per_range;
+  for (uint32_t i = 0; i < d.el_count; ++i) {
+    const uint32_t fe = elist_compact[d.el_begin + i], family = fe >> 26, e = fe & 0x03FFFFFFu;
+    if (family == FEMGPU_TRUSS) atomicMin(first_t + e, r);       // integer min: order independent
+    else if (family == FEMGPU_BEAM) atomicMin(first_b + e, r);
+    else if (family == FEMGPU_PLATE) atomicMin(first_p + e, r);
+  }
+}
+__global__ void iota_u32_kernel(uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+// ends[r] = number of sorted keys <= r (keys of unreferenced elements were clamped to the last range)
+__global__ void range_ends_kernel(uint32_t n, const uint32_t* __restrict__ sorted_keys, uint32_t n_ranges,
+                                  uint32_t* __restrict__ ends) {
+  uint32_t r = threadIdx.x;
+  if (r >= n_ranges) return;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (min(sorted_keys[mid], n_ranges - 1u) <= r) lo = mid + 1;
+    else hi = mid;
+  }
+  ends[r] = lo;
+}
+
 __global__ void element_slots_kernel(int n_nodes_elem, int dof, const uint32_t* __restrict__ nodes,
                                      uint32_t n_blocks, int key_bits,
                                      const uint64_t* __restrict__ blk_key,
@@ -1015,6 +1049,84 @@ static int32_t dist_finalize_plan(Handle* h, const std::vector<int64_t>& ranges)
   return dist_setup_p2p(h);
 }
 
+// Cut the slabs into consecutive ranges and list every family's elements by the first range that needs them.
+static int32_t build_range_plan(Handle* h) {
+  cudaStream_t s = h->stream;
+  const uint32_t n_slabs = h->n_slabs;
+  // a range should keep every persistent CTA busy for a few dozen slabs, or the per-launch ramp costs more than the
+  // overlap buys: ~12 k slabs per range, at most 8 ranges (FEMGPU_NUMERIC_RANGES overrides)
+  int want = int(std::min<uint32_t>(8u, n_slabs / 12000u));
+  if (const char* q = getenv("FEMGPU_NUMERIC_RANGES")) want = atoi(q);
+  want = std::max(1, std::min(want, Handle::kMaxRanges));
+  if (uint32_t(want) > n_slabs) want = int(std::max<uint32_t>(1u, n_slabs));
+  h->n_ranges = want;
+  const uint32_t per = div_up(n_slabs, uint32_t(want));
+  for (int r = 0; r < want; ++r) h->range_slab_end[r] = std::min<uint64_t>(n_slabs, uint64_t(per) * (r + 1));
+  h->range_slab_end[want - 1] = n_slabs;
+  if (want == 1) {
+    for (int f = 0; f < kFamilies; ++f) h->range_elem_end[f][0] = uint32_t(h->fh[f].size());
+    return 0;
+  }
+  Tmp first[kFamilies];
+  for (int f = 0; f < kFamilies; ++f) {
+    const size_t n = h->fh[f].size();
+    SYM_CHECK(first[f].alloc((n + 1) * 4));
+    SYM_CHECK(cudaMemsetAsync(first[f].p, 0xFF, (n + 1) * 4, s));
+  }
+  first_range_kernel<<<div_up(n_slabs, 128), 128, 0, s>>>(n_slabs, per, h->slabs.p, h->elist_compact.p,
+                                                           first[0].as<uint32_t>(), first[1].as<uint32_t>(),
+                                                           first[2].as<uint32_t>());
+  h->launches++;
+  SYM_CHECK(cudaGetLastError());
+  Tmp ends;
+  SYM_CHECK(ends.alloc(size_t(kFamilies) * Handle::kMaxRanges * 4));
+  for (int f = 0; f < kFamilies; ++f) {
+    const uint32_t n = uint32_t(h->fh[f].size());
+    if (n == 0) {
+      for (int r = 0; r < want; ++r) h->range_elem_end[f][r] = 0;
+      continue;
+    }
+    SYM_CHECK(h->prep_order[f].reserve(n));
+    Tmp keys_out, idx_in;
+    SYM_CHECK(keys_out.alloc(size_t(n) * 4));
+    SYM_CHECK(idx_in.alloc(size_t(n) * 4));
+    iota_u32_kernel<<<div_up(n, 256), 256, 0, s>>>(n, idx_in.as<uint32_t>());
+    h->launches++;
+    // stable sort by first range: inside a range the elements keep their index order (coalesced property loads);
+    // 32 key bits so that the 0xFFFFFFFF of an unreferenced element sorts last
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, first[f].as<uint32_t>(), keys_out.as<uint32_t>(), idx_in.as<uint32_t>(),
+                                    h->prep_order[f].p, int(n), 0, 32, s);
+    Tmp t;
+    SYM_CHECK(t.alloc(tb));
+    SYM_CHECK(cub::DeviceRadixSort::SortPairs(t.p, tb, first[f].as<uint32_t>(), keys_out.as<uint32_t>(),
+                                              idx_in.as<uint32_t>(), h->prep_order[f].p, int(n), 0, 32, s));
+    range_ends_kernel<<<1, 32, 0, s>>>(n, keys_out.as<uint32_t>(), uint32_t(want),
+                                       ends.as<uint32_t>() + f * Handle::kMaxRanges);
+    h->launches++;
+    SYM_CHECK(cudaMemcpyAsync(h->range_elem_end[f], ends.as<uint32_t>() + f * Handle::kMaxRanges, size_t(want) * 4,
+                              cudaMemcpyDeviceToHost, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+    h->range_elem_end[f][want - 1] = n;
+  }
+  // nothing to overlap when the first range already needs (almost) every record: one range then
+  uint64_t first_share = 0, total = 0;
+  for (int f = 0; f < kFamilies; ++f) {
+    first_share += h->range_elem_end[f][0];
+    total += h->fh[f].size();
+  }
+  if (!getenv("FEMGPU_NUMERIC_RANGES") && first_share * 10 > total * 6) {
+    h->n_ranges = 1;
+    h->range_slab_end[0] = n_slabs;
+    for (int f = 0; f < kFamilies; ++f) h->range_elem_end[f][0] = uint32_t(h->fh[f].size());
+  }
+  if (getenv("FEMGPU_ASM_INFO")) {
+    fprintf(stderr, "[femgpu ranges] %d ranges of ~%u slabs; first range needs %.1f %% of the element records\n", h->n_ranges,
+            per, total ? 100.0 * double(first_share) / double(total) : 0.0);
+  }
+  return 0;
+}
+
 int32_t run_symbolic(Handle* h) {
   SYM_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
@@ -1068,6 +1180,9 @@ int32_t run_symbolic(Handle* h) {
     SYM_CHECK(cudaStreamSynchronize(s));
     h->n_blocks = h->n_slabs = 0;
     h->nnz = 0;
+    h->n_ranges = 1;
+    h->range_slab_end[0] = 0;
+    for (int f = 0; f < kFamilies; ++f) h->range_elem_end[f][0] = uint32_t(h->fh[f].size());
     if (h->dist.enabled) return dist_finalize_plan(h, ranges);
     return 0;
   }
@@ -1279,6 +1394,11 @@ int32_t run_symbolic(Handle* h) {
   h->asm_bulk = int64_t(flags[14]) >= 4 * int64_t(flags[15]) && flags[15] > 0;
   if (const char* q = getenv("FEMGPU_ASM_BULK")) h->asm_bulk = atoi(q) != 0;  // tuning knob
 
+  {
+    int32_t st = build_range_plan(h);
+    if (st) return st;
+  }
+  mark("range plan");
   if (h->dist.enabled) {
     int32_t st = dist_finalize_plan(h, ranges);
     if (st) return st;

@@ -496,6 +496,12 @@ class FEM:
         self._check(self._L.femgpu_numeric_ms_history(self._h, passes_back, _p(out, _lib.fp)))
         return [float(x) for x in out]
 
+    def numeric_kernel_ms(self, passes_back: int = 0):
+        """(sum of the assemble_kernel launch durations of that pass in ms, number of launches)"""
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self._L.femgpu_numeric_kernel_ms(self._h, passes_back, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def device_bytes(self) -> int:
         v = C.c_uint64()
         self._check(self._L.femgpu_device_bytes(self._h, C.byref(v)))

@@ -326,6 +326,9 @@ int32_t femgpu_last_numeric_ms(femgpu_t* h, float out[4]);
 /* same for the pass issued `passes_back` passes before the last one (0 = last; the handle keeps
  * the events of the most recent 64 passes), so a timed loop needs no sync between passes */
 int32_t femgpu_numeric_ms_history(femgpu_t* h, uint32_t passes_back, float out[4]);
+/* sum of the assemble_kernel launch durations of that pass (the pass may cut the slabs into several ranges, each one
+ * launch, while the element records of the next range are computed on a second stream) and the number of launches */
+int32_t femgpu_numeric_kernel_ms(femgpu_t* h, uint32_t passes_back, float* assemble_ms, int32_t* launches);
 /* bytes of device memory held by the handle */
 int32_t femgpu_device_bytes(const femgpu_t* h, uint64_t* bytes);
 /* the CUDA stream handle (cudaStream_t) work is issued on, for callers that time with events */
