@@ -278,6 +278,8 @@ def measure_numeric(args, scaling, ctx, sample_clocks):
     launches = fem.launch_count()
     hist = [fem.numeric_ms_history(i) for i in range(min(args.steps, 64))]   # the timed passes
     kern = [fem.numeric_kernel_ms(i) for i in range(min(args.steps, 64))]
+    if os.environ.get("FEMGPU_BENCH_DEBUG"):      # every timed pass, oldest first: [total, records, assembly, exchange] ms
+        log(f"{scaling}: per-pass ms " + " | ".join(" ".join(f"{x:.3f}" for x in h) for h in reversed(hist)))
     if dist is not None:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

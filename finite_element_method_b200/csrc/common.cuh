@@ -285,6 +285,7 @@ struct DistState {
   std::vector<unsigned char*> peer_win;  // peers' windows mapped into this process (nullptr: no traffic with that rank)
   size_t win_slot_bytes = 0, win_bytes = 0;
   std::vector<int64_t> peer_recv_off;    // first block of my run in peer r's receive area
+  std::vector<size_t> peer_slot_bytes;   // ring-slot size of peer r's window (its receive area, rounded like mine)
   uint64_t epoch = 0;                    // numeric passes since the plan was built (the same on every rank)
   uint32_t* done_count = nullptr;        // device: per-peer "last CTA" counters of the pack / apply kernels
   volatile uint32_t* h_err = nullptr;    // mapped pinned host word: a kernel timed out waiting for a peer

@@ -297,7 +297,8 @@ static int32_t p2p_numeric_exchange(Handle* h) {
   for (int r = 0; r < W; ++r) {  // my ghost blocks -> the owner's window
     if (r == D.rank || D.send_blocks[r] == 0) continue;
     const uint32_t n = uint32_t(D.send_blocks[r]);
-    double* out = reinterpret_cast<double*>(D.peer_win[r] + flag_bytes + size_t(slot) * D.win_slot_bytes) +
+    // the ring slots of a window are sized by ITS OWNER's receive area
+    double* out = reinterpret_cast<double*>(D.peer_win[r] + flag_bytes + size_t(slot) * D.peer_slot_bytes[r]) +
                   size_t(D.peer_recv_off[r]) * 36;
     const uint64_t need = epoch > uint64_t(DistState::kRing) ? epoch - DistState::kRing : 0;
     pack_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(
@@ -369,7 +370,15 @@ int32_t dist_setup_p2p(Handle* h) {
   bool want = true;
   if (const char* q = getenv("FEMGPU_DIST_P2P")) want = atoi(q) != 0;
   const int64_t n_recv = D.recv_off[W];
-  D.win_slot_bytes = (size_t(n_recv) * 36 * 8 + 255) & ~size_t(255);
+  auto slot_bytes = [](int64_t blocks) { return (size_t(blocks) * 36 * 8 + 255) & ~size_t(255); };
+  D.win_slot_bytes = slot_bytes(n_recv);
+  D.peer_slot_bytes.assign(W, 0);
+  for (int r = 0; r < W; ++r) {  // what rank r receives in total: column r of the count matrix
+    int64_t total = 0;
+    for (int q = 0; q < W; ++q)
+      if (q != r) total += D.count_matrix[size_t(q) * W + r];
+    D.peer_slot_bytes[r] = slot_bytes(total);
+  }
   D.win_bytes = win_flag_bytes(W) + DistState::kRing * D.win_slot_bytes;
   bool ok = want;
   cudaIpcMemHandle_t mine;

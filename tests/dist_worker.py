@@ -100,6 +100,8 @@ def fullsize(rank, world, local, dist, torch):
     """BASELINE.json config 5 as the north star states it: ONE 10M-element mixed mesh partitioned into `world`
     contiguous row strips. Every rank compares sampled rows of the strip it owns — among them its first grid line
     (which received the lower neighbour's ghost contributions) and its last one — with the oracle."""
+    import faulthandler
+    faulthandler.dump_traceback_later(360, exit=True)    # 10M elements per rank to build and check: allow more time
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from finite_element_method_b200 import FEM, meshes
     from fullsize_common import compare_sampled_rows, sample_nodes
@@ -134,4 +136,12 @@ def fullsize(rank, world, local, dist, torch):
 
 
 if __name__ == "__main__":
-    main()
+    import faulthandler
+    import traceback
+    faulthandler.dump_traceback_later(150, exit=True)   # a stuck rank must not hold the test (and the GPU box) for long
+    try:
+        main()
+    except BaseException:
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)                                      # no atexit / NCCL teardown that could wait for the other ranks
