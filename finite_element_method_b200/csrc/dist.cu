@@ -460,6 +460,7 @@ int32_t dist_numeric_exchange(Handle* h) {
   const int W = D.world;
   D.last_sent = D.last_recv = 0;
   if (D.p2p) return p2p_numeric_exchange(h);
+  ++D.epoch;
   // pack ghost blocks, one dense run per destination rank
   for (int r = 0; r < W; ++r) {
     if (r == D.rank || D.send_blocks[r] == 0) continue;

@@ -57,6 +57,16 @@ __device__ unsigned long long g_phase[kPhases + 4];
 #define PHASE_MARK(i)
 #endif
 
+// Ablation builds (make variant NAME=... DEFS=-DFEMGPU_ABL=<bits>; results are WRONG, only the kernel time means
+// something): which part of a slab's work bounds the kernel is found by leaving parts out, one at a time.
+//   1 no bulk store of the image     2 no contribution loop (phase B)     4 no staging loads for the next slab
+//   8 no block flush into the image  16 no fence.proxy.async before the store   32 no plate forms (phase A)
+#ifndef FEMGPU_ABL
+#define FEMGPU_ABL 0
+#endif
+constexpr bool kAblNoStore = (FEMGPU_ABL & 1) != 0, kAblNoLoop = (FEMGPU_ABL & 2) != 0, kAblNoStage = (FEMGPU_ABL & 4) != 0,
+               kAblNoFlush = (FEMGPU_ABL & 8) != 0, kAblNoFence = (FEMGPU_ABL & 16) != 0, kAblNoForms = (FEMGPU_ABL & 32) != 0;
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -305,6 +315,7 @@ __device__ __forceinline__ SlabRegs<kT> read_desc(const unsigned char* dbuf, uin
 template <int kT, bool kBulk>
 __device__ __forceinline__ void issue_stage(const AsmArgs& A, const SlabRegs<kT>& R, uint32_t stage_s,
                                             uint32_t rawp_s, uint32_t mbar_s, uint32_t tid) {
+  if (kAblNoStage) return;
   // block metadata and contribution entries are contiguous: two TMA bulk loads by one thread,
   // completing on the same mbarrier as the record copies
   const uint32_t nt = R.n_truss(), nbm = R.n_beam();
@@ -472,7 +483,7 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
   uint32_t pending = 0;  // merge rounds of the thread's last group (a chunk of a split block)
   bool sender = false;
   uint4 pending_m = make_uint4(0u, 0u, 0u, 0u);
-  if (i < end) {
+  if (!kAblNoLoop && i < end) {
     uint32_t code = ent[i];
     PlatePair pt = pairs[(code >> 26) & 15u];
     for (; i < end; ++i) {
@@ -502,6 +513,8 @@ __device__ __forceinline__ void phase_b(const SlabRegs<kT>& R, const unsigned ch
           pending = defer;
           sender = (code & kEntRmw) != 0;
           pending_m = m;
+        } else if (kAblNoFlush) {
+          if (acc[0] == 1.2345e300) img[0] = acc[7] + acc[35];  // never true: keeps the sums alive
         } else if (code & kEntRmw) {
           store_block<true>(img, m, acc, true);
         } else {
@@ -653,7 +666,7 @@ assemble_kernel(const AsmArgs A) {
       mbar_wait(mbar_s, it & 1u);  // batch it + 2
       double* form_next = form0 + (buf ^ 1u) * (A.smem_form / 8u);
       bool flat = true;
-      for (uint32_t idx = tid - 32u; idx < np_next; idx += 32u) {
+      for (uint32_t idx = tid - 32u; idx < (kAblNoForms ? 0u : np_next); idx += 32u) {
         double raw[20];
         const double2* src = reinterpret_cast<const double2*>(rawp + idx * 20u);
 #pragma unroll
@@ -675,9 +688,9 @@ assemble_kernel(const AsmArgs A) {
       double* out = A.values + cur.val_base();
       if (((uint32_t(cur.val_base()) | n) & 1u) == 0) {
         // 16-byte aligned slab: generic-proxy writes -> async proxy, then one TMA bulk store
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!kAblNoFence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         cta_sync<kT>();
-        if (tid == 0) {
+        if (tid == 0 && !kAblNoStore) {
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out),
                        "r"(smem_u32(img)), "r"(n * 8u)
                        : "memory");
