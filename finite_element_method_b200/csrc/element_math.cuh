@@ -81,8 +81,10 @@ __device__ inline void rotation_align(const double a[3], const double b[3], doub
     y = ax[1] / n;
     z = ax[2] / n;
   }
-  double c = clip_tol(cos(angle), abs_tol);
-  double s = clip_tol(sin(angle), abs_tol);
+  double sn, cs;
+  sincos(angle, &sn, &cs);  // one argument reduction for both (the values are those of sin() and cos())
+  double c = clip_tol(cs, abs_tol);
+  double s = clip_tol(sn, abs_tol);
   double t = 1.0 - c;
   q[0] = clip_tol(t * x * x + c, abs_tol);
   q[1] = clip_tol(t * x * y - z * s, abs_tol);
@@ -168,14 +170,14 @@ __device__ inline void beam_principal_inertia(double i11, double i22, double i12
     }
     angle = atan(2.0 * i12 / (i22_mod - i11_mod)) / 2.0;
   }
-  double ca = cos(angle), sa = sin(angle), s2 = sin(2.0 * angle);
+  double ca, sa, s2 = sin(2.0 * angle);
+  sincos(angle, &sa, &ca);
   double p11 = i11 * (ca * ca) + i22 * (sa * sa) - i12 * s2;
   double p22 = i11 * (sa * sa) + i22 * (ca * ca) + i12 * s2;
   int i = 1;
   while (p11 < p22 && i <= 64) {
     angle = (atan(2.0 * i12 / (i22 - i11)) + PI_F32 * (double)(float)i) / 2.0;
-    ca = cos(angle);
-    sa = sin(angle);
+    sincos(angle, &sa, &ca);
     s2 = sin(2.0 * angle);
     p11 = i11 * (ca * ca) + i22 * (sa * sa) - i12 * s2;
     p22 = i11 * (sa * sa) + i22 * (ca * ca) + i12 * s2;
@@ -230,8 +232,10 @@ __device__ inline int beam_record(const double p1[3], const double p2[3], double
   double c_y = clip_tol(v[1] / len, abs_tol);
   double c_z = clip_tol(v[2] / len, abs_tol);
   double c_xz = clip_tol(sqrt(c_x * c_x + c_z * c_z), abs_tol);
-  double c = clip_tol(cos(total_angle), abs_tol);
-  double s = clip_tol(sin(total_angle), abs_tol);
+  double sn, cs;
+  sincos(total_angle, &sn, &cs);
+  double c = clip_tol(cs, abs_tol);
+  double s = clip_tol(sn, abs_tol);
   bool nz = c_xz != 0.0;
   rec[0] = nz ? c_x : 0.0;
   rec[1] = c_y;

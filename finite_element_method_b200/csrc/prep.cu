@@ -18,6 +18,12 @@ namespace femgpu {
 namespace {
 
 constexpr int kPrepThreads = 256;
+// The record kernels are latency-bound (dependent FP64 chains through acos / sincos / sqrt / divisions): resident warps
+// are what hides that latency, so the beam and plate kernels are held to 64 registers (4 x 256 threads per SM).
+#ifndef FEMGPU_PREP_BLOCKS
+#define FEMGPU_PREP_BLOCKS 4
+#endif
+constexpr int kPrepBlocksPerSm = FEMGPU_PREP_BLOCKS;
 
 __device__ __forceinline__ void load_xyz(const double* __restrict__ x, const double* __restrict__ y,
                                          const double* __restrict__ z, uint32_t i, double p[3]) {
@@ -53,7 +59,7 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
 }
 
 template <bool kWriteErr>
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, kPrepBlocksPerSm)
 beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ n1,
                  const uint32_t* __restrict__ n2, const double* __restrict__ E,
                  const double* __restrict__ nu, const double* __restrict__ A,
@@ -85,7 +91,7 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, 
 }
 
 template <bool kWriteErr>
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, kPrepBlocksPerSm)
 plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ n1,
                   const uint32_t* __restrict__ n2, const uint32_t* __restrict__ n3,
                   const uint32_t* __restrict__ n4, const double* __restrict__ E,

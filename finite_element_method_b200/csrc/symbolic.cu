@@ -1053,9 +1053,12 @@ static int32_t dist_finalize_plan(Handle* h, const std::vector<int64_t>& ranges)
 static int32_t build_range_plan(Handle* h) {
   cudaStream_t s = h->stream;
   const uint32_t n_slabs = h->n_slabs;
-  // a range should keep every persistent CTA busy for a few dozen slabs, or the per-launch ramp costs more than the
-  // overlap buys: ~12 k slabs per range, at most 8 ranges (FEMGPU_NUMERIC_RANGES overrides)
-  int want = int(std::min<uint32_t>(8u, n_slabs / 12000u));
+  // Off by default (one range = the element records of all elements first, then one assembly launch). Measured on
+  // B200 (profiles/README.md, round 2): the record kernels running in the SM resources the assembly kernel leaves
+  // free (one 256-thread block per SM next to 4 x 54 KB assembly CTAs) are ~25 % slower than the assembly of the same
+  // range, so the pipeline is bound by the records again and every extra launch adds its ramp: M 3.93 ms with one
+  // range, 4.01 / 4.02 / 4.04 / 4.12 ms with 2 / 3 / 4 / 8. FEMGPU_NUMERIC_RANGES=n turns it on.
+  int want = 1;
   if (const char* q = getenv("FEMGPU_NUMERIC_RANGES")) want = atoi(q);
   want = std::max(1, std::min(want, Handle::kMaxRanges));
   if (uint32_t(want) > n_slabs) want = int(std::max<uint32_t>(1u, n_slabs));

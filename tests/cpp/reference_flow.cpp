@@ -65,8 +65,9 @@ int main(int argc, char** argv) {
   FEM::Csr K = fem.assemble();
   EXPECT(K.row_ptr.size() == 13 && K.values.size() == 36);  // two nodes, 3x3 blocks: rows 0-2 and 6-8 hold 6 entries
   EXPECT(near(K.values[0], 66666.66666666667, 1e-15));
-  for (int dof = 0; dof < 6; ++dof) fem.add_displacement(1, dof, 0.0);
-  for (int dof = 1; dof < 6; ++dof) fem.add_displacement(2, dof, 0.0);
+  // a truss only has axial stiffness: every other DOF is inactive, and constraining one of them is an error
+  // (methods_for_separate_stiffness_matrix.rs:233-262) — the reference's test constrains node 1 X only
+  fem.add_displacement(1, 0, 0.0);
   fem.add_concentrated_load(2, 0, 100.0);
   // sparse iterative flow (test_fem.rs:83-225)
   auto sep = fem.separate_stiffness_matrix_sparse_iterative();
