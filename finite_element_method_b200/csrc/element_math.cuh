@@ -42,6 +42,22 @@ __device__ __forceinline__ double clip_tol(double v, double abs_tol) {
   return fabs(v) < abs_tol ? 0.0 : v;
 }
 
+// Transcendental functions at their exactly representable special values. acos(1) = 0, atan(+-0) = +-0,
+// sin(+-0) = +-0 and cos(+-0) = 1 hold exactly, so skipping the library call there returns the same bits; it matters
+// because structural models are full of such inputs (members along +x, flat plates with the normal along +z, sections
+// given in their principal axes) and a double-precision acos / sincos costs a few hundred instructions.
+__device__ __forceinline__ double acos_x(double c) { return c == 1.0 ? 0.0 : acos(c); }
+__device__ __forceinline__ double atan_x(double t) { return t == 0.0 ? t : atan(t); }
+__device__ __forceinline__ double sin_x(double a) { return a == 0.0 ? a : sin(a); }
+__device__ __forceinline__ void sincos_x(double a, double* s, double* c) {
+  if (a == 0.0) {
+    *s = a;
+    *c = 1.0;
+  } else {
+    sincos(a, s, c);
+  }
+}
+
 __device__ __forceinline__ double norm3(const double a[3]) {
   double acc = 0.0;
   acc += a[0] * a[0];
@@ -71,7 +87,7 @@ __device__ inline void rotation_align(const double a[3], const double b[3], doub
   double na = norm3(a), nb = norm3(b);
   double cosv = dot3(a, b) / (na * nb);
   cosv = cosv > 1.0 ? 1.0 : (cosv < -1.0 ? -1.0 : cosv);
-  double angle = acos(cosv);
+  double angle = acos_x(cosv);
   double ax[3];
   cross3(a, b, ax);
   double n = norm3(ax);
@@ -82,7 +98,7 @@ __device__ inline void rotation_align(const double a[3], const double b[3], doub
     z = ax[2] / n;
   }
   double sn, cs;
-  sincos(angle, &sn, &cs);  // one argument reduction for both (the values are those of sin() and cos())
+  sincos_x(angle, &sn, &cs);  // one argument reduction for both (the values are those of sin() and cos())
   double c = clip_tol(cs, abs_tol);
   double s = clip_tol(sn, abs_tol);
   double t = 1.0 - c;
@@ -158,7 +174,7 @@ __device__ inline void beam_principal_inertia(double i11, double i22, double i12
   const double PI_F32 = (double)3.14159265358979323846f;  // V::from(std::f32::consts::PI)
   double angle;
   if (i11 != i22) {
-    angle = atan(2.0 * i12 / (i22 - i11)) / 2.0;
+    angle = atan_x(2.0 * i12 / (i22 - i11)) / 2.0;
   } else {
     double i11_mod, i22_mod;
     if (i22 < i11) {
@@ -168,10 +184,10 @@ __device__ inline void beam_principal_inertia(double i11, double i22, double i12
       i11_mod = (fabs(i11) - fabs(i11) * rel_tol) * i11 / fabs(i11);
       i22_mod = i22;
     }
-    angle = atan(2.0 * i12 / (i22_mod - i11_mod)) / 2.0;
+    angle = atan_x(2.0 * i12 / (i22_mod - i11_mod)) / 2.0;
   }
-  double ca, sa, s2 = sin(2.0 * angle);
-  sincos(angle, &sa, &ca);
+  double ca, sa, s2 = sin_x(2.0 * angle);
+  sincos_x(angle, &sa, &ca);
   double p11 = i11 * (ca * ca) + i22 * (sa * sa) - i12 * s2;
   double p22 = i11 * (sa * sa) + i22 * (ca * ca) + i12 * s2;
   int i = 1;
@@ -227,13 +243,13 @@ __device__ inline int beam_record(const double p1[3], const double p2[3], double
   const double ez[3] = {0.0, 0.0, 1.0};
   double cosv = dot3(ez, tp) / (norm3(ez) * norm3(tp));
   cosv = cosv > 1.0 ? 1.0 : (cosv < -1.0 ? -1.0 : cosv);
-  double total_angle = angle + acos(cosv);
+  double total_angle = angle + acos_x(cosv);
   double c_x = clip_tol(v[0] / len, abs_tol);
   double c_y = clip_tol(v[1] / len, abs_tol);
   double c_z = clip_tol(v[2] / len, abs_tol);
   double c_xz = clip_tol(sqrt(c_x * c_x + c_z * c_z), abs_tol);
   double sn, cs;
-  sincos(total_angle, &sn, &cs);
+  sincos_x(total_angle, &sn, &cs);
   double c = clip_tol(cs, abs_tol);
   double s = clip_tol(sn, abs_tol);
   bool nz = c_xz != 0.0;
