@@ -708,6 +708,9 @@ void femgpu_destroy(femgpu_t* h) {
   }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
+  if (h->xchg_stream) cudaStreamDestroy(h->xchg_stream);
+  if (h->ghost_ev) cudaEventDestroy(h->ghost_ev);
+  if (h->pack_ev) cudaEventDestroy(h->pack_ev);
   for (auto& e : h->range_ev)
     if (e) cudaEventDestroy(e);
   for (auto& q : h->range_t0)
@@ -891,6 +894,47 @@ int32_t femgpu_numeric(femgpu_t* h) {
   int32_t st = 0;
   const int R = h->n_ranges;
   h->range_count[slot] = 0;
+  auto range_events = [&]() -> int32_t {
+    if (h->range_t0[0][0]) return 0;
+    for (auto& q : h->range_t0)
+      for (auto& e : q) FEMGPU_CUDA_CHECK(h, cudaEventCreate(&e));
+    for (auto& q : h->range_t1)
+      for (auto& e : q) FEMGPU_CUDA_CHECK(h, cudaEventCreate(&e));
+    return 0;
+  };
+  uint32_t g0 = 0;
+  if (dist_ghost_first(h, &g0)) {
+    // Multi-GPU with peer windows: ghost slabs first, their blocks leave on a second stream while the rest of the
+    // matrix is assembled; the partials of the lower neighbour are added at the end (dist.cu).
+    if (!h->xchg_stream) {
+      FEMGPU_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->xchg_stream, cudaStreamNonBlocking));
+      FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ghost_ev, cudaEventDisableTiming));
+      FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->pack_ev, cudaEventDisableTiming));
+    }
+    if ((st = range_events())) return st;
+    if ((st = run_prep(h, /*validate_only=*/false))) return st;
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
+    if ((st = dist_begin_pass(h))) return st;
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t0[slot][0], h->stream));
+    if ((st = run_assembly(h, g0, h->n_slabs))) return st;  // (the previous pass's pack was joined at its end)
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t1[slot][0], h->stream));
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ghost_ev, h->stream));
+    FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->xchg_stream, h->ghost_ev, 0));
+    if ((st = dist_pack(h, h->xchg_stream))) return st;
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->pack_ev, h->xchg_stream));
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t0[slot][1], h->stream));
+    if ((st = run_assembly(h, 0, g0))) return st;
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t1[slot][1], h->stream));
+    h->range_count[slot] = 2;
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[2], h->stream));
+    if ((st = dist_apply(h))) return st;
+    // join: a synchronised handle has sent its blocks, and the next pass may overwrite the ghost rows
+    FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->pack_ev, 0));
+    FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[3], h->stream));
+    h->n_numeric++;
+    h->values_valid = true;
+    return 0;
+  }
   if (R <= 1) {
     if ((st = run_prep(h, /*validate_only=*/false))) return st;
     FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
@@ -904,11 +948,8 @@ int32_t femgpu_numeric(femgpu_t* h) {
       FEMGPU_CUDA_CHECK(h, cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, least));
       if (!h->fork_ev) FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
       for (auto& e : h->range_ev) FEMGPU_CUDA_CHECK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      for (auto& q : h->range_t0)
-        for (auto& e : q) FEMGPU_CUDA_CHECK(h, cudaEventCreate(&e));
-      for (auto& q : h->range_t1)
-        for (auto& e : q) FEMGPU_CUDA_CHECK(h, cudaEventCreate(&e));
     }
+    if ((st = range_events())) return st;
     FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->fork_ev, h->stream));  // after the previous pass: its kernels read the records
     FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->prep_stream, h->fork_ev, 0));
     auto prep = [&](int r) -> int32_t {

@@ -349,6 +349,7 @@ struct Handle {
   uint32_t smem_img = 0, smem_form = 0, smem_rawp = 0, smem_stage = 0;
   uint32_t n_unstaged = 0;         // slabs handled by assemble_unstaged_kernel
   int sm_count = 0;
+  uint32_t slab_quota = 72;        // node-pair blocks per slab the symbolic pass aimed for
   int asm_threads = 32;            // 32 or 64, fixed by the symbolic pass
   bool asm_split = false;          // some slab splits a block over several lanes (kernel variant with merge rounds)
   bool asm_bulk = false;           // element records are staged run-wise with TMA bulk copies (consecutive numbering)
@@ -429,6 +430,8 @@ struct Handle {
   uint32_t range_elem_end[kFamilies][kMaxRanges] = {};
   DevBuf<uint32_t> prep_order[kFamilies];
   cudaStream_t prep_stream = nullptr;
+  cudaStream_t xchg_stream = nullptr;   // ghost-first multi-GPU pass: the pack kernels run here, under the assembly
+  cudaEvent_t ghost_ev = nullptr, pack_ev = nullptr;
   cudaEvent_t range_ev[kMaxRanges] = {};
   cudaEvent_t range_t0[kEvRing][kMaxRanges] = {}, range_t1[kEvRing][kMaxRanges] = {};  // per-range assembly launch times
   int range_count[kEvRing] = {};  // ranges of the pass in that ring slot (0: one launch between ev[1] and ev[2])
@@ -507,6 +510,10 @@ int32_t run_element_results(Handle* h, int family, const double* d_u, double* d_
 void sol_release(Handle* h);                             // solve.cu
 void sol_invalidate(Handle* h);                          // solve.cu
 int32_t dist_numeric_exchange(Handle* h);                // dist.cu
+bool dist_ghost_first(Handle* h, uint32_t* first_ghost_slab);  // dist.cu: can the ghost slabs be assembled and sent first?
+int32_t dist_begin_pass(Handle* h);                      // dist.cu: ghost-first pass: next epoch
+int32_t dist_pack(Handle* h, cudaStream_t st);           // dist.cu: my ghost blocks -> the owners' windows
+int32_t dist_apply(Handle* h);                           // dist.cu: received partials += into my rows
 int32_t dist_setup_p2p(Handle* h);                       // dist.cu: collective, called when the exchange plan is final
 int32_t dist_check(Handle* h);                           // dist.cu: after a stream sync — did an exchange time out?
 void dist_destroy(Handle* h);                            // dist.cu

@@ -288,27 +288,39 @@ static uint64_t p2p_timeout_ns() {
   return ns;
 }
 
-static int32_t p2p_numeric_exchange(Handle* h) {
+// my ghost blocks -> the owners' windows (pass D.epoch), on stream `st`
+static int32_t p2p_pack(Handle* h, cudaStream_t st) {
   DistState& D = h->dist;
   const int W = D.world;
-  const uint64_t epoch = ++D.epoch;
+  const uint64_t epoch = D.epoch;
   const uint32_t slot = uint32_t((epoch - 1) % DistState::kRing);
   const size_t flag_bytes = win_flag_bytes(W);
-  for (int r = 0; r < W; ++r) {  // my ghost blocks -> the owner's window
+  for (int r = 0; r < W; ++r) {
     if (r == D.rank || D.send_blocks[r] == 0) continue;
     const uint32_t n = uint32_t(D.send_blocks[r]);
     // the ring slots of a window are sized by ITS OWNER's receive area
     double* out = reinterpret_cast<double*>(D.peer_win[r] + flag_bytes + size_t(slot) * D.peer_slot_bytes[r]) +
                   size_t(D.peer_recv_off[r]) * 36;
     const uint64_t need = epoch > uint64_t(DistState::kRing) ? epoch - DistState::kRing : 0;
-    pack_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(
+    pack_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, st>>>(
         n, uint32_t(D.send_first_block[r]), h->key_bits, h->blk_key.p, h->blk_off.p, h->node_len.p, h->node_base.p,
         h->values.p, out, win_consumed(D.win, W, r), need, win_arrived(D.peer_win[r], D.rank), epoch,
         D.done_count + r, p2p_timeout_ns(), 0x100u + uint32_t(r), D.d_err);
     h->launches++;
     D.last_sent += uint64_t(n) * 36 * 8;
   }
-  for (int r = 0; r < W; ++r) {  // partials of the other ranks, in rank order (fixed order of the sums)
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+// partials of the other ranks, in rank order (fixed order of the sums), on the handle's stream
+static int32_t p2p_apply(Handle* h) {
+  DistState& D = h->dist;
+  const int W = D.world;
+  const uint64_t epoch = D.epoch;
+  const uint32_t slot = uint32_t((epoch - 1) % DistState::kRing);
+  const size_t flag_bytes = win_flag_bytes(W);
+  for (int r = 0; r < W; ++r) {
     if (r == D.rank || D.recv_blocks[r] == 0) continue;
     const uint32_t n = uint32_t(D.recv_blocks[r]);
     const double* in = reinterpret_cast<const double*>(D.win + flag_bytes + size_t(slot) * D.win_slot_bytes) +
@@ -323,6 +335,41 @@ static int32_t p2p_numeric_exchange(Handle* h) {
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   return 0;
 }
+
+static int32_t p2p_numeric_exchange(Handle* h) {
+  ++h->dist.epoch;
+  int32_t st = p2p_pack(h, h->stream);
+  if (st) return st;
+  return p2p_apply(h);
+}
+
+// Ghost-first numeric pass (api.cu femgpu_numeric): the ghost rows are the LAST rows of the local matrix, hence the
+// last slabs. When they are assembled first, their blocks can travel to the owners (pack kernel on a second stream)
+// while the rest of the matrix is being assembled, and the owners' apply kernels find the flags already raised.
+bool dist_ghost_first(Handle* h, uint32_t* first_ghost_slab) {
+  DistState& D = h->dist;
+  if (!D.enabled || !D.p2p || h->n_unstaged || h->n_ranges > 1 || h->n_slabs == 0) return false;
+  static const bool off = getenv("FEMGPU_DIST_GHOST_FIRST") && atoi(getenv("FEMGPU_DIST_GHOST_FIRST")) == 0;
+  if (off) return false;
+  int64_t first_block = -1;
+  for (int r = 0; r < D.world; ++r)
+    if (r != D.rank && D.send_blocks[r] > 0 && (first_block < 0 || D.send_first_block[r] < first_block))
+      first_block = D.send_first_block[r];
+  if (first_block < 0) return false;  // nothing to send (the last rank of a strip partition)
+  // slab k starts at the first node whose first block is >= k * quota, and the first ghost block is the first block
+  // of the first ghost node: it lies in slab floor(first_block / quota)
+  const uint32_t g0 = uint32_t(first_block / h->slab_quota);
+  if (g0 == 0 || g0 >= h->n_slabs) return false;
+  *first_ghost_slab = g0;
+  return true;
+}
+int32_t dist_begin_pass(Handle* h) {
+  h->dist.last_sent = h->dist.last_recv = 0;
+  ++h->dist.epoch;
+  return 0;
+}
+int32_t dist_pack(Handle* h, cudaStream_t st) { return p2p_pack(h, st); }
+int32_t dist_apply(Handle* h) { return p2p_apply(h); }
 
 static void p2p_close_peers(Handle* h) {
   for (auto& w : h->dist.peer_win) {

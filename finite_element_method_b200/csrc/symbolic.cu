@@ -1242,6 +1242,7 @@ int32_t run_symbolic(Handle* h) {
   if (const char* q = getenv("FEMGPU_SLAB_QUOTA")) quota = std::max(1, atoi(q));  // tuning knob
   uint32_t n_slabs = div_up(nblk, quota);
   h->n_slabs = n_slabs;
+  h->slab_quota = quota;
   SYM_CHECK(h->slabs.reserve(n_slabs));
   slab_kernel<<<div_up(n_slabs, 256), 256, 0, s>>>(n_slabs, quota, N, h->node_blk_ptr.p, h->node_base.p,
                                                    h->slabs.p, h->d_flag.p);
