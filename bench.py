@@ -209,6 +209,8 @@ def workload(args, scaling, rank, world):
         local = (meshes.mixed_structure(nx, ny, rows=rows, variant=variant) if args.config == "M"
                  else meshes.plate_grid(nx, ny, variant, rows=rows))
         n_el_total = nx * ny * (1 if args.config == "P" else 2) + (len(range(0, nx, 2)) * ny if args.config == "M" else 0)
+        if world > 1:      # the rank is handed its own rows' nodes plus the halo its elements touch, not every node
+            local = meshes.with_node_window(local, begin, end)
         return local, local["name"], n_nodes, n_el_total, begin, end
     jitter = variant == "jitter"
     if args.config == "B":
@@ -217,7 +219,7 @@ def workload(args, scaling, rank, world):
         mesh = meshes.truss_lattice(args.nx or 64, 1_000_000 if args.nx is None else 10 ** 9, jitter=jitter)
     n_nodes = len(mesh["x"])
     begin, end = meshes.partition_rows(mesh, world, None)[rank]
-    local = meshes.local_part(mesh, begin, end) if world > 1 else mesh
+    local = meshes.with_node_window(meshes.local_part(mesh, begin, end), begin, end) if world > 1 else mesh
     return local, mesh["name"], n_nodes, meshes.n_elements(mesh), begin, end
 
 

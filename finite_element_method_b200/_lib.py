@@ -77,6 +77,7 @@ SIGNATURES = {
     "femgpu_dist_unique_id": (C.c_int32, [u8p]),
     "femgpu_dist_init": (C.c_int32, [H, C.c_int32, C.c_int32, u8p]),
     "femgpu_dist_set_ownership": (C.c_int32, [H, C.c_uint32, C.c_uint32]),
+    "femgpu_dist_set_node_window": (C.c_int32, [H, C.c_uint32]),
     "femgpu_dist_last_exchange_bytes": (C.c_int32, [H, u64p, u64p]),
     "femgpu_dist_info": (C.c_int32, [H, i32p, u64p]),
 }

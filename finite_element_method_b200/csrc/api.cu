@@ -675,6 +675,7 @@ int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
     sol_invalidate(h);
   }
   h->nodes_number = nodes_number;
+  h->node_index_base = 0;
   h->node_number.clear(); h->nx.clear(); h->ny.clear(); h->nz.clear();
   h->node_by_number.clear(); h->node_by_xyz.clear();
   h->nodes_uploaded = 0;
@@ -738,8 +739,9 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
   if (n && (!number || !x || !y || !z)) return h->fail(FEMGPU_ERR_USAGE, "null node array");
   if (n == 0) return 0;
   const size_t n0 = h->n_nodes();
+  const size_t g0 = size_t(h->node_index_base) + n0;  // global insertion index of the batch's first node
   // methods_for_node_data_handle.rs:42-64, per node: limit, then number, (index,) coordinates
-  const size_t room = h->nodes_number > n0 ? size_t(h->nodes_number) - n0 : 0;
+  const size_t room = h->nodes_number > g0 ? size_t(h->nodes_number) - g0 : 0;
   const size_t i_limit = std::min(n, room);
   size_t scan_end = std::min(n, i_limit + 0);
   // duplicate numbers (sequential dense-table pass)
@@ -750,7 +752,7 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
       i_num = i;
       break;
     }
-    h->node_by_number.insert(number[i], uint32_t(n0 + i));
+    h->node_by_number.insert(number[i], uint32_t(g0 + i));
     ++inserted;
   }
   scan_end = std::min(scan_end, i_num + 1);

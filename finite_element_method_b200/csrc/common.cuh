@@ -307,6 +307,11 @@ struct Handle {
   float last_ms[4] = {0, 0, 0, 0};
 
   // ---- nodes ----
+  // Node window (multi-GPU, femgpu_dist_set_node_window): the handle is given the nodes with the global insertion
+  // indices [node_index_base, node_index_base + n_nodes()) only — its own rows plus the halo its elements touch. Host
+  // and device coordinate arrays are local to the window; element connectivity and everything the symbolic pass
+  // builds keep GLOBAL node indices (kernels read coordinates through x_global() etc.).
+  uint32_t node_index_base = 0;
   std::vector<uint32_t> node_number;
   std::vector<double> nx, ny, nz;
   NumberMap node_by_number;
@@ -485,6 +490,10 @@ struct Handle {
     return code;
   }
   size_t n_nodes() const { return node_number.size(); }
+  // device coordinate arrays addressed by GLOBAL node index (only the window may be dereferenced)
+  const double* x_global() const { return d_x.p - node_index_base; }
+  const double* y_global() const { return d_y.p - node_index_base; }
+  const double* z_global() const { return d_z.p - node_index_base; }
 };
 
 // ---- kernels' host entry points (one per translation unit) -------------------------------------

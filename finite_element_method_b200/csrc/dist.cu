@@ -187,22 +187,27 @@ pack_ghost_p2p_kernel(uint32_t n, uint32_t first_block, int key_bits, const uint
                       uint64_t* peer_arrived_flag, uint64_t epoch, uint32_t* counter, uint64_t timeout_ns,
                       uint32_t err_code, uint32_t* err) {
   if (need_consumed) wait_flag(consumed_flag, need_consumed, timeout_ns, err_code, err);
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) {
-    uint32_t blk = first_block + t;
-    uint32_t a = uint32_t(blk_key[blk] >> key_bits);
-    uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
-    uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
-    bool full = o35 != 0xFFFFFFFFu;
-    int64_t base = node_base[a];
-    double2* o = reinterpret_cast<double2*>(peer_out + size_t(t) * 36);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 6; j += 2) {
-        const double* r0 = values + base + int64_t(i) * l03 + o03 + j;
-        const double* r3 = values + base + 3 * int64_t(l03) + int64_t(i) * l35 + o35 + j;
-        o[3 * i + j / 2] = make_double2((full || j < 3) ? r0[0] : 0.0, (full || j + 1 < 3) ? r0[1] : 0.0);
-        o[3 * (i + 3) + j / 2] = full ? make_double2(r3[0], r3[1]) : make_double2(0.0, 0.0);
-      }
+  // one thread per (block, dof row): six values in, three 16-byte stores over NVLink out
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, b = t / 6u, row = t - 6u * b;
+  if (b < n) {
+    const uint32_t blk = first_block + b;
+    const uint32_t a = uint32_t(blk_key[blk] >> key_bits);
+    const uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+    const uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
+    const bool full = o35 != 0xFFFFFFFFu;
+    const int64_t base = node_base[a];
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (row < 3u) {
+      const double* r = values + base + int64_t(row) * l03 + o03;
+      for (int j = 0; j < (full ? 6 : 3); ++j) v[j] = r[j];
+    } else if (full) {
+      const double* r = values + base + 3 * int64_t(l03) + int64_t(row - 3u) * l35 + o35;
+      for (int j = 0; j < 6; ++j) v[j] = r[j];
+    }
+    double2* o = reinterpret_cast<double2*>(peer_out + size_t(b) * 36 + 6u * row);
+    o[0] = make_double2(v[0], v[1]);
+    o[1] = make_double2(v[2], v[3]);
+    o[2] = make_double2(v[4], v[5]);
   }
   signal_when_all_done(counter, peer_arrived_flag, epoch);
 }
@@ -217,21 +222,24 @@ apply_ghost_p2p_kernel(uint32_t n, const uint32_t* __restrict__ dst_block, const
                        uint64_t* peer_consumed_flag, uint32_t* counter, uint64_t timeout_ns, uint32_t err_code,
                        uint32_t* err) {
   wait_flag(arrived_flag, epoch, timeout_ns, err_code, err);
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) {
-    uint32_t blk = dst_block[t];
-    uint32_t a = uint32_t(blk_key[blk] >> key_bits);
-    uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
-    uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
-    bool full = src_full[t] != 0;  // the owner's block is full whenever any source's is
-    int64_t base = node_base[a];
-    const double* p = in + size_t(t) * 36;  // written by the peer: read through L2 (never a stale L1 line)
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < (full ? 6 : 3); ++j) values[base + int64_t(i) * l03 + o03 + j] += __ldcg(p + 6 * i + j);
-    if (full)
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 6; ++j)
-          values[base + 3 * int64_t(l03) + int64_t(i) * l35 + o35 + j] += __ldcg(p + 6 * (i + 3) + j);
+  // one thread per (received block, dof row)
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, b = t / 6u, row = t - 6u * b;
+  if (b < n) {
+    const uint32_t blk = dst_block[b];
+    const uint32_t a = uint32_t(blk_key[blk] >> key_bits);
+    const uint32_t l03 = node_len[2 * a], l35 = node_len[2 * a + 1];
+    const uint32_t o03 = blk_off[2 * blk], o35 = blk_off[2 * blk + 1];
+    const bool full = src_full[b] != 0;  // the owner's block is full whenever any source's is
+    const int64_t base = node_base[a];
+    // written by the peer: read through L2 (never a stale L1 line)
+    const double2* p = reinterpret_cast<const double2*>(in + size_t(b) * 36 + 6u * row);
+    if (row < 3u || full) {
+      const double2 v0 = __ldcg(p), v1 = __ldcg(p + 1), v2 = __ldcg(p + 2);
+      const double v[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+      double* r = row < 3u ? values + base + int64_t(row) * l03 + o03
+                           : values + base + 3 * int64_t(l03) + int64_t(row - 3u) * l35 + o35;
+      for (int j = 0; j < (full ? 6 : 3); ++j) r[j] += v[j];
+    }
   }
   signal_when_all_done(counter, peer_consumed_flag, epoch);
 }
@@ -302,7 +310,7 @@ static int32_t p2p_pack(Handle* h, cudaStream_t st) {
     double* out = reinterpret_cast<double*>(D.peer_win[r] + flag_bytes + size_t(slot) * D.peer_slot_bytes[r]) +
                   size_t(D.peer_recv_off[r]) * 36;
     const uint64_t need = epoch > uint64_t(DistState::kRing) ? epoch - DistState::kRing : 0;
-    pack_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, st>>>(
+    pack_ghost_p2p_kernel<<<div_up(uint64_t(n) * 6, 128), 128, 0, st>>>(
         n, uint32_t(D.send_first_block[r]), h->key_bits, h->blk_key.p, h->blk_off.p, h->node_len.p, h->node_base.p,
         h->values.p, out, win_consumed(D.win, W, r), need, win_arrived(D.peer_win[r], D.rank), epoch,
         D.done_count + r, p2p_timeout_ns(), 0x100u + uint32_t(r), D.d_err);
@@ -325,7 +333,7 @@ static int32_t p2p_apply(Handle* h) {
     const uint32_t n = uint32_t(D.recv_blocks[r]);
     const double* in = reinterpret_cast<const double*>(D.win + flag_bytes + size_t(slot) * D.win_slot_bytes) +
                        size_t(D.recv_off[r]) * 36;
-    apply_ghost_p2p_kernel<<<div_up(n, 128), 128, 0, h->stream>>>(
+    apply_ghost_p2p_kernel<<<div_up(uint64_t(n) * 6, 128), 128, 0, h->stream>>>(
         n, D.recv_dst_block.p + D.recv_off[r], D.recv_full.p + D.recv_off[r], h->key_bits, h->blk_key.p, h->blk_off.p,
         h->node_len.p, h->node_base.p, in, h->values.p, win_arrived(D.win, r), epoch,
         win_consumed(D.peer_win[r], W, D.rank), D.done_count + W + r, p2p_timeout_ns(), 0x200u + uint32_t(r), D.d_err);
@@ -613,6 +621,16 @@ int32_t femgpu_dist_set_ownership(femgpu_t* h, uint32_t node_index_begin, uint32
   h->dist.own_begin = node_index_begin;
   h->dist.own_end = node_index_end;
   h->dist.ownership_set = true;
+  h->symbolic_valid = false;
+  h->values_valid = false;
+  return 0;
+}
+
+int32_t femgpu_dist_set_node_window(femgpu_t* h, uint32_t first_node_index) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->n_nodes() != 0) return h->fail(FEMGPU_ERR_USAGE, "femgpu_dist_set_node_window must be called before the first node is added");
+  if (first_node_index > h->nodes_number) return h->fail(FEMGPU_ERR_USAGE, "node window starts beyond nodes_number");
+  h->node_index_base = first_node_index;
   h->symbolic_valid = false;
   h->values_valid = false;
   return 0;

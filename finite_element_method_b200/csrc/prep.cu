@@ -277,9 +277,9 @@ int32_t run_prep(Handle* h, bool validate_only) {
       FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->fork_ev, 0));
     }
     uint32_t grid = div_up(n - from, kPrepThreads);
-    const double* x = h->d_x.p;
-    const double* y = h->d_y.p;
-    const double* z = h->d_z.p;
+    const double* x = h->x_global();
+    const double* y = h->y_global();
+    const double* z = h->z_global();
     auto P = [&](int k) { return (const double*)fd.props[k].p; };
     if (f == FEMGPU_TRUSS) {
       if (validate_only)
@@ -324,9 +324,9 @@ int32_t run_prep(Handle* h, bool validate_only) {
 // after the other on stream `st` (the low-priority stream of api.cu femgpu_numeric; the buffers exist: the symbolic
 // call validated, i.e. ran the record kernels over, every element).
 int32_t run_prep_range(Handle* h, int range, cudaStream_t st) {
-  const double* x = h->d_x.p;
-  const double* y = h->d_y.p;
-  const double* z = h->d_z.p;
+  const double* x = h->x_global();
+  const double* y = h->y_global();
+  const double* z = h->z_global();
   for (int f = kFamilies - 1; f >= 0; --f) {
     FamilyDev& fd = h->fd[f];
     const uint32_t from = range ? h->range_elem_end[f][range - 1] : 0u, to = h->range_elem_end[f][range];
@@ -361,7 +361,7 @@ int32_t run_load_kernel(Handle* h, uint32_t n, const int32_t* d_family, const ui
   const FamilyDev& fp = h->fd[FEMGPU_PLATE];
   load_kernel<<<div_up(n, kPrepThreads), kPrepThreads, 0, h->stream>>>(
       n, d_family, d_elem, d_dof, d_value, fb.conn[0].p, fb.conn[1].p, fp.conn[0].p, fp.conn[1].p, fp.conn[2].p,
-      fp.conn[3].p, h->d_x.p, h->d_y.p, h->d_z.p, h->abs_tol, d_key, d_val);
+      fp.conn[3].p, h->x_global(), h->y_global(), h->z_global(), h->abs_tol, d_key, d_val);
   h->launches++;
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   return 0;
@@ -411,8 +411,8 @@ int32_t element_rotation(Handle* h, int family, size_t index, double* out_host) 
   double* d_out = reinterpret_cast<double*>(h->scratch.p + 1024);
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(d_props, hp, sizeof hp, cudaMemcpyHostToDevice, h->stream));
   rotation_kernel<<<1, 1, 0, h->stream>>>(family, uint32_t(index), fd.conn[0].p, fd.conn[1].p,
-                                          fd.conn[2].p, fd.conn[3].p, d_props, h->d_x.p, h->d_y.p,
-                                          h->d_z.p, h->rel_tol, h->abs_tol, d_out);
+                                          fd.conn[2].p, fd.conn[3].p, d_props, h->x_global(), h->y_global(),
+                                          h->z_global(), h->rel_tol, h->abs_tol, d_out);
   h->launches++;
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(out_host, d_out, 72, cudaMemcpyDeviceToHost, h->stream));

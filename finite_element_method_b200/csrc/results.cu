@@ -281,7 +281,7 @@ int32_t run_element_results(Handle* h, int family, const double* d_u, double* d_
   if (n == 0) return 0;
   const uint32_t grid = div_up(n, kResThreads);
   auto P = [&](int k) { return (const double*)fd.props[k].p; };
-  const double *x = h->d_x.p, *y = h->d_y.p, *z = h->d_z.p;
+  const double *x = h->x_global(), *y = h->y_global(), *z = h->z_global();
   if (family == FEMGPU_TRUSS)
     truss_result_kernel<<<grid, kResThreads, 0, h->stream>>>(n, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
                                                               h->abs_tol, d_u, d_out);

@@ -517,7 +517,8 @@ int32_t run_separate(Handle* h, bool direct) {
   if (bad != ~0ull) {
     // methods_for_separate_stiffness_matrix.rs:233-243
     const size_t node = size_t(bad / 6);
-    const uint32_t number = node < h->n_nodes() ? h->node_number[node] : 0u;
+    const size_t local = node - h->node_index_base;
+    const uint32_t number = node >= h->node_index_base && local < h->n_nodes() ? h->node_number[local] : 0u;
     if (direct && !h->bc.constrained[size_t(bad)])  // :49-58
       return h->fail(FEMGPU_E_NO_STIFFNESS_FOR_LOAD, std::string("There are no stiffness to withstand load ") +
                                                          dof_name(int(bad % 6)) + " applied to node " +

@@ -535,6 +535,10 @@ class FEM:
     def dist_set_ownership(self, node_index_begin: int, node_index_end: int) -> None:
         self._check(self._L.femgpu_dist_set_ownership(self._h, node_index_begin, node_index_end))
 
+    def dist_set_node_window(self, first_node_index: int) -> None:
+        """the nodes added next get the global insertion indices first_node_index, first_node_index + 1, ..."""
+        self._check(self._L.femgpu_dist_set_node_window(self._h, first_node_index))
+
     def dist_last_exchange_bytes(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._L.femgpu_dist_last_exchange_bytes(self._h, C.byref(a), C.byref(b)))
@@ -553,7 +557,10 @@ class FEM:
         insertion order plates -> beams -> trusses)."""
         n = len(mesh["x"])
         first = mesh.get("node_number_offset", 1)
-        self.add_nodes(np.arange(first, first + n, dtype=np.uint32), mesh["x"], mesh["y"], mesh["z"])
+        w0 = int(mesh.get("node_window_begin", 0))   # x / y / z hold the nodes [w0, w0 + n) of the whole model only
+        if w0:
+            self.dist_set_node_window(w0)
+        self.add_nodes(np.arange(first + w0, first + w0 + n, dtype=np.uint32), mesh["x"], mesh["y"], mesh["z"])
         num = mesh.get("element_number_offset", 1)
         pn = np.asarray(mesh["p_n"], np.uint32).reshape(4, -1)
         if pn.shape[1]:

@@ -271,6 +271,25 @@ def local_part(mesh, begin: int, end: int):
     return out
 
 
+def with_node_window(part, begin: int, end: int):
+    """A rank's part (local_part / rows=...) reduced to its node window: the nodes it owns, [begin, end), plus the halo
+    its elements touch — one contiguous index range [w0, w1). x / y / z are cut to it, `node_window_begin` = w0;
+    element connectivity keeps global node indices and `nodes_number` the size of the whole model."""
+    out = dict(part)
+    hi = [end]
+    pn = np.asarray(part["p_n"]).reshape(4, -1)
+    if pn.shape[1]:
+        hi.append(int(pn.max()) + 1)
+    for k in ("b_n1", "b_n2", "t_n1", "t_n2"):
+        if len(part[k]):
+            hi.append(int(np.max(part[k])) + 1)
+    w0, w1 = int(begin), int(max(hi))
+    out["x"], out["y"], out["z"] = part["x"][w0:w1], part["y"][w0:w1], part["z"][w0:w1]
+    out["node_window_begin"] = w0
+    out["nodes_number"] = part.get("nodes_number", len(part["x"]))
+    return out
+
+
 def hub_star(n_spokes=700, beams_every=7):
     """One hub node joined to `n_spokes` rim nodes on a sphere by trusses (every `beams_every`-th spoke
     also carries a beam). The hub's rows are far larger than a slab image, so this mesh drives the

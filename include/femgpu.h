@@ -343,8 +343,8 @@ int32_t femgpu_fp64_fma_peak(femgpu_t* h, double* tflops);
 /* Joins `world` handles (one per process/GPU) into one assembly. `nccl_unique_id` is the 128-byte
  * ncclUniqueId created by rank 0 (femgpu_dist_unique_id) and broadcast by the host. Must be called
  * before femgpu_symbolic(). Rank g owns the contiguous node-index range given by
- * femgpu_dist_set_ownership(); each rank is given every node but only the elements whose
- * lowest-index node it owns. femgpu_symbolic() is collective (NCCL all-gathers and a key exchange; it also maps
+ * femgpu_dist_set_ownership(); each rank is given the elements whose lowest-index node it owns and either every
+ * node or — femgpu_dist_set_node_window() — just the window of nodes those elements touch. femgpu_symbolic() is collective (NCCL all-gathers and a key exchange; it also maps
  * the neighbours' receive windows with CUDA IPC). femgpu_numeric() is NOT a host-level collective: contributions
  * to rows owned by another rank are summed locally, stored into the owner's HBM over NVLink by the sender's pack
  * kernel and added by the owner in (source rank, slot) order once the sender's flag is up; every rank must run the
@@ -354,6 +354,13 @@ int32_t femgpu_fp64_fma_peak(femgpu_t* h, double* tflops);
 int32_t femgpu_dist_unique_id(uint8_t out[128]);
 int32_t femgpu_dist_init(femgpu_t* h, int32_t rank, int32_t world, const uint8_t nccl_unique_id[128]);
 int32_t femgpu_dist_set_ownership(femgpu_t* h, uint32_t node_index_begin, uint32_t node_index_end);
+/* Node window of a rank: the nodes added after this call get the global insertion indices first_node_index,
+ * first_node_index + 1, ... instead of 0, 1, ... — a rank then only has to be given the nodes of its own rows plus the
+ * halo its elements touch (host ingest and node memory O(nodes / world) instead of O(nodes)); the global row of a
+ * node stays 6 * index + dof (structs/node.rs:8) and nodes_number stays the size of the WHOLE model. An element that
+ * names a node outside the window fails like one naming an unknown node. Call after femgpu_create / femgpu_reset,
+ * before the first femgpu_add_nodes. */
+int32_t femgpu_dist_set_node_window(femgpu_t* h, uint32_t first_node_index);
 /* interface traffic of the last numeric pass: bytes sent / received by this rank */
 int32_t femgpu_dist_last_exchange_bytes(femgpu_t* h, uint64_t* sent, uint64_t* received);
 /* how the last symbolic pass set the exchange up: *p2p = 1 peer windows over NVLink, 0 ncclSend/ncclRecv;

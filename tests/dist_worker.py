@@ -28,7 +28,9 @@ def main():
         mesh, width = meshes.truss_lattice(10, 10 ** 9, jitter=True), None
     n = len(mesh["x"])
     begin, end = meshes.partition_rows(mesh, world, width)[rank]
-    part = meshes.local_part(mesh, begin, end)
+    # the rank is given its own elements and only the window of nodes they touch (own rows + halo)
+    part = meshes.with_node_window(meshes.local_part(mesh, begin, end), begin, end)
+    assert len(part["x"]) < n or world == 1
 
     fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=local)
     uid = [FEM.dist_unique_id() if rank == 0 else None]
@@ -110,7 +112,7 @@ def fullsize(rank, world, local, dist, torch):
     mesh = meshes.mixed_structure(nx, ny)
     n = len(mesh["x"])
     begin, end = meshes.partition_rows(mesh, world, w)[rank]
-    part = meshes.mixed_structure(nx, ny, rows=(begin // w, end // w))
+    part = meshes.with_node_window(meshes.mixed_structure(nx, ny, rows=(begin // w, end // w)), begin, end)
     fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=local)
     uid = [FEM.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)

@@ -251,3 +251,31 @@ def test_bulk_wrappers_reject_ragged_arrays():
         f.add_beams([1, 2], [1, 2], [2, 3], [1.0, 1.0], [0.3], [1.0, 1.0], [1.0, 1.0], [1.0, 1.0], [0.0, 0.0],
                     [1.0, 1.0], [1.0, 1.0], np.zeros((3, 2)))
     assert f.counts() == (4, 0, 0, 0)
+
+
+def test_node_window_numbers_nodes_from_its_base():
+    """femgpu_dist_set_node_window: a rank is handed the nodes [base, base + n) of the whole model only; their global
+    insertion indices (hence matrix rows) start at base, the node limit still counts the whole model."""
+    m = meshes.mixed_structure(6, 5)                     # 7 x 6 = 42 nodes
+    n = len(m["x"])
+    begin, end = meshes.partition_rows(m, 3, 7)[1]       # the middle strip
+    part = meshes.with_node_window(meshes.local_part(m, begin, end), begin, end)
+    assert part["node_window_begin"] == begin and len(part["x"]) == (end - begin) + 7 and part["nodes_number"] == n
+    f = staged(n)
+    f.load_mesh(part)
+    assert f.counts() == (len(part["x"]), len(part["t_n1"]), len(part["b_n1"]), part["p_n"].shape[1])
+    # a node outside the window is unknown to this rank
+    raises(2, "Node with number 1 does not exist!", f.add_trusses, [9999], [1], [begin + 1], [1e6], [2.0])
+    # labels inside the window resolve to global indices: duplicate node pair of an existing truss is found
+    t1, t2 = int(part["t_n1"][0]) + 1, int(part["t_n2"][0]) + 1
+    raises(11, f"Truss element with node number {t1} and {t2} already exists!", f.add_trusses, [9998], [t1], [t2], [1e6], [2.0])
+    # the limit is global: the window may be filled up to nodes_number, not beyond
+    g = staged(10)
+    g._check(g._L.femgpu_dist_set_node_window(g._h, 8))
+    g.add_nodes([9, 10], [0.0, 1.0], [0.0, 0.0], [0.0, 0.0])
+    raises(5, "Nodes number could not be greater than 10!", g.add_node, 11, 2.0, 0.0, 0.0)
+    with pytest.raises(FemError):
+        g.dist_set_node_window(3)                        # only before the first node
+    g.reset(10)                                          # FEM::reset forgets the window
+    g.add_nodes(np.arange(1, 11), np.arange(10.0), np.zeros(10), np.zeros(10))
+    assert g.counts()[0] == 10
