@@ -32,6 +32,41 @@ __device__ __forceinline__ void load_xyz(const double* __restrict__ x, const dou
   p[2] = __ldg(z + i);
 }
 
+// Record stores. A thread holds its element's record (kRec doubles) in registers; written directly, one 16-byte store
+// per thread lands in 32 different 128-byte lines per warp instruction (record stride 48 / 144 / 160 B) and the LSU
+// queue throttles (ncu: lg_throttle 6.6 stalls per issue in the plate kernel). When the warp's elements are consecutive
+// (no order list) the records go through a per-warp shared-memory tile laid out exactly like the global range —
+// element-major, unpadded — and leave as fully coalesced 16-byte stores (512 contiguous bytes per instruction).
+template <int kRec>
+__device__ __forceinline__ void write_records(double* __restrict__ rec, uint32_t e, bool live, bool consecutive,
+                                              uint32_t warp_first, uint32_t warp_count, const double (&v)[kRec],
+                                              double* __restrict__ tile /* this warp's 32 * kRec doubles */) {
+  static_assert(kRec % 2 == 0, "records are written as 16-byte pairs");
+  const uint32_t lane = threadIdx.x & 31u;
+  if (!consecutive) {
+    if (live) {
+      double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kRec);
+#pragma unroll
+      for (int i = 0; i < kRec / 2; ++i) out[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    }
+    return;
+  }
+  double2* t2 = reinterpret_cast<double2*>(tile);
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < kRec / 2; ++i) t2[lane * (kRec / 2) + i] = make_double2(v[2 * i], v[2 * i + 1]);
+  }
+  __syncwarp();
+  double2* out = reinterpret_cast<double2*>(rec + size_t(warp_first) * kRec);
+  const uint32_t chunks = warp_count * uint32_t(kRec / 2);
+#pragma unroll
+  for (int j = 0; j < kRec / 2; ++j) {
+    const uint32_t c = uint32_t(j) * 32u + lane;
+    if (c < chunks) out[c] = t2[c];
+  }
+  __syncwarp();
+}
+
 template <bool kWriteErr>
 __global__ void __launch_bounds__(kPrepThreads)
 truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ n1,
@@ -40,22 +75,27 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
                   const double* __restrict__ x, const double* __restrict__ y,
                   const double* __restrict__ z, double abs_tol, double* __restrict__ rec,
                   int32_t* __restrict__ err) {
-  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  if (order) e = order[e];  // positions [from, n) of the range plan's list (Handle::prep_order)
-  double p1[3], p2[3], q[9], k00 = 0.0;
-  load_xyz(x, y, z, n1[e], p1);
-  load_xyz(x, y, z, n2[e], p2);
-  int code = truss_record(p1, p2, E[e], A[e], A2[e], abs_tol, q, &k00);
-  if (code) {
-    q[0] = q[1] = q[2] = 0.0;
-    k00 = 0.0;
+  __shared__ __align__(16) double tile[kPrepThreads * kTrussSlotDoubles];
+  const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
+  const bool live = pos < n;
+  const uint32_t e = live && order ? order[pos] : pos;  // positions [from, n) of the range plan's list (Handle::prep_order)
+  double v[kTrussSlotDoubles] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int code = 0;
+  if (live) {
+    double p1[3], p2[3], q[9], k00 = 0.0;
+    load_xyz(x, y, z, n1[e], p1);
+    load_xyz(x, y, z, n2[e], p2);
+    code = truss_record(p1, p2, E[e], A[e], A2[e], abs_tol, q, &k00);
+    if (!code) {
+      v[0] = q[0];
+      v[1] = q[1];
+      v[2] = q[2];
+      v[3] = k00;
+    }
   }
-  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kTrussSlotDoubles);
-  out[0] = make_double2(q[0], q[1]);
-  out[1] = make_double2(q[2], k00);
-  out[2] = make_double2(0.0, 0.0);
-  if (kWriteErr) err[e] = code;
+  write_records<kTrussSlotDoubles>(rec, e, live, order == nullptr, warp_first, min(32u, n > warp_first ? n - warp_first : 0u), v,
+                                   tile + (threadIdx.x >> 5) * 32 * kTrussSlotDoubles);
+  if (kWriteErr && live) err[e] = code;
 }
 
 template <bool kWriteErr>
@@ -70,24 +110,28 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, 
                  const double* __restrict__ x, const double* __restrict__ y,
                  const double* __restrict__ z, double rel_tol, double abs_tol,
                  double* __restrict__ rec, int32_t* __restrict__ err) {
-  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  if (order) e = order[e];
-  double p1[3], p2[3], r[16];
-  load_xyz(x, y, z, n1[e], p1);
-  load_xyz(x, y, z, n2[e], p2);
-  double axis[3] = {ax[e], ay[e], az[e]};
-  int code = beam_record(p1, p2, E[e], nu[e], A[e], I11[e], I22[e], I12[e], It[e], ks[e], axis,
-                         rel_tol, abs_tol, r);
-  if (code) {
+  __shared__ __align__(16) double tile[kPrepThreads * kBeamSlotDoubles];
+  const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
+  const bool live = pos < n;
+  const uint32_t e = live && order ? order[pos] : pos;
+  double v[kBeamSlotDoubles];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = 0.0;
+  for (int i = 0; i < kBeamSlotDoubles; ++i) v[i] = 0.0;
+  int code = 0;
+  if (live) {
+    double p1[3], p2[3], r[16];
+    load_xyz(x, y, z, n1[e], p1);
+    load_xyz(x, y, z, n2[e], p2);
+    double axis[3] = {ax[e], ay[e], az[e]};
+    code = beam_record(p1, p2, E[e], nu[e], A[e], I11[e], I22[e], I12[e], It[e], ks[e], axis, rel_tol, abs_tol, r);
+    if (!code) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = r[i];
+    }
   }
-  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kBeamSlotDoubles);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) out[i] = make_double2(r[2 * i], r[2 * i + 1]);
-  out[8] = make_double2(0.0, 0.0);
-  if (kWriteErr) err[e] = code;
+  write_records<kBeamSlotDoubles>(rec, e, live, order == nullptr, warp_first, min(32u, n > warp_first ? n - warp_first : 0u), v,
+                                  tile + (threadIdx.x >> 5) * 32 * kBeamSlotDoubles);
+  if (kWriteErr && live) err[e] = code;
 }
 
 template <bool kWriteErr>
@@ -99,26 +143,31 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
                   const double* __restrict__ ks, const double* __restrict__ x,
                   const double* __restrict__ y, const double* __restrict__ z, double abs_tol,
                   double* __restrict__ rec, int32_t* __restrict__ err) {
-  uint32_t e = from + blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  if (order) e = order[e];
-  double p1[3], p2[3], p3[3], p4[3], r[16], m[4];
-  load_xyz(x, y, z, n1[e], p1);
-  load_xyz(x, y, z, n2[e], p2);
-  load_xyz(x, y, z, n3[e], p3);
-  load_xyz(x, y, z, n4[e], p4);
-  int code = plate_record<kWriteErr>(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m);
-  if (code) {
+  __shared__ __align__(16) double tile[kPrepThreads * kPlateRawDoubles];
+  const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
+  const bool live = pos < n;
+  const uint32_t e = live && order ? order[pos] : pos;
+  double v[kPlateRawDoubles];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = 0.0;
-    m[0] = m[1] = m[2] = m[3] = 0.0;
+  for (int i = 0; i < kPlateRawDoubles; ++i) v[i] = 0.0;
+  int code = 0;
+  if (live) {
+    double p1[3], p2[3], p3[3], p4[3], r[16], m[4];
+    load_xyz(x, y, z, n1[e], p1);
+    load_xyz(x, y, z, n2[e], p2);
+    load_xyz(x, y, z, n3[e], p3);
+    load_xyz(x, y, z, n4[e], p4);
+    code = plate_record<kWriteErr>(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m);
+    if (!code) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = r[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[16 + i] = m[i];
+    }
   }
-  double2* out = reinterpret_cast<double2*>(rec + size_t(e) * kPlateRawDoubles);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) out[i] = make_double2(r[2 * i], r[2 * i + 1]);
-  out[8] = make_double2(m[0], m[1]);
-  out[9] = make_double2(m[2], m[3]);
-  if (kWriteErr) err[e] = code;
+  write_records<kPlateRawDoubles>(rec, e, live, order == nullptr, warp_first, min(32u, n > warp_first ? n - warp_first : 0u), v,
+                                  tile + (threadIdx.x >> 5) * 32 * kPlateRawDoubles);
+  if (kWriteErr && live) err[e] = code;
 }
 
 // Uniformly distributed loads -> nodal loads, one thread per load:
