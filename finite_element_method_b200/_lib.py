@@ -40,6 +40,7 @@ SIGNATURES = {
     "femgpu_get_csr_device": (C.c_int32, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p), i64p, i64p]),
     "femgpu_get_nonzero_coo": (C.c_int32, [H, i64p, i64p, i64p, dp]),
+    "femgpu_get_nonzero_csr": (C.c_int32, [H, i64p, i64p, i32p, dp]),
     "femgpu_rotation_elements": (C.c_int32, [H, C.c_int32, C.c_uint32, dp]),
     "femgpu_element_matrix": (C.c_int32, [H, C.c_int32, C.c_uint32, dp]),
     "femgpu_element_slots": (C.c_int32, [H, C.c_int32, C.c_uint32, i64p]),

@@ -133,6 +133,7 @@ int property_check(int family, const double* p /* props of one element */) {
 void invalidate(Handle* h) {
   h->symbolic_valid = false;
   h->values_valid = false;
+  h->nz_valid = false;
   h->sep.valid = false;
   h->sep.sky_valid = false;
   sol_invalidate(h);
@@ -650,6 +651,7 @@ static void free_device(femgpu_t* h) {
     f.cbase.release(); f.rec.release(); f.err.release();
     f.uploaded = f.validated = 0;
   }
+  h->nz_row_ptr.release(); h->nz_col.release(); h->nz_val.release(); h->nz_valid = false;
   h->blk_key.release(); h->blk_full.release(); h->blk_cptr.release(); h->contrib.release();
   h->blk_meta.release(); h->blk_order.release(); h->items.release(); h->items_c.release(); h->elist.release(); h->elist_compact.release(); h->node_blk_ptr.release(); h->node_base.release();
   h->node_len.release(); h->blk_off.release(); h->slabs.release(); h->row_ptr.release();
@@ -1037,6 +1039,15 @@ int32_t femgpu_get_nonzero_coo(femgpu_t* h, int64_t* count, int64_t* rows, int64
   if (h->device < 0) return no_device(h);
   if (!h->symbolic_valid) return h->fail(FEMGPU_ERR_USAGE, "no assembled matrix");
   return nonzero_coo(h, count, rows, cols, values);
+}
+
+int32_t femgpu_get_nonzero_csr(femgpu_t* h, int64_t* count, int64_t* row_ptr, int32_t* col_idx, double* values) {
+  if (!h) return FEMGPU_ERR_USAGE;
+  if (h->device < 0) return no_device(h);
+  if (!h->symbolic_valid || !h->values_valid) return h->fail(FEMGPU_ERR_USAGE, "no assembled matrix");
+  int32_t st = nonzero_csr(h, count, row_ptr, col_idx, values);
+  if (st) return st;
+  return dist_check(h);
 }
 
 static int32_t find_element(femgpu_t* h, int32_t family, uint32_t number, size_t* index) {

@@ -368,6 +368,13 @@ struct Handle {
   DevBuf<int64_t> row_ptr;         // [n_rows+1]
   DevBuf<int32_t> col_idx;         // [nnz]
   DevBuf<double> values;           // [nnz]
+  // the matrix compacted to its entries != 0.0 (femgpu_get_nonzero_csr), valid until the next numeric pass
+  bool nz_valid = false;
+  uint64_t nz_pass = 0;            // n_numeric the compaction was made for
+  int64_t nz_count = 0;
+  DevBuf<int64_t> nz_row_ptr;
+  DevBuf<int32_t> nz_col;
+  DevBuf<double> nz_val;
   DevBuf<uint8_t> scratch;         // CUB temp storage and sort double-buffers
   DevBuf<int32_t> d_flag;          // small device scalars
 
@@ -468,7 +475,7 @@ struct Handle {
     }
     tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(items_c); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
-    tie(col_idx); tie(values); tie(scratch); tie(d_flag);
+    tie(col_idx); tie(values); tie(scratch); tie(d_flag); tie(nz_row_ptr); tie(nz_col); tie(nz_val);
     for (auto& o : prep_order) tie(o);
     tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_dst_block); tie(dist.recv_full);
     tie(dist.remote_keys); tie(dist_scratch.i64);
@@ -508,6 +515,7 @@ int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);  
 int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
 int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host);   // symbolic.cu
 int32_t nonzero_coo(Handle* h, int64_t* count, int64_t* rows, int64_t* cols, double* vals);  // symbolic.cu
+int32_t nonzero_csr(Handle* h, int64_t* count, int64_t* row_ptr, int32_t* cols, double* vals);  // symbolic.cu
 int32_t run_load_kernel(Handle* h, uint32_t n, const int32_t* d_family, const uint32_t* d_elem, const int32_t* d_dof,
                         const double* d_value, uint32_t* d_key, double* d_val);  // prep.cu
 int32_t forces_flush(Handle* h);                         // separate.cu: bc -> sep.d_constrained / d_disp / d_force

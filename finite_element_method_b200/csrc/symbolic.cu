@@ -26,6 +26,10 @@ namespace {
 // stream the scratch allocations of the running pass are ordered on (set by the entry points below)
 thread_local cudaStream_t t_tmp_stream = nullptr;
 
+struct CastToI64 {
+  __host__ __device__ int64_t operator()(int32_t v) const { return int64_t(v); }
+};
+
 struct Tmp {  // RAII scratch allocation from the stream-ordered pool
   void* p = nullptr;
   cudaStream_t s = nullptr;
@@ -815,6 +819,50 @@ __global__ void nz_write_kernel(int64_t nnz, int64_t n_rows, const double* __res
   vals[p] = v;
 }
 
+// ---- compaction to the entries != 0.0, CSR in place of the COO above (femgpu_get_nonzero_csr) ----
+// Rows of a structural model are short (18-54 stored entries): eight lanes share a row.
+constexpr int kNzLanes = 8;
+__global__ void __launch_bounds__(256)
+nz_row_count_kernel(int64_t row_begin, int64_t row_end, const int64_t* __restrict__ row_ptr,
+                    const double* __restrict__ values, int32_t* __restrict__ cnt /* [n_rows + 1], zeroed */) {
+  const int64_t row = row_begin + (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / kNzLanes;
+  const uint32_t sub = threadIdx.x & (kNzLanes - 1);
+  int c = 0;
+  if (row < row_end) {
+    const int64_t b = row_ptr[row], e = row_ptr[row + 1];
+    for (int64_t i = b + sub; i < e; i += kNzLanes) c += values[i] != 0.0 ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = kNzLanes / 2; d > 0; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+  if (row < row_end && sub == 0) cnt[row] = c;
+}
+__global__ void __launch_bounds__(256)
+nz_row_fill_kernel(int64_t row_begin, int64_t row_end, const int64_t* __restrict__ row_ptr,
+                   const int32_t* __restrict__ col_idx, const double* __restrict__ values,
+                   const int64_t* __restrict__ nz_ptr, int32_t* __restrict__ out_col, double* __restrict__ out_val) {
+  const int64_t row = row_begin + (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / kNzLanes;
+  const uint32_t lane = threadIdx.x & 31u, sub = lane & (kNzLanes - 1), shift = lane & ~uint32_t(kNzLanes - 1);
+  const bool live = row < row_end;
+  const int64_t b = live ? row_ptr[row] : 0, e = live ? row_ptr[row + 1] : 0;
+  int64_t w = live ? nz_ptr[row] : 0;
+  // the four row groups of a warp advance together (ballots are warp-wide): as many steps as the longest row needs
+  int64_t steps = (e - b + kNzLanes - 1) / kNzLanes;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, d));
+  for (int64_t k = 0; k < steps; ++k) {
+    const int64_t i = b + k * kNzLanes + sub;
+    const double v = i < e ? values[i] : 0.0;
+    const bool keep = v != 0.0;
+    const uint32_t mask = (__ballot_sync(0xFFFFFFFFu, keep) >> shift) & ((1u << kNzLanes) - 1u);
+    if (keep) {
+      const int64_t p = w + __popc(mask & ((1u << sub) - 1u));
+      out_col[p] = col_idx[i];
+      out_val[p] = v;
+    }
+    w += __popc(mask);
+  }
+}
+
 // placeholder contributions for blocks other ranks will add to (multi-GPU): they only create the
 // slot; the assembly kernel skips family 3
 __global__ void remote_contrib_kernel(uint32_t n, const uint64_t* __restrict__ remote_keys, int64_t base,
@@ -1428,6 +1476,61 @@ int32_t element_slots(Handle* h, int family, size_t index, int64_t* out_host) {
   SYM_CHECK(cudaGetLastError());
   SYM_CHECK(cudaMemcpyAsync(out_host, d_out.p, size_t(n) * n * 8, cudaMemcpyDeviceToHost, h->stream));
   SYM_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// The assembled matrix compacted to its entries != 0.0, as CSR (same rows, columns ascending): computed on the device
+// once per numeric pass and kept in HBM; `count` only -> no copy. Multi-GPU: the rows this rank owns (the others empty).
+int32_t nonzero_csr(Handle* h, int64_t* count, int64_t* row_ptr, int32_t* cols, double* vals) {
+  SYM_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  t_tmp_stream = s;
+  const int64_t n_rows = h->n_rows;
+  if (!h->nz_valid || h->nz_pass != h->n_numeric) {
+    int64_t rb = 0, re = n_rows;
+    if (h->dist.enabled && h->dist.ownership_set) {
+      rb = 6 * int64_t(h->dist.own_begin);
+      re = 6 * int64_t(h->dist.own_end);
+    }
+    Tmp cnt;
+    SYM_CHECK(cnt.alloc((size_t(n_rows) + 1) * 4));
+    SYM_CHECK(cudaMemsetAsync(cnt.p, 0, (size_t(n_rows) + 1) * 4, s));
+    SYM_CHECK(h->nz_row_ptr.reserve(size_t(n_rows) + 1));
+    const uint32_t grid = div_up(uint64_t(re - rb) * kNzLanes, 256);
+    if (re > rb && h->nnz) {
+      nz_row_count_kernel<<<grid, 256, 0, s>>>(rb, re, h->row_ptr.p, h->values.p, cnt.as<int32_t>());
+      h->launches++;
+    }
+    {
+      cub::TransformInputIterator<int64_t, CastToI64, const int32_t*> it(cnt.as<int32_t>(), CastToI64());
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, it, h->nz_row_ptr.p, int(n_rows + 1), s);
+      Tmp t;
+      SYM_CHECK(t.alloc(tb));
+      SYM_CHECK(cub::DeviceScan::ExclusiveSum(t.p, tb, it, h->nz_row_ptr.p, int(n_rows + 1), s));
+    }
+    int64_t nz = 0;
+    SYM_CHECK(cudaMemcpyAsync(&nz, h->nz_row_ptr.p + n_rows, 8, cudaMemcpyDeviceToHost, s));
+    SYM_CHECK(cudaStreamSynchronize(s));
+    SYM_CHECK(h->nz_col.reserve(size_t(nz) + 1));
+    SYM_CHECK(h->nz_val.reserve(size_t(nz) + 1));
+    if (nz) {
+      nz_row_fill_kernel<<<grid, 256, 0, s>>>(rb, re, h->row_ptr.p, h->col_idx.p, h->values.p, h->nz_row_ptr.p,
+                                              h->nz_col.p, h->nz_val.p);
+      h->launches++;
+      SYM_CHECK(cudaGetLastError());
+    }
+    h->nz_count = nz;
+    h->nz_pass = h->n_numeric;
+    h->nz_valid = true;
+  }
+  if (count) *count = h->nz_count;
+  if (row_ptr) SYM_CHECK(cudaMemcpyAsync(row_ptr, h->nz_row_ptr.p, (size_t(n_rows) + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (cols && h->nz_count)
+    SYM_CHECK(cudaMemcpyAsync(cols, h->nz_col.p, size_t(h->nz_count) * 4, cudaMemcpyDeviceToHost, s));
+  if (vals && h->nz_count)
+    SYM_CHECK(cudaMemcpyAsync(vals, h->nz_val.p, size_t(h->nz_count) * 8, cudaMemcpyDeviceToHost, s));
+  SYM_CHECK(cudaStreamSynchronize(s));
   return 0;
 }
 

@@ -266,6 +266,19 @@ class FEM:
         self._check(self._L.femgpu_get_csr_device(self._h, *[C.byref(x) for x in p], C.byref(rb), C.byref(re)))
         return tuple(x.value for x in p), (int(rb.value), int(re.value))
 
+    def nonzero_csr(self, out=None):
+        """The reference's stored set — entries != 0.0 — as CSR (row_ptr, col_idx, values); compacted on the device.
+        out = (row_ptr, col_idx, values) host arrays to fill (values / col_idx at least `count` long; e.g. pinned)."""
+        cnt = C.c_int64()
+        self._check(self._L.femgpu_get_nonzero_csr(self._h, C.byref(cnt), None, None, None))
+        n = int(cnt.value)
+        if out is None:
+            out = (np.empty(self.n_rows + 1, np.int64), np.empty(n, np.int32), np.empty(n, np.float64))
+        rp, ci, v = out
+        assert len(rp) >= self.n_rows + 1 and len(ci) >= n and len(v) >= n
+        self._check(self._L.femgpu_get_nonzero_csr(self._h, C.byref(cnt), _p(rp, _lib.i64p), _p(ci, _lib.i32p), _p(v, _lib.dp)))
+        return rp[:self.n_rows + 1], ci[:n], v[:n]
+
     def nonzero_coo(self):
         """The reference's value-dependent pattern: entries != 0.0, sorted by (row, col)."""
         cnt = C.c_int64()

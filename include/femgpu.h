@@ -182,6 +182,14 @@ int32_t femgpu_get_csr(femgpu_t* h, int64_t* row_ptr, int32_t* col_idx, double* 
 int32_t femgpu_get_csr_device(femgpu_t* h, const int64_t** row_ptr, const int32_t** col_idx,
                               const double** values, int64_t* row_begin, int64_t* row_end);
 
+/* The assembled matrix compacted to the entries that are != 0.0 — exactly the set the reference's position-keyed map
+ * holds (its add_* loops skip exact zeros, methods_for_truss/beam/plate_data_handle.rs:115 / :129 / :204) — as CSR:
+ * row_ptr [n_rows + 1], col_idx / values [count], columns ascending inside a row. The compaction runs on the device once
+ * per numeric pass and stays in HBM; the call copies what is asked for (any pointer may be NULL; NULL arrays = count
+ * only). For a flat plate mesh this is 36 % of the structural pattern: the cheap way to bring K to the host.
+ * Multi-GPU: the rows this rank owns (after the interface exchange); all other rows are empty. */
+int32_t femgpu_get_nonzero_csr(femgpu_t* h, int64_t* count, int64_t* row_ptr, int32_t* col_idx, double* values);
+
 /* Compacts to the reference's value-dependent pattern (entries that are != 0.0) as sorted COO.
  * Call with NULL arrays to get the count. */
 int32_t femgpu_get_nonzero_coo(femgpu_t* h, int64_t* count, int64_t* rows, int64_t* cols,

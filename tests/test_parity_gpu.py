@@ -147,6 +147,32 @@ def test_reference_pattern_is_reproduced_by_compaction(O):
         fem.close()
 
 
+@pytest.mark.parametrize("name", ["truss-cube-27-nodes", "plate-flat", "folded-plate-flat-and-tilted", "mixed", "hub-star-unstaged-slab"])
+def test_nonzero_csr_is_the_structural_csr_without_its_zeros(name):
+    """femgpu_get_nonzero_csr (compaction on the device, what the e2e path reads back) against the structural CSR
+    filtered on the host: identical row pointers, columns and values, bit for bit; recomputed after a new pass."""
+    if name not in SMALL:
+        pytest.skip(f"no mesh {name}")
+    mesh = SMALL[name]()
+    fem, n_rows, nnz = assemble(mesh)
+    rp, ci, v = fem.csr()
+    keep = v != 0.0
+    rows = np.repeat(np.arange(n_rows), np.diff(rp))
+    want_rp = np.zeros(n_rows + 1, np.int64)
+    np.add.at(want_rp, rows[keep] + 1, 1)
+    want_rp = np.cumsum(want_rp)
+    g_rp, g_ci, g_v = fem.nonzero_csr()
+    assert np.array_equal(g_rp, want_rp)
+    assert np.array_equal(g_ci, ci[keep]) and np.array_equal(g_v, v[keep])
+    assert 0 < len(g_v) <= nnz
+    r, c, vv = fem.nonzero_coo()                      # the older COO form agrees
+    assert np.array_equal(c, g_ci) and np.array_equal(vv, g_v) and np.array_equal(r, rows[keep])
+    fem.numeric()                                     # a new pass invalidates the cached compaction
+    g2 = fem.nonzero_csr()
+    assert np.array_equal(g2[0], g_rp) and np.array_equal(g2[2], g_v)
+    fem.close()
+
+
 def test_element_matrices_match_oracle_and_golden(O):
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "element_golden.json")))
     for case in gold["truss"]:

