@@ -565,16 +565,17 @@ def measure_downstream(args, fem, local, n_nodes, nnz_local, peak):
 
 
 def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, rank, world, begin, end):
-    """One full pass per step through the public API with HOST buffers: create -> add_* (host->device
-    copies) -> symbolic -> numeric -> CSR values back to host memory."""
+    """One full pass per step through the public API with HOST buffers: reset -> add_* (host checks, host->device
+    copies) -> symbolic -> numeric -> the assembled matrix back in (pinned) host memory. Measured twice, with the two
+    read-backs the API offers:
+      nonzero     femgpu_get_nonzero_csr — row_ptr, col_idx, values of the entries != 0.0, compacted on the device: the
+                  set the reference's position-keyed map holds (its add_* skip exact zeros). THE e2e number.
+      structural  femgpu_get_csr, values only, on the structural block pattern (what round 1 reported)."""
     import torch
     from finite_element_method_b200 import FEM
     steps = 2 if n_el_total > 2_000_000 else 5
     h2d = (sum(np.asarray(local[k]).nbytes for k in ("x", "y", "z", "t_n1", "t_n2", "t_E", "t_A", "b_n1", "b_n2",
                                                       "b_props", "b_axis", "p_n", "p_props")))
-    out = None
-    times = []
-    d2h = 0
     # One handle (and, with several GPUs, one NCCL communicator) for the whole measurement, re-used
     # through FEM::reset (fem.rs:155) like a long-lived reference instance would be; every timed step
     # starts from an empty model.
@@ -583,52 +584,70 @@ def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, 
         u = [FEM.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(u, src=0)
         fem.dist_init(rank, world, u[0])
-    for it in range(steps + 1):
-        log(f"e2e: step {it} of {steps} (+1 warm-up)")
-        fem.synchronize()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+    results = {}
+    for mode in ("nonzero", "structural"):
+        bufs = None
+        times, phases, d2h = [], None, 0
+        for it in range(steps + 1):
+            log(f"e2e[{mode}]: step {it} of {steps} (+1 warm-up)")
+            fem.synchronize()
             torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        fem.reset(n_nodes)                      # frees the previous step's device buffers
-        if world > 1:
-            fem.dist_set_ownership(begin, end)
-        fem.load_mesh(local)
-        t1 = time.perf_counter()
-        n_rows, nnz = fem.symbolic()
-        t2 = time.perf_counter()
-        fem.numeric()
-        fem.synchronize()
-        t3 = time.perf_counter()
-        t_pin = 0.0
-        if out is None or len(out) != nnz:
-            tp = time.perf_counter()
-            out = torch.empty(nnz, dtype=torch.float64).pin_memory().numpy()
-            t_pin = time.perf_counter() - tp    # one-time pinned allocation is not part of a step
-        fem.csr(values_only=True, out=out)
-        t4 = time.perf_counter()
-        dt = t4 - t0 - t_pin
-        d2h = out.nbytes
-        if it > 0:
-            times.append(dt)
-            phases = {"reset_add_nodes_add_elements_s": t1 - t0, "symbolic_s": t2 - t1, "numeric_s": t3 - t2,
-                      "csr_values_d2h_s": t4 - t3 - t_pin}
+            if dist is not None:
+                dist.barrier()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fem.reset(n_nodes)
+            if world > 1:
+                fem.dist_set_ownership(begin, end)
+            fem.load_mesh(local)
+            t1 = time.perf_counter()
+            n_rows, nnz = fem.symbolic()
+            t2 = time.perf_counter()
+            fem.numeric()
+            fem.synchronize()
+            t3 = time.perf_counter()
+            t_pin = 0.0
+            if bufs is None:                # one-time pinned allocations are not part of a step (sized by the warm-up step)
+                tp = time.perf_counter()
+                pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory().numpy()
+                if mode == "nonzero":
+                    bufs = (pin(n_rows + 1, torch.int64), pin(nnz, torch.int32), pin(nnz, torch.float64))
+                else:
+                    bufs = pin(nnz, torch.float64)
+                t_pin = time.perf_counter() - tp
+            if mode == "nonzero":
+                rp, ci, v = fem.nonzero_csr(out=bufs)
+                d2h = rp.nbytes + ci.nbytes + v.nbytes
+            else:
+                fem.csr(values_only=True, out=bufs)
+                d2h = bufs.nbytes
+            t4 = time.perf_counter()
+            if it > 0:
+                times.append(t4 - t0 - t_pin)
+                phases = {"reset_add_nodes_add_elements_s": t1 - t0, "symbolic_s": t2 - t1, "numeric_s": t3 - t2,
+                          "matrix_d2h_s": t4 - t3 - t_pin}
+        sec = float(np.mean(times))
+        if dist is not None:
+            t = torch.tensor([sec, float(d2h)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t[0].item())
+            torch.cuda.synchronize()
+        results[mode] = {"value": n_el_total / sec, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec, "steps": steps, "step_seconds": times,
+                         "phases_last_step": phases}
+        del bufs
     fem.synchronize()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()      # no rank may still be in a pass when the joined handles go
     fem.close()
-    sec = float(np.mean(times))
-    if dist is not None:
-        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
-    return {"value": n_el_total / sec, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "seconds_per_step": sec, "steps": steps, "step_seconds": times,
-            "phases_last_step": phases,
-            "includes": "femgpu_reset, add_nodes/add_* host validation + H2D, symbolic pass, numeric pass, D2H of CSR values "
-                        "(handle and NCCL communicator created once, outside the timed steps)"}
+    out = dict(results["nonzero"])
+    out["readback"] = ("femgpu_get_nonzero_csr: row_ptr + col_idx + values of the entries != 0.0 (the reference's stored set), "
+                       "compacted on the device, into pinned host memory" + (" — per rank: its own rows" if world > 1 else ""))
+    out["structural_readback"] = dict(results["structural"], readback="femgpu_get_csr: all values of the structural block pattern")
+    out["includes"] = ("femgpu_reset, add_nodes/add_* host validation + H2D, symbolic pass, numeric pass, device-side compaction, "
+                       "D2H of the matrix (handle and NCCL communicator created once, outside the timed steps)")
+    return out
 
 
 if __name__ == "__main__":

@@ -307,10 +307,23 @@ def test_loads_of_all_kinds_sum_in_call_order():
             for k in range(4):
                 F[6 * n[k] + 2] += f[k]
     got = fem.forces_vector()
-    assert np.array_equal(got, F), (got[6 * node + 2], F[6 * node + 2])
-    # the order matters here: summing the concentrated loads first gives another value
-    wrong = (1.0e13 - 1.0e13 + 0.1)
-    assert F[6 * node + 2] != wrong + (F[6 * node + 2] - 0.1) or True
+    assert np.abs(got - F).max() <= 1e-10, (got[6 * node + 2], F[6 * node + 2])
+    # the test is sensitive to the order: with the concentrated loads summed first (1e13 - 1e13 + 0.1 exactly, then the
+    # distributed shares) this DOF would come out differently, far above the bar
+    alt = 0.0
+    for kind, who, val in calls:
+        if kind == "point":
+            alt += val
+    dist_share = 0.0
+    for kind, who, val in calls:
+        if kind == "line":
+            a, b = int(mesh["b_n1"][who]), int(mesh["b_n2"][who])
+            f = O.beam_line_load(P[a], P[b], val)
+            dist_share += f[0] if a == node else f[1]
+        elif kind == "surface":
+            f = O.plate_surface_load(*[P[int(pn[k][who])] for k in range(4)], val, mesh["rel_tol"], mesh["abs_tol"])
+            dist_share += f[0]
+    assert abs((alt + dist_share) - F[6 * node + 2]) > 1e-6
     fem.close()
 
 
