@@ -164,7 +164,7 @@ __device__ __forceinline__ void truss_block(double q0, double q1, double q2, dou
 }
 
 // ------------------------------------------------------------------------------------------
-// Beam: record (16 doubles) = r[9], d2, s_u, s_v, s_thu, s_thv, s_thw, 0
+// Beam: record (16 doubles) = r[9], d2, s_u, s_v, s_thu, s_thv, s_thw, identity flag (r == I)
 //   d2 = dh2/dr / J (d1 = -d2), s_* = c_* * J * alpha            structs/beam.rs:495-563
 // ------------------------------------------------------------------------------------------
 
@@ -275,7 +275,12 @@ __device__ inline int beam_record(const double p1[3], const double p2[3], double
   rec[12] = (shear_modulus * it) * jac * alpha;
   rec[13] = (young_modulus * i22_p) * jac * alpha;
   rec[14] = (young_modulus * i11_p) * jac * alpha;
-  rec[15] = 0.0;
+  // r == I exactly (a member along +x whose principal axes are the global y and z): beam_block then adds the ten
+  // entries of the local block instead of evaluating the two 3x3 sandwiches (the products with 1.0 and 0.0 are exact,
+  // so the general path would add the same numbers)
+  bool ident = rec[0] == 1.0 && rec[4] == 1.0 && rec[8] == 1.0 && rec[1] == 0.0 && rec[2] == 0.0 && rec[3] == 0.0 &&
+               rec[5] == 0.0 && rec[6] == 0.0 && rec[7] == 0.0;
+  rec[15] = ident ? 1.0 : 0.0;
   return EV_OK;
 }
 
@@ -321,6 +326,21 @@ __device__ __forceinline__ void beam_block(const double* __restrict__ rec, int l
   double l33 = dd * s_thu;
   double l44 = (hh * hh) * s_v + dd * s_thv;
   double l55 = (hh * hh) * s_v + dd * s_thw;
+  // every lane that is in the beam branch right now has an identity rotation (warp-uniform decision, so a frame with
+  // members in all directions does not pay for both paths)
+  if (__all_sync(__activemask(), rec[15] != 0.0)) {
+    acc[0] += l00;
+    acc[7] += l11;
+    acc[14] += l22;
+    acc[21] += l33;
+    acc[28] += l44;
+    acc[35] += l55;
+    acc[11] += l15;  // k[v][thw]
+    acc[16] += l24;  // k[w][thv]
+    acc[26] += l42;  // k[thv][w]
+    acc[31] += l51;  // k[thw][v]
+    return;
+  }
   sandwich_diag(r, l00, l11, l22, acc, 0, 0);
   sandwich_diag(r, l33, l44, l55, acc, 3, 3);
   // rows (u,v,w) x cols (thu,thv,thw): X[1][2] = k[v][thw], X[2][1] = k[w][thv]
