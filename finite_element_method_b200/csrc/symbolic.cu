@@ -199,12 +199,16 @@ __global__ void slab_kernel(uint32_t n_slabs, uint32_t quota, uint32_t n_nodes,
   slabs[k] = d;
 }
 
+// relative cost of one contribution per family (truss, beam, plate), used to balance the per-lane work lists; the
+// compile-time defaults can be overridden per process (FEMGPU_COST_T / _B / _P, tuning knob)
+__device__ uint32_t g_cost[3] = {kCostTruss, kCostBeam, kCostPlate};
+
 __device__ __forceinline__ uint32_t block_cost(const uint32_t* __restrict__ cptr,
                                                const uint32_t* __restrict__ contrib, uint32_t i) {
   uint32_t cost = 0;
   for (uint32_t c = cptr[i]; c < cptr[i + 1]; ++c) {
     uint32_t f = contrib[c] >> 30;
-    cost += (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
+    cost += f < 3u ? g_cost[f] : 0u;
   }
   return min(cost, 65535u);
 }
@@ -245,7 +249,7 @@ __global__ void ordered_count_kernel(uint32_t n_blocks, const uint32_t* __restri
 // Only blocks at least 25 % heavier than W are split (a split costs a merge round: 72 shuffles).
 // One thread per slab; items are written to the dense [slab][thread] table.
 __device__ __forceinline__ uint32_t family_cost(uint32_t f) {
-  return (f == FEMGPU_PLATE) ? kCostPlate : (f == FEMGPU_BEAM ? kCostBeam : (f == FEMGPU_TRUSS ? kCostTruss : 0u));
+  return f < 3u ? g_cost[f] : 0u;
 }
 // How the contributions of a block split over kk lanes are dealt to its chunks: every family
 // (execution order: placeholders, plates, beams, trusses) is spread evenly, chunk j taking a
@@ -256,7 +260,7 @@ __device__ __forceinline__ uint32_t family_cost(uint32_t f) {
 // trusses) costs its warp six loop trips, two chunks of (2 plates + beam + truss) cost it four.
 // cnt[g][j] = contributions of family group g in chunk j. Every chunk is non-empty when kk <= total.
 __device__ __forceinline__ void chunk_family_counts(const uint32_t n[4], uint32_t kk, uint32_t cnt[4][kMaxChunks]) {
-  const uint32_t cost[4] = {0u, kCostPlate, kCostBeam, kCostTruss};
+  const uint32_t cost[4] = {0u, g_cost[FEMGPU_PLATE], g_cost[FEMGPU_BEAM], g_cost[FEMGPU_TRUSS]};
   uint32_t load[kMaxChunks], items[kMaxChunks];
   for (uint32_t j = 0; j < uint32_t(kMaxChunks); ++j) load[j] = items[j] = 0;
   for (int g = 0; g < 4; ++g) {
@@ -1192,6 +1196,13 @@ int32_t run_symbolic(Handle* h) {
             std::chrono::duration<double, std::milli>(now - t_last).count());
     t_last = now;
   };
+  {
+    uint32_t cost[3] = {kCostTruss, kCostBeam, kCostPlate};
+    const char* names[3] = {"FEMGPU_COST_T", "FEMGPU_COST_B", "FEMGPU_COST_P"};
+    for (int f = 0; f < 3; ++f)
+      if (const char* q = getenv(names[f])) cost[f] = uint32_t(std::max(1, atoi(q)));
+    SYM_CHECK(cudaMemcpyToSymbolAsync(g_cost, cost, sizeof cost, 0, cudaMemcpyHostToDevice, s));
+  }
   const uint32_t N = h->nodes_number;
   h->n_rows = 6 * int64_t(N);
   const int64_t NC = h->n_contrib;
