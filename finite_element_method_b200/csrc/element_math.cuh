@@ -46,13 +46,38 @@ __device__ __forceinline__ double clip_tol(double v, double abs_tol) {
 // sin(+-0) = +-0 and cos(+-0) = 1 hold exactly, so skipping the library call there returns the same bits; it matters
 // because structural models are full of such inputs (members along +x, flat plates with the normal along +z, sections
 // given in their principal axes) and a double-precision acos / sincos costs a few hundred instructions.
-__device__ __forceinline__ double acos_x(double c) { return c == 1.0 ? 0.0 : acos(c); }
+// `trig` (may be null) is the per-CTA table of trig_table_init(): the library's own results at two more arguments that
+// axis-aligned structures produce all the time — acos(0) (a member along y or z against the x axis) and acos(-1) — and
+// the sin / cos of those two angles, computed once per CTA with the same functions, so a hit returns the same bits.
+//   trig = { acos(0), sin(acos(0)), cos(acos(0)), acos(-1), sin(acos(-1)), cos(acos(-1)) }
+__device__ __forceinline__ void trig_table_init(double* trig, double opaque_zero) {
+  // opaque_zero is 0.0 computed from a kernel argument, so nothing here is folded at compile time (by a host libm)
+  const double a1 = acos(opaque_zero), a2 = acos(opaque_zero - 1.0);
+  trig[0] = a1;
+  sincos(a1, &trig[1], &trig[2]);
+  trig[3] = a2;
+  sincos(a2, &trig[4], &trig[5]);
+}
+__device__ __forceinline__ double acos_x(double c, const double* trig = nullptr) {
+  if (c == 1.0) return 0.0;
+  if (trig) {
+    if (c == 0.0) return trig[0];
+    if (c == -1.0) return trig[3];
+  }
+  return acos(c);
+}
 __device__ __forceinline__ double atan_x(double t) { return t == 0.0 ? t : atan(t); }
 __device__ __forceinline__ double sin_x(double a) { return a == 0.0 ? a : sin(a); }
-__device__ __forceinline__ void sincos_x(double a, double* s, double* c) {
+__device__ __forceinline__ void sincos_x(double a, double* s, double* c, const double* trig = nullptr) {
   if (a == 0.0) {
     *s = a;
     *c = 1.0;
+  } else if (trig && a == trig[0]) {
+    *s = trig[1];
+    *c = trig[2];
+  } else if (trig && a == trig[3]) {
+    *s = trig[4];
+    *c = trig[5];
   } else {
     sincos(a, s, c);
   }
@@ -83,11 +108,11 @@ __device__ __forceinline__ void cross3(const double a[3], const double b[3], dou
 // a x b by acos(a.b/(|a||b|)); cos, sin and every entry clipped by abs_tol; zero axis when the
 // vectors are (anti)parallel.
 __device__ inline void rotation_align(const double a[3], const double b[3], double abs_tol,
-                                      double q[9]) {
+                                      double q[9], const double* trig = nullptr) {
   double na = norm3(a), nb = norm3(b);
   double cosv = dot3(a, b) / (na * nb);
   cosv = cosv > 1.0 ? 1.0 : (cosv < -1.0 ? -1.0 : cosv);
-  double angle = acos_x(cosv);
+  double angle = acos_x(cosv, trig);
   double ax[3];
   cross3(a, b, ax);
   double n = norm3(ax);
@@ -98,7 +123,7 @@ __device__ inline void rotation_align(const double a[3], const double b[3], doub
     z = ax[2] / n;
   }
   double sn, cs;
-  sincos_x(angle, &sn, &cs);  // one argument reduction for both (the values are those of sin() and cos())
+  sincos_x(angle, &sn, &cs, trig);  // one argument reduction for both (the values are those of sin() and cos())
   double c = clip_tol(cs, abs_tol);
   double s = clip_tol(sn, abs_tol);
   double t = 1.0 - c;
@@ -128,7 +153,7 @@ __device__ __forceinline__ double bar_jacobian(double len) {
 // ------------------------------------------------------------------------------------------
 __device__ inline int truss_record(const double p1[3], const double p2[3], double young_modulus,
                                    double area, double area_2 /* NaN = None */, double abs_tol,
-                                   double q[9], double* k00) {
+                                   double q[9], double* k00, const double* trig = nullptr) {
   if (young_modulus <= 0.0) return EV_YOUNG;
   if (area <= 0.0) return EV_AREA;
   bool has2 = !isnan(area_2);
@@ -136,7 +161,7 @@ __device__ inline int truss_record(const double p1[3], const double p2[3], doubl
   double v[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
   double len = norm3(v);
   double dir[3] = {len, 0.0, 0.0};
-  rotation_align(v, dir, abs_tol, q);
+  rotation_align(v, dir, abs_tol, q, trig);
   const double r = 0.0, alpha = 2.0;
   double jac = bar_jacobian(len);
   double inv_j = 1.0 / jac;
@@ -208,7 +233,7 @@ __device__ inline int beam_record(const double p1[3], const double p2[3], double
                                   double poisson_ratio, double area, double i11, double i22,
                                   double i12, double it, double shear_factor,
                                   const double axis1[3], double rel_tol, double abs_tol,
-                                  double rec[16]) {
+                                  double rec[16], const double* trig = nullptr) {
   // structs/beam.rs:63-117
   if (young_modulus <= 0.0) return EV_YOUNG;
   if (poisson_ratio <= 0.0) return EV_POISSON;
@@ -230,7 +255,7 @@ __device__ inline int beam_record(const double p1[3], const double p2[3], double
   double len = norm3(v);
   double dir[3] = {len, 0.0, 0.0};
   double qi[9];
-  rotation_align(v, dir, abs_tol, qi);
+  rotation_align(v, dir, abs_tol, qi, trig);
   double tp[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -243,13 +268,13 @@ __device__ inline int beam_record(const double p1[3], const double p2[3], double
   const double ez[3] = {0.0, 0.0, 1.0};
   double cosv = dot3(ez, tp) / (norm3(ez) * norm3(tp));
   cosv = cosv > 1.0 ? 1.0 : (cosv < -1.0 ? -1.0 : cosv);
-  double total_angle = angle + acos_x(cosv);
+  double total_angle = angle + acos_x(cosv, trig);
   double c_x = clip_tol(v[0] / len, abs_tol);
   double c_y = clip_tol(v[1] / len, abs_tol);
   double c_z = clip_tol(v[2] / len, abs_tol);
   double c_xz = clip_tol(sqrt(c_x * c_x + c_z * c_z), abs_tol);
   double sn, cs;
-  sincos_x(total_angle, &sn, &cs);
+  sincos_x(total_angle, &sn, &cs, trig);
   double c = clip_tol(cs, abs_tol);
   double s = clip_tol(sn, abs_tol);
   bool nz = c_xz != 0.0;
@@ -356,14 +381,14 @@ __device__ __forceinline__ void beam_block(const double* __restrict__ rec, int l
 
 // quadrilateral_4n_element_functions.rs:131-171
 __device__ inline void plate_rotation(const double p2[3], const double p3[3], const double p4[3],
-                                      double abs_tol, double q[9]) {
+                                      double abs_tol, double q[9], const double* trig = nullptr) {
   double e34[3] = {p4[0] - p3[0], p4[1] - p3[1], p4[2] - p3[2]};
   double e32[3] = {p2[0] - p3[0], p2[1] - p3[1], p2[2] - p3[2]};
   double n[3];
   cross3(e34, e32, n);
   double len = norm3(n);
   double dir[3] = {0.0, 0.0, len};
-  rotation_align(n, dir, abs_tol, q);
+  rotation_align(n, dir, abs_tol, q, trig);
 }
 
 __device__ __forceinline__ void mat3_vec(const double q[9], const double d[3], double o[3]) {
@@ -463,7 +488,7 @@ template <bool kCheck = true>
 __device__ inline int plate_record(const double p1[3], const double p2[3], const double p3[3],
                                    const double p4[3], double young_modulus, double poisson_ratio,
                                    double thickness, double shear_factor, double abs_tol,
-                                   double rec[16], double mat[4]) {
+                                   double rec[16], double mat[4], const double* trig = nullptr) {
   // structs/plate.rs:58-158
   if (kCheck) {
     if (young_modulus <= 0.0) return EV_YOUNG;
@@ -495,7 +520,7 @@ __device__ inline int plate_record(const double p1[3], const double p2[3], const
       return EV_NOT_ON_PLANE;
   }
   double* q = rec;
-  plate_rotation(p2, p3, p4, abs_tol, q);
+  plate_rotation(p2, p3, p4, abs_tol, q, trig);
   double d1[3] = {p1[0] - p3[0], p1[1] - p3[1], p1[2] - p3[2]};
   double d2[3] = {p2[0] - p3[0], p2[1] - p3[1], p2[2] - p3[2]};
   double d4[3] = {p4[0] - p3[0], p4[1] - p3[1], p4[2] - p3[2]};

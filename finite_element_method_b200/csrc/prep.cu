@@ -76,6 +76,9 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
                   const double* __restrict__ z, double abs_tol, double* __restrict__ rec,
                   int32_t* __restrict__ err) {
   __shared__ __align__(16) double tile[kPrepThreads * kTrussSlotDoubles];
+  __shared__ double trig[6];
+  if (threadIdx.x == 0) trig_table_init(trig, abs_tol * 0.0);
+  __syncthreads();
   const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
   const bool live = pos < n;
   const uint32_t e = live && order ? order[pos] : pos;  // positions [from, n) of the range plan's list (Handle::prep_order)
@@ -85,7 +88,7 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
     double p1[3], p2[3], q[9], k00 = 0.0;
     load_xyz(x, y, z, n1[e], p1);
     load_xyz(x, y, z, n2[e], p2);
-    code = truss_record(p1, p2, E[e], A[e], A2[e], abs_tol, q, &k00);
+    code = truss_record(p1, p2, E[e], A[e], A2[e], abs_tol, q, &k00, trig);
     if (!code) {
       v[0] = q[0];
       v[1] = q[1];
@@ -111,6 +114,9 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, 
                  const double* __restrict__ z, double rel_tol, double abs_tol,
                  double* __restrict__ rec, int32_t* __restrict__ err) {
   __shared__ __align__(16) double tile[kPrepThreads * kBeamSlotDoubles];
+  __shared__ double trig[6];
+  if (threadIdx.x == 0) trig_table_init(trig, abs_tol * 0.0);
+  __syncthreads();
   const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
   const bool live = pos < n;
   const uint32_t e = live && order ? order[pos] : pos;
@@ -123,7 +129,7 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, 
     load_xyz(x, y, z, n1[e], p1);
     load_xyz(x, y, z, n2[e], p2);
     double axis[3] = {ax[e], ay[e], az[e]};
-    code = beam_record(p1, p2, E[e], nu[e], A[e], I11[e], I22[e], I12[e], It[e], ks[e], axis, rel_tol, abs_tol, r);
+    code = beam_record(p1, p2, E[e], nu[e], A[e], I11[e], I22[e], I12[e], It[e], ks[e], axis, rel_tol, abs_tol, r, trig);
     if (!code) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = r[i];
@@ -144,6 +150,9 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
                   const double* __restrict__ y, const double* __restrict__ z, double abs_tol,
                   double* __restrict__ rec, int32_t* __restrict__ err) {
   __shared__ __align__(16) double tile[kPrepThreads * kPlateRawDoubles];
+  __shared__ double trig[6];
+  if (threadIdx.x == 0) trig_table_init(trig, abs_tol * 0.0);
+  __syncthreads();
   const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
   const bool live = pos < n;
   const uint32_t e = live && order ? order[pos] : pos;
@@ -157,7 +166,7 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
     load_xyz(x, y, z, n2[e], p2);
     load_xyz(x, y, z, n3[e], p3);
     load_xyz(x, y, z, n4[e], p4);
-    code = plate_record<kWriteErr>(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m);
+    code = plate_record<kWriteErr>(p1, p2, p3, p4, E[e], nu[e], t[e], ks[e], abs_tol, r, m, trig);
     if (!code) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = r[i];
