@@ -652,6 +652,7 @@ static void free_device(femgpu_t* h) {
     f.uploaded = f.validated = 0;
   }
   h->nz_row_ptr.release(); h->nz_col.release(); h->nz_val.release(); h->nz_valid = false;
+  h->trig_table.release();
   h->blk_key.release(); h->blk_full.release(); h->blk_cptr.release(); h->contrib.release();
   h->blk_meta.release(); h->blk_order.release(); h->items.release(); h->items_c.release(); h->elist.release(); h->elist_compact.release(); h->node_blk_ptr.release(); h->node_base.release();
   h->node_len.release(); h->blk_off.release(); h->slabs.release(); h->row_ptr.release();

@@ -375,6 +375,7 @@ struct Handle {
   DevBuf<int64_t> nz_row_ptr;
   DevBuf<int32_t> nz_col;
   DevBuf<double> nz_val;
+  DevBuf<double> trig_table;       // element_math.cuh trig_table_init: acos(0), acos(-1), their sin / cos (prep.cu)
   DevBuf<uint8_t> scratch;         // CUB temp storage and sort double-buffers
   DevBuf<int32_t> d_flag;          // small device scalars
 
@@ -475,7 +476,7 @@ struct Handle {
     }
     tie(blk_key); tie(blk_full); tie(blk_cptr); tie(contrib); tie(blk_meta); tie(blk_order); tie(items); tie(items_c); tie(elist); tie(elist_compact);
     tie(node_blk_ptr); tie(node_base); tie(node_len); tie(blk_off); tie(slabs); tie(row_ptr);
-    tie(col_idx); tie(values); tie(scratch); tie(d_flag); tie(nz_row_ptr); tie(nz_col); tie(nz_val);
+    tie(col_idx); tie(values); tie(scratch); tie(d_flag); tie(nz_row_ptr); tie(nz_col); tie(nz_val); tie(trig_table);
     for (auto& o : prep_order) tie(o);
     tie(dist.send_buf); tie(dist.recv_buf); tie(dist.recv_dst_block); tie(dist.recv_full);
     tie(dist.remote_keys); tie(dist_scratch.i64);

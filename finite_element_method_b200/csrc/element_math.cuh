@@ -46,9 +46,11 @@ __device__ __forceinline__ double clip_tol(double v, double abs_tol) {
 // sin(+-0) = +-0 and cos(+-0) = 1 hold exactly, so skipping the library call there returns the same bits; it matters
 // because structural models are full of such inputs (members along +x, flat plates with the normal along +z, sections
 // given in their principal axes) and a double-precision acos / sincos costs a few hundred instructions.
-// `trig` (may be null) is the per-CTA table of trig_table_init(): the library's own results at two more arguments that
+// `trig` (may be null) is the table of trig_table_init(): the library's own results at two more arguments that
 // axis-aligned structures produce all the time — acos(0) (a member along y or z against the x axis) and acos(-1) — and
-// the sin / cos of those two angles, computed once per CTA with the same functions, so a hit returns the same bits.
+// the sin / cos of those two angles, computed once per handle on the device with the same functions, so a hit returns
+// the same bits. (A per-CTA copy in shared memory was measured first: the CTA waits ~500 dependent instructions for
+// its thread 0, which cost more than the table saved.)
 //   trig = { acos(0), sin(acos(0)), cos(acos(0)), acos(-1), sin(acos(-1)), cos(acos(-1)) }
 __device__ __forceinline__ void trig_table_init(double* trig, double opaque_zero) {
   // opaque_zero is 0.0 computed from a kernel argument, so nothing here is folded at compile time (by a host libm)

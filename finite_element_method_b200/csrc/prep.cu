@@ -32,6 +32,9 @@ __device__ __forceinline__ void load_xyz(const double* __restrict__ x, const dou
   p[2] = __ldg(z + i);
 }
 
+// the library's own acos(0), acos(-1) and their sin / cos, computed once per handle (element_math.cuh trig_table_init)
+__global__ void trig_table_kernel(double* __restrict__ trig, double opaque_zero) { trig_table_init(trig, opaque_zero); }
+
 // Record stores. A thread holds its element's record (kRec doubles) in registers; written directly, one 16-byte store
 // per thread lands in 32 different 128-byte lines per warp instruction (record stride 48 / 144 / 160 B) and the LSU
 // queue throttles (ncu: lg_throttle 6.6 stalls per issue in the plate kernel). When the warp's elements are consecutive
@@ -74,11 +77,8 @@ truss_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
                   const double* __restrict__ A, const double* __restrict__ A2,
                   const double* __restrict__ x, const double* __restrict__ y,
                   const double* __restrict__ z, double abs_tol, double* __restrict__ rec,
-                  int32_t* __restrict__ err) {
+                  int32_t* __restrict__ err, const double* __restrict__ trig) {
   __shared__ __align__(16) double tile[kPrepThreads * kTrussSlotDoubles];
-  __shared__ double trig[6];
-  if (threadIdx.x == 0) trig_table_init(trig, abs_tol * 0.0);
-  __syncthreads();
   const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
   const bool live = pos < n;
   const uint32_t e = live && order ? order[pos] : pos;  // positions [from, n) of the range plan's list (Handle::prep_order)
@@ -112,11 +112,8 @@ beam_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order, 
                  const double* __restrict__ ay, const double* __restrict__ az,
                  const double* __restrict__ x, const double* __restrict__ y,
                  const double* __restrict__ z, double rel_tol, double abs_tol,
-                 double* __restrict__ rec, int32_t* __restrict__ err) {
+                 double* __restrict__ rec, int32_t* __restrict__ err, const double* __restrict__ trig) {
   __shared__ __align__(16) double tile[kPrepThreads * kBeamSlotDoubles];
-  __shared__ double trig[6];
-  if (threadIdx.x == 0) trig_table_init(trig, abs_tol * 0.0);
-  __syncthreads();
   const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
   const bool live = pos < n;
   const uint32_t e = live && order ? order[pos] : pos;
@@ -148,11 +145,8 @@ plate_prep_kernel(uint32_t from, uint32_t n, const uint32_t* __restrict__ order,
                   const double* __restrict__ nu, const double* __restrict__ t,
                   const double* __restrict__ ks, const double* __restrict__ x,
                   const double* __restrict__ y, const double* __restrict__ z, double abs_tol,
-                  double* __restrict__ rec, int32_t* __restrict__ err) {
+                  double* __restrict__ rec, int32_t* __restrict__ err, const double* __restrict__ trig) {
   __shared__ __align__(16) double tile[kPrepThreads * kPlateRawDoubles];
-  __shared__ double trig[6];
-  if (threadIdx.x == 0) trig_table_init(trig, abs_tol * 0.0);
-  __syncthreads();
   const uint32_t pos = from + blockIdx.x * blockDim.x + threadIdx.x, warp_first = pos - (threadIdx.x & 31u);
   const bool live = pos < n;
   const uint32_t e = live && order ? order[pos] : pos;
@@ -295,8 +289,21 @@ __global__ void rotation_kernel(int family, uint32_t e, const uint32_t* n1, cons
 
 }  // namespace
 
+static int32_t ensure_trig_table(Handle* h) {
+  if (h->trig_table.p) return 0;
+  FEMGPU_CUDA_CHECK(h, h->trig_table.reserve(8));
+  trig_table_kernel<<<1, 1, 0, h->stream>>>(h->trig_table.p, h->abs_tol * 0.0);
+  h->launches++;
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
 int32_t run_prep(Handle* h, bool validate_only) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  {
+    int32_t st = ensure_trig_table(h);
+    if (st) return st;
+  }
   // buffers first (stream-ordered allocations on the handle's stream), then the kernels
   size_t from_of[kFamilies] = {0, 0, 0};
   int n_live = 0;
@@ -343,29 +350,29 @@ int32_t run_prep(Handle* h, bool validate_only) {
       if (validate_only)
         truss_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
-            h->abs_tol, fd.rec.p, fd.err.p);
+            h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
       else
         truss_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), x, y, z,
-            h->abs_tol, fd.rec.p, fd.err.p);
+            h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
     } else if (f == FEMGPU_BEAM) {
       if (validate_only)
         beam_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
-            P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
+            P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
       else
         beam_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2), P(3), P(4),
-            P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
+            P(5), P(6), P(7), P(8), P(9), P(10), x, y, z, h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
     } else {
       if (validate_only)
         plate_prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
-            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
+            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
       else
         plate_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(
             uint32_t(from), uint32_t(n), nullptr, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p, fd.conn[3].p,
-            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
+            P(0), P(1), P(2), P(3), x, y, z, h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
     }
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
@@ -382,6 +389,10 @@ int32_t run_prep(Handle* h, bool validate_only) {
 // after the other on stream `st` (the low-priority stream of api.cu femgpu_numeric; the buffers exist: the symbolic
 // call validated, i.e. ran the record kernels over, every element).
 int32_t run_prep_range(Handle* h, int range, cudaStream_t st) {
+  {
+    int32_t e = ensure_trig_table(h);  // (already there: the symbolic call ran the record kernels over every element)
+    if (e) return e;
+  }
   const double* x = h->x_global();
   const double* y = h->y_global();
   const double* z = h->z_global();
@@ -396,15 +407,15 @@ int32_t run_prep_range(Handle* h, int range, cudaStream_t st) {
     auto P = [&](int k) { return (const double*)fd.props[k].p; };
     if (f == FEMGPU_TRUSS)
       truss_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(from, to, order, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2),
-                                                             x, y, z, h->abs_tol, fd.rec.p, fd.err.p);
+                                                             x, y, z, h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
     else if (f == FEMGPU_BEAM)
       beam_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(from, to, order, fd.conn[0].p, fd.conn[1].p, P(0), P(1), P(2),
                                                             P(3), P(4), P(5), P(6), P(7), P(8), P(9), P(10), x, y, z,
-                                                            h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p);
+                                                            h->rel_tol, h->abs_tol, fd.rec.p, fd.err.p, h->trig_table.p);
     else
       plate_prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(from, to, order, fd.conn[0].p, fd.conn[1].p, fd.conn[2].p,
                                                              fd.conn[3].p, P(0), P(1), P(2), P(3), x, y, z, h->abs_tol,
-                                                             fd.rec.p, fd.err.p);
+                                                             fd.rec.p, fd.err.p, h->trig_table.p);
     h->launches++;
     FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   }
