@@ -3,6 +3,7 @@
 N=$1
 out=gpurun_out/r2_final_n$N; mkdir -p $out
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $out/gpus.txt
+timeout 300 python __graft_entry__.py smoke > $out/smoke.txt 2>&1; echo "smoke rc=$?"; tail -2 $out/smoke.txt
 if [ "$N" = "2" ]; then K=""; else K='-k mixed_or_full_size'; K='-k "mixed or full_size"'; fi
 if [ "$N" = "2" ]; then
   FEMGPU_DIST_INFO=1 timeout 900 python -m pytest tests/test_dist_gpu.py -q -s > $out/pytest_dist.txt 2>&1
