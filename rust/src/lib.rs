@@ -25,6 +25,7 @@ extern "C" {
     fn femgpu_validate(h: *mut FemGpu, family: *mut i32, number: *mut u32, code: *mut i32) -> i32;
     fn femgpu_assemble(h: *mut FemGpu, n_rows: *mut i64, nnz: *mut i64) -> i32;
     fn femgpu_get_csr(h: *mut FemGpu, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
+    fn femgpu_get_nonzero_csr(h: *mut FemGpu, count: *mut i64, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_rotation_elements(h: *mut FemGpu, family: i32, number: u32, out: *mut f64) -> i32;
     fn femgpu_add_displacement(h: *mut FemGpu, n: usize, node: *const u32, dof: *const i32, value: *const f64) -> i32;
     fn femgpu_add_concentrated_load(h: *mut FemGpu, n: usize, node: *const u32, dof: *const i32, value: *const f64) -> i32;
@@ -140,6 +141,19 @@ impl FEM {
         let mut out = [0f64; 9];
         self.check(unsafe { femgpu_rotation_elements(self.h, family, number, out.as_mut_ptr()) })?;
         Ok(out)
+    }
+    /// The entries != 0.0 of the assembled matrix — exactly what `self.stiffness_matrix` holds in the reference, whose
+    /// add_* skip exact zeros (methods_for_truss/beam/plate_data_handle.rs:115/129/204) — as CSR, compacted on the device.
+    pub fn assemble_nonzero_csr(&mut self) -> Result<(Vec<i64>, Vec<i32>, Vec<f64>), String> {
+        let (mut n_rows, mut nnz) = (0i64, 0i64);
+        self.check(unsafe { femgpu_assemble(self.h, &mut n_rows, &mut nnz) })?;
+        let mut count = 0i64;
+        self.check(unsafe { femgpu_get_nonzero_csr(self.h, &mut count, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        let mut rp = vec![0i64; n_rows as usize + 1];
+        let mut ci = vec![0i32; count as usize];
+        let mut v = vec![0f64; count as usize];
+        self.check(unsafe { femgpu_get_nonzero_csr(self.h, &mut count, rp.as_mut_ptr(), ci.as_mut_ptr(), v.as_mut_ptr()) })?;
+        Ok((rp, ci, v))
     }
     /// The assembled global stiffness matrix as CSR on the structural pattern (what
     /// `self.stiffness_matrix` holds in the reference, fem.rs:17). Stored zeros == absent entries.
