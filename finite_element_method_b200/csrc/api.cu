@@ -920,28 +920,6 @@ int32_t femgpu_numeric(femgpu_t* h) {
     if ((st = run_prep(h, /*validate_only=*/false))) return st;
     FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[1], h->stream));
     if ((st = dist_begin_pass(h))) return st;
-    static const bool two_launches = getenv("FEMGPU_DIST_GHOST_FIRST") && atoi(getenv("FEMGPU_DIST_GHOST_FIRST")) == 2;
-    if (!two_launches) {
-      // ONE assembly launch whose slab order starts with the ghost slabs; they count themselves in a device counter,
-      // a one-thread gate kernel on the second stream holds the pack kernel back until the count is complete
-      // (a separate launch for the ghost slabs was measured first: its ramp cost what the overlap saved)
-      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->ghost_ev, h->stream));   // the records exist: the second stream may start
-      FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->xchg_stream, h->ghost_ev, 0));
-      if ((st = dist_gate(h, h->xchg_stream, h->n_slabs - g0))) return st;
-      if ((st = dist_pack(h, h->xchg_stream))) return st;
-      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->pack_ev, h->xchg_stream));
-      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t0[slot][0], h->stream));
-      if ((st = run_assembly(h, 0, h->n_slabs, g0, h->dist.ghost_done))) return st;
-      FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t1[slot][0], h->stream));
-      h->range_count[slot] = 1;
-      FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[2], h->stream));
-      if ((st = dist_apply(h))) return st;
-      FEMGPU_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->pack_ev, 0));
-      FEMGPU_CUDA_CHECK(h, cudaEventRecord(ev[3], h->stream));
-      h->n_numeric++;
-      h->values_valid = true;
-      return 0;
-    }
     FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t0[slot][0], h->stream));
     if ((st = run_assembly(h, g0, h->n_slabs))) return st;  // (the previous pass's pack was joined at its end)
     FEMGPU_CUDA_CHECK(h, cudaEventRecord(h->range_t1[slot][0], h->stream));

@@ -288,8 +288,6 @@ struct DistState {
   std::vector<size_t> peer_slot_bytes;   // ring-slot size of peer r's window (its receive area, rounded like mine)
   uint64_t epoch = 0;                    // numeric passes since the plan was built (the same on every rank)
   uint32_t* done_count = nullptr;        // device: per-peer "last CTA" counters of the pack / apply kernels
-  unsigned long long* ghost_done = nullptr;  // device: ghost slabs stored so far (cumulative over the passes of this plan)
-  uint64_t ghost_target = 0;             // value of *ghost_done once the current pass's ghost slabs are all stored
   volatile uint32_t* h_err = nullptr;    // mapped pinned host word: a kernel timed out waiting for a peer
   uint32_t* d_err = nullptr;
 };
@@ -512,10 +510,7 @@ int32_t run_prep(Handle* h, bool validate_only);         // prep.cu
 int32_t run_prep_range(Handle* h, int range, cudaStream_t st);  // prep.cu: records of the elements first needed by `range`
 int32_t first_error(Handle* h, int* family, size_t* index, int* code);  // prep.cu
 int32_t run_symbolic(Handle* h);                         // symbolic.cu
-// numeric.cu: staged slabs of [begin, end). With ghost_done: the slabs from first_ghost_slab on come first and count
-// themselves in *ghost_done when their values are in global memory (multi-GPU, dist.cu)
-int32_t run_assembly(Handle* h, uint32_t slab_begin, uint32_t slab_end, uint32_t first_ghost_slab = 0,
-                     unsigned long long* ghost_done = nullptr);
+int32_t run_assembly(Handle* h, uint32_t slab_begin, uint32_t slab_end);  // numeric.cu: staged slabs of [begin, end)
 int32_t run_assembly_unstaged(Handle* h);                // numeric.cu: the oversized slabs
 int32_t element_matrix(Handle* h, int family, size_t index, double* out_host);   // numeric.cu
 int32_t element_rotation(Handle* h, int family, size_t index, double* out_host); // prep.cu
@@ -536,7 +531,6 @@ int32_t dist_numeric_exchange(Handle* h);                // dist.cu
 bool dist_ghost_first(Handle* h, uint32_t* first_ghost_slab);  // dist.cu: can the ghost slabs be assembled and sent first?
 int32_t dist_begin_pass(Handle* h);                      // dist.cu: ghost-first pass: next epoch
 int32_t dist_pack(Handle* h, cudaStream_t st);           // dist.cu: my ghost blocks -> the owners' windows
-int32_t dist_gate(Handle* h, cudaStream_t st, uint32_t n_ghost_slabs);  // dist.cu: hold `st` until this pass's ghost slabs are stored
 int32_t dist_apply(Handle* h);                           // dist.cu: received partials += into my rows
 int32_t dist_setup_p2p(Handle* h);                       // dist.cu: collective, called when the exchange plan is final
 int32_t dist_check(Handle* h);                           // dist.cu: after a stream sync — did an exchange time out?

@@ -177,12 +177,6 @@ __device__ __forceinline__ void signal_when_all_done(uint32_t* counter, uint64_t
   }
 }
 
-// holds its stream until the assembly kernel (other stream) has stored this pass's ghost slabs
-__global__ void ghost_gate_kernel(const unsigned long long* counter, unsigned long long target, uint64_t timeout_ns,
-                                  uint32_t* err) {
-  wait_flag(reinterpret_cast<const uint64_t*>(counter), target, timeout_ns, 0x300u, err);
-}
-
 // pack_ghost_kernel, writing into the owner's window: waits until the owner has consumed the pass that last
 // used this ring slot, stores the blocks over NVLink, raises arrived[me] = epoch in the owner's window
 __global__ void __launch_bounds__(128)
@@ -383,14 +377,6 @@ int32_t dist_begin_pass(Handle* h) {
   return 0;
 }
 int32_t dist_pack(Handle* h, cudaStream_t st) { return p2p_pack(h, st); }
-int32_t dist_gate(Handle* h, cudaStream_t st, uint32_t n_ghost_slabs) {
-  DistState& D = h->dist;
-  D.ghost_target += n_ghost_slabs;
-  ghost_gate_kernel<<<1, 32, 0, st>>>(D.ghost_done, D.ghost_target, p2p_timeout_ns(), D.d_err);
-  h->launches++;
-  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
-  return 0;
-}
 int32_t dist_apply(Handle* h) { return p2p_apply(h); }
 
 static void p2p_close_peers(Handle* h) {
@@ -413,7 +399,6 @@ static void p2p_release(Handle* h) {
   p2p_free_window(D.win, D.done_count);
   D.win = nullptr;
   D.done_count = nullptr;
-  D.ghost_done = nullptr;
 }
 
 // Collective (every rank calls it once the exchange plan of a symbolic pass is final): allocate and zero the
@@ -455,9 +440,9 @@ int32_t dist_setup_p2p(Handle* h) {
   std::memset(&mine, 0, sizeof mine);
   if (ok) {
     ok = cudaMalloc(reinterpret_cast<void**>(&D.win), D.win_bytes) == cudaSuccess &&
-         cudaMalloc(reinterpret_cast<void**>(&D.done_count), size_t(2 * W) * 4 + 16) == cudaSuccess &&
+         cudaMalloc(reinterpret_cast<void**>(&D.done_count), size_t(2 * W) * 4) == cudaSuccess &&
          cudaMemsetAsync(D.win, 0, D.win_bytes, h->stream) == cudaSuccess &&
-         cudaMemsetAsync(D.done_count, 0, size_t(2 * W) * 4 + 16, h->stream) == cudaSuccess &&
+         cudaMemsetAsync(D.done_count, 0, size_t(2 * W) * 4, h->stream) == cudaSuccess &&
          cudaStreamSynchronize(h->stream) == cudaSuccess && cudaIpcGetMemHandle(&mine, D.win) == cudaSuccess;
     if (!ok) cudaGetLastError();
   }
@@ -504,9 +489,6 @@ int32_t dist_setup_p2p(Handle* h) {
     return 0;
   }
   D.p2p = true;
-  // the ghost-slab counter lives behind the per-peer counters (8-byte aligned: 2 W x 4 bytes is a multiple of 8)
-  D.ghost_done = reinterpret_cast<unsigned long long*>(D.done_count + 2 * W);
-  D.ghost_target = 0;
   if (getenv("FEMGPU_DIST_INFO"))
     fprintf(stderr, "[femgpu dist] rank %d/%d: p2p window %.2f MB (%lld blocks in, %lld out)\n", D.rank, W,
             double(D.win_bytes) / 1e6, (long long)n_recv, (long long)D.send_off[W]);
@@ -520,8 +502,6 @@ int32_t dist_check(Handle* h) {
   if (!code) return 0;
   *D.h_err = 0;
   const int peer = int(code & 0xFFu);
-  if ((code & 0x300u) == 0x300u)
-    return h->fail(FEMGPU_ERR_NCCL, "ghost-row exchange: the gate waiting for this rank's own ghost slabs timed out (internal)");
   return h->fail(FEMGPU_ERR_NCCL,
                  std::string("ghost-row exchange timed out on rank ") + std::to_string(D.rank) + " in numeric pass " +
                      std::to_string(D.epoch) + ((code & 0x200u) ? ": the blocks of rank " : ": the ring slot of rank ") +

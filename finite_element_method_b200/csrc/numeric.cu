@@ -41,10 +41,6 @@ struct AsmArgs {
   double* values;
   uint32_t slab_begin;  // this launch works on the slabs [slab_begin, n_slabs)
   uint32_t n_slabs;
-  // multi-GPU, ghost slabs first (dist.cu): the slab order is rotated by `rot` so that the launch starts with the last
-  // (ghost) slabs; each of the first `n_ghost_first` slabs adds 1 to *ghost_done once its values are in global memory
-  uint32_t rot, n_ghost_first;
-  unsigned long long* ghost_done;
   // shared-memory regions of the staged kernel, bytes: [image][plate forms][raw plates][stage x2]
   uint32_t smem_img, smem_form, smem_rawp, smem_stage;
 };
@@ -595,13 +591,8 @@ assemble_kernel(const AsmArgs A) {
   unsigned char* dbuf0 = stage0 + 2 * A.smem_stage;  // three rotating descriptor blocks
   const uint32_t rawp_s = smem_u32(rawp), stage0_s = smem_u32(stage0), dbuf0_s = smem_u32(dbuf0);
 
-  const uint32_t n_launch = A.n_slabs - A.slab_begin;   // slabs of this launch, visited in the order j = 0, 1, ..
-  auto slab_of = [&](uint32_t jj) {                      // rotated: j = 0 is slab slab_begin + rot
-    const uint32_t q = jj + A.rot;
-    return A.slab_begin + (q >= n_launch ? q - n_launch : q);
-  };
-  uint32_t j = blockIdx.x;
-  if (j >= n_launch) return;
+  uint32_t k = A.slab_begin + blockIdx.x;
+  if (k >= A.n_slabs) return;
   const uint32_t mbar_s = dbuf0_s + 3 * desc_bytes<kT>();
   PlatePair* pairs = reinterpret_cast<PlatePair*>(dbuf0 + 3 * desc_bytes<kT>() + 16);
   volatile uint32_t* flat_flag = reinterpret_cast<volatile uint32_t*>(dbuf0 + 3 * desc_bytes<kT>() + 8);  // [2], kAhead
@@ -609,12 +600,12 @@ assemble_kernel(const AsmArgs A) {
   if (tid < 16) pairs[tid] = make_plate_pair(int(tid >> 2), int(tid & 3u));
   cta_sync<kT>();
   // prologue: descriptor of the first slab, then its stage and the descriptor of the second
-  issue_desc<kT>(A, slab_of(j), dbuf0_s, tid);
+  issue_desc<kT>(A, k, dbuf0_s, tid);
   cp_async_arrive(mbar_s);
   mbar_wait(mbar_s, 0);
   SlabRegs<kT> cur = read_desc<kT, kBulk>(dbuf0, tid);
   issue_stage<kT, kBulk>(A, cur, stage0_s, rawp_s, mbar_s, tid);
-  if (j + stride < n_launch) issue_desc<kT>(A, slab_of(j + stride), dbuf0_s + desc_bytes<kT>(), tid);
+  if (k + stride < A.n_slabs) issue_desc<kT>(A, k + stride, dbuf0_s + desc_bytes<kT>(), tid);
   cp_async_arrive(mbar_s);
   if (kAhead) {  // the first slab's forms: both warps, like the classic phase A
     mbar_wait(mbar_s, 1u);
@@ -630,7 +621,7 @@ assemble_kernel(const AsmArgs A) {
     const unsigned char* stage = stage0 + buf * A.smem_stage;
     double* form = kAhead ? form0 + buf * (A.smem_form / 8u) : form0;
     const uint32_t d_nxt = (d_cur == 2u) ? 0u : d_cur + 1u, d_nn = (d_nxt == 2u) ? 0u : d_nxt + 1u;
-    const bool has_next = j + stride < n_launch;
+    const bool has_next = k + stride < A.n_slabs;
     // slab `cur`: its records, metadata and entries (and the next slab's descriptor) were
     // requested one iteration ago (batch it + 1 of the mbarrier)
     // (each thread waits on the mbarrier itself; the previous slab's phase B ended with a CTA barrier)
@@ -653,7 +644,7 @@ assemble_kernel(const AsmArgs A) {
       const SlabRegs<kT> nxt = read_desc<kT, kBulk>(dbuf0 + d_nxt * desc_bytes<kT>(), tid);
       np_next = nxt.n_plate();
       issue_stage<kT, kBulk>(A, nxt, stage0_s + (buf ^ 1u) * A.smem_stage, rawp_s, mbar_s, tid);
-      if (j + 2 * stride < n_launch) issue_desc<kT>(A, slab_of(j + 2 * stride), dbuf0_s + d_nn * desc_bytes<kT>(), tid);
+      if (k + 2 * stride < A.n_slabs) issue_desc<kT>(A, k + 2 * stride, dbuf0_s + d_nn * desc_bytes<kT>(), tid);
       cp_async_arrive(mbar_s);
     }
     // one-warp shape: wait for the previous slab's bulk store to have left the image as late as
@@ -723,17 +714,9 @@ assemble_kernel(const AsmArgs A) {
         if (((n - odd) & 1u) && tid == 0) out[n - 1] = img[n - 1];
       }
     }
-    if (A.ghost_done != nullptr && j < A.n_ghost_first) {  // CTA-uniform
-      // a ghost slab: the pack kernel (second stream, behind a gate on this counter) sends its blocks to their owner
-      // as soon as every ghost slab is in global memory
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      __threadfence();
-      cta_sync<kT>();
-      if (tid == 0) atomicAdd(A.ghost_done, 1ull);
-    }
     PHASE_MARK(7)
     if (!has_next) break;
-    j += stride;
+    k += stride;
     d_cur = d_nxt;
     cur = read_desc<kT, kBulk>(dbuf0 + d_cur * desc_bytes<kT>(), tid);
   }
@@ -847,8 +830,6 @@ static AsmArgs asm_args(Handle* h) {
   A.values = h->values.p;
   A.slab_begin = 0;
   A.n_slabs = h->n_slabs;
-  A.rot = A.n_ghost_first = 0;
-  A.ghost_done = nullptr;
   auto up = [](uint32_t b) { return (b + kSmemAlign - 1u) & ~(kSmemAlign - 1u); };
   A.smem_img = up(h->smem_img);
   A.smem_form = up(h->smem_form);
@@ -866,18 +847,12 @@ int32_t run_assembly_unstaged(Handle* h) {
   return 0;
 }
 
-int32_t run_assembly(Handle* h, uint32_t slab_begin, uint32_t slab_end, uint32_t first_ghost_slab,
-                     unsigned long long* ghost_done) {
+int32_t run_assembly(Handle* h, uint32_t slab_begin, uint32_t slab_end) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   if (h->n_slabs == 0 || slab_end <= slab_begin) return 0;
   AsmArgs A = asm_args(h);
   A.slab_begin = slab_begin;
   A.n_slabs = slab_end;
-  if (ghost_done && first_ghost_slab > slab_begin && first_ghost_slab < slab_end) {
-    A.rot = first_ghost_slab - slab_begin;          // j = 0 is the first ghost slab
-    A.n_ghost_first = slab_end - first_ghost_slab;
-    A.ghost_done = ghost_done;
-  }
   const int threads = h->asm_threads;
   const uint32_t desc = threads == 64 ? desc_bytes<64>() : desc_bytes<32>();
   const uint32_t form_bufs = (threads == 64 && FEMGPU_AHEAD != 0) ? 2u : 1u;  // kAhead of assemble_kernel
