@@ -76,3 +76,23 @@ def test_sampled_rows_harness_on_cpu(make):
     bad[k] = bad[k] * (1 + 1e-9) + 1e-3
     rep = compare_sampled_rows(None, mesh, nodes, device="cpu", csr=(csr[0], csr[1], torch.as_tensor(bad)))
     assert rep["n_fail"] == 1, rep
+
+
+def test_node_windows_cover_what_a_rank_needs():
+    """meshes.with_node_window: one contiguous node range per rank holding its own nodes and every node its elements
+    touch; grid strips need one more grid line (+1 node), a 3D lattice one more plane."""
+    for mesh, width in ((meshes.mixed_structure(10, 12), 11), (meshes.truss_lattice(6, 10 ** 9), None),
+                        (meshes.beam_frame(5, 10 ** 9), None)):
+        n = len(mesh["x"])
+        for world in (2, 3, 4):
+            for begin, end in meshes.partition_rows(mesh, world, width):
+                part = meshes.with_node_window(meshes.local_part(mesh, begin, end), begin, end)
+                w0, w1 = part["node_window_begin"], part["node_window_begin"] + len(part["x"])
+                assert w0 == begin and w1 >= end and w1 <= n and part["nodes_number"] == n
+                used = [np.asarray(part[k]).ravel() for k in ("t_n1", "t_n2", "b_n1", "b_n2", "p_n") if np.asarray(part[k]).size]
+                if used:
+                    u = np.concatenate(used)
+                    assert u.min() >= w0 and u.max() < w1
+                assert np.array_equal(part["x"], mesh["x"][w0:w1]) and np.array_equal(part["z"], mesh["z"][w0:w1])
+                if width and end < n:
+                    assert w1 - end <= width + 1            # halo: one more grid line
