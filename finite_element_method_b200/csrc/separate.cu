@@ -150,7 +150,10 @@ __device__ __forceinline__ void quadrant_row(uint32_t lane, uint32_t rc, int64_t
 // column), so a warp that walks one row at a time is latency-bound. When its rows have at most 64
 // entries each — two chunks of 32 — the warp issues the loads of all of them back to back before
 // the first use; longer rows take the generic loop.
-constexpr int kRowsPerWarp = 4;
+#ifndef FEMGPU_SEP_ROWS
+#define FEMGPU_SEP_ROWS 4
+#endif
+constexpr int kRowsPerWarp = FEMGPU_SEP_ROWS;
 
 template <bool kFill>
 __global__ void __launch_bounds__(256)
