@@ -4,8 +4,8 @@ assembly into the global FP64 CSR matrix. The product is libfemgpu.so (C ABI in 
 this package is its Python host mirror (`FEM`) plus synthetic mesh generators for the benchmarks.
 """
 from .fem import (BEAM, ELEMENT_RESULT_COMPONENTS, PLATE, TRUSS, FEM, DOFParameter, FemError,  # noqa: F401
-                  SeparatedStiffnessMatrixSparse)
+                  SeparatedStiffnessMatrix, SeparatedStiffnessMatrixSparse)
 from . import meshes  # noqa: F401
 
-__all__ = ["FEM", "FemError", "DOFParameter", "SeparatedStiffnessMatrixSparse", "TRUSS", "BEAM", "PLATE",
+__all__ = ["FEM", "FemError", "DOFParameter", "SeparatedStiffnessMatrix", "SeparatedStiffnessMatrixSparse", "TRUSS", "BEAM", "PLATE",
            "ELEMENT_RESULT_COMPONENTS", "meshes"]

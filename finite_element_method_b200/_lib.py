@@ -56,6 +56,7 @@ SIGNATURES = {
     "femgpu_get_separated_csr": (C.c_int32, [H, C.c_int32, i64p, i32p, dp]),
     "femgpu_get_separated_csr_device": (C.c_int32, [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                     C.POINTER(C.c_void_p)]),
+    "femgpu_get_separated_dense": (C.c_int32, [H, C.c_int32, dp]),
     "femgpu_separated_rhs": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_last_separate_ms": (C.c_int32, [H, fp]),
     "femgpu_solve_pcg": (C.c_int32, [H, C.c_int32, C.c_int64, i64p]),

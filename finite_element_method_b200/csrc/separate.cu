@@ -255,6 +255,14 @@ __global__ void rhs_kernel(int64_t n_aa, const int64_t* __restrict__ aa_idx, con
   b[i] = acc;
 }
 
+// dense row-major copy of one CSR quadrant (SeparatedStiffnessMatrix's k_aa_matrix ... of the reference): one thread per row
+__global__ void densify_kernel(int64_t rows, int64_t cols, const int64_t* __restrict__ row_ptr,
+                               const int32_t* __restrict__ col, const double* __restrict__ val, double* __restrict__ out) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  for (int64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) out[i * cols + col[p]] = val[p];
+}
+
 __global__ void iota_kernel(uint32_t n, uint32_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = i;
@@ -804,6 +812,35 @@ int32_t femgpu_get_separated_csr(femgpu_t* h, int32_t which, int64_t* row_ptr, i
   if (values && nnz)
     FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(values, h->sep.val[which].p, size_t(nnz) * 8, cudaMemcpyDeviceToHost, h->stream));
   FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t femgpu_get_separated_dense(femgpu_t* h, int32_t which, double* out) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  if (which < 0 || which > 3) return h->fail(FEMGPU_ERR_USAGE, "quadrant must be 0..3 (aa, ab, ba, bb)");
+  if (!out) return h->fail(FEMGPU_ERR_USAGE, "null output");
+  FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const int64_t rows = which < 2 ? h->sep.n_aa : h->sep.n_bb, cols = (which == 0 || which == 2) ? h->sep.n_aa : h->sep.n_bb;
+  if (rows == 0 || cols == 0) return 0;
+  if (rows > (int64_t(1) << 28) / cols)   // 2 GB of doubles: the dense form is for the model sizes the reference's own
+    return h->fail(FEMGPU_ERR_LIMIT,      // dense separation could handle
+                   "dense quadrant of " + std::to_string(rows) + " x " + std::to_string(cols) +
+                       " entries is too large; use femgpu_get_separated_csr / femgpu_get_skyline");
+  femgpu::DevBuf<double> dense;
+  dense.stream = &h->stream;
+  FEMGPU_CUDA_CHECK(h, dense.reserve(size_t(rows) * size_t(cols)));
+  cudaError_t e = cudaMemsetAsync(dense.p, 0, size_t(rows) * size_t(cols) * 8, h->stream);
+  if (e == cudaSuccess && h->sep.nnz[which]) {
+    femgpu::densify_kernel<<<femgpu::div_up(rows, 128), 128, 0, h->stream>>>(rows, cols, h->sep.row_ptr[which].p, h->sep.col[which].p,
+                                                                     h->sep.val[which].p, dense.p);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dense.p, size_t(rows) * size_t(cols) * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  dense.release();
+  FEMGPU_CUDA_CHECK(h, e);
   return 0;
 }
 

@@ -55,6 +55,48 @@ class SeparatedStiffnessMatrixSparse:
         return rows, ci.astype(np.int64), v
 
 
+class SeparatedStiffnessMatrix:
+    """structs/separated_stiffness_matrix.rs:8-65 — what `separate_stiffness_matrix_direct` returns in the reference, with
+    its getters. The dense quadrants are fetched from the device on first use (`femgpu_get_separated_dense`); `a`, `maxa`
+    are K_aa in the compacted column form the skyline solver consumes (convert_k_aa_into_compacted_form). Unpacks like
+    the tuple (k_aa_indexes, k_bb_indexes, k_aa_skyline, a, maxa) earlier versions returned."""
+
+    def __init__(self, fem, k_aa_indexes, k_bb_indexes, k_aa_skyline, a, maxa):
+        self._fem = fem
+        self.k_aa_indexes, self.k_bb_indexes, self.k_aa_skyline = k_aa_indexes, k_bb_indexes, k_aa_skyline
+        self.a, self.maxa = a, maxa
+        self._dense = {}
+
+    def __iter__(self):
+        return iter((self.k_aa_indexes, self.k_bb_indexes, self.k_aa_skyline, self.a, self.maxa))
+
+    def get_k_aa_indexes(self):
+        return self.k_aa_indexes
+
+    def get_k_bb_indexes(self):
+        return self.k_bb_indexes
+
+    def get_k_aa_skyline(self):
+        return self.k_aa_skyline
+
+    def _quadrant(self, which):
+        if which not in self._dense:
+            self._dense[which] = self._fem.separated_dense(which)
+        return self._dense[which]
+
+    def get_k_aa_matrix(self):
+        return self._quadrant(0)
+
+    def get_k_ab_matrix(self):
+        return self._quadrant(1)
+
+    def get_k_ba_matrix(self):
+        return self._quadrant(2)
+
+    def get_k_bb_matrix(self):
+        return self._quadrant(3)
+
+
 class FemError(Exception):
     """`Err(String)` of the reference. `.code` is the FEMGPU_E_* / FEMGPU_ERR_* status."""
 
@@ -357,10 +399,11 @@ class FEM:
         return SeparatedStiffnessMatrixSparse(ia, ib, quads, b, float(ms.value))
 
     def separate_stiffness_matrix_direct(self):
-        """methods_for_separate_stiffness_matrix.rs:63-215 without the dense detour: (k_aa_indexes, k_bb_indexes,
-        k_aa_skyline, a, maxa) with K_aa in the compacted column form of the skyline solver
-        (convert_k_aa_into_compacted_form, methods_for_global_analysis.rs:50-80). K_ab / K_ba / K_bb stay
-        available as the CSR quadrants of the handle."""
+        """methods_for_separate_stiffness_matrix.rs:63-215 -> SeparatedStiffnessMatrix: k_aa_indexes, k_bb_indexes,
+        k_aa_skyline, the dense quadrants through its get_k_*_matrix() getters (fetched on demand), and K_aa in the
+        compacted column form (a, maxa) of the skyline solver (convert_k_aa_into_compacted_form,
+        methods_for_global_analysis.rs:50-80) — built on the device without the reference's dense detour. K_ab / K_ba /
+        K_bb also stay available as the CSR quadrants of the handle."""
         na, nb, nv = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(self._L.femgpu_separate_direct(self._h, C.byref(na), C.byref(nb), C.byref(nv)))
         self._sep_counts = (int(na.value), int(nb.value))
@@ -368,7 +411,16 @@ class FEM:
         self._check(self._L.femgpu_get_separated_indexes(self._h, _p(ia, _lib.i64p), _p(ib, _lib.i64p)))
         sky, a, maxa = np.empty(na.value, np.int64), np.empty(nv.value, np.float64), np.empty(na.value + 1, np.int64)
         self._check(self._L.femgpu_get_skyline(self._h, _p(sky, _lib.i64p), _p(a, _lib.dp), _p(maxa, _lib.i64p)))
-        return ia, ib, sky, a, maxa
+        return SeparatedStiffnessMatrix(self, ia, ib, sky, a, maxa)
+
+    def separated_dense(self, which: int):
+        """quadrant `which` (0 aa, 1 ab, 2 ba, 3 bb) of the last separation as a dense matrix"""
+        na, nb = self._n_aa_bb()
+        rows, cols = (na if which < 2 else nb), (na if which in (0, 2) else nb)
+        out = np.zeros((rows, cols), np.float64)
+        if rows and cols:
+            self._check(self._L.femgpu_get_separated_dense(self._h, which, _p(out, _lib.dp)))
+        return out
 
     # ------------------------------------------------------------------ global analysis, element results
     def _solve(self, preconditioner: int, max_iter: int, copy_out: bool):

@@ -257,7 +257,9 @@ int32_t femgpu_separate_sparse(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_
  * The reference makes K dense to collect k_aa_skyline and dense quadrants whose only consumer turns K_aa into the
  * compacted column form of its skyline solver (convert_k_aa_into_compacted_form, methods_for_global_analysis.rs:50-80);
  * here k_aa_skyline and (a, maxa) are built straight from the CSR quadrant on the device, and K_ab / K_ba / K_bb
- * stay available as the CSR quadrants of femgpu_get_separated_csr. skyline_values = length of `a`. */
+ * stay available as the CSR quadrants of femgpu_get_separated_csr — or, for a caller that wants the reference's
+ * SeparatedStiffnessMatrix as it is, as dense matrices through femgpu_get_separated_dense.
+ * skyline_values = length of `a`. */
 int32_t femgpu_separate_direct(femgpu_t* h, int64_t* n_aa, int64_t* n_bb, int64_t* skyline_values);
 /* k_aa_skyline [n_aa], a [skyline_values], maxa [n_aa + 1]: column j of K_aa = a[maxa[j]] (diagonal),
  * a[maxa[j] + k] = K_aa[j - k, j] for k <= k_aa_skyline[j]. Pointers may be NULL. */
@@ -268,6 +270,12 @@ int32_t femgpu_get_separated_indexes(femgpu_t* h, int64_t* k_aa_indexes, int64_t
 int32_t femgpu_get_separated_csr(femgpu_t* h, int32_t which, int64_t* row_ptr, int32_t* col_idx, double* values);
 int32_t femgpu_get_separated_csr_device(femgpu_t* h, int32_t which, const int64_t** row_ptr,
                                         const int32_t** col_idx, const double** values);
+/* Quadrant `which` as a dense row-major matrix [rows x cols] — k_aa_matrix / k_ab_matrix / k_ba_matrix / k_bb_matrix of
+ * the reference's SeparatedStiffnessMatrix (structs/separated_stiffness_matrix.rs:8-16), which
+ * separate_stiffness_matrix_direct returns next to k_aa_indexes, k_bb_indexes and k_aa_skyline. Densified on the device
+ * from the CSR quadrant; refused with FEMGPU_ERR_LIMIT above 2^28 entries (the dense form is O((6N)^2): it exists for
+ * callers of the reference signature on the model sizes the reference's own dense separation could handle). */
+int32_t femgpu_get_separated_dense(femgpu_t* h, int32_t which, double* out);
 /* b = R_a - K_ab u_b [n_aa]; either pointer may be NULL */
 int32_t femgpu_separated_rhs(femgpu_t* h, double* b, const double** b_device);
 /* device milliseconds of the last femgpu_separate_sparse() */

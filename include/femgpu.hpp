@@ -106,6 +106,14 @@ class FEM {
     check(femgpu_get_skyline(h_, k.k_aa_skyline.data(), k.a.data(), k.maxa.data()));
     return k;
   }
+  // k_aa_matrix / k_ab_matrix / k_ba_matrix / k_bb_matrix of the reference's SeparatedStiffnessMatrix
+  // (structs/separated_stiffness_matrix.rs:8-16) as a dense row-major matrix; which = 0 aa, 1 ab, 2 ba, 3 bb
+  std::vector<double> separated_dense(int which) {
+    const int64_t rows = which < 2 ? sep_.n_aa : sep_.n_bb, cols = (which == 0 || which == 2) ? sep_.n_aa : sep_.n_bb;
+    std::vector<double> m(size_t(rows) * size_t(cols));
+    if (!m.empty()) check(femgpu_get_separated_dense(h_, which, m.data()));
+    return m;
+  }
   // methods_for_global_analysis.rs:161 (skyline LDL^T, COLSOL)
   std::vector<double> find_ua_vector_direct() {
     check(femgpu_solve_direct(h_));

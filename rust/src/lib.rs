@@ -35,6 +35,7 @@ extern "C" {
     fn femgpu_get_separated_indexes(h: *mut FemGpu, k_aa_indexes: *mut i64, k_bb_indexes: *mut i64) -> i32;
     fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_separated_rhs(h: *mut FemGpu, b: *mut f64, b_device: *mut *const f64) -> i32;
+    fn femgpu_get_separated_dense(h: *mut FemGpu, which: i32, out: *mut f64) -> i32;
     fn femgpu_separate_direct(h: *mut FemGpu, n_aa: *mut i64, n_bb: *mut i64, skyline_values: *mut i64) -> i32;
     fn femgpu_solve_direct(h: *mut FemGpu) -> i32;
     fn femgpu_get_skyline(h: *mut FemGpu, k_aa_skyline: *mut i64, a: *mut f64, maxa: *mut i64) -> i32;

@@ -84,6 +84,9 @@ int main(int argc, char** argv) {
   // direct flow (test_fem.rs:5-64)
   auto sky = fem.separate_stiffness_matrix_direct();
   EXPECT(sky.a.size() == 1 && near(sky.a[0], 66666.66666666667, 1e-15));
+  auto kaa = fem.separated_dense(0);   // SeparatedStiffnessMatrix::get_k_aa_matrix of the reference: 1 x 1 here
+  auto kab = fem.separated_dense(1);
+  EXPECT(kaa.size() == 1 && near(kaa[0], 66666.66666666667, 1e-15) && kab.size() == 1 && near(kab[0], -66666.66666666667, 1e-15));
   auto ud = fem.find_ua_vector_direct();
   EXPECT(near(ud[0], 0.0015, 1e-14));
   std::printf("CPP_HEADER_OK device %d\n", device);

@@ -381,6 +381,15 @@ def test_direct_separation_matches_oracle(which):
     assert np.array_equal(a, ref["a"])
     if which == "reference":
         assert list(sky) == [0] and a[0] == 66666.66666666667
+    # the reference's SeparatedStiffnessMatrix (structs/separated_stiffness_matrix.rs): same getters, dense quadrants
+    sep = fem.separate_stiffness_matrix_direct()
+    assert np.array_equal(sep.get_k_aa_indexes(), ia) and np.array_equal(sep.get_k_bb_indexes(), ib)
+    assert np.array_equal(sep.get_k_aa_skyline(), sky)
+    K = sp.csr_matrix((v, ci, rp), shape=(6 * n, 6 * n)).toarray()
+    for got, (r_idx, c_idx) in ((sep.get_k_aa_matrix(), (ia, ia)), (sep.get_k_ab_matrix(), (ia, ib)),
+                                (sep.get_k_ba_matrix(), (ib, ia)), (sep.get_k_bb_matrix(), (ib, ib))):
+        assert got.shape == (len(r_idx), len(c_idx))
+        assert np.array_equal(got, K[np.ix_(r_idx, c_idx)])        # the values of K itself, bit for bit
     fem.close()
 
 
