@@ -27,3 +27,31 @@ def test_other_ranks_of_the_reference_arm_exit_without_work():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                        text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_workload_partitions_one_mesh_over_the_ranks():
+    """bench.py --gpus N (strong scaling, the default): every element of the configured mesh lands on exactly one rank,
+    every rank gets its own rows' nodes plus the halo; weak scaling multiplies the strip count instead."""
+    import types
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from finite_element_method_b200 import meshes
+    for config in ("M", "P", "B", "T"):
+        for world in (1, 2, 4, 8):
+            args = types.SimpleNamespace(config=config, variant="flat", nx=24 if config in "MP" else 6, ny=16)
+            total, covered, n_el_total = 0, 0, None
+            for rank in range(world):
+                local, name, n_nodes, n_el, begin, end = bench.workload(args, "strong", rank, world)
+                n_el_total = n_el if n_el_total is None else n_el_total
+                assert n_el == n_el_total
+                total += meshes.n_elements(local)
+                covered += end - begin
+                w0 = int(local.get("node_window_begin", 0))
+                assert w0 == (begin if world > 1 else 0) and w0 + len(local["x"]) >= end
+                if world > 1:
+                    assert local["nodes_number"] == n_nodes and len(local["x"]) < n_nodes
+            assert total == n_el_total and covered == n_nodes
+        if config in "MP":
+            sizes = [bench.workload(args, "weak", 0, w)[3] for w in (1, 2, 4)]
+            assert sizes[1] == 2 * sizes[0] and sizes[2] == 4 * sizes[0]

@@ -6,6 +6,7 @@ CPU tests pin the oracle restatement on the reference's own test model
 device separation with the oracle, bit for bit (index work and copied values)."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 from finite_element_method_b200 import FEM, DOFParameter, FemError, meshes
 from oracle import oracle as O
@@ -456,7 +457,6 @@ def test_direct_solve_matches_oracle_and_dense(which):
     u_ref = O.colsol(a, maxa, sep.b)
     assert np.linalg.norm(u - u_ref) <= 1e-9 * np.linalg.norm(u_ref)          # same algorithm, other dot order
     i, j, v = sep.triplets(sep.k_aa)
-    import scipy.sparse as sp
     A = sp.csr_matrix((v, (i, j)), shape=(sep.n_aa, sep.n_aa))
     assert np.linalg.norm(A @ u - sep.b) <= 1e-9 * np.linalg.norm(sep.b)
     assert np.array_equal(u, fem.find_ua_vector_direct())                     # deterministic
