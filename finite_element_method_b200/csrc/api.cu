@@ -323,17 +323,8 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
   // a property failure at i still lets the number / node-set checks of element i run first
   size_t scan_end = std::min(limit, i_prop.load() + 1);
 
-  // B. duplicate element numbers (sequential: dense table updates are a few ns each)
-  size_t i_num = scan_end, inserted_numbers = 0;
-  for (size_t i = 0; i < scan_end; ++i) {
-    uint32_t dummy;
-    if (fh.by_number.find(number[i], &dummy)) {
-      i_num = i;
-      break;
-    }
-    fh.by_number.insert(number[i], uint32_t(start + i));
-    ++inserted_numbers;
-  }
+  // B. duplicate element numbers (NumberMap::insert_batch: all cores for large batches)
+  const size_t i_num = fh.by_number.insert_batch(number, scan_end, uint32_t(start)), inserted_numbers = i_num;
   scan_end = std::min(scan_end, i_num + 1);
   lap("element numbers");
 
@@ -361,7 +352,7 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
         node_set_of(existing, a);
         node_set_of(uint32_t(start + i), b);
         return nodeset_equal(family, a, b);
-      });
+      }, h->add_items);
   lap("node-set index");
   if (family == FEMGPU_PLATE) {
     // Plate::is_nodes_numbers_same is a subset test; with repeated node numbers in the new element
@@ -747,18 +738,18 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
   const size_t room = h->nodes_number > g0 ? size_t(h->nodes_number) - g0 : 0;
   const size_t i_limit = std::min(n, room);
   size_t scan_end = std::min(n, i_limit + 0);
-  // duplicate numbers (sequential dense-table pass)
-  size_t i_num = scan_end, inserted = 0;
-  for (size_t i = 0; i < scan_end; ++i) {
-    uint32_t dummy;
-    if (h->node_by_number.find(number[i], &dummy)) {
-      i_num = i;
-      break;
-    }
-    h->node_by_number.insert(number[i], uint32_t(g0 + i));
-    ++inserted;
-  }
+  static const bool timing = getenv("FEMGPU_HOST_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[femgpu add nodes] %-22s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  // duplicate numbers (NumberMap::insert_batch)
+  const size_t i_num = h->node_by_number.insert_batch(number, scan_end, uint32_t(g0)), inserted = i_num;
   scan_end = std::min(scan_end, i_num + 1);
+  lap("node numbers");
   // duplicate coordinates: sharded hash index, all cores (NaN never compares equal)
   std::vector<uint64_t>& hashes = h->add_hash;
   hashes.resize(scan_end);
@@ -773,7 +764,8 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
       ex = h->nx[existing]; ey = h->ny[existing]; ez = h->nz[existing];
     }
     return ex == x[i] && ey == y[i] && ez == z[i];
-  });
+  }, h->add_items);
+  lap("coordinate index");
   const size_t accepted = std::min(std::min(i_limit, i_num), i_xyz);
   for (size_t i = accepted; i < inserted; ++i) h->node_by_number.erase(number[i]);
   if (accepted < scan_end) h->node_by_xyz.erase_batch(hashes.data(), accepted, scan_end, uint32_t(n0));
@@ -785,6 +777,7 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
       if (j == 3) h->nz.insert(h->nz.end(), z, z + accepted);
     }
   });
+  lap("appends");
   if (accepted) invalidate(h);
   if (accepted < n) {
     const size_t e = accepted;

@@ -130,6 +130,61 @@ struct NumberMap {
     }
     ++count;
   }
+  // Bulk form of `for i: if (find(number[i])) stop; insert(number[i], first_idx + i)`: inserts the labels up to the
+  // first one that already exists (in the map, or earlier in the batch) and returns its position (n if none).
+  // Large batches of table-sized labels are claimed by all host cores: every label takes the smallest index that
+  // asks for it (atomic min on its table entry), a second pass finds the first position that did not get its own.
+  size_t insert_batch(const uint32_t* number, size_t n, uint32_t first_idx) {
+    bool parallel = n >= 65536 && sparse.empty() && host_threads() > 1;
+    uint32_t mx = 0;
+    if (parallel) {
+      std::atomic<uint32_t> amx(0);
+      parallel_chunks(n, 65536, [&](size_t b, size_t e) {
+        uint32_t m = 0;
+        for (size_t i = b; i < e; ++i) m = std::max(m, number[i]);
+        uint32_t cur = amx.load();
+        while (m > cur && !amx.compare_exchange_weak(cur, m)) {
+        }
+      });
+      mx = amx.load();
+      parallel = mx < kDenseLimit && mx <= 8 * (count + n + 1024);
+    }
+    if (!parallel) {
+      for (size_t i = 0; i < n; ++i) {
+        uint32_t dummy;
+        if (find(number[i], &dummy)) return i;
+        insert(number[i], first_idx + uint32_t(i));
+      }
+      return n;
+    }
+    if (mx >= dense.size()) dense.resize(std::max<size_t>(size_t(mx) + 1, dense.size() * 2), 0);
+    uint32_t* tab = dense.data();
+    parallel_chunks(n, 65536, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; ++i) {
+        const uint32_t v = first_idx + uint32_t(i) + 1;
+        uint32_t* slot = tab + number[i];
+        uint32_t cur = __atomic_load_n(slot, __ATOMIC_RELAXED);
+        while ((cur == 0 || cur > v) &&
+               !__atomic_compare_exchange_n(slot, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        }
+      }
+    });
+    std::atomic<size_t> first(n);
+    parallel_chunks(n, 65536, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; ++i)
+        if (tab[number[i]] != first_idx + uint32_t(i) + 1) {
+          size_t cur = first.load();
+          while (i < cur && !first.compare_exchange_weak(cur, i)) {
+          }
+          return;  // later positions of this chunk cannot be the first
+        }
+    });
+    const size_t stop = first.load();
+    for (size_t i = stop; i < n; ++i)  // claims of the positions that are not inserted
+      if (tab[number[i]] == first_idx + uint32_t(i) + 1) tab[number[i]] = 0;
+    count += stop;
+    return stop;
+  }
   void erase(uint32_t number) {
     if (number < dense.size() && dense[number]) {
       dense[number] = 0;
@@ -330,6 +385,7 @@ struct Handle {
   // scratch of the batched adds (node indices of the batch, hashes), kept between calls
   std::vector<uint32_t> add_idx[4];
   std::vector<uint64_t> add_hash;
+  std::vector<ShardedIndex::Item> add_items;  // scratch of ShardedIndex::insert_batch (the batch partitioned by shard)
 
   // ---- symbolic products ----
   bool symbolic_valid = false;

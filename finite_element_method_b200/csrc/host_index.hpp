@@ -1,23 +1,129 @@
 // Host-side indices for the reference's duplicate checks (same node coordinates, same element node
-// set), built for bulk loading: 256 independent open-addressing shards so a batch of millions of
+// set), built for bulk loading: 1024 independent open-addressing shards so a batch of millions of
 // keys can be inserted by all host cores at once (each thread owns a subset of the shards and scans
 // the batch's precomputed hashes), while single adds stay O(1). The reference does a linear scan
 // per add (methods_for_node_data_handle.rs:52-62, methods_for_truss_data_handle.rs:32-47, ...).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <type_traits>
 #include <functional>
 #include <thread>
 #include <vector>
 
 namespace femgpu {
 
+// host threads of the bulk paths: the cores of the machine, at most 32 (FEMGPU_HOST_THREADS overrides)
 inline unsigned host_threads() {
-  unsigned n = std::thread::hardware_concurrency();
-  return std::max(1u, std::min(n ? n : 1u, 32u));
+  static const unsigned cached = [] {
+    unsigned n = std::thread::hardware_concurrency();
+    if (const char* e = getenv("FEMGPU_HOST_THREADS")) {
+      int v = atoi(e);
+      if (v > 0) return unsigned(std::min(v, 256));
+    }
+    return std::max(1u, std::min(n ? n : 1u, 32u));
+  }();
+  return cached;
 }
+
+// Worker threads of the bulk paths, started once per process and parked on a condition variable between
+// regions: a batched add runs a dozen short parallel regions, and starting 31 threads for each of them costs
+// more than some of the regions themselves.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool pool;
+    return pool;
+  }
+  // fn(t, n_threads) for t = 0 .. n_threads-1, t = 0 on the calling thread; returns when all are done.
+  // A region entered while another one is running (a second handle on another user thread, or a nested call)
+  // starts its own threads instead of waiting for the pool.
+  template <typename F>
+  void run(unsigned n_threads, F&& fn) {
+    std::unique_lock<std::mutex> region(region_mutex_, std::try_to_lock);
+    if (!region.owns_lock() || inside()) {
+      std::vector<std::thread> th;
+      th.reserve(n_threads - 1);
+      for (unsigned t = 1; t < n_threads; ++t) th.emplace_back([&, t] { fn(t, n_threads); });
+      fn(0u, n_threads);
+      for (auto& x : th) x.join();
+      return;
+    }
+    grow(n_threads - 1);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      call_ = [](void* ctx, unsigned t, unsigned nt) { (*static_cast<typename std::remove_reference<F>::type*>(ctx))(t, nt); };
+      ctx_ = const_cast<void*>(static_cast<const void*>(&fn));
+      n_threads_ = n_threads;
+      remaining_ = n_threads - 1;
+      ++generation_;
+    }
+    wake_.notify_all();
+    inside() = true;
+    fn(0u, n_threads);
+    inside() = false;
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return remaining_ == 0; });
+  }
+
+ private:
+  HostPool() = default;
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    wake_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  static bool& inside() {
+    static thread_local bool in = false;
+    return in;
+  }
+  void grow(unsigned want) {
+    while (workers_.size() < want) {
+      const unsigned id = unsigned(workers_.size()) + 1;  // thread index inside a region
+      uint64_t seen;
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        seen = generation_;
+      }
+      workers_.emplace_back([this, id, seen]() mutable {
+        inside() = true;
+        for (;;) {
+          void (*call)(void*, unsigned, unsigned);
+          void* ctx;
+          unsigned nt;
+          {
+            std::unique_lock<std::mutex> lk(m_);
+            wake_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            call = call_; ctx = ctx_; nt = n_threads_;
+          }
+          if (id < nt) {
+            call(ctx, id, nt);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--remaining_ == 0) done_.notify_one();
+          }
+        }
+      });
+    }
+  }
+  std::mutex region_mutex_, m_;
+  std::condition_variable wake_, done_;
+  std::vector<std::thread> workers_;
+  void (*call_)(void*, unsigned, unsigned) = nullptr;
+  void* ctx_ = nullptr;
+  unsigned n_threads_ = 0, remaining_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+};
 
 // run fn(t, n_threads) on n_threads threads (inline when n_threads == 1)
 template <typename F>
@@ -26,11 +132,7 @@ inline void parallel_run(unsigned n_threads, F&& fn) {
     fn(0u, 1u);
     return;
   }
-  std::vector<std::thread> th;
-  th.reserve(n_threads - 1);
-  for (unsigned t = 1; t < n_threads; ++t) th.emplace_back([&, t] { fn(t, n_threads); });
-  fn(0u, n_threads);
-  for (auto& x : th) x.join();
+  HostPool::get().run(n_threads, fn);
 }
 
 template <typename F>
@@ -55,7 +157,7 @@ inline uint64_t mix64(uint64_t x) {
 // of two different keys with one hash. id 0xFFFFFFFF marks an empty slot, 0xFFFFFFFE a tombstone.
 class ShardedIndex {
  public:
-  static constexpr unsigned kShards = 256;
+  static constexpr unsigned kShift = 54, kShards = 1u << (64 - kShift);  // 1024 shards, keyed by the top hash bits
   static constexpr uint32_t kEmpty = 0xFFFFFFFFu, kDead = 0xFFFFFFFEu;
 
   // forget the entries, keep the tables (FEM::reset of a re-used instance: no fresh pages to fault in)
@@ -72,7 +174,7 @@ class ShardedIndex {
   // Looks for an entry equal to (hash, probe) under `same(existing_id)`; returns its id or kEmpty.
   template <typename Same>
   uint32_t find(uint64_t hash, Same&& same) const {
-    const Shard& s = shards_[hash >> 56];
+    const Shard& s = shards_[hash >> kShift];
     if (s.cap == 0) return kEmpty;
     size_t mask = s.cap - 1, i = size_t(hash) & mask;
     for (;;) {
@@ -85,14 +187,14 @@ class ShardedIndex {
 
   // insert without duplicate check (the caller has called find)
   void insert(uint64_t hash, uint32_t id) {
-    Shard& s = shards_[hash >> 56];
+    Shard& s = shards_[hash >> kShift];
     if ((s.used + 1) * 2 > s.cap) grow(s, std::max<size_t>(16, s.cap * 2));
     place(s, hash, id);
   }
 
   template <typename Same>
   void erase(uint64_t hash, uint32_t id_to_erase, Same&&) {
-    Shard& s = shards_[hash >> 56];
+    Shard& s = shards_[hash >> kShift];
     if (s.cap == 0) return;
     size_t mask = s.cap - 1, i = size_t(hash) & mask;
     for (;;) {
@@ -108,46 +210,83 @@ class ShardedIndex {
 
   // Bulk: hashes[i] belongs to new id first_id + i. For every i (ascending inside each shard) looks
   // for an equal earlier entry; if none, inserts. Returns the smallest i that found a duplicate
-  // (n if none). `same(existing_id, i)` decides equality. Runs on all host cores.
+  // (n if none). `same(existing_id, i)` decides equality. Runs on all host cores: the batch is first
+  // partitioned by shard (histogram + scatter of (hash, i) pairs, order kept), then every shard is
+  // filled by one thread while its table — a few hundred KB — stays in that core's cache. Probing the
+  // tables in batch order instead costs two cache-line misses per key and is bound by memory traffic.
+  struct Item {
+    uint64_t hash;
+    uint32_t i;
+  };
   template <typename Same>
-  size_t insert_batch(const uint64_t* hashes, size_t n, uint32_t first_id, Same&& same) {
-    unsigned T = n >= 32768 ? std::min(host_threads(), kShards) : 1u;
-    // reserve: expected entries per shard (uniform hash) with slack, so no shard grows mid-batch often
-    size_t per = n / kShards + n / (kShards * 4) + 16;
-    std::atomic<size_t> first_dup(n);
+  size_t insert_batch(const uint64_t* hashes, size_t n, uint32_t first_id, Same&& same, std::vector<Item>& scratch) {
+    if (n < 4096) {  // single adds and small batches: probe in batch order
+      for (size_t i = 0; i < n; ++i) {
+        if (find(hashes[i], [&](uint32_t id) { return same(id, i); }) != kEmpty) return i;
+        insert(hashes[i], first_id + uint32_t(i));
+      }
+      return n;
+    }
+    const unsigned T = n >= 32768 ? host_threads() : 1u;
+    std::vector<uint32_t> hist(size_t(T) * kShards, 0u);
     parallel_run(T, [&](unsigned t, unsigned nt) {
-      for (unsigned sh = t; sh < kShards; sh += nt) {
+      uint32_t* hg = hist.data() + size_t(t) * kShards;
+      for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) hg[hashes[i] >> kShift]++;
+    });
+    std::vector<uint32_t> shard_begin(kShards + 1);
+    uint32_t running = 0;
+    for (unsigned sh = 0; sh < kShards; ++sh) {
+      shard_begin[sh] = running;
+      for (unsigned t = 0; t < T; ++t) {
+        uint32_t c = hist[size_t(t) * kShards + sh];
+        hist[size_t(t) * kShards + sh] = running;
+        running += c;
+      }
+    }
+    shard_begin[kShards] = running;
+    if (scratch.size() < n) scratch.resize(n);
+    Item* items = scratch.data();
+    parallel_run(T, [&](unsigned t, unsigned nt) {
+      uint32_t* at = hist.data() + size_t(t) * kShards;
+      for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) items[at[hashes[i] >> kShift]++] = Item{hashes[i], uint32_t(i)};
+    });
+    std::atomic<size_t> first_dup(n);
+    std::atomic<unsigned> next(0);
+    parallel_run(T, [&](unsigned, unsigned) {
+      size_t local_first = n;
+      for (unsigned sh = next.fetch_add(1); sh < kShards; sh = next.fetch_add(1)) {
+        const size_t b = shard_begin[sh], e = shard_begin[sh + 1];
+        if (b == e) continue;
         Shard& s = shards_[sh];
-        size_t want = (s.used + per) * 2;
+        const size_t want = (s.used + (e - b)) * 2;
         if (want > s.cap) {
           size_t cap = 16;
           while (cap < want) cap <<= 1;
           grow(s, cap);
         }
-      }
-      size_t local_first = n;
-      for (size_t i = 0; i < n; ++i) {
-        uint64_t hsh = hashes[i];
-        unsigned sh = unsigned(hsh >> 56);
-        if (sh % nt != t) continue;
-        Shard& s = shards_[sh];
-        size_t mask = s.cap - 1, p = size_t(hsh) & mask;
-        bool dup = false;
-        for (;;) {
-          uint32_t id = s.id[p];
-          if (id == kEmpty) break;
-          if (id != kDead && s.hash[p] == hsh && same(id, i)) {
-            dup = true;
-            break;
+        const size_t mask = s.cap - 1;
+        for (size_t k = b; k < e; ++k) {
+          const uint64_t hsh = items[k].hash;
+          const size_t i = items[k].i;
+          size_t p = size_t(hsh) & mask;
+          bool dup = false;
+          for (;;) {
+            uint32_t id = s.id[p];
+            if (id == kEmpty) break;
+            if (id != kDead && s.hash[p] == hsh && same(id, i)) {
+              dup = true;
+              break;
+            }
+            p = (p + 1) & mask;
           }
-          p = (p + 1) & mask;
+          if (dup) {
+            if (i < local_first) local_first = i;
+            continue;  // a duplicate is never inserted
+          }
+          s.hash[p] = hsh;  // the probe ended on the first empty slot of the chain
+          s.id[p] = first_id + uint32_t(i);
+          ++s.used;
         }
-        if (dup) {
-          if (i < local_first) local_first = i;
-          continue;  // a duplicate is never inserted
-        }
-        if ((s.used + 1) * 2 > s.cap) grow(s, s.cap * 2);
-        place(s, hsh, first_id + uint32_t(i));
       }
       size_t cur = first_dup.load();
       while (local_first < cur && !first_dup.compare_exchange_weak(cur, local_first)) {

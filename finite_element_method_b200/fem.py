@@ -617,27 +617,56 @@ class FEM:
         return int(a.value), int(b.value)
 
     # ------------------------------------------------------------------ convenience
-    def load_mesh(self, mesh: dict) -> None:
-        """Bulk-load a mesh dict from finite_element_method_b200.meshes (node number = index + 1;
-        insertion order plates -> beams -> trusses)."""
+    _API_SOURCES = ("x", "y", "z", "p_n", "p_props", "b_n1", "b_n2", "b_props", "b_axis", "t_n1", "t_n2", "t_E", "t_A", "t_A2",
+                    "node_number_offset", "element_number_offset", "node_window_begin")
+
+    @classmethod
+    def api_arrays(cls, mesh: dict, cache: bool = False) -> dict:
+        """The arrays the bulk API takes for a mesh dict of finite_element_method_b200.meshes (0-based node indices,
+        implicit labels): node / element numbers and node numbers per element, as a caller of the reference holds
+        them. With `cache` they are built once per mesh dict and kept in it (key "_api") as long as the dict still
+        holds the very same source objects; arrays changed in place need a fresh dict (or cache=False)."""
+        sources = tuple(mesh.get(k) for k in cls._API_SOURCES)
+        api = mesh.get("_api") if cache else None
+        if api is not None and len(api["sources"]) == len(sources) and all(a is b for a, b in zip(api["sources"], sources)):
+            return api
         n = len(mesh["x"])
         first = mesh.get("node_number_offset", 1)
         w0 = int(mesh.get("node_window_begin", 0))   # x / y / z hold the nodes [w0, w0 + n) of the whole model only
-        if w0:
-            self.dist_set_node_window(w0)
-        self.add_nodes(np.arange(first + w0, first + w0 + n, dtype=np.uint32), mesh["x"], mesh["y"], mesh["z"])
         num = mesh.get("element_number_offset", 1)
+        api = {"window": w0, "sources": sources,
+               "nodes": (np.arange(first + w0, first + w0 + n, dtype=np.uint32), _f64(mesh["x"]), _f64(mesh["y"]), _f64(mesh["z"]))}
         pn = np.asarray(mesh["p_n"], np.uint32).reshape(4, -1)
         if pn.shape[1]:
             pp = np.asarray(mesh["p_props"], np.float64).reshape(4, -1)
-            self.add_plates(np.arange(num, num + pn.shape[1], dtype=np.uint32), pn[0] + first, pn[1] + first,
-                            pn[2] + first, pn[3] + first, pp[0], pp[1], pp[2], pp[3])
+            api["plates"] = (np.arange(num, num + pn.shape[1], dtype=np.uint32), *[_u32(pn[i] + first) for i in range(4)],
+                             *[_f64(pp[i]) for i in range(4)])
         nb = len(mesh["b_n1"])
         if nb:
             bp = np.asarray(mesh["b_props"], np.float64).reshape(8, -1)
-            self.add_beams(np.arange(num, num + nb, dtype=np.uint32), np.asarray(mesh["b_n1"], np.uint32) + first,
-                           np.asarray(mesh["b_n2"], np.uint32) + first, *[bp[i] for i in range(8)], mesh["b_axis"])
+            api["beams"] = (np.arange(num, num + nb, dtype=np.uint32), _u32(np.asarray(mesh["b_n1"], np.uint32) + first),
+                            _u32(np.asarray(mesh["b_n2"], np.uint32) + first), *[_f64(bp[i]) for i in range(8)],
+                            _f64(mesh["b_axis"]))
         nt = len(mesh["t_n1"])
         if nt:
-            self.add_trusses(np.arange(num, num + nt, dtype=np.uint32), np.asarray(mesh["t_n1"], np.uint32) + first,
-                             np.asarray(mesh["t_n2"], np.uint32) + first, mesh["t_E"], mesh["t_A"], mesh.get("t_A2"))
+            a2 = mesh.get("t_A2")
+            api["trusses"] = (np.arange(num, num + nt, dtype=np.uint32), _u32(np.asarray(mesh["t_n1"], np.uint32) + first),
+                              _u32(np.asarray(mesh["t_n2"], np.uint32) + first), _f64(mesh["t_E"]), _f64(mesh["t_A"]),
+                              a2 if a2 is None or isinstance(a2, (list, tuple)) else _f64(a2))
+        if cache:
+            mesh["_api"] = api
+        return api
+
+    def load_mesh(self, mesh: dict, cache: bool = False) -> None:
+        """Bulk-load a mesh dict from finite_element_method_b200.meshes (node number = index + 1;
+        insertion order plates -> beams -> trusses). `cache`: see api_arrays."""
+        api = self.api_arrays(mesh, cache)
+        if api["window"]:
+            self.dist_set_node_window(api["window"])
+        self.add_nodes(*api["nodes"])
+        if "plates" in api:
+            self.add_plates(*api["plates"])
+        if "beams" in api:
+            self.add_beams(*api["beams"])
+        if "trusses" in api:
+            self.add_trusses(*api["trusses"])

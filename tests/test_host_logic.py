@@ -279,3 +279,70 @@ def test_node_window_numbers_nodes_from_its_base():
     g.reset(10)                                          # FEM::reset forgets the window
     g.add_nodes(np.arange(1, 11), np.arange(10.0), np.zeros(10), np.zeros(10))
     assert g.counts()[0] == 10
+
+
+def test_parallel_label_claims_and_partitioned_indices_keep_sequential_semantics():
+    """Batches of >= 65536 labels are claimed in the dense number table by all host cores (atomic min per label) and
+    the coordinate / node-set indices are filled shard by shard after a partition of the batch: the outcome must be
+    the one of the reference's one-by-one loop — the first failing position, its check order, a clean prefix."""
+    n = 200_000
+    rng = np.random.default_rng(5)
+    lab = rng.permutation(np.arange(1, n + 1, dtype=np.uint32))       # labels in no order at all
+    x = np.arange(n, dtype=np.float64)
+    zero = np.zeros(n)
+    f = staged(n + 8)
+    f.add_nodes(lab, x, zero, zero)
+    assert f.counts()[0] == n and np.array_equal(f.node_numbers(), lab)
+    raises(1, f"Node with number {lab[77]} already exists!", f.add_node, int(lab[77]), -1.0, 0.0, 0.0)
+    # one label three times in a batch, the later copies in other threads' chunks: the SECOND occurrence fails
+    for first, second, third in ((10, 150_000, 199_999), (120_000, 120_001, 190_000), (0, 1, 2)):
+        g = staged(n + 8)
+        l2 = lab.copy(); l2[second] = l2[first]; l2[third] = l2[first]
+        raises(1, f"Node with number {l2[first]} already exists!", g.add_nodes, l2, x, zero, zero)
+        assert g.counts()[0] == second
+        # nothing of the rejected tail stayed behind: its labels and coordinates are free
+        g.add_nodes(lab[second:], x[second:], zero[second:], zero[second:])
+        assert g.counts()[0] == n and np.array_equal(g.node_numbers(), lab)
+    # a label of an EARLIER batch in the middle of a big one; a coordinate clash before it wins, after it loses
+    g = staged(2 * n)
+    g.add_nodes(np.arange(1, 1001), -1.0 - np.arange(1000.0), np.zeros(1000), np.zeros(1000))
+    l3 = np.arange(1001, 1001 + n, dtype=np.uint32); l3[123_456] = 500
+    x3 = x.copy(); x3[180_000] = x3[5]
+    raises(1, "Node with number 500 already exists!", g.add_nodes, l3, x3, zero, zero)
+    assert g.counts()[0] == 1000 + 123_456
+    x3[100_000] = x3[5]
+    g2 = staged(2 * n)
+    g2.add_nodes(np.arange(1, 1001), -1.0 - np.arange(1000.0), np.zeros(1000), np.zeros(1000))
+    raises(4, "Node with coordinates x: 5.0, y: 0.0, z: 0.0 already exists!", g2.add_nodes, l3, x3, zero, zero)
+    assert g2.counts()[0] == 1000 + 100_000
+    # both checks fail at ONE position: the number check comes first (methods_for_node_data_handle.rs:42-64)
+    l4 = np.arange(1, n + 1, dtype=np.uint32); l4[150_000] = 9
+    x4 = x.copy(); x4[150_000] = x4[3]
+    g3 = staged(n + 8)
+    raises(1, "Node with number 9 already exists!", g3.add_nodes, l4, x4, zero, zero)
+    assert g3.counts()[0] == 150_000
+    # elements: plates on a strip, labels permuted; random duplicate positions against a sequential model
+    m = 100_000
+    h = staged(2 * m + 2)
+    k = np.arange(m + 1)
+    h.add_nodes(np.arange(1, 2 * m + 3), np.concatenate([k, k]).astype(np.float64), np.repeat([0.0, 1.0], m + 1), np.zeros(2 * m + 2))
+    n1 = np.arange(1, m + 1, dtype=np.uint32); n2 = n1 + 1; n3 = n2 + (m + 1); n4 = n1 + (m + 1)
+    props = [np.full(m, 2e11), np.full(m, 0.3), np.full(m, 0.01), np.full(m, 5 / 6)]
+    for trial in range(4):
+        el = rng.permutation(np.arange(1, m + 1, dtype=np.uint32))
+        a, b, c, d = n1.copy(), n2.copy(), n3.copy(), n4.copy()
+        pos = np.sort(rng.choice(np.arange(70_000, m), 3, replace=False))
+        kind = rng.integers(0, 2, 3)
+        for p, kd in zip(pos, kind):
+            src = int(rng.integers(0, p))
+            if kd == 0:
+                el[p] = el[src]                                          # label of an earlier plate
+            else:
+                a[p], b[p], c[p], d[p] = n3[src], n1[src], n4[src], n2[src]   # its node set, permuted
+        hh = staged(2 * m + 2)
+        hh.add_nodes(np.arange(1, 2 * m + 3), np.concatenate([k, k]).astype(np.float64), np.repeat([0.0, 1.0], m + 1), np.zeros(2 * m + 2))
+        with pytest.raises(FemError) as e:
+            hh.add_plates(el, a, b, c, d, *props)
+        assert e.value.code == (10 if kind[0] == 0 else 11), str(e.value)
+        assert hh.counts()[3] == pos[0]
+        assert np.array_equal(hh.element_numbers(PLATE), el[:pos[0]])
