@@ -59,6 +59,7 @@ SIGNATURES = {
     "femgpu_get_separated_dense": (C.c_int32, [H, C.c_int32, dp]),
     "femgpu_separated_rhs": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),
     "femgpu_last_separate_ms": (C.c_int32, [H, fp]),
+    "femgpu_last_separate_path": (C.c_int32, [H, C.POINTER(C.c_int32)]),
     "femgpu_solve_pcg": (C.c_int32, [H, C.c_int32, C.c_int64, i64p]),
     "femgpu_solve_direct": (C.c_int32, [H]),
     "femgpu_get_ua": (C.c_int32, [H, dp, C.POINTER(C.c_void_p)]),

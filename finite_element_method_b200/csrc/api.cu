@@ -172,6 +172,55 @@ inline uint64_t xyz_hash(double x, double y, double z) {
   return h;
 }
 
+// ---- host staging registered with CUDA ---------------------------------------------------------------------------
+// A re-used instance (FEM::reset, then the next model) fills the same host vectors again: from its first reset on
+// the handle registers them with CUDA (cudaHostRegister, once per allocation), so an upload is a DMA straight out of
+// the staging — no bounce through the pinned chunks, no host thread busy — and can be queued right when an add_*
+// call returns, under the host checks of the next one. Rules that keep this safe: a vector is unregistered (after a
+// stream synchronisation) before it may reallocate (make_room) and before the handle goes; whoever rewrites staging
+// that an upload may still be reading (reset, rollback) synchronises the stream first.
+bool pinned_is(Handle* h, const void* base, size_t bytes) {
+  for (const auto& r : h->pinned)
+    if (r.base == base) return r.bytes == bytes;
+  return false;
+}
+
+void pin_drop(Handle* h, const void* base) {
+  for (size_t k = 0; k < h->pinned.size(); ++k)
+    if (h->pinned[k].base == base) {
+      cudaSetDevice(h->device);
+      cudaStreamSynchronize(h->stream);
+      if (cudaHostUnregister(const_cast<void*>(base)) != cudaSuccess) cudaGetLastError();
+      h->pinned.erase(h->pinned.begin() + k);
+      return;
+    }
+}
+
+void pin_drop_all(Handle* h) {
+  while (!h->pinned.empty()) pin_drop(h, h->pinned.back().base);
+}
+
+// true when [base, base + bytes) is registered after the call
+bool pin_take(Handle* h, const void* base, size_t bytes) {
+  if (!h->pin_host || h->device < 0 || bytes < (size_t(4) << 20)) return false;
+  if (pinned_is(h, base, bytes)) return true;
+  pin_drop(h, base);  // the same address with another extent: a vector that moved back to an old block
+  if (cudaHostRegister(const_cast<void*>(base), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();  // not fatal: the staged path works for any memory
+    return false;
+  }
+  h->pinned.push_back({base, bytes});
+  return true;
+}
+
+// room for `extra` more entries; a vector that has to move is unregistered first
+template <typename T>
+void make_room(Handle* h, std::vector<T>& v, size_t extra) {
+  if (v.size() + extra <= v.capacity()) return;
+  if (!h->pinned.empty()) pin_drop(h, v.data());
+  v.reserve(std::max(v.size() + extra, v.capacity() * 2));
+}
+
 // Drop every element inserted at or after element `index` of `family` (global insertion order).
 void rollback_to(Handle* h, int family, size_t index) {
   size_t keep[kFamilies] = {0, 0, 0};
@@ -191,6 +240,7 @@ void rollback_to(Handle* h, int family, size_t index) {
     }
   }
   if (!found) return;
+  if (!h->pinned.empty()) cudaStreamSynchronize(h->stream);  // an upload may still be reading what is dropped here
   h->journal.resize(new_journal);
   for (int f = 0; f < kFamilies; ++f) {
     FamilyHost& fh = h->fh[f];
@@ -257,6 +307,13 @@ int32_t fail_after_prefix(Handle* h, int32_t code, const std::string& text) {
   int32_t st = validate_pending(h, nullptr, nullptr, nullptr);
   if (st) return st;
   return h->fail(code, text);
+}
+
+// With registered staging (pin_take) the accepted part of a large batch goes to the device right away: the copies
+// are DMAs queued on the handle's stream, they run under the host checks of the next add_* call.
+void upload_early(Handle* h, size_t accepted) {
+  if (!h->pin_host || h->device < 0 || accepted < 65536) return;
+  if (upload_pending(h)) h->last = Status();  // nothing is lost: the symbolic pass uploads again and reports
 }
 
 // Batched FEM::add_truss / add_beam / add_plate: every check of the reference, in the reference's
@@ -429,6 +486,9 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
 
   // append the accepted prefix: one bulk copy per array, the arrays spread over the host cores
   {
+    for (int c = 0; c < nn; ++c) make_room(h, fh.conn[c], accepted);
+    for (int p = 0; p < np; ++p) make_room(h, fh.props[p], accepted);
+    make_room(h, fh.cbase, accepted);
     std::vector<std::function<void()>> jobs;
     jobs.emplace_back([&] { fh.number.insert(fh.number.end(), number, number + accepted); });
     for (int c = 0; c < nn; ++c) {
@@ -467,12 +527,14 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
     status = property_check(family, pv);
     // element_error_text reads the host arrays: stage the element temporarily
     fh.number.push_back(number[e_star]);
+    for (int p = 0; p < np; ++p) make_room(h, fh.props[p], 1);
     for (int p = 0; p < np; ++p) fh.props[p].push_back(pv[p]);
     text = element_error_text(h, family, fh.number.size() - 1, status);
     fh.number.pop_back();
     for (int p = 0; p < np; ++p) fh.props[p].pop_back();
   }
   if (status) return fail_after_prefix(h, status, text);
+  upload_early(h, accepted);
   return 0;
 }
 
@@ -506,6 +568,18 @@ int32_t h2d_staged(Handle* h, void* dst, const void* src, size_t bytes) {
   return 0;
 }
 
+// entries [from, size) of a staging vector to the same positions of `dst`: a DMA out of the vector when it is
+// registered with CUDA (see pin_take), else through the pinned chunks
+template <typename T>
+int32_t h2d(Handle* h, T* dst, const std::vector<T>& host, size_t from) {
+  const size_t bytes = (host.size() - from) * sizeof(T);
+  if (pin_take(h, host.data(), host.capacity() * sizeof(T))) {
+    FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(dst + from, host.data() + from, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  }
+  return h2d_staged(h, dst + from, host.data() + from, bytes);
+}
+
 template <typename T>
 int32_t append_to_device(Handle* h, DevBuf<T>& buf, const std::vector<T>& host, size_t from) {
   size_t n = host.size();
@@ -517,13 +591,13 @@ int32_t append_to_device(Handle* h, DevBuf<T>& buf, const std::vector<T>& host, 
     nb.tally = buf.tally;
     nb.stream = buf.stream;
     FEMGPU_CUDA_CHECK(h, nb.reserve(n));
-    int32_t st = h2d_staged(h, nb.p, host.data(), n * sizeof(T));
+    int32_t st = h2d(h, nb.p, host, 0);
     if (st) return st;
     buf.release();
     buf = nb;
     return 0;
   }
-  return h2d_staged(h, buf.p + from, host.data() + from, (n - from) * sizeof(T));
+  return h2d(h, buf.p, host, from);
 }
 
 }  // namespace
@@ -628,6 +702,7 @@ int32_t femgpu_create(femgpu_t** out, double rel_tol, double abs_tol, uint32_t n
   }
   for (auto& q : h->ev)
     for (auto& ev : q) cudaEventCreate(&ev);
+  if (const char* e = getenv("FEMGPU_PIN_HOST")) h->pin_host = atoi(e) == 1;  // 1: from the first upload on, not the first reset
   *out = h;
   return 0;
 }
@@ -657,6 +732,10 @@ static void free_device(femgpu_t* h) {
 int32_t femgpu_reset(femgpu_t* h, uint32_t nodes_number) {
   if (!h) return FEMGPU_ERR_USAGE;
   if (h->device >= 0) cudaStreamSynchronize(h->stream);
+  if (h->device >= 0 && !h->pin_host) {  // a re-used instance: its staging is worth registering (FEMGPU_PIN_HOST=0: never)
+    const char* e = getenv("FEMGPU_PIN_HOST");
+    h->pin_host = !(e && atoi(e) == 0);
+  }
   // FEM::reset of a re-used instance: the device buffers stay with the handle (every one of them is rewritten before
   // it is read again — uploads restart at element 0, the symbolic products are rebuilt), like the host staging does.
   // Handing ~20 GB back to the stream-ordered pool and asking for it again cost 0.04 s on most boxes and 0.7-0.9 s
@@ -692,6 +771,7 @@ void femgpu_destroy(femgpu_t* h) {
   }
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  pin_drop_all(h);
   dist_destroy(h);
   free_device(h);
   for (auto& q : h->ev)
@@ -769,6 +849,9 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
   const size_t accepted = std::min(std::min(i_limit, i_num), i_xyz);
   for (size_t i = accepted; i < inserted; ++i) h->node_by_number.erase(number[i]);
   if (accepted < scan_end) h->node_by_xyz.erase_batch(hashes.data(), accepted, scan_end, uint32_t(n0));
+  make_room(h, h->nx, accepted);
+  make_room(h, h->ny, accepted);
+  make_room(h, h->nz, accepted);
   parallel_run(accepted >= 65536 ? std::min(4u, host_threads()) : 1u, [&](unsigned t, unsigned nt) {
     for (unsigned j = t; j < 4u; j += nt) {
       if (j == 0) h->node_number.insert(h->node_number.end(), number, number + accepted);
@@ -779,6 +862,7 @@ int32_t femgpu_add_nodes(femgpu_t* h, size_t n, const uint32_t* number, const do
   });
   lap("appends");
   if (accepted) invalidate(h);
+  if (accepted == n) upload_early(h, accepted);
   if (accepted < n) {
     const size_t e = accepted;
     if (e == i_limit)

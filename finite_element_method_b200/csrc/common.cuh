@@ -466,6 +466,8 @@ struct Handle {
     DevBuf<int32_t> col[4];
     DevBuf<double> val[4];
     DevBuf<int32_t> tmp[8];           // scratch: class flags, their scans, per-row counts of the 4 quadrants
+    DevBuf<unsigned long long> onepass;  // one-pass separation: tile states of the four running counts, ticket, flags
+    bool last_onepass = false;        // which path the last separation took
     // direct separation: k_aa_skyline and K_aa in the compacted column form (a, maxa) of the skyline solver
     bool sky_valid = false;
     int64_t sky_total = 0;
@@ -513,6 +515,13 @@ struct Handle {
   // Pinned bounce buffers of the bulk host->device path (api.cu h2d_staged): the host staging vectors
   // are pageable, so large uploads are copied chunk-wise into pinned memory by several host threads
   // while the previous chunk is on its way over PCIe.
+  // host staging vectors registered with CUDA (api.cu: pin_take / make_room); on from the first femgpu_reset
+  struct PinnedRegion {
+    const void* base;
+    size_t bytes;
+  };
+  std::vector<PinnedRegion> pinned;
+  bool pin_host = false;
   static constexpr size_t kPinChunk = size_t(16) << 20;
   void* pin_buf[2] = {nullptr, nullptr};
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -542,6 +551,7 @@ struct Handle {
       tie(sep.row_ptr[q]); tie(sep.col[q]); tie(sep.val[q]);
     }
     for (auto& t : sep.tmp) tie(t);
+    tie(sep.onepass);
     tie(sep.sky); tie(sep.maxa); tie(sep.sky_a);
     tie(sol.u_a); tie(sol.r_r); tie(sol.r); tie(sol.z); tie(sol.p); tie(sol.ap); tie(sol.minv); tie(sol.blk);
     tie(sol.partial); tie(sol.scal); tie(sol.disp); tie(sol.force);

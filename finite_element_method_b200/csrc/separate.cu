@@ -243,6 +243,301 @@ quadrant_kernel(int64_t n_rows, const int64_t* __restrict__ row_ptr, const int32
   }
 }
 
+// ---- one-pass separation ------------------------------------------------------------------------------------------
+// count + fill above read col_idx and values from HBM twice: the counts of ALL rows are scanned before the first
+// entry can be placed. Here a CTA takes a tile of 128 consecutive rows (~80 KB of K), counts it, joins four chained
+// scans over the tiles with the tile's counts (aa, ab over its a-rows; ba, bb over its b-rows) — it publishes its own
+// counts at once, then adds up its predecessors' words until it meets one that already holds a running total
+// (decoupled look-back) — and walks the tile a second time to place the entries, while those 80 KB are still in the
+// L2. So K comes out of HBM once. Tiles take their number from a ticket counter: a tile's predecessors are always
+// running or done. The outputs are sized by upper bounds (run_separate); a spin that does not end or a bound that
+// does not hold raises a flag and the caller falls back to the two passes.
+// (A tile of 32 rows kept in registers between the two steps was measured first: 28.5 ms on config M against 12.7 —
+// 750 000 tiles at three CTAs per SM, each waiting on its look-back with its loads already spent.)
+constexpr int kTileIters = 4;
+constexpr int kTileRows = 8 * kRowsPerWarp * kTileIters;       // 256 threads: 8 warps x 4 rows x 4 rounds
+constexpr unsigned long long kTileMask = (1ull << 62) - 1ull;  // word = state << 62 | count; state 1: own count, 2: running total
+constexpr uint32_t kSpinLimit = 1u << 21;
+
+struct OnePass {
+  unsigned long long* state[4];  // [n_tiles] per quadrant
+  unsigned int* ticket;
+  int* error;
+  int64_t cap[4];
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// counts of one row of any length (the loop of quadrant_row<false>)
+__device__ __forceinline__ void count_long_row(uint32_t lane, int64_t begin, int64_t end, const int32_t* __restrict__ col_idx,
+                                               const double* __restrict__ values, const uint32_t* __restrict__ cls_pos,
+                                               uint32_t& na, uint32_t& nb) {
+  na = nb = 0;
+  for (int64_t p = begin + lane; p - lane < end; p += 32) {
+    bool in_a = false, in_b = false;
+    if (p < end && values[p] != 0.0) {
+      const uint32_t cc = cls_pos[col_idx[p]];
+      in_a = (cc >> 30) == kClsA;
+      in_b = (cc >> 30) == kClsB;
+    }
+    na += __popc(__ballot_sync(0xFFFFFFFFu, in_a));
+    nb += __popc(__ballot_sync(0xFFFFFFFFu, in_b));
+  }
+}
+
+__device__ __forceinline__ void fill_long_row(uint32_t lane, int qa, int64_t wa, int64_t wb, int64_t begin, int64_t end,
+                                              const int32_t* __restrict__ col_idx, const double* __restrict__ values,
+                                              const uint32_t* __restrict__ cls_pos, const SepOut& out) {
+  const int qb = qa + 1;
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t na = 0, nb = 0;
+  for (int64_t p = begin + lane; p - lane < end; p += 32) {
+    bool in_a = false, in_b = false;
+    double v = 0.0;
+    uint32_t cloc = 0;
+    if (p < end) {
+      v = values[p];
+      if (v != 0.0) {
+        const uint32_t cc = cls_pos[col_idx[p]];
+        in_a = (cc >> 30) == kClsA;
+        in_b = (cc >> 30) == kClsB;
+        cloc = cc & 0x3FFFFFFFu;
+      }
+    }
+    const uint32_t ma = __ballot_sync(0xFFFFFFFFu, in_a), mb = __ballot_sync(0xFFFFFFFFu, in_b);
+    if (in_a) {
+      const int64_t w = wa + na + __popc(ma & below);
+      out.col[qa][w] = int32_t(cloc);
+      out.val[qa][w] = v;
+    } else if (in_b) {
+      const int64_t w = wb + nb + __popc(mb & below);
+      out.col[qb][w] = int32_t(cloc);
+      out.val[qb][w] = v;
+    }
+    na += __popc(ma);
+    nb += __popc(mb);
+  }
+}
+
+// kRowsPerWarp consecutive rows of one warp: pointers, classes and — when none is longer than 64 entries — the
+// entries with their columns' classes in registers (the loads of all rows issued back to back)
+struct WarpRows {
+  int64_t begin[kRowsPerWarp], end[kRowsPerWarp];
+  uint32_t rc[kRowsPerWarp];
+  double v[kRowsPerWarp][2];
+  uint32_t cc[kRowsPerWarp][2];
+  bool all_short;
+};
+
+__device__ __forceinline__ void load_warp_rows(WarpRows& w, int64_t row0, uint32_t lane, int64_t n_rows,
+                                               const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                               const double* __restrict__ values, const uint32_t* __restrict__ cls_pos) {
+  const int64_t my_row = row0 + lane;
+  const int64_t ptr_l = (lane <= uint32_t(kRowsPerWarp) && my_row <= n_rows) ? row_ptr[my_row] : 0;
+  const uint32_t cls_l = (lane < uint32_t(kRowsPerWarp) && my_row < n_rows) ? cls_pos[my_row] : 0u;
+  w.all_short = true;
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    w.begin[r] = __shfl_sync(0xFFFFFFFFu, ptr_l, r);
+    w.end[r] = __shfl_sync(0xFFFFFFFFu, ptr_l, r + 1);
+    w.rc[r] = __shfl_sync(0xFFFFFFFFu, cls_l, r);
+    if (row0 + r >= n_rows) {
+      w.rc[r] = 0u;
+      w.end[r] = w.begin[r];
+    }
+    w.all_short = w.all_short && (w.end[r] - w.begin[r] <= 64);
+  }
+  if (!w.all_short) return;
+  int32_t c[kRowsPerWarp][2];
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int64_t p = w.begin[r] + lane + 32 * k;
+      const bool on = (w.rc[r] >> 30) != kClsNone && p < w.end[r];
+      w.v[r][k] = on ? values[p] : 0.0;
+      c[r][k] = on ? col_idx[p] : 0;
+    }
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) w.cc[r][k] = (w.v[r][k] != 0.0) ? cls_pos[c[r][k]] : 0u;
+}
+
+__global__ void __launch_bounds__(256, 4)
+quadrant_onepass_kernel(int64_t n_rows, uint32_t n_tiles, const int64_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ col_idx, const double* __restrict__ values,
+                        const uint32_t* __restrict__ cls_pos, SepOut out, OnePass op) {
+  static_assert(kTileRows == 128, "four rows per lane in the scan step");
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_n[2][kTileRows], s_rc[kTileRows], s_ex[2][kTileRows];
+  __shared__ unsigned long long s_base[4];
+  if (threadIdx.x == 0) s_tile = atomicAdd(op.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  if (tile >= n_tiles) return;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const int64_t tile_row0 = int64_t(tile) * kTileRows;
+
+  // ---- 1. count: in round `it` the eight warps take 32 consecutive rows
+#pragma unroll 1
+  for (int it = 0; it < kTileIters; ++it) {
+    const uint32_t t0 = (uint32_t(it) * 8 + warp) * kRowsPerWarp;
+    WarpRows w;
+    load_warp_rows(w, tile_row0 + t0, lane, n_rows, row_ptr, col_idx, values, cls_pos);
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      uint32_t na = 0, nb = 0;
+      if (w.all_short) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          na += __popc(__ballot_sync(0xFFFFFFFFu, (w.cc[r][k] >> 30) == kClsA));
+          nb += __popc(__ballot_sync(0xFFFFFFFFu, (w.cc[r][k] >> 30) == kClsB));
+        }
+      } else if ((w.rc[r] >> 30) != kClsNone) {
+        count_long_row(lane, w.begin[r], w.end[r], col_idx, values, cls_pos, na, nb);
+      }
+      if (lane == 0) {
+        s_n[0][t0 + r] = na;
+        s_n[1][t0 + r] = nb;
+        s_rc[t0 + r] = w.rc[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. warps 0..3: quadrant q = warp. In-tile offsets (four rows per lane), then the tile's place among the tiles
+  if (warp < 4) {
+    const int q = int(warp);
+    const uint32_t want = q < 2 ? kClsA : kClsB;
+    uint32_t cnt[4], lane_sum = 0;
+    bool mine[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mine[j] = (s_rc[4 * lane + j] >> 30) == want;
+      cnt[j] = mine[j] ? s_n[q & 1][4 * lane + j] : 0u;
+      lane_sum += cnt[j];
+    }
+    uint32_t incl = lane_sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= uint32_t(d)) incl += t;
+    }
+    uint32_t run = incl - lane_sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (mine[j]) s_ex[q & 1][4 * lane + j] = run;
+      run += cnt[j];
+    }
+    const unsigned long long agg = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long* state = op.state[q];
+    unsigned long long before = 0;
+    if (tile == 0) {
+      if (lane == 0) st_relaxed_u64(state, (2ull << 62) | agg);
+    } else {
+      if (lane == 0) st_relaxed_u64(state + tile, (1ull << 62) | agg);
+      int64_t look = int64_t(tile) - 1;
+      uint32_t spins = 0;
+      for (;;) {
+        const int64_t idx = look - lane;  // lane 0: the nearest predecessor
+        unsigned long long w = idx >= 0 ? ld_relaxed_u64(state + idx) : (2ull << 62);
+        while (__any_sync(0xFFFFFFFFu, (w >> 62) == 0)) {
+          if ((w >> 62) == 0) w = ld_relaxed_u64(state + idx);
+          if (++spins > kSpinLimit) break;
+        }
+        if (spins > kSpinLimit) {  // warp-uniform (every lane counts the same rounds)
+          if (lane == 0) atomicExch(op.error, 1);
+          break;
+        }
+        const uint32_t done = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
+        const uint32_t upto = done ? uint32_t(__ffs(done) - 1) : 31u;
+        unsigned long long part = lane <= upto ? (w & kTileMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+        before += part;
+        if (done) break;
+        look -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(state + tile, (2ull << 62) | ((before + agg) & kTileMask));
+    }
+    if (lane == 0) {
+      s_base[q] = before;
+      if (int64_t(before + agg) > op.cap[q]) atomicExch(op.error, 2);
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. fill: the same walk again (the tile is in the L2), row pointers and entries at their final places
+  const uint32_t below = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int it = 0; it < kTileIters; ++it) {
+    const uint32_t t0 = (uint32_t(it) * 8 + warp) * kRowsPerWarp;
+    WarpRows w;
+    load_warp_rows(w, tile_row0 + t0, lane, n_rows, row_ptr, col_idx, values, cls_pos);
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const uint32_t rcls = w.rc[r] >> 30, rloc = w.rc[r] & 0x3FFFFFFFu;
+      if (rcls == kClsNone) continue;  // warp-uniform
+      const int qa = rcls == kClsA ? 0 : 2, qb = qa + 1;
+      const int64_t wa = int64_t(s_base[qa]) + s_ex[0][t0 + r], wb = int64_t(s_base[qb]) + s_ex[1][t0 + r];
+      if (lane == 0) {
+        out.row_ptr[qa][rloc] = wa;
+        out.row_ptr[qb][rloc] = wb;
+      }
+      if (wa + s_n[0][t0 + r] > op.cap[qa] || wb + s_n[1][t0 + r] > op.cap[qb]) continue;  // flagged in step 2: nothing goes out of bounds
+      if (!w.all_short) {
+        fill_long_row(lane, qa, wa, wb, w.begin[r], w.end[r], col_idx, values, cls_pos, out);
+        continue;
+      }
+      uint32_t ka = 0, kb = 0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const bool in_a = (w.cc[r][k] >> 30) == kClsA, in_b = (w.cc[r][k] >> 30) == kClsB;
+        const uint32_t ma = __ballot_sync(0xFFFFFFFFu, in_a), mb = __ballot_sync(0xFFFFFFFFu, in_b);
+        if (in_a) {
+          const int64_t pos = wa + ka + __popc(ma & below);
+          out.col[qa][pos] = int32_t(w.cc[r][k] & 0x3FFFFFFFu);
+          out.val[qa][pos] = w.v[r][k];
+        } else if (in_b) {
+          const int64_t pos = wb + kb + __popc(mb & below);
+          out.col[qb][pos] = int32_t(w.cc[r][k] & 0x3FFFFFFFu);
+          out.val[qb][pos] = w.v[r][k];
+        }
+        ka += __popc(ma);
+        kb += __popc(mb);
+      }
+    }
+  }
+}
+
+// closes the four row-pointer arrays with the totals of the last tile and hands the totals to the host
+__global__ void onepass_finish_kernel(uint32_t n_tiles, OnePass op, SepOut out, int64_t n_aa, int64_t n_bb,
+                                      unsigned long long* __restrict__ totals) {
+  const int q = threadIdx.x;
+  if (q >= 4) return;
+  const unsigned long long total = n_tiles ? (op.state[q][n_tiles - 1] & kTileMask) : 0ull;
+  out.row_ptr[q][q < 2 ? n_aa : n_bb] = int64_t(total);
+  totals[q] = total;
+}
+
+// structural entries of the constrained rows: with the symmetric block pattern, no quadrant but aa holds more
+__global__ void b_rows_entries_kernel(int64_t n_rows, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ is_b,
+                                      unsigned long long* __restrict__ sum) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  unsigned long long len = (i < n_rows && is_b[i]) ? (unsigned long long)(row_ptr[i + 1] - row_ptr[i]) : 0ull;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) len += __shfl_xor_sync(0xFFFFFFFFu, len, d);
+  if ((threadIdx.x & 31u) == 0 && len) atomicAdd(sum, len);
+}
+
 // b = R_a - K_ab u_b, one thread per a-row, summed in row order (find_b_sparse)
 __global__ void rhs_kernel(int64_t n_aa, const int64_t* __restrict__ aa_idx, const int64_t* __restrict__ bb_idx,
                            const double* __restrict__ force, const double* __restrict__ disp,
@@ -341,6 +636,7 @@ void sep_release(Handle* h) {
   S.aa_idx.release(); S.bb_idx.release(); S.rhs.release(); S.sky.release(); S.maxa.release(); S.sky_a.release();
   S.sky_valid = false;
   for (auto& t : S.tmp) t.release();
+  S.onepass.release();
   for (int q = 0; q < 4; ++q) {
     S.row_ptr[q].release(); S.col[q].release(); S.val[q].release();
   }
@@ -516,11 +812,17 @@ int32_t run_separate(Handle* h, bool direct) {
                                                   direct ? S.d_force.p : nullptr, is_a.p, is_b.p, d_bad);
     h->launches++;
   }
+  FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(d_bad + 1, 0, 8, s));
+  if (n) {
+    b_rows_entries_kernel<<<div_up(n, 256), 256, 0, s>>>(n, h->row_ptr.p, is_b.p, d_bad + 1);
+    h->launches++;
+  }
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
   FEMGPU_CUDA_CHECK(h, scan_i32(is_a.p, pos_a.p, n + 1, s));
   FEMGPU_CUDA_CHECK(h, scan_i32(is_b.p, pos_b.p, n + 1, s));
-  unsigned long long bad = 0;
+  unsigned long long bad = 0, b_entries = 0;
   int32_t n_aa = 0, n_bb = 0;
+  FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&b_entries, d_bad + 1, 8, cudaMemcpyDeviceToHost, s));
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&n_aa, pos_a.p + n, 4, cudaMemcpyDeviceToHost, s));
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&n_bb, pos_b.p + n, 4, cudaMemcpyDeviceToHost, s));
@@ -549,10 +851,64 @@ int32_t run_separate(Handle* h, bool direct) {
                                               S.bb_idx.p);
   h->launches++;
 
-  // ---- 3. counts per row and quadrant -> row pointers
   const int64_t rows_q[4] = {n_aa, n_aa, n_bb, n_bb};
-  DevBuf<int32_t>* cnt = S.tmp + 4;
   SepOut out{};
+  // ---- 3 + 4 in one pass over K (quadrant_onepass_kernel), on request: FEMGPU_SEP_ONE_PASS=1. Same result, K out of
+  // HBM once instead of twice — and slower than count + fill on every configuration measured (16.4 ms against 12.7 on
+  // config M, profiles/README.md round 2): the second walk over a tile pays the same dependent load chains out of the
+  // L2, and a CTA waits on two barriers and its look-back in between. Kept with its tests as the starting point for
+  // a tile staged in shared memory by bulk copies. The four outputs are sized by upper bounds: K_aa by the entries
+  // != 0.0 of K when the compacted copy of this pass exists (femgpu_get_nonzero_csr), else by the structural entries;
+  // the other three by the structural entries of the constrained rows. Not enough memory for that, a bound that
+  // does not hold or a scan that does not finish -> the two passes below.
+  S.last_onepass = false;
+  const char* one_pass_env = getenv("FEMGPU_SEP_ONE_PASS");
+  if (one_pass_env && atoi(one_pass_env) == 1 && n > 0) {
+    const uint32_t n_tiles = uint32_t(div_up(n, kTileRows));
+    int64_t all = h->nnz;
+    if (h->nz_valid && h->nz_pass == h->n_numeric) all = std::min(all, h->nz_count);
+    const int64_t side = std::min<int64_t>(all, int64_t(b_entries));
+    OnePass op{};
+    const int64_t cap[4] = {all, side, side, side};
+    bool room = S.onepass.reserve(4 * size_t(n_tiles) + 16) == cudaSuccess;
+    for (int q = 0; q < 4 && room; ++q) {
+      room = S.row_ptr[q].reserve(size_t(rows_q[q]) + 1) == cudaSuccess && S.col[q].reserve(size_t(cap[q]) + 1) == cudaSuccess &&
+             S.val[q].reserve(size_t(cap[q]) + 1) == cudaSuccess;
+      op.cap[q] = cap[q];
+    }
+    if (!room) cudaGetLastError();
+    if (room) {
+      FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(S.onepass.p, 0, (4 * size_t(n_tiles) + 16) * 8, s));
+      unsigned long long* tail = S.onepass.p + 4 * size_t(n_tiles);  // [0] ticket, [1] error, [2..5] totals
+      for (int q = 0; q < 4; ++q) {
+        op.state[q] = S.onepass.p + size_t(q) * n_tiles;
+        out.row_ptr[q] = S.row_ptr[q].p;
+        out.col[q] = S.col[q].p;
+        out.val[q] = S.val[q].p;
+      }
+      op.ticket = reinterpret_cast<unsigned int*>(tail);
+      op.error = reinterpret_cast<int*>(tail + 1);
+      quadrant_onepass_kernel<<<n_tiles, 256, 0, s>>>(n, n_tiles, h->row_ptr.p, h->col_idx.p, h->values.p, S.cls_pos.p, out, op);
+      onepass_finish_kernel<<<1, 32, 0, s>>>(n_tiles, op, out, n_aa, n_bb, tail + 2);
+      h->launches += 2;
+      FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+      unsigned long long back[5] = {0, 0, 0, 0, 0};
+      FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(back, tail + 1, sizeof back, cudaMemcpyDeviceToHost, s));
+      FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(s));
+      if (int(back[0] & 0xFFFFFFFFull) == 0) {
+        for (int q = 0; q < 4; ++q) S.nnz[q] = int64_t(back[1 + q]);
+        S.last_onepass = true;
+      } else if (getenv("FEMGPU_ASM_INFO")) {
+        fprintf(stderr, "[femgpu separate] one-pass kernel gave up (flag %d): two passes\n", int(back[0] & 0xFFFFFFFFull));
+      }
+    }
+  }
+  if (S.last_onepass && !direct && S.nnz[0] == 0)
+    return h->fail(FEMGPU_E_KAA_EMPTY, "Sparse separation: K_aa is empty (structure has no free stiffness?)");
+
+  if (!S.last_onepass) {
+  // ---- 3. counts per row and quadrant -> row pointers
+  DevBuf<int32_t>* cnt = S.tmp + 4;
   for (int q = 0; q < 4; ++q) {
     FEMGPU_CUDA_CHECK(h, cnt[q].reserve(size_t(rows_q[q]) + 1));
     FEMGPU_CUDA_CHECK(h, cudaMemsetAsync(cnt[q].p, 0, (size_t(rows_q[q]) + 1) * 4, s));
@@ -582,6 +938,7 @@ int32_t run_separate(Handle* h, bool direct) {
   quadrant_kernel<true><<<warp_grid, 256, 0, s>>>(n, h->row_ptr.p, h->col_idx.p, h->values.p, S.cls_pos.p, out);
   h->launches++;
   FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  }
 
   // ---- b = R_a - K_ab u_b
   FEMGPU_CUDA_CHECK(h, S.rhs.reserve(size_t(n_aa) + 1));
@@ -864,6 +1221,13 @@ int32_t femgpu_separated_rhs(femgpu_t* h, double* b, const double** b_device) {
     FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   }
   if (b_device) *b_device = h->sep.rhs.p;
+  return 0;
+}
+
+int32_t femgpu_last_separate_path(femgpu_t* h, int32_t* one_pass) {
+  int32_t st = sep_ready(h);
+  if (st) return st;
+  if (one_pass) *one_pass = h->sep.last_onepass ? 1 : 0;
   return 0;
 }
 

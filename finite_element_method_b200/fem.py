@@ -374,6 +374,12 @@ class FEM:
         self._check(self._L.femgpu_get_forces(self._h, _p(out, _lib.dp), None))
         return out
 
+    def last_separation_read_k_once(self) -> bool:
+        """True when the last separation took the one-pass path (femgpu_last_separate_path)"""
+        flag = C.c_int32()
+        self._check(self._L.femgpu_last_separate_path(self._h, C.byref(flag)))
+        return bool(flag.value)
+
     def separate_stiffness_matrix_sparse_iterative(self, copy_out: bool = True):
         """methods_for_separate_stiffness_matrix.rs:217, on the device. copy_out=False leaves the
         quadrants in HBM (returns counts only): (n_aa, n_bb, [nnz_aa, nnz_ab, nnz_ba, nnz_bb], device_ms)."""

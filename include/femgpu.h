@@ -280,6 +280,10 @@ int32_t femgpu_get_separated_dense(femgpu_t* h, int32_t which, double* out);
 int32_t femgpu_separated_rhs(femgpu_t* h, double* b, const double** b_device);
 /* device milliseconds of the last femgpu_separate_sparse() */
 int32_t femgpu_last_separate_ms(femgpu_t* h, float* ms);
+/* *one_pass = 1 when the last separation read K from HBM once (FEMGPU_SEP_ONE_PASS=1: tiles of 128 rows chained by a
+ * scan over the tiles, outputs sized by upper bounds), 0 for count + fill (the default: faster as measured; also the
+ * fallback when the bounds do not fit in memory). Same result either way. */
+int32_t femgpu_last_separate_path(femgpu_t* h, int32_t* one_pass);
 
 /* ---- global analysis and element results (downstream of the separated matrix, all in HBM) ---- */
 

@@ -194,6 +194,56 @@ def test_gpu_separation_fullsize_properties():
     fem.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["plates", "mixed", "long-rows"])
+def test_one_pass_separation_equals_count_and_fill(which, monkeypatch):
+    """FEMGPU_SEP_ONE_PASS=1: the separation reads K from HBM once (tiles of 128 rows chained by a scan over the
+    tiles); count + fill is the default. Both must give the same four CSR quadrants, indexes and right-hand side, bit for bit — on meshes of
+    tens of thousands of tiles, with constrained DOFs spread over the model (large K_ab / K_ba / K_bb), and with rows
+    longer than the 64 entries a warp keeps in registers."""
+    if which == "plates":
+        mesh = meshes.plate_grid(600, 400, "flat")
+    elif which == "mixed":
+        mesh = meshes.mixed_structure(300, 250, variant="x0")
+    else:
+        mesh = meshes.truss_lattice(40, 10**9, jitter=True)     # lattice + body diagonals: up to 8 neighbours x 3 ... and
+        # a hub: every 50th node (53, 103, ...) tied to node 0 -> one row of several thousand entries, its neighbours above 64
+        hub = np.arange(53, len(mesh["x"]), 50, dtype=np.uint32)
+        mesh["t_n1"] = np.concatenate([mesh["t_n1"], np.zeros(len(hub), np.uint32)])
+        mesh["t_n2"] = np.concatenate([mesh["t_n2"], hub])
+        mesh["t_E"] = np.concatenate([mesh["t_E"], np.full(len(hub), 2.1e11)])
+        mesh["t_A"] = np.concatenate([mesh["t_A"], np.full(len(hub), 1e-4)])
+    n = len(mesh["x"])
+    fem = FEM(mesh["rel_tol"], mesh["abs_tol"], n, device=0)
+    fem.load_mesh(mesh)
+    fem.assemble()
+    rng = np.random.default_rng(3)
+    nodes = np.sort(rng.choice(n, n // 7, replace=False))
+    ndof = 3 if which == "long-rows" else 6                      # trusses carry no rotational stiffness
+    fem.add_displacement(np.repeat(nodes + 1, ndof), np.tile(np.arange(ndof), len(nodes)), rng.normal(0, 1e-3, ndof * len(nodes)))
+    free = np.setdiff1d(np.arange(n), nodes)[::11]
+    fem.add_concentrated_load(free + 1, np.full(len(free), 2), rng.normal(0, 1e3, len(free)))
+    monkeypatch.setenv("FEMGPU_SEP_ONE_PASS", "1")
+    one = fem.separate_stiffness_matrix_sparse_iterative()
+    assert fem.last_separation_read_k_once()
+    monkeypatch.delenv("FEMGPU_SEP_ONE_PASS")
+    two = fem.separate_stiffness_matrix_sparse_iterative()
+    assert not fem.last_separation_read_k_once()
+    assert np.array_equal(one.k_aa_indexes, two.k_aa_indexes) and np.array_equal(one.k_bb_indexes, two.k_bb_indexes)
+    for a, b in zip((one.k_aa, one.k_ab, one.k_ba, one.k_bb), (two.k_aa, two.k_ab, two.k_ba, two.k_bb)):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert np.array_equal(one.b, two.b)
+    assert min(len(q[2]) for q in (one.k_aa, one.k_ab, one.k_ba, one.k_bb)) > 1000
+    if which == "long-rows":
+        rp = fem.csr()[0]
+        assert np.diff(rp).max() > 1000
+    monkeypatch.setenv("FEMGPU_SEP_ONE_PASS", "1")
+    again = fem.separate_stiffness_matrix_sparse_iterative()     # and deterministic
+    assert fem.last_separation_read_k_once() and np.array_equal(again.k_aa[2], one.k_aa[2]) and np.array_equal(again.k_aa[0], one.k_aa[0])
+    fem.close()
+
+
 # ---------------------------------------------------------------------------- distributed loads (§8f rank 2)
 def test_oracle_distributed_loads_analytic():
     """beam.rs:775-797 / plate.rs:1145-1185: a uniform load q on a straight member of length L gives
