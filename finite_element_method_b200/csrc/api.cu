@@ -258,7 +258,7 @@ void rollback_to(Handle* h, int family, size_t index) {
       fh.conn_number[c].resize(keep[f]);
     }
     for (int p = 0; p < kPropsPerElem[f]; ++p) fh.props[p].resize(keep[f]);
-    fh.cbase.resize(keep[f]);
+    fh.cbase_truncate(keep[f]);
     h->fd[f].uploaded = std::min(h->fd[f].uploaded, keep[f]);
     h->fd[f].validated = std::min(h->fd[f].validated, keep[f]);
   }
@@ -488,7 +488,6 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
   {
     for (int c = 0; c < nn; ++c) make_room(h, fh.conn[c], accepted);
     for (int p = 0; p < np; ++p) make_room(h, fh.props[p], accepted);
-    make_room(h, fh.cbase, accepted);
     std::vector<std::function<void()>> jobs;
     jobs.emplace_back([&] { fh.number.insert(fh.number.end(), number, number + accepted); });
     for (int c = 0; c < nn; ++c) {
@@ -507,12 +506,8 @@ int32_t add_elements(Handle* h, int family, size_t n, const uint32_t* number,
     });
   }
   lap("appends");
-  fh.cbase.resize(start + accepted);
-  parallel_chunks(accepted, 65536, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) fh.cbase[start + i] = h->n_contrib + int64_t(i) * kPairsPerElem[family];
-  });
+  fh.cbase_append(start, accepted, h->n_contrib, kPairsPerElem[family]);
   h->n_contrib += int64_t(accepted) * kPairsPerElem[family];
-  lap("cbase");
   if (accepted) {
     if (!h->journal.empty() && h->journal.back().first == family)
       h->journal.back().second += accepted;
@@ -604,6 +599,37 @@ int32_t append_to_device(Handle* h, DevBuf<T>& buf, const std::vector<T>& host, 
 
 namespace femgpu {
 
+namespace {
+
+__global__ void cbase_fill_kernel(int64_t* __restrict__ out, uint32_t count, int64_t base, int pairs) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = base + int64_t(i) * pairs;
+}
+
+// device cbase of the elements [from, size) of family f, run by run (FamilyHost::cbase_runs)
+int32_t fill_cbase(Handle* h, int f, size_t from) {
+  FamilyHost& fh = h->fh[f];
+  FamilyDev& fd = h->fd[f];
+  const size_t n = fh.size();
+  if (n <= from) return 0;
+  if (n > fd.cbase.cap) {  // grow: everything again, like append_to_device
+    fd.cbase.release();
+    FEMGPU_CUDA_CHECK(h, fd.cbase.reserve(n));
+    from = 0;
+  }
+  for (const auto& r : fh.cbase_runs) {
+    const size_t b = std::max(r.start, from), e = r.start + r.count;
+    if (b >= e) continue;
+    cbase_fill_kernel<<<div_up(e - b, 256), 256, 0, h->stream>>>(fd.cbase.p + b, uint32_t(e - b),
+                                                               r.base + int64_t(b - r.start) * kPairsPerElem[f], kPairsPerElem[f]);
+    h->launches++;
+  }
+  FEMGPU_CUDA_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
 int32_t upload_pending(Handle* h) {
   FEMGPU_CUDA_CHECK(h, cudaSetDevice(h->device));
   int32_t st;
@@ -618,7 +644,7 @@ int32_t upload_pending(Handle* h) {
       if ((st = append_to_device(h, fd.conn[c], fh.conn[c], fd.uploaded))) return st;
     for (int p = 0; p < kPropsPerElem[f]; ++p)
       if ((st = append_to_device(h, fd.props[p], fh.props[p], fd.uploaded))) return st;
-    if ((st = append_to_device(h, fd.cbase, fh.cbase, fd.uploaded))) return st;
+    if ((st = fill_cbase(h, f, fd.uploaded))) return st;
     fd.uploaded = fh.size();
   }
   return 0;

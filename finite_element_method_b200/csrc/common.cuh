@@ -232,8 +232,48 @@ struct FamilyHost {
   std::vector<uint32_t> conn[4];      // node indices (0-based), SoA
   std::vector<uint32_t> conn_number[4];  // node numbers as given (for messages)
   std::vector<double> props[11];      // SoA
-  std::vector<int64_t> cbase;         // offset of the element's first contribution in global
-                                      // insertion order (= accumulation order of the reference)
+  // Offset of every element's first contribution in global insertion order (= accumulation order of the reference).
+  // Inside one accepted batch it is affine in the element index, so the host keeps one run per batch and the device
+  // array is filled by a kernel (api.cu upload_pending) instead of being written, copied and uploaded per element.
+  struct CbaseRun {
+    size_t start, count;  // elements [start, start + count) of the family
+    int64_t base;         // cbase of element `start`; + pairs per element for each following one
+  };
+  std::vector<CbaseRun> cbase_runs;
+  int64_t cbase_at(size_t i, int pairs) const {
+    size_t lo = 0, hi = cbase_runs.size();
+    while (hi - lo > 1) {
+      size_t mid = (lo + hi) / 2;
+      if (cbase_runs[mid].start <= i) lo = mid;
+      else hi = mid;
+    }
+    return cbase_runs[lo].base + int64_t(i - cbase_runs[lo].start) * pairs;
+  }
+  // the element whose first contribution sits at `cb` (runs ascend in base as they do in start)
+  size_t index_of_cbase(int64_t cb, int pairs) const {
+    size_t lo = 0, hi = cbase_runs.size();
+    while (hi - lo > 1) {
+      size_t mid = (lo + hi) / 2;
+      if (cbase_runs[mid].base <= cb) lo = mid;
+      else hi = mid;
+    }
+    return cbase_runs[lo].start + size_t((cb - cbase_runs[lo].base) / pairs);
+  }
+  void cbase_append(size_t start, size_t count, int64_t base, int pairs) {
+    if (!count) return;
+    if (!cbase_runs.empty()) {
+      CbaseRun& b = cbase_runs.back();
+      if (b.start + b.count == start && b.base + int64_t(b.count) * pairs == base) {
+        b.count += count;
+        return;
+      }
+    }
+    cbase_runs.push_back({start, count, base});
+  }
+  void cbase_truncate(size_t keep) {
+    while (!cbase_runs.empty() && cbase_runs.back().start >= keep) cbase_runs.pop_back();
+    if (!cbase_runs.empty()) cbase_runs.back().count = std::min(cbase_runs.back().count, keep - cbase_runs.back().start);
+  }
   NumberMap by_number;
   size_t size() const { return number.size(); }
   // FEM::reset: forget the elements, keep the storage (a re-used instance re-fills the same pages instead of
@@ -243,7 +283,7 @@ struct FamilyHost {
     for (auto& v : conn) v.clear();
     for (auto& v : conn_number) v.clear();
     for (auto& v : props) v.clear();
-    cbase.clear();
+    cbase_runs.clear();
     by_number.clear();
   }
 };

@@ -459,8 +459,7 @@ int32_t first_error(Handle* h, int* family, size_t* index, int* code) {
   }
   int f = int(key & 3);
   int64_t cb = int64_t(key >> 2);
-  const auto& cbv = h->fh[f].cbase;
-  size_t idx = size_t(std::lower_bound(cbv.begin(), cbv.end(), cb) - cbv.begin());
+  size_t idx = h->fh[f].index_of_cbase(cb, kPairsPerElem[f]);
   int32_t ec = 0;
   FEMGPU_CUDA_CHECK(h, cudaMemcpyAsync(&ec, h->fd[f].err.p + idx, 4, cudaMemcpyDeviceToHost, h->stream));
   FEMGPU_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));

@@ -124,6 +124,16 @@ def fullsize(rank, world, local, dist, torch):
     nodes = sample_nodes(n, w, lo=begin, hi=end, n_random=max(2000, 10_000 // world), lines=(j0, j0 + 1, j1 - 1))
     rep = compare_sampled_rows(fem, mesh, nodes, rtol=1e-12, faithful=True, device=f"cuda:{local}")
     assert rep["n_fail"] == 0 and rep["max_block_rel"] <= 1e-12, (rank, rep)
+    # the instance re-used (FEM::reset): staging registered with CUDA, every batch uploaded as it is added — with a
+    # node window and ghost rows in play. Same strip, same bits.
+    v1 = fem.csr(values_only=True).copy()
+    for _ in range(2):
+        fem.reset(n)
+        fem.dist_set_ownership(begin, end)
+        fem.load_mesh(part, cache=True)
+        fem.assemble()
+        assert np.array_equal(v1, fem.csr(values_only=True)), "assembly of the re-used handle differs"
+    del v1
     tot = torch.tensor([float(rep["nodes"]), float(rep["entries"]), rep["max_block_rel"]], device="cuda", dtype=torch.float64)
     mx = tot.clone()
     dist.all_reduce(tot)
