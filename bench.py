@@ -654,7 +654,9 @@ def measure_e2e(args, local, n_nodes, local_rank, n_el_local, n_el_total, dist, 
                        "compacted on the device, into pinned host memory" + (" — per rank: its own rows" if world > 1 else ""))
     out["structural_readback"] = dict(results["structural"], readback="femgpu_get_csr: all values of the structural block pattern")
     out["includes"] = ("femgpu_reset, add_nodes/add_* host validation + H2D, symbolic pass, numeric pass, device-side compaction, "
-                       "D2H of the matrix (handle and NCCL communicator created once, outside the timed steps)")
+                       "D2H of the matrix (handle and NCCL communicator created once, outside the timed steps; the label arrays "
+                       "the caller passes — node / element numbers — are built once per mesh, every step passes all arrays again "
+                       "from pageable host memory; a re-used handle DMAs from its own CUDA-registered staging copy)")
     return out
 
 

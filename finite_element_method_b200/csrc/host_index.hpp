@@ -5,6 +5,7 @@
 // per add (methods_for_node_data_handle.rs:52-62, methods_for_truss_data_handle.rs:32-47, ...).
 #pragma once
 #include <stdint.h>
+#include <pthread.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -36,16 +37,22 @@ inline unsigned host_threads() {
 // more than some of the regions themselves.
 class HostPool {
  public:
+  // never destroyed: at process exit the parked workers simply go with the process (no join against threads that a
+  // fork()ed child does not have); after a fork the child starts threads per region instead of using the pool
   static HostPool& get() {
-    static HostPool pool;
-    return pool;
+    static HostPool* pool = [] {
+      pthread_atfork(nullptr, nullptr, [] { forked() = true; });
+      return new HostPool;
+    }();
+    return *pool;
   }
   // fn(t, n_threads) for t = 0 .. n_threads-1, t = 0 on the calling thread; returns when all are done.
   // A region entered while another one is running (a second handle on another user thread, or a nested call)
   // starts its own threads instead of waiting for the pool.
   template <typename F>
   void run(unsigned n_threads, F&& fn) {
-    std::unique_lock<std::mutex> region(region_mutex_, std::try_to_lock);
+    std::unique_lock<std::mutex> region(region_mutex_, std::defer_lock);
+    if (!forked()) region.try_lock();
     if (!region.owns_lock() || inside()) {
       std::vector<std::thread> th;
       th.reserve(n_threads - 1);
@@ -73,13 +80,9 @@ class HostPool {
 
  private:
   HostPool() = default;
-  ~HostPool() {
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      stop_ = true;
-    }
-    wake_.notify_all();
-    for (auto& t : workers_) t.join();
+  static bool& forked() {
+    static bool f = false;
+    return f;
   }
   static bool& inside() {
     static thread_local bool in = false;
