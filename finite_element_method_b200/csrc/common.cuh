@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
 #include <string>
@@ -101,6 +102,7 @@ struct NumberMap {
   std::vector<uint32_t> dense;  // value+1, 0 = absent
   std::unordered_map<uint32_t, uint32_t> sparse;
   size_t count = 0;
+  uint32_t max_label = 0;  // largest label inserted since clear() (labels erased by a rollback may still count: only a fast path asks)
   static constexpr uint32_t kDenseLimit = 1u << 28;
   // A label may sit in `sparse` although it is below dense.size(): it was inserted while the dense table was
   // still short (labels added out of order, e.g. 100000 before 1..70000) and the table grew past it later. So a
@@ -120,6 +122,7 @@ struct NumberMap {
     return true;
   }
   void insert(uint32_t number, uint32_t idx) {
+    max_label = std::max(max_label, number);
     if (number < kDenseLimit && number <= 8 * (count + 1024)) {
       if (number >= dense.size()) dense.resize(std::max<size_t>(size_t(number) + 1, dense.size() * 2), 0);
       dense[number] = idx + 1;
@@ -137,16 +140,22 @@ struct NumberMap {
   size_t insert_batch(const uint32_t* number, size_t n, uint32_t first_idx) {
     bool parallel = n >= 65536 && sparse.empty() && host_threads() > 1;
     uint32_t mx = 0;
+    bool ascending = false;
     if (parallel) {
       std::atomic<uint32_t> amx(0);
+      std::atomic<bool> asc(true);
       parallel_chunks(n, 65536, [&](size_t b, size_t e) {
         uint32_t m = 0;
+        bool up = b == 0 || number[b - 1] < number[b];
         for (size_t i = b; i < e; ++i) m = std::max(m, number[i]);
+        for (size_t i = b + 1; i < e; ++i) up &= number[i - 1] < number[i];
+        if (!up) asc.store(false);
         uint32_t cur = amx.load();
         while (m > cur && !amx.compare_exchange_weak(cur, m)) {
         }
       });
       mx = amx.load();
+      ascending = asc.load() && (count == 0 || number[0] > max_label);
       parallel = mx < kDenseLimit && mx <= 8 * (count + n + 1024);
     }
     if (!parallel) {
@@ -159,6 +168,14 @@ struct NumberMap {
     }
     if (mx >= dense.size()) dense.resize(std::max<size_t>(size_t(mx) + 1, dense.size() * 2), 0);
     uint32_t* tab = dense.data();
+    max_label = std::max(max_label, mx);
+    if (ascending) {  // strictly ascending labels above every label of the map: no two can meet, nothing to claim
+      parallel_chunks(n, 65536, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) tab[number[i]] = first_idx + uint32_t(i) + 1;
+      });
+      count += n;
+      return n;
+    }
     parallel_chunks(n, 65536, [&](size_t b, size_t e) {
       for (size_t i = b; i < e; ++i) {
         const uint32_t v = first_idx + uint32_t(i) + 1;
@@ -193,10 +210,14 @@ struct NumberMap {
     }
     if (!sparse.empty() && sparse.erase(number)) --count;
   }
+  // forget the labels, keep the table (zeroed by all cores: a re-used instance does not value-initialise it again
+  // entry by entry when the next batch sizes it)
   void clear() {
-    dense.clear();
+    uint32_t* tab = dense.data();
+    parallel_chunks(dense.size(), size_t(1) << 20, [&](size_t b, size_t e) { memset(tab + b, 0, (e - b) * sizeof(uint32_t)); });
     sparse.clear();
     count = 0;
+    max_label = 0;
   }
 };
 

@@ -52,7 +52,7 @@ class HostPool {
   template <typename F>
   void run(unsigned n_threads, F&& fn) {
     std::unique_lock<std::mutex> region(region_mutex_, std::defer_lock);
-    if (!forked()) region.try_lock();
+    if (!forked()) (void)region.try_lock();
     if (!region.owns_lock() || inside()) {
       std::vector<std::thread> th;
       th.reserve(n_threads - 1);
@@ -157,7 +157,9 @@ inline uint64_t mix64(uint64_t x) {
 }
 
 // (hash, id) multiset keyed by a 64-bit hash; the caller supplies equality on ids for the rare case
-// of two different keys with one hash. id 0xFFFFFFFF marks an empty slot, 0xFFFFFFFE a tombstone.
+// of two different keys with one hash. A slot is one 64-bit word: bits 22..53 of the hash in the upper half
+// (they give the slot inside the shard and the quick comparison — the top ten bits chose the shard), the id in the
+// lower half; id 0xFFFFFFFF marks an empty slot, 0xFFFFFFFE a tombstone. One cache line per probe.
 class ShardedIndex {
  public:
   static constexpr unsigned kShift = 54, kShards = 1u << (64 - kShift);  // 1024 shards, keyed by the top hash bits
@@ -165,10 +167,10 @@ class ShardedIndex {
 
   // forget the entries, keep the tables (FEM::reset of a re-used instance: no fresh pages to fault in)
   void clear() {
-    parallel_run(std::min(host_threads(), 8u), [&](unsigned t, unsigned nt) {
+    parallel_run(host_threads(), [&](unsigned t, unsigned nt) {
       for (unsigned sh = t; sh < kShards; sh += nt) {
         Shard& s = shards_[sh];
-        if (s.used) std::fill(s.id.begin(), s.id.end(), kEmpty);
+        if (s.used) std::fill(s.slot.begin(), s.slot.end(), ~0ull);
         s.used = 0;
       }
     });
@@ -179,11 +181,13 @@ class ShardedIndex {
   uint32_t find(uint64_t hash, Same&& same) const {
     const Shard& s = shards_[hash >> kShift];
     if (s.cap == 0) return kEmpty;
-    size_t mask = s.cap - 1, i = size_t(hash) & mask;
+    const uint32_t tag = tag_of(hash);
+    size_t mask = s.cap - 1, i = tag & mask;
     for (;;) {
-      uint32_t id = s.id[i];
+      const uint64_t w = s.slot[i];
+      const uint32_t id = uint32_t(w);
       if (id == kEmpty) return kEmpty;
-      if (id != kDead && s.hash[i] == hash && same(id)) return id;
+      if (id != kDead && uint32_t(w >> 32) == tag && same(id)) return id;
       i = (i + 1) & mask;
     }
   }
@@ -192,19 +196,19 @@ class ShardedIndex {
   void insert(uint64_t hash, uint32_t id) {
     Shard& s = shards_[hash >> kShift];
     if ((s.used + 1) * 2 > s.cap) grow(s, std::max<size_t>(16, s.cap * 2));
-    place(s, hash, id);
+    place(s, tag_of(hash), id);
   }
 
   template <typename Same>
   void erase(uint64_t hash, uint32_t id_to_erase, Same&&) {
     Shard& s = shards_[hash >> kShift];
     if (s.cap == 0) return;
-    size_t mask = s.cap - 1, i = size_t(hash) & mask;
+    size_t mask = s.cap - 1, i = tag_of(hash) & mask;
     for (;;) {
-      uint32_t id = s.id[i];
+      const uint32_t id = uint32_t(s.slot[i]);
       if (id == kEmpty) return;
-      if (id == id_to_erase && s.hash[i] == hash) {
-        s.id[i] = kDead;
+      if (id == id_to_erase) {  // ids are unique
+        s.slot[i] = (s.slot[i] & 0xFFFFFFFF00000000ull) | kDead;
         return;
       }
       i = (i + 1) & mask;
@@ -215,10 +219,10 @@ class ShardedIndex {
   // for an equal earlier entry; if none, inserts. Returns the smallest i that found a duplicate
   // (n if none). `same(existing_id, i)` decides equality. Runs on all host cores: the batch is first
   // partitioned by shard (histogram + scatter of (hash, i) pairs, order kept), then every shard is
-  // filled by one thread while its table — a few hundred KB — stays in that core's cache. Probing the
-  // tables in batch order instead costs two cache-line misses per key and is bound by memory traffic.
+  // filled by one thread while its table — a hundred KB or so — stays in that core's cache. Probing the
+  // tables in batch order instead costs a cache-line miss per key and is bound by memory traffic.
   struct Item {
-    uint64_t hash;
+    uint32_t tag;
     uint32_t i;
   };
   template <typename Same>
@@ -251,7 +255,8 @@ class ShardedIndex {
     Item* items = scratch.data();
     parallel_run(T, [&](unsigned t, unsigned nt) {
       uint32_t* at = hist.data() + size_t(t) * kShards;
-      for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) items[at[hashes[i] >> kShift]++] = Item{hashes[i], uint32_t(i)};
+      for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i)
+        items[at[hashes[i] >> kShift]++] = Item{tag_of(hashes[i]), uint32_t(i)};
     });
     std::atomic<size_t> first_dup(n);
     std::atomic<unsigned> next(0);
@@ -268,15 +273,19 @@ class ShardedIndex {
           grow(s, cap);
         }
         const size_t mask = s.cap - 1;
+        uint64_t* slot = s.slot.data();
+        constexpr size_t kAhead = 8;
         for (size_t k = b; k < e; ++k) {
-          const uint64_t hsh = items[k].hash;
+          if (k + kAhead < e) __builtin_prefetch(slot + (items[k + kAhead].tag & mask), 1);
+          const uint32_t tag = items[k].tag;
           const size_t i = items[k].i;
-          size_t p = size_t(hsh) & mask;
+          size_t p = tag & mask;
           bool dup = false;
           for (;;) {
-            uint32_t id = s.id[p];
+            const uint64_t w = slot[p];
+            const uint32_t id = uint32_t(w);
             if (id == kEmpty) break;
-            if (id != kDead && s.hash[p] == hsh && same(id, i)) {
+            if (id != kDead && uint32_t(w >> 32) == tag && same(id, i)) {
               dup = true;
               break;
             }
@@ -286,8 +295,7 @@ class ShardedIndex {
             if (i < local_first) local_first = i;
             continue;  // a duplicate is never inserted
           }
-          s.hash[p] = hsh;  // the probe ended on the first empty slot of the chain
-          s.id[p] = first_id + uint32_t(i);
+          slot[p] = (uint64_t(tag) << 32) | (first_id + uint32_t(i));  // the probe ended on the first empty slot of the chain
           ++s.used;
         }
       }
@@ -305,24 +313,24 @@ class ShardedIndex {
 
  private:
   struct Shard {
-    std::vector<uint64_t> hash;
-    std::vector<uint32_t> id;
+    std::vector<uint64_t> slot;  // tag << 32 | id
     size_t cap = 0, used = 0;
   };
-  static void place(Shard& s, uint64_t hash, uint32_t id) {
-    size_t mask = s.cap - 1, i = size_t(hash) & mask;
-    while (s.id[i] != kEmpty) i = (i + 1) & mask;  // tombstones are not reused; tables only grow
-    s.hash[i] = hash;
-    s.id[i] = id;
+  static uint32_t tag_of(uint64_t hash) { return uint32_t(hash >> 22); }
+  static void place(Shard& s, uint32_t tag, uint32_t id) {
+    size_t mask = s.cap - 1, i = tag & mask;
+    while (uint32_t(s.slot[i]) != kEmpty) i = (i + 1) & mask;  // tombstones are not reused; tables only grow
+    s.slot[i] = (uint64_t(tag) << 32) | id;
     ++s.used;
   }
   static void grow(Shard& s, size_t cap) {
     Shard n;
     n.cap = cap;
-    n.hash.assign(cap, 0);
-    n.id.assign(cap, kEmpty);
-    for (size_t i = 0; i < s.cap; ++i)
-      if (s.id[i] != kEmpty && s.id[i] != kDead) place(n, s.hash[i], s.id[i]);
+    n.slot.assign(cap, ~0ull);
+    for (size_t i = 0; i < s.cap; ++i) {
+      const uint32_t id = uint32_t(s.slot[i]);
+      if (id != kEmpty && id != kDead) place(n, uint32_t(s.slot[i] >> 32), id);
+    }
     s = std::move(n);
   }
   Shard shards_[kShards];

@@ -321,6 +321,21 @@ def test_parallel_label_claims_and_partitioned_indices_keep_sequential_semantics
     g3 = staged(n + 8)
     raises(1, "Node with number 9 already exists!", g3.add_nodes, l4, x4, zero, zero)
     assert g3.counts()[0] == 150_000
+    # strictly ascending labels above everything known take a path without claims; an ascending batch that reaches
+    # back into known labels must still find its first clash
+    g4 = staged(3 * n)
+    g4.add_nodes(np.arange(1, n + 1), x, zero, zero)
+    g4.add_nodes(np.arange(n + 1, 2 * n + 1), x + n, zero, zero)
+    assert g4.counts()[0] == 2 * n
+    raises(1, f"Node with number {2 * n - 4} already exists!", g4.add_nodes, np.arange(2 * n - 4, 3 * n - 4), x + 2 * n, zero, zero)
+    l5 = np.arange(2 * n + 1, 3 * n + 1, dtype=np.uint32); l5[70_000] = l5[69_999]       # not ascending: a repeat
+    raises(1, f"Node with number {l5[69_999]} already exists!", g4.add_nodes, l5, x + 2 * n, zero, zero)
+    assert g4.counts()[0] == 2 * n + 70_000
+    g4.reset(3 * n)                                                                    # the table is zeroed, not dropped
+    g4.add_nodes(np.arange(5, n + 5), x, zero, zero)
+    raises(1, "Node with number 5 already exists!", g4.add_node, 5, -1.0, 0.0, 0.0)
+    g4.add_node(4, -1.0, 0.0, 0.0)
+    assert g4.counts()[0] == n + 1
     # elements: plates on a strip, labels permuted; random duplicate positions against a sequential model
     m = 100_000
     h = staged(2 * m + 2)
