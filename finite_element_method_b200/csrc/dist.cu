@@ -609,6 +609,14 @@ int32_t femgpu_dist_init(femgpu_t* h, int32_t rank, int32_t world, const uint8_t
   D.send_off.assign(world + 1, 0);
   D.recv_off.assign(world + 1, 0);
   D.send_first_block.assign(world, 0);
+  {  // the ranks of one machine share its cores for their batched adds (torchrun exports LOCAL_WORLD_SIZE)
+    int local = world;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+      const int v = atoi(e);
+      if (v > 0 && v <= world) local = v;
+    }
+    host_threads_share(unsigned(local));
+  }
   h->symbolic_valid = false;
   h->values_valid = false;
   return 0;

@@ -19,17 +19,31 @@
 
 namespace femgpu {
 
-// host threads of the bulk paths: the cores of the machine, at most 32 (FEMGPU_HOST_THREADS overrides)
+// host threads of the bulk paths: the cores of the machine, at most 32 (FEMGPU_HOST_THREADS overrides), divided by
+// the number of ranks that share the machine once a handle joins a multi-rank run (host_threads_share: every rank
+// runs its own batched adds at the same time; 8 ranks x 16 threads on 16 cores only wait for each other)
+inline std::atomic<unsigned>& host_threads_divisor() {
+  static std::atomic<unsigned> d(1);
+  return d;
+}
 inline unsigned host_threads() {
-  static const unsigned cached = [] {
-    unsigned n = std::thread::hardware_concurrency();
+  static const int forced = [] {
     if (const char* e = getenv("FEMGPU_HOST_THREADS")) {
       int v = atoi(e);
-      if (v > 0) return unsigned(std::min(v, 256));
+      if (v > 0) return std::min(v, 256);
     }
+    return 0;
+  }();
+  if (forced) return unsigned(forced);
+  static const unsigned cores = [] {
+    unsigned n = std::thread::hardware_concurrency();
     return std::max(1u, std::min(n ? n : 1u, 32u));
   }();
-  return cached;
+  const unsigned d = std::max(1u, host_threads_divisor().load(std::memory_order_relaxed));
+  return std::max(1u, (cores + d - 1) / d);
+}
+inline void host_threads_share(unsigned ranks_on_this_machine) {
+  host_threads_divisor().store(std::max(1u, ranks_on_this_machine), std::memory_order_relaxed);
 }
 
 // Worker threads of the bulk paths, started once per process and parked on a condition variable between
