@@ -41,7 +41,10 @@ if rows:
           "1/N. At N = 8 a pass is 0.536 ms against 3.603 / 8 = 0.450: the assembly kernel takes 0.421 instead of 0.389 ms (two launches — ghost slabs, then the rest — "
           "each with its ramp and tail, at ~105 slabs per CTA), the three record kernels 0.074 instead of 0.061 (launch and fork / join latency of ~20 µs kernels), and a "
           "receiving rank adds ~0.025 for the apply kernel with its system-scope fences and the join of the second stream; rank 0 (sends only) and the last rank (receives "
-          "only) finish ~0.03 ms before the middle ranks. The exchange itself is hidden (0.003 ms on the sender). Weak scaling: 0.986-0.993.", ""]
+          "only) finish ~0.03 ms before the middle ranks. The exchange itself is hidden (0.003 ms on the sender). Weak scaling: 0.986-0.993. "
+          "The N = 2 and N = 4 lines are runs of the final tree (session 3: faster host ingest, registered staging); the N = 8 line is the session-2 tree — the "
+          "same numeric pass, its e2e column predates the faster ingest. e2e does not scale past two ranks on one host: at N = 4 the four ranks' read-backs share the "
+          "host's memory and PCIe complex (rank 0: 1.70 GB in 0.081 s) and its 16 cores (the ranks divide them: `host_threads_share`).", ""]
 er = M["separation"]["analysis"]["element_results"]; an = M["separation"]["analysis"]
 ref = load("r2_bench_reference.json"); cpu = M["cpu_baseline"]; e = M["e2e"]; ph = e["phases_last_step"]; fp = M["fp64"]
 tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["M"]     # the final tree's captures (profiles/r2_fp64_counts.md, r2_assemble_M.md)
