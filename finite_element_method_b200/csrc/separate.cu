@@ -254,8 +254,12 @@ quadrant_kernel(int64_t n_rows, const int64_t* __restrict__ row_ptr, const int32
 // does not hold raises a flag and the caller falls back to the two passes.
 // (A tile of 32 rows kept in registers between the two steps was measured first: 28.5 ms on config M against 12.7 —
 // 750 000 tiles at three CTAs per SM, each waiting on its look-back with its loads already spent.)
-constexpr int kTileIters = 4;
+#ifndef FEMGPU_SEP_TILE_ITERS
+#define FEMGPU_SEP_TILE_ITERS 4
+#endif
+constexpr int kTileIters = FEMGPU_SEP_TILE_ITERS;             // rounds per tile (build knob: 1, 2 or 4)
 constexpr int kTileRows = 8 * kRowsPerWarp * kTileIters;       // 256 threads: 8 warps x 4 rows x 4 rounds
+constexpr int kRowsPerLane = kTileRows / 32;                   // rows per lane in the scan step
 constexpr unsigned long long kTileMask = (1ull << 62) - 1ull;  // word = state << 62 | count; state 1: own count, 2: running total
 constexpr uint32_t kSpinLimit = 1u << 21;
 
@@ -374,8 +378,12 @@ __device__ __forceinline__ void load_warp_rows(WarpRows& w, int64_t row0, uint32
 __global__ void __launch_bounds__(256, 4)
 quadrant_onepass_kernel(int64_t n_rows, uint32_t n_tiles, const int64_t* __restrict__ row_ptr,
                         const int32_t* __restrict__ col_idx, const double* __restrict__ values,
-                        const uint32_t* __restrict__ cls_pos, SepOut out, OnePass op) {
-  static_assert(kTileRows == 128, "four rows per lane in the scan step");
+                        const uint32_t* __restrict__ cls_pos, const __grid_constant__ SepOut out,
+                        const __grid_constant__ OnePass op) {
+  // (__grid_constant__: out / op are indexed by the quadrant at run time; without it every thread copied both structs
+  // to its local-memory stack frame first — 248 B x 48 M threads = 12 GB of stores per launch, ncu: 16.7 GB written
+  // to DRAM against 6.3 GB of output)
+  static_assert(kTileRows % 32 == 0 && kRowsPerLane >= 1, "whole rows per lane in the scan step");
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_n[2][kTileRows], s_rc[kTileRows], s_ex[2][kTileRows];
   __shared__ unsigned long long s_base[4];
@@ -417,12 +425,12 @@ quadrant_onepass_kernel(int64_t n_rows, uint32_t n_tiles, const int64_t* __restr
   if (warp < 4) {
     const int q = int(warp);
     const uint32_t want = q < 2 ? kClsA : kClsB;
-    uint32_t cnt[4], lane_sum = 0;
-    bool mine[4];
+    uint32_t cnt[kRowsPerLane], lane_sum = 0;
+    bool mine[kRowsPerLane];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mine[j] = (s_rc[4 * lane + j] >> 30) == want;
-      cnt[j] = mine[j] ? s_n[q & 1][4 * lane + j] : 0u;
+    for (int j = 0; j < kRowsPerLane; ++j) {
+      mine[j] = (s_rc[kRowsPerLane * lane + j] >> 30) == want;
+      cnt[j] = mine[j] ? s_n[q & 1][kRowsPerLane * lane + j] : 0u;
       lane_sum += cnt[j];
     }
     uint32_t incl = lane_sum;
@@ -433,8 +441,8 @@ quadrant_onepass_kernel(int64_t n_rows, uint32_t n_tiles, const int64_t* __restr
     }
     uint32_t run = incl - lane_sum;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (mine[j]) s_ex[q & 1][4 * lane + j] = run;
+    for (int j = 0; j < kRowsPerLane; ++j) {
+      if (mine[j]) s_ex[q & 1][kRowsPerLane * lane + j] = run;
       run += cnt[j];
     }
     const unsigned long long agg = __shfl_sync(0xFFFFFFFFu, incl, 31);
