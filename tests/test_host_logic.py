@@ -361,3 +361,22 @@ def test_parallel_label_claims_and_partitioned_indices_keep_sequential_semantics
         assert e.value.code == (10 if kind[0] == 0 else 11), str(e.value)
         assert hh.counts()[3] == pos[0]
         assert np.array_equal(hh.element_numbers(PLATE), el[:pos[0]])
+
+
+def test_label_arrays_of_a_mesh_are_cached_only_while_the_sources_stay_the_same_objects():
+    """FEM.api_arrays(mesh, cache=True) (what bench.py's e2e steps pass to load_mesh): built once per mesh dict, rebuilt
+    when a source array was replaced; without `cache` nothing is kept in the dict."""
+    mesh = meshes.mixed_structure(6, 4)
+    a = FEM.api_arrays(mesh)
+    assert "_api" not in mesh
+    b = FEM.api_arrays(mesh, cache=True)
+    assert FEM.api_arrays(mesh, cache=True) is b and mesh["_api"] is b
+    for x, y in zip(a["plates"], b["plates"]):
+        assert np.array_equal(x, y)
+    m2 = dict(mesh)                                   # a copy of the dict carries the cache along ...
+    m2["p_props"] = mesh["p_props"] * 2.0             # ... but not past a replaced source array
+    c = FEM.api_arrays(m2, cache=True)
+    assert c is not b and np.array_equal(c["plates"][5], 2.0 * b["plates"][5])
+    f, g = staged(len(mesh["x"])), staged(len(mesh["x"]))
+    f.load_mesh(mesh, cache=True); g.load_mesh(mesh)
+    assert f.counts() == g.counts() == (len(mesh["x"]), 12, 24, 24)
