@@ -95,6 +95,13 @@ class FEM {
     std::vector<int64_t> k_aa_skyline, maxa;
     std::vector<double> a;
   };
+  // diagnostics: did the last separation take the opt-in one-pass kernel (FEMGPU_SEP_ONE_PASS=1)?
+  bool last_separation_read_k_once() {
+    int32_t flag = 0;
+    check(femgpu_last_separate_path(h_, &flag));
+    return flag != 0;
+  }
+
   // methods_for_separate_stiffness_matrix.rs:63 without the dense detour: K_aa as (a, maxa), the compacted column form
   // of methods_for_global_analysis.rs:50-80
   Skyline separate_stiffness_matrix_direct() {

@@ -36,6 +36,7 @@ extern "C" {
     fn femgpu_get_separated_csr(h: *mut FemGpu, which: i32, row_ptr: *mut i64, col_idx: *mut i32, values: *mut f64) -> i32;
     fn femgpu_separated_rhs(h: *mut FemGpu, b: *mut f64, b_device: *mut *const f64) -> i32;
     fn femgpu_get_separated_dense(h: *mut FemGpu, which: i32, out: *mut f64) -> i32;
+    fn femgpu_last_separate_path(h: *mut FemGpu, one_pass: *mut i32) -> i32;
     fn femgpu_separate_direct(h: *mut FemGpu, n_aa: *mut i64, n_bb: *mut i64, skyline_values: *mut i64) -> i32;
     fn femgpu_solve_direct(h: *mut FemGpu) -> i32;
     fn femgpu_get_skyline(h: *mut FemGpu, k_aa_skyline: *mut i64, a: *mut f64, maxa: *mut i64) -> i32;
@@ -213,6 +214,13 @@ impl FEM {
 }
 
 impl FEM {
+    /// diagnostics: did the last separation take the opt-in one-pass kernel (FEMGPU_SEP_ONE_PASS=1)?
+    pub fn last_separation_read_k_once(&mut self) -> Result<bool, String> {
+        let mut flag = 0i32;
+        self.check(unsafe { femgpu_last_separate_path(self.h, &mut flag) })?;
+        Ok(flag != 0)
+    }
+
     /// methods_for_separate_stiffness_matrix.rs:63 without the dense detour: (k_aa_indexes, k_bb_indexes,
     /// k_aa_skyline, a, maxa) — K_aa already in the compacted column form colsol::factorization takes
     /// (methods_for_global_analysis.rs:50-80, :183)
