@@ -478,8 +478,11 @@ def main():
 
     watchdog(args.phase_timeout)
     if rank == 0:
-        log("cpu baseline")
-        cpu = None if args.no_cpu_baseline else cpu_baseline(args.config)
+        # the CPU legs are a single-GPU matter (rank 0 at N = 1 only): with several ranks the others would only wait
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            log("cpu baseline")
+            cpu = cpu_baseline(args.config)
         line = {
             "metric": "elements assembled/s (FP64)", "value": m["value"], "unit": "elements/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
